@@ -1,0 +1,11 @@
+"""feature_intertwiner_b200 -- the Feature Intertwiner hot path (RoIAlign -> reliable / less-reliable split ->
+class-mean buffer -> L2 / Sinkhorn intertwiner loss) as hand-written sm_100a CUDA behind a C ABI
+(include/fi_b200.h), with the reference's own operator API on top.  See DESIGN.md.
+"""
+from ._lib import FiError, lib, library_path  # noqa: F401
+from .roi_align import CropAndResizeFunction, RoIAlign, crop_and_resize, crop_taps  # noqa: F401
+from .roi_pool import RoIPoolFunction, _RoIPooling  # noqa: F401
+from .nms import nms, nms_batched, pth_nms  # noqa: F401
+from .ot import OptTrans, sinkhorn_loss  # noqa: F401
+from .intertwiner import (Dev, IntertwinerLoss, LevelSplit, assign_feat2cls, pyramid_roi_align, roi_level,  # noqa: F401
+                          split_levels)

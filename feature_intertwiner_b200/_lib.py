@@ -1,0 +1,96 @@
+"""ctypes binding of libfi_b200.so (include/fi_b200.h).
+
+There is no CPU fallback anywhere in this package: if the library is missing it is built with nvcc, and if
+that fails -- or a kernel is asked to run on a non-CUDA tensor -- the call raises.
+"""
+import ctypes as C
+import os
+
+import torch
+
+from . import build as _build
+
+_LIB = None
+
+_P = C.c_void_p
+_I = C.c_int
+_F = C.c_float
+
+# name -> (restype, argtypes); one row per declaration in include/fi_b200.h
+SIGNATURES = {
+    "fi_abi_version": (_I, []),
+    "fi_last_error": (C.c_char_p, []),
+    "fi_last_status": (_I, []),
+    "CropAndResizeLaucher": (None, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P]),
+    "CropAndResizeBackpropImageLaucher": (None, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "ROIPoolForwardLaucher": (_I, [_P, _F, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "ROIPoolBackwardLaucher": (_I, [_P, _F, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "_nms": (None, [_I, _P, _P, _F]),
+    "fi_crop_and_resize_forward": (_I, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _I, _P]),
+    "fi_crop_and_resize_backward": (_I, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P]),
+    "fi_crop_taps": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
+    "fi_roi_level": (_I, [_P, _I, _F, _F, _P, _P]),
+    "fi_split_levels": (_I, [_P, _I, _P, _P, _P, _P, _P, _P]),
+    "fi_segment_mean_forward": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
+    "fi_segment_mean_backward": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    "fi_sinkhorn": (_I, [_P, _P, _I, _I, _I, _F, _I, _P, _P, _P, _P]),
+    "fi_buffer_update": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "fi_nms_batched": (_I, [_P, _I, _I, _F, _P, _P, _P, _P]),
+    "fi_roi_pool_forward": (_I, [_P, _F, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "fi_roi_pool_backward": (_I, [_P, _F, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+}
+
+
+def lib():
+    """Load (building first if stale/missing) libfi_b200.so.  Raises if it cannot be had."""
+    global _LIB
+    if _LIB is None:
+        path = _build.build_library()
+        handle = C.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError here == ABI drift; fail loudly
+            fn.restype, fn.argtypes = res, args
+        _LIB = handle
+    return _LIB
+
+
+def library_path():
+    return _build.LIB_PATH
+
+
+class FiError(RuntimeError):
+    pass
+
+
+def check(status):
+    if status != 0:
+        raise FiError("libfi_b200 status %d: %s" % (status, lib().fi_last_error().decode()))
+
+
+def stream_ptr(device=None):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL).  Refuses anything that is not CUDA memory."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise FiError("libfi_b200 kernels need CUDA tensors; got a %s tensor (there is no CPU fallback)" % t.device)
+    return t.data_ptr()
+
+
+FI_LAYOUT_NCHW = 0
+FI_LAYOUT_NHWC = 1
+
+
+def layout_of(t):
+    """(layout flag, tensor laid out that way) for a logical NCHW 4-D tensor."""
+    if t.dim() != 4:
+        raise FiError("expected a 4-D [N,C,H,W] tensor, got %s" % (tuple(t.shape),))
+    if t.is_contiguous():
+        # NB: a tensor with C == 1 or H == W == 1 is contiguous in BOTH formats; NCHW wins (same bytes)
+        return FI_LAYOUT_NCHW, t
+    if t.is_contiguous(memory_format=torch.channels_last):
+        return FI_LAYOUT_NHWC, t
+    return FI_LAYOUT_NCHW, t.contiguous()

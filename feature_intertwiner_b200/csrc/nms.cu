@@ -1,0 +1,139 @@
+// Greedy IoU NMS, batched over images, with the reduce ON the device.
+//
+// The reference (lib/nms/src/nms_cuda.c:17-67) builds the 64x64-tile suppression bitmask on the GPU, copies
+// all N*ceil(N/64) words to the host (4.5 MB for N=6000, a blocking D2H on the legacy stream) and walks it
+// serially on the CPU, once per image.  Here: one launch builds the upper-triangular mask of every image, a
+// second launch (one warp per image) performs the greedy sweep 64 boxes at a time:
+//   A. the diagonal tile resolves suppression INSIDE the block of 64 (serial over bits, words passed by
+//      warp shuffle, no memory traffic);
+//   B. the rows of the boxes that survived are OR-ed into the running `removed` bitmap, all loads of a
+//      block issued independently (coalesced: lane w owns words w, w+32, ...).
+// Rule: suppress when IoU > thresh (nms_kernel.cu:63), +1 pixel convention (nms_kernel.cu:16-24).
+#include "fi_common.cuh"
+
+namespace fi {
+
+constexpr int kNmsTile = 64;
+constexpr int kNmsMaxWordsPerLane = 8;      // n <= 32 * 8 * 64 = 16384 boxes per image
+
+__device__ __forceinline__ float iou_plus1(const float *a, const float *b) {
+    const float left = fmaxf(a[0], b[0]), right = fminf(a[2], b[2]);
+    const float top = fmaxf(a[1], b[1]), bottom = fminf(a[3], b[3]);
+    const float w = fmaxf(__fadd_rn(__fsub_rn(right, left), 1.f), 0.f), h = fmaxf(__fadd_rn(__fsub_rn(bottom, top), 1.f), 0.f);
+    const float inter = __fmul_rn(w, h);
+    const float sa = __fmul_rn(__fadd_rn(__fsub_rn(a[2], a[0]), 1.f), __fadd_rn(__fsub_rn(a[3], a[1]), 1.f));
+    const float sb = __fmul_rn(__fadd_rn(__fsub_rn(b[2], b[0]), 1.f), __fadd_rn(__fsub_rn(b[3], b[1]), 1.f));
+    return __fdiv_rn(inter, __fsub_rn(__fadd_rn(sa, sb), inter));
+}
+
+// grid (col tiles, row tiles, images), 64 threads.  `full` = also fill the lower triangle like the reference.
+__global__ void __launch_bounds__(kNmsTile) nms_mask_kernel(const float *__restrict__ boxes, int n, float thresh,
+                                                           unsigned long long *__restrict__ mask, int full) {
+    const int row_t = blockIdx.y, col_t = blockIdx.x, img = blockIdx.z;
+    if (!full && col_t < row_t) return;
+    const int col_blocks = ceil_div(n, kNmsTile);
+    const float *bx = boxes + (long)img * n * 5;
+    unsigned long long *mk = mask + (long)img * n * col_blocks;
+    const int row_size = min(n - row_t * kNmsTile, kNmsTile), col_size = min(n - col_t * kNmsTile, kNmsTile);
+    __shared__ float tile[kNmsTile * 5];
+    if ((int)threadIdx.x < col_size) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) tile[threadIdx.x * 5 + k] = bx[(long)(col_t * kNmsTile + threadIdx.x) * 5 + k];
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < row_size) {
+        const int i = row_t * kNmsTile + threadIdx.x;
+        float me[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) me[k] = bx[(long)i * 5 + k];
+        unsigned long long bits = 0;
+        const int start = (row_t == col_t) ? threadIdx.x + 1 : 0;
+        for (int j = start; j < col_size; ++j)
+            if (iou_plus1(me, tile + j * 5) > thresh) bits |= 1ULL << j;
+        mk[(long)i * col_blocks + col_t] = bits;
+    }
+}
+
+// one warp per image
+__global__ void __launch_bounds__(32) nms_reduce_kernel(const unsigned long long *__restrict__ mask, int n, int *__restrict__ keep,
+                                                       int *__restrict__ num_keep) {
+    const int img = blockIdx.x, lane = threadIdx.x;
+    const int col_blocks = ceil_div(n, kNmsTile);
+    const unsigned long long *mk = mask + (long)img * n * col_blocks;
+    int *kp = keep + (long)img * n;
+    unsigned long long removed[kNmsMaxWordsPerLane];
+#pragma unroll
+    for (int q = 0; q < kNmsMaxWordsPerLane; ++q) removed[q] = 0;
+    int kept_total = 0;
+    for (int blk = 0; blk < col_blocks; ++blk) {
+        const int base = blk * kNmsTile;
+        const int size = min(n - base, kNmsTile);
+        // diagonal words of this block: lane holds boxes `lane` and `lane + 32`
+        unsigned long long d0 = 0, d1 = 0;
+        if (lane < size) d0 = mk[(long)(base + lane) * col_blocks + blk];
+        if (lane + 32 < size) d1 = mk[(long)(base + lane + 32) * col_blocks + blk];
+        // current removed word of this block lives in lane (blk % 32), slot blk / 32
+        unsigned long long cur = 0;
+#pragma unroll
+        for (int q = 0; q < kNmsMaxWordsPerLane; ++q)
+            if (q == blk / 32) cur = removed[q];
+        cur = __shfl_sync(0xffffffffu, cur, blk & 31);
+        unsigned long long kept_bits = 0;
+        for (int b = 0; b < size; ++b) {                       // A: serial inside the block, registers only
+            const unsigned long long row = __shfl_sync(0xffffffffu, b < 32 ? d0 : d1, b & 31);
+            if (!((cur >> b) & 1ULL)) { kept_bits |= 1ULL << b; cur |= row; }
+        }
+        // B: OR the rows of the survivors into the words to the right of this block
+        unsigned long long todo = kept_bits;
+        while (todo) {
+            const int b = __ffsll((long long)todo) - 1;
+            todo &= todo - 1;
+            const unsigned long long *row = mk + (long)(base + b) * col_blocks;
+#pragma unroll
+            for (int q = 0; q < kNmsMaxWordsPerLane; ++q) {
+                const int w = q * 32 + lane;
+                if (w > blk && w < col_blocks) removed[q] |= row[w];
+            }
+        }
+        // emit kept indices in order
+        {
+            const unsigned long long lo = kept_bits & 0xffffffffULL, hi = kept_bits >> 32;
+            const int nlo = __popcll(lo);
+            if ((lo >> lane) & 1ULL) kp[kept_total + __popcll(lo & ((1ULL << lane) - 1ULL))] = base + lane;
+            if ((hi >> lane) & 1ULL) kp[kept_total + nlo + __popcll(hi & ((1ULL << lane) - 1ULL))] = base + 32 + lane;
+            kept_total += __popcll(kept_bits);
+        }
+    }
+    for (int i = kept_total + lane; i < n; i += 32) kp[i] = -1;
+    if (lane == 0) num_keep[img] = kept_total;
+}
+
+}  // namespace fi
+
+using namespace fi;
+
+FI_API void _nms(int boxes_num, float *boxes_dev, unsigned long long *mask_dev, float nms_overlap_thresh) {
+    if (boxes_num <= 0) { ok(); return; }
+    dim3 grid(ceil_div(boxes_num, kNmsTile), ceil_div(boxes_num, kNmsTile), 1);
+    nms_mask_kernel<<<grid, kNmsTile>>>(boxes_dev, boxes_num, nms_overlap_thresh, mask_dev, /*full=*/1);   // legacy stream, like nms_kernel.cu:79
+    check_launch("_nms");
+}
+
+FI_API int fi_nms_batched(const float *boxes, int n_images, int n, float thresh, unsigned long long *mask, int *keep, int *num_keep,
+                          cudaStream_t stream) {
+    FI_REQUIRE(n_images >= 0 && n >= 0 && n <= 32 * kNmsMaxWordsPerLane * kNmsTile, "fi_nms_batched: n=%d outside [0,%d]", n,
+               32 * kNmsMaxWordsPerLane * kNmsTile);
+    if (n_images == 0) return ok();
+    FI_REQUIRE(num_keep && (n == 0 || (boxes && mask && keep)), "fi_nms_batched: null pointer");
+    if (n == 0) {
+        cudaError_t e = cudaMemsetAsync(num_keep, 0, sizeof(int) * n_images, stream);
+        if (e != cudaSuccess) { set_error(FI_ERR_CUDA, "fi_nms_batched: %s", cudaGetErrorString(e)); return FI_ERR_CUDA; }
+        return ok();
+    }
+    FI_REQUIRE(n_images <= 65535, "fi_nms_batched: too many images");
+    const int t = ceil_div(n, kNmsTile);
+    nms_mask_kernel<<<dim3(t, t, n_images), kNmsTile, 0, stream>>>(boxes, n, thresh, mask, /*full=*/0);
+    if (int e = check_launch("fi_nms_batched[mask]")) return e;
+    nms_reduce_kernel<<<n_images, 32, 0, stream>>>(mask, n, keep, num_keep);
+    return check_launch("fi_nms_batched[reduce]");
+}

@@ -1,0 +1,361 @@
+// Batched Sinkhorn optimal-transport loss for B200 / sm_100a.
+//
+// Replaces the inner loop of lib/OT_module.py:104-135, which per problem launches ~4L+10 tiny cuBLAS /
+// pointwise kernels and streams the N x N kernel matrix K through L2/HBM 2L+4 times.  Here one thread-block
+// CLUSTER owns one problem and K never leaves the chip:
+//
+//   * rows of K are split across the CTAs of the cluster (1 CTA when K fits one SM's shared memory,
+//     a CTA pair for N = 256 where K alone is 256 KB); every CTA keeps all N columns of its rows;
+//   * a-update (K b) is local; b-update (K^T a) produces per-CTA partial column sums that are exchanged
+//     through distributed shared memory, one cluster barrier per iteration (double-buffered partials);
+//   * the loss <P,C> and, because P is a constant for autograd (no_bp_P_L=True, OT_module.py:130-131),
+//     the analytic gradients dL/dx, dL/dy are produced by the same launch.
+//
+// The bound is shared-memory bandwidth (2 N^2 words per iteration), not HBM and not tensor cores: the
+// iteration is a pair of mat-VECs.  The cost "GEMM" x^ y^T (dense only when D is large: N=64, D>=256 in the
+// FPN-level loss) is done in fp32 FMA with 64x64 register tiles -- TF32/bf16 tensor cores would break the
+// 1e-4 loss tolerance through the three-term cancellation 2W(x,y)-W(x,x)-W(y,y).
+#include <cooperative_groups.h>
+
+#include "fi_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace fi {
+
+constexpr int kSinkThreads = 256;
+constexpr int kTile = 64;     // C/K tile edge
+constexpr int kDT = 16;       // feature-dimension chunk staged per step
+constexpr float kEps = 1e-20f;
+
+struct SinkParams {
+    const float *x, *y;        // [P, N, D]
+    float *loss;               // [P]
+    float *gx, *gy;            // [P, N, D] or null
+    int N, D, L;
+    float inv_eps;
+    int NR;                    // rows of K per CTA
+    int pitch;                 // row pitch of K/C in shared memory (floats)
+    int TPR;                   // threads cooperating on one row in the a-update
+    int TPC;                   // threads cooperating on one column in the b-update
+    int keepC;                 // C kept in shared memory next to K (else recomputed for the loss)
+};
+
+__host__ __device__ inline int round4(int v) { return (v + 3) & ~3; }
+
+// Shared-memory carve-up (floats), identical on host and device.
+struct SinkSmem {
+    int K, C, a, b, part, colp, denx, deny, xs, ys, red, total;
+    __host__ __device__ SinkSmem(int N, int NR, int pitch, int TPC, int keepC) {
+        int o = 0;
+        K = o; o += NR * pitch;
+        C = o; o += keepC ? NR * pitch : 0;
+        o = round4(o);
+        a = o; o += round4(NR);
+        b = o; o += round4(N);
+        part = o; o += 2 * round4(N);
+        colp = o; o += TPC * round4(N);
+        denx = o; o += round4(NR);
+        deny = o; o += round4(N);
+        xs = o; o += kDT * kTile;
+        ys = o; o += kDT * kTile;
+        red = o; o += 32;
+        total = o;
+    }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+// One 64x64 tile of  S = x^_rows . y^_cols^T  accumulated over D in kDT chunks (fp32 FMA).
+// x rows are this CTA's local rows; operands are normalised on load with a true division, exactly as the
+// reference normalises before its mm (OT_module.py:111-113).
+__device__ __forceinline__ void gram_tile(const float *__restrict__ xp, const float *__restrict__ yp, int N, int D, int row0g, int nrows,
+                                          int ti, int tj, const float *denx, const float *deny, float *xs, float *ys, float acc[4][4]) {
+    const int t = threadIdx.x;
+    const int tx = t & 15, ty = t >> 4;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = 0.f;
+    for (int d0 = 0; d0 < D; d0 += kDT) {
+#pragma unroll
+        for (int k = 0; k < (kTile * kDT) / kSinkThreads; ++k) {
+            const int e = t + k * kSinkThreads;
+            const int dd = e % kDT, r = e / kDT;
+            const int d = d0 + dd;
+            const int il = ti * kTile + r;          // local x row
+            const int j = tj * kTile + r;           // y row (= column of K)
+            float xv = 0.f, yv = 0.f;
+            if (d < D) {
+                if (il < nrows) xv = __fdiv_rn(__ldg(xp + (long)(row0g + il) * D + d), denx[il]);
+                if (j < N) yv = __fdiv_rn(__ldg(yp + (long)j * D + d), deny[j]);
+            }
+            xs[dd * kTile + r] = xv;
+            ys[dd * kTile + r] = yv;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int dd = 0; dd < kDT; ++dd) {
+            const float4 a4 = *reinterpret_cast<const float4 *>(xs + dd * kTile + ty * 4);
+            const float4 b4 = *reinterpret_cast<const float4 *>(ys + dd * kTile + tx * 4);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(av[u], bv[v], acc[u][v]);
+        }
+        __syncthreads();
+    }
+}
+
+template <int CS>
+__global__ void __launch_bounds__(kSinkThreads) sinkhorn_kernel(const SinkParams p) {
+    extern __shared__ __align__(16) float smem[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = CS > 1 ? (int)cluster.block_rank() : 0;
+    const int prob = blockIdx.x / CS;
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const int N = p.N, D = p.D, NR = p.NR, pitch = p.pitch;
+    const SinkSmem L(N, NR, pitch, p.TPC, p.keepC);
+    float *Ks = smem + L.K, *Cs = smem + L.C, *a_s = smem + L.a, *b_s = smem + L.b, *part = smem + L.part;
+    float *colp = smem + L.colp, *denx = smem + L.denx, *deny = smem + L.deny, *xs = smem + L.xs, *ys = smem + L.ys;
+    float *red = smem + L.red;
+    const int Np = round4(N);
+
+    const int row0g = rank * NR;                                  // first global row owned by this CTA
+    const int nrows = max(0, min(NR, N - row0g));                 // valid local rows
+    const float *xp = p.x + (long)prob * N * D;
+    const float *yp = p.y + (long)prob * N * D;
+
+    // ---- phase 0: row norms (warp per row; OT_module.py:111-112), stored as (norm + EPS) -------------
+    for (int q = wid; q < nrows + N; q += kSinkThreads / 32) {
+        const float *src = q < nrows ? xp + (long)(row0g + q) * D : yp + (long)(q - nrows) * D;
+        float s = 0.f;
+        for (int d = lane; d < D; d += 32) { const float v = __ldg(src + d); s = fmaf(v, v, s); }
+        s = warp_sum(s);
+        if (lane == 0) {
+            const float den = __fadd_rn(sqrtf(s), kEps);
+            if (q < nrows) denx[q] = den; else deny[q - nrows] = den;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 1: C = 1 - x^ y^T,  K = exp(-C / eps)   (OT_module.py:113,116) ------------------------
+    const int tx = t & 15, ty = t >> 4;
+    for (int ti = 0; ti * kTile < nrows; ++ti)
+        for (int tj = 0; tj * kTile < N; ++tj) {
+            float acc[4][4];
+            gram_tile(xp, yp, N, D, row0g, nrows, ti, tj, denx, deny, xs, ys, acc);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const int il = ti * kTile + ty * 4 + u, j = tj * kTile + tx * 4 + v;
+                    if (il < nrows && j < N) {
+                        const float c = __fsub_rn(1.f, acc[u][v]);
+                        Ks[il * pitch + j] = expf(-p.inv_eps * c);
+                        if (p.keepC) Cs[il * pitch + j] = c;
+                    }
+                }
+        }
+    const float c0 = 1.0f / (float)N;                              // OT_module.py:118-119
+    for (int j = t; j < N; j += kSinkThreads) b_s[j] = c0;
+    __syncthreads();
+
+    // ---- phase 2: L Sinkhorn iterations (OT_module.py:120-122) ---------------------------------------
+    const int TPR = p.TPR, TPC = p.TPC;
+    const int r_row = t / TPR, r_part = t - r_row * TPR;           // a-update role
+    const int cthreads = kSinkThreads / TPC;
+    const int c_col = t % cthreads, c_part = t / cthreads;         // b-update role
+    for (int it = 0; it < p.L; ++it) {
+        // a_i = c0 / (sum_j K_ij b_j + EPS), local rows
+        {
+            float s = 0.f;
+            if (r_row < nrows) {
+                const float *kr = Ks + r_row * pitch;
+#pragma unroll 8
+                for (int j = r_part; j < N; j += TPR) s = fmaf(kr[j], b_s[j], s);
+            }
+            for (int d = TPR >> 1; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+            if (r_row < nrows && r_part == 0) a_s[r_row] = __fdiv_rn(c0, __fadd_rn(s, kEps));
+        }
+        __syncthreads();
+        // partial_j = sum_{local i} K_ij a_i
+        {
+            float s = 0.f;
+            if (c_col < N) {
+                const float *kc = Ks + c_col;
+#pragma unroll 8
+                for (int il = c_part; il < nrows; il += TPC) s = fmaf(kc[il * pitch], a_s[il], s);
+            }
+            if (TPC > 1) {
+                if (c_col < N) colp[c_part * Np + c_col] = s;
+                __syncthreads();
+                if (c_part == 0 && c_col < N) {
+                    for (int q = 1; q < TPC; ++q) s += colp[q * Np + c_col];
+                }
+            }
+            float *mine = part + (it & 1) * Np;
+            if (CS > 1) {
+                if (c_part == 0 && c_col < N) mine[c_col] = s;
+                cluster.sync();                                    // partials of every CTA are visible
+                if (c_part == 0 && c_col < N) {
+                    float tot = 0.f;
+#pragma unroll
+                    for (int r = 0; r < CS; ++r) tot += cluster.map_shared_rank(mine, r)[c_col];   // rank order: same bits everywhere
+                    b_s[c_col] = __fdiv_rn(c0, __fadd_rn(tot, kEps));
+                }
+            } else {
+                if (c_part == 0 && c_col < N) b_s[c_col] = __fdiv_rn(c0, __fadd_rn(s, kEps));
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- phase 3: P = a K b^T (in place over K), loss = <P, C>   (OT_module.py:129-134) -------------
+    float lsum = 0.f;
+    if (p.keepC) {
+        if (r_row < nrows) {
+            const float ai = a_s[r_row];
+            for (int j = r_part; j < N; j += TPR) {
+                const float pij = __fmul_rn(__fmul_rn(ai, Ks[r_row * pitch + j]), b_s[j]);
+                Ks[r_row * pitch + j] = pij;
+                lsum = fmaf(pij, Cs[r_row * pitch + j], lsum);
+            }
+        }
+    } else {
+        for (int ti = 0; ti * kTile < nrows; ++ti)
+            for (int tj = 0; tj * kTile < N; ++tj) {
+                float acc[4][4];
+                gram_tile(xp, yp, N, D, row0g, nrows, ti, tj, denx, deny, xs, ys, acc);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        const int il = ti * kTile + ty * 4 + u, j = tj * kTile + tx * 4 + v;
+                        if (il < nrows && j < N) {
+                            const float pij = __fmul_rn(__fmul_rn(a_s[il], Ks[il * pitch + j]), b_s[j]);
+                            Ks[il * pitch + j] = pij;
+                            lsum = fmaf(pij, __fsub_rn(1.f, acc[u][v]), lsum);
+                        }
+                    }
+            }
+    }
+    lsum = warp_sum(lsum);
+    if (lane == 0) red[wid] = lsum;
+    __syncthreads();
+    if (t == 0) {
+        float s = 0.f;
+        for (int w = 0; w < kSinkThreads / 32; ++w) s += red[w];
+        if (CS > 1) atomicAdd(p.loss + prob, s);                   // two addends: order-independent
+        else p.loss[prob] = s;
+    }
+
+    // ---- phase 4: gradients with P constant ----------------------------------------------------------
+    //   dL/dx^_i = -sum_j P_ij y^_j ,  dL/dy^_j = -sum_i P_ij x^_i ,
+    //   x^ = x / (|x| + EPS)  =>  dL/dx = (g - x^ <x^,g> |x|/(|x|+EPS)) / (|x|+EPS)
+    if (p.gx != nullptr) {
+        float *gxp = p.gx + (long)prob * N * D, *gyp = p.gy + (long)prob * N * D;
+        for (long e = t; e < (long)nrows * D; e += kSinkThreads) {
+            const int il = (int)(e / D), d = (int)(e - (long)il * D);
+            float s = 0.f;
+            for (int j = 0; j < N; ++j) s = fmaf(Ks[il * pitch + j], __fdiv_rn(__ldg(yp + (long)j * D + d), deny[j]), s);
+            gxp[(long)(row0g + il) * D + d] = -s;
+        }
+        for (long e = t; e < (long)N * D; e += kSinkThreads) {
+            const int j = (int)(e / D), d = (int)(e - (long)j * D);
+            float s = 0.f;
+            for (int il = 0; il < nrows; ++il) s = fmaf(Ks[il * pitch + j], __fdiv_rn(__ldg(xp + (long)(row0g + il) * D + d), denx[il]), s);
+            if (CS > 1) atomicAdd(gyp + e, -s);
+            else gyp[e] = -s;
+        }
+        __threadfence();
+        if (CS > 1) cluster.sync(); else __syncthreads();
+        // chain through the row normalisation; this CTA finalises the rows it owns (x and y alike)
+        for (int q = wid; q < 2 * nrows; q += kSinkThreads / 32) {
+            const bool isx = q < nrows;
+            const int il = isx ? q : q - nrows;
+            const int i = row0g + il;
+            const float *src = (isx ? xp : yp) + (long)i * D;
+            float *g = (isx ? gxp : gyp) + (long)i * D;
+            const float den = isx ? denx[il] : deny[i];
+            float dot = 0.f;
+            for (int d = lane; d < D; d += 32) dot = fmaf(__ldcg(g + d), __fdiv_rn(__ldg(src + d), den), dot);
+            dot = warp_sum(dot);
+            const float shrink = __fdiv_rn(__fsub_rn(den, kEps), den);   // |x| / (|x| + EPS)
+            for (int d = lane; d < D; d += 32) {
+                const float xh = __fdiv_rn(__ldg(src + d), den);
+                g[d] = __fdiv_rn(__fsub_rn(__ldcg(g + d), __fmul_rn(__fmul_rn(xh, dot), shrink)), den);
+            }
+        }
+    }
+    if (CS > 1) cluster.sync();   // no CTA may exit while a peer can still read its shared memory
+}
+
+constexpr int kMaxSmemBytes = 227 * 1024;
+
+static int pow2_floor(int v) { int r = 1; while (r * 2 <= v) r *= 2; return r; }
+
+static bool plan(int N, int CS, int keepC, SinkParams &p, size_t &bytes) {
+    p.NR = (N + CS - 1) / CS;
+    p.TPR = pow2_floor(kSinkThreads / p.NR > 0 ? kSinkThreads / p.NR : 1);
+    if (p.TPR > 32) p.TPR = 32;
+    p.TPC = pow2_floor(kSinkThreads / N > 0 ? kSinkThreads / N : 1);
+    if (p.TPC > 8) p.TPC = 8;
+    int pitch = N;
+    while (pitch % 32 != p.TPR % 32) ++pitch;          // a-update: lane -> distinct bank
+    p.pitch = pitch;
+    p.keepC = keepC;
+    SinkSmem L(N, p.NR, pitch, p.TPC, keepC);
+    bytes = (size_t)L.total * sizeof(float);
+    return bytes <= (size_t)kMaxSmemBytes && p.NR <= kSinkThreads;
+}
+
+}  // namespace fi
+
+using namespace fi;
+
+FI_API int fi_sinkhorn(const float *x, const float *y, int n_problems, int N, int D, float inv_eps, int L, float *loss,
+                       float *grad_x, float *grad_y, cudaStream_t stream) {
+    FI_REQUIRE(n_problems >= 0 && N >= 1 && N <= 256 && D >= 1 && L >= 1, "fi_sinkhorn: need N in [1,256], D >= 1, L >= 1 (N=%d D=%d L=%d)", N, D, L);
+    if (n_problems == 0) return ok();
+    FI_REQUIRE(x && y && loss, "fi_sinkhorn: null pointer");
+    FI_REQUIRE((grad_x == nullptr) == (grad_y == nullptr), "fi_sinkhorn: grad_x and grad_y must both be given or both be NULL");
+    SinkParams p;
+    p.x = x; p.y = y; p.loss = loss; p.gx = grad_x; p.gy = grad_y;
+    p.N = N; p.D = D; p.L = L; p.inv_eps = inv_eps;
+    size_t bytes = 0;
+    int CS = 1;
+    if (!plan(N, 1, 1, p, bytes) && !plan(N, 1, 0, p, bytes)) {
+        CS = 2;
+        if (!plan(N, 2, 1, p, bytes) && !plan(N, 2, 0, p, bytes)) {
+            set_error(FI_ERR_UNSUPPORTED, "fi_sinkhorn: N=%d does not fit a CTA pair", N);
+            return FI_ERR_UNSUPPORTED;
+        }
+    }
+    cudaError_t e;
+    if (CS > 1) {
+        e = cudaMemsetAsync(loss, 0, sizeof(float) * n_problems, stream);
+        if (e == cudaSuccess && grad_y) e = cudaMemsetAsync(grad_y, 0, sizeof(float) * (size_t)n_problems * N * D, stream);
+        if (e != cudaSuccess) { set_error(FI_ERR_CUDA, "fi_sinkhorn: memset: %s", cudaGetErrorString(e)); return FI_ERR_CUDA; }
+    }
+    auto kern = CS == 1 ? sinkhorn_kernel<1> : sinkhorn_kernel<2>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) { set_error(FI_ERR_CUDA, "fi_sinkhorn: smem attr (%zu B): %s", bytes, cudaGetErrorString(e)); return FI_ERR_CUDA; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_problems * CS));
+    cfg.blockDim = dim3(kSinkThreads);
+    cfg.dynamicSmemBytes = bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, p);
+    if (e != cudaSuccess) { set_error(FI_ERR_CUDA, "fi_sinkhorn: launch: %s", cudaGetErrorString(e)); return FI_ERR_CUDA; }
+    return check_launch("fi_sinkhorn");
+}

@@ -1,0 +1,404 @@
+"""The intertwiner proper: ``Dev`` (lib/sub_module.py:286-692, structure 'beta') and the meta loss with its
+historical class buffer (lib/model.py:106-111,143-224), on the kernels of libfi_b200.
+
+What changes relative to the reference, and what does not:
+
+* same constructor arguments, sub-module names (``upsample``, ``feat_extract`` -> identical state_dict keys),
+  same forward signature and return structure (``pooled_out, mask_out, feat_out``);
+* the level rule, the four small / four big index lists and every count come from TWO kernel launches and ONE
+  8-int device->host read per forward, instead of ~10 pointwise launches, 8 ``nonzero`` and 8 ``.any()`` syncs;
+* 7x7 crops are written straight into their final row of ``pooled_out`` (the scatter of
+  lib/sub_module.py:645-662 is fused into the RoIAlign kernel); so are the 14x14 crops of level 5;
+* ``_assign_feat2cls`` is one deterministic segment-mean kernel instead of a python loop over classes;
+* the buffer is a ring for BUFFER_SIZE > 1 (no 332 MB shift per iteration) and the class statistics can be
+  all-reduced across ranks (one process per GPU) before the identical update on every rank.
+
+The make-up layer (``upsample``) and the critic (``feat_extract``) are dense convolutions and stay stock
+PyTorch / cuDNN.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from .roi_align import crop_and_resize
+from .roi_pool import RoIPoolFunction
+
+EPS = 1e-20
+
+
+# ----------------------------------------------------------------------------------------------- level rule / split
+def roi_level(rois, image_shape, base=224.0):
+    """rois[bs,R,4] normalised -> int32 [bs,R] pyramid level in 2..5 (lib/sub_module.py:397-410)."""
+    flat = rois.detach().float().contiguous().view(-1, 4)
+    level = torch.empty((flat.size(0),), device=flat.device, dtype=torch.int32)
+    with torch.cuda.device(flat.device):
+        _lib.check(_lib.lib().fi_roi_level(_lib.ptr(flat), flat.size(0), float(image_shape[0] * image_shape[1]), float(base),
+                                           _lib.ptr(level), _lib.stream_ptr(flat.device)))
+    return level.view(rois.shape[:-1])
+
+
+class LevelSplit(object):
+    """Per-level index lists of flat RoI ids (torch.nonzero order) for levels 2..5."""
+
+    def __init__(self, small_idx, small_cnt, big_idx, big_cnt, slot):
+        self.small_idx, self.big_idx, self.slot = small_idx, big_idx, slot
+        counts = torch.cat([small_cnt, big_cnt]).tolist()        # the only host sync of the split
+        self.small_cnt, self.big_cnt = counts[:4], counts[4:]
+
+    def small(self, i):
+        return self.small_idx[i, : self.small_cnt[i]]
+
+    def big(self, i):
+        return self.big_idx[i, : self.big_cnt[i]]
+
+
+def split_levels(level):
+    """level[...] int32 -> LevelSplit: small(l) = {level == l}, big(l) = {level > l} (lib/sub_module.py:442,367-378)."""
+    flat = level.contiguous().view(-1)
+    n = flat.numel()
+    dev = flat.device
+    small_idx = torch.empty((4, max(n, 1)), device=dev, dtype=torch.int32)
+    big_idx = torch.empty((4, max(n, 1)), device=dev, dtype=torch.int32)
+    small_cnt = torch.empty((4,), device=dev, dtype=torch.int32)
+    big_cnt = torch.empty((4,), device=dev, dtype=torch.int32)
+    slot = torch.empty((max(n, 1),), device=dev, dtype=torch.int32)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().fi_split_levels(_lib.ptr(flat), n, _lib.ptr(small_idx), _lib.ptr(small_cnt), _lib.ptr(big_idx),
+                                              _lib.ptr(big_cnt), _lib.ptr(slot), _lib.stream_ptr(dev)))
+    return LevelSplit(small_idx, small_cnt, big_idx, big_cnt, slot)
+
+
+# ----------------------------------------------------------------------------------------------- segment mean
+class _SegmentMean(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gt, feat, ncls):
+        feat2 = feat.reshape(feat.size(0), -1).float().contiguous()
+        gt = gt.detach().to(torch.int32).contiguous()
+        k, Fd = feat2.shape
+        mean = torch.empty((Fd, ncls), device=feat2.device, dtype=torch.float32)
+        cnt = torch.empty((1, ncls), device=feat2.device, dtype=torch.float32)
+        with torch.cuda.device(feat2.device):
+            _lib.check(_lib.lib().fi_segment_mean_forward(_lib.ptr(gt), _lib.ptr(feat2), k, Fd, ncls, _lib.ptr(mean), _lib.ptr(cnt),
+                                                          _lib.stream_ptr(feat2.device)))
+        ctx.save_for_backward(gt, cnt)
+        ctx.shape = tuple(feat.shape)
+        ctx.dims = (k, Fd, ncls)
+        ctx.mark_non_differentiable(cnt)
+        return mean, cnt
+
+    @staticmethod
+    def backward(ctx, gmean, _gcnt):
+        gt, cnt = ctx.saved_tensors
+        k, Fd, ncls = ctx.dims
+        gmean = gmean.contiguous()
+        gfeat = torch.empty((k, Fd), device=gmean.device, dtype=torch.float32)
+        with torch.cuda.device(gmean.device):
+            _lib.check(_lib.lib().fi_segment_mean_backward(_lib.ptr(gt), _lib.ptr(gmean), _lib.ptr(cnt), k, Fd, ncls, _lib.ptr(gfeat),
+                                                           _lib.stream_ptr(gmean.device)))
+        return None, gfeat.view(ctx.shape), None
+
+
+def assign_feat2cls(box_gt, input_feat, num_classes):
+    """lib/sub_module.py:664-684: per-class mean of instance features -> (feat[F,ncls], cnt[1,ncls]); background skipped."""
+    return _SegmentMean.apply(box_gt, input_feat, int(num_classes))
+
+
+# ----------------------------------------------------------------------------------------------- Dev
+class Dev(nn.Module):
+    def __init__(self, config, depth):
+        super().__init__()
+        self.depth = depth
+        self.use_dev = config.DEV.SWITCH
+        self.pool_size = config.MRCNN.POOL_SIZE
+        self.mask_pool_size = config.MRCNN.MASK_POOL_SIZE
+        self.image_shape = config.DATA.IMAGE_SHAPE
+        self.num_classs = config.DATASET.NUM_CLASSES
+        self.config = config
+        self.dis_upsample = config.DEV.DIS_UPSAMPLER
+        self.structure = config.DEV.STRUCTURE
+        self.roi_type = config.ROIS.METHOD
+        self.roi_spatial_scale = [1. / 4, 1. / 8, 1. / 16, 1. / 32]
+        if self.use_dev:
+            self.feat_pool_size = config.DEV.FEAT_BRANCH_POOL_SIZE
+            self.upsample_fac = config.DEV.UPSAMPLE_FAC
+            assert self.feat_pool_size % 2 == 0, 'pool size of feature branch has to be even'
+            if not self.dis_upsample:
+                if config.DEV.UPSAMPLE_FAC == 1.:
+                    conv_opt = nn.Conv2d(depth, depth, kernel_size=3, padding=1)
+                elif config.DEV.UPSAMPLE_FAC == 2.:
+                    conv_opt = nn.ConvTranspose2d(depth, depth, kernel_size=3, stride=2, padding=1, output_padding=1)
+                upsample_num = 4 if config.DEV.MULTI_UPSAMPLER else 1
+                # one conv object shared by all make-up layers, as in the reference (sub_module.py:310-321)
+                self.upsample = nn.ModuleList([nn.Sequential(conv_opt, nn.BatchNorm2d(depth), nn.ReLU(inplace=True))
+                                               for _ in range(upsample_num)])
+            if not config.DEV.BASELINE:
+                ksize = int(self.feat_pool_size / 2)
+                self.feat_extract = nn.Sequential(
+                    nn.Conv2d(depth, 512, kernel_size=3, padding=1, stride=2), nn.BatchNorm2d(512), nn.ReLU(inplace=True),
+                    nn.Conv2d(512, 1024, kernel_size=ksize, stride=1), nn.BatchNorm2d(1024), nn.ReLU(inplace=True),
+                    nn.Conv2d(1024, 1024, kernel_size=1, stride=1), nn.BatchNorm2d(1024), nn.ReLU(inplace=True))
+                if config.DEV.LOSS_CHOICE in ('l2', 'l1'):
+                    self.last_op = nn.Sigmoid()
+                elif config.DEV.LOSS_CHOICE == 'kl':
+                    self.last_op = nn.Softmax(dim=1)
+                if config.DEV.BIG_SUPERVISE:
+                    self.big_fc_layer = nn.Linear(1024, self.num_classs)
+
+    # -- RoI feature op in either flavour (lib/sub_module.py:500-507) ------------------------------------
+    def _roi_op(self, level_i, size, fmap, boxes, box_ind, out=None, dst_row=None):
+        if self.roi_type == 'roi_align':
+            return crop_and_resize(fmap, boxes, box_ind, size, size, 0.0, out=out, dst_row=dst_row)
+        pooled = RoIPoolFunction(size, size, self.roi_spatial_scale[level_i])(fmap, self._make_roi_pool_box_input(boxes, box_ind))
+        if out is not None:
+            out.index_copy_(0, dst_row.long(), pooled)
+            return out
+        return pooled
+
+    def _critic(self, pooled):
+        out = self.feat_extract(pooled)
+        if self.config.DEV.LOSS_CHOICE != 'ot':
+            out = self.last_op(out)
+        return out
+
+    def forward(self, x, rois, roi_cls_gt=None):
+        cfg = self.config
+        base = cfg.ROIS.ASSIGN_ANCHOR_BASE
+        if not self.use_dev:
+            pooled_out = pyramid_roi_align([rois] + list(x), self.pool_size, self.image_shape, base=base)
+            mask_out = pyramid_roi_align([rois] + list(x), self.mask_pool_size, self.image_shape, base=base)
+            return pooled_out, mask_out, None
+        if self.structure != 'beta' or cfg.DEV.ASSIGN_BOX_ON_ALL_SCALE:
+            # the reference itself only implements 'beta' (sub_module.py:385-391,642)
+            raise _lib.FiError("Dev: only STRUCTURE='beta' with ASSIGN_BOX_ON_ALL_SCALE=False is built")
+        train_phase = roi_cls_gt is not None
+        use_stats = train_phase and not cfg.DEV.BASELINE
+        bs, R = rois.size(0), rois.size(1)
+        total_box = bs * R
+        dev = rois.device
+        rois_flat = rois.detach().float().contiguous().view(total_box, 4)
+        gt_flat = roi_cls_gt.contiguous().view(total_box) if train_phase else None
+
+        split = split_levels(roi_level(rois, self.image_shape, base))          # steps 1+2a: no per-level syncs below
+        fmt = torch.channels_last if x[0].is_contiguous(memory_format=torch.channels_last) and not x[0].is_contiguous() \
+            else torch.contiguous_format
+        pooled_out = torch.zeros((total_box, self.depth, self.pool_size, self.pool_size), device=dev).contiguous(memory_format=fmt)
+        mask_out = torch.zeros((total_box, self.depth, self.mask_pool_size, self.mask_pool_size), device=dev).contiguous(memory_format=fmt)
+        big_feat, big_cnt, small_feat, small_cnt, big_loss = [], [], [], [], []
+        small_output_all = torch.zeros(total_box, 1024, device=dev)
+        small_gt_all = torch.zeros(total_box, device=dev)
+        small_out_cnt = 0
+        zf = lambda: torch.zeros(1024, self.num_classs, device=dev)
+        zc = lambda: torch.zeros(1, self.num_classs, device=dev)
+
+        for i, level in enumerate(range(2, 6)):
+            curr_feat_maps = x[i]
+            use_meta = level in (2, 3, 4)
+            n_small, n_big = split.small_cnt[i], split.big_cnt[i]
+            if n_small == 0:                                                    # sub_module.py:456-467
+                if use_meta and use_stats:
+                    small_feat.append(zf()); small_cnt.append(zc()); big_feat.append(zf()); big_cnt.append(zc())
+                    big_loss.append(torch.zeros(1, device=dev))
+                continue
+            if use_stats:                                                       # sub_module.py:472-536 (reliable set)
+                if n_big == 0:
+                    if use_meta:
+                        big_feat.append(zf()); big_cnt.append(zc()); big_loss.append(torch.zeros(1, device=dev))
+                else:
+                    bidx = split.big(i).long()
+                    big_boxes = rois_flat[bidx]
+                    big_box_gt = gt_flat[bidx]
+                    big_box_ind = (bidx // R).int()
+                    big_pooled = self._roi_op(i, self.feat_pool_size, curr_feat_maps, big_boxes, big_box_ind)
+                    big_before_last = self.feat_extract(big_pooled)
+                    big_output = big_before_last if cfg.DEV.LOSS_CHOICE == 'ot' else self.last_op(big_before_last)
+                    b_feat, b_cnt = assign_feat2cls(big_box_gt, big_output, self.num_classs)
+                    big_feat.append(b_feat); big_cnt.append(b_cnt)
+                    if cfg.DEV.BIG_SUPERVISE:
+                        digits = self.big_fc_layer(big_before_last.view(-1, 1024))
+                        big_loss.append(F.cross_entropy(digits, big_box_gt.long()).view(1))
+                    else:
+                        big_loss.append(torch.zeros(1, device=dev))
+            # less-reliable set: RoIs assigned to this level (sub_module.py:539-600)
+            sidx32 = split.small(i)
+            sidx = sidx32.long()
+            small_boxes = rois_flat[sidx]
+            box_ind = (sidx // R).int()
+            feat_maps = self.upsample[i if cfg.DEV.MULTI_UPSAMPLER else 0](curr_feat_maps)
+            # 7x7 crops land directly in their final (image, roi) row -- fused _reshape_result
+            pooled_out = self._roi_op(i, self.pool_size, feat_maps, small_boxes, box_ind, out=pooled_out, dst_row=sidx32)
+            if use_meta and not cfg.DEV.BASELINE:
+                mask_and_feat = self._roi_op(i, self.mask_pool_size, feat_maps, small_boxes, box_ind)
+                mask_out.index_copy_(0, sidx, mask_and_feat)    # the critic needs the compact crop too, so no fused scatter here
+                small_output = self._critic(mask_and_feat)
+                n = n_small
+                small_output_all[small_out_cnt:small_out_cnt + n, :] = small_output.view(n, -1)
+                if train_phase:
+                    small_box_gt = gt_flat[sidx]
+                    s_feat, s_cnt = assign_feat2cls(small_box_gt, small_output, self.num_classs)
+                    small_feat.append(s_feat); small_cnt.append(s_cnt)
+                    small_gt_all[small_out_cnt:small_out_cnt + n] = small_box_gt.float()
+                else:
+                    small_gt_all[small_out_cnt:small_out_cnt + n] = 1
+                small_out_cnt += n
+            else:
+                mask_out = self._roi_op(i, self.mask_pool_size, feat_maps, small_boxes, box_ind, out=mask_out, dst_row=sidx32)
+
+        if use_stats:
+            bf = torch.stack(big_feat).unsqueeze(dim=0)
+            if cfg.DEV.BIG_FEAT_DETACH:
+                bf = bf.detach()
+            feat_out = [bf, torch.stack(big_cnt).unsqueeze(dim=0), torch.stack(small_feat).unsqueeze(dim=0),
+                        torch.stack(small_cnt).unsqueeze(dim=0), torch.stack(big_loss).unsqueeze(dim=0),
+                        small_output_all, small_gt_all]
+        elif not train_phase:
+            feat_out = [small_output_all, small_gt_all]
+        else:
+            feat_out = []
+        return pooled_out, mask_out, feat_out
+
+    def _make_roi_pool_box_input(self, boxes, box_ind):
+        """lib/sub_module.py:686-692: (b, x1, y1, x2, y2) in pixels; both axes scaled by image_shape[0] as the reference does."""
+        b = boxes * float(self.image_shape[0])
+        return torch.stack([box_ind.float(), b[:, 1], b[:, 0], b[:, 3], b[:, 2]], dim=1)
+
+
+def pyramid_roi_align(inputs, pool_size, image_shape, base=224.):
+    """lib/layers.py:145-218: vanilla FPN RoIAlign (intertwiner off); crops written straight to their final rows."""
+    boxes, feature_maps = inputs[0], inputs[1:]
+    bs, R = boxes.size(0), boxes.size(1)
+    split = split_levels(roi_level(boxes, image_shape, base))
+    flat = boxes.detach().float().contiguous().view(bs * R, 4)
+    fm0 = feature_maps[0]
+    fmt = torch.channels_last if fm0.is_contiguous(memory_format=torch.channels_last) and not fm0.is_contiguous() else torch.contiguous_format
+    out = torch.zeros((bs * R, fm0.size(1), pool_size, pool_size), device=boxes.device).contiguous(memory_format=fmt)
+    for i in range(4):
+        if split.small_cnt[i] == 0:
+            continue
+        idx32 = split.small(i)
+        idx = idx32.long()
+        out = crop_and_resize(feature_maps[i], flat[idx], (idx // R).int(), pool_size, pool_size, 0.0, out=out, dst_row=idx32)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- meta loss
+class _AllReduceSum(torch.autograd.Function):
+    """Differentiable all-reduce(SUM).  Backward: every rank's contribution enters the total with weight 1, so the
+    local gradient is the incoming one -- times world_size when ``compensate`` is set, because DDP will later AVERAGE
+    parameter gradients over ranks whereas the reference's DataParallel SUMS the replicas' (SURVEY.md section 7)."""
+
+    @staticmethod
+    def forward(ctx, t, group, compensate):
+        import torch.distributed as dist
+        ctx.scale = float(dist.get_world_size(group)) if compensate else 1.0
+        out = t.clone()
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g * ctx.scale, None, None
+
+
+class IntertwinerLoss(nn.Module):
+    """``MaskRCNN.initialize_buffer`` + ``meta_loss`` + ``_merge_feat_vec`` (lib/model.py:106-111,143-224) as a module.
+
+    ``forward(feat_input)`` takes exactly what the reference's ``meta_loss`` takes:
+    ``[big_feat, big_cnt, small_feat, small_cnt, small_output_all, small_gt_all]`` with the leading
+    ``[gpu_num, scale_num]`` axes of lib/model.py:394-402.  With ``process_group`` set (one process per GPU) the
+    un-normalised class statistics are all-reduced first, replacing the gather-to-GPU-0 of nn.DataParallel.
+    """
+
+    def __init__(self, config, ot_loss=None, feat_dim=1024, process_group=None, distributed=False, ddp_compensate=True):
+        super().__init__()
+        self.config = config
+        self.feat_dim = feat_dim
+        self.distributed = distributed
+        self.process_group = process_group
+        self.ddp_compensate = ddp_compensate
+        B, ncls = config.DEV.BUFFER_SIZE, config.DATASET.NUM_CLASSES
+        # persistent state of the hot path; round-trips through checkpoints like tools/utils.py:374-389,575-585
+        self.register_buffer('buffer', torch.zeros(B, feat_dim, ncls))
+        self.register_buffer('buffer_cnt', torch.zeros(B, 1, ncls))
+        self.register_buffer('ring_pos', torch.zeros((), dtype=torch.long))   # next slot to overwrite (B > 1)
+        if ot_loss is not None:
+            self.ot_loss = ot_loss
+        self.last_idx = None
+
+    def initialize_buffer(self, log_file=None):
+        self.buffer.zero_(); self.buffer_cnt.zero_(); self.ring_pos.zero_()
+
+    def fifo_buffer(self):
+        """(buffer, buffer_cnt) in the reference's oldest-first order, e.g. for a reference-format checkpoint."""
+        B = self.buffer.size(0)
+        if B == 1:
+            return self.buffer, self.buffer_cnt
+        order = (torch.arange(B, device=self.buffer.device) + self.ring_pos) % B
+        return self.buffer[order], self.buffer_cnt[order]
+
+    def _sums(self, feat, cnt, differentiable):
+        """_merge_feat_vec's numerator and denominator (lib/model.py:219-222), all-reduced when distributed."""
+        s = (feat * cnt).sum(dim=(0, 1))
+        n = cnt.sum(dim=(0, 1)).view(-1)
+        if self.distributed:
+            import torch.distributed as dist
+            packed = torch.cat([s.reshape(-1), n])
+            if differentiable and packed.requires_grad:
+                packed = _AllReduceSum.apply(packed, self.process_group, self.ddp_compensate)
+            else:
+                packed = packed.detach().clone()
+                dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=self.process_group)
+            s, n = packed[: s.numel()].view_as(s), packed[s.numel():]
+        return s, n
+
+    def forward(self, feat_input):
+        big_feat, big_cnt, small_feat, small_cnt, small_output_all, small_gt_all = feat_input
+        cfg = self.config
+        Fd, ncls = self.feat_dim, cfg.DATASET.NUM_CLASSES
+        B = self.buffer.size(0)
+        dev = self.buffer.device
+        # ---- reliable-set statistics -> historical buffer (model.py:148-166), one kernel
+        big_sum, big_n = self._sums(big_feat.detach(), big_cnt.detach(), differentiable=False)
+        big_sum, big_n = big_sum.contiguous(), big_n.contiguous()
+        final_big = torch.empty((Fd, ncls), device=dev, dtype=torch.float32)
+        slot = int(self.ring_pos.item()) if B > 1 else 0
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().fi_buffer_update(_lib.ptr(big_sum), _lib.ptr(big_n), B, slot, Fd, ncls, _lib.ptr(self.buffer),
+                                                   _lib.ptr(self.buffer_cnt), _lib.ptr(final_big), _lib.stream_ptr(dev)))
+        if B > 1:
+            self.ring_pos.fill_((slot + 1) % B)
+        in_buffer = self.buffer_cnt.sum(dim=0).view(-1) > 0
+        lc = cfg.DEV.LOSS_CHOICE
+        # ---- comparison set (model.py:168-190)
+        if cfg.DEV.INST_LOSS:
+            gt = small_gt_all.long()
+            mask = (gt != 0) & in_buffer[gt]
+            SMALL_all, BIG_all = small_output_all, final_big.t()[gt]
+        else:
+            s_sum, s_n = self._sums(small_feat, small_cnt, differentiable=True)
+            final_small = s_sum / (s_n + EPS)
+            s_n = s_n.clone(); s_n[0] = 0                                      # background excluded (model.py:178)
+            mask = (s_n > 0) & in_buffer
+            SMALL_all, BIG_all = final_small.t(), final_big.t()
+        if lc == 'ot' or lc == 'kl':
+            idx = torch.nonzero(mask).squeeze(1)                               # host-visible size: the reference's API returns [n]
+            self.last_idx = idx
+            if idx.numel() == 0:
+                return torch.zeros(1, device=dev)
+            SMALL, BIG = SMALL_all[idx], BIG_all[idx]
+            if lc == 'kl':
+                return F.kl_div(torch.log(SMALL), BIG, reduction='mean')
+            return self.ot_loss(SMALL.unsqueeze(dim=-1), BIG.unsqueeze(dim=-1).contiguous())
+        # l1 / l2: masked mean == F.mse_loss(SMALL[idx], BIG[idx]) without materialising idx (no host sync);
+        # an empty comparison set gives 0 like model.py:208-209
+        self.last_idx = None
+        self.last_mask = mask
+        diff = SMALL_all - BIG_all
+        per = diff * diff if lc == 'l2' else diff.abs()
+        m = mask.to(per.dtype).unsqueeze(1)
+        denom = (m.sum() * per.size(1)).clamp(min=1.0)
+        return (per * m).sum() / denom
+
+
+def meta_loss_module(config, ot_loss=None, **kw):
+    return IntertwinerLoss(config, ot_loss=ot_loss, **kw)

@@ -1,0 +1,137 @@
+"""RoIAlign operator layer -- same names and call shapes as the reference's lib/roi_align package.
+
+* ``CropAndResizeFunction(crop_h, crop_w, extrapolation_value=0)(image, boxes, box_ind)``
+  mirrors lib/roi_align/crop_and_resize.py:14-54 (construct with hyper-parameters, call on tensors;
+  gradient w.r.t. ``image`` only).
+* ``RoIAlign(crop_h, crop_w, extrapolation_value=0, transform_fpcoor=True)`` mirrors
+  lib/roi_align/roi_align.py:6-48.
+
+Both accept the image in either memory format: contiguous NCHW (the reference's) or
+``torch.channels_last`` (the native one here -- see csrc/roi_align.cu); crops come back in the same format,
+logical shape ``[R, C, crop_h, crop_w]`` either way.
+"""
+import torch
+from torch import nn
+
+from . import _lib
+
+
+def _mem_format(layout):
+    return torch.channels_last if layout == _lib.FI_LAYOUT_NHWC else torch.contiguous_format
+
+
+def _prep_boxes(boxes, box_ind, device):
+    if boxes.dim() != 2 or boxes.size(1) != 4:
+        raise _lib.FiError("boxes must be [R,4] (y1,x1,y2,x2), got %s" % (tuple(boxes.shape),))
+    if box_ind.dim() != 1 or box_ind.size(0) != boxes.size(0):
+        raise _lib.FiError("box_ind must be [R]")
+    boxes = boxes.detach().to(device=device, dtype=torch.float32).contiguous()
+    box_ind = box_ind.detach().to(device=device, dtype=torch.int32).contiguous()
+    return boxes, box_ind
+
+
+class _CropAndResize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image, boxes, box_ind, crop_h, crop_w, extrap, out, dst_row):
+        if image.dtype != torch.float32:
+            raise _lib.FiError("crop_and_resize computes in fp32 like the reference; got %s" % image.dtype)
+        layout, image = _lib.layout_of(image)
+        boxes, box_ind = _prep_boxes(boxes, box_ind, image.device)
+        B, Cc, H, W = image.shape
+        R = boxes.size(0)
+        if out is None:
+            if dst_row is not None:
+                raise _lib.FiError("dst_row needs a preallocated `out`")
+            crops = torch.empty((R, Cc, crop_h, crop_w), device=image.device, dtype=torch.float32,
+                                memory_format=_mem_format(layout))
+        else:
+            crops = out
+            ok = crops.is_contiguous(memory_format=_mem_format(layout)) and crops.dtype == torch.float32 \
+                and tuple(crops.shape[1:]) == (Cc, crop_h, crop_w)
+            if not ok:
+                raise _lib.FiError("`out` must be fp32 [rows,%d,%d,%d] in the image's memory format" % (Cc, crop_h, crop_w))
+            ctx.mark_dirty(crops)
+        ctx.has_out = out is not None
+        if dst_row is not None:
+            dst_row = dst_row.to(device=image.device, dtype=torch.int32).contiguous()
+        with torch.cuda.device(image.device):
+            _lib.check(_lib.lib().fi_crop_and_resize_forward(
+                _lib.ptr(image), layout, _lib.ptr(boxes), _lib.ptr(box_ind), _lib.ptr(dst_row), R, B, H, W,
+                crop_h, crop_w, Cc, float(extrap), _lib.ptr(crops), layout, _lib.stream_ptr(image.device)))
+        ctx.save_for_backward(boxes, box_ind, dst_row if dst_row is not None else torch.empty(0))
+        ctx.has_rows = dst_row is not None
+        ctx.im_size = (B, Cc, H, W)
+        ctx.layout = layout
+        ctx.crop = (crop_h, crop_w)
+        return crops
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        boxes, box_ind, rows = ctx.saved_tensors
+        rows = rows if ctx.has_rows else None
+        B, Cc, H, W = ctx.im_size
+        layout = ctx.layout
+        grad_out = grad_out.contiguous(memory_format=_mem_format(layout))
+        grad_image = torch.empty(ctx.im_size, device=grad_out.device, dtype=torch.float32, memory_format=_mem_format(layout))
+        with torch.cuda.device(grad_out.device):
+            _lib.check(_lib.lib().fi_crop_and_resize_backward(
+                _lib.ptr(grad_out), layout, _lib.ptr(boxes), _lib.ptr(box_ind), _lib.ptr(rows), boxes.size(0), B, H, W,
+                ctx.crop[0], ctx.crop[1], Cc, _lib.ptr(grad_image), layout, 0, _lib.stream_ptr(grad_out.device)))
+        # `out` was written in place: rows this call did not touch pass their gradient through to whoever wrote them
+        return grad_image, None, None, None, None, None, (grad_out if ctx.has_out else None), None
+
+
+def crop_and_resize(image, boxes, box_ind, crop_h, crop_w, extrapolation_value=0.0, out=None, dst_row=None):
+    """Functional form.  ``out``/``dst_row`` fuse the scatter-back of lib/sub_module.py:645-662: crop ``r`` is
+    written into row ``dst_row[r]`` of the preallocated ``out`` (rows not named by ``dst_row`` are left untouched)."""
+    return _CropAndResize.apply(image, boxes, box_ind, int(crop_h), int(crop_w), float(extrapolation_value), out, dst_row)
+
+
+class CropAndResizeFunction(object):
+    """Old-style call shape of lib/roi_align/crop_and_resize.py:14-54 on top of a modern static Function."""
+
+    def __init__(self, crop_height, crop_width, extrapolation_value=0):
+        self.crop_height = crop_height
+        self.crop_width = crop_width
+        self.extrapolation_value = extrapolation_value
+
+    def __call__(self, image, boxes, box_ind):
+        return crop_and_resize(image, boxes, box_ind, self.crop_height, self.crop_width, self.extrapolation_value)
+
+
+class RoIAlign(nn.Module):
+    """lib/roi_align/roi_align.py:6-48: boxes are (x1,y1,x2,y2) in pixels of the feature map."""
+
+    def __init__(self, crop_height, crop_width, extrapolation_value=0, transform_fpcoor=True):
+        super().__init__()
+        self.crop_height = crop_height
+        self.crop_width = crop_width
+        self.extrapolation_value = extrapolation_value
+        self.transform_fpcoor = transform_fpcoor
+
+    def forward(self, featuremap, boxes, box_ind):
+        x1, y1, x2, y2 = torch.split(boxes, 1, dim=1)
+        image_height, image_width = featuremap.size()[2:4]
+        if self.transform_fpcoor:
+            spacing_w = (x2 - x1) / float(self.crop_width)
+            spacing_h = (y2 - y1) / float(self.crop_height)
+            nx0 = (x1 + spacing_w / 2 - 0.5) / float(image_width - 1)
+            ny0 = (y1 + spacing_h / 2 - 0.5) / float(image_height - 1)
+            nw = spacing_w * float(self.crop_width - 1) / float(image_width - 1)
+            nh = spacing_h * float(self.crop_height - 1) / float(image_height - 1)
+            boxes = torch.cat((ny0, nx0, ny0 + nh, nx0 + nw), 1)
+        else:
+            boxes = torch.cat((y1 / float(image_height - 1), x1 / float(image_width - 1),
+                               y2 / float(image_height - 1), x2 / float(image_width - 1)), 1)
+        return crop_and_resize(featuremap, boxes.detach().contiguous(), box_ind.detach(),
+                               self.crop_height, self.crop_width, self.extrapolation_value)
+
+
+def crop_taps(boxes, image_height, image_width, crop_h, crop_w):
+    """Integer bilinear taps [R,crop_h,crop_w,5] = (y_lo,y_hi,x_lo,x_hi,inside) computed on the device."""
+    boxes = boxes.detach().to(dtype=torch.float32).contiguous()
+    taps = torch.empty((boxes.size(0), crop_h, crop_w, 5), device=boxes.device, dtype=torch.int32)
+    with torch.cuda.device(boxes.device):
+        _lib.check(_lib.lib().fi_crop_taps(_lib.ptr(boxes), boxes.size(0), image_height, image_width, crop_h, crop_w,
+                                           _lib.ptr(taps), _lib.stream_ptr(boxes.device)))
+    return taps

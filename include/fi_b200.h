@@ -1,0 +1,175 @@
+/* fi_b200.h -- C ABI of libfi_b200.so, the B200 (sm_100a) implementation of the Feature Intertwiner
+ * hot path.  Plain pointers and sizes only; every pointer is a DEVICE pointer owned by the caller;
+ * every entry point enqueues on the given stream and returns without synchronising.
+ *
+ * The reference's drop-in boundary is the `extern "C"` launcher layer underneath its (long dead)
+ * torch.utils.ffi modules -- SURVEY.md section 8(b).  Section 1 below re-exports those launchers with
+ * their exact names and signatures; section 2 onwards are the B200-native entry points the Python
+ * operator layer (feature_intertwiner_b200/*.py) binds.  Citations are relative to the reference tree.
+ *
+ * Error convention: the reference's launchers print and exit(-1) on a launch failure
+ * (crop_and_resize_kernel.cu:186-191).  Here nothing ever exits: the fi_* entry points return FI_OK or
+ * a negative status and fi_last_error() describes it; the void reference-named launchers record the
+ * status where fi_last_status() can read it.
+ */
+#ifndef FI_B200_H
+#define FI_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if !defined(__DRIVER_TYPES_H__) && !defined(__CUDA_RUNTIME_H__)
+typedef struct CUstream_st *cudaStream_t;
+#endif
+
+#define FI_OK 0
+#define FI_ERR_INVALID (-1)     /* bad argument (null pointer, negative size, unsupported shape) */
+#define FI_ERR_CUDA (-2)        /* a CUDA call or kernel launch failed                             */
+#define FI_ERR_UNSUPPORTED (-3) /* valid request this build has no kernel for                      */
+
+#define FI_LAYOUT_NCHW 0 /* [N,C,H,W] contiguous -- the reference's layout                           */
+#define FI_LAYOUT_NHWC 1 /* torch.channels_last: same logical tensor, C innermost in memory        */
+
+int fi_abi_version(void);
+const char *fi_last_error(void); /* thread-local, never NULL */
+int fi_last_status(void);        /* status of the last call made by this thread */
+
+/* ---------------------------------------------------------------------------------------------
+ * 1. Reference-named launchers (exact signatures).
+ * ------------------------------------------------------------------------------------------- */
+
+/* lib/roi_align/src/cuda/crop_and_resize_kernel.h:8-12.  image[batch,depth,H,W] NCHW, boxes[num_boxes,4]
+ * normalised (y1,x1,y2,x2), box_ind[num_boxes] -> crops[num_boxes,depth,crop_h,crop_w] NCHW.
+ * Unlike the reference the caller need NOT zero `crops` first (crop_and_resize_gpu.c:25): rows whose
+ * box_ind is out of range are written as zeros by the kernel itself. */
+void CropAndResizeLaucher(const float *image_ptr, const float *boxes_ptr, const int *box_ind_ptr, int num_boxes,
+                          int batch, int image_height, int image_width, int crop_height, int crop_width, int depth,
+                          float extrapolation_value, float *crops_ptr, cudaStream_t stream);
+
+/* lib/roi_align/src/cuda/crop_and_resize_kernel.h:14-18.  ACCUMULATES into grads_image exactly like the
+ * reference kernel; the caller zeroes it first (crop_and_resize_gpu.c:57). */
+void CropAndResizeBackpropImageLaucher(const float *grads_ptr, const float *boxes_ptr, const int *box_ind_ptr,
+                                       int num_boxes, int batch, int image_height, int image_width, int crop_height,
+                                       int crop_width, int depth, float *grads_image_ptr, cudaStream_t stream);
+
+/* lib/roi_pooling/src/roi_pooling_kernel.h:8-18.  bottom[B,C,H,W] NCHW, rois[num_rois,5]=(b,x1,y1,x2,y2) px.
+ * Return 1 on success (the reference's convention), 0 on failure. */
+int ROIPoolForwardLaucher(const float *bottom_data, const float spatial_scale, const int num_rois, const int height,
+                          const int width, const int channels, const int pooled_height, const int pooled_width,
+                          const float *bottom_rois, float *top_data, int *argmax_data, cudaStream_t stream);
+int ROIPoolBackwardLaucher(const float *top_diff, const float spatial_scale, const int batch_size, const int num_rois,
+                           const int height, const int width, const int channels, const int pooled_height,
+                           const int pooled_width, const float *bottom_rois, float *bottom_diff,
+                           const int *argmax_data, cudaStream_t stream);
+
+/* lib/nms/src/cuda/nms_kernel.h:11-12.  boxes_dev[boxes_num,5]=(x1,y1,x2,y2,score) sorted by score;
+ * mask_dev[boxes_num, ceil(boxes_num/64)] bit j of word (i,w) set <=> IoU(i, 64w+j) > thresh, j > i.
+ * Runs on the legacy default stream like the reference (nms_kernel.cu:79). */
+void _nms(int boxes_num, float *boxes_dev, unsigned long long *mask_dev, float nms_overlap_thresh);
+
+/* ---------------------------------------------------------------------------------------------
+ * 2. RoIAlign (TF crop_and_resize semantics), B200-native.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Forward.  Replaces crop_and_resize_gpu_forward (lib/roi_align/src/crop_and_resize_gpu.c:7-37).
+ *   image         [batch,depth,H,W] in `image_layout`
+ *   boxes         [num_boxes,4] (y1,x1,y2,x2) normalised; box_ind [num_boxes] int32
+ *   dst_row       NULL, or [num_boxes] int32: crop r is written to row dst_row[r] of `crops` (fuses the
+ *                 scatter-back of lib/sub_module.py:645-662 into the op); rows are never zero-filled here
+ *   crops         [>=num_boxes,depth,crop_h,crop_w] in `crops_layout`
+ * image_layout and crops_layout must be equal (NCHW/NCHW or NHWC/NHWC); NHWC needs depth % 4 == 0. */
+int fi_crop_and_resize_forward(const float *image, int image_layout, const float *boxes, const int *box_ind,
+                               const int *dst_row, int num_boxes, int batch, int image_height, int image_width,
+                               int crop_height, int crop_width, int depth, float extrapolation_value, float *crops,
+                               int crops_layout, cudaStream_t stream);
+
+/* Backward.  Replaces crop_and_resize_gpu_backward (crop_and_resize_gpu.c:40-69).
+ *   grads        [>=num_boxes,depth,crop_h,crop_w] in `grads_layout`; src_row as dst_row above
+ *   grads_image  [batch,depth,H,W] in `image_layout`; zero-filled first unless accumulate != 0 */
+int fi_crop_and_resize_backward(const float *grads, int grads_layout, const float *boxes, const int *box_ind,
+                                const int *src_row, int num_boxes, int batch, int image_height, int image_width,
+                                int crop_height, int crop_width, int depth, float *grads_image, int image_layout,
+                                int accumulate, cudaStream_t stream);
+
+/* Integer taps of every sample, taps[num_boxes,crop_h,crop_w,5] = (y_lo,y_hi,x_lo,x_hi,inside): the "RoI
+ * indices" the parity bar requires bit-exact (crop_and_resize_kernel.cu:40-70). */
+int fi_crop_taps(const float *boxes, int num_boxes, int image_height, int image_width, int crop_height,
+                 int crop_width, int *taps, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * 3. RoI -> pyramid level, reliable / less-reliable split (lib/sub_module.py:397-448,474-493,541-548).
+ * ------------------------------------------------------------------------------------------- */
+
+/* level[n] = clamp(round(4 + log2(sqrt(w*h) / (base / sqrt(image_area)))), 2, 5); zero-padded RoIs -> 2. */
+int fi_roi_level(const float *rois, int n, float image_area, float base, int *level, cudaStream_t stream);
+
+/* One launch builds every per-level index list of Dev.forward in torch.nonzero (row-major) order:
+ *   small_idx [4,n]  flat RoI ids with level == 2+l          small_cnt [4]
+ *   big_idx   [4,n]  flat RoI ids with level  > 2+l          big_cnt   [4]
+ *   slot      [n]    position of RoI i inside its own level's small list (its row in that level's crop)
+ * n <= 65536. */
+int fi_split_levels(const int *level, int n, int *small_idx, int *small_cnt, int *big_idx, int *big_cnt, int *slot,
+                    cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * 4. Per-class statistics (lib/sub_module.py:664-684 _assign_feat2cls).
+ * ------------------------------------------------------------------------------------------- */
+
+/* gt[k] int32 class ids, feat[k,F] -> mean[F,ncls] (class-minor like the reference), cnt[ncls];
+ * class 0 (background) and ids outside [0,ncls) contribute nothing.  ncls <= 1024.  Deterministic. */
+int fi_segment_mean_forward(const int *gt, const float *feat, int k, int F, int ncls, float *mean, float *cnt,
+                            cudaStream_t stream);
+/* grad_feat[i,:] = grad_mean[:,gt_i] / cnt[gt_i]  (0 for background rows) */
+int fi_segment_mean_backward(const int *gt, const float *grad_mean, const float *cnt, int k, int F, int ncls,
+                             float *grad_feat, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * 5. Sinkhorn optimal-transport loss (lib/OT_module.py:104-135), batched.
+ * ------------------------------------------------------------------------------------------- */
+
+/* n_problems independent problems; x,y [n_problems,N,D] (rows = critic channels, cols = positions).
+ * loss[p] = <P,C>, C = 1 - xh yh^T, K = exp(-inv_eps C), L iterations, P = diag(a) K diag(b).
+ * grad_x / grad_y (NULL or [n_problems,N,D]): d loss / d x, y with P held constant (no_bp_P_L=True,
+ * OT_module.py:130-131) through the row normalisation.  N <= 256; any D >= 1. */
+int fi_sinkhorn(const float *x, const float *y, int n_problems, int N, int D, float inv_eps, int L, float *loss,
+                float *grad_x, float *grad_y, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * 6. Buffer update + class match (lib/model.py:143-224, B == 1 running mean and B > 1 FIFO).
+ * ------------------------------------------------------------------------------------------- */
+
+/* Inputs are the UN-normalised sums an all-reduce produces: big_sum[F,ncls] = sum_{gpu,scale} feat*cnt,
+ * big_n[ncls] = sum cnt.  Updates buffer[B,F,ncls] / buffer_cnt[B,ncls] in place and writes
+ * final_big[F,ncls] (the count-weighted mean over the B slots).  B == 1: running mean over all history
+ * (model.py:153-158), slot must be 0.  B > 1: the buffer is a RING -- `slot` is the position this call
+ * overwrites (the reference instead shifts the whole buffer left each iteration, model.py:161-164). */
+int fi_buffer_update(const float *big_sum, const float *big_n, int B, int slot, int F, int ncls, float *buffer,
+                     float *buffer_cnt, float *final_big, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * 7. NMS with the reduce on the device (lib/nms/src/nms_cuda.c:17-67, no host round trip).
+ * ------------------------------------------------------------------------------------------- */
+
+/* boxes[n_images, n, 5] = (x1,y1,x2,y2,score), each image sorted by descending score.
+ * mask: workspace [n_images, n, ceil(n/64)] u64.  keep[n_images, n] int32 (kept indices first, rest -1),
+ * num_keep[n_images].  Suppress when IoU > thresh (the reference's GPU rule, nms_kernel.cu:63). */
+int fi_nms_batched(const float *boxes, int n_images, int n, float thresh, unsigned long long *mask, int *keep,
+                   int *num_keep, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * 8. RoIPool with an argmax-scatter backward (lib/roi_pooling/src/roi_pooling_cuda.c:7-88).
+ * ------------------------------------------------------------------------------------------- */
+int fi_roi_pool_forward(const float *bottom, float spatial_scale, int batch, int num_rois, int height, int width,
+                        int channels, int pooled_h, int pooled_w, const float *rois, float *top, int *argmax,
+                        cudaStream_t stream);
+/* bottom_diff is zero-filled here, then receives exactly what ROIPoolBackward (roi_pooling_kernel.cu:128-203)
+ * computes, at O(outputs) instead of O(inputs x rois) work. */
+int fi_roi_pool_backward(const float *top_diff, float spatial_scale, int batch, int num_rois, int height, int width,
+                         int channels, int pooled_h, int pooled_w, const float *rois, float *bottom_diff,
+                         const int *argmax, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FI_B200_H */

@@ -1,0 +1,185 @@
+"""RoIAlign CUDA path vs the oracle (bit-exact values forward, bit-exact taps; backward to fp32 summation-order
+tolerance), through the C ABI, in both memory formats.  Edge cases follow SURVEY.md 8(c)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import clib
+
+pytestmark = pytest.mark.gpu
+
+BWD_RTOL, BWD_ATOL = 1e-5, 1e-5   # fp32 scatter-add: order of summation differs from the serial CPU loop
+
+
+def _fi():
+    import feature_intertwiner_b200 as fi
+    return fi
+
+
+def _case(seed, B, C, H, W, R, zero_rows=2):
+    from feature_intertwiner_b200 import synth
+    g = torch.Generator().manual_seed(seed)
+    image = torch.randn(B, C, H, W, generator=g)
+    rois = synth.make_rois(1, R, (H * 4, W * 4), g, zero_frac=zero_rows / R, straddle_frac=2.0 / R)[0]
+    box_ind = torch.randint(0, B, (R,), generator=g, dtype=torch.int32)
+    return image, rois, box_ind
+
+
+@pytest.mark.parametrize("fmt", ["nchw", "nhwc"])
+@pytest.mark.parametrize("P", [1, 7, 14, (3, 5)])
+@pytest.mark.parametrize("C", [256, 6])
+def test_forward_bit_exact(fmt, P, C):
+    fi = _fi()
+    ph, pw = (P, P) if isinstance(P, int) else P
+    image, rois, box_ind = _case(1, 3, C, 40, 52, 97)
+    want = clib.oracle_crop_and_resize_fwd(image.numpy(), rois.numpy(), box_ind.numpy(), ph, pw, 0.5)
+    img = image.cuda()
+    if fmt == "nhwc":
+        img = img.contiguous(memory_format=torch.channels_last)
+    got = fi.CropAndResizeFunction(ph, pw, 0.5)(img, rois.cuda(), box_ind.cuda())
+    assert got.shape == want.shape
+    if fmt == "nhwc" and ph * pw > 1 and C > 1:
+        assert got.is_contiguous(memory_format=torch.channels_last)
+    np.testing.assert_array_equal(got.cpu().numpy(), want)      # bit-exact
+
+
+@pytest.mark.parametrize("P", [1, 2, 7, 14])
+def test_taps_bit_exact(P):
+    fi = _fi()
+    _, rois, _ = _case(2, 1, 1, 208, 336, 512, zero_rows=20)
+    want = clib.oracle_crop_taps(208, 336, rois.numpy(), P, P)
+    got = fi.crop_taps(rois.cuda(), 208, 336, P, P).cpu().numpy()
+    np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("fmt", ["nchw", "nhwc"])
+@pytest.mark.parametrize("P", [1, 7, 14])
+@pytest.mark.parametrize("C", [256, 6])
+def test_backward_matches_oracle(fmt, P, C):
+    fi = _fi()
+    image, rois, box_ind = _case(3, 2, C, 26, 42, 150, zero_rows=10)
+    g = torch.Generator().manual_seed(5)
+    grads = torch.randn(150, C, P, P, generator=g)
+    want = clib.oracle_crop_and_resize_bwd(grads.numpy(), rois.numpy(), box_ind.numpy(), tuple(image.shape))
+    img = image.cuda().requires_grad_()
+    x = img.contiguous(memory_format=torch.channels_last) if fmt == "nhwc" else img
+    out = fi.CropAndResizeFunction(P, P)(x, rois.cuda(), box_ind.cuda())
+    out.backward(grads.cuda())
+    np.testing.assert_allclose(img.grad.cpu().numpy(), want, rtol=BWD_RTOL, atol=BWD_ATOL)
+
+
+def test_golden_vectors(golden_dir):
+    """Outputs of the reference's own crop_and_resize.c (tests/golden/make_golden.py)."""
+    fi = _fi()
+    z = np.load(golden_dir + "/roi_align.npz")
+    image, boxes, box_ind = (torch.from_numpy(z[k]).cuda() for k in ("image", "boxes", "box_ind"))
+    for fmt in ("nchw", "nhwc"):
+        img = image.contiguous(memory_format=torch.channels_last) if fmt == "nhwc" else image
+        for P in (1, 2, 7, 14):
+            x = img.clone().requires_grad_()
+            out = fi.CropAndResizeFunction(P, P, 0.25)(x, boxes, box_ind)
+            np.testing.assert_array_equal(out.detach().cpu().numpy(), z[f"crops_{P}"])
+            out.backward(torch.from_numpy(z[f"grads_{P}"]).cuda())
+            np.testing.assert_allclose(x.grad.cpu().numpy(), z[f"grad_image_{P}"], rtol=BWD_RTOL, atol=BWD_ATOL)
+        out = fi.crop_and_resize(img, boxes, box_ind, 3, 5)
+        np.testing.assert_array_equal(out.cpu().numpy(), z["crops_3x5"])
+
+
+def test_known_answers():
+    """SURVEY.md 8(c) i-vi: identity crop, constant image, linear ramp, extrapolation, P=1 centre, zero box."""
+    fi = _fi()
+    H, W = 9, 13
+    g = torch.Generator().manual_seed(7)
+    image = torch.randn(2, 4, H, W, generator=g).cuda()
+    ind0 = torch.zeros(1, dtype=torch.int32).cuda()
+    # (i) identity
+    out = fi.crop_and_resize(image, torch.tensor([[0., 0., 1., 1.]]).cuda(), ind0, H, W)
+    torch.testing.assert_close(out[0], image[0], rtol=0, atol=1e-6)
+    # (ii) constant image -> constant crop
+    const = torch.full((1, 3, H, W), 2.5).cuda()
+    out = fi.crop_and_resize(const, torch.tensor([[0.1, 0.2, 0.7, 0.9]]).cuda(), ind0, 7, 7)
+    assert torch.all(out == 2.5)
+    # (iii) linear ramp f(y,x) = 2y + 3x -> exact analytic values
+    yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    ramp = (2 * yy + 3 * xx)[None, None].cuda()
+    y1, x1, y2, x2 = 0.125, 0.25, 0.75, 0.875
+    out = fi.crop_and_resize(ramp, torch.tensor([[y1, x1, y2, x2]]).cuda(), ind0, 5, 5)[0, 0].cpu()
+    ys = y1 * (H - 1) + torch.arange(5) * (y2 - y1) * (H - 1) / 4
+    xs = x1 * (W - 1) + torch.arange(5) * (x2 - x1) * (W - 1) / 4
+    torch.testing.assert_close(out, 2 * ys[:, None] + 3 * xs[None, :], rtol=1e-5, atol=1e-5)
+    # (iv) partly outside -> extrapolation value exactly there
+    out = fi.crop_and_resize(const, torch.tensor([[-0.5, 0.0, 0.5, 1.0]]).cuda(), ind0, 5, 3, extrapolation_value=-7.0)[0, 0].cpu()
+    assert torch.all(out[:2] == -7.0) and torch.all(out[2:] == 2.5)     # rows at y=-4,-2 are outside; 0,2,4 inside
+    # (v) P=1 -> centre sample
+    out = fi.crop_and_resize(ramp, torch.tensor([[0.25, 0.25, 0.75, 0.75]]).cuda(), ind0, 1, 1)
+    assert abs(out.item() - (2 * 0.5 * (H - 1) + 3 * 0.5 * (W - 1))) < 1e-5
+    # (vi) all-zero padded box -> every sample is image[b,:,0,0]
+    out = fi.crop_and_resize(image, torch.zeros(1, 4).cuda(), torch.ones(1, dtype=torch.int32).cuda(), 7, 7)
+    assert torch.all(out[0] == image[1, :, 0, 0][:, None, None])
+
+
+@pytest.mark.parametrize("fmt", ["nchw", "nhwc"])
+def test_backward_is_transpose_of_forward(fmt):
+    """SURVEY.md 8(c) vii at a BASELINE-sized level map: <fwd(x), g> == <x, bwd(g)>."""
+    fi = _fi()
+    from feature_intertwiner_b200 import synth
+    g = torch.Generator().manual_seed(11)
+    B, C, H, W, R = 2, 256, 104, 168, 1024
+    x = torch.randn(B, C, H, W, generator=g).cuda()
+    if fmt == "nhwc":
+        x = x.contiguous(memory_format=torch.channels_last)
+    x.requires_grad_()
+    rois = synth.make_rois(1, R, (832, 1344), g)[0].cuda()
+    ind = torch.randint(0, B, (R,), generator=g, dtype=torch.int32).cuda()
+    out = fi.crop_and_resize(x, rois, ind, 7, 7)
+    gy = torch.randn(out.shape, generator=g).cuda()
+    out.backward(gy)
+    lhs = (out.detach().double() * gy.double()).sum()
+    rhs = (x.detach().double() * x.grad.double()).sum()
+    assert abs(lhs - rhs) / abs(lhs) < 1e-5
+
+
+def test_bad_box_ind_rows_are_zero_and_dst_row_scatter():
+    fi = _fi()
+    image, rois, box_ind = _case(4, 2, 8, 20, 20, 16)
+    box_ind[3] = 5
+    box_ind[7] = -1
+    for fmt in ("nchw", "nhwc"):
+        img = image.cuda()
+        if fmt == "nhwc":
+            img = img.contiguous(memory_format=torch.channels_last)
+        out = fi.crop_and_resize(img, rois.cuda(), box_ind.cuda(), 7, 7)
+        assert torch.all(out[3] == 0) and torch.all(out[7] == 0)       # crop_and_resize_kernel.cu:34-38
+        keep = [i for i in range(16) if i not in (3, 7)]
+        want = clib.oracle_crop_and_resize_fwd(image.numpy(), rois.numpy()[keep], box_ind.numpy()[keep], 7, 7)
+        np.testing.assert_array_equal(out[keep].cpu().numpy(), want)
+        # fused scatter-back (lib/sub_module.py:645-662)
+        perm = torch.randperm(16, generator=torch.Generator().manual_seed(0)).int()
+        dest = torch.zeros(16, 8, 7, 7, device="cuda").contiguous(memory_format=torch.channels_last if fmt == "nhwc" else torch.contiguous_format)
+        fi.crop_and_resize(img, rois.cuda(), box_ind.cuda(), 7, 7, out=dest, dst_row=perm.cuda())
+        torch.testing.assert_close(dest[perm.long().cuda()], out, rtol=0, atol=0)
+
+
+def test_reference_named_launchers():
+    """The exact C symbols of crop_and_resize_kernel.h:8-18, raw pointers, caller-zeroed grads."""
+    from feature_intertwiner_b200 import _lib
+    image, rois, box_ind = _case(6, 2, 16, 30, 34, 40)
+    img, b, bi = image.cuda(), rois.cuda(), box_ind.cuda()
+    crops = torch.empty(40, 16, 7, 7, device="cuda")
+    L = _lib.lib()
+    s = torch.cuda.current_stream().cuda_stream
+    L.CropAndResizeLaucher(img.data_ptr(), b.data_ptr(), bi.data_ptr(), 40, 2, 30, 34, 7, 7, 16, 0.0, crops.data_ptr(), s)
+    assert L.fi_last_status() == 0
+    want = clib.oracle_crop_and_resize_fwd(image.numpy(), rois.numpy(), box_ind.numpy(), 7, 7)
+    np.testing.assert_array_equal(crops.cpu().numpy(), want)
+    g = torch.randn(40, 16, 7, 7, device="cuda")
+    gi = torch.zeros_like(img)
+    L.CropAndResizeBackpropImageLaucher(g.data_ptr(), b.data_ptr(), bi.data_ptr(), 40, 2, 30, 34, 7, 7, 16, gi.data_ptr(), s)
+    want = clib.oracle_crop_and_resize_bwd(g.cpu().numpy(), rois.numpy(), box_ind.numpy(), tuple(image.shape))
+    np.testing.assert_allclose(gi.cpu().numpy(), want, rtol=BWD_RTOL, atol=BWD_ATOL)
+
+
+def test_refuses_cpu_tensors():
+    fi = _fi()
+    with pytest.raises(fi.FiError):
+        fi.crop_and_resize(torch.randn(1, 4, 8, 8), torch.zeros(1, 4), torch.zeros(1, dtype=torch.int32), 7, 7)
