@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""Benchmark of the Feature Intertwiner hot path on B200 (BASELINE.json metric: RoIs/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one batch of synthetic input:
+
+    level rule + reliable/less-reliable split  ->  every RoIAlign call of Dev.forward (big 14x14 on the raw
+    level maps, small 7x7 + 14x14 on the made-up maps; 7x7 written straight to its final row)  ->  per-class
+    segment means of the critic features  ->  buffer update + class match  ->  OptTrans / Sinkhorn(L) loss
+    ->  backward of all of it (Sinkhorn gradient, segment-mean backward, RoIAlign backward of every crop).
+
+The make-up conv and the critic convs are stock cuDNN and are NOT part of the path:
+their outputs (made-up maps, critic features) and the upstream crop gradients are synthetic inputs.
+
+`value`  : RoIs/s with all inputs resident in HBM (device-timed, CUDA events, max over ranks).
+`e2e`    : the same step through the public API starting from pinned HOST buffers (H2D of every input,
+           D2H of the loss) inside the timed region.
+`--impl reference`: the reference's own CPU implementation (oracle/_ref: lib/roi_align/src/crop_and_resize.c
+           compiled unmodified, OpenMP forward + serial backward) plus the torch-CPU restatement of
+           lib/OT_module.py for the loss, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FEAT = 1024
+NCLS = 81
+DEPTH = 256
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 6 for k in range(4) if r[2 + k].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+# =================================================================================================== inputs
+def make_inputs(wl, seed):
+    """Everything a step consumes, on the HOST (pinned), seeded.  The split itself is computed by the step."""
+    from feature_intertwiner_b200 import synth
+    g = torch.Generator().manual_seed(seed)
+    B, R, hw = wl["batch"], wl["rois_per_image"], wl["image"]
+    host = {
+        "rois": synth.make_rois(B, R, hw, g),
+        "gt": synth.make_class_ids(B, R, g, NCLS),
+        "raw": synth.make_feature_maps(B, hw, DEPTH, g, channels_last=True),      # P2..P5
+        "madeup": synth.make_feature_maps(B, hw, DEPTH, g, channels_last=True),   # upsample(P2..P5): stock conv output
+    }
+    return host
+
+
+def pin(t):
+    return t.pin_memory() if torch.cuda.is_available() else t
+
+
+def build_config(wl):
+    import types
+    import numpy as np
+    ns = types.SimpleNamespace
+    return ns(
+        DEV=ns(SWITCH=True, STRUCTURE="beta", BASELINE=False, BUFFER_SIZE=1, LOSS_CHOICE="ot", OT_ONE_DIM_FORM="conv", LOSS_FAC=0.5,
+               INST_LOSS=False, FEAT_BRANCH_POOL_SIZE=14, ASSIGN_BOX_ON_ALL_SCALE=False, BIG_FEAT_DETACH=True, UPSAMPLE_FAC=1.0,
+               MULTI_UPSAMPLER=False, BIG_SUPERVISE=False, DIS_UPSAMPLER=False, INIT_BUFFER_WEIGHT="scratch"),
+        ROIS=ns(METHOD="roi_align", ASSIGN_ANCHOR_BASE=224.0), MRCNN=ns(POOL_SIZE=7, MASK_POOL_SIZE=14),
+        DATA=ns(IMAGE_SHAPE=np.array([wl["image"][0], wl["image"][1], 3])), DATASET=ns(NUM_CLASSES=NCLS))
+
+
+class Step(object):
+    """Device-side state + one pass of the hot path through the public API."""
+
+    def __init__(self, wl, device, world, seed):
+        import feature_intertwiner_b200 as fi
+        self.fi, self.wl, self.dev, self.world = fi, wl, device, world
+        self.cfg = build_config(wl)
+        torch.manual_seed(2000)
+        self.ot = fi.OptTrans(self.cfg, ch_x=FEAT, L=wl["sinkhorn_iters"]).to(device)
+        self.loss_mod = fi.IntertwinerLoss(self.cfg, ot_loss=self.ot, feat_dim=FEAT, distributed=world > 1).to(device)
+        self.host = make_inputs(wl, seed)
+        B, R = wl["batch"], wl["rois_per_image"]
+        # the split of THIS input fixes the shapes of the synthetic critic features / upstream gradients
+        rois_d = self.host["rois"].to(device)
+        split = fi.split_levels(fi.roi_level(rois_d, self.cfg.DATA.IMAGE_SHAPE))
+        self.counts = (list(split.small_cnt), list(split.big_cnt))
+        g = torch.Generator().manual_seed(seed + 1)
+        self.host["small_feat"] = [torch.rand(split.small_cnt[i], FEAT, generator=g) for i in range(3)]
+        self.host["big_feat"] = [torch.rand(split.big_cnt[i], FEAT, generator=g) for i in range(3)]
+        self.host["g_pooled"] = torch.randn(B * R, DEPTH, 7, 7, generator=g).contiguous(memory_format=torch.channels_last)
+        self.host["g_mask"] = torch.randn(B * R, DEPTH, 14, 14, generator=g).contiguous(memory_format=torch.channels_last)
+        self.host["g_big"] = [torch.randn(split.big_cnt[i], DEPTH, 14, 14, generator=g).contiguous(memory_format=torch.channels_last)
+                              for i in range(3)]
+        self.h2d_bytes = 0
+        self.pinned = self._map(self.host, pin)
+        self.resident = self._map(self.host, lambda t: t.to(device))
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self._flat(self.host))
+        self.algo = None
+
+    @staticmethod
+    def _map(d, f):
+        return {k: ([f(t) for t in v] if isinstance(v, list) else f(v)) for k, v in d.items()}
+
+    @staticmethod
+    def _flat(d):
+        for v in d.values():
+            for t in (v if isinstance(v, list) else [v]):
+                yield t
+
+    def upload(self):
+        """H2D of every input of the step from pinned host memory (the e2e leg)."""
+        return self._map(self.pinned, lambda t: t.to(self.dev, non_blocking=True))
+
+    def run(self, inp):
+        fi, cfg = self.fi, self.cfg
+        B, R = self.wl["batch"], self.wl["rois_per_image"]
+        total = B * R
+        rois, gt = inp["rois"], inp["gt"]
+        rois_flat, gt_flat = rois.view(total, 4), gt.view(total)
+        raw = [m.requires_grad_() for m in inp["raw"]]
+        madeup = [m.requires_grad_() for m in inp["madeup"]]
+        small_f = [t.requires_grad_() for t in inp["small_feat"]]
+        big_f = inp["big_feat"]
+        split = fi.split_levels(fi.roi_level(rois, cfg.DATA.IMAGE_SHAPE, cfg.ROIS.ASSIGN_ANCHOR_BASE))
+        pooled_out = torch.zeros((total, DEPTH, 7, 7), device=self.dev).contiguous(memory_format=torch.channels_last)
+        mask_out = torch.zeros((total, DEPTH, 14, 14), device=self.dev).contiguous(memory_format=torch.channels_last)
+        outs, grads = [], []
+        bfeat, bcnt, sfeat, scnt = [], [], [], []
+        for i in range(4):
+            if split.small_cnt[i] == 0:
+                continue
+            if i < 3 and split.big_cnt[i]:
+                bidx = split.big(i).long()
+                crop = fi.crop_and_resize(raw[i], rois_flat[bidx], (bidx // R).int(), 14, 14)
+                outs.append(crop); grads.append(inp["g_big"][i])
+                f, c = fi.assign_feat2cls(gt_flat[bidx], big_f[i], NCLS)
+                bfeat.append(f); bcnt.append(c)
+            s32 = split.small(i)
+            sidx = s32.long()
+            boxes, ind = rois_flat[sidx], (sidx // R).int()
+            pooled_out = fi.crop_and_resize(madeup[i], boxes, ind, 7, 7, out=pooled_out, dst_row=s32)
+            if i < 3:
+                mf = fi.crop_and_resize(madeup[i], boxes, ind, 14, 14)
+                mask_out.index_copy_(0, sidx, mf)
+                f, c = fi.assign_feat2cls(gt_flat[sidx], small_f[i], NCLS)
+                sfeat.append(f); scnt.append(c)
+            else:
+                mask_out = fi.crop_and_resize(madeup[i], boxes, ind, 14, 14, out=mask_out, dst_row=s32)
+        feat_in = [torch.stack(bfeat)[None].detach(), torch.stack(bcnt)[None], torch.stack(sfeat)[None], torch.stack(scnt)[None], None, None]
+        loss = self.loss_mod(feat_in).sum()
+        torch.autograd.backward([loss, pooled_out, mask_out] + outs, [torch.ones_like(loss), inp["g_pooled"], inp["g_mask"]] + grads)
+        if self.world > 1:
+            import torch.distributed as dist
+            flat = torch.cat([p.grad.reshape(-1) for p in self.ot.parameters()])
+            dist.all_reduce(flat)                     # gradient all-reduce of the path's own parameters (OptTrans)
+        for p in self.ot.parameters():
+            p.grad = None
+        return loss
+
+
+# =================================================================================================== ours
+def run_ours(args):
+    rank, world, local = dist_env()
+    import feature_intertwiner_b200 as fi
+    from feature_intertwiner_b200 import _lib, synth
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    wl = synth.WORKLOADS[args.workload]
+    step = Step(wl, dev, world, seed=2000 + rank)
+    lib = _lib.lib()
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)    # 256 MB > 126 MB L2 (inputs alone are > 3 GB anyway)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        evs = []
+        for _ in range(steps):
+            flush.add_(1.0)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            evs.append((a, b))
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps
+
+    # ---- device-resident value ------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    prof = fi.roi_align.enable_profiling()
+    n0 = lib.fi_kernel_launches()
+    ms = timed(lambda: step.run(step.resident), args.steps, args.warmup)
+    launches = (lib.fi_kernel_launches() - n0) // (args.steps + args.warmup)
+    records = fi.roi_align.disable_profiling()
+    clocks = sampler.stop() if rank == 0 else None
+    # ---- e2e: pinned host -> device -> step -> loss back on the host ------------------------------
+    def e2e_step():
+        loss = step.run(step.upload())
+        return float(loss.item())
+    ms_e2e = timed(e2e_step, max(2, args.steps // 2), 2)
+
+    rois_per_step = wl["batch"] * wl["rois_per_image"] * world
+    if rank != 0:
+        return
+    peak, peak_kind = measured_peak()
+    # ---- roofline of the dominant kernel family, from the per-launch events of the timed region ----
+    fam = {}
+    per_step = len(records) // (args.steps + args.warmup)
+    for rec in records[args.warmup * per_step:]:
+        d = fam.setdefault(rec["kernel"], [0.0, 0.0, 0])
+        d[0] += fi.roi_align.algorithmic_bytes(rec); d[1] += rec["start"].elapsed_time(rec["end"]); d[2] += 1
+    kernels = {k: {"launches_per_step": v[2] // args.steps, "avg_ms": v[1] / v[2], "alg_bytes_per_launch": v[0] / v[2], "gbs": v[0] / v[1] / 1e6,
+                   "frac": v[0] / v[1] / 1e6 / peak, "share_of_step": v[1] / args.steps / ms} for k, v in fam.items()}
+    dom = max(kernels, key=lambda k: kernels[k]["share_of_step"])
+    out = {
+        "metric": "RoIs/sec (RoIAlign fwd+bwd + split + class means + Sinkhorn intertwiner loss, fwd+bwd)",
+        "value": rois_per_step / (ms / 1e3), "unit": "RoIs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s: batch %d/GPU, %dx%d, %d RoIs/img, FPN P2-P5 C=256, pools 7+14, Sinkhorn N=256 L=%d, class-level OT loss"
+                               % (args.workload, wl["batch"], wl["image"][0], wl["image"][1], wl["rois_per_image"], wl["sinkhorn_iters"]),
+                   "layout": "channels_last maps/crops (logical NCHW)", "critic_and_makeup_convs": "excluded (stock cuDNN; SURVEY.md 8 a5)",
+                   "l2": "512 MB-class working set per step (> 126 MB L2) + 256 MB flush write between steps",
+                   "small_counts": step.counts[0], "big_counts": step.counts[1], "parallelism": "dp%d by image batch" % world},
+        "e2e": {"value": rois_per_step / (ms_e2e / 1e3), "unit": "RoIs/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": step.h2d_bytes, "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                     "frac": kernels[dom]["frac"], "traffic": None, "peak_kind": peak_kind},
+        "kernels": kernels,
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_reference(wl, seed=2000, budget_s=args.cpu_budget)
+    print(json.dumps(out), flush=True)
+
+
+# =================================================================================================== reference (CPU)
+def cpu_reference(wl, seed, budget_s=20.0):
+    """The reference's CPU path on a bounded sample: crop_and_resize.c (compiled unmodified, oracle/_ref) for every
+    RoIAlign call of the step on 1/k of the boxes, forward (OpenMP, all cores) + backward (serial, as written), plus
+    the whole class-level OT loss (torch-CPU restatement of lib/OT_module.py, all cores).  Throughput is scaled to
+    the full step: t_full = t_roialign_sample * k + t_loss."""
+    import numpy as np
+    from oracle import clib, pyref
+    from feature_intertwiner_b200 import synth
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    torch.set_num_threads(cores)
+    kind = "reference" if clib.have_ref() else "port"
+    fwd = clib.ref_crop_and_resize_fwd if clib.have_ref() else clib.oracle_crop_and_resize_fwd
+    bwd = clib.ref_crop_and_resize_bwd if clib.have_ref() else clib.oracle_crop_and_resize_bwd
+    g = torch.Generator().manual_seed(seed)
+    B, R, hw = wl["batch"], wl["rois_per_image"], wl["image"]
+    rois = synth.make_rois(B, R, hw, g)
+    level, _ = pyref.roi_level_ref(rois, (hw[0], hw[1], 3))
+    level = level.view(-1).numpy()
+    flat = rois.view(-1, 4).numpy()
+    shapes = synth.level_shapes(hw)
+    rng = np.random.default_rng(seed)
+    maps = [rng.standard_normal((B, DEPTH, h, w), dtype=np.float32) for (h, w) in shapes]
+    calls = []
+    for i in range(4):
+        sm = np.nonzero(level == i + 2)[0]
+        bg = np.nonzero(level > i + 2)[0]
+        if len(sm) == 0:
+            continue
+        calls += [(i, 7, sm), (i, 14, sm)]
+        if i < 3 and len(bg):
+            calls += [(i, 14, bg)]
+    total_crops = sum(len(c[2]) for c in calls)
+    # one probe call sizes the sample so the whole baseline costs about budget_s
+    t0 = time.perf_counter()
+    probe = calls[0][2][:16]
+    o = fwd(maps[0], flat[probe], (probe // R).astype(np.int32), 7, 7)
+    bwd(o, flat[probe], (probe // R).astype(np.int32), maps[0].shape)
+    per_crop = (time.perf_counter() - t0) / 16 * 2.5
+    k = max(1, int(np.ceil(total_crops * per_crop / (0.6 * budget_s))))
+    t_roi, n_sample = 0.0, 0
+    for (i, P, idx) in calls:
+        sub = idx[::k]
+        ind = (sub // R).astype(np.int32)
+        t0 = time.perf_counter()
+        o = fwd(maps[i], flat[sub], ind, P, P)
+        bwd(o, flat[sub], ind, maps[i].shape)          # includes the full memset of the dense grad map, as the reference does
+        t_roi += time.perf_counter() - t0
+        n_sample += len(sub)
+    torch.manual_seed(seed)
+    ot = pyref.OptTransRef(ch_x=FEAT, L=wl["sinkhorn_iters"])
+    n_cls = NCLS - 1
+    x = torch.rand(n_cls, FEAT, 1).requires_grad_()
+    y = torch.rand(n_cls, FEAT, 1)
+    t0 = time.perf_counter()
+    ot(x, y).sum().backward()
+    t_loss = time.perf_counter() - t0
+    t_full = t_roi * k + t_loss
+    return {"value": B * R / t_full, "unit": "RoIs/s", "cores": cores, "kind": kind,
+            "sample": "every RoIAlign call of the step on 1/%d of its boxes (%d of %d crops; fwd OpenMP x%d + bwd serial: %.2f s) "
+                      "+ the full %d-class OT loss fwd+bwd, L=%d (%.2f s); scaled to the full step (%.1f s)"
+                      % (k, n_sample, total_crops, cores, t_roi, n_cls, wl["sinkhorn_iters"], t_loss, t_full),
+            "roialign_s_full_step": t_roi * k, "loss_s": t_loss}
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    from feature_intertwiner_b200 import synth
+    wl = synth.WORKLOADS[args.workload]
+    vals = []
+    for s in range(args.warmup + args.steps):
+        r = cpu_reference(wl, seed=2000, budget_s=args.cpu_budget)
+        if s >= args.warmup:
+            vals.append(r)
+    v = sum(r["value"] for r in vals) / len(vals)
+    out = {
+        "impl": "reference",
+        "metric": "RoIs/sec (RoIAlign fwd+bwd + split + class means + Sinkhorn intertwiner loss, fwd+bwd)",
+        "value": v, "unit": "RoIs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * wl["batch"] * wl["rois_per_image"] / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s: batch %d/GPU, %dx%d, %d RoIs/img, FPN P2-P5 C=256, pools 7+14, Sinkhorn N=256 L=%d, class-level OT loss"
+                               % (args.workload, wl["batch"], wl["image"][0], wl["image"][1], wl["rois_per_image"], wl["sinkhorn_iters"])},
+        "cpu_baseline": dict(vals[-1], value=v),
+        "e2e": {"value": v, "unit": "RoIs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work per reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps > 3:
+            args.steps, args.warmup = min(args.steps, 3), min(args.warmup, 1)     # each step is ~cpu_budget seconds of CPU work
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

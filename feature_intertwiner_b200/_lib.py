@@ -21,6 +21,7 @@ SIGNATURES = {
     "fi_abi_version": (_I, []),
     "fi_last_error": (C.c_char_p, []),
     "fi_last_status": (_I, []),
+    "fi_kernel_launches": (C.c_ulonglong, []),
     "CropAndResizeLaucher": (None, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P]),
     "CropAndResizeBackpropImageLaucher": (None, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "ROIPoolForwardLaucher": (_I, [_P, _F, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
@@ -78,6 +79,12 @@ def ptr(t):
     if not t.is_cuda:
         raise FiError("libfi_b200 kernels need CUDA tensors; got a %s tensor (there is no CPU fallback)" % t.device)
     return t.data_ptr()
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise FiError("libfi_b200 kernels need CUDA tensors; got a %s tensor (there is no CPU fallback)" % t.device)
 
 
 FI_LAYOUT_NCHW = 0

@@ -17,6 +17,9 @@ void set_error(int status, const char *fmt, ...) {
     va_end(ap);
 }
 
+static unsigned long long g_launches = 0;   // relaxed counter; exactness under concurrent callers is not required
+void count_launch() { __atomic_fetch_add(&g_launches, 1ULL, __ATOMIC_RELAXED); }
+
 int ok() {
     g_status = FI_OK;
     g_message[0] = 0;
@@ -28,3 +31,4 @@ int ok() {
 FI_API int fi_abi_version(void) { return 1; }
 FI_API const char *fi_last_error(void) { return fi::g_message; }
 FI_API int fi_last_status(void) { return fi::g_status; }
+FI_API unsigned long long fi_kernel_launches(void) { return __atomic_load_n(&fi::g_launches, __ATOMIC_RELAXED); }

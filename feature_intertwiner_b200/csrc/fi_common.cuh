@@ -14,6 +14,7 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multi
 
 void set_error(int status, const char *fmt, ...);
 int ok();
+void count_launch();   // bumps the process-wide kernel-launch counter behind fi_kernel_launches()
 
 // Checks the launch that was just enqueued (no sync).
 inline int check_launch(const char *what) {
@@ -22,6 +23,7 @@ inline int check_launch(const char *what) {
         set_error(FI_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
         return FI_ERR_CUDA;
     }
+    count_launch();
     return ok();
 }
 

@@ -33,152 +33,273 @@ __global__ void crop_taps_kernel(const float *__restrict__ boxes, int R, int H, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// NHWC forward.  `lanes` threads cooperate on one sample, each moving VEC floats per channel step;
-// a block works on blockDim.x/lanes samples at a time.  Per float4 of output: 4 coalesced 128-bit
-// read-only loads (L1/L2 absorb the tap overlap between neighbouring samples and boxes) and one
-// streaming 128-bit store.  No shared memory: there is nothing to transpose in this layout.
+// NHWC kernels: one WARP per crop row (box r, row i).
+//
+// A thread-per-output-vector mapping re-derives the sample coordinates (two IEEE divisions, floor/ceil,
+// index div/mod) in every thread and is issue-bound at ~1/4 of HBM speed (measured, profiles/r01).  Here
+// the y tap is computed once per row, lane j computes the x tap of sample j, and the row is walked with
+// the taps handed around by warp shuffle: per sample a lane only forms 4 addresses, moves VPL float4 per
+// tap and does the lerps.  Loads are coalesced 512 B per tap row (C=256: two float4 per lane).
+//
+// Column reuse: consecutive samples of an up-sampling crop (step < 1 px -- every 14x14 crop of a box
+// assigned to its own level) share pixel columns; the (top,bottom) values of the current left/right
+// columns stay in registers and only columns that actually change are loaded.
 // ------------------------------------------------------------------------------------------------
-template <int VEC>
-__global__ void __launch_bounds__(256) crop_fwd_nhwc_kernel(const float *__restrict__ image, const float *__restrict__ boxes,
-                                                           const int *__restrict__ box_ind, const int *__restrict__ dst_row,
-                                                           long nsamples, int B, int H, int W, int ph, int pw, int C, int lanes,
-                                                           float extrap, float *__restrict__ crops) {
-    const int spb = blockDim.x / lanes;           // samples in flight per block
-    const int ls = threadIdx.x / lanes;
-    const int lc = threadIdx.x - ls * lanes;
-    if (ls >= spb) return;
-    const int pp = ph * pw;
-    const int CV = C / VEC;
-    for (long s = (long)blockIdx.x * spb + ls; s < nsamples; s += (long)gridDim.x * spb) {
-        const int r = (int)(s / pp);
-        const int rem = (int)(s - (long)r * pp);
-        const int i = rem / pw, j = rem - i * pw;
+constexpr int kWarpsPerBlock = 8;
+
+__device__ __forceinline__ AxisTap shfl_tap(const AxisTap &t, int src) {
+    AxisTap o;
+    o.lo = __shfl_sync(0xffffffffu, t.lo, src);
+    o.hi = __shfl_sync(0xffffffffu, t.hi, src);
+    o.frac = __shfl_sync(0xffffffffu, t.frac, src);
+    o.inside = __shfl_sync(0xffffffffu, (int)t.inside, src) != 0;
+    return o;
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) crop_fwd_nhwc_kernel(const float *__restrict__ image, const float *__restrict__ boxes,
+                                                                           const int *__restrict__ box_ind, const int *__restrict__ dst_row,
+                                                                           long nunits, int B, int H, int W, int ph, int pw, int C, float extrap,
+                                                                           float *__restrict__ crops) {
+    const int lane = threadIdx.x & 31;
+    const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    const int C4 = C >> 2;
+    for (long u = warp; u < nunits; u += nwarps) {
+        const int r = (int)(u / ph), i = (int)(u - (long)r * ph);
         const int b = box_ind[r];
         const long orow = dst_row ? (long)dst_row[r] : (long)r;
-        float *out = crops + (orow * pp + rem) * (long)C;
-        if (b < 0 || b >= B) {   // reference leaves such rows at their zero fill (crop_and_resize_kernel.cu:34-38)
-            for (int cv = lc; cv < CV; cv += lanes) {
-                if (VEC == 4) st_stream4(out + cv * 4, make_float4(0.f, 0.f, 0.f, 0.f));
-                else out[cv] = 0.f;
-            }
-            continue;
-        }
+        float *out = crops + ((orow * ph + i) * (long)pw) * C;
+        const bool bad = (b < 0 || b >= B);     // reference leaves such rows at their zero fill (crop_and_resize_kernel.cu:34-38)
         const float y1 = boxes[4 * r + 0], x1 = boxes[4 * r + 1], y2 = boxes[4 * r + 2], x2 = boxes[4 * r + 3];
         const AxisTap ty = axis_sample(y1, y2, axis_step(y1, y2, H, ph), i, H, ph);
-        const AxisTap tx = axis_sample(x1, x2, axis_step(x1, x2, W, pw), j, W, pw);
-        if (!(ty.inside && tx.inside)) {
-            for (int cv = lc; cv < CV; cv += lanes) {
-                if (VEC == 4) st_stream4(out + cv * 4, make_float4(extrap, extrap, extrap, extrap));
-                else out[cv] = extrap;
-            }
+        if (bad || !ty.inside) {
+            const float v = bad ? 0.f : extrap;
+            const float4 v4 = make_float4(v, v, v, v);
+            for (int e = lane; e < pw * C4; e += 32) st_stream4(out + e * 4, v4);
             continue;
         }
-        const float *img = image + (long)b * H * W * C;
-        const float *ptl = img + ((long)ty.lo * W + tx.lo) * C;
-        const float *ptr = img + ((long)ty.lo * W + tx.hi) * C;
-        const float *pbl = img + ((long)ty.hi * W + tx.lo) * C;
-        const float *pbr = img + ((long)ty.hi * W + tx.hi) * C;
-        for (int cv = lc; cv < CV; cv += lanes) {
-            if (VEC == 4) {
-                const float4 tl = ldg4(ptl + cv * 4), tr = ldg4(ptr + cv * 4);
-                const float4 bl = ldg4(pbl + cv * 4), br = ldg4(pbr + cv * 4);
-                const float4 top = lerp_rn(tl, tr, tx.frac);
-                const float4 bot = lerp_rn(bl, br, tx.frac);
-                st_stream4(out + cv * 4, lerp_rn(top, bot, ty.frac));
-            } else {
-                const float top = lerp_rn(__ldg(ptl + cv), __ldg(ptr + cv), tx.frac);
-                const float bot = lerp_rn(__ldg(pbl + cv), __ldg(pbr + cv), tx.frac);
-                out[cv] = lerp_rn(top, bot, ty.frac);
+        const float sx = axis_step(x1, x2, W, pw);
+        const float *rowT = image + ((long)b * H + ty.lo) * (long)W * C;
+        const float *rowB = image + ((long)b * H + ty.hi) * (long)W * C;
+        const bool one_row = ty.hi == ty.lo;
+        for (int cv0 = 0; cv0 < C4; cv0 += 32 * VPL) {
+            float4 Lt[VPL], Lb[VPL], Rt[VPL], Rb[VPL];
+            int cur_lo = -1, cur_hi = -1;
+            AxisTap mine;
+            for (int j = 0; j < pw; ++j) {
+                if ((j & 31) == 0) mine = axis_sample(x1, x2, sx, j + lane, W, pw);     // lane l holds the x tap of sample j + l
+                const AxisTap tx = shfl_tap(mine, j & 31);
+                float *o = out + (long)j * C;
+                if (!tx.inside) {
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v) {
+                        const int cv = cv0 + v * 32 + lane;
+                        if (cv < C4) st_stream4(o + cv * 4, make_float4(extrap, extrap, extrap, extrap));
+                    }
+                    continue;
+                }
+                if (!(tx.lo == cur_lo && tx.hi == cur_hi)) {
+                    const bool slide = (tx.lo == cur_hi);
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v) {
+                        const int cv = cv0 + v * 32 + lane;
+                        if (cv >= C4) continue;
+                        if (slide) { Lt[v] = Rt[v]; Lb[v] = Rb[v]; }
+                        else {
+                            Lt[v] = ldg4(rowT + (long)tx.lo * C + cv * 4);
+                            Lb[v] = one_row ? Lt[v] : ldg4(rowB + (long)tx.lo * C + cv * 4);
+                        }
+                        if (tx.hi == tx.lo) { Rt[v] = Lt[v]; Rb[v] = Lb[v]; }
+                        else {
+                            Rt[v] = ldg4(rowT + (long)tx.hi * C + cv * 4);
+                            Rb[v] = one_row ? Rt[v] : ldg4(rowB + (long)tx.hi * C + cv * 4);
+                        }
+                    }
+                    cur_lo = tx.lo; cur_hi = tx.hi;
+                }
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) {
+                    const int cv = cv0 + v * 32 + lane;
+                    if (cv >= C4) continue;
+                    const float4 top = lerp_rn(Lt[v], Rt[v], tx.frac);       // crop_and_resize.c:102
+                    const float4 bot = lerp_rn(Lb[v], Rb[v], tx.frac);       // :103-104
+                    st_stream4(o + cv * 4, lerp_rn(top, bot, ty.frac));      // :106
+                }
+            }
+        }
+    }
+}
+
+// Scalar-channel variant for C % 4 != 0 or unaligned pointers (same structure, one float per lane).
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) crop_fwd_nhwc_scalar_kernel(const float *__restrict__ image, const float *__restrict__ boxes,
+                                                                                  const int *__restrict__ box_ind, const int *__restrict__ dst_row,
+                                                                                  long nunits, int B, int H, int W, int ph, int pw, int C, float extrap,
+                                                                                  float *__restrict__ crops) {
+    const int lane = threadIdx.x & 31;
+    const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    for (long u = warp; u < nunits; u += nwarps) {
+        const int r = (int)(u / ph), i = (int)(u - (long)r * ph);
+        const int b = box_ind[r];
+        const long orow = dst_row ? (long)dst_row[r] : (long)r;
+        float *out = crops + ((orow * ph + i) * (long)pw) * C;
+        const bool bad = (b < 0 || b >= B);
+        const float y1 = boxes[4 * r + 0], x1 = boxes[4 * r + 1], y2 = boxes[4 * r + 2], x2 = boxes[4 * r + 3];
+        const AxisTap ty = axis_sample(y1, y2, axis_step(y1, y2, H, ph), i, H, ph);
+        if (bad || !ty.inside) {
+            const float v = bad ? 0.f : extrap;
+            for (int e = lane; e < pw * C; e += 32) out[e] = v;
+            continue;
+        }
+        const float sx = axis_step(x1, x2, W, pw);
+        const float *rowT = image + ((long)b * H + ty.lo) * (long)W * C;
+        const float *rowB = image + ((long)b * H + ty.hi) * (long)W * C;
+        AxisTap mine;
+        for (int j = 0; j < pw; ++j) {
+            if ((j & 31) == 0) mine = axis_sample(x1, x2, sx, j + lane, W, pw);
+            const AxisTap tx = shfl_tap(mine, j & 31);
+            float *o = out + (long)j * C;
+            for (int c = lane; c < C; c += 32) {
+                float v = extrap;
+                if (tx.inside) {
+                    const float top = lerp_rn(__ldg(rowT + (long)tx.lo * C + c), __ldg(rowT + (long)tx.hi * C + c), tx.frac);
+                    const float bot = lerp_rn(__ldg(rowB + (long)tx.lo * C + c), __ldg(rowB + (long)tx.hi * C + c), tx.frac);
+                    v = lerp_rn(top, bot, ty.frac);
+                }
+                o[c] = v;
             }
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// NHWC backward (scatter form).  One thread owns VEC channels of one crop ROW (i fixed) and walks the
-// row's samples j = 0..pw-1 in order, keeping the contributions to the current (x_lo, x_hi) pixel pair
-// of the top and of the bottom image row in registers.  They are flushed with vector reductions
-// (red.global.add.v4.f32, coalesced across the C-lanes of the pixel) only when the pixel pair changes.
-// Upsampling crops (step < 1 px: every small box pooled at 14x14) and degenerate / zero-padded RoIs (step 0:
-// all samples on one pixel, which in the reference serialise hundreds of atomics on one address) thus
-// issue one reduction per DISTINCT pixel instead of one per tap.
+// NHWC backward, scatter form.  Same warp-per-crop-row walk.  The contributions to the current
+// (x_lo, x_hi) pixel pair of the top and of the bottom image row are kept in registers and flushed with
+// 128-bit vector reductions (red.global.add.v4.f32, coalesced across the channel lanes) only when the pair
+// changes: up-sampling crops and degenerate / zero-padded RoIs (all samples on one pixel -- in the
+// reference hundreds of serialised atomics on one address) issue one reduction per DISTINCT pixel.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void red_add(float *p, float4 v) {
-    // sm_90+ 128-bit vector reduction; result unused -> RED, not ATOM
-    atomicAdd(reinterpret_cast<float4 *>(p), v);
+    atomicAdd(reinterpret_cast<float4 *>(p), v);     // sm_90+: REDG.E.ADD.F32x4 (result unused)
 }
-__device__ __forceinline__ void red_add(float *p, float v) { atomicAdd(p, v); }
-
 __device__ __forceinline__ float4 f4_scale(float4 a, float w) {
     return make_float4(__fmul_rn(a.x, w), __fmul_rn(a.y, w), __fmul_rn(a.z, w), __fmul_rn(a.w, w));
 }
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
-__device__ __forceinline__ float f4_scale(float a, float w) { return __fmul_rn(a, w); }
-__device__ __forceinline__ float f4_add(float a, float b) { return a + b; }
-template <typename T> __device__ __forceinline__ T vzero();
-template <> __device__ __forceinline__ float4 vzero<float4>() { return make_float4(0.f, 0.f, 0.f, 0.f); }
-template <> __device__ __forceinline__ float vzero<float>() { return 0.f; }
-__device__ __forceinline__ float4 ld_stream(const float4 *p) { return __ldcs(p); }
-__device__ __forceinline__ float ld_stream(const float *p) { return __ldcs(p); }
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
-template <typename VT>
-__global__ void __launch_bounds__(256) crop_bwd_nhwc_kernel(const float *__restrict__ grads, const float *__restrict__ boxes,
-                                                           const int *__restrict__ box_ind, const int *__restrict__ src_row,
-                                                           long nrows, int B, int H, int W, int ph, int pw, int C, int lanes,
-                                                           float *__restrict__ gimg) {
-    constexpr int VEC = sizeof(VT) / sizeof(float);
-    const int rpb = blockDim.x / lanes;           // crop rows in flight per block
-    const int lr = threadIdx.x / lanes;
-    const int lc = threadIdx.x - lr * lanes;
-    if (lr >= rpb) return;
-    const int CV = C / VEC;
-    for (long q = (long)blockIdx.x * rpb + lr; q < nrows; q += (long)gridDim.x * rpb) {
-        const int r = (int)(q / ph);
-        const int i = (int)(q - (long)r * ph);
+template <int VPL>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) crop_bwd_nhwc_kernel(const float *__restrict__ grads, const float *__restrict__ boxes,
+                                                                           const int *__restrict__ box_ind, const int *__restrict__ src_row,
+                                                                           long nunits, int B, int H, int W, int ph, int pw, int C,
+                                                                           float *__restrict__ gimg) {
+    const int lane = threadIdx.x & 31;
+    const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    const int C4 = C >> 2;
+    for (long u = warp; u < nunits; u += nwarps) {
+        const int r = (int)(u / ph), i = (int)(u - (long)r * ph);
         const int b = box_ind[r];
         if (b < 0 || b >= B) continue;
         const float y1 = boxes[4 * r + 0], x1 = boxes[4 * r + 1], y2 = boxes[4 * r + 2], x2 = boxes[4 * r + 3];
         const AxisTap ty = axis_sample(y1, y2, axis_step(y1, y2, H, ph), i, H, ph);
         if (!ty.inside) continue;
         const float sx = axis_step(x1, x2, W, pw);
-        const float wy_hi = ty.frac, wy_lo = __fsub_rn(1.f, ty.frac);     // crop_and_resize.c:241,245
+        const float wy_hi = ty.frac, wy_lo = __fsub_rn(1.f, ty.frac);            // crop_and_resize.c:241,245
         const long grow = src_row ? (long)src_row[r] : (long)r;
         const float *g = grads + ((grow * ph + i) * (long)pw) * C;
-        float *img_top = gimg + ((long)b * H + ty.lo) * (long)W * C;
-        float *img_bot = gimg + ((long)b * H + ty.hi) * (long)W * C;
-        for (int cv = lc; cv < CV; cv += lanes) {
-            VT t_lo = vzero<VT>(), t_hi = vzero<VT>(), b_lo = vzero<VT>(), b_hi = vzero<VT>();
+        float *rowT = gimg + ((long)b * H + ty.lo) * (long)W * C;
+        float *rowB = gimg + ((long)b * H + ty.hi) * (long)W * C;
+        for (int cv0 = 0; cv0 < C4; cv0 += 32 * VPL) {
+            float4 Lt[VPL], Lb[VPL], Rt[VPL], Rb[VPL];
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) { Lt[v] = f4_zero(); Lb[v] = f4_zero(); Rt[v] = f4_zero(); Rb[v] = f4_zero(); }
             int cur_lo = -1, cur_hi = -1;
+            AxisTap mine;
             for (int j = 0; j < pw; ++j) {
-                const AxisTap tx = axis_sample(x1, x2, sx, j, W, pw);
+                if ((j & 31) == 0) mine = axis_sample(x1, x2, sx, j + lane, W, pw);
+                const AxisTap tx = shfl_tap(mine, j & 31);
                 if (!tx.inside) continue;
-                if (tx.lo != cur_lo || tx.hi != cur_hi) {
+                if (!(tx.lo == cur_lo && tx.hi == cur_hi)) {
                     if (cur_lo >= 0) {
-                        red_add(img_top + (long)cur_lo * C + cv * VEC, t_lo);
-                        red_add(img_bot + (long)cur_lo * C + cv * VEC, b_lo);
-                        if (tx.lo == cur_hi && tx.hi != cur_hi) {
-                            // window slides by one pixel: the old `hi` column becomes the new `lo`
-                            t_lo = t_hi; b_lo = b_hi;
-                        } else {
-                            red_add(img_top + (long)cur_hi * C + cv * VEC, t_hi);
-                            red_add(img_bot + (long)cur_hi * C + cv * VEC, b_hi);
-                            t_lo = vzero<VT>(); b_lo = vzero<VT>();
+                        const bool slide = (tx.lo == cur_hi) && (tx.hi != cur_hi);
+#pragma unroll
+                        for (int v = 0; v < VPL; ++v) {
+                            const int cv = cv0 + v * 32 + lane;
+                            if (cv >= C4) continue;
+                            red_add(rowT + (long)cur_lo * C + cv * 4, Lt[v]);
+                            red_add(rowB + (long)cur_lo * C + cv * 4, Lb[v]);
+                            if (slide) { Lt[v] = Rt[v]; Lb[v] = Rb[v]; }     // old right column becomes the new left one
+                            else {
+                                red_add(rowT + (long)cur_hi * C + cv * 4, Rt[v]);
+                                red_add(rowB + (long)cur_hi * C + cv * 4, Rb[v]);
+                                Lt[v] = f4_zero(); Lb[v] = f4_zero();
+                            }
+                            Rt[v] = f4_zero(); Rb[v] = f4_zero();
                         }
-                        t_hi = vzero<VT>(); b_hi = vzero<VT>();
                     }
                     cur_lo = tx.lo; cur_hi = tx.hi;
                 }
-                const VT gv = ld_stream(reinterpret_cast<const VT *>(g + (long)j * C) + cv);
-                const VT dtop = f4_scale(gv, wy_lo), dbot = f4_scale(gv, wy_hi);
                 const float wx_hi = tx.frac, wx_lo = __fsub_rn(1.f, tx.frac);
-                t_lo = f4_add(t_lo, f4_scale(dtop, wx_lo)); t_hi = f4_add(t_hi, f4_scale(dtop, wx_hi));
-                b_lo = f4_add(b_lo, f4_scale(dbot, wx_lo)); b_hi = f4_add(b_hi, f4_scale(dbot, wx_hi));
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) {
+                    const int cv = cv0 + v * 32 + lane;
+                    if (cv >= C4) continue;
+                    const float4 gv = __ldcs(reinterpret_cast<const float4 *>(g + (long)j * C) + cv);
+                    const float4 dtop = f4_scale(gv, wy_lo), dbot = f4_scale(gv, wy_hi);
+                    Lt[v] = f4_add(Lt[v], f4_scale(dtop, wx_lo)); Rt[v] = f4_add(Rt[v], f4_scale(dtop, wx_hi));
+                    Lb[v] = f4_add(Lb[v], f4_scale(dbot, wx_lo)); Rb[v] = f4_add(Rb[v], f4_scale(dbot, wx_hi));
+                }
             }
             if (cur_lo >= 0) {
-                red_add(img_top + (long)cur_lo * C + cv * VEC, t_lo);
-                red_add(img_bot + (long)cur_lo * C + cv * VEC, b_lo);
-                red_add(img_top + (long)cur_hi * C + cv * VEC, t_hi);
-                red_add(img_bot + (long)cur_hi * C + cv * VEC, b_hi);
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) {
+                    const int cv = cv0 + v * 32 + lane;
+                    if (cv >= C4) continue;
+                    red_add(rowT + (long)cur_lo * C + cv * 4, Lt[v]);
+                    red_add(rowB + (long)cur_lo * C + cv * 4, Lb[v]);
+                    red_add(rowT + (long)cur_hi * C + cv * 4, Rt[v]);
+                    red_add(rowB + (long)cur_hi * C + cv * 4, Rb[v]);
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) crop_bwd_nhwc_scalar_kernel(const float *__restrict__ grads, const float *__restrict__ boxes,
+                                                                                  const int *__restrict__ box_ind, const int *__restrict__ src_row,
+                                                                                  long nunits, int B, int H, int W, int ph, int pw, int C,
+                                                                                  float *__restrict__ gimg) {
+    const int lane = threadIdx.x & 31;
+    const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    for (long u = warp; u < nunits; u += nwarps) {
+        const int r = (int)(u / ph), i = (int)(u - (long)r * ph);
+        const int b = box_ind[r];
+        if (b < 0 || b >= B) continue;
+        const float y1 = boxes[4 * r + 0], x1 = boxes[4 * r + 1], y2 = boxes[4 * r + 2], x2 = boxes[4 * r + 3];
+        const AxisTap ty = axis_sample(y1, y2, axis_step(y1, y2, H, ph), i, H, ph);
+        if (!ty.inside) continue;
+        const float sx = axis_step(x1, x2, W, pw);
+        const float wy_hi = ty.frac, wy_lo = __fsub_rn(1.f, ty.frac);
+        const long grow = src_row ? (long)src_row[r] : (long)r;
+        const float *g = grads + ((grow * ph + i) * (long)pw) * C;
+        float *rowT = gimg + ((long)b * H + ty.lo) * (long)W * C;
+        float *rowB = gimg + ((long)b * H + ty.hi) * (long)W * C;
+        AxisTap mine;
+        for (int j = 0; j < pw; ++j) {
+            if ((j & 31) == 0) mine = axis_sample(x1, x2, sx, j + lane, W, pw);
+            const AxisTap tx = shfl_tap(mine, j & 31);
+            if (!tx.inside) continue;
+            const float wx_hi = tx.frac, wx_lo = __fsub_rn(1.f, tx.frac);
+            for (int c = lane; c < C; c += 32) {
+                const float gv = g[(long)j * C + c];
+                const float dtop = __fmul_rn(wy_lo, gv), dbot = __fmul_rn(wy_hi, gv);
+                atomicAdd(rowT + (long)tx.lo * C + c, __fmul_rn(wx_lo, dtop));
+                atomicAdd(rowT + (long)tx.hi * C + c, __fmul_rn(wx_hi, dtop));
+                atomicAdd(rowB + (long)tx.lo * C + c, __fmul_rn(wx_lo, dbot));
+                atomicAdd(rowB + (long)tx.hi * C + c, __fmul_rn(wx_hi, dbot));
             }
         }
     }
@@ -333,13 +454,6 @@ __global__ void crop_bwd_nchw_generic_kernel(const float *__restrict__ grads, co
     }
 }
 
-// lanes cooperating on one sample/row: the largest power of two <= min(CV, 256) that divides 256
-static int pick_lanes(int CV) {
-    int l = 1;
-    while (l * 2 <= CV && l * 2 <= 256) l *= 2;
-    return l;
-}
-
 static int grid_for(long work_items, int per_block, int blocks_per_sm) {
     long need = (work_items + per_block - 1) / per_block;
     long cap = (long)kNumSMs * blocks_per_sm;
@@ -377,17 +491,15 @@ FI_API int fi_crop_and_resize_forward(const float *image, int image_layout, cons
         return FI_ERR_UNSUPPORTED;
     }
     if (image_layout == FI_LAYOUT_NHWC) {
-        const long nsamples = (long)R * ph * pw;
+        const long nunits = (long)R * ph;            // one warp per crop row
         const bool vec = (C % 4 == 0) && ((uintptr_t)image % 16 == 0) && ((uintptr_t)crops % 16 == 0);
-        if (vec) {
-            const int lanes = pick_lanes(C / 4);
-            crop_fwd_nhwc_kernel<4><<<grid_for(nsamples, 256 / lanes, 8), 256, 0, stream>>>(
-                image, boxes, box_ind, dst_row, nsamples, B, H, W, ph, pw, C, lanes, extrap, crops);
-        } else {
-            const int lanes = pick_lanes(C);
-            crop_fwd_nhwc_kernel<1><<<grid_for(nsamples, 256 / lanes, 8), 256, 0, stream>>>(
-                image, boxes, box_ind, dst_row, nsamples, B, H, W, ph, pw, C, lanes, extrap, crops);
-        }
+        const int grid = grid_for(nunits, kWarpsPerBlock, 8);
+        if (vec && (C / 4) % 64 == 0)
+            crop_fwd_nhwc_kernel<2><<<grid, kWarpsPerBlock * 32, 0, stream>>>(image, boxes, box_ind, dst_row, nunits, B, H, W, ph, pw, C, extrap, crops);
+        else if (vec)
+            crop_fwd_nhwc_kernel<1><<<grid, kWarpsPerBlock * 32, 0, stream>>>(image, boxes, box_ind, dst_row, nunits, B, H, W, ph, pw, C, extrap, crops);
+        else
+            crop_fwd_nhwc_scalar_kernel<<<grid, kWarpsPerBlock * 32, 0, stream>>>(image, boxes, box_ind, dst_row, nunits, B, H, W, ph, pw, C, extrap, crops);
         return check_launch("fi_crop_and_resize_forward[nhwc]");
     }
     if (image_layout == FI_LAYOUT_NCHW) {
@@ -420,17 +532,15 @@ FI_API int fi_crop_and_resize_backward(const float *grads, int grads_layout, con
         return FI_ERR_UNSUPPORTED;
     }
     if (image_layout == FI_LAYOUT_NHWC) {
-        const long nrows = (long)R * ph;
+        const long nunits = (long)R * ph;
         const bool vec = (C % 4 == 0) && ((uintptr_t)gimg % 16 == 0) && ((uintptr_t)grads % 16 == 0);
-        if (vec) {
-            const int lanes = pick_lanes(C / 4);
-            crop_bwd_nhwc_kernel<float4><<<grid_for(nrows, 256 / lanes, 8), 256, 0, stream>>>(
-                grads, boxes, box_ind, src_row, nrows, B, H, W, ph, pw, C, lanes, gimg);
-        } else {
-            const int lanes = pick_lanes(C);
-            crop_bwd_nhwc_kernel<float><<<grid_for(nrows, 256 / lanes, 8), 256, 0, stream>>>(
-                grads, boxes, box_ind, src_row, nrows, B, H, W, ph, pw, C, lanes, gimg);
-        }
+        const int grid = grid_for(nunits, kWarpsPerBlock, 8);
+        if (vec && (C / 4) % 64 == 0)
+            crop_bwd_nhwc_kernel<2><<<grid, kWarpsPerBlock * 32, 0, stream>>>(grads, boxes, box_ind, src_row, nunits, B, H, W, ph, pw, C, gimg);
+        else if (vec)
+            crop_bwd_nhwc_kernel<1><<<grid, kWarpsPerBlock * 32, 0, stream>>>(grads, boxes, box_ind, src_row, nunits, B, H, W, ph, pw, C, gimg);
+        else
+            crop_bwd_nhwc_scalar_kernel<<<grid, kWarpsPerBlock * 32, 0, stream>>>(grads, boxes, box_ind, src_row, nunits, B, H, W, ph, pw, C, gimg);
         return check_launch("fi_crop_and_resize_backward[nhwc]");
     }
     if (image_layout == FI_LAYOUT_NCHW) {

@@ -30,6 +30,7 @@ EPS = 1e-20
 # ----------------------------------------------------------------------------------------------- level rule / split
 def roi_level(rois, image_shape, base=224.0):
     """rois[bs,R,4] normalised -> int32 [bs,R] pyramid level in 2..5 (lib/sub_module.py:397-410)."""
+    _lib.require_cuda(rois)
     flat = rois.detach().float().contiguous().view(-1, 4)
     level = torch.empty((flat.size(0),), device=flat.device, dtype=torch.int32)
     with torch.cuda.device(flat.device):
@@ -55,6 +56,7 @@ class LevelSplit(object):
 
 def split_levels(level):
     """level[...] int32 -> LevelSplit: small(l) = {level == l}, big(l) = {level > l} (lib/sub_module.py:442,367-378)."""
+    _lib.require_cuda(level)
     flat = level.contiguous().view(-1)
     n = flat.numel()
     dev = flat.device
@@ -73,7 +75,8 @@ def split_levels(level):
 class _SegmentMean(torch.autograd.Function):
     @staticmethod
     def forward(ctx, gt, feat, ncls):
-        feat2 = feat.reshape(feat.size(0), -1).float().contiguous()
+        _lib.require_cuda(feat, gt)
+        feat2 = feat.flatten(1).float().contiguous()
         gt = gt.detach().to(torch.int32).contiguous()
         k, Fd = feat2.shape
         mean = torch.empty((Fd, ncls), device=feat2.device, dtype=torch.float32)

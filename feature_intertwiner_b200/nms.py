@@ -21,6 +21,7 @@ def nms_batched(dets, thresh):
     -1, num_keep[bs] int32), no host synchronisation."""
     if dets.dim() != 3 or dets.size(2) != 5:
         raise _lib.FiError("dets must be [bs,N,5], got %s" % (tuple(dets.shape),))
+    _lib.require_cuda(dets)
     bs, n, _ = dets.shape
     dets = dets.detach().float()
     order = torch.sort(dets[:, :, 4], dim=1, descending=True, stable=True)[1]            # pth_nms.py:37

@@ -16,6 +16,7 @@ class _Sinkhorn(torch.autograd.Function):
     def forward(ctx, x, y, inv_eps, L):
         if x.shape != y.shape or x.dim() != 3:
             raise _lib.FiError("sinkhorn: x and y must both be [P,N,D]; got %s / %s" % (tuple(x.shape), tuple(y.shape)))
+        _lib.require_cuda(x, y)
         x = x.detach().float().contiguous()
         y = y.detach().float().contiguous()
         P, N, D = x.shape

@@ -16,6 +16,66 @@ from torch import nn
 from . import _lib
 
 
+# ---- optional per-launch timing (bench.py): CUDA events on the launching stream + what is needed to count the
+# launch's algorithmic bytes afterwards.  Off by default; nothing is recorded and no event is created then.
+_PROFILE = None
+
+
+def enable_profiling():
+    global _PROFILE
+    _PROFILE = []
+    return _PROFILE
+
+
+def disable_profiling():
+    global _PROFILE
+    rec, _PROFILE = _PROFILE, None
+    return rec or []
+
+
+class _Timed(object):
+    def __init__(self, kernel, **meta):
+        self.rec = None
+        if _PROFILE is not None:
+            self.rec = dict(kernel=kernel, start=torch.cuda.Event(enable_timing=True), end=torch.cuda.Event(enable_timing=True), **meta)
+
+    def __enter__(self):
+        if self.rec is not None:
+            self.rec["start"].record()
+
+    def __exit__(self, *exc):
+        if self.rec is not None:
+            self.rec["end"].record()
+            _PROFILE.append(self.rec)
+
+
+_UNIQUE_CACHE = {}
+
+
+def algorithmic_bytes(rec):
+    """Algorithmic bytes of one recorded launch:
+    forward  = 4*C*R*P^2 (write crops) + 4*C*U (each touched feature pixel read once) + 20*R (boxes, box_ind)
+    backward = 4*C*R*P^2 (read grads)  + 4*C*B*H*W (dense grad map written once)      + 20*R
+    U = distinct (b,y,x) tap pixels, counted on the device from the kernel's own tap table."""
+    B, Cc, H, W = rec["im_size"]
+    ph, pw = rec["crop"]
+    R = rec["boxes"].size(0)
+    base = 4 * Cc * R * ph * pw + 20 * R
+    if rec["kernel"].startswith("crop_bwd"):
+        return base + 4 * Cc * B * H * W
+    key = (rec["boxes"].data_ptr(), R, H, W, ph, pw)
+    if key not in _UNIQUE_CACHE:
+        taps = crop_taps(rec["boxes"], H, W, ph, pw).view(R, -1, 5).long()
+        b = rec["box_ind"].long().view(R, 1).expand(R, taps.size(1))
+        ok = (taps[:, :, 4] == 1) & (b >= 0) & (b < B)
+        seen = torch.zeros(B * H * W, dtype=torch.bool, device=taps.device)
+        for yy, xx in ((0, 2), (0, 3), (1, 2), (1, 3)):
+            lin = (b * H + taps[:, :, yy]) * W + taps[:, :, xx]
+            seen[lin[ok]] = True
+        _UNIQUE_CACHE[key] = int(seen.sum().item())
+    return base + 4 * Cc * _UNIQUE_CACHE[key]
+
+
 def _mem_format(layout):
     return torch.channels_last if layout == _lib.FI_LAYOUT_NHWC else torch.contiguous_format
 
@@ -33,6 +93,7 @@ def _prep_boxes(boxes, box_ind, device):
 class _CropAndResize(torch.autograd.Function):
     @staticmethod
     def forward(ctx, image, boxes, box_ind, crop_h, crop_w, extrap, out, dst_row):
+        _lib.require_cuda(image)
         if image.dtype != torch.float32:
             raise _lib.FiError("crop_and_resize computes in fp32 like the reference; got %s" % image.dtype)
         layout, image = _lib.layout_of(image)
@@ -54,7 +115,8 @@ class _CropAndResize(torch.autograd.Function):
         ctx.has_out = out is not None
         if dst_row is not None:
             dst_row = dst_row.to(device=image.device, dtype=torch.int32).contiguous()
-        with torch.cuda.device(image.device):
+        tag = "crop_fwd_nhwc" if layout == _lib.FI_LAYOUT_NHWC else "crop_fwd_nchw"
+        with torch.cuda.device(image.device), _Timed(tag, im_size=(B, Cc, H, W), crop=(crop_h, crop_w), boxes=boxes, box_ind=box_ind):
             _lib.check(_lib.lib().fi_crop_and_resize_forward(
                 _lib.ptr(image), layout, _lib.ptr(boxes), _lib.ptr(box_ind), _lib.ptr(dst_row), R, B, H, W,
                 crop_h, crop_w, Cc, float(extrap), _lib.ptr(crops), layout, _lib.stream_ptr(image.device)))
@@ -73,7 +135,8 @@ class _CropAndResize(torch.autograd.Function):
         layout = ctx.layout
         grad_out = grad_out.contiguous(memory_format=_mem_format(layout))
         grad_image = torch.empty(ctx.im_size, device=grad_out.device, dtype=torch.float32, memory_format=_mem_format(layout))
-        with torch.cuda.device(grad_out.device):
+        tag = "crop_bwd_nhwc" if layout == _lib.FI_LAYOUT_NHWC else "crop_bwd_nchw"
+        with torch.cuda.device(grad_out.device), _Timed(tag, im_size=ctx.im_size, crop=ctx.crop, boxes=boxes, box_ind=box_ind):
             _lib.check(_lib.lib().fi_crop_and_resize_backward(
                 _lib.ptr(grad_out), layout, _lib.ptr(boxes), _lib.ptr(box_ind), _lib.ptr(rows), boxes.size(0), B, H, W,
                 ctx.crop[0], ctx.crop[1], Cc, _lib.ptr(grad_image), layout, 0, _lib.stream_ptr(grad_out.device)))
@@ -129,6 +192,7 @@ class RoIAlign(nn.Module):
 
 def crop_taps(boxes, image_height, image_width, crop_h, crop_w):
     """Integer bilinear taps [R,crop_h,crop_w,5] = (y_lo,y_hi,x_lo,x_hi,inside) computed on the device."""
+    _lib.require_cuda(boxes)
     boxes = boxes.detach().to(dtype=torch.float32).contiguous()
     taps = torch.empty((boxes.size(0), crop_h, crop_w, 5), device=boxes.device, dtype=torch.int32)
     with torch.cuda.device(boxes.device):

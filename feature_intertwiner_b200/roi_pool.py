@@ -8,6 +8,7 @@ from . import _lib
 class _RoIPool(torch.autograd.Function):
     @staticmethod
     def forward(ctx, features, rois, ph, pw, scale):
+        _lib.require_cuda(features, rois)
         features = features.contiguous()          # NCHW only: flat argmax indices are NCHW offsets (roi_pooling_kernel.cu:78-91)
         rois = rois.detach().float().contiguous()
         if rois.dim() != 2 or rois.size(1) != 5:

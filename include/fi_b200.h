@@ -34,6 +34,7 @@ typedef struct CUstream_st *cudaStream_t;
 int fi_abi_version(void);
 const char *fi_last_error(void); /* thread-local, never NULL */
 int fi_last_status(void);        /* status of the last call made by this thread */
+unsigned long long fi_kernel_launches(void); /* kernels this library has launched in this process */
 
 /* ---------------------------------------------------------------------------------------------
  * 1. Reference-named launchers (exact signatures).

@@ -88,7 +88,7 @@ def big_mask_ref(level, roi_level):
 
 def assign_feat2cls_ref(gt, feat, ncls):
     """lib/sub_module.py:664-684.  gt[k] ints, feat[k,F(,1,1)] -> feat[F,ncls], cnt[1,ncls]."""
-    feat = feat.reshape(feat.shape[0], -1)
+    feat = feat.flatten(1)
     out = torch.zeros(feat.shape[1], ncls)
     cnt = torch.zeros(1, ncls)
     cols = []

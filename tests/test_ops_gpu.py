@@ -1,0 +1,322 @@
+"""Sinkhorn / OptTrans / level rule / split / segment mean / buffer / NMS / RoIPool: CUDA path (through the
+C ABI) vs the oracle and the golden vectors generated from the reference itself."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import clib, pyref
+
+pytestmark = pytest.mark.gpu
+
+LOSS_TOL = 1e-4   # north_star: "loss within 1e-4 fp32 of the reference"
+
+
+def _fi():
+    import feature_intertwiner_b200 as fi
+    return fi
+
+
+# ------------------------------------------------------------------------------------------------ Sinkhorn
+def test_sinkhorn_golden(golden_dir):
+    """Values produced by the reference's own OptTrans._sinkhorn_iterate (lib/OT_module.py:104-135)."""
+    fi = _fi()
+    z = np.load(golden_dir + "/sinkhorn.npz")
+    for name in ("n256_d1", "n64_d256", "n16_d3"):
+        x = torch.from_numpy(z[name + "_x"]).cuda()[None]
+        y = torch.from_numpy(z[name + "_y"]).cuda()[None]
+        for L in (1, 5, 50):
+            for eps in (1.0, 0.1):
+                got = fi.sinkhorn_loss(x, y, epsilon=eps, L=L).item()
+                want = float(z[f"{name}_L{L}_eps{eps}"])
+                assert abs(got - want) < LOSS_TOL, (name, L, eps, got, want)
+
+
+@pytest.mark.parametrize("N,D", [(256, 1), (256, 5), (64, 256), (64, 1024), (100, 7), (224, 2), (1, 1), (33, 40)])
+def test_sinkhorn_vs_oracle_values_and_grads(N, D):
+    fi = _fi()
+    g = torch.Generator().manual_seed(N * 1000 + D)
+    P = 5
+    x = torch.randn(P, N, D, generator=g).abs()
+    y = torch.randn(P, N, D, generator=g).abs()
+    if N > 8:
+        x[:, ::9] = 0
+    xc, yc = x.cuda().requires_grad_(), y.cuda().requires_grad_()
+    loss = fi.sinkhorn_loss(xc, yc, epsilon=0.5, L=20)
+    w = torch.arange(1, P + 1, dtype=torch.float32).cuda()
+    (loss * w).sum().backward()
+    for p in range(P):
+        want, _, gx, gy = clib.oracle_sinkhorn(x[p].numpy(), y[p].numpy(), inv_eps=2.0, L=20, wide=True, want_grad=True)
+        assert abs(loss[p].item() - want) < 2e-5, (p, loss[p].item(), want)
+        rows = (x[p].norm(dim=1) > 0).numpy()      # d/dx of x/(|x|+1e-20) at x == 0 is 1e20: compare the well-posed rows
+        np.testing.assert_allclose(xc.grad[p].cpu().numpy()[rows] / w[p].item(), gx[rows], rtol=2e-3, atol=2e-6)
+        np.testing.assert_allclose(yc.grad[p].cpu().numpy() / w[p].item(), gy, rtol=2e-3, atol=2e-6)
+
+
+def test_sinkhorn_properties_full_size():
+    """Size-independent properties at BASELINE sizes: x == y => debiased loss 0; batch order invariance."""
+    fi = _fi()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(240, 256, 1, generator=g).abs().cuda()
+    y = torch.randn(240, 256, 1, generator=g).abs().cuda()
+    wxy = fi.sinkhorn_loss(x, y, 1.0, 50)
+    wxx = fi.sinkhorn_loss(x, x, 1.0, 50)
+    wyx = fi.sinkhorn_loss(y, x, 1.0, 50)
+    assert torch.all(torch.isfinite(wxy))
+    # W(x,x) with x^ in {0,1}: identical arguments -> 2W(x,x) - W(x,x) - W(x,x) == 0 exactly
+    assert torch.equal(2 * wxx - wxx - wxx, torch.zeros_like(wxx))
+    perm = torch.randperm(240, generator=g).cuda()
+    assert torch.equal(fi.sinkhorn_loss(x[perm], y[perm], 1.0, 50), wxy[perm])     # problems are independent, deterministic
+    assert wyx.shape == wxy.shape
+
+
+def test_opttrans_golden(golden_dir):
+    """OptTrans.forward of the reference (1-D and 2-D), same weights."""
+    fi = _fi()
+    z = np.load(golden_dir + "/opttrans.npz")
+    cfg = pyref.make_config()
+    m = fi.OptTrans(cfg, ch_x=64, L=5).eval()
+    m.load_state_dict({k[len("d1_sd_"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("d1_sd_")})
+    m.cuda()
+    got = m(torch.from_numpy(z["d1_x"]).cuda(), torch.from_numpy(z["d1_y"]).cuda())
+    np.testing.assert_allclose(got.detach().cpu().numpy(), z["d1_loss"], atol=LOSS_TOL, rtol=0)
+    m2 = fi.OptTrans(cfg, ch_x=16, spatial_x=8, spatial_y=16, L=5).eval()
+    m2.load_state_dict({k[len("d2_sd_"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("d2_sd_")})
+    m2.cuda()
+    got2 = m2(torch.from_numpy(z["d2_x"]).cuda(), torch.from_numpy(z["d2_y"]).cuda())
+    np.testing.assert_allclose(got2.detach().cpu().numpy(), z["d2_loss"], atol=LOSS_TOL, rtol=0)
+
+
+def test_opttrans_backward_matches_restatement():
+    fi = _fi()
+    torch.manual_seed(0)
+    ref = pyref.OptTransRef(ch_x=32, L=7)
+    m = fi.OptTrans(pyref.make_config(), ch_x=32, L=7)
+    m.load_state_dict(ref.state_dict())
+    m.cuda()
+    x, y = torch.randn(4, 32, 1), torch.randn(4, 32, 1).abs()
+    xr = x.clone().requires_grad_()
+    lr = ref(xr, y)
+    lr.sum().backward()
+    xc = x.cuda().requires_grad_()
+    lc = m(xc, y.cuda())
+    lc.sum().backward()
+    np.testing.assert_allclose(lc.detach().cpu().numpy(), lr.detach().numpy(), atol=LOSS_TOL, rtol=0)
+    np.testing.assert_allclose(xc.grad.cpu().numpy(), xr.grad.numpy(), atol=1e-5, rtol=1e-3)
+    for (n, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
+        np.testing.assert_allclose(p.grad.cpu().numpy(), q.grad.numpy(), atol=1e-5, rtol=1e-3, err_msg=n)
+
+
+# ------------------------------------------------------------------------------------------------ level / split
+def test_roi_level_bit_exact_vs_torch_and_oracle():
+    fi = _fi()
+    from feature_intertwiner_b200 import synth
+    g = torch.Generator().manual_seed(2000)
+    rois = synth.make_rois(8, 2000, (832, 1344), g)
+    shape = (832, 1344, 3)
+    got = fi.roi_level(rois.cuda(), shape, 224.0).cpu()
+    # (1) the reference's op sequence executed by torch on the SAME device (what the reference itself would do)
+    r = rois.cuda()
+    y1, x1, y2, x2 = r.chunk(4, dim=2)
+    area = (x2 - x1) * (y2 - y1)
+    ia = torch.tensor([float(shape[0] * shape[1])]).cuda()
+    ln2 = torch.log(torch.tensor([2.0])).cuda()
+    lvl = (4 + torch.log(torch.sqrt(area) / (224.0 / torch.sqrt(ia))) / ln2).round().clamp(2, 5).int().squeeze(-1).cpu()
+    assert torch.equal(got, lvl)
+    # (2) the C oracle; a mismatch is only tolerated on an exact .5 tie of the pre-round value (none expected)
+    want, pre = clib.oracle_roi_level(rois.numpy().reshape(-1, 4), float(shape[0] * shape[1]), 224.0)
+    diff = got.numpy().reshape(-1) != want
+    assert not np.any(diff & (np.abs(pre - np.floor(pre) - 0.5) > 1e-5))
+    assert set(np.unique(want)) == {2, 3, 4, 5}
+    assert np.all(got.numpy()[:, -100:] == 2)        # zero-padded RoIs: log(0) = -inf -> level 2
+
+
+@pytest.mark.parametrize("n", [0, 1, 257, 4096, 16000])
+def test_split_matches_nonzero(n):
+    fi = _fi()
+    g = torch.Generator().manual_seed(n)
+    level = torch.randint(2, 6, (n,), generator=g, dtype=torch.int32).cuda()
+    if n == 257:
+        level[:] = 3                                  # empty lists
+    sp = fi.split_levels(level)
+    for i, l in enumerate(range(2, 6)):
+        small = torch.nonzero(level == l).squeeze(1).int()
+        big = torch.nonzero(level > l).squeeze(1).int()
+        assert sp.small_cnt[i] == small.numel() and sp.big_cnt[i] == big.numel()
+        assert torch.equal(sp.small(i), small) and torch.equal(sp.big(i), big)
+        if small.numel():
+            assert torch.equal(sp.slot[small.long()], torch.arange(small.numel(), dtype=torch.int32).cuda())
+
+
+# ------------------------------------------------------------------------------------------------ segment mean / buffer
+@pytest.mark.parametrize("k", [0, 1, 500, 3000])
+def test_segment_mean_fwd_bwd(k):
+    fi = _fi()
+    g = torch.Generator().manual_seed(k)
+    gt = torch.randint(0, 81, (k,), generator=g, dtype=torch.int32)
+    if k > 10:
+        gt[k // 2:] = 0
+        gt[:5] = 7
+    feat = torch.randn(k, 1024, 1, 1, generator=g)
+    want_f, want_c = clib.oracle_segment_mean(gt.numpy(), feat.view(k, 1024).numpy(), 81)
+    fc = feat.cuda().requires_grad_()
+    mean, cnt = fi.assign_feat2cls(gt.cuda(), fc, 81)
+    np.testing.assert_array_equal(cnt.cpu().numpy(), want_c)
+    np.testing.assert_allclose(mean.detach().cpu().numpy(), want_f, rtol=1e-5, atol=1e-6)
+    w = torch.randn(1024, 81, generator=g)
+    (mean * w.cuda()).sum().backward()
+    fr = feat.clone().requires_grad_()
+    mr, _ = pyref.assign_feat2cls_ref(gt.long(), fr, 81)
+    (mr * w).sum().backward()
+    np.testing.assert_allclose(fc.grad.cpu().numpy(), fr.grad.numpy(), rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("B,loss", [(1, "l2"), (1, "l1"), (3, "l2"), (1, "ot")])
+@pytest.mark.parametrize("inst", [False, True])
+def test_intertwiner_loss_vs_restatement(B, loss, inst):
+    fi = _fi()
+    torch.manual_seed(B * 10 + inst)
+    cfg = pyref.make_config(DEV__BUFFER_SIZE=B, DEV__LOSS_CHOICE=loss, DEV__INST_LOSS=inst)
+    Fd, ncls, S, n_inst = 1024, 81, 3, 60
+    ot_ref = pyref.OptTransRef(ch_x=Fd, L=5) if loss == "ot" else None
+    ref = pyref.MetaLossRef(cfg, Fd, ot_loss=ot_ref)
+    ot = None
+    if loss == "ot":
+        ot = fi.OptTrans(cfg, ch_x=Fd, L=5)
+        ot.load_state_dict(ot_ref.state_dict())
+    mod = fi.IntertwinerLoss(cfg, ot_loss=ot, feat_dim=Fd).cuda()
+    for step in range(4):                                    # several iterations: the buffer is state
+        def stats():
+            cnt = torch.randint(0, 4, (1, S, 1, ncls)).float()
+            feat = torch.rand(1, S, Fd, ncls) * (cnt > 0)
+            return feat, cnt
+        bf, bc = stats()
+        sf, sc = stats()
+        so = torch.rand(n_inst, Fd)
+        sg = torch.randint(0, ncls, (n_inst,)).float()
+        sf_r, so_r = sf.clone().requires_grad_(), so.clone().requires_grad_()
+        want = ref([bf, bc, sf_r, sc, so_r, sg])
+        sf_c, so_c = sf.cuda().requires_grad_(), so.cuda().requires_grad_()
+        got = mod([bf.cuda(), bc.cuda(), sf_c, sc.cuda(), so_c, sg.cuda()])
+        np.testing.assert_allclose(got.detach().cpu().numpy().reshape(-1), want.detach().numpy().reshape(-1), atol=LOSS_TOL, rtol=1e-5)
+        fb, fbc = mod.fifo_buffer()
+        np.testing.assert_allclose(fb.cpu().numpy(), ref.buffer.numpy(), rtol=1e-5, atol=1e-6)
+        np.testing.assert_array_equal(fbc.cpu().numpy(), ref.buffer_cnt.numpy())
+        if want.requires_grad:
+            want.sum().backward(); got.sum().backward()
+            a, b = (so_c, so_r) if inst else (sf_c, sf_r)
+            np.testing.assert_allclose(a.grad.cpu().numpy(), b.grad.numpy(), rtol=1e-3, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------ NMS
+def test_nms_golden_and_oracle(golden_dir):
+    fi = _fi()
+    z = np.load(golden_dir + "/nms.npz")
+    d = torch.from_numpy(z["dets"]).cuda()
+    for thr in (0.3, 0.5, 0.7):
+        got = fi.pth_nms(d, thr).cpu().numpy()
+        strict = clib.oracle_nms(z["dets"][:, [1, 0, 3, 2, 4]], thr, True)
+        np.testing.assert_array_equal(got, strict)
+        # reference's compiled cpu_nms uses >=; identical unless an IoU sits exactly on the threshold
+        np.testing.assert_array_equal(got, z[f"keep_cpu_{thr}"])
+
+
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 1000, 6000])
+def test_nms_batched_vs_oracle(n):
+    fi = _fi()
+    from feature_intertwiner_b200 import synth
+    g = torch.Generator().manual_seed(n)
+    dets = synth.make_nms_boxes(3, n, g)
+    keep = fi.nms(dets.cuda(), 0.7)
+    want = pyref.nms_ref(dets, 0.7, strict=True)
+    assert keep.dtype == np.int32
+    np.testing.assert_array_equal(keep, want)
+
+
+def test_nms_known_answers_and_threshold_rule():
+    fi = _fi()
+    # disjoint boxes keep all; identical boxes keep the first
+    d = torch.tensor([[0, 0, 10, 10, .9], [20, 20, 30, 30, .8], [0, 0, 10, 10, .7]], dtype=torch.float32).cuda()
+    assert fi.pth_nms(d, 0.5).tolist() == [0, 1]
+    # IoU exactly at the threshold: the GPU rule (>) keeps, the CPU rule (>=) would suppress (Appendix B.7)
+    a = torch.tensor([[0, 0, 9, 9, .9], [0, 0, 9, 4, .8]], dtype=torch.float32).cuda()     # inter 50, union 100 -> 0.5
+    assert fi.pth_nms(a, 0.5).tolist() == [0, 1]
+    assert clib.oracle_nms(a.cpu().numpy()[:, [1, 0, 3, 2, 4]], 0.5, False).tolist() == [0]
+    # mask words of the reference-named _nms launcher
+    from feature_intertwiner_b200 import _lib
+    b = synth_boxes = torch.tensor([[0, 0, 10, 10, .9], [1, 1, 10, 10, .8], [50, 50, 60, 60, .7]], dtype=torch.float32).cuda()
+    mask = torch.zeros(3, 1, dtype=torch.int64).cuda()
+    _lib.lib()._nms(3, b.data_ptr(), mask.data_ptr(), 0.5)
+    torch.cuda.synchronize()
+    assert mask.view(-1).tolist() == [2, 0, 0]
+
+
+# ------------------------------------------------------------------------------------------------ RoIPool
+@pytest.mark.parametrize("scale", [0.25, 0.0625])
+def test_roi_pool_fwd_bwd(scale):
+    fi = _fi()
+    g = torch.Generator().manual_seed(1)
+    B, C, H, W, R = 2, 16, 30, 40, 50
+    feat = torch.randn(B, C, H, W, generator=g)
+    xy = torch.rand(R, 2, generator=g) * torch.tensor([W / scale, H / scale])
+    wh = torch.rand(R, 2, generator=g) * 60 + 1
+    rois = torch.cat([torch.randint(0, B, (R, 1), generator=g).float(), xy, xy + wh], 1)
+    rois[0, 1:] = torch.tensor([40., 40., 20., 20.])          # malformed (end < start): forced 1x1, no gradient
+    rois[1, 1:] = torch.tensor([1e4, 1e4, 1e4 + 5, 1e4 + 5])  # outside the map: empty bins -> 0 / argmax -1
+    top, arg = clib.oracle_roi_pool_fwd(feat.numpy(), rois.numpy(), 7, 7, scale)
+    fc = feat.cuda().requires_grad_()
+    out = fi.RoIPoolFunction(7, 7, scale)(fc, rois.cuda())
+    np.testing.assert_array_equal(out.detach().cpu().numpy(), top)
+    gy = torch.randn(out.shape, generator=g)
+    out.backward(gy.cuda())
+    want = clib.oracle_roi_pool_bwd(gy.numpy(), arg, rois.numpy(), feat.shape, scale)
+    np.testing.assert_allclose(fc.grad.cpu().numpy(), want, rtol=1e-5, atol=1e-6)
+    assert np.all(top[1] == 0) and np.all(arg[1] == -1)
+
+
+# ------------------------------------------------------------------------------------------------ Dev end to end
+@pytest.mark.parametrize("fmt", ["nchw", "nhwc"])
+@pytest.mark.parametrize("loss", ["l2", "ot"])
+def test_dev_forward_backward_vs_restatement(fmt, loss):
+    """Dev.forward + meta loss vs the CPU restatement (lib/sub_module.py:380-642, lib/model.py:143-210), same weights."""
+    fi = _fi()
+    from feature_intertwiner_b200 import synth
+    torch.manual_seed(5)
+    g = torch.Generator().manual_seed(5)
+    shape = (256, 256, 3)
+    cfg = pyref.make_config(DATA__IMAGE_SHAPE=np.array(shape), DEV__LOSS_CHOICE=loss)
+    depth, bs, R = 256, 2, 48
+    ref = pyref.DevRef(cfg, depth=depth, feat_dim=1024).eval()
+    dev = fi.Dev(cfg, depth).eval()
+    dev.load_state_dict(ref.state_dict())
+    dev.cuda()
+    maps = [torch.randn(bs, depth, 64 >> i, 64 >> i, generator=g) for i in range(4)]
+    rois = synth.make_rois(bs, R, (256, 256), g, zero_frac=0.1)
+    rois[:, :, :] = rois[:, :, :] * 1.0
+    # shrink the side range so every level 2..5 is populated at this image size
+    gt = synth.make_class_ids(bs, R, g)
+    maps_r = [m.clone().requires_grad_() for m in maps]
+    po_r, mo_r, fo_r = ref(maps_r, rois, gt.long())
+    maps_c = [m.cuda().requires_grad_() for m in maps]
+    xin = [m.contiguous(memory_format=torch.channels_last) if fmt == "nhwc" else m for m in maps_c]
+    po, mo, fo = dev(xin, rois.cuda(), gt.cuda())
+    np.testing.assert_allclose(po.detach().cpu().numpy(), po_r.detach().numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(mo.detach().cpu().numpy(), mo_r.detach().numpy(), rtol=1e-4, atol=1e-4)
+    for a, b in zip(fo, fo_r):
+        np.testing.assert_allclose(a.detach().cpu().numpy(), b.detach().numpy(), rtol=1e-3, atol=1e-4)
+    ot_ref = pyref.OptTransRef(ch_x=1024, L=5) if loss == "ot" else None
+    ml_r = pyref.MetaLossRef(cfg, 1024, ot_loss=ot_ref)
+    ot = None
+    if loss == "ot":
+        ot = fi.OptTrans(cfg, ch_x=1024, L=5)
+        ot.load_state_dict(ot_ref.state_dict())
+    ml = fi.IntertwinerLoss(cfg, ot_loss=ot).cuda()
+    l_r = ml_r([fo_r[0], fo_r[1], fo_r[2], fo_r[3], fo_r[5], fo_r[6]])
+    l_c = ml([fo[0], fo[1], fo[2], fo[3], fo[5], fo[6]])
+    np.testing.assert_allclose(l_c.detach().cpu().numpy().reshape(-1), l_r.detach().numpy().reshape(-1), atol=LOSS_TOL, rtol=1e-4)
+    (l_r.sum() + 1e-3 * po_r.sum() + 1e-3 * mo_r.pow(2).sum()).backward()
+    (l_c.sum() + 1e-3 * po.sum() + 1e-3 * mo.pow(2).sum()).backward()
+    for a, b in zip(maps_c, maps_r):
+        if b.grad is None:
+            assert a.grad is None or float(a.grad.abs().max()) == 0
+            continue
+        np.testing.assert_allclose(a.grad.cpu().numpy(), b.grad.numpy(), rtol=1e-3, atol=2e-5)

@@ -1,0 +1,182 @@
+"""CPU suite, part 1: pin the oracle.
+
+* against the golden vectors generated from the reference itself (tests/golden/make_golden.py);
+* against oracle/_ref (the reference's C compiled unmodified) on fresh seeded inputs, where it is present
+  (it is built only where /root/reference exists; the committed golden vectors cover the other case);
+* against closed-form known answers.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import clib, pyref
+
+
+def test_roi_align_oracle_vs_golden(golden_dir):
+    z = np.load(golden_dir + "/roi_align.npz")
+    for P in (1, 2, 7, 14):
+        got = clib.oracle_crop_and_resize_fwd(z["image"], z["boxes"], z["box_ind"], P, P, 0.25)
+        np.testing.assert_array_equal(got, z[f"crops_{P}"])
+        gi = clib.oracle_crop_and_resize_bwd(z[f"grads_{P}"], z["boxes"], z["box_ind"], z["image"].shape)
+        np.testing.assert_array_equal(gi, z[f"grad_image_{P}"])
+    np.testing.assert_array_equal(clib.oracle_crop_and_resize_fwd(z["image"], z["boxes"], z["box_ind"], 3, 5, 0.0), z["crops_3x5"])
+
+
+@pytest.mark.skipif(not clib.have_ref(), reason="oracle/_ref is only built where /root/reference exists")
+def test_roi_align_oracle_vs_compiled_reference():
+    rng = np.random.default_rng(7)
+    B, C, H, W, R = 3, 5, 26, 42, 200
+    img = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    ctr, size = rng.uniform(0, 1, (R, 2)), rng.uniform(0.01, 0.9, (R, 2))
+    boxes = np.concatenate([ctr - size / 2, ctr + size / 2], 1).astype(np.float32)
+    boxes[:10] = 0
+    bi = rng.integers(0, B, R).astype(np.int32)
+    for P in (1, 7, 14):
+        a = clib.oracle_crop_and_resize_fwd(img, boxes, bi, P, P, -1.5)
+        np.testing.assert_array_equal(a, clib.ref_crop_and_resize_fwd(img, boxes, bi, P, P, -1.5))
+        g = rng.standard_normal(a.shape).astype(np.float32)
+        np.testing.assert_array_equal(clib.oracle_crop_and_resize_bwd(g, boxes, bi, img.shape),
+                                      clib.ref_crop_and_resize_bwd(g, boxes, bi, img.shape))
+
+
+def test_roi_align_known_answers():
+    H, W = 9, 13
+    rng = np.random.default_rng(0)
+    img = rng.standard_normal((1, 2, H, W)).astype(np.float32)
+    z = np.zeros(1, np.int32)
+    np.testing.assert_allclose(clib.oracle_crop_and_resize_fwd(img, [[0, 0, 1, 1]], z, H, W)[0], img[0], atol=1e-6)
+    yy, xx = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
+    ramp = (2 * yy + 3 * xx)[None, None]
+    out = clib.oracle_crop_and_resize_fwd(ramp, [[0.125, 0.25, 0.75, 0.875]], z, 5, 5)[0, 0]
+    ys = 0.125 * (H - 1) + np.arange(5) * (0.75 - 0.125) * (H - 1) / 4
+    xs = 0.25 * (W - 1) + np.arange(5) * (0.875 - 0.25) * (W - 1) / 4
+    np.testing.assert_allclose(out, 2 * ys[:, None] + 3 * xs[None, :], rtol=1e-5, atol=1e-5)
+    out = clib.oracle_crop_and_resize_fwd(img, [[0, 0, 0, 0]], z, 7, 7)
+    assert np.all(out[0] == img[0, :, 0, 0][:, None, None])
+    taps = clib.oracle_crop_taps(H, W, [[-0.5, 0.0, 0.5, 1.0]], 5, 3)
+    assert taps[0, :, :, 4].tolist() == [[0, 0, 0], [0, 0, 0], [1, 1, 1], [1, 1, 1], [1, 1, 1]]
+    # backward is the transpose of forward
+    boxes = np.concatenate([rng.uniform(0, .5, (30, 2)), rng.uniform(.5, 1, (30, 2))], 1).astype(np.float32)
+    bi = np.zeros(30, np.int32)
+    out = clib.oracle_crop_and_resize_fwd(img, boxes, bi, 7, 7)
+    g = rng.standard_normal(out.shape).astype(np.float32)
+    gi = clib.oracle_crop_and_resize_bwd(g, boxes, bi, img.shape)
+    assert abs((out.astype(np.float64) * g).sum() - (img.astype(np.float64) * gi).sum()) < 1e-3
+
+
+def test_nms_oracle_vs_golden(golden_dir):
+    z = np.load(golden_dir + "/nms.npz")
+    xyxy = z["dets"][:, [1, 0, 3, 2, 4]]
+    for thr in (0.3, 0.5, 0.7):
+        np.testing.assert_array_equal(clib.oracle_nms(xyxy, thr, False), z[f"keep_cpu_{thr}"])
+        np.testing.assert_array_equal(pyref.pth_nms_ref(torch.from_numpy(z["dets"]), thr, strict=False).numpy(), z[f"keep_cpu_{thr}"])
+
+
+def test_sinkhorn_oracle_vs_golden(golden_dir):
+    """C oracle (fp32 and wide) and the torch restatement against lib/OT_module.py's own outputs."""
+    z = np.load(golden_dir + "/sinkhorn.npz")
+    for name in ("n256_d1", "n64_d256", "n16_d3"):
+        x, y = z[name + "_x"], z[name + "_y"]
+        for L in (1, 5, 50):
+            for eps in (1.0, 0.1):
+                want = float(z[f"{name}_L{L}_eps{eps}"])
+                for wide in (False, True):
+                    got = clib.oracle_sinkhorn(x, y, 1.0 / eps, L, wide=wide)[0]
+                    assert abs(got - want) < 2e-5, (name, L, eps, wide, got, want)
+                got = pyref.sinkhorn_iterate_ref(torch.from_numpy(x), torch.from_numpy(y), 1.0 / eps, L).item()
+                assert abs(got - want) < 1e-6
+
+
+def test_opttrans_restatement_vs_golden(golden_dir):
+    z = np.load(golden_dir + "/opttrans.npz")
+    m = pyref.OptTransRef(ch_x=64, L=5).eval()
+    m.load_state_dict({k[len("d1_sd_"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("d1_sd_")})
+    with torch.no_grad():
+        got = m(torch.from_numpy(z["d1_x"]), torch.from_numpy(z["d1_y"]))
+    np.testing.assert_allclose(got.numpy(), z["d1_loss"], atol=1e-6, rtol=0)
+    m2 = pyref.OptTransRef(ch_x=16, spatial_x=8, spatial_y=16, L=5).eval()
+    m2.load_state_dict({k[len("d2_sd_"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("d2_sd_")})
+    with torch.no_grad():
+        got2 = m2(torch.from_numpy(z["d2_x"]), torch.from_numpy(z["d2_y"]))
+    np.testing.assert_allclose(got2.numpy(), z["d2_loss"], atol=1e-6, rtol=0)
+
+
+def test_sinkhorn_oracle_properties_and_grad():
+    rng = np.random.default_rng(1)
+    x = np.abs(rng.standard_normal((32, 6))).astype(np.float32)
+    y = np.abs(rng.standard_normal((32, 6))).astype(np.float32)
+    loss, P, gx, gy = clib.oracle_sinkhorn(x, y, 2.0, 200, wide=True, want_plan=True, want_grad=True)
+    np.testing.assert_allclose(P.sum(0), 1 / 32, rtol=1e-4)          # doubly stochastic after convergence
+    np.testing.assert_allclose(P.sum(1), 1 / 32, rtol=1e-3)
+    # analytic gradient (P constant) == autograd through the torch restatement
+    xt, yt = torch.from_numpy(x).requires_grad_(), torch.from_numpy(y).requires_grad_()
+    pyref.sinkhorn_iterate_ref(xt, yt, 2.0, 200).backward()
+    np.testing.assert_allclose(gx, xt.grad.numpy(), rtol=1e-3, atol=1e-7)
+    np.testing.assert_allclose(gy, yt.grad.numpy(), rtol=1e-3, atol=1e-7)
+    # x == y: the debiased combination vanishes
+    w = clib.oracle_sinkhorn(x, x, 1.0, 5, wide=True)[0]
+    assert abs(2 * w - w - w) == 0
+
+
+def test_level_rule_oracle_vs_torch_restatement():
+    from feature_intertwiner_b200 import synth
+    g = torch.Generator().manual_seed(2000)
+    rois = synth.make_rois(4, 1000, (832, 1344), g)
+    lvl, pre = pyref.roi_level_ref(rois, (832, 1344, 3), 224.0)
+    want, pre_c = clib.oracle_roi_level(rois.numpy().reshape(-1, 4), float(832 * 1344), 224.0)
+    bad = lvl.numpy().reshape(-1) != want
+    # glibc logf vs torch's vectorised log may differ by an ulp: only exact .5 ties may flip
+    assert not np.any(bad & (np.abs(pre_c - np.floor(pre_c) - 0.5) > 1e-5))
+    assert set(np.unique(want)) == {2, 3, 4, 5}
+    # FPN Eq.1 known answers: a 224 px square -> P4, 112 -> P3, 448 -> P5, 56 and smaller -> P2
+    for side, level in ((224, 4), (112, 3), (448, 5), (56, 2), (20, 2), (800, 5)):
+        r = np.array([[0, 0, side / 832.0, side / 1344.0]], np.float32)
+        assert clib.oracle_roi_level(r, float(832 * 1344), 224.0)[0][0] == level
+    assert clib.oracle_roi_level(np.zeros((1, 4), np.float32), 1e6, 224.0)[0][0] == 2
+
+
+def test_segment_mean_oracle_vs_restatement():
+    g = torch.Generator().manual_seed(0)
+    gt = torch.randint(0, 81, (300,), generator=g)
+    f = torch.randn(300, 64, generator=g)
+    a, c = clib.oracle_segment_mean(gt.numpy(), f.numpy(), 81)
+    b, d = pyref.assign_feat2cls_ref(gt, f, 81)
+    np.testing.assert_allclose(a, b.numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_array_equal(c, d.numpy())
+    assert np.all(a[:, 0] == 0) and c[0, 0] == 0
+
+
+def test_roi_pool_oracle_known_answers():
+    feat = np.arange(2 * 1 * 8 * 8, dtype=np.float32).reshape(2, 1, 8, 8)
+    # integer-aligned RoI covering the whole 8x8 map at scale 1 with 4x4 bins -> plain 2x2 max-pool
+    top, arg = clib.oracle_roi_pool_fwd(feat, [[1, 0, 0, 7, 7]], 4, 4, 1.0)
+    want = feat[1, 0].reshape(4, 2, 4, 2).max(axis=(1, 3))
+    np.testing.assert_array_equal(top[0, 0], want)
+    assert arg[0, 0, 0, 0] == 64 + 9
+    top, arg = clib.oracle_roi_pool_fwd(feat, [[0, 100, 100, 120, 120]], 2, 2, 1.0)      # outside: empty bins
+    assert np.all(top == 0) and np.all(arg == -1)
+    g = np.ones((1, 1, 4, 4), np.float32)
+    top, arg = clib.oracle_roi_pool_fwd(feat, [[1, 0, 0, 7, 7]], 4, 4, 1.0)
+    gi = clib.oracle_roi_pool_bwd(g, arg, [[1, 0, 0, 7, 7]], feat.shape, 1.0)
+    assert gi.sum() == 16 and gi[0].sum() == 0
+
+
+def test_dev_restatement_runs_and_scatter_order():
+    """DevRef: pooled rows come back in (image, roi) order and match a direct per-box crop."""
+    from feature_intertwiner_b200 import synth
+    torch.manual_seed(0)
+    g = torch.Generator().manual_seed(0)
+    cfg = pyref.make_config(DATA__IMAGE_SHAPE=np.array([256, 256, 3]))
+    dev = pyref.DevRef(cfg, depth=8, feat_dim=32).eval()
+    maps = [torch.randn(2, 8, 64 >> i, 64 >> i, generator=g) for i in range(4)]
+    rois = synth.make_rois(2, 40, (256, 256), g, zero_frac=0.1)
+    gt = synth.make_class_ids(2, 40, g)
+    po, mo, fo = dev(maps, rois, gt.long())
+    assert po.shape == (80, 8, 7, 7) and mo.shape == (80, 8, 14, 14) and len(fo) == 7
+    lvl, _ = pyref.roi_level_ref(rois, (256, 256, 3))
+    with torch.no_grad():
+        for b, r in ((0, 3), (1, 17), (1, 39)):
+            l = int(lvl[b, r]) - 2
+            fm = dev.upsample[0](maps[l])
+            want = pyref.crop_and_resize_ref(fm, rois[b, r][None], torch.tensor([b], dtype=torch.int32), 7, 7)
+            torch.testing.assert_close(po[b * 40 + r], want[0])
