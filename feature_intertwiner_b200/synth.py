@@ -69,7 +69,8 @@ def make_nms_boxes(n_images, n, gen, extent=1024.0):
     (callers pre-sort, lib/layers.py:103)."""
     ctr = torch.rand(n_images, n, 2, generator=gen) * extent
     size = torch.exp(torch.empty(n_images, n, 2).uniform_(math.log(16.0), math.log(400.0), generator=gen))
-    score = torch.rand(n_images, n, generator=gen).sort(dim=1, descending=True)[0]
+    # strictly decreasing scores: fp32 rand collides at these sizes and the reference's sort is unstable on ties
+    score = torch.linspace(1.0, 0.0, n).expand(n_images, n).contiguous()
     lo = (ctr - size / 2).clamp(0, extent)
     hi = (ctr + size / 2).clamp(0, extent)
     return torch.cat([lo, hi, score.unsqueeze(2)], dim=2).float().contiguous()

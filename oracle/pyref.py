@@ -249,6 +249,7 @@ class MetaLossRef:
         B, ncls = config.DEV.BUFFER_SIZE, config.DATASET.NUM_CLASSES
         self.buffer = torch.zeros(B, feat_dim, ncls)
         self.buffer_cnt = torch.zeros(B, 1, ncls)
+        self.device = torch.device('cpu')
         self.ot_loss = ot_loss
 
     def __call__(self, feat_input):
@@ -273,7 +274,7 @@ class MetaLossRef:
             idx = torch.nonzero((fc.squeeze(0) > 0) & in_buffer).squeeze(1)
         self.last_idx = idx
         if idx.numel() == 0:
-            return torch.zeros(1)
+            return torch.zeros(1, device=self.buffer.device)
         if self.config.DEV.INST_LOSS:
             SMALL = small_output_all[idx]
             BIG = final_big[:, small_gt_all[idx].long()].t()
@@ -302,8 +303,8 @@ def sinkhorn_iterate_ref(x, y, inv_eps=1.0, L=5, detach_plan=True):
     y = y / (torch.norm(y, p=2, dim=1, keepdim=True) + EPS)
     C = 1 - torch.mm(x, y.permute(1, 0))
     K = torch.exp(-inv_eps * C)
-    b = torch.ones(n, 1, dtype=x.dtype) * (1.0 / n)
-    const = torch.ones(n, 1, dtype=x.dtype) * (1.0 / n)
+    b = torch.ones(n, 1, dtype=x.dtype, device=x.device) * (1.0 / n)
+    const = torch.ones(n, 1, dtype=x.dtype, device=x.device) * (1.0 / n)
     a = const
     for _ in range(L):
         a = const / (torch.mm(K, b) + EPS)
@@ -354,7 +355,9 @@ def pth_nms_ref(dets, thresh, strict=True):
     (IoU > thr, nms_kernel.cu:63; the mask kernel sees boxes in INPUT order, Appendix B.6),
     strict=False the CPU branch (IoU >= thr, nms.c:59; boxes visited in score order)."""
     d = dets.detach().cpu().numpy().astype(np.float32)
-    order = torch.sort(dets[:, 4], 0, descending=True)[1].cpu().numpy()
+    # the reference's sort is unstable (pth_nms.py:37): with tied scores its result is implementation-defined;
+    # a stable sort is used here and in the product so the two agree
+    order = torch.sort(dets[:, 4], 0, descending=True, stable=True)[1].cpu().numpy()
     xyxy = d[:, [1, 0, 3, 2, 4]]
     if strict:
         keep = clib.oracle_nms(xyxy, thresh, True)          # un-reordered dets_temp (pth_nms.py:28-44)

@@ -162,6 +162,9 @@ def test_segment_mean_fwd_bwd(k):
     mean, cnt = fi.assign_feat2cls(gt.cuda(), fc, 81)
     np.testing.assert_array_equal(cnt.cpu().numpy(), want_c)
     np.testing.assert_allclose(mean.detach().cpu().numpy(), want_f, rtol=1e-5, atol=1e-6)
+    if k == 0:
+        assert float(mean.abs().sum()) == 0
+        return
     w = torch.randn(1024, 81, generator=g)
     (mean * w.cuda()).sum().backward()
     fr = feat.clone().requires_grad_()
@@ -177,8 +180,12 @@ def test_intertwiner_loss_vs_restatement(B, loss, inst):
     torch.manual_seed(B * 10 + inst)
     cfg = pyref.make_config(DEV__BUFFER_SIZE=B, DEV__LOSS_CHOICE=loss, DEV__INST_LOSS=inst)
     Fd, ncls, S, n_inst = 1024, 81, 3, 60
-    ot_ref = pyref.OptTransRef(ch_x=Fd, L=5) if loss == "ot" else None
+    # The restatement runs on the SAME device: with D=1 the cosine normalisation is a sign function of the critic
+    # output, so a 1e-7 difference between a CPU and a cuDNN convolution can flip x^ between
+    # 0 and 1.  Same device => identical stock-conv outputs => only the Sinkhorn kernel itself is under test.
+    ot_ref = pyref.OptTransRef(ch_x=Fd, L=5).cuda() if loss == "ot" else None
     ref = pyref.MetaLossRef(cfg, Fd, ot_loss=ot_ref)
+    ref.buffer, ref.buffer_cnt = ref.buffer.cuda(), ref.buffer_cnt.cuda()
     ot = None
     if loss == "ot":
         ot = fi.OptTrans(cfg, ch_x=Fd, L=5)
@@ -193,18 +200,18 @@ def test_intertwiner_loss_vs_restatement(B, loss, inst):
         sf, sc = stats()
         so = torch.rand(n_inst, Fd)
         sg = torch.randint(0, ncls, (n_inst,)).float()
-        sf_r, so_r = sf.clone().requires_grad_(), so.clone().requires_grad_()
-        want = ref([bf, bc, sf_r, sc, so_r, sg])
+        sf_r, so_r = sf.cuda().requires_grad_(), so.cuda().requires_grad_()
+        want = ref([bf.cuda(), bc.cuda(), sf_r, sc.cuda(), so_r, sg.cuda()])
         sf_c, so_c = sf.cuda().requires_grad_(), so.cuda().requires_grad_()
         got = mod([bf.cuda(), bc.cuda(), sf_c, sc.cuda(), so_c, sg.cuda()])
-        np.testing.assert_allclose(got.detach().cpu().numpy().reshape(-1), want.detach().numpy().reshape(-1), atol=LOSS_TOL, rtol=1e-5)
+        np.testing.assert_allclose(got.detach().cpu().numpy().reshape(-1), want.detach().cpu().numpy().reshape(-1), atol=LOSS_TOL, rtol=1e-5)
         fb, fbc = mod.fifo_buffer()
-        np.testing.assert_allclose(fb.cpu().numpy(), ref.buffer.numpy(), rtol=1e-5, atol=1e-6)
-        np.testing.assert_array_equal(fbc.cpu().numpy(), ref.buffer_cnt.numpy())
+        np.testing.assert_allclose(fb.cpu().numpy(), ref.buffer.cpu().numpy(), rtol=1e-5, atol=1e-6)
+        np.testing.assert_array_equal(fbc.cpu().numpy(), ref.buffer_cnt.cpu().numpy())
         if want.requires_grad:
             want.sum().backward(); got.sum().backward()
             a, b = (so_c, so_r) if inst else (sf_c, sf_r)
-            np.testing.assert_allclose(a.grad.cpu().numpy(), b.grad.numpy(), rtol=1e-3, atol=1e-7)
+            np.testing.assert_allclose(a.grad.cpu().numpy(), b.grad.cpu().numpy(), rtol=1e-3, atol=1e-7)
 
 
 # ------------------------------------------------------------------------------------------------ NMS
@@ -269,7 +276,7 @@ def test_roi_pool_fwd_bwd(scale):
     gy = torch.randn(out.shape, generator=g)
     out.backward(gy.cuda())
     want = clib.oracle_roi_pool_bwd(gy.numpy(), arg, rois.numpy(), feat.shape, scale)
-    np.testing.assert_allclose(fc.grad.cpu().numpy(), want, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(fc.grad.cpu().numpy(), want, rtol=1e-5, atol=1e-5)   # atomics: summation order
     assert np.all(top[1] == 0) and np.all(arg[1] == -1)
 
 
