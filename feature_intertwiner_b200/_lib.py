@@ -29,6 +29,7 @@ SIGNATURES = {
     "_nms": (None, [_I, _P, _P, _F]),
     "fi_crop_and_resize_forward": (_I, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _I, _P]),
     "fi_crop_and_resize_backward": (_I, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P]),
+    "fi_crop_and_resize_backward_multi": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P]),
     "fi_crop_taps": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "fi_roi_level": (_I, [_P, _I, _F, _F, _P, _P]),
     "fi_split_levels": (_I, [_P, _I, _P, _P, _P, _P, _P, _P]),
@@ -40,6 +41,12 @@ SIGNATURES = {
     "fi_roi_pool_forward": (_I, [_P, _F, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "fi_roi_pool_backward": (_I, [_P, _F, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
 }
+
+
+class CropSet(C.Structure):
+    """struct fi_crop_set (include/fi_b200.h)."""
+    _fields_ = [("grads", _P), ("grads2", _P), ("boxes", _P), ("box_ind", _P), ("src_row", _P),
+                ("num_boxes", _I), ("crop_height", _I), ("crop_width", _I)]
 
 
 def lib():

@@ -41,9 +41,6 @@ __global__ void crop_taps_kernel(const float *__restrict__ boxes, int R, int H, 
 // the taps handed around by warp shuffle: per sample a lane only forms 4 addresses, moves VPL float4 per
 // tap and does the lerps.  Loads are coalesced 512 B per tap row (C=256: two float4 per lane).
 //
-// Column reuse: consecutive samples of an up-sampling crop (step < 1 px -- every 14x14 crop of a box
-// assigned to its own level) share pixel columns; the (top,bottom) values of the current left/right
-// columns stay in registers and only columns that actually change are loaded.
 // ------------------------------------------------------------------------------------------------
 constexpr int kWarpsPerBlock = 8;
 
@@ -56,75 +53,68 @@ __device__ __forceinline__ AxisTap shfl_tap(const AxisTap &t, int src) {
     return o;
 }
 
-template <int VPL>
+// Forward.  Unit of work = (box r, crop row i, 128-channel slab): one warp, one float4 per lane per tap.
+// The row is walked in batches of U samples: all 4*U tap loads of a batch are issued back to back
+// (branch-free: outside samples read a clamped pixel and are overwritten with the extrapolation value
+// afterwards), then the batch is interpolated and stored.  ncu on the first, branchy version of this kernel
+// showed 16 % issue-active with every warp parked on long_scoreboard: the bound was memory-level
+// parallelism, not bytes, so the loop is written to keep 4*U*512 B in flight per warp.
+// Overlap between neighbouring samples / rows / boxes is left to L1 and L2.
+template <int U>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) crop_fwd_nhwc_kernel(const float *__restrict__ image, const float *__restrict__ boxes,
                                                                            const int *__restrict__ box_ind, const int *__restrict__ dst_row,
-                                                                           long nunits, int B, int H, int W, int ph, int pw, int C, float extrap,
-                                                                           float *__restrict__ crops) {
+                                                                           long nunits, int slabs, int B, int H, int W, int ph, int pw, int C,
+                                                                           float extrap, float *__restrict__ crops) {
     const int lane = threadIdx.x & 31;
     const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
-    const int C4 = C >> 2;
     for (long u = warp; u < nunits; u += nwarps) {
-        const int r = (int)(u / ph), i = (int)(u - (long)r * ph);
+        const int slab = (int)(u % slabs);
+        const long q = u / slabs;
+        const int r = (int)(q / ph), i = (int)(q - (long)r * ph);
         const int b = box_ind[r];
         const long orow = dst_row ? (long)dst_row[r] : (long)r;
-        float *out = crops + ((orow * ph + i) * (long)pw) * C;
+        const int coff = slab * 128 + lane * 4;
+        float *out = crops + ((orow * ph + i) * (long)pw) * C + coff;
         const bool bad = (b < 0 || b >= B);     // reference leaves such rows at their zero fill (crop_and_resize_kernel.cu:34-38)
         const float y1 = boxes[4 * r + 0], x1 = boxes[4 * r + 1], y2 = boxes[4 * r + 2], x2 = boxes[4 * r + 3];
         const AxisTap ty = axis_sample(y1, y2, axis_step(y1, y2, H, ph), i, H, ph);
         if (bad || !ty.inside) {
             const float v = bad ? 0.f : extrap;
             const float4 v4 = make_float4(v, v, v, v);
-            for (int e = lane; e < pw * C4; e += 32) st_stream4(out + e * 4, v4);
+            for (int j = 0; j < pw; ++j) st_stream4(out + (long)j * C, v4);
             continue;
         }
         const float sx = axis_step(x1, x2, W, pw);
-        const float *rowT = image + ((long)b * H + ty.lo) * (long)W * C;
-        const float *rowB = image + ((long)b * H + ty.hi) * (long)W * C;
-        const bool one_row = ty.hi == ty.lo;
-        for (int cv0 = 0; cv0 < C4; cv0 += 32 * VPL) {
-            float4 Lt[VPL], Lb[VPL], Rt[VPL], Rb[VPL];
-            int cur_lo = -1, cur_hi = -1;
-            AxisTap mine;
-            for (int j = 0; j < pw; ++j) {
-                if ((j & 31) == 0) mine = axis_sample(x1, x2, sx, j + lane, W, pw);     // lane l holds the x tap of sample j + l
-                const AxisTap tx = shfl_tap(mine, j & 31);
-                float *o = out + (long)j * C;
-                if (!tx.inside) {
+        const float *rowT = image + ((long)b * H + ty.lo) * (long)W * C + coff;
+        const float *rowB = image + ((long)b * H + ty.hi) * (long)W * C + coff;
+        for (int jb = 0; jb < pw; jb += 32) {                        // lane l computes the x tap of sample jb + l
+            const AxisTap mine = axis_sample(x1, x2, sx, jb + lane, W, pw);
+            const int lo_c = min(max(mine.lo, 0), W - 1), hi_c = min(max(mine.hi, 0), W - 1);
+            const int packed = lo_c | (hi_c << 15) | (mine.inside ? (1 << 30) : 0);      // W <= 32768
+            const int jn = min(32, pw - jb);
+            for (int j0 = 0; j0 < jn; j0 += U) {
+                float4 tl[U], tr[U], bl[U], br[U];
+                int pk[U];
 #pragma unroll
-                    for (int v = 0; v < VPL; ++v) {
-                        const int cv = cv0 + v * 32 + lane;
-                        if (cv < C4) st_stream4(o + cv * 4, make_float4(extrap, extrap, extrap, extrap));
-                    }
-                    continue;
-                }
-                if (!(tx.lo == cur_lo && tx.hi == cur_hi)) {
-                    const bool slide = (tx.lo == cur_hi);
-#pragma unroll
-                    for (int v = 0; v < VPL; ++v) {
-                        const int cv = cv0 + v * 32 + lane;
-                        if (cv >= C4) continue;
-                        if (slide) { Lt[v] = Rt[v]; Lb[v] = Rb[v]; }
-                        else {
-                            Lt[v] = ldg4(rowT + (long)tx.lo * C + cv * 4);
-                            Lb[v] = one_row ? Lt[v] : ldg4(rowB + (long)tx.lo * C + cv * 4);
-                        }
-                        if (tx.hi == tx.lo) { Rt[v] = Lt[v]; Rb[v] = Lb[v]; }
-                        else {
-                            Rt[v] = ldg4(rowT + (long)tx.hi * C + cv * 4);
-                            Rb[v] = one_row ? Rt[v] : ldg4(rowB + (long)tx.hi * C + cv * 4);
-                        }
-                    }
-                    cur_lo = tx.lo; cur_hi = tx.hi;
+                for (int k = 0; k < U; ++k) {
+                    const int j = min(j0 + k, jn - 1);               // tail lanes re-read the last sample (discarded)
+                    pk[k] = __shfl_sync(0xffffffffu, packed, j);
+                    const long xl = (long)(pk[k] & 0x7fff) * C, xh = (long)((pk[k] >> 15) & 0x7fff) * C;
+                    tl[k] = ldg4(rowT + xl); tr[k] = ldg4(rowT + xh);
+                    bl[k] = ldg4(rowB + xl); br[k] = ldg4(rowB + xh);
                 }
 #pragma unroll
-                for (int v = 0; v < VPL; ++v) {
-                    const int cv = cv0 + v * 32 + lane;
-                    if (cv >= C4) continue;
-                    const float4 top = lerp_rn(Lt[v], Rt[v], tx.frac);       // crop_and_resize.c:102
-                    const float4 bot = lerp_rn(Lb[v], Rb[v], tx.frac);       // :103-104
-                    st_stream4(o + cv * 4, lerp_rn(top, bot, ty.frac));      // :106
+                for (int k = 0; k < U; ++k) {
+                    const int j = j0 + k;
+                    const float fx = __shfl_sync(0xffffffffu, mine.frac, min(j, jn - 1));
+                    if (j < jn) {
+                        const float4 top = lerp_rn(tl[k], tr[k], fx);            // crop_and_resize.c:102
+                        const float4 bot = lerp_rn(bl[k], br[k], fx);            // :103-104
+                        float4 v = lerp_rn(top, bot, ty.frac);                   // :106
+                        if (!(pk[k] & (1 << 30))) v = make_float4(extrap, extrap, extrap, extrap);
+                        st_stream4(out + (long)(jb + j) * C, v);
+                    }
                 }
             }
         }
@@ -472,6 +462,22 @@ static int check_common(const void *a, const void *boxes, const void *box_ind, c
 
 using namespace fi;
 
+// NHWC scatter backward (reduction kernels); gimg must already hold the values to accumulate onto.
+int fi_scatter_backward_nhwc(const float *grads, const float *boxes, const int *box_ind, const int *src_row, int R, int B, int H, int W, int ph,
+                             int pw, int C, float *gimg, cudaStream_t stream) {
+    if (R == 0) return ok();
+    const long nunits = (long)R * ph;
+    const bool vec = (C % 4 == 0) && ((uintptr_t)gimg % 16 == 0) && ((uintptr_t)grads % 16 == 0);
+    const int grid = grid_for(nunits, kWarpsPerBlock, 8);
+    if (vec && (C / 4) % 64 == 0)
+        crop_bwd_nhwc_kernel<2><<<grid, kWarpsPerBlock * 32, 0, stream>>>(grads, boxes, box_ind, src_row, nunits, B, H, W, ph, pw, C, gimg);
+    else if (vec)
+        crop_bwd_nhwc_kernel<1><<<grid, kWarpsPerBlock * 32, 0, stream>>>(grads, boxes, box_ind, src_row, nunits, B, H, W, ph, pw, C, gimg);
+    else
+        crop_bwd_nhwc_scalar_kernel<<<grid, kWarpsPerBlock * 32, 0, stream>>>(grads, boxes, box_ind, src_row, nunits, B, H, W, ph, pw, C, gimg);
+    return check_launch("fi_crop_and_resize_backward[nhwc scatter]");
+}
+
 FI_API int fi_crop_taps(const float *boxes, int num_boxes, int H, int W, int ph, int pw, int *taps, cudaStream_t stream) {
     FI_REQUIRE(num_boxes >= 0 && H > 0 && W > 0 && ph > 0 && pw > 0, "fi_crop_taps: bad sizes");
     if (num_boxes == 0) return ok();
@@ -491,15 +497,19 @@ FI_API int fi_crop_and_resize_forward(const float *image, int image_layout, cons
         return FI_ERR_UNSUPPORTED;
     }
     if (image_layout == FI_LAYOUT_NHWC) {
-        const long nunits = (long)R * ph;            // one warp per crop row
-        const bool vec = (C % 4 == 0) && ((uintptr_t)image % 16 == 0) && ((uintptr_t)crops % 16 == 0);
-        const int grid = grid_for(nunits, kWarpsPerBlock, 8);
-        if (vec && (C / 4) % 64 == 0)
-            crop_fwd_nhwc_kernel<2><<<grid, kWarpsPerBlock * 32, 0, stream>>>(image, boxes, box_ind, dst_row, nunits, B, H, W, ph, pw, C, extrap, crops);
-        else if (vec)
-            crop_fwd_nhwc_kernel<1><<<grid, kWarpsPerBlock * 32, 0, stream>>>(image, boxes, box_ind, dst_row, nunits, B, H, W, ph, pw, C, extrap, crops);
-        else
-            crop_fwd_nhwc_scalar_kernel<<<grid, kWarpsPerBlock * 32, 0, stream>>>(image, boxes, box_ind, dst_row, nunits, B, H, W, ph, pw, C, extrap, crops);
+        const bool vec = (C % 128 == 0) && (W <= 32768) && ((uintptr_t)image % 16 == 0) && ((uintptr_t)crops % 16 == 0);
+        if (vec) {
+            const int slabs = C / 128;
+            const long nunits = (long)R * ph * slabs;    // one warp per (crop row, 128-channel slab)
+            const int grid = grid_for(nunits, kWarpsPerBlock, 8);
+            if (pw % 4 == 0 || pw > 12)
+                crop_fwd_nhwc_kernel<4><<<grid, kWarpsPerBlock * 32, 0, stream>>>(image, boxes, box_ind, dst_row, nunits, slabs, B, H, W, ph, pw, C, extrap, crops);
+            else
+                crop_fwd_nhwc_kernel<2><<<grid, kWarpsPerBlock * 32, 0, stream>>>(image, boxes, box_ind, dst_row, nunits, slabs, B, H, W, ph, pw, C, extrap, crops);
+        } else {
+            const long nunits = (long)R * ph;
+            crop_fwd_nhwc_scalar_kernel<<<grid_for(nunits, kWarpsPerBlock, 8), kWarpsPerBlock * 32, 0, stream>>>(image, boxes, box_ind, dst_row, nunits, B, H, W, ph, pw, C, extrap, crops);
+        }
         return check_launch("fi_crop_and_resize_forward[nhwc]");
     }
     if (image_layout == FI_LAYOUT_NCHW) {
@@ -521,6 +531,14 @@ FI_API int fi_crop_and_resize_backward(const float *grads, int grads_layout, con
                                        const int *src_row, int R, int B, int H, int W, int ph, int pw, int C,
                                        float *gimg, int image_layout, int accumulate, cudaStream_t stream) {
     FI_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && gimg, "fi_crop_and_resize_backward: bad image");
+    if (image_layout == FI_LAYOUT_NHWC && grads_layout == FI_LAYOUT_NHWC) {
+        // gather (write-once) path when the shape qualifies, reduction kernels otherwise -- roi_align_bwd.cu
+        fi_crop_set one;
+        one.grads = grads; one.grads2 = nullptr; one.boxes = boxes; one.box_ind = box_ind; one.src_row = src_row;
+        one.num_boxes = R; one.crop_height = ph; one.crop_width = pw;
+        FI_REQUIRE(R >= 0 && ph > 0 && pw > 0, "fi_crop_and_resize_backward: bad sizes");
+        return fi_crop_and_resize_backward_multi(&one, 1, B, H, W, C, gimg, accumulate, stream);
+    }
     if (!accumulate) {
         cudaError_t e = cudaMemsetAsync(gimg, 0, sizeof(float) * (size_t)B * C * H * W, stream);
         if (e != cudaSuccess) { set_error(FI_ERR_CUDA, "fi_crop_and_resize_backward: memset: %s", cudaGetErrorString(e)); return FI_ERR_CUDA; }
@@ -531,18 +549,7 @@ FI_API int fi_crop_and_resize_backward(const float *grads, int grads_layout, con
         set_error(FI_ERR_UNSUPPORTED, "fi_crop_and_resize_backward: mixed layouts (grads %d, image %d)", grads_layout, image_layout);
         return FI_ERR_UNSUPPORTED;
     }
-    if (image_layout == FI_LAYOUT_NHWC) {
-        const long nunits = (long)R * ph;
-        const bool vec = (C % 4 == 0) && ((uintptr_t)gimg % 16 == 0) && ((uintptr_t)grads % 16 == 0);
-        const int grid = grid_for(nunits, kWarpsPerBlock, 8);
-        if (vec && (C / 4) % 64 == 0)
-            crop_bwd_nhwc_kernel<2><<<grid, kWarpsPerBlock * 32, 0, stream>>>(grads, boxes, box_ind, src_row, nunits, B, H, W, ph, pw, C, gimg);
-        else if (vec)
-            crop_bwd_nhwc_kernel<1><<<grid, kWarpsPerBlock * 32, 0, stream>>>(grads, boxes, box_ind, src_row, nunits, B, H, W, ph, pw, C, gimg);
-        else
-            crop_bwd_nhwc_scalar_kernel<<<grid, kWarpsPerBlock * 32, 0, stream>>>(grads, boxes, box_ind, src_row, nunits, B, H, W, ph, pw, C, gimg);
-        return check_launch("fi_crop_and_resize_backward[nhwc]");
-    }
+    if (image_layout == FI_LAYOUT_NHWC) return fi_scatter_backward_nhwc(grads, boxes, box_ind, src_row, R, B, H, W, ph, pw, C, gimg, stream);
     if (image_layout == FI_LAYOUT_NCHW) {
         if (ph <= kNchwMaxTaps && pw <= kNchwMaxTaps) {
             dim3 grid(R, ceil_div(C, kNchwChunk));

@@ -93,6 +93,23 @@ int fi_crop_and_resize_backward(const float *grads, int grads_layout, const floa
                                 int crop_height, int crop_width, int depth, float *grads_image, int image_layout,
                                 int accumulate, cudaStream_t stream);
 
+/* Several crop sets that were taken from the SAME feature map (e.g. the 7x7 and the 14x14 crops of one level,
+ * lib/sub_module.py:555-572), back-propagated in ONE pass that writes grads_image exactly once.  NHWC only.
+ *   grads    [rows,crop_h,crop_w,depth]: gradient of crop r is row src_row[r] (row r when src_row is NULL)
+ *   grads2   NULL, or a second gradient for the same crops in compact row order (row r), added to the first
+ * When every set has crop_h, crop_w <= 16 and depth % 128 == 0 the result is deterministic and bit-identical
+ * to the reference's serial CPU backward (crop_and_resize.c:157-252); other shapes use vector reductions. */
+typedef struct fi_crop_set {
+    const float *grads;
+    const float *grads2;
+    const float *boxes;   /* [num_boxes,4] */
+    const int *box_ind;   /* [num_boxes]   */
+    const int *src_row;   /* [num_boxes] or NULL */
+    int num_boxes, crop_height, crop_width;
+} fi_crop_set;
+int fi_crop_and_resize_backward_multi(const fi_crop_set *sets, int num_sets, int batch, int image_height, int image_width,
+                                      int depth, float *grads_image, int accumulate, cudaStream_t stream);
+
 /* Integer taps of every sample, taps[num_boxes,crop_h,crop_w,5] = (y_lo,y_hi,x_lo,x_hi,inside): the "RoI
  * indices" the parity bar requires bit-exact (crop_and_resize_kernel.cu:40-70). */
 int fi_crop_taps(const float *boxes, int num_boxes, int image_height, int image_width, int crop_height,
