@@ -136,6 +136,8 @@ class Step(object):
         self.host["big_feat"] = [torch.rand(split.big_cnt[i], FEAT, generator=g) for i in range(3)]
         self.host["g_pooled"] = torch.randn(B * R, DEPTH, 7, 7, generator=g).contiguous(memory_format=torch.channels_last)
         self.host["g_mask"] = torch.randn(B * R, DEPTH, 14, 14, generator=g).contiguous(memory_format=torch.channels_last)
+        self.host["g_small"] = [torch.randn(split.small_cnt[i], DEPTH, 14, 14, generator=g).contiguous(memory_format=torch.channels_last)
+                                for i in range(3)]           # gradient the critic sends back into the compact 14x14 crops
         self.host["g_big"] = [torch.randn(split.big_cnt[i], DEPTH, 14, 14, generator=g).contiguous(memory_format=torch.channels_last)
                               for i in range(3)]
         self.h2d_bytes = 0
@@ -169,8 +171,8 @@ class Step(object):
         small_f = [t.requires_grad_() for t in inp["small_feat"]]
         big_f = inp["big_feat"]
         split = fi.split_levels(fi.roi_level(rois, cfg.DATA.IMAGE_SHAPE, cfg.ROIS.ASSIGN_ANCHOR_BASE))
-        pooled_out = torch.zeros((total, DEPTH, 7, 7), device=self.dev).contiguous(memory_format=torch.channels_last)
-        mask_out = torch.zeros((total, DEPTH, 14, 14), device=self.dev).contiguous(memory_format=torch.channels_last)
+        pooled_out = torch.empty((total, DEPTH, 7, 7), device=self.dev, memory_format=torch.channels_last)
+        mask_out = torch.empty((total, DEPTH, 14, 14), device=self.dev, memory_format=torch.channels_last)
         outs, grads = [], []
         bfeat, bcnt, sfeat, scnt = [], [], [], []
         for i in range(4):
@@ -185,14 +187,12 @@ class Step(object):
             s32 = split.small(i)
             sidx = s32.long()
             boxes, ind = rois_flat[sidx], (sidx // R).int()
-            pooled_out = fi.crop_and_resize(madeup[i], boxes, ind, 7, 7, out=pooled_out, dst_row=s32)
+            res = fi.crop_pair(madeup[i], boxes, ind, s32, pooled_out, 7, mask_out, 14, compact_b=(i < 3))
+            pooled_out, mask_out = res[0], res[1]
             if i < 3:
-                mf = fi.crop_and_resize(madeup[i], boxes, ind, 14, 14)
-                mask_out.index_copy_(0, sidx, mf)
+                outs.append(res[2]); grads.append(inp["g_small"][i])        # compact 14x14 crop -> critic (stock conv, not timed)
                 f, c = fi.assign_feat2cls(gt_flat[sidx], small_f[i], NCLS)
                 sfeat.append(f); scnt.append(c)
-            else:
-                mask_out = fi.crop_and_resize(madeup[i], boxes, ind, 14, 14, out=mask_out, dst_row=s32)
         feat_in = [torch.stack(bfeat)[None].detach(), torch.stack(bcnt)[None], torch.stack(sfeat)[None], torch.stack(scnt)[None], None, None]
         loss = self.loss_mod(feat_in).sum()
         torch.autograd.backward([loss, pooled_out, mask_out] + outs, [torch.ones_like(loss), inp["g_pooled"], inp["g_mask"]] + grads)

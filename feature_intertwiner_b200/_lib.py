@@ -28,8 +28,11 @@ SIGNATURES = {
     "ROIPoolBackwardLaucher": (_I, [_P, _F, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "_nms": (None, [_I, _P, _P, _F]),
     "fi_crop_and_resize_forward": (_I, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _I, _P]),
+    "fi_crop_and_resize_forward_dual": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P]),
     "fi_crop_and_resize_backward": (_I, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P]),
-    "fi_crop_and_resize_backward_multi": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P]),
+    "fi_crop_and_resize_backward_multi": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _I, _P]),
+    "fi_set_deterministic": (_I, [_I]),
+    "fi_get_deterministic": (_I, []),
     "fi_crop_taps": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "fi_roi_level": (_I, [_P, _I, _F, _F, _P, _P]),
     "fi_split_levels": (_I, [_P, _I, _P, _P, _P, _P, _P, _P]),

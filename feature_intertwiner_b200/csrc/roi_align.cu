@@ -64,7 +64,7 @@ template <int U>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) crop_fwd_nhwc_kernel(const float *__restrict__ image, const float *__restrict__ boxes,
                                                                            const int *__restrict__ box_ind, const int *__restrict__ dst_row,
                                                                            long nunits, int slabs, int B, int H, int W, int ph, int pw, int C,
-                                                                           float extrap, float *__restrict__ crops) {
+                                                                           float extrap, float *__restrict__ crops, float *__restrict__ crops2) {
     const int lane = threadIdx.x & 31;
     const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
@@ -76,13 +76,17 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) crop_fwd_nhwc_kernel(cons
         const long orow = dst_row ? (long)dst_row[r] : (long)r;
         const int coff = slab * 128 + lane * 4;
         float *out = crops + ((orow * ph + i) * (long)pw) * C + coff;
+        float *out2 = crops2 ? crops2 + (((long)r * ph + i) * (long)pw) * C + coff : nullptr;   // optional compact copy (row r)
         const bool bad = (b < 0 || b >= B);     // reference leaves such rows at their zero fill (crop_and_resize_kernel.cu:34-38)
         const float y1 = boxes[4 * r + 0], x1 = boxes[4 * r + 1], y2 = boxes[4 * r + 2], x2 = boxes[4 * r + 3];
         const AxisTap ty = axis_sample(y1, y2, axis_step(y1, y2, H, ph), i, H, ph);
         if (bad || !ty.inside) {
             const float v = bad ? 0.f : extrap;
             const float4 v4 = make_float4(v, v, v, v);
-            for (int j = 0; j < pw; ++j) st_stream4(out + (long)j * C, v4);
+            for (int j = 0; j < pw; ++j) {
+                st_stream4(out + (long)j * C, v4);
+                if (out2) st_stream4(out2 + (long)j * C, v4);
+            }
             continue;
         }
         const float sx = axis_step(x1, x2, W, pw);
@@ -114,6 +118,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) crop_fwd_nhwc_kernel(cons
                         float4 v = lerp_rn(top, bot, ty.frac);                   // :106
                         if (!(pk[k] & (1 << 30))) v = make_float4(extrap, extrap, extrap, extrap);
                         st_stream4(out + (long)(jb + j) * C, v);
+                        if (out2) st_stream4(out2 + (long)(jb + j) * C, v);
                     }
                 }
             }
@@ -179,17 +184,19 @@ __device__ __forceinline__ float4 f4_scale(float4 a, float w) {
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
-template <int VPL>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) crop_bwd_nhwc_kernel(const float *__restrict__ grads, const float *__restrict__ boxes,
-                                                                           const int *__restrict__ box_ind, const int *__restrict__ src_row,
-                                                                           long nunits, int B, int H, int W, int ph, int pw, int C,
-                                                                           float *__restrict__ gimg) {
+// unit = (box r, crop row i, 128-channel slab); gradient loads of a batch of U samples are issued together
+template <int U>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) crop_bwd_nhwc_kernel(const float *__restrict__ grads, const float *__restrict__ grads2,
+                                                                           const float *__restrict__ boxes, const int *__restrict__ box_ind,
+                                                                           const int *__restrict__ src_row, long nunits, int slabs, int B, int H,
+                                                                           int W, int ph, int pw, int C, float *__restrict__ gimg) {
     const int lane = threadIdx.x & 31;
     const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
-    const int C4 = C >> 2;
     for (long u = warp; u < nunits; u += nwarps) {
-        const int r = (int)(u / ph), i = (int)(u - (long)r * ph);
+        const int slab = (int)(u % slabs);
+        const long q = u / slabs;
+        const int r = (int)(q / ph), i = (int)(q - (long)r * ph);
         const int b = box_ind[r];
         if (b < 0 || b >= B) continue;
         const float y1 = boxes[4 * r + 0], x1 = boxes[4 * r + 1], y2 = boxes[4 * r + 2], x2 = boxes[4 * r + 3];
@@ -198,61 +205,55 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) crop_bwd_nhwc_kernel(cons
         const float sx = axis_step(x1, x2, W, pw);
         const float wy_hi = ty.frac, wy_lo = __fsub_rn(1.f, ty.frac);            // crop_and_resize.c:241,245
         const long grow = src_row ? (long)src_row[r] : (long)r;
-        const float *g = grads + ((grow * ph + i) * (long)pw) * C;
-        float *rowT = gimg + ((long)b * H + ty.lo) * (long)W * C;
-        float *rowB = gimg + ((long)b * H + ty.hi) * (long)W * C;
-        for (int cv0 = 0; cv0 < C4; cv0 += 32 * VPL) {
-            float4 Lt[VPL], Lb[VPL], Rt[VPL], Rb[VPL];
+        const int coff = slab * 128 + lane * 4;
+        const float *g = grads + ((grow * ph + i) * (long)pw) * C + coff;
+        const float *g2 = grads2 ? grads2 + (((long)r * ph + i) * (long)pw) * C + coff : nullptr;
+        float *rowT = gimg + ((long)b * H + ty.lo) * (long)W * C + coff;
+        float *rowB = gimg + ((long)b * H + ty.hi) * (long)W * C + coff;
+        float4 Lt = f4_zero(), Lb = f4_zero(), Rt = f4_zero(), Rb = f4_zero();
+        int cur_lo = -1, cur_hi = -1;
+        for (int jb = 0; jb < pw; jb += 32) {
+            const AxisTap mine = axis_sample(x1, x2, sx, jb + lane, W, pw);
+            const int jn = min(32, pw - jb);
+            for (int j0 = 0; j0 < jn; j0 += U) {
+                float4 gv[U];
 #pragma unroll
-            for (int v = 0; v < VPL; ++v) { Lt[v] = f4_zero(); Lb[v] = f4_zero(); Rt[v] = f4_zero(); Rb[v] = f4_zero(); }
-            int cur_lo = -1, cur_hi = -1;
-            AxisTap mine;
-            for (int j = 0; j < pw; ++j) {
-                if ((j & 31) == 0) mine = axis_sample(x1, x2, sx, j + lane, W, pw);
-                const AxisTap tx = shfl_tap(mine, j & 31);
-                if (!tx.inside) continue;
-                if (!(tx.lo == cur_lo && tx.hi == cur_hi)) {
-                    if (cur_lo >= 0) {
-                        const bool slide = (tx.lo == cur_hi) && (tx.hi != cur_hi);
+                for (int k = 0; k < U; ++k) {
+                    const int j = jb + min(j0 + k, jn - 1);
+                    gv[k] = __ldcs(reinterpret_cast<const float4 *>(g + (long)j * C));
+                    if (g2) gv[k] = f4_add(gv[k], __ldcs(reinterpret_cast<const float4 *>(g2 + (long)j * C)));
+                }
 #pragma unroll
-                        for (int v = 0; v < VPL; ++v) {
-                            const int cv = cv0 + v * 32 + lane;
-                            if (cv >= C4) continue;
-                            red_add(rowT + (long)cur_lo * C + cv * 4, Lt[v]);
-                            red_add(rowB + (long)cur_lo * C + cv * 4, Lb[v]);
-                            if (slide) { Lt[v] = Rt[v]; Lb[v] = Rb[v]; }     // old right column becomes the new left one
+                for (int k = 0; k < U; ++k) {
+                    if (j0 + k >= jn) break;
+                    const AxisTap tx = shfl_tap(mine, j0 + k);
+                    if (!tx.inside) continue;
+                    if (!(tx.lo == cur_lo && tx.hi == cur_hi)) {
+                        if (cur_lo >= 0) {
+                            red_add(rowT + (long)cur_lo * C, Lt);
+                            red_add(rowB + (long)cur_lo * C, Lb);
+                            if ((tx.lo == cur_hi) && (tx.hi != cur_hi)) { Lt = Rt; Lb = Rb; }     // old right column becomes the new left one
                             else {
-                                red_add(rowT + (long)cur_hi * C + cv * 4, Rt[v]);
-                                red_add(rowB + (long)cur_hi * C + cv * 4, Rb[v]);
-                                Lt[v] = f4_zero(); Lb[v] = f4_zero();
+                                red_add(rowT + (long)cur_hi * C, Rt);
+                                red_add(rowB + (long)cur_hi * C, Rb);
+                                Lt = f4_zero(); Lb = f4_zero();
                             }
-                            Rt[v] = f4_zero(); Rb[v] = f4_zero();
+                            Rt = f4_zero(); Rb = f4_zero();
                         }
+                        cur_lo = tx.lo; cur_hi = tx.hi;
                     }
-                    cur_lo = tx.lo; cur_hi = tx.hi;
-                }
-                const float wx_hi = tx.frac, wx_lo = __fsub_rn(1.f, tx.frac);
-#pragma unroll
-                for (int v = 0; v < VPL; ++v) {
-                    const int cv = cv0 + v * 32 + lane;
-                    if (cv >= C4) continue;
-                    const float4 gv = __ldcs(reinterpret_cast<const float4 *>(g + (long)j * C) + cv);
-                    const float4 dtop = f4_scale(gv, wy_lo), dbot = f4_scale(gv, wy_hi);
-                    Lt[v] = f4_add(Lt[v], f4_scale(dtop, wx_lo)); Rt[v] = f4_add(Rt[v], f4_scale(dtop, wx_hi));
-                    Lb[v] = f4_add(Lb[v], f4_scale(dbot, wx_lo)); Rb[v] = f4_add(Rb[v], f4_scale(dbot, wx_hi));
+                    const float wx_hi = tx.frac, wx_lo = __fsub_rn(1.f, tx.frac);
+                    const float4 dtop = f4_scale(gv[k], wy_lo), dbot = f4_scale(gv[k], wy_hi);
+                    Lt = f4_add(Lt, f4_scale(dtop, wx_lo)); Rt = f4_add(Rt, f4_scale(dtop, wx_hi));
+                    Lb = f4_add(Lb, f4_scale(dbot, wx_lo)); Rb = f4_add(Rb, f4_scale(dbot, wx_hi));
                 }
             }
-            if (cur_lo >= 0) {
-#pragma unroll
-                for (int v = 0; v < VPL; ++v) {
-                    const int cv = cv0 + v * 32 + lane;
-                    if (cv >= C4) continue;
-                    red_add(rowT + (long)cur_lo * C + cv * 4, Lt[v]);
-                    red_add(rowB + (long)cur_lo * C + cv * 4, Lb[v]);
-                    red_add(rowT + (long)cur_hi * C + cv * 4, Rt[v]);
-                    red_add(rowB + (long)cur_hi * C + cv * 4, Rb[v]);
-                }
-            }
+        }
+        if (cur_lo >= 0) {
+            red_add(rowT + (long)cur_lo * C, Lt);
+            red_add(rowB + (long)cur_lo * C, Lb);
+            red_add(rowT + (long)cur_hi * C, Rt);
+            red_add(rowB + (long)cur_hi * C, Rb);
         }
     }
 }
@@ -463,19 +464,26 @@ static int check_common(const void *a, const void *boxes, const void *box_ind, c
 using namespace fi;
 
 // NHWC scatter backward (reduction kernels); gimg must already hold the values to accumulate onto.
-int fi_scatter_backward_nhwc(const float *grads, const float *boxes, const int *box_ind, const int *src_row, int R, int B, int H, int W, int ph,
-                             int pw, int C, float *gimg, cudaStream_t stream) {
+int fi_scatter_backward_nhwc(const float *grads, const float *grads2, const float *boxes, const int *box_ind, const int *src_row, int R, int B,
+                             int H, int W, int ph, int pw, int C, float *gimg, cudaStream_t stream) {
     if (R == 0) return ok();
+    const bool vec = (C % 128 == 0) && ((uintptr_t)gimg % 16 == 0) && ((uintptr_t)grads % 16 == 0) && ((uintptr_t)grads2 % 16 == 0);
+    if (vec) {
+        const int slabs = C / 128;
+        const long nunits = (long)R * ph * slabs;
+        crop_bwd_nhwc_kernel<4><<<grid_for(nunits, kWarpsPerBlock, 8), kWarpsPerBlock * 32, 0, stream>>>(grads, grads2, boxes, box_ind, src_row, nunits,
+                                                                                                       slabs, B, H, W, ph, pw, C, gimg);
+        return check_launch("fi_crop_and_resize_backward[nhwc scatter]");
+    }
     const long nunits = (long)R * ph;
-    const bool vec = (C % 4 == 0) && ((uintptr_t)gimg % 16 == 0) && ((uintptr_t)grads % 16 == 0);
     const int grid = grid_for(nunits, kWarpsPerBlock, 8);
-    if (vec && (C / 4) % 64 == 0)
-        crop_bwd_nhwc_kernel<2><<<grid, kWarpsPerBlock * 32, 0, stream>>>(grads, boxes, box_ind, src_row, nunits, B, H, W, ph, pw, C, gimg);
-    else if (vec)
-        crop_bwd_nhwc_kernel<1><<<grid, kWarpsPerBlock * 32, 0, stream>>>(grads, boxes, box_ind, src_row, nunits, B, H, W, ph, pw, C, gimg);
-    else
-        crop_bwd_nhwc_scalar_kernel<<<grid, kWarpsPerBlock * 32, 0, stream>>>(grads, boxes, box_ind, src_row, nunits, B, H, W, ph, pw, C, gimg);
-    return check_launch("fi_crop_and_resize_backward[nhwc scatter]");
+    crop_bwd_nhwc_scalar_kernel<<<grid, kWarpsPerBlock * 32, 0, stream>>>(grads, boxes, box_ind, src_row, nunits, B, H, W, ph, pw, C, gimg);
+    if (int e = check_launch("fi_crop_and_resize_backward[nhwc scatter]")) return e;
+    if (grads2) {
+        crop_bwd_nhwc_scalar_kernel<<<grid, kWarpsPerBlock * 32, 0, stream>>>(grads2, boxes, box_ind, nullptr, nunits, B, H, W, ph, pw, C, gimg);
+        return check_launch("fi_crop_and_resize_backward[nhwc scatter 2]");
+    }
+    return ok();
 }
 
 FI_API int fi_crop_taps(const float *boxes, int num_boxes, int H, int W, int ph, int pw, int *taps, cudaStream_t stream) {
@@ -487,9 +495,8 @@ FI_API int fi_crop_taps(const float *boxes, int num_boxes, int H, int W, int ph,
     return check_launch("fi_crop_taps");
 }
 
-FI_API int fi_crop_and_resize_forward(const float *image, int image_layout, const float *boxes, const int *box_ind,
-                                      const int *dst_row, int R, int B, int H, int W, int ph, int pw, int C, float extrap,
-                                      float *crops, int crops_layout, cudaStream_t stream) {
+static int forward_impl(const float *image, int image_layout, const float *boxes, const int *box_ind, const int *dst_row, int R, int B, int H,
+                        int W, int ph, int pw, int C, float extrap, float *crops, int crops_layout, float *crops2, cudaStream_t stream) {
     if (int e = check_common(image, boxes, box_ind, crops, R, B, H, W, ph, pw, C)) return e;
     if (R == 0) return ok();
     if (image_layout != crops_layout) {
@@ -497,22 +504,24 @@ FI_API int fi_crop_and_resize_forward(const float *image, int image_layout, cons
         return FI_ERR_UNSUPPORTED;
     }
     if (image_layout == FI_LAYOUT_NHWC) {
-        const bool vec = (C % 128 == 0) && (W <= 32768) && ((uintptr_t)image % 16 == 0) && ((uintptr_t)crops % 16 == 0);
+        const bool vec = (C % 128 == 0) && (W <= 32768) && ((uintptr_t)image % 16 == 0) && ((uintptr_t)crops % 16 == 0) && ((uintptr_t)crops2 % 16 == 0);
         if (vec) {
             const int slabs = C / 128;
             const long nunits = (long)R * ph * slabs;    // one warp per (crop row, 128-channel slab)
             const int grid = grid_for(nunits, kWarpsPerBlock, 8);
             if (pw % 4 == 0 || pw > 12)
-                crop_fwd_nhwc_kernel<4><<<grid, kWarpsPerBlock * 32, 0, stream>>>(image, boxes, box_ind, dst_row, nunits, slabs, B, H, W, ph, pw, C, extrap, crops);
+                crop_fwd_nhwc_kernel<4><<<grid, kWarpsPerBlock * 32, 0, stream>>>(image, boxes, box_ind, dst_row, nunits, slabs, B, H, W, ph, pw, C, extrap, crops, crops2);
             else
-                crop_fwd_nhwc_kernel<2><<<grid, kWarpsPerBlock * 32, 0, stream>>>(image, boxes, box_ind, dst_row, nunits, slabs, B, H, W, ph, pw, C, extrap, crops);
+                crop_fwd_nhwc_kernel<2><<<grid, kWarpsPerBlock * 32, 0, stream>>>(image, boxes, box_ind, dst_row, nunits, slabs, B, H, W, ph, pw, C, extrap, crops, crops2);
         } else {
+            if (crops2) { set_error(FI_ERR_UNSUPPORTED, "fi_crop_and_resize_forward_dual needs depth %% 128 == 0 and 16-byte aligned tensors"); return FI_ERR_UNSUPPORTED; }
             const long nunits = (long)R * ph;
             crop_fwd_nhwc_scalar_kernel<<<grid_for(nunits, kWarpsPerBlock, 8), kWarpsPerBlock * 32, 0, stream>>>(image, boxes, box_ind, dst_row, nunits, B, H, W, ph, pw, C, extrap, crops);
         }
         return check_launch("fi_crop_and_resize_forward[nhwc]");
     }
     if (image_layout == FI_LAYOUT_NCHW) {
+        if (crops2) { set_error(FI_ERR_UNSUPPORTED, "fi_crop_and_resize_forward_dual is NHWC only"); return FI_ERR_UNSUPPORTED; }
         if (ph <= kNchwMaxTaps && pw <= kNchwMaxTaps) {
             dim3 grid(R, ceil_div(C, kNchwChunk));
             crop_fwd_nchw_kernel<<<grid, 256, 0, stream>>>(image, boxes, box_ind, dst_row, B, H, W, ph, pw, C, extrap, crops);
@@ -527,17 +536,29 @@ FI_API int fi_crop_and_resize_forward(const float *image, int image_layout, cons
     return FI_ERR_INVALID;
 }
 
+FI_API int fi_crop_and_resize_forward(const float *image, int image_layout, const float *boxes, const int *box_ind,
+                                      const int *dst_row, int R, int B, int H, int W, int ph, int pw, int C, float extrap,
+                                      float *crops, int crops_layout, cudaStream_t stream) {
+    return forward_impl(image, image_layout, boxes, box_ind, dst_row, R, B, H, W, ph, pw, C, extrap, crops, crops_layout, nullptr, stream);
+}
+
+FI_API int fi_crop_and_resize_forward_dual(const float *image, const float *boxes, const int *box_ind, const int *dst_row, int R, int B, int H,
+                                           int W, int ph, int pw, int C, float extrap, float *crops, float *crops_compact, cudaStream_t stream) {
+    FI_REQUIRE(R == 0 || (dst_row && crops_compact), "fi_crop_and_resize_forward_dual: dst_row and crops_compact are required");
+    return forward_impl(image, FI_LAYOUT_NHWC, boxes, box_ind, dst_row, R, B, H, W, ph, pw, C, extrap, crops, FI_LAYOUT_NHWC, crops_compact, stream);
+}
+
 FI_API int fi_crop_and_resize_backward(const float *grads, int grads_layout, const float *boxes, const int *box_ind,
                                        const int *src_row, int R, int B, int H, int W, int ph, int pw, int C,
                                        float *gimg, int image_layout, int accumulate, cudaStream_t stream) {
     FI_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && gimg, "fi_crop_and_resize_backward: bad image");
     if (image_layout == FI_LAYOUT_NHWC && grads_layout == FI_LAYOUT_NHWC) {
-        // gather (write-once) path when the shape qualifies, reduction kernels otherwise -- roi_align_bwd.cu
+        // reduction kernels, or the deterministic write-once gather when fi_set_deterministic(1) -- roi_align_bwd.cu
         fi_crop_set one;
         one.grads = grads; one.grads2 = nullptr; one.boxes = boxes; one.box_ind = box_ind; one.src_row = src_row;
         one.num_boxes = R; one.crop_height = ph; one.crop_width = pw;
         FI_REQUIRE(R >= 0 && ph > 0 && pw > 0, "fi_crop_and_resize_backward: bad sizes");
-        return fi_crop_and_resize_backward_multi(&one, 1, B, H, W, C, gimg, accumulate, stream);
+        return fi_crop_and_resize_backward_multi(&one, 1, B, H, W, C, gimg, accumulate, fi_get_deterministic(), stream);
     }
     if (!accumulate) {
         cudaError_t e = cudaMemsetAsync(gimg, 0, sizeof(float) * (size_t)B * C * H * W, stream);
@@ -549,7 +570,7 @@ FI_API int fi_crop_and_resize_backward(const float *grads, int grads_layout, con
         set_error(FI_ERR_UNSUPPORTED, "fi_crop_and_resize_backward: mixed layouts (grads %d, image %d)", grads_layout, image_layout);
         return FI_ERR_UNSUPPORTED;
     }
-    if (image_layout == FI_LAYOUT_NHWC) return fi_scatter_backward_nhwc(grads, boxes, box_ind, src_row, R, B, H, W, ph, pw, C, gimg, stream);
+    if (image_layout == FI_LAYOUT_NHWC) return fi_scatter_backward_nhwc(grads, nullptr, boxes, box_ind, src_row, R, B, H, W, ph, pw, C, gimg, stream);
     if (image_layout == FI_LAYOUT_NCHW) {
         if (ph <= kNchwMaxTaps && pw <= kNchwMaxTaps) {
             dim3 grid(R, ceil_div(C, kNchwChunk));

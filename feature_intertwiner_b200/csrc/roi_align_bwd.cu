@@ -1,5 +1,7 @@
 // RoIAlign backward as a GATHER: every pixel of the dense gradient map is computed by exactly one warp and
-// written exactly once.
+// written exactly once.  This is the DETERMINISTIC mode of the backward (fi_set_deterministic(1) or the
+// `deterministic` argument of fi_crop_and_resize_backward_multi); the default mode is the reduction kernel of
+// roi_align.cu, which is faster today on heavily overlapping RoIs ("backward: two formulations").
 //
 // The reference (crop_and_resize_kernel.cu:84-165) zero-fills the dense map and then issues 4 scalar
 // atomicAdds per crop element: memset + read-modify-write traffic on the map, contention where RoIs
@@ -41,6 +43,7 @@ struct SetDev {                        // one crop set as the tile kernel sees i
     const int *src_row;
     const TapEntry *taps;              // [R, 32]
     const int4 *bounds;                // [R] (ymin, ymax, xmin, xmax) of the tap footprint; ymin > ymax = empty
+    const int *range;                  // [B,2] first / last box index whose box_ind == b (first > last: none)
     int R, ph, pw;
 };
 
@@ -52,12 +55,13 @@ struct SetsDev {
 
 // ---- prep: one warp per box: tap table + footprint bounds --------------------------------------------
 __global__ void __launch_bounds__(256) bwd_prep_kernel(const float *__restrict__ boxes, const int *__restrict__ box_ind, int R, int B, int H,
-                                                      int W, int ph, int pw, TapEntry *__restrict__ taps, int4 *__restrict__ bounds) {
+                                                      int W, int ph, int pw, TapEntry *__restrict__ taps, int4 *__restrict__ bounds, int *__restrict__ range) {
     const int lane = threadIdx.x & 31;
     const int r = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (r >= R) return;
     const int b = box_ind[r];
     const bool bad = (b < 0 || b >= B);
+    if (!bad && lane == 0) { atomicMin(range + 2 * b, r); atomicMax(range + 2 * b + 1, r); }
     const float y1 = boxes[4 * r + 0], x1 = boxes[4 * r + 1], y2 = boxes[4 * r + 2], x2 = boxes[4 * r + 3];
     const bool is_y = lane < 16;
     const int k = is_y ? lane : lane - 16;
@@ -81,6 +85,11 @@ __global__ void __launch_bounds__(256) bwd_prep_kernel(const float *__restrict__
         const bool empty = (lo > hi) || (xlo > xhi);
         bounds[r] = empty ? make_int4(1, 0, 1, 0) : make_int4(lo, hi, xlo, xhi);
     }
+}
+
+__global__ void range_init_kernel(int *range, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) { range[2 * b] = 0x7fffffff; range[2 * b + 1] = -1; }
 }
 
 __device__ __forceinline__ float4 add_rn4(float4 a, float4 b) {
@@ -107,23 +116,75 @@ __device__ __forceinline__ void acc_add(float4 (&acc)[kTile], int x, float4 v) {
 
 // ---- tile kernel ---------------------------------------------------------------------------------------
 // grid (tiles_x, tiles_y, B * slabs), 256 threads: warp w = pixel row Y0 + w, lane = channel quad of the slab.
+//
+// A warp's work is an ORDERED stream of (sample -> this pixel row) contributions.  Walking it naively
+// (find a sample, load it, add it) leaves one 512 B load in flight per warp; the first version of this kernel
+// did that and ran 6x slower than the reduction kernels.  So the stream is split in two stages per warp:
+//   enumerate  lanes expand (crop rows touching y) x (crop columns touching the tile) of a box in parallel --
+//              candidate c -> (i, j) by find-nth-set-bit on the two ballot masks -- and append 32-byte
+//              descriptors (pointers, lerp weights, target columns) to a per-warp queue in shared memory;
+//   drain      the queue is consumed in order, 8 gradient loads in flight, then the ordered adds.
+struct __align__(16) Desc {
+    const float *g1, *g2;          // crop gradient(s) of the sample (slab offset not yet applied); g2 may be null
+    float fy, fx;
+    short xlo, xhi;                // target columns relative to the tile (may lie outside 0..7: skipped)
+    short top, bot;                // does the sample's top / bottom tap row equal this warp's pixel row?
+};
+constexpr int kQueue = 64;
+
+__device__ __forceinline__ void drain_queue(const Desc *queue, int qn, int coff, float4 (&acc)[kTile]) {
+    for (int t0 = 0; t0 < qn; t0 += 8) {
+        float4 gv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if (t0 + q < qn) {
+                const Desc &d = queue[t0 + q];
+                gv[q] = __ldg(reinterpret_cast<const float4 *>(d.g1 + coff));
+                if (d.g2) gv[q] = add_rn4(gv[q], __ldg(reinterpret_cast<const float4 *>(d.g2 + coff)));
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if (t0 + q < qn) {
+                const Desc &d = queue[t0 + q];
+                const float fy = d.fy, fx = d.fx;
+                const float wx_lo = __fsub_rn(1.f, fx);
+                if (d.top) {                                                      // TL, TR  (crop_and_resize.c:241-243)
+                    const float4 dtop = mul_rn4(__fsub_rn(1.f, fy), gv[q]);
+                    acc_add(acc, d.xlo, mul_rn4(wx_lo, dtop));
+                    acc_add(acc, d.xhi, mul_rn4(fx, dtop));
+                }
+                if (d.bot) {                                                      // BL, BR  (:245-247)
+                    const float4 dbot = mul_rn4(fy, gv[q]);
+                    acc_add(acc, d.xlo, mul_rn4(wx_lo, dbot));
+                    acc_add(acc, d.xhi, mul_rn4(fx, dbot));
+                }
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kTile * 32) bwd_tile_kernel(const SetsDev sets, int B, int H, int W, int C, int slabs, int accumulate,
                                                              float *__restrict__ gimg) {
     __shared__ int list[256];
     __shared__ int warp_hits[kTile];
     __shared__ int nlist;
+    __shared__ Desc queues[kTile][kQueue];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int b = blockIdx.z / slabs, slab = blockIdx.z - b * slabs;
     const int X0 = blockIdx.x * kTile, Y0 = blockIdx.y * kTile;
     const int y = Y0 + w;
     const int coff = slab * 128 + lane * 4;
+    Desc *queue = queues[w];
+    int qn = 0;
     float4 acc[kTile];
 #pragma unroll
     for (int x = 0; x < kTile; ++x) acc[x] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     for (int si = 0; si < sets.n; ++si) {
         const SetDev &S = sets.s[si];
-        for (int base = 0; base < S.R; base += 256) {
+        const int r_begin = S.range[2 * b] & ~255, r_end = S.range[2 * b + 1];   // boxes of image b live in [r_begin, r_end]
+        for (int base = r_begin; base <= r_end; base += 256) {
             // ---- ordered compaction of the boxes of this chunk whose footprint overlaps the tile
             const int r = base + threadIdx.x;
             bool hit = false;
@@ -152,58 +213,35 @@ __global__ void __launch_bounds__(kTile * 32) bwd_tile_kernel(const SetsDev sets
                     const unsigned xmask = __ballot_sync(0xffffffffu, lane >= 16 && ((e.lo >= X0 && e.lo < X0 + kTile) || (e.hi >= X0 && e.hi < X0 + kTile))) >> 16;
                     if (ymask == 0 || xmask == 0) continue;
                     const long grow = S.src_row ? (long)S.src_row[rr] : (long)rr;
-                    unsigned ym = ymask;
-                    while (ym) {
-                        const int i = __ffs(ym) - 1;
-                        ym &= ym - 1;
+                    const int nx = __popc(xmask), ncand = __popc(ymask) * nx;
+                    for (int c0 = 0; c0 < ncand; c0 += 32) {
+                        if (qn + 32 > kQueue) { __syncwarp(); drain_queue(queue, qn, coff, acc); qn = 0; __syncwarp(); }
+                        const int c = c0 + lane;
+                        const bool valid = c < ncand;
+                        const int ii = valid ? c / nx : 0, jj = valid ? c - ii * nx : 0;
+                        const int i = __fns(ymask, 0, ii + 1), j = __fns(xmask, 0, jj + 1);   // (i major, j minor): the CPU loop order
                         const int ylo = __shfl_sync(0xffffffffu, (int)e.lo, i), yhi = __shfl_sync(0xffffffffu, (int)e.hi, i);
                         const float fy = __shfl_sync(0xffffffffu, e.frac, i);
-                        const float wy_top = __fsub_rn(1.f, fy);                              // crop_and_resize.c:241
-                        const float *g1 = S.grads + ((grow * S.ph + i) * (long)S.pw) * C + coff;
-                        const float *g2 = S.grads2 ? S.grads2 + (((long)rr * S.ph + i) * (long)S.pw) * C + coff : nullptr;
-                        unsigned xm = xmask;
-                        while (xm) {
-                            // up to 4 samples of this crop row per batch: loads first, then the ordered adds
-                            int js[4];
-                            float4 gv[4];
-                            int nb = 0;
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                if (xm) { js[q] = __ffs(xm) - 1; xm &= xm - 1; nb = q + 1; } else js[q] = js[q > 0 ? q - 1 : 0];
-                            }
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                if (q < nb) {
-                                    gv[q] = __ldg(reinterpret_cast<const float4 *>(g1 + (long)js[q] * C));
-                                    if (g2) gv[q] = add_rn4(gv[q], __ldg(reinterpret_cast<const float4 *>(g2 + (long)js[q] * C)));
-                                }
-                            }
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                if (q < nb) {
-                                    const int j = js[q];
-                                    const int xlo = __shfl_sync(0xffffffffu, (int)e.lo, 16 + j) - X0, xhi = __shfl_sync(0xffffffffu, (int)e.hi, 16 + j) - X0;
-                                    const float fx = __shfl_sync(0xffffffffu, e.frac, 16 + j);
-                                    const float wx_lo = __fsub_rn(1.f, fx);
-                                    if (ylo == y) {                                           // TL, TR   (:242-243)
-                                        const float4 dtop = mul_rn4(wy_top, gv[q]);
-                                        acc_add(acc, xlo, mul_rn4(wx_lo, dtop));
-                                        acc_add(acc, xhi, mul_rn4(fx, dtop));
-                                    }
-                                    if (yhi == y) {                                           // BL, BR   (:245-247)
-                                        const float4 dbot = mul_rn4(fy, gv[q]);
-                                        acc_add(acc, xlo, mul_rn4(wx_lo, dbot));
-                                        acc_add(acc, xhi, mul_rn4(fx, dbot));
-                                    }
-                                }
-                            }
+                        const int xlo = __shfl_sync(0xffffffffu, (int)e.lo, 16 + j), xhi = __shfl_sync(0xffffffffu, (int)e.hi, 16 + j);
+                        const float fx = __shfl_sync(0xffffffffu, e.frac, 16 + j);
+                        if (valid) {
+                            Desc d;
+                            d.g1 = S.grads + (((grow * S.ph + i) * (long)S.pw) + j) * C;
+                            d.g2 = S.grads2 ? S.grads2 + ((((long)rr * S.ph + i) * (long)S.pw) + j) * C : nullptr;
+                            d.fy = fy; d.fx = fx;
+                            d.xlo = (short)(xlo - X0); d.xhi = (short)(xhi - X0);
+                            d.top = (ylo == y); d.bot = (yhi == y);
+                            queue[qn + (c - c0)] = d;
                         }
+                        qn += min(32, ncand - c0);
                     }
                 }
             }
             __syncthreads();           // the list is rebuilt by the next chunk
         }
     }
+    __syncwarp();
+    drain_queue(queue, qn, coff, acc);
     if (y < H) {
         float *dst = gimg + (((long)b * H + y) * (long)W + X0) * C + coff;
 #pragma unroll
@@ -211,7 +249,7 @@ __global__ void __launch_bounds__(kTile * 32) bwd_tile_kernel(const SetsDev sets
             if (X0 + x < W) {
                 float4 v = acc[x];
                 if (accumulate) v = add_rn4(*reinterpret_cast<const float4 *>(dst + (long)x * C), v);
-                *reinterpret_cast<float4 *>(dst + (long)x * C) = v;
+                __stcs(reinterpret_cast<float4 *>(dst + (long)x * C), v);
             }
         }
     }
@@ -230,10 +268,20 @@ static int gather_backward(const fi_crop_set *sets, int nsets, int B, int H, int
         const fi_crop_set &s = sets[i];
         if (s.crop_height > kMaxCrop || s.crop_width > kMaxCrop || s.crop_height < 1 || s.crop_width < 1) return FI_ERR_UNSUPPORTED;
         if (((uintptr_t)s.grads % 16) != 0 || ((uintptr_t)s.grads2 % 16) != 0) return FI_ERR_UNSUPPORTED;
-        bytes += (size_t)s.num_boxes * (32 * sizeof(TapEntry) + sizeof(int4));
+        bytes += (size_t)s.num_boxes * (32 * sizeof(TapEntry) + sizeof(int4)) + (size_t)B * 2 * sizeof(int) + 16;
     }
     char *ws = nullptr;
     if (bytes) {
+        static bool pool_ready = false;      // keep freed workspace cached in the stream-ordered pool across synchronisations
+        if (!pool_ready) {
+            int dev = 0;
+            cudaMemPool_t pool;
+            if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                unsigned long long keep = ~0ULL;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            pool_ready = true;
+        }
         cudaError_t e = cudaMallocAsync((void **)&ws, bytes, stream);
         if (e != cudaSuccess) { set_error(FI_ERR_CUDA, "crop_and_resize backward: workspace (%zu B): %s", bytes, cudaGetErrorString(e)); return FI_ERR_CUDA; }
     }
@@ -248,8 +296,10 @@ static int gather_backward(const fi_crop_set *sets, int nsets, int B, int H, int
         d.R = s.num_boxes; d.ph = s.crop_height; d.pw = s.crop_width;
         d.bounds = reinterpret_cast<const int4 *>(p); p += (size_t)s.num_boxes * sizeof(int4);
         d.taps = reinterpret_cast<const TapEntry *>(p); p += (size_t)s.num_boxes * 32 * sizeof(TapEntry);
+        d.range = reinterpret_cast<const int *>(p); p += ((size_t)B * 2 * sizeof(int) + 15) / 16 * 16;
+        range_init_kernel<<<ceil_div(B, 128), 128, 0, stream>>>(const_cast<int *>(d.range), B);
         bwd_prep_kernel<<<ceil_div(s.num_boxes, 8), 256, 0, stream>>>(s.boxes, s.box_ind, s.num_boxes, B, H, W, s.crop_height, s.crop_width,
-                                                                     const_cast<TapEntry *>(d.taps), const_cast<int4 *>(d.bounds));
+                                                                     const_cast<TapEntry *>(d.taps), const_cast<int4 *>(d.bounds), const_cast<int *>(d.range));
         if (int e = check_launch("crop_and_resize backward[prep]")) { if (ws) cudaFreeAsync(ws, stream); return e; }
     }
     const int slabs = C / 128;
@@ -261,36 +311,37 @@ static int gather_backward(const fi_crop_set *sets, int nsets, int B, int H, int
     return rc;
 }
 
-int fi_scatter_backward_nhwc(const float *grads, const float *boxes, const int *box_ind, const int *src_row, int R, int B, int H, int W, int ph,
-                             int pw, int C, float *gimg, cudaStream_t stream);   // roi_align.cu
+int fi_scatter_backward_nhwc(const float *grads, const float *grads2, const float *boxes, const int *box_ind, const int *src_row, int R, int B,
+                             int H, int W, int ph, int pw, int C, float *gimg, cudaStream_t stream);   // roi_align.cu
+
+static int g_deterministic = 0;
+FI_API int fi_set_deterministic(int on) { const int old = g_deterministic; g_deterministic = on ? 1 : 0; return old; }
+FI_API int fi_get_deterministic(void) { return g_deterministic; }
 
 FI_API int fi_crop_and_resize_backward_multi(const fi_crop_set *sets, int num_sets, int batch, int image_height, int image_width, int depth,
-                                             float *grads_image, int accumulate, cudaStream_t stream) {
+                                             float *grads_image, int accumulate, int deterministic, cudaStream_t stream) {
     FI_REQUIRE(sets && num_sets >= 1 && batch > 0 && image_height > 0 && image_width > 0 && depth > 0 && grads_image, "fi_crop_and_resize_backward_multi: bad arguments");
     for (int i = 0; i < num_sets; ++i) {
         const fi_crop_set &s = sets[i];
         FI_REQUIRE(s.num_boxes >= 0 && s.crop_height > 0 && s.crop_width > 0, "fi_crop_and_resize_backward_multi: bad set %d", i);
         FI_REQUIRE(s.num_boxes == 0 || (s.grads && s.boxes && s.box_ind), "fi_crop_and_resize_backward_multi: null pointer in set %d", i);
     }
-    const char *force = getenv("FI_BWD");      // "scatter" forces the reduction kernels (A/B measurements)
-    int rc = (force && force[0] == 's') ? FI_ERR_UNSUPPORTED : gather_backward(sets, num_sets, batch, image_height, image_width, depth, grads_image, accumulate, stream);
-    if (rc != FI_ERR_UNSUPPORTED) return rc;
-    // fallback: zero-fill + scatter, set by set
+    if (deterministic) {
+        const int rc = gather_backward(sets, num_sets, batch, image_height, image_width, depth, grads_image, accumulate, stream);
+        if (rc != FI_ERR_UNSUPPORTED) return rc;
+        set_error(FI_ERR_UNSUPPORTED, "deterministic RoIAlign backward needs depth %% 128 == 0, crops <= 16x16, 16-byte aligned NHWC tensors");
+        return FI_ERR_UNSUPPORTED;
+    }
+    // one zero-fill for all sets, then vector reductions set by set
     if (!accumulate) {
         cudaError_t e = cudaMemsetAsync(grads_image, 0, sizeof(float) * (size_t)batch * depth * image_height * image_width, stream);
         if (e != cudaSuccess) { set_error(FI_ERR_CUDA, "fi_crop_and_resize_backward_multi: memset: %s", cudaGetErrorString(e)); return FI_ERR_CUDA; }
     }
     for (int i = 0; i < num_sets; ++i) {
         const fi_crop_set &s = sets[i];
-        if (s.num_boxes == 0) continue;
-        rc = fi_scatter_backward_nhwc(s.grads, s.boxes, s.box_ind, s.src_row, s.num_boxes, batch, image_height, image_width, s.crop_height,
-                                      s.crop_width, depth, grads_image, stream);
+        const int rc = fi_scatter_backward_nhwc(s.grads, s.grads2, s.boxes, s.box_ind, s.src_row, s.num_boxes, batch, image_height, image_width,
+                                                s.crop_height, s.crop_width, depth, grads_image, stream);
         if (rc) return rc;
-        if (s.grads2) {
-            rc = fi_scatter_backward_nhwc(s.grads2, s.boxes, s.box_ind, nullptr, s.num_boxes, batch, image_height, image_width, s.crop_height,
-                                          s.crop_width, depth, grads_image, stream);
-            if (rc) return rc;
-        }
     }
     return ok();
 }

@@ -21,7 +21,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib
-from .roi_align import crop_and_resize
+from .roi_align import crop_and_resize, crop_pair
 from .roi_pool import RoIPoolFunction
 
 EPS = 1e-20
@@ -185,8 +185,9 @@ class Dev(nn.Module):
         split = split_levels(roi_level(rois, self.image_shape, base))          # steps 1+2a: no per-level syncs below
         fmt = torch.channels_last if x[0].is_contiguous(memory_format=torch.channels_last) and not x[0].is_contiguous() \
             else torch.contiguous_format
-        pooled_out = torch.zeros((total_box, self.depth, self.pool_size, self.pool_size), device=dev).contiguous(memory_format=fmt)
-        mask_out = torch.zeros((total_box, self.depth, self.mask_pool_size, self.mask_pool_size), device=dev).contiguous(memory_format=fmt)
+        # every RoI is assigned to exactly one level, so every row below is written by a crop: no zero fill (sub_module.py:650,656)
+        pooled_out = torch.empty((total_box, self.depth, self.pool_size, self.pool_size), device=dev, memory_format=fmt)
+        mask_out = torch.empty((total_box, self.depth, self.mask_pool_size, self.mask_pool_size), device=dev, memory_format=fmt)
         big_feat, big_cnt, small_feat, small_cnt, big_loss = [], [], [], [], []
         small_output_all = torch.zeros(total_box, 1024, device=dev)
         small_gt_all = torch.zeros(total_box, device=dev)
@@ -227,12 +228,24 @@ class Dev(nn.Module):
             sidx = sidx32.long()
             small_boxes = rois_flat[sidx]
             box_ind = (sidx // R).int()
-            feat_maps = self.upsample[i if cfg.DEV.MULTI_UPSAMPLER else 0](curr_feat_maps)
-            # 7x7 crops land directly in their final (image, roi) row -- fused _reshape_result
-            pooled_out = self._roi_op(i, self.pool_size, feat_maps, small_boxes, box_ind, out=pooled_out, dst_row=sidx32)
-            if use_meta and not cfg.DEV.BASELINE:
-                mask_and_feat = self._roi_op(i, self.mask_pool_size, feat_maps, small_boxes, box_ind)
-                mask_out.index_copy_(0, sidx, mask_and_feat)    # the critic needs the compact crop too, so no fused scatter here
+            feat_maps = self.upsample[i if cfg.DEV.MULTI_UPSAMPLER else 0](curr_feat_maps).contiguous(memory_format=fmt)
+            want_critic = use_meta and not cfg.DEV.BASELINE
+            fused = self.roi_type == 'roi_align' and fmt == torch.channels_last and feat_maps.size(1) % 128 == 0
+            if fused:
+                # both crops of this level in one autograd node: 7x7 and 14x14 land directly in their final (image, roi)
+                # rows (fused _reshape_result), the 14x14 one is also emitted compact for the critic, ONE backward pass
+                res = crop_pair(feat_maps, small_boxes, box_ind, sidx32, pooled_out, self.pool_size, mask_out, self.mask_pool_size,
+                                compact_b=want_critic)
+                pooled_out, mask_out = res[0], res[1]
+                mask_and_feat = res[2] if want_critic else None
+            else:
+                pooled_out = self._roi_op(i, self.pool_size, feat_maps, small_boxes, box_ind, out=pooled_out, dst_row=sidx32)
+                if want_critic:
+                    mask_and_feat = self._roi_op(i, self.mask_pool_size, feat_maps, small_boxes, box_ind)
+                    mask_out.index_copy_(0, sidx, mask_and_feat)
+                else:
+                    mask_out = self._roi_op(i, self.mask_pool_size, feat_maps, small_boxes, box_ind, out=mask_out, dst_row=sidx32)
+            if want_critic:
                 small_output = self._critic(mask_and_feat)
                 n = n_small
                 small_output_all[small_out_cnt:small_out_cnt + n, :] = small_output.view(n, -1)
@@ -244,8 +257,6 @@ class Dev(nn.Module):
                 else:
                     small_gt_all[small_out_cnt:small_out_cnt + n] = 1
                 small_out_cnt += n
-            else:
-                mask_out = self._roi_op(i, self.mask_pool_size, feat_maps, small_boxes, box_ind, out=mask_out, dst_row=sidx32)
 
         if use_stats:
             bf = torch.stack(big_feat).unsqueeze(dim=0)

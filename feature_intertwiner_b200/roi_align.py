@@ -57,10 +57,12 @@ def algorithmic_bytes(rec):
     forward  = 4*C*R*P^2 (write crops) + 4*C*U (each touched feature pixel read once) + 20*R (boxes, box_ind)
     backward = 4*C*R*P^2 (read grads)  + 4*C*B*H*W (dense grad map written once)      + 20*R
     U = distinct (b,y,x) tap pixels, counted on the device from the kernel's own tap table."""
+    if "alg_bytes" in rec:
+        return rec["alg_bytes"]
     B, Cc, H, W = rec["im_size"]
     ph, pw = rec["crop"]
     R = rec["boxes"].size(0)
-    base = 4 * Cc * R * ph * pw + 20 * R
+    base = 4 * Cc * R * ph * pw * (2 if rec.get("dual") else 1) + 20 * R
     if rec["kernel"].startswith("crop_bwd"):
         return base + 4 * Cc * B * H * W
     key = (rec["boxes"].data_ptr(), R, H, W, ph, pw)
@@ -142,6 +144,85 @@ class _CropAndResize(torch.autograd.Function):
                 ctx.crop[0], ctx.crop[1], Cc, _lib.ptr(grad_image), layout, 0, _lib.stream_ptr(grad_out.device)))
         # `out` was written in place: rows this call did not touch pass their gradient through to whoever wrote them
         return grad_image, None, None, None, None, None, (grad_out if ctx.has_out else None), None
+
+
+class _CropPair(torch.autograd.Function):
+    """Both crops Dev.forward takes of one level's made-up map (lib/sub_module.py:555-572) as ONE autograd node:
+    size_a x size_a into rows ``dst_row`` of ``out_a``; size_b x size_b into rows ``dst_row`` of ``out_b`` and, when
+    ``compact_b``, also into a compact [R,...] tensor for the critic.  Backward is ONE pass over the map
+    (fi_crop_and_resize_backward_multi): one zero fill instead of two, no grad-accumulation add, no index_copy."""
+
+    @staticmethod
+    def forward(ctx, image, boxes, box_ind, dst_row, out_a, out_b, size_a, size_b, compact_b):
+        _lib.require_cuda(image, out_a, out_b)
+        layout, image = _lib.layout_of(image)
+        if layout != _lib.FI_LAYOUT_NHWC or image.dtype != torch.float32:
+            raise _lib.FiError("crop_pair needs an fp32 channels_last feature map")
+        boxes, box_ind = _prep_boxes(boxes, box_ind, image.device)
+        dst_row = dst_row.to(device=image.device, dtype=torch.int32).contiguous()
+        B, Cc, H, W = image.shape
+        R = boxes.size(0)
+        for o, sz in ((out_a, size_a), (out_b, size_b)):
+            if not (o.is_contiguous(memory_format=torch.channels_last) and o.dtype == torch.float32 and tuple(o.shape[1:]) == (Cc, sz, sz)):
+                raise _lib.FiError("crop_pair outputs must be fp32 channels_last [rows,%d,%d,%d]" % (Cc, sz, sz))
+        compact = torch.empty((R, Cc, size_b, size_b), device=image.device, memory_format=torch.channels_last) if compact_b else None
+        L, s = _lib.lib(), _lib.stream_ptr(image.device)
+        with torch.cuda.device(image.device):
+            with _Timed("crop_fwd_nhwc", im_size=(B, Cc, H, W), crop=(size_a, size_a), boxes=boxes, box_ind=box_ind):
+                _lib.check(L.fi_crop_and_resize_forward(_lib.ptr(image), layout, _lib.ptr(boxes), _lib.ptr(box_ind), _lib.ptr(dst_row), R, B, H, W,
+                                                        size_a, size_a, Cc, 0.0, _lib.ptr(out_a), layout, s))
+            with _Timed("crop_fwd_nhwc", im_size=(B, Cc, H, W), crop=(size_b, size_b), boxes=boxes, box_ind=box_ind, dual=compact_b):
+                if compact_b:
+                    _lib.check(L.fi_crop_and_resize_forward_dual(_lib.ptr(image), _lib.ptr(boxes), _lib.ptr(box_ind), _lib.ptr(dst_row), R, B, H, W,
+                                                                 size_b, size_b, Cc, 0.0, _lib.ptr(out_b), _lib.ptr(compact), s))
+                else:
+                    _lib.check(L.fi_crop_and_resize_forward(_lib.ptr(image), layout, _lib.ptr(boxes), _lib.ptr(box_ind), _lib.ptr(dst_row), R, B, H, W,
+                                                            size_b, size_b, Cc, 0.0, _lib.ptr(out_b), layout, s))
+        ctx.mark_dirty(out_a, out_b)
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(boxes, box_ind, dst_row)
+        ctx.meta = (B, Cc, H, W, size_a, size_b, compact_b)
+        return (out_a, out_b, compact) if compact_b else (out_a, out_b)
+
+    @staticmethod
+    def backward(ctx, g_a, g_b, g_c=None):
+        boxes, box_ind, dst_row = ctx.saved_tensors
+        B, Cc, H, W, size_a, size_b, compact_b = ctx.meta
+        R = boxes.size(0)
+        cl = torch.channels_last
+        g_a = None if g_a is None else g_a.contiguous(memory_format=cl)
+        g_b = None if g_b is None else g_b.contiguous(memory_format=cl)
+        g_c = None if g_c is None else g_c.contiguous(memory_format=cl)
+        dev = boxes.device
+        sets = []
+        if g_a is not None:
+            sets.append(_lib.CropSet(_lib.ptr(g_a), None, _lib.ptr(boxes), _lib.ptr(box_ind), _lib.ptr(dst_row), R, size_a, size_a))
+        if g_b is not None:
+            sets.append(_lib.CropSet(_lib.ptr(g_b), _lib.ptr(g_c), _lib.ptr(boxes), _lib.ptr(box_ind), _lib.ptr(dst_row), R, size_b, size_b))
+        elif g_c is not None:
+            sets.append(_lib.CropSet(_lib.ptr(g_c), None, _lib.ptr(boxes), _lib.ptr(box_ind), None, R, size_b, size_b))
+        grad_image = torch.empty((B, Cc, H, W), device=dev, dtype=torch.float32, memory_format=cl)
+        if not sets:
+            grad_image.zero_()
+        else:
+            arr = (_lib.CropSet * len(sets))(*sets)
+            nbytes = sum(4 * Cc * R * st.crop_height * st.crop_width * (2 if st.grads2 else 1) for st in sets) + 20 * R * len(sets) + 4 * Cc * B * H * W
+            with torch.cuda.device(dev), _Timed("crop_bwd_nhwc", im_size=(B, Cc, H, W), crop=(size_b, size_b), boxes=boxes, box_ind=box_ind, alg_bytes=nbytes):
+                _lib.check(_lib.lib().fi_crop_and_resize_backward_multi(arr, len(sets), B, H, W, Cc, _lib.ptr(grad_image), 0,
+                                                                        _lib.lib().fi_get_deterministic(), _lib.stream_ptr(dev)))
+        return grad_image, None, None, None, g_a, g_b, None, None, None
+
+
+def crop_pair(image, boxes, box_ind, dst_row, out_a, size_a, out_b, size_b, compact_b=False):
+    """See _CropPair.  Returns (out_a, out_b[, compact_b])."""
+    return _CropPair.apply(image, boxes, box_ind, dst_row, out_a, out_b, int(size_a), int(size_b), bool(compact_b))
+
+
+def set_deterministic(on=True):
+    """Deterministic RoIAlign backward (channels_last, C % 128 == 0, crops <= 16x16): every pixel is summed by one warp in
+    the order of the reference's serial CPU loop -- run-to-run identical and bit-identical to crop_and_resize.c:157-252.
+    Slower than the default vector reductions when many RoIs overlap.  Returns the previous setting."""
+    return bool(_lib.lib().fi_set_deterministic(1 if on else 0))
 
 
 def crop_and_resize(image, boxes, box_ind, crop_h, crop_w, extrapolation_value=0.0, out=None, dst_row=None):

@@ -85,6 +85,14 @@ int fi_crop_and_resize_forward(const float *image, int image_layout, const float
                                int crop_height, int crop_width, int depth, float extrapolation_value, float *crops,
                                int crops_layout, cudaStream_t stream);
 
+/* Forward with two destinations (NHWC, depth % 128 == 0): crop r goes to row dst_row[r] of `crops` AND to row r of
+ * `crops_compact`.  Dev.forward needs both for the 14x14 crops of levels 2-4: the scattered copy feeds the mask head in
+ * (image, roi) order (lib/sub_module.py:645-662), the compact one feeds the critic (:582). */
+int fi_crop_and_resize_forward_dual(const float *image, const float *boxes, const int *box_ind, const int *dst_row,
+                                    int num_boxes, int batch, int image_height, int image_width, int crop_height,
+                                    int crop_width, int depth, float extrapolation_value, float *crops,
+                                    float *crops_compact, cudaStream_t stream);
+
 /* Backward.  Replaces crop_and_resize_gpu_backward (crop_and_resize_gpu.c:40-69).
  *   grads        [>=num_boxes,depth,crop_h,crop_w] in `grads_layout`; src_row as dst_row above
  *   grads_image  [batch,depth,H,W] in `image_layout`; zero-filled first unless accumulate != 0 */
@@ -97,8 +105,10 @@ int fi_crop_and_resize_backward(const float *grads, int grads_layout, const floa
  * lib/sub_module.py:555-572), back-propagated in ONE pass that writes grads_image exactly once.  NHWC only.
  *   grads    [rows,crop_h,crop_w,depth]: gradient of crop r is row src_row[r] (row r when src_row is NULL)
  *   grads2   NULL, or a second gradient for the same crops in compact row order (row r), added to the first
- * When every set has crop_h, crop_w <= 16 and depth % 128 == 0 the result is deterministic and bit-identical
- * to the reference's serial CPU backward (crop_and_resize.c:157-252); other shapes use vector reductions. */
+ * deterministic != 0 (needs crop_h, crop_w <= 16 and depth % 128 == 0): every pixel is summed by one warp in the order
+ * of the reference's serial CPU loop with un-fused fp32 arithmetic -- run-to-run identical and bit-identical to
+ * crop_and_resize.c:157-252 for a single set -- and the map is written once (no zero fill, no atomics).
+ * deterministic == 0: one zero fill, then 128-bit vector reductions set by set. */
 typedef struct fi_crop_set {
     const float *grads;
     const float *grads2;
@@ -108,7 +118,12 @@ typedef struct fi_crop_set {
     int num_boxes, crop_height, crop_width;
 } fi_crop_set;
 int fi_crop_and_resize_backward_multi(const fi_crop_set *sets, int num_sets, int batch, int image_height, int image_width,
-                                      int depth, float *grads_image, int accumulate, cudaStream_t stream);
+                                      int depth, float *grads_image, int accumulate, int deterministic, cudaStream_t stream);
+
+/* Process-wide default for fi_crop_and_resize_backward (NHWC): 0 = vector reductions (default; like the reference's
+ * atomics the summation order varies from run to run), 1 = deterministic write-once gather.  Returns the old value. */
+int fi_set_deterministic(int on);
+int fi_get_deterministic(void);
 
 /* Integer taps of every sample, taps[num_boxes,crop_h,crop_w,5] = (y_lo,y_hi,x_lo,x_hi,inside): the "RoI
  * indices" the parity bar requires bit-exact (crop_and_resize_kernel.cu:40-70). */

@@ -357,7 +357,7 @@ def pth_nms_ref(dets, thresh, strict=True):
     d = dets.detach().cpu().numpy().astype(np.float32)
     # the reference's sort is unstable (pth_nms.py:37): with tied scores its result is implementation-defined;
     # a stable sort is used here and in the product so the two agree
-    order = torch.sort(dets[:, 4], 0, descending=True, stable=True)[1].cpu().numpy()
+    order = torch.sort(dets[:, 4], dim=0, descending=True, stable=True)[1].cpu().numpy()
     xyxy = d[:, [1, 0, 3, 2, 4]]
     if strict:
         keep = clib.oracle_nms(xyxy, thresh, True)          # un-reordered dets_temp (pth_nms.py:28-44)

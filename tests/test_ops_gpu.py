@@ -211,7 +211,8 @@ def test_intertwiner_loss_vs_restatement(B, loss, inst):
         if want.requires_grad:
             want.sum().backward(); got.sum().backward()
             a, b = (so_c, so_r) if inst else (sf_c, sf_r)
-            np.testing.assert_allclose(a.grad.cpu().numpy(), b.grad.cpu().numpy(), rtol=1e-3, atol=1e-7)
+            # OT with D=1: d/dx of x/(|x|+1e-20) underflows to exactly 0 in the kernel; autograd leaves ~1e-7 rounding noise
+            np.testing.assert_allclose(a.grad.cpu().numpy(), b.grad.cpu().numpy(), rtol=1e-3, atol=1e-6 if loss == "ot" else 1e-7)
 
 
 # ------------------------------------------------------------------------------------------------ NMS

@@ -70,16 +70,21 @@ def test_backward_matches_oracle(fmt, P, C):
     g = torch.Generator().manual_seed(5)
     grads = torch.randn(150, C, P, P, generator=g)
     want = clib.oracle_crop_and_resize_bwd(grads.numpy(), rois.numpy(), box_ind.numpy(), tuple(image.shape))
-    img = image.cuda().requires_grad_()
-    x = img.contiguous(memory_format=torch.channels_last) if fmt == "nhwc" else img
-    out = fi.CropAndResizeFunction(P, P)(x, rois.cuda(), box_ind.cuda())
-    out.backward(grads.cuda())
-    got = img.grad.cpu().numpy()
-    if fmt == "nhwc" and C % 128 == 0:
-        # gather backward (csrc/roi_align_bwd.cu): same order, same un-fused arithmetic as the serial CPU loop
-        np.testing.assert_array_equal(got, want)
-    else:
-        assert_bwd_close(got, grads.numpy(), rois.numpy(), box_ind.numpy(), tuple(image.shape), want)
+    for deterministic in ((False, True) if (fmt == "nhwc" and C % 128 == 0) else (False,)):
+        img = image.cuda().requires_grad_()
+        x = img.contiguous(memory_format=torch.channels_last) if fmt == "nhwc" else img
+        old = fi.set_deterministic(deterministic)
+        try:
+            out = fi.CropAndResizeFunction(P, P)(x, rois.cuda(), box_ind.cuda())
+            out.backward(grads.cuda())
+        finally:
+            fi.set_deterministic(old)
+        got = img.grad.cpu().numpy()
+        if deterministic:
+            # gather backward (csrc/roi_align_bwd.cu): same order, same un-fused arithmetic as the serial CPU loop
+            np.testing.assert_array_equal(got, want)
+        else:
+            assert_bwd_close(got, grads.numpy(), rois.numpy(), box_ind.numpy(), tuple(image.shape), want)
 
 
 def test_golden_vectors(golden_dir):
@@ -120,18 +125,45 @@ def test_backward_multi_sets_bit_exact_and_scatter_fallback(monkeypatch):
     sets[1] = _lib.CropSet(d["g14"].data_ptr(), d["g14b"].data_ptr(), d["boxes"].data_ptr(), d["ind"].data_ptr(), d["perm"].data_ptr(), 120, 14, 14)
     out = torch.full((2, 256, 26, 42), 7.0, device="cuda").contiguous(memory_format=cl)      # garbage: must be overwritten
     s = torch.cuda.current_stream().cuda_stream
-    _lib.check(_lib.lib().fi_crop_and_resize_backward_multi(sets, 2, 2, 26, 42, 256, out.data_ptr(), 0, s))
+    _lib.check(_lib.lib().fi_crop_and_resize_backward_multi(sets, 2, 2, 26, 42, 256, out.data_ptr(), 0, 1, s))
     got = out.cpu().numpy()
     mag = clib.oracle_crop_and_resize_bwd(np.abs(g7.numpy()), rois.numpy(), box_ind.numpy(), tuple(image.shape)) + \
         clib.oracle_crop_and_resize_bwd(np.abs(g14.numpy()) + np.abs(g14b.numpy()), rois.numpy(), box_ind.numpy(), tuple(image.shape))
     assert np.all(np.abs(got - (want + want14)) <= 1e-6 * mag + 1e-7)
     # determinism: the same call twice gives the same bits
     out2 = torch.empty_like(out)
-    _lib.check(_lib.lib().fi_crop_and_resize_backward_multi(sets, 2, 2, 26, 42, 256, out2.data_ptr(), 0, s))
+    _lib.check(_lib.lib().fi_crop_and_resize_backward_multi(sets, 2, 2, 26, 42, 256, out2.data_ptr(), 0, 1, s))
     assert torch.equal(out, out2)
     # accumulate=1 adds onto the existing map
-    _lib.check(_lib.lib().fi_crop_and_resize_backward_multi(sets, 1, 2, 26, 42, 256, out2.data_ptr(), 1, s))
+    _lib.check(_lib.lib().fi_crop_and_resize_backward_multi(sets, 1, 2, 26, 42, 256, out2.data_ptr(), 1, 1, s))
     np.testing.assert_allclose(out2.cpu().numpy(), got + want, rtol=1e-5, atol=1e-5)
+    # the default (vector reduction) mode computes the same sums in another order
+    out3 = torch.full_like(out, 3.0)
+    _lib.check(_lib.lib().fi_crop_and_resize_backward_multi(sets, 2, 2, 26, 42, 256, out3.data_ptr(), 0, 0, s))
+    assert np.all(np.abs(out3.cpu().numpy() - (want + want14)) <= 1e-6 * mag + 1e-7)
+
+
+def test_crop_pair_matches_separate_calls():
+    """crop_pair == two crop_and_resize calls + index_copy, forward (bit-exact) and backward."""
+    fi = _fi()
+    image, rois, box_ind = _case(12, 2, 256, 30, 34, 90, zero_rows=4)
+    g = torch.Generator().manual_seed(2)
+    rows = torch.randperm(200, generator=g)[:90].int()
+    cl = torch.channels_last
+    img = image.cuda().contiguous(memory_format=cl)
+    xa = img.clone().requires_grad_()
+    oa = torch.zeros(200, 256, 7, 7, device="cuda").contiguous(memory_format=cl)
+    ob = torch.zeros(200, 256, 14, 14, device="cuda").contiguous(memory_format=cl)
+    pa, pb, comp = fi.crop_pair(xa, rois.cuda(), box_ind.cuda(), rows.cuda(), oa, 7, ob, 14, compact_b=True)
+    xb = img.clone().requires_grad_()
+    ra = fi.crop_and_resize(xb, rois.cuda(), box_ind.cuda(), 7, 7)
+    rb = fi.crop_and_resize(xb, rois.cuda(), box_ind.cuda(), 14, 14)
+    idx = rows.long().cuda()
+    assert torch.equal(pa[idx], ra) and torch.equal(pb[idx], rb) and torch.equal(comp, rb)
+    ga, gb, gc = torch.randn(pa.shape, generator=g).cuda(), torch.randn(pb.shape, generator=g).cuda(), torch.randn(comp.shape, generator=g).cuda()
+    torch.autograd.backward([pa, pb, comp], [ga, gb, gc])
+    torch.autograd.backward([ra, rb], [ga[idx], gb[idx] + gc])
+    torch.testing.assert_close(xa.grad, xb.grad, rtol=1e-4, atol=1e-4)
 
 
 def test_known_answers():
