@@ -166,9 +166,11 @@ class Step(object):
         total = B * R
         rois, gt = inp["rois"], inp["gt"]
         rois_flat, gt_flat = rois.view(total, 4), gt.view(total)
-        raw = [m.requires_grad_() for m in inp["raw"]]
-        madeup = [m.requires_grad_() for m in inp["madeup"]]
-        small_f = [t.requires_grad_() for t in inp["small_feat"]]
+        # fresh leaves every step (a training loop clears .grad each iteration; re-using the leaf would time an extra
+        # read-modify-write of every map in AccumulateGrad)
+        raw = [m.detach().requires_grad_() for m in inp["raw"]]
+        madeup = [m.detach().requires_grad_() for m in inp["madeup"]]
+        small_f = [t.detach().requires_grad_() for t in inp["small_feat"]]
         big_f = inp["big_feat"]
         split = fi.split_levels(fi.roi_level(rois, cfg.DATA.IMAGE_SHAPE, cfg.ROIS.ASSIGN_ANCHOR_BASE))
         pooled_out = torch.empty((total, DEPTH, 7, 7), device=self.dev, memory_format=torch.channels_last)

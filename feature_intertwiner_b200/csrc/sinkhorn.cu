@@ -16,6 +16,7 @@
 // FPN-level loss) is done in fp32 FMA with 64x64 register tiles -- TF32/bf16 tensor cores would break the
 // 1e-4 loss tolerance through the three-term cancellation 2W(x,y)-W(x,x)-W(y,y).
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "fi_common.cuh"
 
@@ -296,6 +297,203 @@ __global__ void __launch_bounds__(kSinkThreads) sinkhorn_kernel(const SinkParams
     if (CS > 1) cluster.sync();   // no CTA may exit while a peer can still read its shared memory
 }
 
+// ------------------------------------------------------------------------------------------------
+// N = 256, D = 1 -- the RoI-level intertwiner loss (critic output [n,256,1], lib/OT_module.py:95-101) --
+// with K resident in REGISTERS.
+//
+// The generic kernel above streams K from shared memory twice per iteration and is bound by shared-memory
+// bandwidth (2*N^2 words / 128 B/clk).  For this shape a CTA pair owns a problem, each CTA 128 rows, and
+// every thread keeps a 4-row x 32-column tile of K (128 registers): an iteration is 256 FMAs per thread
+// plus two small cross-lane reductions, and the only traffic is the b / partial-sum vectors:
+//   lane = cg | rl << 3 : cg = column group (8), rl = row lane (4); warp w, row group rg = 4w + rl
+//   rows    4 rg .. 4 rg + 3
+//   columns 32 k + 4 cg + e, k = 0..7, e = 0..3 (a warp's 8 column groups read 128 contiguous bytes of b)
+//   K b     per-thread partial over its 32 columns, xor-shuffle over the 3 cg bits
+//   K^T a   per-thread partial over its 4 rows for 32 columns, reduce-scatter butterfly over the 2 rl
+//           bits (24 shuffles, 8 column sums left per lane), 8 warps combined through shared memory, the
+//           two CTAs through distributed shared memory -- one cluster barrier per iteration.
+// ------------------------------------------------------------------------------------------------
+struct Sink256Smem {
+    float xh[128], yh[256], b[256], denx[128], deny[256];
+    float colp[8][256];
+    float part[2][256];
+    float red[8];
+};
+
+// reduce 32 per-thread column partials over the row lanes of the warp and over the 8 warps; returns the CTA
+// total of column `threadIdx.x`.  Ends with a __syncthreads-protected read, so `colp` may be reused afterwards
+// only after the caller's next barrier.
+__device__ __forceinline__ float cta_column_sum(float (&cp)[32], Sink256Smem &sm, int lane, int w, int cg) {
+    const bool hi = (lane >> 3) & 1, hi2 = (lane >> 4) & 1;
+    float q[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float keep = hi ? cp[16 + j] : cp[j], send = hi ? cp[j] : cp[16 + j];
+        q[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    float z[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float keep = hi2 ? q[8 + j] : q[j], send = hi2 ? q[j] : q[8 + j];
+        z[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    const int k0 = (hi ? 4 : 0) + (hi2 ? 2 : 0);          // the two float4 column chunks this lane now owns
+    *reinterpret_cast<float4 *>(&sm.colp[w][32 * k0 + 4 * cg]) = make_float4(z[0], z[1], z[2], z[3]);
+    *reinterpret_cast<float4 *>(&sm.colp[w][32 * (k0 + 1) + 4 * cg]) = make_float4(z[4], z[5], z[6], z[7]);
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int q8 = 0; q8 < 8; ++q8) tot += sm.colp[q8][threadIdx.x];
+    return tot;
+}
+
+__global__ void __launch_bounds__(256, 1) sinkhorn_n256_d1_kernel(const float *__restrict__ x, const float *__restrict__ y, float *__restrict__ loss,
+                                                                 float *__restrict__ gx, float *__restrict__ gy, float inv_eps, int L) {
+    __shared__ __align__(16) Sink256Smem sm;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int prob = blockIdx.x >> 1;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int cgp = lane & 7, rl = lane >> 3;
+    const int r0 = (w * 4 + rl) * 4;                       // first of this thread's 4 local rows
+    const float *xp = x + (long)prob * 256, *yp = y + (long)prob * 256;
+    const float c0 = 1.0f / 256.0f;
+
+    // ---- normalise (OT_module.py:111-112); D == 1: |v| = sqrt(v*v)
+    if (t < 128) {
+        const float v = __ldg(xp + rank * 128 + t);
+        const float den = __fadd_rn(sqrtf(__fmul_rn(v, v)), kEps);
+        sm.denx[t] = den; sm.xh[t] = __fdiv_rn(v, den);
+    }
+    {
+        const float v = __ldg(yp + t);
+        const float den = __fadd_rn(sqrtf(__fmul_rn(v, v)), kEps);
+        sm.deny[t] = den; sm.yh[t] = __fdiv_rn(v, den);
+        sm.b[t] = c0;
+    }
+    __syncthreads();
+    float xh[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) xh[u] = sm.xh[r0 + u];
+
+    // ---- K = exp(-(1 - xh yh) / eps) straight into registers (OT_module.py:113,116)
+    float Kr[4][32];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float4 y4 = *reinterpret_cast<const float4 *>(&sm.yh[32 * k + 4 * cgp]);
+        const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) Kr[u][4 * k + e] = expf(-inv_eps * __fsub_rn(1.f, __fmul_rn(xh[u], yv[e])));
+    }
+
+    // ---- L Sinkhorn iterations (OT_module.py:120-122)
+    float a[4] = {c0, c0, c0, c0};
+    for (int it = 0; it < L; ++it) {
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float4 b4 = *reinterpret_cast<const float4 *>(&sm.b[32 * k + 4 * cgp]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                s[u] = fmaf(Kr[u][4 * k + 0], b4.x, s[u]); s[u] = fmaf(Kr[u][4 * k + 1], b4.y, s[u]);
+                s[u] = fmaf(Kr[u][4 * k + 2], b4.z, s[u]); s[u] = fmaf(Kr[u][4 * k + 3], b4.w, s[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            s[u] += __shfl_xor_sync(0xffffffffu, s[u], 1);
+            s[u] += __shfl_xor_sync(0xffffffffu, s[u], 2);
+            s[u] += __shfl_xor_sync(0xffffffffu, s[u], 4);
+            a[u] = __fdiv_rn(c0, __fadd_rn(s[u], kEps));
+        }
+        float cp[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) cp[j] = fmaf(Kr[3][j], a[3], fmaf(Kr[2][j], a[2], fmaf(Kr[1][j], a[1], Kr[0][j] * a[0])));
+        const float mine = cta_column_sum(cp, sm, lane, w, cgp);
+        float *slot = sm.part[it & 1];
+        slot[t] = mine;
+        cluster.sync();                                    // both CTAs' partial column sums are visible
+        const float tot = cluster.map_shared_rank(slot, 0)[t] + cluster.map_shared_rank(slot, 1)[t];   // rank order: same bits on both CTAs
+        sm.b[t] = __fdiv_rn(c0, __fadd_rn(tot, kEps));
+        __syncthreads();
+    }
+
+    // ---- P = a K b^T, loss = <P, C>   (OT_module.py:129-134); K registers now hold P
+    float lsum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float4 b4 = *reinterpret_cast<const float4 *>(&sm.b[32 * k + 4 * cgp]);
+        const float4 y4 = *reinterpret_cast<const float4 *>(&sm.yh[32 * k + 4 * cgp]);
+        const float bv[4] = {b4.x, b4.y, b4.z, b4.w}, yv[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float pij = __fmul_rn(__fmul_rn(a[u], Kr[u][4 * k + e]), bv[e]);
+                Kr[u][4 * k + e] = pij;
+                lsum = fmaf(pij, __fsub_rn(1.f, __fmul_rn(xh[u], yv[e])), lsum);
+            }
+    }
+    lsum = warp_sum(lsum);
+    if (lane == 0) sm.red[w] = lsum;
+    __syncthreads();
+    if (t == 0) {
+        float s = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s += sm.red[q];
+        atomicAdd(loss + prob, s);                         // two addends (one per CTA): order-independent
+    }
+
+    // ---- gradients with P constant (see the generic kernel); D == 1
+    if (gx != nullptr) {
+        float gxh[4] = {0.f, 0.f, 0.f, 0.f};
+        float cp[32];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float4 y4 = *reinterpret_cast<const float4 *>(&sm.yh[32 * k + 4 * cgp]);
+            const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float c = 0.f;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    gxh[u] = fmaf(Kr[u][4 * k + e], yv[e], gxh[u]);
+                    c = fmaf(Kr[u][4 * k + e], xh[u], c);
+                }
+                cp[4 * k + e] = c;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            gxh[u] += __shfl_xor_sync(0xffffffffu, gxh[u], 1);
+            gxh[u] += __shfl_xor_sync(0xffffffffu, gxh[u], 2);
+            gxh[u] += __shfl_xor_sync(0xffffffffu, gxh[u], 4);
+        }
+        if (cgp == 0) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float den = sm.denx[r0 + u], g = -gxh[u];
+                const float shrink = __fdiv_rn(__fsub_rn(den, kEps), den);
+                gx[(long)prob * 256 + rank * 128 + r0 + u] = __fdiv_rn(__fsub_rn(g, __fmul_rn(__fmul_rn(xh[u], __fmul_rn(g, xh[u])), shrink)), den);
+            }
+        }
+        const float mine = cta_column_sum(cp, sm, lane, w, cgp);     // colp is free again: barrier at the end of the loss phase
+        float *slot = sm.part[L & 1];
+        cluster.sync();                                    // peer is past its last read of `part`
+        slot[t] = mine;
+        cluster.sync();
+        if ((t >> 7) == rank) {                            // this CTA finalises the y rows it owns
+            const float g = -(cluster.map_shared_rank(slot, 0)[t] + cluster.map_shared_rank(slot, 1)[t]);
+            const float den = sm.deny[t], yh = sm.yh[t];
+            const float shrink = __fdiv_rn(__fsub_rn(den, kEps), den);
+            gy[(long)prob * 256 + t] = __fdiv_rn(__fsub_rn(g, __fmul_rn(__fmul_rn(yh, __fmul_rn(g, yh)), shrink)), den);
+        }
+    }
+    cluster.sync();   // no CTA may exit while its peer can still read its shared memory
+}
+
 constexpr int kMaxSmemBytes = 227 * 1024;
 
 static int pow2_floor(int v) { int r = 1; while (r * 2 <= v) r *= 2; return r; }
@@ -325,6 +523,22 @@ FI_API int fi_sinkhorn(const float *x, const float *y, int n_problems, int N, in
     if (n_problems == 0) return ok();
     FI_REQUIRE(x && y && loss, "fi_sinkhorn: null pointer");
     FI_REQUIRE((grad_x == nullptr) == (grad_y == nullptr), "fi_sinkhorn: grad_x and grad_y must both be given or both be NULL");
+    if (N == 256 && D == 1 && getenv("FI_SINKHORN_GENERIC") == nullptr) {      // RoI-level loss: K in registers
+        cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(float) * n_problems, stream);
+        if (e != cudaSuccess) { set_error(FI_ERR_CUDA, "fi_sinkhorn: memset: %s", cudaGetErrorString(e)); return FI_ERR_CUDA; }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(n_problems * 2));
+        cfg.blockDim = dim3(256);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, sinkhorn_n256_d1_kernel, x, y, loss, grad_x, grad_y, inv_eps, L);
+        if (e != cudaSuccess) { set_error(FI_ERR_CUDA, "fi_sinkhorn: launch: %s", cudaGetErrorString(e)); return FI_ERR_CUDA; }
+        return check_launch("fi_sinkhorn[n256 d1]");
+    }
     SinkParams p;
     p.x = x; p.y = y; p.loss = loss; p.gx = grad_x; p.gy = grad_y;
     p.N = N; p.D = D; p.L = L; p.inv_eps = inv_eps;
