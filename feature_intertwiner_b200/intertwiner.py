@@ -23,6 +23,7 @@ import torch.nn.functional as F
 from . import _lib
 from .roi_align import crop_and_resize, crop_pair
 from .roi_pool import RoIPoolFunction
+from .dist import merged_class_sums
 
 EPS = 1e-20
 
@@ -296,24 +297,6 @@ def pyramid_roi_align(inputs, pool_size, image_shape, base=224.):
 
 
 # ----------------------------------------------------------------------------------------------- meta loss
-class _AllReduceSum(torch.autograd.Function):
-    """Differentiable all-reduce(SUM).  Backward: every rank's contribution enters the total with weight 1, so the
-    local gradient is the incoming one -- times world_size when ``compensate`` is set, because DDP will later AVERAGE
-    parameter gradients over ranks whereas the reference's DataParallel SUMS the replicas' (SURVEY.md section 7)."""
-
-    @staticmethod
-    def forward(ctx, t, group, compensate):
-        import torch.distributed as dist
-        ctx.scale = float(dist.get_world_size(group)) if compensate else 1.0
-        out = t.clone()
-        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
-        return out
-
-    @staticmethod
-    def backward(ctx, g):
-        return g * ctx.scale, None, None
-
-
 class IntertwinerLoss(nn.Module):
     """``MaskRCNN.initialize_buffer`` + ``meta_loss`` + ``_merge_feat_vec`` (lib/model.py:106-111,143-224) as a module.
 
@@ -352,18 +335,8 @@ class IntertwinerLoss(nn.Module):
 
     def _sums(self, feat, cnt, differentiable):
         """_merge_feat_vec's numerator and denominator (lib/model.py:219-222), all-reduced when distributed."""
-        s = (feat * cnt).sum(dim=(0, 1))
-        n = cnt.sum(dim=(0, 1)).view(-1)
-        if self.distributed:
-            import torch.distributed as dist
-            packed = torch.cat([s.reshape(-1), n])
-            if differentiable and packed.requires_grad:
-                packed = _AllReduceSum.apply(packed, self.process_group, self.ddp_compensate)
-            else:
-                packed = packed.detach().clone()
-                dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=self.process_group)
-            s, n = packed[: s.numel()].view_as(s), packed[s.numel():]
-        return s, n
+        return merged_class_sums(feat, cnt, self.process_group if self.distributed else None, self.distributed,
+                                 differentiable, self.ddp_compensate)
 
     def forward(self, feat_input):
         big_feat, big_cnt, small_feat, small_cnt, small_output_all, small_gt_all = feat_input
