@@ -175,24 +175,36 @@ class Step(object):
         split = fi.split_levels(fi.roi_level(rois, cfg.DATA.IMAGE_SHAPE, cfg.ROIS.ASSIGN_ANCHOR_BASE))
         pooled_out = torch.empty((total, DEPTH, 7, 7), device=self.dev, memory_format=torch.channels_last)
         mask_out = torch.empty((total, DEPTH, 14, 14), device=self.dev, memory_format=torch.channels_last)
-        outs, grads = [], []
-        bfeat, bcnt, sfeat, scnt = [], [], [], []
+        # every crop of the pass in one level-batched launch (fi.crop_sets), like Dev.forward
+        specs, where = [], {}
         for i in range(4):
             if split.small_cnt[i] == 0:
                 continue
             if i < 3 and split.big_cnt[i]:
                 bidx = split.big(i).long()
-                crop = fi.crop_and_resize(raw[i], rois_flat[bidx], (bidx // R).int(), 14, 14)
-                outs.append(crop); grads.append(inp["g_big"][i])
-                f, c = fi.assign_feat2cls(gt_flat[bidx], big_f[i], NCLS)
-                bfeat.append(f); bcnt.append(c)
+                where[("big", i)] = (len(specs), bidx)
+                specs.append(dict(image=raw[i], boxes=rois_flat[bidx], box_ind=(bidx // R).int(), size=14))
             s32 = split.small(i)
             sidx = s32.long()
             boxes, ind = rois_flat[sidx], (sidx // R).int()
-            res = fi.crop_pair(madeup[i], boxes, ind, s32, pooled_out, 7, mask_out, 14, compact_b=(i < 3))
-            pooled_out, mask_out = res[0], res[1]
+            where[("small", i)] = (len(specs), sidx)
+            specs.append(dict(image=madeup[i], boxes=boxes, box_ind=ind, size=7, out=pooled_out, dst_row=s32))
+            specs.append(dict(image=madeup[i], boxes=boxes, box_ind=ind, size=14, out=mask_out, dst_row=s32, compact=(i < 3)))
+        res_out, res_comp = fi.crop_sets(specs)
+        outs, grads = [], []
+        bfeat, bcnt, sfeat, scnt = [], [], [], []
+        for i in range(4):
+            if ("small", i) not in where:
+                continue
+            if ("big", i) in where:
+                k, bidx = where[("big", i)]
+                outs.append(res_comp[k]); grads.append(inp["g_big"][i])      # compact 14x14 crop -> critic (stock conv, not timed)
+                f, c = fi.assign_feat2cls(gt_flat[bidx], big_f[i], NCLS)
+                bfeat.append(f); bcnt.append(c)
+            k, sidx = where[("small", i)]
+            pooled_out, mask_out = res_out[k], res_out[k + 1]
             if i < 3:
-                outs.append(res[2]); grads.append(inp["g_small"][i])        # compact 14x14 crop -> critic (stock conv, not timed)
+                outs.append(res_comp[k + 1]); grads.append(inp["g_small"][i])
                 f, c = fi.assign_feat2cls(gt_flat[sidx], small_f[i], NCLS)
                 sfeat.append(f); scnt.append(c)
         feat_in = [torch.stack(bfeat)[None].detach(), torch.stack(bcnt)[None], torch.stack(sfeat)[None], torch.stack(scnt)[None], None, None]

@@ -3,7 +3,7 @@ class-mean buffer -> L2 / Sinkhorn intertwiner loss) as hand-written sm_100a CUD
 (include/fi_b200.h), with the reference's own operator API on top.  See DESIGN.md.
 """
 from ._lib import FiError, lib, library_path  # noqa: F401
-from .roi_align import (CropAndResizeFunction, RoIAlign, crop_and_resize, crop_pair, crop_taps,  # noqa: F401
+from .roi_align import (CropAndResizeFunction, RoIAlign, crop_and_resize, crop_pair, crop_sets, crop_taps,  # noqa: F401
                         set_deterministic)
 from .roi_pool import RoIPoolFunction, _RoIPooling  # noqa: F401
 from .nms import nms, nms_batched, pth_nms  # noqa: F401

@@ -33,6 +33,8 @@ SIGNATURES = {
     "fi_crop_and_resize_backward_multi": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _I, _P]),
     "fi_set_deterministic": (_I, [_I]),
     "fi_get_deterministic": (_I, []),
+    "fi_crop_sets_forward": (_I, [_P, _I, _P]),
+    "fi_crop_sets_backward": (_I, [_P, _I, _I, _P]),
     "fi_crop_taps": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "fi_roi_level": (_I, [_P, _I, _F, _F, _P, _P]),
     "fi_split_levels": (_I, [_P, _I, _P, _P, _P, _P, _P, _P]),
@@ -50,6 +52,20 @@ class CropSet(C.Structure):
     """struct fi_crop_set (include/fi_b200.h)."""
     _fields_ = [("grads", _P), ("grads2", _P), ("boxes", _P), ("box_ind", _P), ("src_row", _P),
                 ("num_boxes", _I), ("crop_height", _I), ("crop_width", _I)]
+
+
+class FwdSet(C.Structure):
+    """struct fi_fwd_set."""
+    _fields_ = [("image", _P), ("boxes", _P), ("box_ind", _P), ("dst_row", _P), ("crops", _P), ("crops_compact", _P),
+                ("batch", _I), ("image_height", _I), ("image_width", _I), ("depth", _I), ("num_boxes", _I),
+                ("crop_height", _I), ("crop_width", _I), ("extrapolation_value", _F)]
+
+
+class BwdSet(C.Structure):
+    """struct fi_bwd_set."""
+    _fields_ = [("grads_image", _P), ("grads", _P), ("grads2", _P), ("boxes", _P), ("box_ind", _P), ("src_row", _P),
+                ("batch", _I), ("image_height", _I), ("image_width", _I), ("depth", _I), ("num_boxes", _I),
+                ("crop_height", _I), ("crop_width", _I)]
 
 
 def lib():

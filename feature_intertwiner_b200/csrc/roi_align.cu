@@ -60,69 +60,106 @@ __device__ __forceinline__ AxisTap shfl_tap(const AxisTap &t, int src) {
 // showed 16 % issue-active with every warp parked on long_scoreboard: the bound was memory-level
 // parallelism, not bytes, so the loop is written to keep 4*U*512 B in flight per warp.
 // Overlap between neighbouring samples / rows / boxes is left to L1 and L2.
+struct FwdSet {                  // one forward crop set (device view)
+    const float *image, *boxes;
+    const int *box_ind, *dst_row;
+    float *crops, *crops2;
+    int B, H, W, C, ph, pw, slabs;
+    float extrap;
+};
+
 template <int U>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) crop_fwd_nhwc_kernel(const float *__restrict__ image, const float *__restrict__ boxes,
-                                                                           const int *__restrict__ box_ind, const int *__restrict__ dst_row,
-                                                                           long nunits, int slabs, int B, int H, int W, int ph, int pw, int C,
-                                                                           float extrap, float *__restrict__ crops, float *__restrict__ crops2) {
+__device__ __forceinline__ void fwd_unit(const FwdSet &S, long u, int lane) {
+    const float *__restrict__ image = S.image;
+    const float *__restrict__ boxes = S.boxes;
+    const int *__restrict__ box_ind = S.box_ind;
+    const int *__restrict__ dst_row = S.dst_row;
+    float *__restrict__ crops = S.crops;
+    float *__restrict__ crops2 = S.crops2;
+    const int slabs = S.slabs, B = S.B, H = S.H, W = S.W, ph = S.ph, pw = S.pw, C = S.C;
+    const float extrap = S.extrap;
+    const int slab = (int)(u % slabs);
+    const long q = u / slabs;
+    const int r = (int)(q / ph), i = (int)(q - (long)r * ph);
+    const int b = box_ind[r];
+    const long orow = dst_row ? (long)dst_row[r] : (long)r;
+    const int coff = slab * 128 + lane * 4;
+    float *out = crops + ((orow * ph + i) * (long)pw) * C + coff;
+    float *out2 = crops2 ? crops2 + (((long)r * ph + i) * (long)pw) * C + coff : nullptr;   // optional compact copy (row r)
+    const bool bad = (b < 0 || b >= B);     // reference leaves such rows at their zero fill (crop_and_resize_kernel.cu:34-38)
+    const float y1 = boxes[4 * r + 0], x1 = boxes[4 * r + 1], y2 = boxes[4 * r + 2], x2 = boxes[4 * r + 3];
+    const AxisTap ty = axis_sample(y1, y2, axis_step(y1, y2, H, ph), i, H, ph);
+    if (bad || !ty.inside) {
+        const float v = bad ? 0.f : extrap;
+        const float4 v4 = make_float4(v, v, v, v);
+        for (int j = 0; j < pw; ++j) {
+            st_stream4(out + (long)j * C, v4);
+            if (out2) st_stream4(out2 + (long)j * C, v4);
+        }
+        return;
+    }
+    const float sx = axis_step(x1, x2, W, pw);
+    const float *rowT = image + ((long)b * H + ty.lo) * (long)W * C + coff;
+    const float *rowB = image + ((long)b * H + ty.hi) * (long)W * C + coff;
+    for (int jb = 0; jb < pw; jb += 32) {                        // lane l computes the x tap of sample jb + l
+        const AxisTap mine = axis_sample(x1, x2, sx, jb + lane, W, pw);
+        const int lo_c = min(max(mine.lo, 0), W - 1), hi_c = min(max(mine.hi, 0), W - 1);
+        const int packed = lo_c | (hi_c << 15) | (mine.inside ? (1 << 30) : 0);      // W <= 32768
+        const int jn = min(32, pw - jb);
+        for (int j0 = 0; j0 < jn; j0 += U) {
+            float4 tl[U], tr[U], bl[U], br[U];
+            int pk[U];
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                const int j = min(j0 + k, jn - 1);               // tail lanes re-read the last sample (discarded)
+                pk[k] = __shfl_sync(0xffffffffu, packed, j);
+                const long xl = (long)(pk[k] & 0x7fff) * C, xh = (long)((pk[k] >> 15) & 0x7fff) * C;
+                tl[k] = ldg4(rowT + xl); tr[k] = ldg4(rowT + xh);
+                bl[k] = ldg4(rowB + xl); br[k] = ldg4(rowB + xh);
+            }
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                const int j = j0 + k;
+                const float fx = __shfl_sync(0xffffffffu, mine.frac, min(j, jn - 1));
+                if (j < jn) {
+                    const float4 top = lerp_rn(tl[k], tr[k], fx);            // crop_and_resize.c:102
+                    const float4 bot = lerp_rn(bl[k], br[k], fx);            // :103-104
+                    float4 v = lerp_rn(top, bot, ty.frac);                   // :106
+                    if (!(pk[k] & (1 << 30))) v = make_float4(extrap, extrap, extrap, extrap);
+                    st_stream4(out + (long)(jb + j) * C, v);
+                    if (out2) st_stream4(out2 + (long)(jb + j) * C, v);
+                }
+            }
+        }
+    }
+}
+
+template <int U>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) crop_fwd_nhwc_kernel(const FwdSet S, long nunits) {
     const int lane = threadIdx.x & 31;
     const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
-    for (long u = warp; u < nunits; u += nwarps) {
-        const int slab = (int)(u % slabs);
-        const long q = u / slabs;
-        const int r = (int)(q / ph), i = (int)(q - (long)r * ph);
-        const int b = box_ind[r];
-        const long orow = dst_row ? (long)dst_row[r] : (long)r;
-        const int coff = slab * 128 + lane * 4;
-        float *out = crops + ((orow * ph + i) * (long)pw) * C + coff;
-        float *out2 = crops2 ? crops2 + (((long)r * ph + i) * (long)pw) * C + coff : nullptr;   // optional compact copy (row r)
-        const bool bad = (b < 0 || b >= B);     // reference leaves such rows at their zero fill (crop_and_resize_kernel.cu:34-38)
-        const float y1 = boxes[4 * r + 0], x1 = boxes[4 * r + 1], y2 = boxes[4 * r + 2], x2 = boxes[4 * r + 3];
-        const AxisTap ty = axis_sample(y1, y2, axis_step(y1, y2, H, ph), i, H, ph);
-        if (bad || !ty.inside) {
-            const float v = bad ? 0.f : extrap;
-            const float4 v4 = make_float4(v, v, v, v);
-            for (int j = 0; j < pw; ++j) {
-                st_stream4(out + (long)j * C, v4);
-                if (out2) st_stream4(out2 + (long)j * C, v4);
-            }
-            continue;
-        }
-        const float sx = axis_step(x1, x2, W, pw);
-        const float *rowT = image + ((long)b * H + ty.lo) * (long)W * C + coff;
-        const float *rowB = image + ((long)b * H + ty.hi) * (long)W * C + coff;
-        for (int jb = 0; jb < pw; jb += 32) {                        // lane l computes the x tap of sample jb + l
-            const AxisTap mine = axis_sample(x1, x2, sx, jb + lane, W, pw);
-            const int lo_c = min(max(mine.lo, 0), W - 1), hi_c = min(max(mine.hi, 0), W - 1);
-            const int packed = lo_c | (hi_c << 15) | (mine.inside ? (1 << 30) : 0);      // W <= 32768
-            const int jn = min(32, pw - jb);
-            for (int j0 = 0; j0 < jn; j0 += U) {
-                float4 tl[U], tr[U], bl[U], br[U];
-                int pk[U];
-#pragma unroll
-                for (int k = 0; k < U; ++k) {
-                    const int j = min(j0 + k, jn - 1);               // tail lanes re-read the last sample (discarded)
-                    pk[k] = __shfl_sync(0xffffffffu, packed, j);
-                    const long xl = (long)(pk[k] & 0x7fff) * C, xh = (long)((pk[k] >> 15) & 0x7fff) * C;
-                    tl[k] = ldg4(rowT + xl); tr[k] = ldg4(rowT + xh);
-                    bl[k] = ldg4(rowB + xl); br[k] = ldg4(rowB + xh);
-                }
-#pragma unroll
-                for (int k = 0; k < U; ++k) {
-                    const int j = j0 + k;
-                    const float fx = __shfl_sync(0xffffffffu, mine.frac, min(j, jn - 1));
-                    if (j < jn) {
-                        const float4 top = lerp_rn(tl[k], tr[k], fx);            // crop_and_resize.c:102
-                        const float4 bot = lerp_rn(bl[k], br[k], fx);            // :103-104
-                        float4 v = lerp_rn(top, bot, ty.frac);                   // :106
-                        if (!(pk[k] & (1 << 30))) v = make_float4(extrap, extrap, extrap, extrap);
-                        st_stream4(out + (long)(jb + j) * C, v);
-                        if (out2) st_stream4(out2 + (long)(jb + j) * C, v);
-                    }
-                }
-            }
-        }
+    for (long u = warp; u < nunits; u += nwarps) fwd_unit<U>(S, u, lane);
+}
+
+// Every crop set of a Dev.forward pass (up to 3 "big" + 4x2 "small") in ONE launch: the small levels (a few hundred
+// boxes on a 26x42 map) are far too small to fill 148 SMs on their own.
+constexpr int kMaxFwdSets = 12;
+struct FwdSets {
+    FwdSet s[kMaxFwdSets];
+    long first_unit[kMaxFwdSets + 1];
+    int n;
+};
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) crop_fwd_nhwc_sets_kernel(const FwdSets sets) {
+    const int lane = threadIdx.x & 31;
+    const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    const long total = sets.first_unit[sets.n];
+    for (long u = warp; u < total; u += nwarps) {
+        int k = 0;
+        while (u >= sets.first_unit[k + 1]) ++k;
+        fwd_unit<4>(sets.s[k], u - sets.first_unit[k], lane);
     }
 }
 
@@ -184,77 +221,110 @@ __device__ __forceinline__ float4 f4_scale(float4 a, float w) {
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
+struct BwdSet {                  // one backward crop set (device view)
+    const float *grads, *grads2, *boxes;
+    const int *box_ind, *src_row;
+    float *gimg;
+    int B, H, W, C, ph, pw, slabs;
+};
+
 // unit = (box r, crop row i, 128-channel slab); gradient loads of a batch of U samples are issued together
 template <int U>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) crop_bwd_nhwc_kernel(const float *__restrict__ grads, const float *__restrict__ grads2,
-                                                                           const float *__restrict__ boxes, const int *__restrict__ box_ind,
-                                                                           const int *__restrict__ src_row, long nunits, int slabs, int B, int H,
-                                                                           int W, int ph, int pw, int C, float *__restrict__ gimg) {
+__device__ __forceinline__ void bwd_unit(const BwdSet &S, long u, int lane) {
+    const float *__restrict__ grads = S.grads;
+    const float *__restrict__ grads2 = S.grads2;
+    const float *__restrict__ boxes = S.boxes;
+    const int *__restrict__ box_ind = S.box_ind;
+    const int *__restrict__ src_row = S.src_row;
+    float *__restrict__ gimg = S.gimg;
+    const int slabs = S.slabs, B = S.B, H = S.H, W = S.W, ph = S.ph, pw = S.pw, C = S.C;
+    const int slab = (int)(u % slabs);
+    const long q = u / slabs;
+    const int r = (int)(q / ph), i = (int)(q - (long)r * ph);
+    const int b = box_ind[r];
+    if (b < 0 || b >= B) return;
+    const float y1 = boxes[4 * r + 0], x1 = boxes[4 * r + 1], y2 = boxes[4 * r + 2], x2 = boxes[4 * r + 3];
+    const AxisTap ty = axis_sample(y1, y2, axis_step(y1, y2, H, ph), i, H, ph);
+    if (!ty.inside) return;
+    const float sx = axis_step(x1, x2, W, pw);
+    const float wy_hi = ty.frac, wy_lo = __fsub_rn(1.f, ty.frac);            // crop_and_resize.c:241,245
+    const long grow = src_row ? (long)src_row[r] : (long)r;
+    const int coff = slab * 128 + lane * 4;
+    const float *g = grads + ((grow * ph + i) * (long)pw) * C + coff;
+    const float *g2 = grads2 ? grads2 + (((long)r * ph + i) * (long)pw) * C + coff : nullptr;
+    float *rowT = gimg + ((long)b * H + ty.lo) * (long)W * C + coff;
+    float *rowB = gimg + ((long)b * H + ty.hi) * (long)W * C + coff;
+    float4 Lt = f4_zero(), Lb = f4_zero(), Rt = f4_zero(), Rb = f4_zero();
+    int cur_lo = -1, cur_hi = -1;
+    for (int jb = 0; jb < pw; jb += 32) {
+        const AxisTap mine = axis_sample(x1, x2, sx, jb + lane, W, pw);
+        const int jn = min(32, pw - jb);
+        for (int j0 = 0; j0 < jn; j0 += U) {
+            float4 gv[U];
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                const int j = jb + min(j0 + k, jn - 1);
+                gv[k] = __ldcs(reinterpret_cast<const float4 *>(g + (long)j * C));
+                if (g2) gv[k] = f4_add(gv[k], __ldcs(reinterpret_cast<const float4 *>(g2 + (long)j * C)));
+            }
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                if (j0 + k >= jn) break;
+                const AxisTap tx = shfl_tap(mine, j0 + k);
+                if (!tx.inside) continue;
+                if (!(tx.lo == cur_lo && tx.hi == cur_hi)) {
+                    if (cur_lo >= 0) {
+                        red_add(rowT + (long)cur_lo * C, Lt);
+                        red_add(rowB + (long)cur_lo * C, Lb);
+                        if ((tx.lo == cur_hi) && (tx.hi != cur_hi)) { Lt = Rt; Lb = Rb; }     // old right column becomes the new left one
+                        else {
+                            red_add(rowT + (long)cur_hi * C, Rt);
+                            red_add(rowB + (long)cur_hi * C, Rb);
+                            Lt = f4_zero(); Lb = f4_zero();
+                        }
+                        Rt = f4_zero(); Rb = f4_zero();
+                    }
+                    cur_lo = tx.lo; cur_hi = tx.hi;
+                }
+                const float wx_hi = tx.frac, wx_lo = __fsub_rn(1.f, tx.frac);
+                const float4 dtop = f4_scale(gv[k], wy_lo), dbot = f4_scale(gv[k], wy_hi);
+                Lt = f4_add(Lt, f4_scale(dtop, wx_lo)); Rt = f4_add(Rt, f4_scale(dtop, wx_hi));
+                Lb = f4_add(Lb, f4_scale(dbot, wx_lo)); Rb = f4_add(Rb, f4_scale(dbot, wx_hi));
+            }
+        }
+    }
+    if (cur_lo >= 0) {
+        red_add(rowT + (long)cur_lo * C, Lt);
+        red_add(rowB + (long)cur_lo * C, Lb);
+        red_add(rowT + (long)cur_hi * C, Rt);
+        red_add(rowB + (long)cur_hi * C, Rb);
+    }
+}
+
+template <int U>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) crop_bwd_nhwc_kernel(const BwdSet S, long nunits) {
     const int lane = threadIdx.x & 31;
     const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
-    for (long u = warp; u < nunits; u += nwarps) {
-        const int slab = (int)(u % slabs);
-        const long q = u / slabs;
-        const int r = (int)(q / ph), i = (int)(q - (long)r * ph);
-        const int b = box_ind[r];
-        if (b < 0 || b >= B) continue;
-        const float y1 = boxes[4 * r + 0], x1 = boxes[4 * r + 1], y2 = boxes[4 * r + 2], x2 = boxes[4 * r + 3];
-        const AxisTap ty = axis_sample(y1, y2, axis_step(y1, y2, H, ph), i, H, ph);
-        if (!ty.inside) continue;
-        const float sx = axis_step(x1, x2, W, pw);
-        const float wy_hi = ty.frac, wy_lo = __fsub_rn(1.f, ty.frac);            // crop_and_resize.c:241,245
-        const long grow = src_row ? (long)src_row[r] : (long)r;
-        const int coff = slab * 128 + lane * 4;
-        const float *g = grads + ((grow * ph + i) * (long)pw) * C + coff;
-        const float *g2 = grads2 ? grads2 + (((long)r * ph + i) * (long)pw) * C + coff : nullptr;
-        float *rowT = gimg + ((long)b * H + ty.lo) * (long)W * C + coff;
-        float *rowB = gimg + ((long)b * H + ty.hi) * (long)W * C + coff;
-        float4 Lt = f4_zero(), Lb = f4_zero(), Rt = f4_zero(), Rb = f4_zero();
-        int cur_lo = -1, cur_hi = -1;
-        for (int jb = 0; jb < pw; jb += 32) {
-            const AxisTap mine = axis_sample(x1, x2, sx, jb + lane, W, pw);
-            const int jn = min(32, pw - jb);
-            for (int j0 = 0; j0 < jn; j0 += U) {
-                float4 gv[U];
-#pragma unroll
-                for (int k = 0; k < U; ++k) {
-                    const int j = jb + min(j0 + k, jn - 1);
-                    gv[k] = __ldcs(reinterpret_cast<const float4 *>(g + (long)j * C));
-                    if (g2) gv[k] = f4_add(gv[k], __ldcs(reinterpret_cast<const float4 *>(g2 + (long)j * C)));
-                }
-#pragma unroll
-                for (int k = 0; k < U; ++k) {
-                    if (j0 + k >= jn) break;
-                    const AxisTap tx = shfl_tap(mine, j0 + k);
-                    if (!tx.inside) continue;
-                    if (!(tx.lo == cur_lo && tx.hi == cur_hi)) {
-                        if (cur_lo >= 0) {
-                            red_add(rowT + (long)cur_lo * C, Lt);
-                            red_add(rowB + (long)cur_lo * C, Lb);
-                            if ((tx.lo == cur_hi) && (tx.hi != cur_hi)) { Lt = Rt; Lb = Rb; }     // old right column becomes the new left one
-                            else {
-                                red_add(rowT + (long)cur_hi * C, Rt);
-                                red_add(rowB + (long)cur_hi * C, Rb);
-                                Lt = f4_zero(); Lb = f4_zero();
-                            }
-                            Rt = f4_zero(); Rb = f4_zero();
-                        }
-                        cur_lo = tx.lo; cur_hi = tx.hi;
-                    }
-                    const float wx_hi = tx.frac, wx_lo = __fsub_rn(1.f, tx.frac);
-                    const float4 dtop = f4_scale(gv[k], wy_lo), dbot = f4_scale(gv[k], wy_hi);
-                    Lt = f4_add(Lt, f4_scale(dtop, wx_lo)); Rt = f4_add(Rt, f4_scale(dtop, wx_hi));
-                    Lb = f4_add(Lb, f4_scale(dbot, wx_lo)); Rb = f4_add(Rb, f4_scale(dbot, wx_hi));
-                }
-            }
-        }
-        if (cur_lo >= 0) {
-            red_add(rowT + (long)cur_lo * C, Lt);
-            red_add(rowB + (long)cur_lo * C, Lb);
-            red_add(rowT + (long)cur_hi * C, Rt);
-            red_add(rowB + (long)cur_hi * C, Rb);
-        }
+    for (long u = warp; u < nunits; u += nwarps) bwd_unit<U>(S, u, lane);
+}
+
+constexpr int kMaxBwdSets = 12;
+struct BwdSets {
+    BwdSet s[kMaxBwdSets];
+    long first_unit[kMaxBwdSets + 1];
+    int n;
+};
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) crop_bwd_nhwc_sets_kernel(const BwdSets sets) {
+    const int lane = threadIdx.x & 31;
+    const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    const long total = sets.first_unit[sets.n];
+    for (long u = warp; u < total; u += nwarps) {
+        int k = 0;
+        while (u >= sets.first_unit[k + 1]) ++k;
+        bwd_unit<4>(sets.s[k], u - sets.first_unit[k], lane);
     }
 }
 
@@ -469,10 +539,11 @@ int fi_scatter_backward_nhwc(const float *grads, const float *grads2, const floa
     if (R == 0) return ok();
     const bool vec = (C % 128 == 0) && ((uintptr_t)gimg % 16 == 0) && ((uintptr_t)grads % 16 == 0) && ((uintptr_t)grads2 % 16 == 0);
     if (vec) {
-        const int slabs = C / 128;
-        const long nunits = (long)R * ph * slabs;
-        crop_bwd_nhwc_kernel<4><<<grid_for(nunits, kWarpsPerBlock, 8), kWarpsPerBlock * 32, 0, stream>>>(grads, grads2, boxes, box_ind, src_row, nunits,
-                                                                                                       slabs, B, H, W, ph, pw, C, gimg);
+        BwdSet S;
+        S.grads = grads; S.grads2 = grads2; S.boxes = boxes; S.box_ind = box_ind; S.src_row = src_row; S.gimg = gimg;
+        S.B = B; S.H = H; S.W = W; S.C = C; S.ph = ph; S.pw = pw; S.slabs = C / 128;
+        const long nunits = (long)R * ph * S.slabs;
+        crop_bwd_nhwc_kernel<4><<<grid_for(nunits, kWarpsPerBlock, 8), kWarpsPerBlock * 32, 0, stream>>>(S, nunits);
         return check_launch("fi_crop_and_resize_backward[nhwc scatter]");
     }
     const long nunits = (long)R * ph;
@@ -506,13 +577,15 @@ static int forward_impl(const float *image, int image_layout, const float *boxes
     if (image_layout == FI_LAYOUT_NHWC) {
         const bool vec = (C % 128 == 0) && (W <= 32768) && ((uintptr_t)image % 16 == 0) && ((uintptr_t)crops % 16 == 0) && ((uintptr_t)crops2 % 16 == 0);
         if (vec) {
-            const int slabs = C / 128;
-            const long nunits = (long)R * ph * slabs;    // one warp per (crop row, 128-channel slab)
+            FwdSet S;
+            S.image = image; S.boxes = boxes; S.box_ind = box_ind; S.dst_row = dst_row; S.crops = crops; S.crops2 = crops2;
+            S.B = B; S.H = H; S.W = W; S.C = C; S.ph = ph; S.pw = pw; S.slabs = C / 128; S.extrap = extrap;
+            const long nunits = (long)R * ph * S.slabs;  // one warp per (crop row, 128-channel slab)
             const int grid = grid_for(nunits, kWarpsPerBlock, 8);
             if (pw % 4 == 0 || pw > 12)
-                crop_fwd_nhwc_kernel<4><<<grid, kWarpsPerBlock * 32, 0, stream>>>(image, boxes, box_ind, dst_row, nunits, slabs, B, H, W, ph, pw, C, extrap, crops, crops2);
+                crop_fwd_nhwc_kernel<4><<<grid, kWarpsPerBlock * 32, 0, stream>>>(S, nunits);
             else
-                crop_fwd_nhwc_kernel<2><<<grid, kWarpsPerBlock * 32, 0, stream>>>(image, boxes, box_ind, dst_row, nunits, slabs, B, H, W, ph, pw, C, extrap, crops, crops2);
+                crop_fwd_nhwc_kernel<2><<<grid, kWarpsPerBlock * 32, 0, stream>>>(S, nunits);
         } else {
             if (crops2) { set_error(FI_ERR_UNSUPPORTED, "fi_crop_and_resize_forward_dual needs depth %% 128 == 0 and 16-byte aligned tensors"); return FI_ERR_UNSUPPORTED; }
             const long nunits = (long)R * ph;
@@ -584,6 +657,67 @@ FI_API int fi_crop_and_resize_backward(const float *grads, int grads_layout, con
     }
     set_error(FI_ERR_INVALID, "fi_crop_and_resize_backward: unknown layout %d", image_layout);
     return FI_ERR_INVALID;
+}
+
+FI_API int fi_crop_sets_forward(const fi_fwd_set *sets, int num_sets, cudaStream_t stream) {
+    FI_REQUIRE(sets && num_sets >= 1 && num_sets <= kMaxFwdSets, "fi_crop_sets_forward: 1..%d sets", kMaxFwdSets);
+    FwdSets dev;
+    dev.n = 0;
+    long units = 0;
+    for (int i = 0; i < num_sets; ++i) {
+        const fi_fwd_set &h = sets[i];
+        if (int e = check_common(h.image, h.boxes, h.box_ind, h.crops, h.num_boxes, h.batch, h.image_height, h.image_width, h.crop_height,
+                                 h.crop_width, h.depth)) return e;
+        const bool vec = (h.depth % 128 == 0) && (h.image_width <= 32768) && ((uintptr_t)h.image % 16 == 0) && ((uintptr_t)h.crops % 16 == 0) &&
+                         ((uintptr_t)h.crops_compact % 16 == 0);
+        if (!vec) { set_error(FI_ERR_UNSUPPORTED, "fi_crop_sets_forward: set %d needs NHWC, depth %% 128 == 0, 16-byte aligned tensors", i); return FI_ERR_UNSUPPORTED; }
+        if (h.num_boxes == 0) continue;
+        FwdSet &S = dev.s[dev.n];
+        S.image = h.image; S.boxes = h.boxes; S.box_ind = h.box_ind; S.dst_row = h.dst_row; S.crops = h.crops; S.crops2 = h.crops_compact;
+        S.B = h.batch; S.H = h.image_height; S.W = h.image_width; S.C = h.depth; S.ph = h.crop_height; S.pw = h.crop_width;
+        S.slabs = h.depth / 128; S.extrap = h.extrapolation_value;
+        dev.first_unit[dev.n] = units;
+        units += (long)h.num_boxes * h.crop_height * S.slabs;
+        ++dev.n;
+    }
+    dev.first_unit[dev.n] = units;
+    if (units == 0) return ok();
+    crop_fwd_nhwc_sets_kernel<<<grid_for(units, kWarpsPerBlock, 8), kWarpsPerBlock * 32, 0, stream>>>(dev);
+    return check_launch("fi_crop_sets_forward");
+}
+
+FI_API int fi_crop_sets_backward(const fi_bwd_set *sets, int num_sets, int zero_first, cudaStream_t stream) {
+    FI_REQUIRE(sets && num_sets >= 1 && num_sets <= kMaxBwdSets, "fi_crop_sets_backward: 1..%d sets", kMaxBwdSets);
+    BwdSets dev;
+    dev.n = 0;
+    long units = 0;
+    for (int i = 0; i < num_sets; ++i) {
+        const fi_bwd_set &h = sets[i];
+        FI_REQUIRE(h.grads_image && h.batch > 0 && h.image_height > 0 && h.image_width > 0 && h.depth > 0, "fi_crop_sets_backward: bad map in set %d", i);
+        if (int e = check_common(h.grads, h.boxes, h.box_ind, h.grads_image, h.num_boxes, h.batch, h.image_height, h.image_width, h.crop_height,
+                                 h.crop_width, h.depth)) return e;
+        const bool vec = (h.depth % 128 == 0) && ((uintptr_t)h.grads_image % 16 == 0) && ((uintptr_t)h.grads % 16 == 0) && ((uintptr_t)h.grads2 % 16 == 0);
+        if (!vec) { set_error(FI_ERR_UNSUPPORTED, "fi_crop_sets_backward: set %d needs NHWC, depth %% 128 == 0, 16-byte aligned tensors", i); return FI_ERR_UNSUPPORTED; }
+        if (zero_first) {                       // each distinct map once
+            bool seen = false;
+            for (int q = 0; q < i; ++q) seen = seen || (sets[q].grads_image == h.grads_image);
+            if (!seen) {
+                cudaError_t e = cudaMemsetAsync(h.grads_image, 0, sizeof(float) * (size_t)h.batch * h.depth * h.image_height * h.image_width, stream);
+                if (e != cudaSuccess) { set_error(FI_ERR_CUDA, "fi_crop_sets_backward: memset: %s", cudaGetErrorString(e)); return FI_ERR_CUDA; }
+            }
+        }
+        if (h.num_boxes == 0) continue;
+        BwdSet &S = dev.s[dev.n];
+        S.grads = h.grads; S.grads2 = h.grads2; S.boxes = h.boxes; S.box_ind = h.box_ind; S.src_row = h.src_row; S.gimg = h.grads_image;
+        S.B = h.batch; S.H = h.image_height; S.W = h.image_width; S.C = h.depth; S.ph = h.crop_height; S.pw = h.crop_width; S.slabs = h.depth / 128;
+        dev.first_unit[dev.n] = units;
+        units += (long)h.num_boxes * h.crop_height * S.slabs;
+        ++dev.n;
+    }
+    dev.first_unit[dev.n] = units;
+    if (units == 0) return ok();
+    crop_bwd_nhwc_sets_kernel<<<grid_for(units, kWarpsPerBlock, 8), kWarpsPerBlock * 32, 0, stream>>>(dev);
+    return check_launch("fi_crop_sets_backward");
 }
 
 // ---- reference-named launchers (lib/roi_align/src/cuda/crop_and_resize_kernel.h:8-18) ------------

@@ -21,7 +21,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib
-from .roi_align import crop_and_resize, crop_pair
+from .roi_align import crop_and_resize, crop_pair, crop_sets
 from .roi_pool import RoIPoolFunction
 from .dist import merged_class_sums
 
@@ -166,6 +166,114 @@ class Dev(nn.Module):
         return out
 
     def forward(self, x, rois, roi_cls_gt=None):
+        """Same contract as the reference (lib/sub_module.py:380-642).  With channels_last maps and roi_align every crop of
+        the pass is taken by ONE level-batched launch (crop_sets); otherwise level by level like the reference."""
+        cfg = self.config
+        if self.use_dev and self.structure == 'beta' and not cfg.DEV.ASSIGN_BOX_ON_ALL_SCALE and self.roi_type == 'roi_align' \
+                and all(m.dim() == 4 and m.size(1) % 128 == 0 and m.is_contiguous(memory_format=torch.channels_last) and not m.is_contiguous()
+                        for m in x[:4]):
+            return self._forward_batched(x, rois, roi_cls_gt)
+        return self._forward_per_level(x, rois, roi_cls_gt)
+
+    def _forward_batched(self, x, rois, roi_cls_gt=None):
+        cfg = self.config
+        train_phase = roi_cls_gt is not None
+        use_stats = train_phase and not cfg.DEV.BASELINE
+        bs, R = rois.size(0), rois.size(1)
+        total_box = bs * R
+        dev = rois.device
+        cl = torch.channels_last
+        rois_flat = rois.detach().float().contiguous().view(total_box, 4)
+        gt_flat = roi_cls_gt.contiguous().view(total_box) if train_phase else None
+        split = split_levels(roi_level(rois, self.image_shape, cfg.ROIS.ASSIGN_ANCHOR_BASE))
+        # every RoI is assigned to exactly one level, so every row below is written by a crop: no zero fill (sub_module.py:650,656)
+        pooled_out = torch.empty((total_box, self.depth, self.pool_size, self.pool_size), device=dev, memory_format=cl)
+        mask_out = torch.empty((total_box, self.depth, self.mask_pool_size, self.mask_pool_size), device=dev, memory_format=cl)
+        zf = lambda: torch.zeros(1024, self.num_classs, device=dev)
+        zc = lambda: torch.zeros(1, self.num_classs, device=dev)
+
+        # ---- pass 1: plan every crop of every level (sub_module.py:489-502,541-572)
+        specs, plan = [], []
+        for i, level in enumerate(range(2, 6)):
+            use_meta = level in (2, 3, 4)
+            want_critic = use_meta and not cfg.DEV.BASELINE
+            n_small, n_big = split.small_cnt[i], split.big_cnt[i]
+            info = dict(i=i, use_meta=use_meta, want_critic=want_critic, n_small=n_small, n_big=n_big, big=None, s7=None, s14=None)
+            if n_small > 0:
+                if use_stats and n_big > 0:
+                    bidx = split.big(i).long()
+                    info["bidx"] = bidx
+                    info["big"] = len(specs)
+                    specs.append(dict(image=x[i], boxes=rois_flat[bidx], box_ind=(bidx // R).int(), size=self.feat_pool_size))
+                s32 = split.small(i)
+                sidx = s32.long()
+                info["sidx"] = sidx
+                feat_maps = self.upsample[i if cfg.DEV.MULTI_UPSAMPLER else 0](x[i]).contiguous(memory_format=cl)   # make-up layer
+                boxes, ind = rois_flat[sidx], (sidx // R).int()
+                info["s7"] = len(specs)
+                specs.append(dict(image=feat_maps, boxes=boxes, box_ind=ind, size=self.pool_size, out=pooled_out, dst_row=s32))
+                info["s14"] = len(specs)
+                specs.append(dict(image=feat_maps, boxes=boxes, box_ind=ind, size=self.mask_pool_size, out=mask_out, dst_row=s32,
+                                  compact=want_critic))
+            plan.append(info)
+        outs, comps = crop_sets(specs) if specs else ([], [])
+        for info in plan:                          # the tensors after the (single) in-place node
+            if info["s7"] is not None:
+                pooled_out, mask_out = outs[info["s7"]], outs[info["s14"]]
+
+        # ---- pass 2: critic, class statistics, in the reference's per-level order
+        big_feat, big_cnt, small_feat, small_cnt, big_loss = [], [], [], [], []
+        small_output_all = torch.zeros(total_box, 1024, device=dev)
+        small_gt_all = torch.zeros(total_box, device=dev)
+        small_out_cnt = 0
+        for info in plan:
+            use_meta = info["use_meta"]
+            if info["n_small"] == 0:                                            # sub_module.py:456-467
+                if use_meta and use_stats:
+                    small_feat.append(zf()); small_cnt.append(zc()); big_feat.append(zf()); big_cnt.append(zc())
+                    big_loss.append(torch.zeros(1, device=dev))
+                continue
+            if use_stats:                                                       # sub_module.py:472-536
+                if info["n_big"] == 0:
+                    if use_meta:
+                        big_feat.append(zf()); big_cnt.append(zc()); big_loss.append(torch.zeros(1, device=dev))
+                else:
+                    big_box_gt = gt_flat[info["bidx"]]
+                    big_before_last = self.feat_extract(comps[info["big"]])
+                    big_output = big_before_last if cfg.DEV.LOSS_CHOICE == 'ot' else self.last_op(big_before_last)
+                    b_feat, b_cnt = assign_feat2cls(big_box_gt, big_output, self.num_classs)
+                    big_feat.append(b_feat); big_cnt.append(b_cnt)
+                    if cfg.DEV.BIG_SUPERVISE:
+                        digits = self.big_fc_layer(big_before_last.view(-1, 1024))
+                        big_loss.append(F.cross_entropy(digits, big_box_gt.long()).view(1))
+                    else:
+                        big_loss.append(torch.zeros(1, device=dev))
+            if info["want_critic"]:                                             # sub_module.py:580-600
+                small_output = self._critic(comps[info["s14"]])
+                n = info["n_small"]
+                small_output_all[small_out_cnt:small_out_cnt + n, :] = small_output.view(n, -1)
+                if train_phase:
+                    small_box_gt = gt_flat[info["sidx"]]
+                    s_feat, s_cnt = assign_feat2cls(small_box_gt, small_output, self.num_classs)
+                    small_feat.append(s_feat); small_cnt.append(s_cnt)
+                    small_gt_all[small_out_cnt:small_out_cnt + n] = small_box_gt.float()
+                else:
+                    small_gt_all[small_out_cnt:small_out_cnt + n] = 1
+                small_out_cnt += n
+        if use_stats:
+            bf = torch.stack(big_feat).unsqueeze(dim=0)
+            if cfg.DEV.BIG_FEAT_DETACH:
+                bf = bf.detach()
+            feat_out = [bf, torch.stack(big_cnt).unsqueeze(dim=0), torch.stack(small_feat).unsqueeze(dim=0),
+                        torch.stack(small_cnt).unsqueeze(dim=0), torch.stack(big_loss).unsqueeze(dim=0),
+                        small_output_all, small_gt_all]
+        elif not train_phase:
+            feat_out = [small_output_all, small_gt_all]
+        else:
+            feat_out = []
+        return pooled_out, mask_out, feat_out
+
+    def _forward_per_level(self, x, rois, roi_cls_gt=None):
         cfg = self.config
         base = cfg.ROIS.ASSIGN_ANCHOR_BASE
         if not self.use_dev:

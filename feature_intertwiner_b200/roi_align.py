@@ -59,6 +59,8 @@ def algorithmic_bytes(rec):
     U = distinct (b,y,x) tap pixels, counted on the device from the kernel's own tap table."""
     if "alg_bytes" in rec:
         return rec["alg_bytes"]
+    if "sets" in rec:
+        return sum(algorithmic_bytes(dict(kernel=rec["kernel"], **st)) for st in rec["sets"])
     B, Cc, H, W = rec["im_size"]
     ph, pw = rec["crop"]
     R = rec["boxes"].size(0)
@@ -216,6 +218,133 @@ class _CropPair(torch.autograd.Function):
 def crop_pair(image, boxes, box_ind, dst_row, out_a, size_a, out_b, size_b, compact_b=False):
     """See _CropPair.  Returns (out_a, out_b[, compact_b])."""
     return _CropPair.apply(image, boxes, box_ind, dst_row, out_a, out_b, int(size_a), int(size_b), bool(compact_b))
+
+
+class _CropSets(torch.autograd.Function):
+    """Every RoIAlign of one Dev.forward pass as ONE autograd node and ONE launch each way (fi_crop_sets_forward /
+    fi_crop_sets_backward): the per-level calls of lib/sub_module.py:429-600 are far too small to fill a B200 one at a
+    time (a few hundred boxes on the 26x42 map of P5).  apply(plan, *images, *outs)."""
+
+    @staticmethod
+    def forward(ctx, plan, *tensors):
+        n_img, n_out = plan["n_img"], plan["n_out"]
+        images, outs = list(tensors[:n_img]), list(tensors[n_img:n_img + n_out])
+        cl = torch.channels_last
+        dev = images[0].device
+        fixed = []
+        for im in images:
+            _lib.require_cuda(im)
+            layout, im = _lib.layout_of(im)
+            if layout != _lib.FI_LAYOUT_NHWC or im.dtype != torch.float32 or im.size(1) % 128 != 0:
+                raise _lib.FiError("crop_sets needs fp32 channels_last feature maps with C % 128 == 0")
+            fixed.append(im)
+        images = fixed
+        arr = (_lib.FwdSet * len(plan["sets"]))()
+        compacts, keep = [], []
+        for k, sp in enumerate(plan["sets"]):
+            im = images[sp["image"]]
+            B, Cc, H, W = im.shape
+            boxes, box_ind = _prep_boxes(sp["boxes"], sp["box_ind"], dev)
+            R, P = boxes.size(0), sp["size"]
+            dst_row = None if sp["dst_row"] is None else sp["dst_row"].to(device=dev, dtype=torch.int32).contiguous()
+            out = outs[sp["out"]] if sp["out"] is not None else None
+            if out is not None and not (out.is_contiguous(memory_format=cl) and tuple(out.shape[1:]) == (Cc, P, P) and out.dtype == torch.float32):
+                raise _lib.FiError("crop_sets: `out` of set %d must be fp32 channels_last [rows,%d,%d,%d]" % (k, Cc, P, P))
+            comp = torch.empty((R, Cc, P, P), device=dev, memory_format=cl) if (sp["compact"] or out is None) else None
+            compacts.append(comp)
+            primary, second = (out, comp) if out is not None else (comp, None)
+            arr[k] = _lib.FwdSet(_lib.ptr(im), _lib.ptr(boxes), _lib.ptr(box_ind), _lib.ptr(dst_row) if out is not None else None,
+                                 _lib.ptr(primary), _lib.ptr(second), B, H, W, Cc, R, P, P, float(sp.get("extrapolation", 0.0)))
+            keep.append(dict(boxes=boxes, box_ind=box_ind, dst_row=dst_row, im_size=(B, Cc, H, W), crop=(P, P), dual=(out is not None and comp is not None)))
+        with torch.cuda.device(dev), _Timed("crop_fwd_nhwc", sets=keep):
+            _lib.check(_lib.lib().fi_crop_sets_forward(arr, len(plan["sets"]), _lib.stream_ptr(dev)))
+        ctx.mark_dirty(*outs)
+        ctx.set_materialize_grads(False)
+        ctx.plan, ctx.keep = plan, keep
+        ctx.comp_slots = [k for k, c in enumerate(compacts) if c is not None]
+        return tuple(outs) + tuple(c for c in compacts if c is not None)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        plan, keep = ctx.plan, ctx.keep
+        n_img, n_out = plan["n_img"], plan["n_out"]
+        cl = torch.channels_last
+        g_outs = [None if g is None else g.contiguous(memory_format=cl) for g in grads[:n_out]]
+        g_comp = {k: (None if g is None else g.contiguous(memory_format=cl)) for k, g in zip(ctx.comp_slots, grads[n_out:])}
+        dev = keep[0]["boxes"].device
+        # one flat, zero-filled buffer holds every dense gradient map (one memset instead of one per map)
+        sizes = {}
+        for k, sp in enumerate(plan["sets"]):
+            sizes[sp["image"]] = keep[k]["im_size"]
+        numel = {i: sz[0] * sz[1] * sz[2] * sz[3] for i, sz in sizes.items()}
+        flat = torch.zeros(sum(numel.values()), device=dev, dtype=torch.float32)
+        g_images, off = {}, 0
+        for i in sorted(sizes):
+            B, Cc, H, W = sizes[i]
+            g_images[i] = flat[off:off + numel[i]].view(B, H, W, Cc).permute(0, 3, 1, 2)
+            off += numel[i]
+        sets, nbytes = [], 0
+        for k, sp in enumerate(plan["sets"]):
+            kp = keep[k]
+            B, Cc, H, W = kp["im_size"]
+            P = kp["crop"][0]
+            R = kp["boxes"].size(0)
+            gs = g_outs[sp["out"]] if sp["out"] is not None else None
+            gc = g_comp.get(k)
+            if gs is not None:
+                g1, g2, rows = gs, gc, kp["dst_row"]
+            elif gc is not None:
+                g1, g2, rows = gc, None, None
+            else:
+                continue
+            sets.append(_lib.BwdSet(_lib.ptr(g_images[sp["image"]]), _lib.ptr(g1), _lib.ptr(g2), _lib.ptr(kp["boxes"]), _lib.ptr(kp["box_ind"]),
+                                    _lib.ptr(rows), B, H, W, Cc, R, P, P))
+            nbytes += 4 * Cc * R * P * P * (2 if g2 is not None else 1) + 20 * R
+        nbytes += 4 * sum(numel.values())
+        if sets:
+            L = _lib.lib()
+            with torch.cuda.device(dev), _Timed("crop_bwd_nhwc", alg_bytes=nbytes):
+                if L.fi_get_deterministic():
+                    by_map = {}
+                    for st in sets:
+                        by_map.setdefault(st.grads_image, []).append(st)
+                    for ptr, group in by_map.items():
+                        arr = (_lib.CropSet * len(group))(*[_lib.CropSet(g.grads, g.grads2, g.boxes, g.box_ind, g.src_row, g.num_boxes, g.crop_height, g.crop_width)
+                                                            for g in group])
+                        g0 = group[0]
+                        _lib.check(L.fi_crop_and_resize_backward_multi(arr, len(group), g0.batch, g0.image_height, g0.image_width, g0.depth, ptr, 0, 1,
+                                                                       _lib.stream_ptr(dev)))
+                else:
+                    arr = (_lib.BwdSet * len(sets))(*sets)
+                    _lib.check(L.fi_crop_sets_backward(arr, len(sets), 0, _lib.stream_ptr(dev)))
+        return (None,) + tuple(g_images.get(i) for i in range(n_img)) + tuple(g_outs)
+
+
+def crop_sets(specs):
+    """specs: list of dict(image=Tensor, boxes=[R,4], box_ind=[R], size=int, out=Tensor|None, dst_row=[R]|None, compact=bool).
+    A set with ``out`` writes crop r into row ``dst_row[r]`` of ``out`` (several sets may share one ``out``) and, with
+    ``compact``, also returns the compact [R,C,size,size] crop; a set without ``out`` returns the compact crop only.
+    Returns (outs_by_spec, compacts_by_spec): per spec the (updated) ``out`` or None, and the compact crop or None."""
+    images, outs, sets = [], [], []
+
+    def slot(lst, t):
+        for i, u in enumerate(lst):
+            if u is t:
+                return i
+        lst.append(t)
+        return len(lst) - 1
+    for sp in specs:
+        sets.append(dict(image=slot(images, sp["image"]), out=(slot(outs, sp["out"]) if sp.get("out") is not None else None),
+                         boxes=sp["boxes"], box_ind=sp["box_ind"], dst_row=sp.get("dst_row"), size=int(sp["size"]),
+                         compact=bool(sp.get("compact", False)), extrapolation=float(sp.get("extrapolation", 0.0))))
+        if sets[-1]["out"] is not None and sets[-1]["dst_row"] is None:
+            raise _lib.FiError("crop_sets: a set with `out` needs `dst_row`")
+    plan = dict(n_img=len(images), n_out=len(outs), sets=sets)
+    res = _CropSets.apply(plan, *images, *outs)
+    new_outs, comps = res[:len(outs)], list(res[len(outs):])
+    out_by_spec = [new_outs[st["out"]] if st["out"] is not None else None for st in sets]
+    comp_by_spec = [comps.pop(0) if (st["compact"] or st["out"] is None) else None for st in sets]
+    return out_by_spec, comp_by_spec
 
 
 def set_deterministic(on=True):

@@ -125,6 +125,33 @@ int fi_crop_and_resize_backward_multi(const fi_crop_set *sets, int num_sets, int
 int fi_set_deterministic(int on);
 int fi_get_deterministic(void);
 
+/* Level-batched RoIAlign: every crop set of one Dev.forward pass (lib/sub_module.py:429-600: up to 3 "big" sets on the raw
+ * maps and 4 x 2 "small" sets on the made-up maps, each with its own map, boxes and crop size) in ONE launch, forward and
+ * backward.  NHWC, depth % 128 == 0.  At most 12 sets. */
+typedef struct fi_fwd_set {
+    const float *image;      /* [batch,H,W,depth] */
+    const float *boxes;      /* [num_boxes,4] */
+    const int *box_ind;      /* [num_boxes] */
+    const int *dst_row;      /* [num_boxes] or NULL (row r) */
+    float *crops;            /* rows dst_row[r] */
+    float *crops_compact;    /* NULL, or a second copy at row r */
+    int batch, image_height, image_width, depth, num_boxes, crop_height, crop_width;
+    float extrapolation_value;
+} fi_fwd_set;
+int fi_crop_sets_forward(const fi_fwd_set *sets, int num_sets, cudaStream_t stream);
+
+typedef struct fi_bwd_set {
+    float *grads_image;      /* [batch,H,W,depth]; several sets may name the same map */
+    const float *grads;      /* rows src_row[r] (row r when NULL) */
+    const float *grads2;     /* NULL, or a second gradient at row r, added to the first */
+    const float *boxes;
+    const int *box_ind;
+    const int *src_row;
+    int batch, image_height, image_width, depth, num_boxes, crop_height, crop_width;
+} fi_bwd_set;
+/* zero_first != 0: every distinct grads_image is zero-filled once before the (single) reduction launch. */
+int fi_crop_sets_backward(const fi_bwd_set *sets, int num_sets, int zero_first, cudaStream_t stream);
+
 /* Integer taps of every sample, taps[num_boxes,crop_h,crop_w,5] = (y_lo,y_hi,x_lo,x_hi,inside): the "RoI
  * indices" the parity bar requires bit-exact (crop_and_resize_kernel.cu:40-70). */
 int fi_crop_taps(const float *boxes, int num_boxes, int image_height, int image_width, int crop_height,

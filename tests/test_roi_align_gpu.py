@@ -166,6 +166,47 @@ def test_crop_pair_matches_separate_calls():
     torch.testing.assert_close(xa.grad, xb.grad, rtol=1e-4, atol=1e-4)
 
 
+def test_crop_sets_matches_separate_calls():
+    """The level-batched launch (fi_crop_sets_forward/backward) == the same crops taken one call at a time."""
+    fi = _fi()
+    cl = torch.channels_last
+    g = torch.Generator().manual_seed(21)
+    maps = [torch.randn(2, 256, 30 >> k, 34 >> k, generator=g).cuda().contiguous(memory_format=cl) for k in range(2)]
+    cases = []
+    for k in range(2):
+        _, rois, box_ind = _case(30 + k, 2, 1, 30 >> k, 34 >> k, 40 + 10 * k, zero_rows=3)
+        cases.append((rois.cuda(), box_ind.cuda()))
+    total = 40 + 50
+    rows = torch.randperm(total, generator=g).int().cuda()
+    dst = [rows[:40], rows[40:]]
+    for deterministic in (False, True):
+        old = fi.set_deterministic(deterministic)
+        try:
+            xa = [m.clone().requires_grad_() for m in maps]
+            o7 = torch.empty(total, 256, 7, 7, device="cuda").contiguous(memory_format=cl)
+            o14 = torch.empty(total, 256, 14, 14, device="cuda").contiguous(memory_format=cl)
+            specs = [dict(image=xa[0], boxes=cases[1][0], box_ind=cases[1][1], size=14)]          # a compact-only "big" set
+            for k in range(2):
+                specs.append(dict(image=xa[k], boxes=cases[k][0], box_ind=cases[k][1], size=7, out=o7, dst_row=dst[k]))
+                specs.append(dict(image=xa[k], boxes=cases[k][0], box_ind=cases[k][1], size=14, out=o14, dst_row=dst[k], compact=(k == 0)))
+            outs, comps = fi.crop_sets(specs)
+            o7n, o14n = outs[1], outs[2]
+            xb = [m.clone().requires_grad_() for m in maps]
+            big = fi.crop_and_resize(xb[0], cases[1][0], cases[1][1], 14, 14)
+            r7 = [fi.crop_and_resize(xb[k], cases[k][0], cases[k][1], 7, 7) for k in range(2)]
+            r14 = [fi.crop_and_resize(xb[k], cases[k][0], cases[k][1], 14, 14) for k in range(2)]
+            assert torch.equal(comps[0], big) and torch.equal(comps[2], r14[0]) and comps[1] is None and comps[4] is None
+            for k in range(2):
+                assert torch.equal(o7n[dst[k].long()], r7[k]) and torch.equal(o14n[dst[k].long()], r14[k])
+            gb, g7, g14, gc = (torch.randn(t.shape, generator=g).cuda() for t in (big.cpu(), o7n.cpu(), o14n.cpu(), r14[0].cpu()))
+            torch.autograd.backward([comps[0], o7n, o14n, comps[2]], [gb, g7, g14, gc])
+            torch.autograd.backward([big] + r7 + r14, [gb, g7[dst[0].long()], g7[dst[1].long()], g14[dst[0].long()] + gc, g14[dst[1].long()]])
+            for a, b in zip(xa, xb):
+                torch.testing.assert_close(a.grad, b.grad, rtol=1e-4, atol=1e-4)
+        finally:
+            fi.set_deterministic(old)
+
+
 def test_known_answers():
     """SURVEY.md 8(c) i-vi: identity crop, constant image, linear ramp, extrapolation, P=1 centre, zero box."""
     fi = _fi()
