@@ -31,9 +31,19 @@ __global__ void roi_level_kernel(const float *__restrict__ rois, int n, float de
 constexpr int kSplitThreads = 1024;
 constexpr int kLists = 8;
 
+// Optional gather outputs (all [4, n, ...], same order as the index lists) so the host does not have to run
+// rois[idx], idx // R, gt[idx] as separate torch ops per level:
+struct SplitGather {
+    const float4 *rois;        // [n] (y1,x1,y2,x2)
+    const int *gt;             // [n] class ids or null
+    int rois_per_image;
+    float4 *small_boxes, *big_boxes;
+    int *small_ind, *big_ind, *small_gt, *big_gt;
+};
+
 __global__ void __launch_bounds__(kSplitThreads) split_levels_kernel(const int *__restrict__ level, int n, int *__restrict__ small_idx,
                                                                     int *__restrict__ small_cnt, int *__restrict__ big_idx,
-                                                                    int *__restrict__ big_cnt, int *__restrict__ slot) {
+                                                                    int *__restrict__ big_cnt, int *__restrict__ slot, const SplitGather G) {
     __shared__ int warp_tot[kLists][kSplitThreads / 32];
     __shared__ int list_tot[kLists];
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
@@ -81,8 +91,16 @@ __global__ void __launch_bounds__(kSplitThreads) split_levels_kernel(const int *
         const int l = level[i];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            if (l == 2 + k) { small_idx[k * n + base[k]] = i; slot[i] = base[k]; ++base[k]; }
-            if (l > 2 + k) { big_idx[k * n + base[4 + k]] = i; ++base[4 + k]; }
+            if (l == 2 + k) {
+                const int o = k * n + base[k];
+                small_idx[o] = i; slot[i] = base[k]; ++base[k];
+                if (G.rois) { G.small_boxes[o] = G.rois[i]; G.small_ind[o] = i / G.rois_per_image; if (G.gt) G.small_gt[o] = G.gt[i]; }
+            }
+            if (l > 2 + k) {
+                const int o = k * n + base[4 + k];
+                big_idx[o] = i; ++base[4 + k];
+                if (G.rois) { G.big_boxes[o] = G.rois[i]; G.big_ind[o] = i / G.rois_per_image; if (G.gt) G.big_gt[o] = G.gt[i]; }
+            }
         }
     }
     if (t < 4) { small_cnt[t] = list_tot[t]; big_cnt[t] = list_tot[4 + t]; }
@@ -217,8 +235,25 @@ FI_API int fi_split_levels(const int *level, int n, int *small_idx, int *small_c
                            cudaStream_t stream) {
     FI_REQUIRE(n >= 0 && n <= 65536, "fi_split_levels: n=%d outside [0,65536]", n);
     FI_REQUIRE(small_cnt && big_cnt && (n == 0 || (level && small_idx && big_idx && slot)), "fi_split_levels: null pointer");
-    split_levels_kernel<<<1, kSplitThreads, 0, stream>>>(level, n, small_idx, small_cnt, big_idx, big_cnt, slot);
+    SplitGather G = {};
+    split_levels_kernel<<<1, kSplitThreads, 0, stream>>>(level, n, small_idx, small_cnt, big_idx, big_cnt, slot, G);
     return check_launch("fi_split_levels");
+}
+
+FI_API int fi_split_levels_gather(const int *level, const float *rois, const int *gt, int n, int rois_per_image, int *small_idx, int *small_cnt,
+                                  int *big_idx, int *big_cnt, int *slot, float *small_boxes, int *small_ind, int *small_gt, float *big_boxes,
+                                  int *big_ind, int *big_gt, cudaStream_t stream) {
+    FI_REQUIRE(n >= 0 && n <= 65536 && rois_per_image > 0, "fi_split_levels_gather: n=%d outside [0,65536] or bad rois_per_image", n);
+    FI_REQUIRE(small_cnt && big_cnt && (n == 0 || (level && rois && small_idx && big_idx && slot && small_boxes && small_ind && big_boxes && big_ind)),
+               "fi_split_levels_gather: null pointer");
+    FI_REQUIRE(gt == nullptr || (small_gt && big_gt), "fi_split_levels_gather: gt given without small_gt / big_gt");
+    FI_REQUIRE(((uintptr_t)rois % 16 == 0) && ((uintptr_t)small_boxes % 16 == 0) && ((uintptr_t)big_boxes % 16 == 0), "fi_split_levels_gather: box arrays must be 16-byte aligned");
+    SplitGather G;
+    G.rois = reinterpret_cast<const float4 *>(rois); G.gt = gt; G.rois_per_image = rois_per_image;
+    G.small_boxes = reinterpret_cast<float4 *>(small_boxes); G.big_boxes = reinterpret_cast<float4 *>(big_boxes);
+    G.small_ind = small_ind; G.big_ind = big_ind; G.small_gt = small_gt; G.big_gt = big_gt;
+    split_levels_kernel<<<1, kSplitThreads, 0, stream>>>(level, n, small_idx, small_cnt, big_idx, big_cnt, slot, G);
+    return check_launch("fi_split_levels_gather");
 }
 
 FI_API int fi_segment_mean_forward(const int *gt, const float *feat, int k, int F, int ncls, float *mean, float *cnt,

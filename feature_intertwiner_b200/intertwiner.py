@@ -41,10 +41,12 @@ def roi_level(rois, image_shape, base=224.0):
 
 
 class LevelSplit(object):
-    """Per-level index lists of flat RoI ids (torch.nonzero order) for levels 2..5."""
+    """Per-level index lists of flat RoI ids (torch.nonzero order) for levels 2..5, optionally with the gathered boxes,
+    image indices and class ids of every list (one kernel, one 8-int host read for all of it)."""
 
-    def __init__(self, small_idx, small_cnt, big_idx, big_cnt, slot):
+    def __init__(self, small_idx, small_cnt, big_idx, big_cnt, slot, gathered=None):
         self.small_idx, self.big_idx, self.slot = small_idx, big_idx, slot
+        self.g = gathered
         counts = torch.cat([small_cnt, big_cnt]).tolist()        # the only host sync of the split
         self.small_cnt, self.big_cnt = counts[:4], counts[4:]
 
@@ -54,22 +56,55 @@ class LevelSplit(object):
     def big(self, i):
         return self.big_idx[i, : self.big_cnt[i]]
 
+    def small_boxes(self, i):
+        return self.g["small_boxes"][i, : self.small_cnt[i]]
 
-def split_levels(level):
-    """level[...] int32 -> LevelSplit: small(l) = {level == l}, big(l) = {level > l} (lib/sub_module.py:442,367-378)."""
+    def small_ind(self, i):
+        return self.g["small_ind"][i, : self.small_cnt[i]]
+
+    def small_gt(self, i):
+        return self.g["small_gt"][i, : self.small_cnt[i]]
+
+    def big_boxes(self, i):
+        return self.g["big_boxes"][i, : self.big_cnt[i]]
+
+    def big_ind(self, i):
+        return self.g["big_ind"][i, : self.big_cnt[i]]
+
+    def big_gt(self, i):
+        return self.g["big_gt"][i, : self.big_cnt[i]]
+
+
+def split_levels(level, rois=None, gt=None):
+    """level[...] int32 -> LevelSplit: small(l) = {level == l}, big(l) = {level > l} (lib/sub_module.py:442,367-378).
+    With ``rois`` ([bs,R,4]) the same launch also gathers boxes / image index / class id (``gt`` [bs,R]) of every list."""
     _lib.require_cuda(level)
     flat = level.contiguous().view(-1)
     n = flat.numel()
     dev = flat.device
-    small_idx = torch.empty((4, max(n, 1)), device=dev, dtype=torch.int32)
-    big_idx = torch.empty((4, max(n, 1)), device=dev, dtype=torch.int32)
+    m = max(n, 1)
+    small_idx = torch.empty((4, m), device=dev, dtype=torch.int32)
+    big_idx = torch.empty((4, m), device=dev, dtype=torch.int32)
     small_cnt = torch.empty((4,), device=dev, dtype=torch.int32)
     big_cnt = torch.empty((4,), device=dev, dtype=torch.int32)
-    slot = torch.empty((max(n, 1),), device=dev, dtype=torch.int32)
+    slot = torch.empty((m,), device=dev, dtype=torch.int32)
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().fi_split_levels(_lib.ptr(flat), n, _lib.ptr(small_idx), _lib.ptr(small_cnt), _lib.ptr(big_idx),
-                                              _lib.ptr(big_cnt), _lib.ptr(slot), _lib.stream_ptr(dev)))
-    return LevelSplit(small_idx, small_cnt, big_idx, big_cnt, slot)
+        if rois is None:
+            _lib.check(_lib.lib().fi_split_levels(_lib.ptr(flat), n, _lib.ptr(small_idx), _lib.ptr(small_cnt), _lib.ptr(big_idx),
+                                                  _lib.ptr(big_cnt), _lib.ptr(slot), _lib.stream_ptr(dev)))
+            return LevelSplit(small_idx, small_cnt, big_idx, big_cnt, slot)
+        rois_flat = rois.detach().float().contiguous().view(-1, 4)
+        gt_flat = None if gt is None else gt.detach().to(torch.int32).contiguous().view(-1)
+        g = dict(small_boxes=torch.empty((4, m, 4), device=dev), big_boxes=torch.empty((4, m, 4), device=dev),
+                 small_ind=torch.empty((4, m), device=dev, dtype=torch.int32), big_ind=torch.empty((4, m), device=dev, dtype=torch.int32))
+        if gt_flat is not None:
+            g["small_gt"] = torch.empty((4, m), device=dev, dtype=torch.int32)
+            g["big_gt"] = torch.empty((4, m), device=dev, dtype=torch.int32)
+        _lib.check(_lib.lib().fi_split_levels_gather(
+            _lib.ptr(flat), _lib.ptr(rois_flat), _lib.ptr(gt_flat), n, int(rois.size(-2)), _lib.ptr(small_idx), _lib.ptr(small_cnt),
+            _lib.ptr(big_idx), _lib.ptr(big_cnt), _lib.ptr(slot), _lib.ptr(g["small_boxes"]), _lib.ptr(g["small_ind"]), _lib.ptr(g.get("small_gt")),
+            _lib.ptr(g["big_boxes"]), _lib.ptr(g["big_ind"]), _lib.ptr(g.get("big_gt")), _lib.stream_ptr(dev)))
+    return LevelSplit(small_idx, small_cnt, big_idx, big_cnt, slot, gathered=g)
 
 
 # ----------------------------------------------------------------------------------------------- segment mean
@@ -184,8 +219,8 @@ class Dev(nn.Module):
         dev = rois.device
         cl = torch.channels_last
         rois_flat = rois.detach().float().contiguous().view(total_box, 4)
-        gt_flat = roi_cls_gt.contiguous().view(total_box) if train_phase else None
-        split = split_levels(roi_level(rois, self.image_shape, cfg.ROIS.ASSIGN_ANCHOR_BASE))
+        # one launch: level lists + rois[idx], idx // R, gt[idx] of every list (sub_module.py:489-493,541-548)
+        split = split_levels(roi_level(rois, self.image_shape, cfg.ROIS.ASSIGN_ANCHOR_BASE), rois=rois, gt=roi_cls_gt if train_phase else None)
         # every RoI is assigned to exactly one level, so every row below is written by a crop: no zero fill (sub_module.py:650,656)
         pooled_out = torch.empty((total_box, self.depth, self.pool_size, self.pool_size), device=dev, memory_format=cl)
         mask_out = torch.empty((total_box, self.depth, self.mask_pool_size, self.mask_pool_size), device=dev, memory_format=cl)
@@ -201,15 +236,11 @@ class Dev(nn.Module):
             info = dict(i=i, use_meta=use_meta, want_critic=want_critic, n_small=n_small, n_big=n_big, big=None, s7=None, s14=None)
             if n_small > 0:
                 if use_stats and n_big > 0:
-                    bidx = split.big(i).long()
-                    info["bidx"] = bidx
                     info["big"] = len(specs)
-                    specs.append(dict(image=x[i], boxes=rois_flat[bidx], box_ind=(bidx // R).int(), size=self.feat_pool_size))
+                    specs.append(dict(image=x[i], boxes=split.big_boxes(i), box_ind=split.big_ind(i), size=self.feat_pool_size))
                 s32 = split.small(i)
-                sidx = s32.long()
-                info["sidx"] = sidx
                 feat_maps = self.upsample[i if cfg.DEV.MULTI_UPSAMPLER else 0](x[i]).contiguous(memory_format=cl)   # make-up layer
-                boxes, ind = rois_flat[sidx], (sidx // R).int()
+                boxes, ind = split.small_boxes(i), split.small_ind(i)
                 info["s7"] = len(specs)
                 specs.append(dict(image=feat_maps, boxes=boxes, box_ind=ind, size=self.pool_size, out=pooled_out, dst_row=s32))
                 info["s14"] = len(specs)
@@ -238,7 +269,7 @@ class Dev(nn.Module):
                     if use_meta:
                         big_feat.append(zf()); big_cnt.append(zc()); big_loss.append(torch.zeros(1, device=dev))
                 else:
-                    big_box_gt = gt_flat[info["bidx"]]
+                    big_box_gt = split.big_gt(info["i"])
                     big_before_last = self.feat_extract(comps[info["big"]])
                     big_output = big_before_last if cfg.DEV.LOSS_CHOICE == 'ot' else self.last_op(big_before_last)
                     b_feat, b_cnt = assign_feat2cls(big_box_gt, big_output, self.num_classs)
@@ -253,7 +284,7 @@ class Dev(nn.Module):
                 n = info["n_small"]
                 small_output_all[small_out_cnt:small_out_cnt + n, :] = small_output.view(n, -1)
                 if train_phase:
-                    small_box_gt = gt_flat[info["sidx"]]
+                    small_box_gt = split.small_gt(info["i"])
                     s_feat, s_cnt = assign_feat2cls(small_box_gt, small_output, self.num_classs)
                     small_feat.append(s_feat); small_cnt.append(s_cnt)
                     small_gt_all[small_out_cnt:small_out_cnt + n] = small_box_gt.float()

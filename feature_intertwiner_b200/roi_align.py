@@ -272,17 +272,13 @@ class _CropSets(torch.autograd.Function):
         g_outs = [None if g is None else g.contiguous(memory_format=cl) for g in grads[:n_out]]
         g_comp = {k: (None if g is None else g.contiguous(memory_format=cl)) for k, g in zip(ctx.comp_slots, grads[n_out:])}
         dev = keep[0]["boxes"].device
-        # one flat, zero-filled buffer holds every dense gradient map (one memset instead of one per map)
+        # one standalone tensor per dense gradient map (autograd can then hand it to the leaf without a copy); the C entry
+        # zero-fills each distinct map once
         sizes = {}
         for k, sp in enumerate(plan["sets"]):
             sizes[sp["image"]] = keep[k]["im_size"]
         numel = {i: sz[0] * sz[1] * sz[2] * sz[3] for i, sz in sizes.items()}
-        flat = torch.zeros(sum(numel.values()), device=dev, dtype=torch.float32)
-        g_images, off = {}, 0
-        for i in sorted(sizes):
-            B, Cc, H, W = sizes[i]
-            g_images[i] = flat[off:off + numel[i]].view(B, H, W, Cc).permute(0, 3, 1, 2)
-            off += numel[i]
+        g_images = {i: torch.empty(sizes[i], device=dev, dtype=torch.float32, memory_format=cl) for i in sorted(sizes)}
         sets, nbytes = [], 0
         for k, sp in enumerate(plan["sets"]):
             kp = keep[k]
@@ -308,7 +304,7 @@ class _CropSets(torch.autograd.Function):
                     by_map = {}
                     for st in sets:
                         by_map.setdefault(st.grads_image, []).append(st)
-                    for ptr, group in by_map.items():
+                    for ptr, group in by_map.items():     # write-once gather: no zero fill needed
                         arr = (_lib.CropSet * len(group))(*[_lib.CropSet(g.grads, g.grads2, g.boxes, g.box_ind, g.src_row, g.num_boxes, g.crop_height, g.crop_width)
                                                             for g in group])
                         g0 = group[0]
@@ -316,7 +312,11 @@ class _CropSets(torch.autograd.Function):
                                                                        _lib.stream_ptr(dev)))
                 else:
                     arr = (_lib.BwdSet * len(sets))(*sets)
-                    _lib.check(L.fi_crop_sets_backward(arr, len(sets), 0, _lib.stream_ptr(dev)))
+                    _lib.check(L.fi_crop_sets_backward(arr, len(sets), 1, _lib.stream_ptr(dev)))
+        touched = {st.grads_image for st in sets}
+        for i, gi in g_images.items():
+            if _lib.ptr(gi) not in touched:
+                gi.zero_()                       # a map none of whose crops received a gradient
         return (None,) + tuple(g_images.get(i) for i in range(n_img)) + tuple(g_outs)
 
 

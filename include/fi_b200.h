@@ -172,6 +172,13 @@ int fi_roi_level(const float *rois, int n, float image_area, float base, int *le
 int fi_split_levels(const int *level, int n, int *small_idx, int *small_cnt, int *big_idx, int *big_cnt, int *slot,
                     cudaStream_t stream);
 
+/* Same launch, additionally emitting what Dev.forward gathers per level (lib/sub_module.py:489-493,541-548):
+ * small_boxes/big_boxes [4,n,4] = rois[idx], small_ind/big_ind [4,n] = idx / rois_per_image (the image a RoI belongs to),
+ * small_gt/big_gt [4,n] = gt[idx] (only when gt != NULL). */
+int fi_split_levels_gather(const int *level, const float *rois, const int *gt, int n, int rois_per_image, int *small_idx,
+                           int *small_cnt, int *big_idx, int *big_cnt, int *slot, float *small_boxes, int *small_ind,
+                           int *small_gt, float *big_boxes, int *big_ind, int *big_gt, cudaStream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * 4. Per-class statistics (lib/sub_module.py:664-684 _assign_feat2cls).
  * ------------------------------------------------------------------------------------------- */

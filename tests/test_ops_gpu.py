@@ -145,6 +145,19 @@ def test_split_matches_nonzero(n):
         assert torch.equal(sp.small(i), small) and torch.equal(sp.big(i), big)
         if small.numel():
             assert torch.equal(sp.slot[small.long()], torch.arange(small.numel(), dtype=torch.int32).cuda())
+    if n >= 257:
+        # same launch + gathers: rois[idx], idx // R, gt[idx] (lib/sub_module.py:489-493,541-548)
+        R = 257 if n == 257 else 16
+        g2 = torch.Generator().manual_seed(n + 1)
+        rois = torch.rand(n // R, R, 4, generator=g2).cuda()
+        gt = torch.randint(0, 81, (n // R, R), generator=g2, dtype=torch.int32).cuda()
+        lv = level[: (n // R) * R].view(n // R, R)
+        sg = fi.split_levels(lv, rois=rois, gt=gt)
+        flat_r, flat_g = rois.view(-1, 4), gt.view(-1)
+        for i, l in enumerate(range(2, 6)):
+            for idx, boxes, ind, cls in ((sg.small(i), sg.small_boxes(i), sg.small_ind(i), sg.small_gt(i)),
+                                         (sg.big(i), sg.big_boxes(i), sg.big_ind(i), sg.big_gt(i))):
+                assert torch.equal(boxes, flat_r[idx.long()]) and torch.equal(ind, (idx // R).int()) and torch.equal(cls, flat_g[idx.long()])
 
 
 # ------------------------------------------------------------------------------------------------ segment mean / buffer
