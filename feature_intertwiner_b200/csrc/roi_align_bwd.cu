@@ -332,7 +332,19 @@ FI_API int fi_crop_and_resize_backward_multi(const fi_crop_set *sets, int num_se
         set_error(FI_ERR_UNSUPPORTED, "deterministic RoIAlign backward needs depth %% 128 == 0, crops <= 16x16, 16-byte aligned NHWC tensors");
         return FI_ERR_UNSUPPORTED;
     }
-    // one zero-fill for all sets, then vector reductions set by set
+    // L2-resident banded reduction when the shape qualifies (roi_align_bwd_banded.cu) ...
+    if (num_sets <= 12 && depth % 128 == 0) {
+        fi_bwd_set tmp[12];
+        for (int i = 0; i < num_sets; ++i) {
+            tmp[i].grads_image = grads_image; tmp[i].grads = sets[i].grads; tmp[i].grads2 = sets[i].grads2; tmp[i].boxes = sets[i].boxes;
+            tmp[i].box_ind = sets[i].box_ind; tmp[i].src_row = sets[i].src_row; tmp[i].batch = batch; tmp[i].image_height = image_height;
+            tmp[i].image_width = image_width; tmp[i].depth = depth; tmp[i].num_boxes = sets[i].num_boxes;
+            tmp[i].crop_height = sets[i].crop_height; tmp[i].crop_width = sets[i].crop_width;
+        }
+        const int rc = fi_crop_sets_backward(tmp, num_sets, accumulate ? 0 : 1, stream);
+        if (rc != FI_ERR_UNSUPPORTED) return rc;
+    }
+    // ... else one zero-fill for all sets, then vector reductions set by set
     if (!accumulate) {
         cudaError_t e = cudaMemsetAsync(grads_image, 0, sizeof(float) * (size_t)batch * depth * image_height * image_width, stream);
         if (e != cudaSuccess) { set_error(FI_ERR_CUDA, "fi_crop_and_resize_backward_multi: memset: %s", cudaGetErrorString(e)); return FI_ERR_CUDA; }
