@@ -511,9 +511,10 @@ FI_API int fi_crop_sets_backward(const fi_bwd_set *sets, int num_sets, int zero_
         if (int e = check_common(h.grads, h.boxes, h.box_ind, h.grads_image, h.num_boxes, h.batch, h.image_height, h.image_width, h.crop_height,
                                  h.crop_width, h.depth)) return e;
     }
-    {   // L2-resident banded reduction (one persistent launch, zero fill fused); FI_BWD=plain selects the kernel below
+    {   // FI_BWD=banded selects the L2-resident banded reduction (roi_align_bwd_banded.cu): ideal DRAM traffic (4.6 GB vs
+        // 9.5 GB on C2, ncu) but band-boundary stalls make it slower today (2.7 ms vs 1.95 ms) -- experimental, see DESIGN.md
         const char *mode = getenv("FI_BWD");
-        if (!(mode && mode[0] == 'p')) {
+        if (mode && mode[0] == 'b') {
             const int rc = fi_banded_backward(sets, num_sets, zero_first, stream);
             if (rc != FI_ERR_UNSUPPORTED) return rc;
         }

@@ -8,10 +8,10 @@
 // RoIs come grouped by image (torch.nonzero order), and one image of the largest map is 71.5 MB.  So the work is
 // ordered in BANDS: zero image b of a map, immediately reduce into it every crop of every set whose box lies in
 // image b (the band is still in L2: reductions hit, nothing is fetched), move on; the band is written to DRAM once,
-// when the next band pushes it out.  One persistent launch, no grid barrier: CTAs draw tickets from an ordered item
-// list  Z(m,0) S(m,0) Z(m,1) S(m,1) ...  (Z = 256 KB zero-fill chunks, S = 8 warp-units of reduction work); an S item
-// waits on its band's zero-fill counter.  Tickets are handed out in order and Z items never wait, so a waiting CTA is
-// always waiting on CTAs that are already running: no deadlock for any grid size.
+// when the next band pushes it out.  One persistent launch, no grid barrier: the warps of a chip-filling grid walk an
+// ordered unit list  S(m,0) S(m,1) ...  (the usual (box,row,slab) reduction units) with a fixed stride; the first
+// warps to reach a band clear it cooperatively (32 KB chunks drawn from a per-band counter -- no chunk has a static
+// owner, so nobody waits on a warp that is busy elsewhere) and everyone waits only for the last chunks in flight.
 //
 // A tiny single-CTA planner checks on the device that box_ind is non-decreasing per set and builds the item table;
 // sets that are not sorted by image fall back to one band per map (zero everything, then reduce).
@@ -22,8 +22,8 @@ namespace fi {
 constexpr int kMaxBandSets = 12;
 constexpr int kMaxBandImages = 64;
 constexpr int kMaxEntries = 2 * kMaxBandSets * kMaxBandImages + 2 * kMaxBandSets;
-constexpr long kZeroChunkFloats = 64 * 1024;          // 256 KB per zero item
-constexpr int kUnitsPerItem = kWarpsPerBlock;         // one unit per warp
+constexpr long kZeroChunkFloats = 8 * 1024;           // 32 KB per zero unit (one warp)
+constexpr int kUnitsPerItem = 1;                      // list positions are warp-units
 
 struct BandEntry {
     long first_ticket, count;
@@ -42,7 +42,7 @@ struct BandCtl {
     long total;
     int n_entries;
     int pad;
-    int counters[kMaxBandSets * kMaxBandImages + kMaxBandSets];
+    int counters[2 * (kMaxBandSets * kMaxBandImages + kMaxBandSets)];
     BandEntry e[kMaxEntries];
 };
 
@@ -87,34 +87,35 @@ __global__ void __launch_bounds__(1024) band_plan_kernel(const BandSets sets, Ba
         int done_boxes[kMaxBandSets];
         for (int s = 0; s < sets.n; ++s) done_boxes[s] = 0;
         for (int band = 0; band < nbands; ++band) {
-            const int counter = nc++;
-            ctl->counters[counter] = 0;
-            int need = 0;
-            if (sets.zero_first) {
-                BandEntry &z = ctl->e[ne++];
-                z.type = 0; z.set = m; z.counter = counter;
-                z.zero_base = M.gimg + (banded ? (long)band * img_floats : 0);
-                z.zero_floats = banded ? img_floats : img_floats * M.B;
-                z.first_ticket = ticket;
-                z.count = (z.zero_floats + kZeroChunkFloats - 1) / kZeroChunkFloats;
-                z.r_lo = z.nbox = z.need = 0;
-                ticket += z.count;
-                need = (int)z.count;
-            }
+            const int counter = nc; nc += 2;                                     // [counter] = chunks handed out, [counter+1] = chunks done
+            ctl->counters[counter] = 0; ctl->counters[counter + 1] = 0;
+            float *zbase = M.gimg + (banded ? (long)band * img_floats : 0);
+            const long zfloats = banded ? img_floats : img_floats * M.B;
+            const int need = sets.zero_first ? (int)((zfloats + kZeroChunkFloats - 1) / kZeroChunkFloats) : 0;
+            bool any = false;
             for (int s = 0; s < sets.n; ++s) {
                 if (sets.map_of[s] != m) continue;
                 const int nbox = banded ? hist[s][band] : sets.R[s];
                 if (nbox == 0) continue;
+                any = true;
                 BandEntry &e = ctl->e[ne++];
                 e.type = 1; e.set = s; e.counter = counter; e.need = need;
                 e.r_lo = banded ? done_boxes[s] : 0;
                 e.nbox = nbox;
-                e.zero_base = nullptr; e.zero_floats = 0;
-                const long units = (long)nbox * sets.s[s].ph * sets.s[s].slabs;
+                e.zero_base = zbase; e.zero_floats = zfloats;
                 e.first_ticket = ticket;
-                e.count = (units + kUnitsPerItem - 1) / kUnitsPerItem;
+                e.count = (long)nbox * sets.s[s].ph * sets.s[s].slabs;
                 ticket += e.count;
                 done_boxes[s] += nbox;
+            }
+            if (!any && need > 0) {                                              // nothing reduces into this band: one unit just clears it
+                BandEntry &e = ctl->e[ne++];
+                e.type = 0; e.set = m; e.counter = counter; e.need = need;
+                e.r_lo = e.nbox = 0;
+                e.zero_base = zbase; e.zero_floats = zfloats;
+                e.first_ticket = ticket;
+                e.count = 1;
+                ticket += 1;
             }
         }
     }
@@ -130,48 +131,47 @@ __device__ __forceinline__ int ld_acquire(const int *p) {
 }
 
 // ---- persistent worker -----------------------------------------------------------------------------------
+// Exactly as many CTAs as fit on the chip at once (cooperative launch: co-residency guaranteed), every WARP walks the
+// ordered unit list with a fixed stride, no block-level synchronisation at all.  A reduce unit spins (lane 0, then
+// __syncwarp) until its band's zero-fill counter is complete; zero units never wait, and since every warp is resident
+// a waiting warp always waits on warps that are running.
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) band_run_kernel(const BandSets sets, BandCtl *__restrict__ ctl) {
-    __shared__ long s_ticket;
-    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int lane = threadIdx.x & 31;
+    const long gw = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long nw = ((long)gridDim.x * blockDim.x) >> 5;
     const long total = ctl->total;
     const int ne = ctl->n_entries;
-    if (t == 0) s_ticket = (long)atomicAdd(&ctl->ticket, 1ULL);
-    __syncthreads();
-    long ticket = s_ticket;
-    while (ticket < total) {
-        __syncthreads();                                            // everyone has read s_ticket
-        if (t == 0) s_ticket = (long)atomicAdd(&ctl->ticket, 1ULL);  // prefetch the next ticket while this item runs
-        int lo = 0, hi = ne - 1;                                    // entry with first_ticket <= ticket < first_ticket + count
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (ctl->e[mid].first_ticket <= ticket) lo = mid; else hi = mid - 1;
-        }
-        const BandEntry &e = ctl->e[lo];
-        const long k = ticket - e.first_ticket;
-        if (e.type == 0) {
-            float4 *p = reinterpret_cast<float4 *>(e.zero_base + k * kZeroChunkFloats);
-            const long n4 = min(kZeroChunkFloats, e.zero_floats - k * kZeroChunkFloats) >> 2;
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (long q = t; q < n4; q += kWarpsPerBlock * 32) p[q] = z;                    // default policy: stays in L2
-            __syncthreads();
-            if (t == 0) { __threadfence(); atomicAdd(&ctl->counters[e.counter], 1); }
-        } else {
-            if (e.need > 0) {
-                if (t == 0) while (ld_acquire(&ctl->counters[e.counter]) < e.need) __nanosleep(64);
-                __syncthreads();
+    int cur = 0;                                                    // entries are visited in increasing order: resume the search
+    int ready_counter = -1;                                         // last band this warp has seen fully cleared
+    for (long u = gw; u < total; u += nw) {
+        while (cur + 1 < ne && ctl->e[cur + 1].first_ticket <= u) ++cur;
+        const BandEntry &e = ctl->e[cur];
+        if (e.need > 0 && ready_counter != e.counter) {
+            // The band is cleared by whoever gets here first: grab 32 KB chunks until none are left, then wait for the
+            // stragglers' chunks.  (No static owner of a chunk, so nobody waits on a warp that is busy elsewhere.)
+            int *handed = &ctl->counters[e.counter], *done = &ctl->counters[e.counter + 1];
+            if (ld_acquire(done) < e.need) {
+                for (;;) {
+                    int c = 0;
+                    if (lane == 0) c = atomicAdd(handed, 1);
+                    c = __shfl_sync(0xffffffffu, c, 0);
+                    if (c >= e.need) break;
+                    float4 *p = reinterpret_cast<float4 *>(e.zero_base + (long)c * kZeroChunkFloats);
+                    const long n4 = min(kZeroChunkFloats, e.zero_floats - (long)c * kZeroChunkFloats) >> 2;
+                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (long q = lane; q < n4; q += 32) p[q] = z;                          // default policy: stays in L2
+                    __syncwarp();
+                    if (lane == 0) { __threadfence(); atomicAdd(done, 1); }
+                }
+                if (lane == 0) while (ld_acquire(done) < e.need) __nanosleep(32);
+                __syncwarp();
             }
+            ready_counter = e.counter;
+        }
+        if (e.type == 1) {
             const BwdSet &S = sets.s[e.set];
-            const long lu = k * kUnitsPerItem + w;                                          // local unit inside the band
-            const long units = (long)e.nbox * S.ph * S.slabs;
-            if (lu < units) {
-                const int slab = (int)(lu % S.slabs);
-                const long q = lu / S.slabs;
-                const int r = e.r_lo + (int)(q / S.ph), i = (int)(q % S.ph);
-                bwd_unit<4>(S, ((long)r * S.ph + i) * S.slabs + slab, lane);
-            }
+            bwd_unit<4>(S, (long)e.r_lo * S.ph * S.slabs + (u - e.first_ticket), lane);     // the band's units are contiguous in the set
         }
-        __syncthreads();
-        ticket = s_ticket;
     }
 }
 
@@ -205,7 +205,17 @@ int fi_banded_backward(const fi_bwd_set *sets, int num_sets, int zero_first, cud
     band_plan_kernel<<<1, 1024, 0, stream>>>(dev, ctl);
     int rc = check_launch("banded backward[plan]");
     if (rc == FI_OK) {
-        band_run_kernel<<<kNumSMs * 2, kWarpsPerBlock * 32, 0, stream>>>(dev, ctl);
+        static int blocks_per_sm = -1, num_sms = kNumSMs;
+        if (blocks_per_sm < 0) {
+            int devid = 0;
+            cudaGetDevice(&devid);
+            cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, devid);
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, band_run_kernel, kWarpsPerBlock * 32, 0) != cudaSuccess || blocks_per_sm < 1)
+                blocks_per_sm = 1;
+        }
+        void *args[] = {(void *)&dev, (void *)&ctl};
+        e = cudaLaunchCooperativeKernel((const void *)band_run_kernel, dim3(num_sms * blocks_per_sm), dim3(kWarpsPerBlock * 32), args, 0, stream);
+        if (e != cudaSuccess) { cudaGetLastError(); cudaFreeAsync(ctl, stream); return FI_ERR_UNSUPPORTED; }   // caller falls back to the plain kernel
         rc = check_launch("banded backward[run]");
     }
     cudaFreeAsync(ctl, stream);
