@@ -121,10 +121,13 @@ class Step(object):
     def __init__(self, wl, device, world, seed):
         import feature_intertwiner_b200 as fi
         self.fi, self.wl, self.dev, self.world = fi, wl, device, world
+        self.spatial_sort = os.environ.get("FI_SPATIAL_SORT", "1") != "0"
+        self.use_graph = world == 1 and os.environ.get("FI_GRAPH", "1") != "0"     # CUDA-graph the fixed-shape loss head
+        self.graph_tried, self.graphed = False, False
         self.cfg = build_config(wl)
         torch.manual_seed(2000)
         self.ot = fi.OptTrans(self.cfg, ch_x=FEAT, L=wl["sinkhorn_iters"]).to(device)
-        self.loss_mod = fi.IntertwinerLoss(self.cfg, ot_loss=self.ot, feat_dim=FEAT, distributed=world > 1).to(device)
+        self.loss_mod = fi.IntertwinerLoss(self.cfg, ot_loss=self.ot, feat_dim=FEAT, distributed=world > 1, ot_padded=True).to(device)
         self.host = make_inputs(wl, seed)
         B, R = wl["batch"], wl["rois_per_image"]
         # the split of THIS input fixes the shapes of the synthetic critic features / upstream gradients
@@ -171,7 +174,8 @@ class Step(object):
         madeup = [m.detach().requires_grad_() for m in inp["madeup"]]
         small_f = [t.detach().requires_grad_() for t in inp["small_feat"]]
         big_f = inp["big_feat"]
-        split = fi.split_levels(fi.roi_level(rois, cfg.DATA.IMAGE_SHAPE, cfg.ROIS.ASSIGN_ANCHOR_BASE), rois=rois, gt=gt)
+        split = fi.split_levels(fi.roi_level(rois, cfg.DATA.IMAGE_SHAPE, cfg.ROIS.ASSIGN_ANCHOR_BASE), rois=rois, gt=gt,
+                                order=fi.spatial_order(rois) if self.spatial_sort else None)
         pooled_out = torch.empty((total, DEPTH, 7, 7), device=self.dev, memory_format=torch.channels_last)
         mask_out = torch.empty((total, DEPTH, 14, 14), device=self.dev, memory_format=torch.channels_last)
         # every crop of the pass in one level-batched launch (fi.crop_sets), like Dev.forward
@@ -205,6 +209,9 @@ class Step(object):
                 f, c = fi.assign_feat2cls(split.small_gt(i), small_f[i], NCLS)
                 sfeat.append(f); scnt.append(c)
         feat_in = [torch.stack(bfeat)[None].detach(), torch.stack(bcnt)[None], torch.stack(sfeat)[None], torch.stack(scnt)[None], None, None]
+        if self.use_graph and not self.graph_tried:
+            self.graph_tried = True
+            self.graphed = self.loss_mod.enable_cuda_graph([feat_in[0], feat_in[1], feat_in[2].detach().requires_grad_(), feat_in[3]])
         loss = self.loss_mod(feat_in).sum()
         torch.autograd.backward([loss, pooled_out, mask_out] + outs, [torch.ones_like(loss), inp["g_pooled"], inp["g_mask"]] + grads)
         if self.world > 1:
@@ -278,6 +285,10 @@ def run_ours(args):
     ms_e2e = timed(e2e_step, max(2, args.steps // 2), 2)
 
     rois_per_step = wl["batch"] * wl["rois_per_image"] * world
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     peak, peak_kind = measured_peak()
@@ -296,7 +307,9 @@ def run_ours(args):
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%s: batch %d/GPU, %dx%d, %d RoIs/img, FPN P2-P5 C=256, pools 7+14, Sinkhorn N=256 L=%d, class-level OT loss"
                                % (args.workload, wl["batch"], wl["image"][0], wl["image"][1], wl["rois_per_image"], wl["sinkhorn_iters"]),
-                   "layout": "channels_last maps/crops (logical NCHW)", "critic_and_makeup_convs": "excluded (stock cuDNN; SURVEY.md 8 a5)",
+                   "layout": "channels_last maps/crops (logical NCHW)", "ot": "all 80 foreground classes, absent ones masked (fixed shapes, no host sync)",
+                   "roi_order": "spatially sorted per image (L2 reuse)" if step.spatial_sort else "index order",
+                   "loss_head": "CUDA graph (fwd+bwd)" if step.graphed else "eager", "critic_and_makeup_convs": "excluded (stock cuDNN; SURVEY.md 8 a5)",
                    "l2": "512 MB-class working set per step (> 126 MB L2) + 256 MB flush write between steps",
                    "small_counts": step.counts[0], "big_counts": step.counts[1], "parallelism": "dp%d by image batch" % world},
         "e2e": {"value": rois_per_step / (ms_e2e / 1e3), "unit": "RoIs/s", "ms_per_step": ms_e2e,

@@ -9,4 +9,4 @@ from .roi_pool import RoIPoolFunction, _RoIPooling  # noqa: F401
 from .nms import nms, nms_batched, pth_nms  # noqa: F401
 from .ot import OptTrans, sinkhorn_loss  # noqa: F401
 from .intertwiner import (Dev, IntertwinerLoss, LevelSplit, assign_feat2cls, pyramid_roi_align, roi_level,  # noqa: F401
-                          split_levels)
+                          spatial_order, split_levels)

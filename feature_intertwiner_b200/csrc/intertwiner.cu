@@ -34,6 +34,7 @@ constexpr int kLists = 8;
 // Optional gather outputs (all [4, n, ...], same order as the index lists) so the host does not have to run
 // rois[idx], idx // R, gt[idx] as separate torch ops per level:
 struct SplitGather {
+    const int *order;          // optional visiting order (a permutation of 0..n-1): lists come out in THIS order
     const float4 *rois;        // [n] (y1,x1,y2,x2)
     const int *gt;             // [n] class ids or null
     int rois_per_image;
@@ -52,8 +53,8 @@ __global__ void __launch_bounds__(kSplitThreads) split_levels_kernel(const int *
     int cnt[kLists];
 #pragma unroll
     for (int k = 0; k < kLists; ++k) cnt[k] = 0;
-    for (int i = lo; i < hi; ++i) {
-        const int l = level[i];
+    for (int p = lo; p < hi; ++p) {
+        const int l = level[G.order ? G.order[p] : p];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             cnt[k] += (l == 2 + k);
@@ -87,7 +88,8 @@ __global__ void __launch_bounds__(kSplitThreads) split_levels_kernel(const int *
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < kLists; ++k) base[k] += warp_tot[k][wid];
-    for (int i = lo; i < hi; ++i) {
+    for (int p = lo; p < hi; ++p) {
+        const int i = G.order ? G.order[p] : p;
         const int l = level[i];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -240,7 +242,7 @@ FI_API int fi_split_levels(const int *level, int n, int *small_idx, int *small_c
     return check_launch("fi_split_levels");
 }
 
-FI_API int fi_split_levels_gather(const int *level, const float *rois, const int *gt, int n, int rois_per_image, int *small_idx, int *small_cnt,
+FI_API int fi_split_levels_gather(const int *level, const float *rois, const int *gt, const int *order, int n, int rois_per_image, int *small_idx, int *small_cnt,
                                   int *big_idx, int *big_cnt, int *slot, float *small_boxes, int *small_ind, int *small_gt, float *big_boxes,
                                   int *big_ind, int *big_gt, cudaStream_t stream) {
     FI_REQUIRE(n >= 0 && n <= 65536 && rois_per_image > 0, "fi_split_levels_gather: n=%d outside [0,65536] or bad rois_per_image", n);
@@ -249,6 +251,7 @@ FI_API int fi_split_levels_gather(const int *level, const float *rois, const int
     FI_REQUIRE(gt == nullptr || (small_gt && big_gt), "fi_split_levels_gather: gt given without small_gt / big_gt");
     FI_REQUIRE(((uintptr_t)rois % 16 == 0) && ((uintptr_t)small_boxes % 16 == 0) && ((uintptr_t)big_boxes % 16 == 0), "fi_split_levels_gather: box arrays must be 16-byte aligned");
     SplitGather G;
+    G.order = order;
     G.rois = reinterpret_cast<const float4 *>(rois); G.gt = gt; G.rois_per_image = rois_per_image;
     G.small_boxes = reinterpret_cast<float4 *>(small_boxes); G.big_boxes = reinterpret_cast<float4 *>(big_boxes);
     G.small_ind = small_ind; G.big_ind = big_ind; G.small_gt = small_gt; G.big_gt = big_gt;

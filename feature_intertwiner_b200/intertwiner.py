@@ -16,6 +16,8 @@ What changes relative to the reference, and what does not:
 The make-up layer (``upsample``) and the critic (``feat_extract``) are dense convolutions and stay stock
 PyTorch / cuDNN.
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -75,9 +77,25 @@ class LevelSplit(object):
         return self.g["big_gt"][i, : self.big_cnt[i]]
 
 
-def split_levels(level, rois=None, gt=None):
+def spatial_order(rois, grid=None):
+    """Visiting order that walks every image tile by tile (grid x grid coarse tiles by box centre): RoIs that overlap are
+    then processed close together in time, so their taps / gradient lines are still in L2 (measured on C2: forward DRAM
+    reads and backward read-modify-write traffic drop).  Results do not depend on the order (forward is
+    bit-identical; backward sums in another order)."""
+    if grid is None:
+        grid = int(os.environ.get("FI_SORT_GRID", "8"))
+    bs, R = rois.shape[0], rois.shape[1]
+    cy = ((rois[..., 0] + rois[..., 2]) * (0.5 * grid)).clamp(0, grid - 1).floor()
+    cx = ((rois[..., 1] + rois[..., 3]) * (0.5 * grid)).clamp(0, grid - 1).floor()
+    snake = torch.where(cy.long() % 2 == 0, cx, grid - 1 - cx)            # boustrophedon: neighbouring tiles stay neighbours
+    key = (torch.arange(bs, device=rois.device).view(bs, 1) * (grid * grid) + cy * grid + snake).view(-1)
+    return torch.sort(key, stable=True)[1].int()
+
+
+def split_levels(level, rois=None, gt=None, order=None):
     """level[...] int32 -> LevelSplit: small(l) = {level == l}, big(l) = {level > l} (lib/sub_module.py:442,367-378).
-    With ``rois`` ([bs,R,4]) the same launch also gathers boxes / image index / class id (``gt`` [bs,R]) of every list."""
+    With ``rois`` ([bs,R,4]) the same launch also gathers boxes / image index / class id (``gt`` [bs,R]) of every list;
+    ``order`` (a permutation, e.g. ``spatial_order(rois)``) replaces torch.nonzero order by that visiting order."""
     _lib.require_cuda(level)
     flat = level.contiguous().view(-1)
     n = flat.numel()
@@ -100,8 +118,9 @@ def split_levels(level, rois=None, gt=None):
         if gt_flat is not None:
             g["small_gt"] = torch.empty((4, m), device=dev, dtype=torch.int32)
             g["big_gt"] = torch.empty((4, m), device=dev, dtype=torch.int32)
+        order = None if order is None else order.to(device=dev, dtype=torch.int32).contiguous()
         _lib.check(_lib.lib().fi_split_levels_gather(
-            _lib.ptr(flat), _lib.ptr(rois_flat), _lib.ptr(gt_flat), n, int(rois.size(-2)), _lib.ptr(small_idx), _lib.ptr(small_cnt),
+            _lib.ptr(flat), _lib.ptr(rois_flat), _lib.ptr(gt_flat), _lib.ptr(order), n, int(rois.size(-2)), _lib.ptr(small_idx), _lib.ptr(small_cnt),
             _lib.ptr(big_idx), _lib.ptr(big_cnt), _lib.ptr(slot), _lib.ptr(g["small_boxes"]), _lib.ptr(g["small_ind"]), _lib.ptr(g.get("small_gt")),
             _lib.ptr(g["big_boxes"]), _lib.ptr(g["big_ind"]), _lib.ptr(g.get("big_gt")), _lib.stream_ptr(dev)))
     return LevelSplit(small_idx, small_cnt, big_idx, big_cnt, slot, gathered=g)
@@ -158,6 +177,10 @@ class Dev(nn.Module):
         self.structure = config.DEV.STRUCTURE
         self.roi_type = config.ROIS.METHOD
         self.roi_spatial_scale = [1. / 4, 1. / 8, 1. / 16, 1. / 32]
+        # spatial_sort: visit RoIs tile by tile inside each image (L2 reuse) instead of in index order.  Off by default: the
+        # rows of small_output_all / small_gt_all are then level-major in THAT order rather than torch.nonzero order
+        # (lib/sub_module.py:586-600); every other output is unchanged.
+        self.spatial_sort = False
         if self.use_dev:
             self.feat_pool_size = config.DEV.FEAT_BRANCH_POOL_SIZE
             self.upsample_fac = config.DEV.UPSAMPLE_FAC
@@ -220,7 +243,8 @@ class Dev(nn.Module):
         cl = torch.channels_last
         rois_flat = rois.detach().float().contiguous().view(total_box, 4)
         # one launch: level lists + rois[idx], idx // R, gt[idx] of every list (sub_module.py:489-493,541-548)
-        split = split_levels(roi_level(rois, self.image_shape, cfg.ROIS.ASSIGN_ANCHOR_BASE), rois=rois, gt=roi_cls_gt if train_phase else None)
+        split = split_levels(roi_level(rois, self.image_shape, cfg.ROIS.ASSIGN_ANCHOR_BASE), rois=rois, gt=roi_cls_gt if train_phase else None,
+                             order=spatial_order(rois) if self.spatial_sort else None)
         # every RoI is assigned to exactly one level, so every row below is written by a crop: no zero fill (sub_module.py:650,656)
         pooled_out = torch.empty((total_box, self.depth, self.pool_size, self.pool_size), device=dev, memory_format=cl)
         mask_out = torch.empty((total_box, self.depth, self.mask_pool_size, self.mask_pool_size), device=dev, memory_format=cl)
@@ -445,13 +469,17 @@ class IntertwinerLoss(nn.Module):
     un-normalised class statistics are all-reduced first, replacing the gather-to-GPU-0 of nn.DataParallel.
     """
 
-    def __init__(self, config, ot_loss=None, feat_dim=1024, process_group=None, distributed=False, ddp_compensate=True):
+    def __init__(self, config, ot_loss=None, feat_dim=1024, process_group=None, distributed=False, ddp_compensate=True,
+                 ot_padded=False):
         super().__init__()
         self.config = config
         self.feat_dim = feat_dim
         self.distributed = distributed
         self.process_group = process_group
         self.ddp_compensate = ddp_compensate
+        # ot_padded: class-level OT loss over ALL foreground classes with the absent ones masked to 0 -> fixed shapes, no
+        # `nonzero` host sync; returns [ncls-1] instead of the reference's [n] (same sum, same gradients)
+        self.ot_padded = ot_padded
         B, ncls = config.DEV.BUFFER_SIZE, config.DATASET.NUM_CLASSES
         # persistent state of the hot path; round-trips through checkpoints like tools/utils.py:374-389,575-585
         self.register_buffer('buffer', torch.zeros(B, feat_dim, ncls))
@@ -477,7 +505,41 @@ class IntertwinerLoss(nn.Module):
         return merged_class_sums(feat, cnt, self.process_group if self.distributed else None, self.distributed,
                                  differentiable, self.ddp_compensate)
 
+    # ---- optional CUDA-graph capture of the loss head ------------------------------------------------------------
+    def enable_cuda_graph(self, feat_input):
+        """Capture forward AND backward of the loss head (statistics merge -> buffer update -> match -> OptTrans / Sinkhorn)
+        into CUDA graphs: ~60 small launches per iteration become two graph launches.  Possible when every shape is fixed:
+        class-level loss, l1 / l2 or padded OT, BUFFER_SIZE == 1, single process.  ``feat_input`` is a representative input
+        (shapes / requires_grad as in training).  Returns True when the graphed path is active; falls back to eager on any
+        failure.  The buffer is snapshotted around the warm-up replays, so capture does not disturb the running means."""
+        cfg = self.config
+        ok = (not self.distributed) and self.buffer.size(0) == 1 and not cfg.DEV.INST_LOSS and \
+            (cfg.DEV.LOSS_CHOICE in ('l1', 'l2') or (cfg.DEV.LOSS_CHOICE == 'ot' and self.ot_padded))
+        if not ok:
+            return False
+        big_feat, big_cnt, small_feat, small_cnt = feat_input[:4]
+        snap = (self.buffer.clone(), self.buffer_cnt.clone())
+        try:
+            head = _LossHead(self)
+            sample = (big_feat.detach().clone(), big_cnt.detach().clone(), small_feat.detach().clone().requires_grad_(), small_cnt.detach().clone())
+            graphed = torch.cuda.make_graphed_callables(head, sample)
+            self._graphed = graphed
+            self._graph_shapes = tuple(tuple(t.shape) for t in sample)
+        except Exception as exc:           # noqa: BLE001 -- capture is an optimisation, never a requirement
+            self._graphed = None
+            self._graph_error = repr(exc)
+        finally:
+            self.buffer.copy_(snap[0]); self.buffer_cnt.copy_(snap[1])
+        return self._graphed is not None
+
     def forward(self, feat_input):
+        g = getattr(self, '_graphed', None)
+        if g is not None and torch.is_grad_enabled() and feat_input[2].requires_grad and \
+                tuple(tuple(t.shape) for t in feat_input[:4]) == self._graph_shapes:
+            return g(feat_input[0].detach(), feat_input[1].detach(), feat_input[2], feat_input[3].detach())
+        return self._forward_eager(feat_input)
+
+    def _forward_eager(self, feat_input):
         big_feat, big_cnt, small_feat, small_cnt, small_output_all, small_gt_all = feat_input
         cfg = self.config
         Fd, ncls = self.feat_dim, cfg.DATASET.NUM_CLASSES
@@ -506,6 +568,10 @@ class IntertwinerLoss(nn.Module):
             s_n = s_n.clone(); s_n[0] = 0                                      # background excluded (model.py:178)
             mask = (s_n > 0) & in_buffer
             SMALL_all, BIG_all = final_small.t(), final_big.t()
+        if lc == 'ot' and self.ot_padded and not cfg.DEV.INST_LOSS:
+            self.last_idx, self.last_mask = None, mask
+            w = self.ot_loss(SMALL_all[1:].unsqueeze(dim=-1).contiguous(), BIG_all[1:].unsqueeze(dim=-1).contiguous())
+            return w * mask[1:].to(w.dtype)
         if lc == 'ot' or lc == 'kl':
             idx = torch.nonzero(mask).squeeze(1)                               # host-visible size: the reference's API returns [n]
             self.last_idx = idx
@@ -524,6 +590,20 @@ class IntertwinerLoss(nn.Module):
         m = mask.to(per.dtype).unsqueeze(1)
         denom = (m.sum() * per.size(1)).clamp(min=1.0)
         return (per * m).sum() / denom
+
+
+class _LossHead(nn.Module):
+    """The fixed-shape part of IntertwinerLoss as a 4-tensor callable for torch.cuda.make_graphed_callables.  Shares the
+    OptTrans module (so its parameters receive gradients) and reaches the buffers through the parent."""
+
+    def __init__(self, parent):
+        super().__init__()
+        object.__setattr__(self, '_parent', parent)
+        if hasattr(parent, 'ot_loss'):
+            self.ot_loss = parent.ot_loss
+
+    def forward(self, big_feat, big_cnt, small_feat, small_cnt):
+        return self._parent._forward_eager([big_feat, big_cnt, small_feat, small_cnt, None, None])
 
 
 def meta_loss_module(config, ot_loss=None, **kw):

@@ -174,8 +174,10 @@ int fi_split_levels(const int *level, int n, int *small_idx, int *small_cnt, int
 
 /* Same launch, additionally emitting what Dev.forward gathers per level (lib/sub_module.py:489-493,541-548):
  * small_boxes/big_boxes [4,n,4] = rois[idx], small_ind/big_ind [4,n] = idx / rois_per_image (the image a RoI belongs to),
- * small_gt/big_gt [4,n] = gt[idx] (only when gt != NULL). */
-int fi_split_levels_gather(const int *level, const float *rois, const int *gt, int n, int rois_per_image, int *small_idx,
+ * small_gt/big_gt [4,n] = gt[idx] (only when gt != NULL).  `order` (NULL or a permutation of 0..n-1) is the order in which RoIs
+ * are visited: with a spatially sorted order the lists -- and so the RoIAlign work -- walk each image coherently, which is what
+ * keeps overlapping RoIs' taps in L2; NULL gives torch.nonzero order. */
+int fi_split_levels_gather(const int *level, const float *rois, const int *gt, const int *order, int n, int rois_per_image, int *small_idx,
                            int *small_cnt, int *big_idx, int *big_cnt, int *slot, float *small_boxes, int *small_ind,
                            int *small_gt, float *big_boxes, int *big_ind, int *big_gt, cudaStream_t stream);
 

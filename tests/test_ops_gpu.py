@@ -158,6 +158,14 @@ def test_split_matches_nonzero(n):
             for idx, boxes, ind, cls in ((sg.small(i), sg.small_boxes(i), sg.small_ind(i), sg.small_gt(i)),
                                          (sg.big(i), sg.big_boxes(i), sg.big_ind(i), sg.big_gt(i))):
                 assert torch.equal(boxes, flat_r[idx.long()]) and torch.equal(ind, (idx // R).int()) and torch.equal(cls, flat_g[idx.long()])
+        # a visiting order: same sets, listed in that order
+        order = fi.spatial_order(rois)
+        assert torch.equal(torch.sort(order.long())[0], torch.arange(order.numel()).cuda())
+        so = fi.split_levels(lv, rois=rois, gt=gt, order=order)
+        for i, l in enumerate(range(2, 6)):
+            want = order[(lv.view(-1)[order.long()] == l)]
+            assert torch.equal(so.small(i), want) and torch.equal(so.small_boxes(i), flat_r[want.long()])
+            assert torch.equal(torch.sort(so.big(i))[0], torch.sort(sg.big(i))[0])
 
 
 # ------------------------------------------------------------------------------------------------ segment mean / buffer
@@ -226,6 +234,64 @@ def test_intertwiner_loss_vs_restatement(B, loss, inst):
             a, b = (so_c, so_r) if inst else (sf_c, sf_r)
             # OT with D=1: d/dx of x/(|x|+1e-20) underflows to exactly 0 in the kernel; autograd leaves ~1e-7 rounding noise
             np.testing.assert_allclose(a.grad.cpu().numpy(), b.grad.cpu().numpy(), rtol=1e-3, atol=1e-6 if loss == "ot" else 1e-7)
+
+
+def test_intertwiner_ot_padded_equals_compact():
+    """ot_padded=True (fixed shapes, no nonzero sync) gives the same total loss and gradients as the reference-shaped [n] vector."""
+    fi = _fi()
+    torch.manual_seed(3)
+    cfg = pyref.make_config(DEV__LOSS_CHOICE="ot")
+    ot = fi.OptTrans(cfg, ch_x=1024, L=5).cuda()
+    a = fi.IntertwinerLoss(cfg, ot_loss=ot).cuda()
+    b = fi.IntertwinerLoss(cfg, ot_loss=ot, ot_padded=True).cuda()
+    cnt = torch.randint(0, 3, (1, 3, 1, 81)).float().cuda()
+    bf = torch.rand(1, 3, 1024, 81).cuda() * (cnt > 0)
+    scnt = torch.randint(0, 3, (1, 3, 1, 81)).float().cuda()
+    sf = torch.rand(1, 3, 1024, 81).cuda() * (scnt > 0)
+    s1, s2 = sf.clone().requires_grad_(), sf.clone().requires_grad_()
+    la = a([bf, cnt, s1, scnt, None, None])
+    lb = b([bf, cnt, s2, scnt, None, None])
+    assert lb.numel() == 80 and la.numel() == int(a.last_idx.numel())
+    torch.testing.assert_close(la.sum(), lb.sum(), rtol=1e-5, atol=1e-6)
+    la.sum().backward(); lb.sum().backward()
+    torch.testing.assert_close(s1.grad, s2.grad, rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("loss", ["l2", "ot"])
+def test_intertwiner_loss_cuda_graph_matches_eager(loss):
+    """enable_cuda_graph(): graphed forward+backward of the loss head == eager, including the buffer's evolution."""
+    fi = _fi()
+    torch.manual_seed(4)
+    cfg = pyref.make_config(DEV__LOSS_CHOICE=loss)
+    ot_a = fi.OptTrans(cfg, ch_x=1024, L=5).cuda() if loss == "ot" else None
+    ot_b = fi.OptTrans(cfg, ch_x=1024, L=5).cuda() if loss == "ot" else None
+    if loss == "ot":
+        ot_b.load_state_dict(ot_a.state_dict())
+    a = fi.IntertwinerLoss(cfg, ot_loss=ot_a, ot_padded=True).cuda()
+    b = fi.IntertwinerLoss(cfg, ot_loss=ot_b, ot_padded=True).cuda()
+
+    def batch(seed):
+        g = torch.Generator().manual_seed(seed)
+        cnt = torch.randint(0, 3, (1, 3, 1, 81), generator=g).float().cuda()
+        bf = torch.rand(1, 3, 1024, 81, generator=g).cuda() * (cnt > 0)
+        scnt = torch.randint(0, 3, (1, 3, 1, 81), generator=g).float().cuda()
+        sf = torch.rand(1, 3, 1024, 81, generator=g).cuda() * (scnt > 0)
+        return bf, cnt, sf, scnt
+    bf, cnt, sf, scnt = batch(0)
+    assert b.enable_cuda_graph([bf, cnt, sf.clone().requires_grad_(), scnt]), getattr(b, "_graph_error", "")
+    assert float(b.buffer_cnt.sum()) == 0          # capture left the buffer untouched
+    for step in range(3):
+        bf, cnt, sf, scnt = batch(step + 1)
+        s1, s2 = sf.clone().requires_grad_(), sf.clone().requires_grad_()
+        la = a([bf, cnt, s1, scnt, None, None]).sum()
+        lb = b([bf, cnt, s2, scnt, None, None]).sum()
+        la.backward(); lb.backward()
+        torch.testing.assert_close(la, lb, rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(s1.grad, s2.grad, rtol=1e-4, atol=1e-7)
+        torch.testing.assert_close(a.buffer, b.buffer, rtol=1e-6, atol=1e-7)
+        if loss == "ot":
+            for p, q in zip(ot_a.parameters(), ot_b.parameters()):
+                torch.testing.assert_close(p.grad, q.grad, rtol=1e-4, atol=1e-6)
 
 
 # ------------------------------------------------------------------------------------------------ NMS
