@@ -485,6 +485,8 @@ class IntertwinerLoss(nn.Module):
         self.register_buffer('buffer', torch.zeros(B, feat_dim, ncls))
         self.register_buffer('buffer_cnt', torch.zeros(B, 1, ncls))
         self.register_buffer('ring_pos', torch.zeros((), dtype=torch.long))   # next slot to overwrite (B > 1)
+        fg = torch.ones(ncls); fg[0] = 0
+        self.register_buffer('fg_mask', fg, persistent=False)                  # background excluded (model.py:178)
         if ot_loss is not None:
             self.ot_loss = ot_loss
         self.last_idx = None
@@ -565,7 +567,7 @@ class IntertwinerLoss(nn.Module):
         else:
             s_sum, s_n = self._sums(small_feat, small_cnt, differentiable=True)
             final_small = s_sum / (s_n + EPS)
-            s_n = s_n.clone(); s_n[0] = 0                                      # background excluded (model.py:178)
+            s_n = s_n * self.fg_mask                                            # background excluded (model.py:178); no host scalar
             mask = (s_n > 0) & in_buffer
             SMALL_all, BIG_all = final_small.t(), final_big.t()
         if lc == 'ot' and self.ot_padded and not cfg.DEV.INST_LOSS:
