@@ -260,7 +260,9 @@ def run_ours(args):
             host["s"] += time.perf_counter() - t0          # host time to ENQUEUE a step (no sync inside except the split read)
             evs.append((a, b))
         barrier()
-        ms = sum(a.elapsed_time(b) for a, b in evs)
+        per_step = [a.elapsed_time(b) for a, b in evs]
+        host["per_step"] = per_step
+        ms = sum(per_step)
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         if world > 1:
             import torch.distributed as dist
@@ -275,6 +277,7 @@ def run_ours(args):
     n0 = lib.fi_kernel_launches()
     ms = timed(lambda: step.run(step.resident), args.steps, args.warmup)
     host_ms = 1e3 * host["s"] / args.steps
+    per_step_ms = [round(v, 3) for v in host["per_step"]]
     launches = (lib.fi_kernel_launches() - n0) // (args.steps + args.warmup)
     records = fi.roi_align.disable_profiling()
     clocks = sampler.stop() if rank == 0 else None
@@ -301,6 +304,14 @@ def run_ours(args):
     kernels = {k: {"launches_per_step": v[2] // args.steps, "avg_ms": v[1] / v[2], "alg_bytes_per_launch": v[0] / v[2], "gbs": v[0] / v[1] / 1e6,
                    "frac": v[0] / v[1] / 1e6 / peak, "share_of_step": v[1] / args.steps / ms} for k, v in fam.items()}
     dom = max(kernels, key=lambda k: kernels[k]["share_of_step"])
+    # DRAM bytes per launch of the same kernels from the committed `ncu --set full` capture of this command (profiles/)
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath) and args.workload == "c2":
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj.get(dom), tj.get("source")
+        for k in kernels:
+            kernels[k]["dram_traffic_per_launch"] = tj.get(k)
     out = {
         "metric": "RoIs/sec (RoIAlign fwd+bwd + split + class means + Sinkhorn intertwiner loss, fwd+bwd)",
         "value": rois_per_step / (ms / 1e3), "unit": "RoIs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -314,9 +325,9 @@ def run_ours(args):
                    "small_counts": step.counts[0], "big_counts": step.counts[1], "parallelism": "dp%d by image batch" % world},
         "e2e": {"value": rois_per_step / (ms_e2e / 1e3), "unit": "RoIs/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": step.h2d_bytes, "d2h_bytes_per_step": 4},
-        "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms,
+        "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms, "ms_each_step": per_step_ms,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                     "frac": kernels[dom]["frac"], "traffic": None, "peak_kind": peak_kind},
+                     "frac": kernels[dom]["frac"], "traffic": traffic, "traffic_source": traffic_src, "peak_kind": peak_kind},
         "kernels": kernels,
         "clocks": clocks,
     }
