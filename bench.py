@@ -185,12 +185,13 @@ class Step(object):
                 continue
             if i < 3 and split.big_cnt[i]:
                 where[("big", i)] = len(specs)
-                specs.append(dict(image=raw[i], boxes=split.big_boxes(i), box_ind=split.big_ind(i), size=14))
+                specs.append(dict(image=raw[i], boxes=split.big_boxes(i), box_ind=split.big_ind(i), size=14, img_offsets=split.big_img_offsets(i)))
             s32 = split.small(i)
             boxes, ind = split.small_boxes(i), split.small_ind(i)
             where[("small", i)] = len(specs)
-            specs.append(dict(image=madeup[i], boxes=boxes, box_ind=ind, size=7, out=pooled_out, dst_row=s32))
-            specs.append(dict(image=madeup[i], boxes=boxes, box_ind=ind, size=14, out=mask_out, dst_row=s32, compact=(i < 3)))
+            specs.append(dict(image=madeup[i], boxes=boxes, box_ind=ind, size=7, out=pooled_out, dst_row=s32, img_offsets=split.small_img_offsets(i)))
+            specs.append(dict(image=madeup[i], boxes=boxes, box_ind=ind, size=14, out=mask_out, dst_row=s32, compact=(i < 3),
+                              img_offsets=split.small_img_offsets(i)))
         res_out, res_comp = fi.crop_sets(specs)
         outs, grads = [], []
         bfeat, bcnt, sfeat, scnt = [], [], [], []

@@ -40,6 +40,8 @@ struct SplitGather {
     int rois_per_image;
     float4 *small_boxes, *big_boxes;
     int *small_ind, *big_ind, *small_gt, *big_gt;
+    int *img_cnt;              // optional [8, num_images]: members of list k that belong to image b (lists 0-3 small, 4-7 big)
+    int num_images;
 };
 
 __global__ void __launch_bounds__(kSplitThreads) split_levels_kernel(const int *__restrict__ level, int n, int *__restrict__ small_idx,
@@ -48,6 +50,7 @@ __global__ void __launch_bounds__(kSplitThreads) split_levels_kernel(const int *
     __shared__ int warp_tot[kLists][kSplitThreads / 32];
     __shared__ int list_tot[kLists];
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    if (G.img_cnt) for (int q = t; q < kLists * G.num_images; q += kSplitThreads) G.img_cnt[q] = 0;   // ordered before the atomics by the barriers below
     const int per = (n + kSplitThreads - 1) / kSplitThreads;
     const int lo = min(t * per, n), hi = min(lo + per, n);
     int cnt[kLists];
@@ -96,11 +99,13 @@ __global__ void __launch_bounds__(kSplitThreads) split_levels_kernel(const int *
             if (l == 2 + k) {
                 const int o = k * n + base[k];
                 small_idx[o] = i; slot[i] = base[k]; ++base[k];
+                if (G.img_cnt) atomicAdd(&G.img_cnt[k * G.num_images + i / G.rois_per_image], 1);
                 if (G.rois) { G.small_boxes[o] = G.rois[i]; G.small_ind[o] = i / G.rois_per_image; if (G.gt) G.small_gt[o] = G.gt[i]; }
             }
             if (l > 2 + k) {
                 const int o = k * n + base[4 + k];
                 big_idx[o] = i; ++base[4 + k];
+                if (G.img_cnt) atomicAdd(&G.img_cnt[(4 + k) * G.num_images + i / G.rois_per_image], 1);
                 if (G.rois) { G.big_boxes[o] = G.rois[i]; G.big_ind[o] = i / G.rois_per_image; if (G.gt) G.big_gt[o] = G.gt[i]; }
             }
         }
@@ -244,7 +249,7 @@ FI_API int fi_split_levels(const int *level, int n, int *small_idx, int *small_c
 
 FI_API int fi_split_levels_gather(const int *level, const float *rois, const int *gt, const int *order, int n, int rois_per_image, int *small_idx, int *small_cnt,
                                   int *big_idx, int *big_cnt, int *slot, float *small_boxes, int *small_ind, int *small_gt, float *big_boxes,
-                                  int *big_ind, int *big_gt, cudaStream_t stream) {
+                                  int *big_ind, int *big_gt, int *img_cnt, cudaStream_t stream) {
     FI_REQUIRE(n >= 0 && n <= 65536 && rois_per_image > 0, "fi_split_levels_gather: n=%d outside [0,65536] or bad rois_per_image", n);
     FI_REQUIRE(small_cnt && big_cnt && (n == 0 || (level && rois && small_idx && big_idx && slot && small_boxes && small_ind && big_boxes && big_ind)),
                "fi_split_levels_gather: null pointer");
@@ -255,6 +260,7 @@ FI_API int fi_split_levels_gather(const int *level, const float *rois, const int
     G.rois = reinterpret_cast<const float4 *>(rois); G.gt = gt; G.rois_per_image = rois_per_image;
     G.small_boxes = reinterpret_cast<float4 *>(small_boxes); G.big_boxes = reinterpret_cast<float4 *>(big_boxes);
     G.small_ind = small_ind; G.big_ind = big_ind; G.small_gt = small_gt; G.big_gt = big_gt;
+    G.img_cnt = img_cnt; G.num_images = (n + rois_per_image - 1) / rois_per_image;
     split_levels_kernel<<<1, kSplitThreads, 0, stream>>>(level, n, small_idx, small_cnt, big_idx, big_cnt, slot, G);
     return check_launch("fi_split_levels_gather");
 }

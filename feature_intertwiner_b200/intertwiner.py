@@ -46,11 +46,28 @@ class LevelSplit(object):
     """Per-level index lists of flat RoI ids (torch.nonzero order) for levels 2..5, optionally with the gathered boxes,
     image indices and class ids of every list (one kernel, one 8-int host read for all of it)."""
 
-    def __init__(self, small_idx, small_cnt, big_idx, big_cnt, slot, gathered=None):
+    def __init__(self, small_idx, small_cnt, big_idx, big_cnt, slot, gathered=None, img_cnt=None):
         self.small_idx, self.big_idx, self.slot = small_idx, big_idx, slot
         self.g = gathered
-        counts = torch.cat([small_cnt, big_cnt]).tolist()        # the only host sync of the split
-        self.small_cnt, self.big_cnt = counts[:4], counts[4:]
+        parts = [small_cnt, big_cnt] + ([img_cnt.view(-1)] if img_cnt is not None else [])
+        counts = torch.cat(parts).tolist()                       # the only host sync of the split
+        self.small_cnt, self.big_cnt = counts[:4], counts[4:8]
+        self.img_offsets = None
+        if img_cnt is not None:                                  # per list: first member of every image (lists are image-major)
+            nb = img_cnt.size(1)
+            self.img_offsets = []
+            for k in range(8):
+                off, acc = [0], 0
+                for v in counts[8 + k * nb: 8 + (k + 1) * nb]:
+                    acc += v
+                    off.append(acc)
+                self.img_offsets.append(off)
+
+    def small_img_offsets(self, i):
+        return None if self.img_offsets is None else self.img_offsets[i]
+
+    def big_img_offsets(self, i):
+        return None if self.img_offsets is None else self.img_offsets[4 + i]
 
     def small(self, i):
         return self.small_idx[i, : self.small_cnt[i]]
@@ -119,11 +136,13 @@ def split_levels(level, rois=None, gt=None, order=None):
             g["small_gt"] = torch.empty((4, m), device=dev, dtype=torch.int32)
             g["big_gt"] = torch.empty((4, m), device=dev, dtype=torch.int32)
         order = None if order is None else order.to(device=dev, dtype=torch.int32).contiguous()
+        img_cnt = torch.empty((8, max(int(rois.size(0)), 1)), device=dev, dtype=torch.int32) if rois.dim() == 3 else None
         _lib.check(_lib.lib().fi_split_levels_gather(
             _lib.ptr(flat), _lib.ptr(rois_flat), _lib.ptr(gt_flat), _lib.ptr(order), n, int(rois.size(-2)), _lib.ptr(small_idx), _lib.ptr(small_cnt),
             _lib.ptr(big_idx), _lib.ptr(big_cnt), _lib.ptr(slot), _lib.ptr(g["small_boxes"]), _lib.ptr(g["small_ind"]), _lib.ptr(g.get("small_gt")),
-            _lib.ptr(g["big_boxes"]), _lib.ptr(g["big_ind"]), _lib.ptr(g.get("big_gt")), _lib.stream_ptr(dev)))
-    return LevelSplit(small_idx, small_cnt, big_idx, big_cnt, slot, gathered=g)
+            _lib.ptr(g["big_boxes"]), _lib.ptr(g["big_ind"]), _lib.ptr(g.get("big_gt")), _lib.ptr(img_cnt), _lib.stream_ptr(dev)))
+    # per-image extents are only meaningful when the visiting order is image-major (index order and spatial_order are)
+    return LevelSplit(small_idx, small_cnt, big_idx, big_cnt, slot, gathered=g, img_cnt=img_cnt)
 
 
 # ----------------------------------------------------------------------------------------------- segment mean
@@ -261,15 +280,17 @@ class Dev(nn.Module):
             if n_small > 0:
                 if use_stats and n_big > 0:
                     info["big"] = len(specs)
-                    specs.append(dict(image=x[i], boxes=split.big_boxes(i), box_ind=split.big_ind(i), size=self.feat_pool_size))
+                    specs.append(dict(image=x[i], boxes=split.big_boxes(i), box_ind=split.big_ind(i), size=self.feat_pool_size,
+                                      img_offsets=split.big_img_offsets(i)))
                 s32 = split.small(i)
                 feat_maps = self.upsample[i if cfg.DEV.MULTI_UPSAMPLER else 0](x[i]).contiguous(memory_format=cl)   # make-up layer
                 boxes, ind = split.small_boxes(i), split.small_ind(i)
                 info["s7"] = len(specs)
-                specs.append(dict(image=feat_maps, boxes=boxes, box_ind=ind, size=self.pool_size, out=pooled_out, dst_row=s32))
+                specs.append(dict(image=feat_maps, boxes=boxes, box_ind=ind, size=self.pool_size, out=pooled_out, dst_row=s32,
+                                  img_offsets=split.small_img_offsets(i)))
                 info["s14"] = len(specs)
                 specs.append(dict(image=feat_maps, boxes=boxes, box_ind=ind, size=self.mask_pool_size, out=mask_out, dst_row=s32,
-                                  compact=want_critic))
+                                  compact=want_critic, img_offsets=split.small_img_offsets(i)))
             plan.append(info)
         outs, comps = crop_sets(specs) if specs else ([], [])
         for info in plan:                          # the tensors after the (single) in-place node

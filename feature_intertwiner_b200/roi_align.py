@@ -10,10 +10,16 @@ Both accept the image in either memory format: contiguous NCHW (the reference's)
 ``torch.channels_last`` (the native one here -- see csrc/roi_align.cu); crops come back in the same format,
 logical shape ``[R, C, crop_h, crop_w]`` either way.
 """
+import ctypes as C
+import os
+
 import torch
 from torch import nn
 
 from . import _lib
+
+# image-by-image (L2-resident) backward of crop_sets when per-image extents are known; FI_BWD_BY_IMAGE=0 disables
+_BY_IMAGE = os.environ.get("FI_BWD_BY_IMAGE", "1") != "0"
 
 
 # ---- optional per-launch timing (bench.py): CUDA events on the launching stream + what is needed to count the
@@ -255,7 +261,8 @@ class _CropSets(torch.autograd.Function):
             primary, second = (out, comp) if out is not None else (comp, None)
             arr[k] = _lib.FwdSet(_lib.ptr(im), _lib.ptr(boxes), _lib.ptr(box_ind), _lib.ptr(dst_row) if out is not None else None,
                                  _lib.ptr(primary), _lib.ptr(second), B, H, W, Cc, R, P, P, float(sp.get("extrapolation", 0.0)))
-            keep.append(dict(boxes=boxes, box_ind=box_ind, dst_row=dst_row, im_size=(B, Cc, H, W), crop=(P, P), dual=(out is not None and comp is not None)))
+            keep.append(dict(boxes=boxes, box_ind=box_ind, dst_row=dst_row, im_size=(B, Cc, H, W), crop=(P, P), dual=(out is not None and comp is not None),
+                             img_offsets=sp.get("img_offsets")))
         with torch.cuda.device(dev), _Timed("crop_fwd_nhwc", sets=keep):
             _lib.check(_lib.lib().fi_crop_sets_forward(arr, len(plan["sets"]), _lib.stream_ptr(dev)))
         ctx.mark_dirty(*outs)
@@ -279,7 +286,7 @@ class _CropSets(torch.autograd.Function):
             sizes[sp["image"]] = keep[k]["im_size"]
         numel = {i: sz[0] * sz[1] * sz[2] * sz[3] for i, sz in sizes.items()}
         g_images = {i: torch.empty(sizes[i], device=dev, dtype=torch.float32, memory_format=cl) for i in sorted(sizes)}
-        sets, nbytes = [], 0
+        sets, nbytes, offsets = [], 0, []
         for k, sp in enumerate(plan["sets"]):
             kp = keep[k]
             B, Cc, H, W = kp["im_size"]
@@ -295,6 +302,7 @@ class _CropSets(torch.autograd.Function):
                 continue
             sets.append(_lib.BwdSet(_lib.ptr(g_images[sp["image"]]), _lib.ptr(g1), _lib.ptr(g2), _lib.ptr(kp["boxes"]), _lib.ptr(kp["box_ind"]),
                                     _lib.ptr(rows), B, H, W, Cc, R, P, P))
+            offsets.append(kp.get("img_offsets"))
             nbytes += 4 * Cc * R * P * P * (2 if g2 is not None else 1) + 20 * R
         nbytes += 4 * sum(numel.values())
         if sets:
@@ -312,7 +320,15 @@ class _CropSets(torch.autograd.Function):
                                                                        _lib.stream_ptr(dev)))
                 else:
                     arr = (_lib.BwdSet * len(sets))(*sets)
-                    _lib.check(L.fi_crop_sets_backward(arr, len(sets), 1, _lib.stream_ptr(dev)))
+                    nb = sets[0].batch
+                    by_image = _BY_IMAGE and all(o is not None and len(o) == nb + 1 for o in offsets) and all(st.batch == nb for st in sets) \
+                        and len({st.grads_image for st in sets}) == len(g_images)
+                    if by_image:
+                        # image by image: zero a slice, reduce into it while it is L2-resident (fi_crop_sets_backward_by_image)
+                        flat_off = (C.c_int * (len(sets) * (nb + 1)))(*[v for o in offsets for v in o])
+                        _lib.check(L.fi_crop_sets_backward_by_image(arr, len(sets), flat_off, nb, _lib.stream_ptr(dev)))
+                    else:
+                        _lib.check(L.fi_crop_sets_backward(arr, len(sets), 1, _lib.stream_ptr(dev)))
         touched = {st.grads_image for st in sets}
         for i, gi in g_images.items():
             if _lib.ptr(gi) not in touched:
@@ -336,7 +352,8 @@ def crop_sets(specs):
     for sp in specs:
         sets.append(dict(image=slot(images, sp["image"]), out=(slot(outs, sp["out"]) if sp.get("out") is not None else None),
                          boxes=sp["boxes"], box_ind=sp["box_ind"], dst_row=sp.get("dst_row"), size=int(sp["size"]),
-                         compact=bool(sp.get("compact", False)), extrapolation=float(sp.get("extrapolation", 0.0))))
+                         compact=bool(sp.get("compact", False)), extrapolation=float(sp.get("extrapolation", 0.0)),
+                         img_offsets=sp.get("img_offsets")))
         if sets[-1]["out"] is not None and sets[-1]["dst_row"] is None:
             raise _lib.FiError("crop_sets: a set with `out` needs `dst_row`")
     plan = dict(n_img=len(images), n_out=len(outs), sets=sets)

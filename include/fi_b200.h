@@ -152,6 +152,13 @@ typedef struct fi_bwd_set {
 /* zero_first != 0: every distinct grads_image is zero-filled once before the (single) reduction launch. */
 int fi_crop_sets_backward(const fi_bwd_set *sets, int num_sets, int zero_first, cudaStream_t stream);
 
+/* The same reduction, image by image: for every image b, the slices of the dense maps that belong to b are zero-filled and
+ * IMMEDIATELY reduced into while they are still in the 126 MB L2 (maps are packed into groups of <= ~100 MB per image), so
+ * reductions hit L2 and every line goes to DRAM once -- instead of zero-filling 1.5 GB up front and fetching each line
+ * back.  Requires box_ind non-decreasing in every set; img_offsets (HOST array [num_sets, batch + 1]) gives, for each set, the
+ * first box of each image (img_offsets[s][batch] = num_boxes). */
+int fi_crop_sets_backward_by_image(const fi_bwd_set *sets, int num_sets, const int *img_offsets, int batch, cudaStream_t stream);
+
 /* Integer taps of every sample, taps[num_boxes,crop_h,crop_w,5] = (y_lo,y_hi,x_lo,x_hi,inside): the "RoI
  * indices" the parity bar requires bit-exact (crop_and_resize_kernel.cu:40-70). */
 int fi_crop_taps(const float *boxes, int num_boxes, int image_height, int image_width, int crop_height,
@@ -176,10 +183,12 @@ int fi_split_levels(const int *level, int n, int *small_idx, int *small_cnt, int
  * small_boxes/big_boxes [4,n,4] = rois[idx], small_ind/big_ind [4,n] = idx / rois_per_image (the image a RoI belongs to),
  * small_gt/big_gt [4,n] = gt[idx] (only when gt != NULL).  `order` (NULL or a permutation of 0..n-1) is the order in which RoIs
  * are visited: with a spatially sorted order the lists -- and so the RoIAlign work -- walk each image coherently, which is what
- * keeps overlapping RoIs' taps in L2; NULL gives torch.nonzero order. */
+ * keeps overlapping RoIs' taps in L2; NULL gives torch.nonzero order.  img_cnt (NULL or [8, ceil(n / rois_per_image)]): how many
+ * members of list k (0-3 small, 4-7 big) belong to image b -- with an image-major visiting order these are the per-image extents
+ * of every list, which fi_crop_sets_backward_by_image needs. */
 int fi_split_levels_gather(const int *level, const float *rois, const int *gt, const int *order, int n, int rois_per_image, int *small_idx,
                            int *small_cnt, int *big_idx, int *big_cnt, int *slot, float *small_boxes, int *small_ind,
-                           int *small_gt, float *big_boxes, int *big_ind, int *big_gt, cudaStream_t stream);
+                           int *small_gt, float *big_boxes, int *big_ind, int *big_gt, int *img_cnt, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * 4. Per-class statistics (lib/sub_module.py:664-684 _assign_feat2cls).

@@ -369,9 +369,9 @@ def test_dev_forward_backward_vs_restatement(fmt, loss):
     from feature_intertwiner_b200 import synth
     torch.manual_seed(5)
     g = torch.Generator().manual_seed(5)
-    shape = (256, 256, 3)
+    shape = (256, 256, 3)                       # BASELINE.json config 1: 4 x 256x256 images, 64 RoIs/img, P2 64^2 .. P5 8^2
     cfg = pyref.make_config(DATA__IMAGE_SHAPE=np.array(shape), DEV__LOSS_CHOICE=loss)
-    depth, bs, R = 256, 2, 48
+    depth, bs, R = 256, 4, 64
     ref = pyref.DevRef(cfg, depth=depth, feat_dim=1024).eval()
     dev = fi.Dev(cfg, depth).eval()
     dev.load_state_dict(ref.state_dict())
@@ -407,3 +407,64 @@ def test_dev_forward_backward_vs_restatement(fmt, loss):
             assert a.grad is None or float(a.grad.abs().max()) == 0
             continue
         np.testing.assert_allclose(a.grad.cpu().numpy(), b.grad.numpy(), rtol=1e-3, atol=2e-5)
+
+
+def test_dev_inference_and_disabled_paths():
+    """Dev.forward without class ids (test phase, lib/sub_module.py:593-600,636-638) and with the intertwiner switched off
+    (pyramid_roi_align, lib/layers.py:145-218), channels_last and NCHW, vs the restatements."""
+    fi = _fi()
+    from feature_intertwiner_b200 import synth
+    torch.manual_seed(6)
+    g = torch.Generator().manual_seed(6)
+    shape = (256, 256, 3)
+    bs, R, depth = 2, 40, 256
+    maps = [torch.randn(bs, depth, 64 >> i, 64 >> i, generator=g) for i in range(4)]
+    rois = synth.make_rois(bs, R, (256, 256), g, zero_frac=0.1)
+    cfg = pyref.make_config(DATA__IMAGE_SHAPE=np.array(shape))
+    ref = pyref.DevRef(cfg, depth=depth).eval()
+    dev = fi.Dev(cfg, depth).eval()
+    dev.load_state_dict(ref.state_dict())
+    dev.cuda()
+    with torch.no_grad():
+        po_r, mo_r, fo_r = ref(maps, rois, None)
+        for fmt in ("nhwc", "nchw"):
+            xin = [m.cuda().contiguous(memory_format=torch.channels_last) if fmt == "nhwc" else m.cuda() for m in maps]
+            po, mo, fo = dev(xin, rois.cuda(), None)
+            assert len(fo) == 2
+            np.testing.assert_allclose(po.cpu().numpy(), po_r.numpy(), rtol=1e-4, atol=1e-4)
+            np.testing.assert_allclose(mo.cpu().numpy(), mo_r.numpy(), rtol=1e-4, atol=1e-4)
+            np.testing.assert_allclose(fo[0].cpu().numpy(), fo_r[0].numpy(), rtol=1e-3, atol=1e-4)
+            np.testing.assert_array_equal(fo[1].cpu().numpy(), fo_r[1].numpy())
+        # intertwiner off -> plain pyramid RoIAlign, bit-exact against the C oracle through the restatement
+        cfg_off = pyref.make_config(DATA__IMAGE_SHAPE=np.array(shape), DEV__SWITCH=False)
+        plain = fi.Dev(cfg_off, depth).cuda()
+        for fmt in ("nhwc", "nchw"):
+            xin = [m.cuda().contiguous(memory_format=torch.channels_last) if fmt == "nhwc" else m.cuda() for m in maps]
+            po, mo, fo = plain(xin, rois.cuda())
+            assert fo is None
+            np.testing.assert_array_equal(po.cpu().numpy(), pyref.pyramid_roi_align_ref(rois, maps, 7, shape).numpy())
+            np.testing.assert_array_equal(mo.cpu().numpy(), pyref.pyramid_roi_align_ref(rois, maps, 14, shape).numpy())
+
+
+def test_dev_spatial_sort_changes_only_row_order():
+    """spatial_sort=True: pooled / mask outputs and the class statistics are unchanged (forward is order independent)."""
+    fi = _fi()
+    from feature_intertwiner_b200 import synth
+    torch.manual_seed(7)
+    g = torch.Generator().manual_seed(7)
+    cfg = pyref.make_config(DATA__IMAGE_SHAPE=np.array((256, 256, 3)))
+    dev = fi.Dev(cfg, 256).eval().cuda()
+    maps = [torch.randn(3, 256, 64 >> i, 64 >> i, generator=g).cuda().contiguous(memory_format=torch.channels_last) for i in range(4)]
+    rois = synth.make_rois(3, 64, (256, 256), g).cuda()
+    gt = synth.make_class_ids(3, 64, g).cuda()
+    with torch.no_grad():
+        po, mo, fo = dev(maps, rois, gt)
+        dev.spatial_sort = True
+        po2, mo2, fo2 = dev(maps, rois, gt)
+    assert torch.equal(po, po2) and torch.equal(mo, mo2)
+    for a, b in zip(fo[:5], fo2[:5]):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
+    # the same (feature row, class id) pairs, level-major in another order
+    ka = torch.sort(fo[5].sum(1) * 1000 + fo[6])[0]
+    kb = torch.sort(fo2[5].sum(1) * 1000 + fo2[6])[0]
+    torch.testing.assert_close(ka, kb, rtol=1e-5, atol=1e-4)

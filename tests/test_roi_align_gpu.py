@@ -305,3 +305,36 @@ def test_refuses_cpu_tensors():
     fi = _fi()
     with pytest.raises(fi.FiError):
         fi.crop_and_resize(torch.randn(1, 4, 8, 8), torch.zeros(1, 4), torch.zeros(1, dtype=torch.int32), 7, 7)
+
+
+def test_full_size_properties_c5():
+    """BASELINE.json config 5 sizes (batch 4, 2000 RoIs/img, P2 208x336): size-independent properties where the oracle would
+    take minutes -- <fwd(x),g> == <x,bwd(g)>, constant map -> constant crop, determinism of the deterministic mode."""
+    fi = _fi()
+    from feature_intertwiner_b200 import synth
+    g = torch.Generator().manual_seed(55)
+    B, R = 4, 2000
+    rois = synth.make_rois(B, R, (832, 1344), g)
+    lvl = fi.roi_level(rois.cuda(), (832, 1344, 3))
+    sp = fi.split_levels(lvl, rois=rois.cuda())
+    boxes, ind = sp.small_boxes(0), sp.small_ind(0)
+    x = torch.randn(B, 256, 208, 336, generator=g).cuda().contiguous(memory_format=torch.channels_last).requires_grad_()
+    out = fi.crop_and_resize(x, boxes, ind, 14, 14)
+    gy = torch.randn(out.shape, generator=g).cuda().contiguous(memory_format=torch.channels_last)
+    out.backward(gy)
+    lhs = (out.detach().double() * gy.double()).sum()
+    rhs = (x.detach().double() * x.grad.double()).sum()
+    assert abs(lhs - rhs) / abs(lhs) < 1e-5
+    const = torch.full((B, 256, 208, 336), 1.5, device="cuda").contiguous(memory_format=torch.channels_last)
+    inside = (boxes.min(dim=1)[0] >= 0) & (boxes.max(dim=1)[0] <= 1)
+    assert torch.all(fi.crop_and_resize(const, boxes, ind, 7, 7)[inside] == 1.5)
+    old = fi.set_deterministic(True)
+    try:
+        grads = []
+        for _ in range(2):
+            x.grad = None
+            fi.crop_and_resize(x, boxes[:300], ind[:300], 7, 7).backward(gy[:300, :, :7, :7].contiguous(memory_format=torch.channels_last))
+            grads.append(x.grad.clone())
+        assert torch.equal(grads[0], grads[1])
+    finally:
+        fi.set_deterministic(old)
