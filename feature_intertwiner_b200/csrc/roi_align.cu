@@ -381,6 +381,9 @@ FI_API int fi_crop_taps(const float *boxes, int num_boxes, int H, int W, int ph,
     return check_launch("fi_crop_taps");
 }
 
+int fi_crop_forward_nchw_tma(const float *image, const float *boxes, const int *box_ind, const int *dst_row, int R, int B, int H, int W, int ph,
+                             int pw, int C, float extrap, float *crops, cudaStream_t stream);   // roi_align_nchw_tma.cu
+
 static int forward_impl(const float *image, int image_layout, const float *boxes, const int *box_ind, const int *dst_row, int R, int B, int H,
                         int W, int ph, int pw, int C, float extrap, float *crops, int crops_layout, float *crops2, cudaStream_t stream) {
     if (int e = check_common(image, boxes, box_ind, crops, R, B, H, W, ph, pw, C)) return e;
@@ -410,6 +413,13 @@ static int forward_impl(const float *image, int image_layout, const float *boxes
     }
     if (image_layout == FI_LAYOUT_NCHW) {
         if (crops2) { set_error(FI_ERR_UNSUPPORTED, "fi_crop_and_resize_forward_dual is NHWC only"); return FI_ERR_UNSUPPORTED; }
+        {   // TMA-staged region tiles (roi_align_nchw_tma.cu) when the shape qualifies; FI_NCHW_TMA=0 selects the plain kernel
+            const char *mode = getenv("FI_NCHW_TMA");
+            if (!(mode && mode[0] == '0')) {
+                const int rc = fi_crop_forward_nchw_tma(image, boxes, box_ind, dst_row, R, B, H, W, ph, pw, C, extrap, crops, stream);
+                if (rc != FI_ERR_UNSUPPORTED) return rc;
+            }
+        }
         if (ph <= kNchwMaxTaps && pw <= kNchwMaxTaps) {
             dim3 grid(R, ceil_div(C, kNchwChunk));
             crop_fwd_nchw_kernel<<<grid, 256, 0, stream>>>(image, boxes, box_ind, dst_row, B, H, W, ph, pw, C, extrap, crops);
