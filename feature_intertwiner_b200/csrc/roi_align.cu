@@ -413,9 +413,10 @@ static int forward_impl(const float *image, int image_layout, const float *boxes
     }
     if (image_layout == FI_LAYOUT_NCHW) {
         if (crops2) { set_error(FI_ERR_UNSUPPORTED, "fi_crop_and_resize_forward_dual is NHWC only"); return FI_ERR_UNSUPPORTED; }
-        {   // TMA-staged region tiles (roi_align_nchw_tma.cu) when the shape qualifies; FI_NCHW_TMA=0 selects the plain kernel
+        {   // TMA-staged region tiles (roi_align_nchw_tma.cu) when the shape qualifies; opt-in (FI_NCHW_TMA=1): measured on
+            // C2 it is 0-60 % slower than the L1-cached direct loads below (profiles/r01_microbench_c2_tma.json), so it is not the default
             const char *mode = getenv("FI_NCHW_TMA");
-            if (!(mode && mode[0] == '0')) {
+            if (mode && mode[0] == '1') {
                 const int rc = fi_crop_forward_nchw_tma(image, boxes, box_ind, dst_row, R, B, H, W, ph, pw, C, extrap, crops, stream);
                 if (rc != FI_ERR_UNSUPPORTED) return rc;
             }

@@ -12,7 +12,8 @@
 // Tile shapes are baked into the tensor maps, so nine maps (8/16/32 x 8/16/32 pixels, channel depth chosen for ~32 KB
 // per stage) are encoded per call and the CTA picks the smallest one that covers its rectangle.  Boxes whose footprint
 // exceeds 32x32 pixels (RoIs pooled on much finer maps) take the direct-load path of roi_align.cu.
-// Needs W % 4 == 0 (TMA global strides are multiples of 16 B), C % 64 == 0 and a 16-byte aligned map.
+// Needs W % 4 == 0 (TMA global strides are multiples of 16 B), C % 64 == 0 and a 16-byte aligned map; the tile's x origin is
+// rounded down to a multiple of 4 pixels (16 B), which the copy engine requires of the innermost coordinate.
 #include <cuda.h>
 
 #include "fi_common.cuh"
@@ -106,6 +107,9 @@ __global__ void __launch_bounds__(kTmaThreads) crop_fwd_nchw_tma_kernel(const __
         for (int k = 0; k < pw; ++k) if (t.xin[k]) { xmin = min(xmin, t.xlo[k]); xmax = max(xmax, t.xhi[k]); }
         int cfg = -2;
         if (xmax >= 0 && ymax >= 0) {
+            // The innermost start coordinate of a tiled copy must be 16-byte aligned (x % 4 == 0 for fp32): an unaligned x
+            // faults with "illegal instruction" on B200 (tools/probe/tma_probe.cu).  Rows and planes may start anywhere.
+            xmin &= ~3;
             const int w = xmax - xmin + 1, h = ymax - ymin + 1;
             cfg = -1;
             if (w <= 32 && h <= 32) cfg = (h <= 8 ? 0 : (h <= 16 ? 1 : 2)) * 3 + (w <= 8 ? 0 : (w <= 16 ? 1 : 2));
@@ -114,6 +118,7 @@ __global__ void __launch_bounds__(kTmaThreads) crop_fwd_nchw_tma_kernel(const __
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
     const int cfg = rect[2];

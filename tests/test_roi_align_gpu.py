@@ -360,6 +360,7 @@ def test_nchw_tma_path_matches_plain_kernel(monkeypatch):
     for P in (7, 14, (3, 5)):
         ph, pw = (P, P) if isinstance(P, int) else P
         want = clib.oracle_crop_and_resize_fwd(image.numpy(), boxes.numpy(), ind.numpy(), ph, pw, 0.25)
+        monkeypatch.setenv("FI_NCHW_TMA", "1")
         got = fi.crop_and_resize(image.cuda(), boxes.cuda(), ind.cuda(), ph, pw, 0.25)
         np.testing.assert_array_equal(got.cpu().numpy(), want)
         monkeypatch.setenv("FI_NCHW_TMA", "0")
