@@ -513,6 +513,7 @@ FI_API int fi_crop_sets_forward(const fi_fwd_set *sets, int num_sets, cudaStream
 }
 
 int fi_banded_backward(const fi_bwd_set *sets, int num_sets, int zero_first, cudaStream_t stream);   // roi_align_bwd_banded.cu
+int fi_tile_backward(const fi_bwd_set *sets, int num_sets, int accumulate, int exact, cudaStream_t stream);   // roi_align_bwd_tile.cu
 
 FI_API int fi_crop_sets_backward(const fi_bwd_set *sets, int num_sets, int zero_first, cudaStream_t stream) {
     FI_REQUIRE(sets && num_sets >= 1 && num_sets <= kMaxBwdSets, "fi_crop_sets_backward: 1..%d sets", kMaxBwdSets);
@@ -522,11 +523,18 @@ FI_API int fi_crop_sets_backward(const fi_bwd_set *sets, int num_sets, int zero_
         if (int e = check_common(h.grads, h.boxes, h.box_ind, h.grads_image, h.num_boxes, h.batch, h.image_height, h.image_width, h.crop_height,
                                  h.crop_width, h.depth)) return e;
     }
-    {   // FI_BWD=banded selects the L2-resident banded reduction (roi_align_bwd_banded.cu): ideal DRAM traffic (4.6 GB vs
-        // 9.5 GB on C2, ncu) but band-boundary stalls make it slower today (2.7 ms vs 1.95 ms) -- experimental, see DESIGN.md
+    {   // Formulation.  Default: tile-owner kernel (roi_align_bwd_tile.cu) -- shared-memory accumulation,
+        // every map pixel written once, no zero fill, no atomics; exact (bit-identical to crop_and_resize.c) when
+        // fi_set_deterministic(1) or FI_BWD=exact.  FI_BWD=red: vector reductions (below).  FI_BWD=banded: L2-resident banded
+        // reductions (roi_align_bwd_banded.cu, experimental).
         const char *mode = getenv("FI_BWD");
         if (mode && mode[0] == 'b') {
             const int rc = fi_banded_backward(sets, num_sets, zero_first, stream);
+            if (rc != FI_ERR_UNSUPPORTED) return rc;
+        }
+        if (!(mode && mode[0] == 'r')) {
+            const int exact = fi_get_deterministic() || (mode && mode[0] == 'e');
+            const int rc = fi_tile_backward(sets, num_sets, zero_first ? 0 : 1, exact, stream);
             if (rc != FI_ERR_UNSUPPORTED) return rc;
         }
     }

@@ -314,6 +314,8 @@ static int gather_backward(const fi_crop_set *sets, int nsets, int B, int H, int
 int fi_scatter_backward_nhwc(const float *grads, const float *grads2, const float *boxes, const int *box_ind, const int *src_row, int R, int B,
                              int H, int W, int ph, int pw, int C, float *gimg, cudaStream_t stream);   // roi_align.cu
 
+int fi_tile_backward(const fi_bwd_set *sets, int num_sets, int accumulate, int exact, cudaStream_t stream);   // roi_align_bwd_tile.cu
+
 static int g_deterministic = 0;
 FI_API int fi_set_deterministic(int on) { const int old = g_deterministic; g_deterministic = on ? 1 : 0; return old; }
 FI_API int fi_get_deterministic(void) { return g_deterministic; }
@@ -326,21 +328,26 @@ FI_API int fi_crop_and_resize_backward_multi(const fi_crop_set *sets, int num_se
         FI_REQUIRE(s.num_boxes >= 0 && s.crop_height > 0 && s.crop_width > 0, "fi_crop_and_resize_backward_multi: bad set %d", i);
         FI_REQUIRE(s.num_boxes == 0 || (s.grads && s.boxes && s.box_ind), "fi_crop_and_resize_backward_multi: null pointer in set %d", i);
     }
+    fi_bwd_set tmp[12];
+    const bool fits = num_sets <= 12 && depth % 128 == 0;
+    for (int i = 0; fits && i < num_sets; ++i) {
+        tmp[i].grads_image = grads_image; tmp[i].grads = sets[i].grads; tmp[i].grads2 = sets[i].grads2; tmp[i].boxes = sets[i].boxes;
+        tmp[i].box_ind = sets[i].box_ind; tmp[i].src_row = sets[i].src_row; tmp[i].batch = batch; tmp[i].image_height = image_height;
+        tmp[i].image_width = image_width; tmp[i].depth = depth; tmp[i].num_boxes = sets[i].num_boxes;
+        tmp[i].crop_height = sets[i].crop_height; tmp[i].crop_width = sets[i].crop_width;
+    }
     if (deterministic) {
-        const int rc = gather_backward(sets, num_sets, batch, image_height, image_width, depth, grads_image, accumulate, stream);
+        // exact tile-owner kernel (roi_align_bwd_tile.cu); FI_BWD=gather keeps the older register-accumulator gather of this file
+        const char *mode = getenv("FI_BWD");
+        int rc = FI_ERR_UNSUPPORTED;
+        if (mode && mode[0] == 'g') rc = gather_backward(sets, num_sets, batch, image_height, image_width, depth, grads_image, accumulate, stream);
+        else if (fits) rc = fi_tile_backward(tmp, num_sets, accumulate, 1, stream);
         if (rc != FI_ERR_UNSUPPORTED) return rc;
         set_error(FI_ERR_UNSUPPORTED, "deterministic RoIAlign backward needs depth %% 128 == 0, crops <= 16x16, 16-byte aligned NHWC tensors");
         return FI_ERR_UNSUPPORTED;
     }
-    // L2-resident banded reduction when the shape qualifies (roi_align_bwd_banded.cu) ...
-    if (num_sets <= 12 && depth % 128 == 0) {
-        fi_bwd_set tmp[12];
-        for (int i = 0; i < num_sets; ++i) {
-            tmp[i].grads_image = grads_image; tmp[i].grads = sets[i].grads; tmp[i].grads2 = sets[i].grads2; tmp[i].boxes = sets[i].boxes;
-            tmp[i].box_ind = sets[i].box_ind; tmp[i].src_row = sets[i].src_row; tmp[i].batch = batch; tmp[i].image_height = image_height;
-            tmp[i].image_width = image_width; tmp[i].depth = depth; tmp[i].num_boxes = sets[i].num_boxes;
-            tmp[i].crop_height = sets[i].crop_height; tmp[i].crop_width = sets[i].crop_width;
-        }
+    // tile-owner kernel / reductions when the shape qualifies (fi_crop_sets_backward picks) ...
+    if (fits) {
         const int rc = fi_crop_sets_backward(tmp, num_sets, accumulate ? 0 : 1, stream);
         if (rc != FI_ERR_UNSUPPORTED) return rc;
     }

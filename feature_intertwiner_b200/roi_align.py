@@ -18,9 +18,9 @@ from torch import nn
 
 from . import _lib
 
-# FI_BWD_BY_IMAGE=1: image-by-image (L2-resident) backward of crop_sets when per-image extents are known.  Measured on C2:
-# DRAM traffic drops to the algorithmic 4.6 GB but the time does not (1.81 vs 1.69 ms) -- the reduction kernel is bound by
-# L2 reduction throughput (~3.5 TB/s of RED payload), not by DRAM -- so it is off by default.
+# FI_BWD_BY_IMAGE=1 (with FI_BWD=red): image-by-image (L2-resident) REDUCTION backward of crop_sets when per-image extents are
+# known.  Measured on C2: DRAM traffic drops to the algorithmic 4.6 GB but the time does not (1.81 vs 1.69 ms) -- the reduction
+# kernel is bound by L2 reduction throughput (~3.5 TB/s of RED payload), not by DRAM.  Experimental.
 _BY_IMAGE = os.environ.get("FI_BWD_BY_IMAGE", "0") == "1"
 
 
@@ -310,27 +310,17 @@ class _CropSets(torch.autograd.Function):
         if sets:
             L = _lib.lib()
             with torch.cuda.device(dev), _Timed("crop_bwd_nhwc", alg_bytes=nbytes):
-                if L.fi_get_deterministic():
-                    by_map = {}
-                    for st in sets:
-                        by_map.setdefault(st.grads_image, []).append(st)
-                    for ptr, group in by_map.items():     # write-once gather: no zero fill needed
-                        arr = (_lib.CropSet * len(group))(*[_lib.CropSet(g.grads, g.grads2, g.boxes, g.box_ind, g.src_row, g.num_boxes, g.crop_height, g.crop_width)
-                                                            for g in group])
-                        g0 = group[0]
-                        _lib.check(L.fi_crop_and_resize_backward_multi(arr, len(group), g0.batch, g0.image_height, g0.image_width, g0.depth, ptr, 0, 1,
-                                                                       _lib.stream_ptr(dev)))
+                arr = (_lib.BwdSet * len(sets))(*sets)
+                nb = sets[0].batch
+                by_image = _BY_IMAGE and not L.fi_get_deterministic() and all(o is not None and len(o) == nb + 1 for o in offsets) \
+                    and all(st.batch == nb for st in sets) and len({st.grads_image for st in sets}) == len(g_images)
+                if by_image:
+                    # image by image: zero a slice, reduce into it while it is L2-resident (fi_crop_sets_backward_by_image)
+                    flat_off = (C.c_int * (len(sets) * (nb + 1)))(*[v for o in offsets for v in o])
+                    _lib.check(L.fi_crop_sets_backward_by_image(arr, len(sets), flat_off, nb, _lib.stream_ptr(dev)))
                 else:
-                    arr = (_lib.BwdSet * len(sets))(*sets)
-                    nb = sets[0].batch
-                    by_image = _BY_IMAGE and all(o is not None and len(o) == nb + 1 for o in offsets) and all(st.batch == nb for st in sets) \
-                        and len({st.grads_image for st in sets}) == len(g_images)
-                    if by_image:
-                        # image by image: zero a slice, reduce into it while it is L2-resident (fi_crop_sets_backward_by_image)
-                        flat_off = (C.c_int * (len(sets) * (nb + 1)))(*[v for o in offsets for v in o])
-                        _lib.check(L.fi_crop_sets_backward_by_image(arr, len(sets), flat_off, nb, _lib.stream_ptr(dev)))
-                    else:
-                        _lib.check(L.fi_crop_sets_backward(arr, len(sets), 1, _lib.stream_ptr(dev)))
+                    # default: tile-owner kernel, every map written once (exact arithmetic under set_deterministic)
+                    _lib.check(L.fi_crop_sets_backward(arr, len(sets), 1, _lib.stream_ptr(dev)))
         touched = {st.grads_image for st in sets}
         for i, gi in g_images.items():
             if _lib.ptr(gi) not in touched:
@@ -367,9 +357,10 @@ def crop_sets(specs):
 
 
 def set_deterministic(on=True):
-    """Deterministic RoIAlign backward (channels_last, C % 128 == 0, crops <= 16x16): every pixel is summed by one warp in
-    the order of the reference's serial CPU loop -- run-to-run identical and bit-identical to crop_and_resize.c:157-252.
-    Slower than the default vector reductions when many RoIs overlap.  Returns the previous setting."""
+    """Exact RoIAlign backward (channels_last, C % 128 == 0, crops <= 16x16): every pixel is summed by one warp in the order
+    AND with the un-fused arithmetic of the reference's serial CPU loop -- bit-identical to crop_and_resize.c:157-252.
+    The default mode of the tile-owner kernel sums in the same (run-to-run deterministic) order with packed FMAs.
+    Returns the previous setting."""
     return bool(_lib.lib().fi_set_deterministic(1 if on else 0))
 
 

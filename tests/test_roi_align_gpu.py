@@ -367,3 +367,76 @@ def test_nchw_tma_path_matches_plain_kernel(monkeypatch):
         plain = fi.crop_and_resize(image.cuda(), boxes.cuda(), ind.cuda(), ph, pw, 0.25)
         monkeypatch.delenv("FI_NCHW_TMA")
         assert torch.equal(plain, got)
+
+
+@pytest.mark.parametrize("mode", ["tile", "exact", "red", "gather"])
+@pytest.mark.parametrize("shape", [(2, 256, 26, 42, 150), (3, 128, 9, 11, 40), (1, 384, 33, 70, 300)])
+def test_backward_formulations_agree(monkeypatch, mode, shape):
+    """Every formulation of the NHWC backward (csrc/roi_align_bwd_tile.cu default + exact, reductions, register gather) on
+    the same maps: ragged tile edges (H, W not multiples of 4 / 8), 1-3 channel slabs, many boxes per tile (> the 64-entry hit
+    list), zero-padded / inverted / outside boxes.  exact and gather are bit-identical to the serial CPU reference."""
+    fi = _fi()
+    B, C, H, W, R = shape
+    image, rois, box_ind = _case(77, B, C, H, W, R, zero_rows=8)
+    rois[3] = torch.tensor([0.9, 0.8, 0.1, 0.2])          # inverted
+    rois[4] = torch.tensor([-0.5, -0.5, 1.5, 1.5])        # mostly outside
+    rois[5] = torch.tensor([0.5, 0.25, 0.5, 0.25])        # degenerate, on one (fractional) position
+    g = torch.Generator().manual_seed(6)
+    for P in (7, 14, 16):
+        grads = torch.randn(R, C, P, P, generator=g)
+        want = clib.oracle_crop_and_resize_bwd(grads.numpy(), rois.numpy(), box_ind.numpy(), tuple(image.shape))
+        img = image.cuda().contiguous(memory_format=torch.channels_last).requires_grad_()
+        if mode in ("red", "exact"):
+            monkeypatch.setenv("FI_BWD", mode)
+        if mode == "gather":
+            monkeypatch.setenv("FI_BWD", "gather")
+        old = fi.set_deterministic(mode == "gather")
+        try:
+            fi.crop_and_resize(img, rois.cuda(), box_ind.cuda(), P, P).backward(grads.cuda().contiguous(memory_format=torch.channels_last))
+        finally:
+            fi.set_deterministic(old)
+            monkeypatch.delenv("FI_BWD", raising=False)
+        got = img.grad.cpu().numpy()
+        if mode in ("exact", "gather"):
+            np.testing.assert_array_equal(got, want)
+        else:
+            assert_bwd_close(got, grads.numpy(), rois.numpy(), box_ind.numpy(), tuple(image.shape), want)
+
+
+def test_tile_backward_full_size_c2_properties():
+    """C2 sizes through the level-batched entry: transpose property per map and exact == default within summation tolerance,
+    run-to-run identical bits in both modes (the tile-owner kernel has a fixed summation order)."""
+    fi = _fi()
+    from feature_intertwiner_b200 import synth
+    g = torch.Generator().manual_seed(56)
+    B, R = 8, 512
+    hw = (832, 1344)
+    rois = synth.make_rois(B, R, hw, g).cuda()
+    sp = fi.split_levels(fi.roi_level(rois, (hw[0], hw[1], 3)), rois=rois)
+    cl = torch.channels_last
+    maps = [torch.randn(B, 256, hw[0] >> (2 + i), hw[1] >> (2 + i), generator=g).cuda().contiguous(memory_format=cl) for i in range(2)]
+    res = {}
+    for mode in ("tile", "tile2", "exact", "exact2"):
+        xs = [m.clone().requires_grad_() for m in maps]
+        specs = []
+        for i in range(2):
+            specs.append(dict(image=xs[i], boxes=sp.small_boxes(i), box_ind=sp.small_ind(i), size=7))
+            specs.append(dict(image=xs[i], boxes=sp.small_boxes(i), box_ind=sp.small_ind(i), size=14))
+            specs.append(dict(image=xs[i], boxes=sp.big_boxes(i), box_ind=sp.big_ind(i), size=14))
+        _, comps = fi.crop_sets(specs)
+        gg = torch.Generator().manual_seed(9)
+        gys = [torch.randn(c.shape, generator=gg).cuda().contiguous(memory_format=cl) for c in comps]
+        old = fi.set_deterministic(mode.startswith("exact"))
+        try:
+            torch.autograd.backward(comps, gys)
+        finally:
+            fi.set_deterministic(old)
+        res[mode] = [x.grad for x in xs]
+        if mode == "tile":
+            for i in range(2):
+                lhs = sum((comps[3 * i + k].detach().double() * gys[3 * i + k].double()).sum() for k in range(3))
+                rhs = (xs[i].detach().double() * xs[i].grad.double()).sum()
+                assert abs(lhs - rhs) / abs(lhs) < 1e-5
+    for i in range(2):
+        assert torch.equal(res["tile"][i], res["tile2"][i]) and torch.equal(res["exact"][i], res["exact2"][i])
+        torch.testing.assert_close(res["tile"][i], res["exact"][i], rtol=1e-4, atol=1e-4)
