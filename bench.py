@@ -21,6 +21,7 @@ their outputs (made-up maps, critic features) and the upstream crop gradients ar
            lib/OT_module.py for the loss, on a bounded sample of the same workload.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -54,14 +55,34 @@ def measured_peak():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  NVML is queried in-process from
+    a thread (every 10 ms; a K-step region lasts tens of ms, an `nvidia-smi -lms 100` loop would see 0-1 samples of it and
+    its per-loop device enumeration stalls kernel launches); `nvidia-smi` is the fallback when pynvml is unavailable."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self.stop_flag = index, [], None, None, False
+        self.mode = os.environ.get("FI_SAMPLER", "nvml")
 
     def start(self):
+        if self.mode == "none":
+            return
+        if self.mode == "nvml":
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+                phys = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
+                h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+                self.nvml = (pynvml, h)
+                self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+                self.thread = threading.Thread(target=self._poll, daemon=True)
+                self.thread.start()
+                return
+            except Exception:
+                self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -69,19 +90,36 @@ class ClockSampler(object):
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        pynvml, h = self.nvml
+        bits = [getattr(pynvml, n, 0) for n in ("nvmlClocksThrottleReasonHwSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown",
+                                                "nvmlClocksThrottleReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwPowerCap")]
+        while not self.stop_flag:
+            try:
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append([str(sm), str(self.sm_max)] + ["Active" if (b and (r & b)) else "Not Active" for b in bits])
+            except Exception:
+                pass
+            time.sleep(0.01)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+        elif self.proc is not None:
+            self.proc.terminate()
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampler unavailable"]}
         sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
         mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[k] for r in self.rows if len(r) >= 6 for k in range(4) if r[2 + k].lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        reasons = sorted({self.NAMES[k] for r in self.rows if len(r) >= 6 for k in range(4) if r[2 + k].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm),
+                "how": "nvml thread, 10 ms" if self.nvml is not None else "nvidia-smi -lms 100"}
 
 
 # =================================================================================================== inputs
@@ -251,6 +289,11 @@ def run_ours(args):
         for _ in range(warmup):
             fn()
         barrier()
+        # the cyclic collector of a process with torch loaded walks millions of objects: a generation-2 pass landing inside a
+        # 4 ms step shows up as a 6-60 ms step.  Collect now, keep it off for the K timed steps (training loops do the same with
+        # gc.freeze / a manual collection between iterations).
+        gc.collect()
+        gc.disable()
         evs = []
         host["s"] = 0.0
         host["launch0"] = lib.fi_kernel_launches()
@@ -262,6 +305,7 @@ def run_ours(args):
             host["s"] += time.perf_counter() - t0          # host time to ENQUEUE a step (no sync inside except the split read)
             evs.append((a, b))
         barrier()
+        gc.enable()
         host["launches"] = lib.fi_kernel_launches() - host["launch0"]
         per_step = [a.elapsed_time(b) for a, b in evs]
         host["per_step"] = per_step
@@ -323,7 +367,7 @@ def run_ours(args):
                    "layout": "channels_last maps/crops (logical NCHW)", "ot": "all 80 foreground classes, absent ones masked (fixed shapes, no host sync)",
                    "roi_order": "spatially sorted per image (L2 reuse)" if step.spatial_sort else "index order",
                    "loss_head": "CUDA graph (fwd+bwd)" if step.graphed else "eager", "critic_and_makeup_convs": "excluded (stock cuDNN; SURVEY.md 8 a5)",
-                   "l2": "512 MB-class working set per step (> 126 MB L2) + 256 MB flush write between steps",
+                   "l2": "512 MB-class working set per step (> 126 MB L2) + 256 MB flush write between steps", "gc": "python cyclic GC collected before and disabled during the timed steps",
                    "small_counts": step.counts[0], "big_counts": step.counts[1], "parallelism": "dp%d by image batch" % world},
         "e2e": {"value": rois_per_step / (ms_e2e / 1e3), "unit": "RoIs/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": step.h2d_bytes, "d2h_bytes_per_step": 4},

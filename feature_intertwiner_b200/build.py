@@ -11,7 +11,8 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
-LIB_PATH = os.path.join(LIB_DIR, "libfi_b200.so")
+# FI_LIB_NAME / FI_NVCC_EXTRA: experiment builds (e.g. FI_NVCC_EXTRA="-DFI_TILE_PAIR=0" FI_LIB_NAME=libfi_b200_nopair.so)
+LIB_PATH = os.path.join(LIB_DIR, os.environ.get("FI_LIB_NAME", "libfi_b200.so"))
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -38,7 +39,7 @@ def build_library(force=False, verbose=False):
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + _sources()
+    cmd = [nvcc] + NVCC_FLAGS + os.environ.get("FI_NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + _sources()
     env = dict(os.environ)
     # the image exports CC/CXX wrappers; nvcc wants the distro host compiler
     if os.path.exists("/usr/bin/g++"):

@@ -5,16 +5,20 @@
 // The vector-reduction rewrite of that formulation (roi_align.cu) is bound by L2 reduction throughput (~3.5 TB/s of
 // RED payload, ~5 GB per C2 step) plus a 1.5 GB zero fill -- 37 % of the HBM roofline.  Here the only HBM traffic is
 // the algorithmic one: every crop gradient is read (once, plus re-reads by neighbouring tiles that L2 absorbs) and
-// every map pixel is written once; no memset, no atomics, no read-modify-write in L2/HBM.
+// every map pixel is written once; no memset, no atomics, no read-modify-write in L2/HBM (ncu: 4.17 GB for 4.06 GB).
 //
-// Work decomposition.  CTA = 2 warps = one tile x two 128-channel slabs; the warps never synchronise with each other
-// (each owns its slab of the tile in shared memory).  Per warp:
-//   scan     the boxes of the tile's image (index range from the prep kernel), 32 at a time, footprint-bounds test,
-//            ballot-compacted IN BOX ORDER into a hit list;
-//   expand   per hit box the warp loads the box's tap table (lanes 0-15 = y taps, 16-31 = x taps, 8 B per lane),
-//            two ballots give the crop rows / columns that touch the tile; lanes then describe the samples of that
-//            rectangle in parallel (tap offsets, in-tile flags, lerp weights, gradient row) and append the ones with at
-//            least one tap inside the tile to a per-warp queue -- in (box, crop row, crop column) order;
+// Launches: prep (thread per box: footprint bounds, per-image index range, list of degenerate boxes), collapse
+// (degenerate boxes only, see below), tile kernel.
+//
+// Tile kernel.  CTA = 2 warps = one tile x two 128-channel slabs; the warps never synchronise with each other (each owns
+// its slab of the tile in shared memory).  Per warp, per crop set of the map:
+//   scan     the boxes of the tile's image (index range from prep), 32 at a time: one 16 B record (bounds, image) +
+//            the box + its gradient row per lane, loads of the next chunk in flight while this one is expanded;
+//   expand   per hit box (ballot order = box order) the box is broadcast by shuffle and the lanes recompute its taps
+//            (lanes 0-15 = y taps, 16-31 = x taps, same device function as the forward); two ballots give the crop rows /
+//            columns that touch the tile; lanes then describe the samples of that rectangle in parallel (tap offsets,
+//            in-tile flags, lerp weights, gradient row) and append the ones with at least one tap inside the tile to a
+//            per-warp queue -- in (box, crop row, crop column) order.  No memory access on this path;
 //   drain    the queue is consumed in order, 8 (4 for two-source sets) 512-byte gradient loads in flight ahead of the
 //            adds (double-buffered in registers); each tap is one conflict-free LDS.128 / add / STS.128;
 //   store    the tile is streamed out, 512 B per warp instruction.
@@ -22,31 +26,49 @@
 // run-to-run deterministic; with EXACT arithmetic (un-fused fp32 mul then add, crop_and_resize.c:241-247) it is
 // bit-identical to the reference's serial CPU loop (crop_and_resize.c:190-250).  The default mode uses packed FMAs
 // (fma.rn.f32x2 -> FFMA2) with pre-multiplied weights: same order, one rounding fewer per contribution.
+//
+// Degenerate boxes.  The reference zero-pads its RoI lists (lib/layers.py:413,427): every all-zero box puts ALL its
+// P*P samples on pixel (0,0) of its image, so one tile per image would have to stream hundreds of crops through a
+// single warp (measured: a 1.6 ms serial tail).  In the default mode boxes whose footprint is at most 2x2 pixels are
+// therefore pre-reduced by the collapse kernel (one CTA per box, all warps loading in parallel) into 4 corner sums
+// that the tile kernel consumes as 4 unit-weight samples.  EXACT mode keeps the reference's sample-by-sample order.
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "fi_common.cuh"
+
+#ifndef FI_TILE_PAIR
+#define FI_TILE_PAIR 0      // 1: overlap the shared-memory round trips of two consecutive samples that touch disjoint pixels
+                            // (measured on C2: 1.65-1.69 ms vs 1.52 ms without -- bigger drain loop, spills, i-cache misses)
+#endif
+#ifndef FI_TILE_ILV
+#define FI_TILE_ILV 0       // 1: default mode queues even crop columns before odd ones, so that neighbours rarely share a pixel
+                            // (only useful with FI_TILE_PAIR; alone it measures the same 1.51 ms)
+#endif
+#ifndef FI_SCAN_DEPTH
+#define FI_SCAN_DEPTH 1     // chunks of box records in flight ahead of the scan (3 measured 1.58 ms vs 1.52 ms: register pressure)
+#endif
+#ifndef FI_TILE_MINB
+#define FI_TILE_MINB 6      // resident CTAs per SM the 4x8 kernel is compiled for (register cap)
+#endif
 
 namespace fi {
 namespace tile {
 
-constexpr int kTX = 8, kTY = 4, kTP = kTX * kTY;   // tile: 4 rows x 8 pixels; a tile row is 8 KB contiguous in NHWC (C=256)
 constexpr int kQ = 64;                             // per-warp sample queue
-constexpr int kList = 64;                          // per-warp hit list
 constexpr int kMaxCrop = 16;                       // crop_h, crop_w <= 16 (the model uses 7 and 14)
-constexpr short kNoTap = -32768;
+constexpr int kNoTap = -32768;
 constexpr int kMaxSets = 12, kMaxMaps = 8;
 
-struct TapEntry {                      // 8 bytes
-    short lo, hi;
-    float frac;
-};
-
 struct TSet {
-    const float *grads, *grads2, *boxes;
+    const float *grads, *grads2;
+    const float4 *boxes;
     const int *box_ind, *src_row;
-    TapEntry *taps;                    // [R,32]
-    int4 *bounds;                      // [R] (ymin, ymax, xmin, xmax) of the tap footprint; ymin > ymax: empty
+    int4 *rec;                         // [R] (ymin | ymax << 16, xmin | xmax << 16, image or -1, degenerate)
+    float4 *geom;                      // [R] (y of sample row 0, y step, x of sample column 0, x step) in pixels
     unsigned *range;                   // [B,2]: min box index of image b, ~(max box index); memset 0xFF = "none"
+    float *coll;                       // [R,4,C] corner sums of degenerate boxes (only those rows are written)
     int R, ph, pw, map;
 };
 struct TMap {
@@ -56,42 +78,63 @@ struct TMap {
 struct TParams {
     TSet s[kMaxSets];
     TMap m[kMaxMaps];
-    int nsets, nmaps, accumulate;
+    int *deg_list;                     // [0] = count, then (set << 24 | box) entries
+    int nsets, nmaps, accumulate, collapse;
 };
 
-// ---- prep: one warp per box (all sets in one launch): tap table, footprint bounds, per-image index range ----------
-__global__ void __launch_bounds__(256) tile_prep_kernel(const TParams P) {
+struct Tap {                           // one axis tap as the tile kernel uses it
+    int lo, hi;                        // kNoTap when the sample is outside the image
+    float frac;
+};
+// One axis tap from the per-box geometry record (base, step): the same fp32 operations as fi_common.cuh::axis_sample.
+__device__ __forceinline__ Tap geom_tap(float base, float step, int k, int extent) {
+    const float pos = __fadd_rn(base, __fmul_rn((float)k, step));
+    Tap t;
+    t.lo = kNoTap; t.hi = kNoTap; t.frac = 0.f;
+    if (!(pos < 0.f || pos > (float)(extent - 1))) {
+        t.lo = (int)floorf(pos);
+        t.hi = (int)ceilf(pos);
+        t.frac = __fsub_rn(pos, (float)t.lo);
+    }
+    return t;
+}
+__device__ __forceinline__ float geom_base(float c1, float c2, int extent, int crop) {      // crop_and_resize.c:52-56
+    if (crop > 1) return __fmul_rn(c1, (float)(extent - 1));
+    return (float)(0.5 * (double)__fadd_rn(c1, c2) * (double)(extent - 1));
+}
+
+// ---- prep: one thread per box (all sets in one launch): footprint bounds, per-image index range, degenerate list ----
+__global__ void __launch_bounds__(128) tile_prep_kernel(const TParams P) {
     const TSet &S = P.s[blockIdx.y];
-    const int lane = threadIdx.x & 31;
-    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= S.R) return;
     const int B = P.m[S.map].B, H = P.m[S.map].H, W = P.m[S.map].W;
     const int b = S.box_ind[r];
-    const bool bad = (b < 0 || b >= B);            // skipped like crop_and_resize_kernel.cu:34-38
-    if (!bad && lane == 0) { atomicMin(S.range + 2 * b, (unsigned)r); atomicMin(S.range + 2 * b + 1, ~(unsigned)r); }
-    const float y1 = S.boxes[4 * r + 0], x1 = S.boxes[4 * r + 1], y2 = S.boxes[4 * r + 2], x2 = S.boxes[4 * r + 3];
-    const bool is_y = lane < 16;
-    const int k = is_y ? lane : lane - 16;
-    const int crop = is_y ? S.ph : S.pw, extent = is_y ? H : W;
-    const float c1 = is_y ? y1 : x1, c2 = is_y ? y2 : x2;
-    TapEntry e;
-    e.lo = kNoTap; e.hi = kNoTap; e.frac = 0.f;
-    int lo = 1 << 30, hi = -(1 << 30);
-    if (!bad && k < crop) {
-        const AxisTap t = axis_sample(c1, c2, axis_step(c1, c2, extent, crop), k, extent, crop);
-        if (t.inside) { e.lo = (short)t.lo; e.hi = (short)t.hi; e.frac = t.frac; lo = t.lo; hi = t.hi; }
+    const float4 bx = S.boxes[r];                  // (y1, x1, y2, x2)
+    const float4 geom = make_float4(geom_base(bx.x, bx.z, H, S.ph), axis_step(bx.x, bx.z, H, S.ph), geom_base(bx.y, bx.w, W, S.pw),
+                                    axis_step(bx.y, bx.w, W, S.pw));
+    S.geom[r] = geom;
+    int ymin = 1 << 30, ymax = -(1 << 30), xmin = 1 << 30, xmax = -(1 << 30);
+    if (b >= 0 && b < B) {                         // others are skipped like crop_and_resize_kernel.cu:34-38
+        for (int k = 0; k < S.ph; ++k) {
+            const Tap t = geom_tap(geom.x, geom.y, k, H);
+            if (t.lo != kNoTap) { ymin = min(ymin, t.lo); ymax = max(ymax, t.hi); }
+        }
+        for (int k = 0; k < S.pw; ++k) {
+            const Tap t = geom_tap(geom.z, geom.w, k, W);
+            if (t.lo != kNoTap) { xmin = min(xmin, t.lo); xmax = max(xmax, t.hi); }
+        }
     }
-    S.taps[(long)r * 32 + lane] = e;
-#pragma unroll
-    for (int d = 8; d > 0; d >>= 1) {              // min / max inside each half-warp
-        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
-        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+    const bool live = ymin <= ymax && xmin <= xmax;
+    int4 rec = make_int4(0, 0, -1, 0);
+    if (live) {
+        const bool degenerate = (ymax - ymin <= 1) && (xmax - xmin <= 1) && S.ph * S.pw > 4;
+        rec = make_int4(ymin | (ymax << 16), xmin | (xmax << 16), b, degenerate ? 1 : 0);
+        atomicMin(S.range + 2 * b, (unsigned)r);
+        atomicMin(S.range + 2 * b + 1, ~(unsigned)r);
+        if (degenerate && P.collapse) P.deg_list[1 + atomicAdd(P.deg_list, 1)] = ((int)blockIdx.y << 24) | r;
     }
-    const int xlo = __shfl_sync(0xffffffffu, lo, 16), xhi = __shfl_sync(0xffffffffu, hi, 16);
-    if (lane == 0) {
-        const bool empty = (lo > hi) || (xlo > xhi);
-        S.bounds[r] = empty ? make_int4(1, 0, 1, 0) : make_int4(lo, hi, xlo, xhi);
-    }
+    S.rec[r] = rec;
 }
 
 // ---- arithmetic -----------------------------------------------------------------------------------------------------
@@ -117,89 +160,235 @@ __device__ __forceinline__ float4 fma4(float4 g, float w, float4 a) {
     return r;
 }
 
-struct __align__(16) WarpSmem {
-    float tile[kTP * 128];             // this warp's slab of the tile: [pixel][128 channels]
-    uint4 q4[kQ];                      // sample queue: (row of grads, row of grads2, fy bits, fx bits)
-    int qp[kQ];                        //               in-tile flags TL|TR|BL|BR (bits 0-3), TL pixel offset + 16 (bits 4..)
-    int list[kList];                   // hit boxes, in index order
-};
-
-// One queued sample: up to 4 read-modify-writes of this lane's float4 in the tile.  Flags / offsets are warp-uniform.
-template <bool EXACT>
-__device__ __forceinline__ void apply_sample(float *tile_lane, int pk, float fy, float fx, float4 g) {
-    float4 *tp = reinterpret_cast<float4 *>(tile_lane + ((pk >> 4) - 16) * 128);
-    const float wy0 = __fsub_rn(1.f, fy), wx0 = __fsub_rn(1.f, fx);                 // crop_and_resize.c:241-247
-    if (EXACT) {
-        const float4 dtop = mul_rn4(wy0, g), dbot = mul_rn4(fy, g);
-        if (pk & 1) tp[0] = add_rn4(tp[0], mul_rn4(wx0, dtop));
-        if (pk & 2) tp[32] = add_rn4(tp[32], mul_rn4(fx, dtop));
-        if (pk & 4) tp[kTX * 32] = add_rn4(tp[kTX * 32], mul_rn4(wx0, dbot));
-        if (pk & 8) tp[kTX * 32 + 32] = add_rn4(tp[kTX * 32 + 32], mul_rn4(fx, dbot));
-    } else {
-        if (pk & 1) tp[0] = fma4(g, wy0 * wx0, tp[0]);
-        if (pk & 2) tp[32] = fma4(g, wy0 * fx, tp[32]);
-        if (pk & 4) tp[kTX * 32] = fma4(g, fy * wx0, tp[kTX * 32]);
-        if (pk & 8) tp[kTX * 32 + 32] = fma4(g, fy * fx, tp[kTX * 32 + 32]);
+// ---- collapse: corner sums of degenerate boxes (footprint <= 2x2 pixels), one CTA per box -------------------------
+// coll[r][corner][c] = sum over the box's samples of (tap weight on that corner) * (grads + grads2); corner =
+// 2 * (y - ymin) + (x - xmin).  8 warps split the samples, lanes hold float4 of a 128-channel slab.
+__global__ void __launch_bounds__(256) tile_collapse_kernel(const TParams P) {
+    __shared__ float4 part[8][4][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int count = P.deg_list[0];
+    for (int it = blockIdx.x; it < count; it += gridDim.x) {
+        const int code = P.deg_list[1 + it];
+        const TSet &S = P.s[code >> 24];
+        const int r = code & 0xffffff;
+        const int H = P.m[S.map].H, W = P.m[S.map].W, C = P.m[S.map].C;
+        const int4 rec = S.rec[r];
+        const int ymin = (short)(rec.x & 0xffff), xmin = (short)(rec.y & 0xffff);
+        const float4 geom = S.geom[r];
+        const long grow = S.src_row ? (long)S.src_row[r] : (long)r;
+        const int pp = S.ph * S.pw;
+        for (int slab = 0; slab * 128 < C; ++slab) {
+            const int coff = slab * 128 + lane * 4;
+            float4 acc[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int s0 = w; s0 < pp; s0 += 32) {                      // 4 samples per warp per round, loads first
+                float4 g[4];
+                Tap ty[4], tx[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int s = s0 + 8 * q;
+                    const int sc = min(s, pp - 1);
+                    const int i = sc / S.pw, j = sc - i * S.pw;
+                    ty[q] = geom_tap(geom.x, geom.y, i, H);
+                    tx[q] = geom_tap(geom.z, geom.w, j, W);
+                    if (s >= pp) ty[q].lo = kNoTap;
+                    g[q] = __ldcs(reinterpret_cast<const float4 *>(S.grads + ((grow * S.ph + i) * S.pw + j) * (long)C + coff));
+                    if (S.grads2) g[q] = add_rn4(g[q], __ldcs(reinterpret_cast<const float4 *>(S.grads2 + (((long)r * S.ph + i) * S.pw + j) * (long)C + coff)));
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (ty[q].lo == kNoTap || tx[q].lo == kNoTap) continue;
+                    const float wy1 = ty[q].frac, wy0 = 1.f - wy1, wx1 = tx[q].frac, wx0 = 1.f - wx1;
+                    const int cy0 = ty[q].lo - ymin, cy1 = ty[q].hi - ymin, cx0 = tx[q].lo - xmin, cx1 = tx[q].hi - xmin;   // each 0 or 1
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int cy = c >> 1, cx = c & 1;
+                        float wgt = 0.f;                                   // coinciding taps: the `hi` one carries weight 0
+                        if (cy == cy0 && cx == cx0) wgt += wy0 * wx0;
+                        if (cy == cy0 && cx == cx1 && cx1 != cx0) wgt += wy0 * wx1;
+                        if (cy == cy1 && cy1 != cy0 && cx == cx0) wgt += wy1 * wx0;
+                        if (cy == cy1 && cy1 != cy0 && cx == cx1 && cx1 != cx0) wgt += wy1 * wx1;
+                        acc[c] = fma4(g[q], wgt, acc[c]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) part[w][c][lane] = acc[c];
+            __syncthreads();
+            if (w < 4) {
+                float4 v = part[0][w][lane];
+#pragma unroll
+                for (int q = 1; q < 8; ++q) v = add_rn4(v, part[q][w][lane]);
+                *reinterpret_cast<float4 *>(S.coll + ((long)r * 4 + w) * C + coff) = v;
+            }
+            __syncthreads();
+        }
     }
 }
 
+template <int TY, int TX>
+struct __align__(16) WarpSmemT {
+    float tile[TY * TX * 128];         // this warp's slab of the tile: [pixel][128 channels]
+    uint4 qa[kQ];                      // sample queue: (row of grads, row of grads2, pk, -)
+    float4 qw[kQ];                     //               tap weights (TL, TR, BL, BR); EXACT: (1 - fy, fy, 1 - fx, fx)
+    int list[64];                      // hit boxes, in index order
+};
+// pk: in-tile flags TL|TR|BL|BR (bits 0-3), kCollapsed (bit 4), byte offset of the TL pixel inside the warp's tile (bits 9.., signed)
+constexpr int kCollapsed = 1 << 4;
+constexpr int kIndep = 1 << 5;                    // this sample (odd queue slot) shares no pixel with the one before it
+
+// One queued sample: up to 4 read-modify-writes of this lane's float4 in the tile.  Flags / offsets are warp-uniform.
+struct TapVals { float4 v0, v1, v2, v3; };
+
+template <int TX>
+__device__ __forceinline__ TapVals taps_load(const float *tile_lane, int pk) {
+    const float4 *tp = reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(tile_lane) + (pk & ~0x1ff));
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    TapVals t;
+    t.v0 = z; t.v1 = z; t.v2 = z; t.v3 = z;
+    if (pk & 1) t.v0 = tp[0];
+    if (pk & 2) t.v1 = tp[32];
+    if (pk & 4) t.v2 = tp[TX * 32];
+    if (pk & 8) t.v3 = tp[TX * 32 + 32];
+    return t;
+}
+template <bool EXACT>
+__device__ __forceinline__ void taps_add(TapVals &t, float4 w, float4 g) {
+    if (EXACT) {                                                                     // crop_and_resize.c:241-247
+        const float4 dtop = mul_rn4(w.x, g), dbot = mul_rn4(w.y, g);
+        t.v0 = add_rn4(t.v0, mul_rn4(w.z, dtop));
+        t.v1 = add_rn4(t.v1, mul_rn4(w.w, dtop));
+        t.v2 = add_rn4(t.v2, mul_rn4(w.z, dbot));
+        t.v3 = add_rn4(t.v3, mul_rn4(w.w, dbot));
+    } else {
+        t.v0 = fma4(g, w.x, t.v0);
+        t.v1 = fma4(g, w.y, t.v1);
+        t.v2 = fma4(g, w.z, t.v2);
+        t.v3 = fma4(g, w.w, t.v3);
+    }
+}
+template <int TX>
+__device__ __forceinline__ void taps_store(float *tile_lane, int pk, const TapVals &t) {
+    float4 *tp = reinterpret_cast<float4 *>(reinterpret_cast<char *>(tile_lane) + (pk & ~0x1ff));
+    if (pk & 1) tp[0] = t.v0;
+    if (pk & 2) tp[32] = t.v1;
+    if (pk & 4) tp[TX * 32] = t.v2;
+    if (pk & 8) tp[TX * 32 + 32] = t.v3;
+}
+
+// One queued sample: up to 4 read-modify-writes of this lane's float4 in the tile.  Flags / offsets are warp-uniform.  The
+// four taps are distinct pixels (coinciding ones were dropped by the emitter): read all, then add, then write.
+template <bool EXACT, int TX>
+__device__ __forceinline__ void apply_sample(float *tile_lane, int pk, float4 w, float4 g) {
+    TapVals t = taps_load<TX>(tile_lane, pk);
+    taps_add<EXACT>(t, w, g);
+    taps_store<TX>(tile_lane, pk, t);
+}
+// Two consecutive samples that the emitter found to touch disjoint pixels (kIndep on the second): their shared-memory
+// round trips overlap instead of queueing behind each other -- the LDS -> FFMA -> STS latency chain is what bounds a warp.
+template <bool EXACT, int TX>
+__device__ __forceinline__ void apply_pair(float *tile_lane, int pkA, float4 wA, float4 gA, int pkB, float4 wB, float4 gB) {
+    TapVals ta = taps_load<TX>(tile_lane, pkA);
+    TapVals tb = taps_load<TX>(tile_lane, pkB);
+    taps_add<EXACT>(ta, wA, gA);
+    taps_add<EXACT>(tb, wB, gB);
+    taps_store<TX>(tile_lane, pkA, ta);
+    taps_store<TX>(tile_lane, pkB, tb);
+}
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // Consume the queue in order.  Groups of U samples; the loads of group i+1 are in flight while group i is added.
-template <bool EXACT, bool DUAL>
-__device__ __forceinline__ void drain(WarpSmem &ws, int qn, const float *__restrict__ G1, const float *__restrict__ G2, int C,
-                                      float *tile_lane) {
+// qn is a multiple of U: the emitter pads the tail with flag-less copies of the last sample.
+template <bool EXACT, bool DUAL, int TX>
+__device__ __forceinline__ void drain(const uint4 *qa, const float4 *qw, int qn, const float *__restrict__ G1, const float *__restrict__ G2,
+                                      const float *__restrict__ COLL, int C, float *tile_lane) {
     constexpr int U = DUAL ? 4 : 8;
     constexpr int UB = DUAL ? U : 1;
-    if (qn <= 0) return;
+    constexpr int kAhead = 24;                         // samples kept on their way into L2 ahead of the register loads
+    const int lane = threadIdx.x & 31;
     float4 a0[U], a1[U], b0[UB], b1[UB];
+    // 8 samples per call: lane -> (sample e0 + lane / 4, 128-byte line lane % 4 of the warp's 512-byte slab run).  Register
+    // double-buffering alone keeps ~4 KB per warp in flight -- at 12 warps / SM that is latency-bound against HBM -- so the
+    // lines are requested into L2 a window ahead and the register loads then see L2 latency.
+    auto prefetch8 = [&](int e0) {
+        const int idx = e0 + (lane >> 2);
+        if (idx < qn) {
+            const uint4 e = qa[idx];
+            const bool coll = (!EXACT) && (e.z & kCollapsed);
+            const float *src = (coll ? COLL : G1) - lane * 4 + (lane & 3) * 32;
+            prefetch_l2(src + (size_t)e.x * C);
+            if (DUAL && !coll) prefetch_l2(G2 - lane * 4 + (lane & 3) * 32 + (size_t)e.y * C);
+        }
+    };
     auto load = [&](int g0, float4(&a)[U], float4(&b)[UB]) {
 #pragma unroll
         for (int k = 0; k < U; ++k) {
-            const int idx = min(g0 + k, qn - 1);           // the tail re-reads the last sample (discarded): branch-free
-            const uint2 rows = *reinterpret_cast<const uint2 *>(&ws.q4[idx]);
-            a[k] = __ldcg(reinterpret_cast<const float4 *>(G1 + (size_t)rows.x * C));
-            if (DUAL) b[k] = __ldcg(reinterpret_cast<const float4 *>(G2 + (size_t)rows.y * C));
+            const uint4 e = qa[g0 + k];
+            const bool coll = (!EXACT) && (e.z & kCollapsed);
+            const float *src = coll ? COLL : G1;
+            a[k] = __ldcg(reinterpret_cast<const float4 *>(src + (size_t)e.x * C));
+            if (DUAL) b[k] = coll ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldcg(reinterpret_cast<const float4 *>(G2 + (size_t)e.y * C));
         }
     };
     auto process = [&](int g0, float4(&a)[U], float4(&b)[UB]) {
 #pragma unroll
-        for (int k = 0; k < U; ++k) {
-            const int idx = g0 + k;
-            if (idx < qn) {
-                const uint4 d = ws.q4[idx];
-                const int pk = ws.qp[idx];
-                const float4 g = DUAL ? add_rn4(a[k], b[k]) : a[k];
-                apply_sample<EXACT>(tile_lane, pk, __uint_as_float(d.z), __uint_as_float(d.w), g);
+        for (int k = 0; k < U; k += 2) {
+            const int pkA = (int)qa[g0 + k].z, pkB = (int)qa[g0 + k + 1].z;
+            const float4 wA = qw[g0 + k], wB = qw[g0 + k + 1];
+            const float4 gA = DUAL ? add_rn4(a[k], b[k]) : a[k];
+            const float4 gB = DUAL ? add_rn4(a[k + 1], b[k + 1]) : a[k + 1];
+            if (FI_TILE_PAIR && (pkB & kIndep)) {
+                apply_pair<EXACT, TX>(tile_lane, pkA, wA, gA, pkB, wB, gB);
+            } else {
+                apply_sample<EXACT, TX>(tile_lane, pkA, wA, gA);
+                apply_sample<EXACT, TX>(tile_lane, pkB, wB, gB);
             }
         }
     };
+#pragma unroll
+    for (int e0 = U; e0 < U + kAhead + (DUAL ? 8 : 0); e0 += 8) prefetch8(e0);
     load(0, a0, b0);
     for (int g0 = 0; g0 < qn; g0 += 2 * U) {
         const bool more = g0 + U < qn;
+        prefetch8(g0 + U + kAhead + (DUAL ? 8 : 0));
         if (more) load(g0 + U, a1, b1);
         process(g0, a0, b0);
         if (more) {
+            if (!DUAL) prefetch8(g0 + U + kAhead + 8);
             if (g0 + 2 * U < qn) load(g0 + 2 * U, a0, b0);
             process(g0 + U, a1, b1);
         }
     }
 }
 
-template <bool EXACT>
-__device__ __noinline__ void drain_any(WarpSmem &ws, int qn, const float *G1, const float *G2, int C, float *tile_lane, bool zero) {
+template <bool EXACT, int TY, int TX>
+__device__ __noinline__ void drain_any(uint4 *qa, float4 *qw, int qn, const float *G1, const float *G2, const float *COLL, int C,
+                                       float *tile_lane, bool zero) {
+    const int lane = threadIdx.x & 31;
     if (zero) {                                        // first use of the tile
 #pragma unroll
-        for (int p = 0; p < kTP; ++p) *reinterpret_cast<float4 *>(tile_lane + p * 128) = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int p = 0; p < TY * TX; ++p) *reinterpret_cast<float4 *>(tile_lane + p * 128) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncwarp();
-    if (G2) drain<EXACT, true>(ws, qn, G1, G2, C, tile_lane);
-    else drain<EXACT, false>(ws, qn, G1, nullptr, C, tile_lane);
+    const int qnp = (qn + 7) & ~7;                     // pad to whole groups: flag-less copies of the last sample (valid address)
+    if (qn + lane < qnp) {
+        uint4 e = qa[qn - 1];
+        e.z &= kCollapsed;
+        qa[qn + lane] = e;
+        qw[qn + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();
+    if (G2) drain<EXACT, true, TX>(qa, qw, qnp, G1, G2, COLL, C, tile_lane);
+    else drain<EXACT, false, TX>(qa, qw, qnp, G1, nullptr, COLL, C, tile_lane);
     __syncwarp();
 }
 
 // grid (total tiles of all maps, ceil(slabs / 2)), 64 threads
-template <bool EXACT>
-__global__ void __launch_bounds__(64, 6) bwd_smem_tile_kernel(const TParams P) {
-    __shared__ WarpSmem smem[2];
+template <bool EXACT, int TY, int TX, int MINB>
+__global__ void __launch_bounds__(64, MINB) bwd_smem_tile_kernel(const TParams P) {
+    __shared__ WarpSmemT<TY, TX> smem[2];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int t = blockIdx.x, mi = 0;
     while (mi + 1 < P.nmaps && t >= P.m[mi + 1].first_tile) ++mi;
@@ -208,13 +397,14 @@ __global__ void __launch_bounds__(64, 6) bwd_smem_tile_kernel(const TParams P) {
     const int slab = blockIdx.y * 2 + w;
     if (slab * 128 >= C) return;                       // the warps of a CTA never synchronise with each other
     t -= M.first_tile;
-    const int per_img = M.tiles_x * M.tiles_y;
+    const int tiles_x = ceil_div(W, TX), tiles_y = ceil_div(H, TY);
+    const int per_img = tiles_x * tiles_y;
     const int b = t / per_img;
     t -= b * per_img;
-    const int tyi = t / M.tiles_x, txi = t - tyi * M.tiles_x;
-    const int X0 = txi * kTX, Y0 = tyi * kTY;
+    const int tyi = t / tiles_x, txi = t - tyi * tiles_x;
+    const int X0 = txi * TX, Y0 = tyi * TY;
     const int coff = slab * 128 + lane * 4;
-    WarpSmem &ws = smem[w];
+    WarpSmemT<TY, TX> &ws = smem[w];
     float *tile_lane = ws.tile + lane * 4;
     const unsigned lt = (1u << lane) - 1u;
     bool dirty = false;                                // tile zeroed lazily, on the first queued sample
@@ -224,101 +414,182 @@ __global__ void __launch_bounds__(64, 6) bwd_smem_tile_kernel(const TParams P) {
         const unsigned first = S.range[2 * b], last = ~S.range[2 * b + 1];
         if (first > last) continue;                    // no box of this set lives in image b
         const int ph = S.ph, pw = S.pw;
-        int nl = 0, qn = 0;
+        const float *G1 = S.grads + coff, *G2 = S.grads2 ? S.grads2 + coff : nullptr, *COLL = S.coll + coff;
+        int qn = 0, nl = 0;
+        unsigned carry_mask = 0;                       // pixels of the last queued sample
+        int4 nxt = __ldg(S.rec + min((first & ~31u) + lane, last));
+#if FI_SCAN_DEPTH >= 3
+        int4 nxt2 = __ldg(S.rec + min((first & ~31u) + 32 + lane, last));
+        int4 nxt3 = __ldg(S.rec + min((first & ~31u) + 64 + lane, last));
+#endif
         for (unsigned base = first & ~31u; base <= last; base += 32) {
-            // ---- scan: ordered compaction of the boxes whose footprint overlaps the tile
+            // ---- scan: ordered compaction of the boxes whose footprint overlaps the tile (the next 3 chunks' records in flight)
+            const int4 rec = nxt;
+            const bool last_chunk = base + 32 > last;
+#if FI_SCAN_DEPTH >= 3
+            nxt = nxt2;
+            nxt2 = nxt3;
+            if (base + 96 <= last) nxt3 = __ldg(S.rec + min(base + 96 + lane, last));
+#else
+            if (!last_chunk) nxt = __ldg(S.rec + min(base + 32 + lane, last));
+#endif
             const unsigned r = base + lane;
-            bool hit = false;
-            if (r >= first && r <= last && S.box_ind[r] == b) {
-                const int4 bd = S.bounds[r];
-                hit = bd.x <= Y0 + kTY - 1 && bd.y >= Y0 && bd.z <= X0 + kTX - 1 && bd.w >= X0;
-            }
+            const int ymin = (short)(rec.x & 0xffff), ymax = (short)(rec.x >> 16);
+            const int xmin = (short)(rec.y & 0xffff), xmax = (short)(rec.y >> 16);
+            const bool hit = r >= first && r <= last && rec.z == b && ymin <= Y0 + TY - 1 && ymax >= Y0 && xmin <= X0 + TX - 1 && xmax >= X0;
             const unsigned hm = __ballot_sync(0xffffffffu, hit);
             if (hit) ws.list[nl + __popc(hm & lt)] = (int)r;
             nl += __popc(hm);
-            const bool last_chunk = base + 32 > last || base + 32 < base;
-            if (!(nl > kList - 32 || last_chunk)) continue;
             __syncwarp();
-            // ---- expand the hit boxes into queued samples
-            long long e_next = 0;
-            int grow_next = 0;
-            if (nl > 0) {
-                const int r0 = ws.list[0];
-                e_next = *reinterpret_cast<const long long *>(S.taps + (long)r0 * 32 + lane);
-                grow_next = S.src_row ? S.src_row[r0] : r0;
-            }
-            for (int k = 0; k < nl; ++k) {
-                const int rr = ws.list[k];
-                const long long e_cur = e_next;
-                const int grow = grow_next;
-                if (k + 1 < nl) {                                                  // prefetch the next box's taps
-                    const int rn = ws.list[k + 1];
-                    e_next = *reinterpret_cast<const long long *>(S.taps + (long)rn * 32 + lane);
-                    grow_next = S.src_row ? S.src_row[rn] : rn;
+            // ---- expand: a batch of up to 32 hit boxes, lane i <-> hit i
+            while (nl >= 32 || (last_chunk && nl > 0)) {
+                const int nb = min(nl, 32);
+                const bool mine = lane < nb;
+                const int rr = mine ? ws.list[lane] : 0;
+                float4 geom = make_float4(0.f, 0.f, 0.f, 0.f);
+                int4 hr = make_int4(0, 0, 0, 0);
+                int grow = 0;
+                if (mine) {
+                    geom = __ldg(S.geom + rr);
+                    hr = __ldg(S.rec + rr);
+                    grow = S.src_row ? __ldg(S.src_row + rr) : rr;
                 }
-                const int lohi = (int)(e_cur & 0xffffffffll);
-                const float frac = __int_as_float((int)(e_cur >> 32));
-                const int lo = (short)(lohi & 0xffff), hi = (short)(lohi >> 16);
-                const bool touch = lane < 16 ? ((lo >= Y0 && lo < Y0 + kTY) || (hi >= Y0 && hi < Y0 + kTY))
-                                             : ((lo >= X0 && lo < X0 + kTX) || (hi >= X0 && hi < X0 + kTX));
-                const unsigned bal = __ballot_sync(0xffffffffu, touch);
-                const unsigned ymask = bal & 0xffffu, xmask = bal >> 16;
-                if (ymask == 0 || xmask == 0) continue;
-                const int iy0 = __ffs(ymask) - 1, iy1 = 31 - __clz(ymask);
-                const int ix0 = __ffs(xmask) - 1, ix1 = 31 - __clz(xmask);
-                const int nx = ix1 - ix0 + 1, n = (iy1 - iy0 + 1) * nx;          // <= 256 samples of this box may touch the tile
-                const unsigned inv = (65536u + nx - 1) / nx;                       // s / nx == (s * inv) >> 16 for s < 256, nx <= 16
-                for (int c0 = 0; c0 < n; c0 += 32) {
-                    const int s = c0 + lane;
-                    const bool valid = s < n;
-                    const int ii = valid ? (int)((s * inv) >> 16) : 0;
-                    const int jj = valid ? s - ii * nx : 0;
-                    const int iy = iy0 + ii, ix = ix0 + jj;
-                    const int py = __shfl_sync(0xffffffffu, lohi, iy), px = __shfl_sync(0xffffffffu, lohi, 16 + ix);
-                    const float fy = __shfl_sync(0xffffffffu, frac, iy), fx = __shfl_sync(0xffffffffu, frac, 16 + ix);
-                    const int ylo = (short)(py & 0xffff), yhi = (short)(py >> 16);
-                    const int xlo = (short)(px & 0xffff), xhi = (short)(px >> 16);
-                    // a tap that coincides with its partner (integer sample position) carries weight 0: dropped
-                    const bool top = ylo >= Y0 && ylo < Y0 + kTY, bot = yhi >= Y0 && yhi < Y0 + kTY && yhi != ylo;
-                    const bool lef = xlo >= X0 && xlo < X0 + kTX, rig = xhi >= X0 && xhi < X0 + kTX && xhi != xlo;
-                    int f = (top && lef ? 1 : 0) | (top && rig ? 2 : 0) | (bot && lef ? 4 : 0) | (bot && rig ? 8 : 0);
-                    if (!valid) f = 0;
-                    const unsigned am = __ballot_sync(0xffffffffu, f != 0);
-                    if (f) {
-                        const int pos = qn + __popc(am & lt);
-                        const int tl = (ylo - Y0) * kTX + (xlo - X0) + 16;         // >= 16 - 9
-                        const unsigned row1 = (unsigned)((grow * ph + iy) * pw + ix);
-                        const unsigned row2 = (unsigned)((rr * ph + iy) * pw + ix);
-                        ws.q4[pos] = make_uint4(row1, row2, __float_as_uint(fy), __float_as_uint(fx));
-                        ws.qp[pos] = f | (tl << 4);
+                __syncwarp();
+                if (nl > 32) ws.list[lane] = ws.list[32 + lane];      // keep the overflow for the next batch
+                nl -= nb;
+                __syncwarp();
+                // crop rows / columns of MY box whose taps touch the tile (positions are monotone in k: contiguous ranges)
+                unsigned ymask = 0, xmask = 0;
+                for (int k = 0; k < ph; ++k) {
+                    const Tap tp = geom_tap(geom.x, geom.y, k, H);
+                    if ((tp.lo >= Y0 && tp.lo < Y0 + TY) || (tp.hi >= Y0 && tp.hi < Y0 + TY)) ymask |= 1u << k;
+                }
+                for (int k = 0; k < pw; ++k) {
+                    const Tap tp = geom_tap(geom.z, geom.w, k, W);
+                    if ((tp.lo >= X0 && tp.lo < X0 + TX) || (tp.hi >= X0 && tp.hi < X0 + TX)) xmask |= 1u << k;
+                }
+                const bool deg = (!EXACT) && hr.w != 0;
+                int iy0 = 0, ix0 = 0, nx = 1, cnt = 0;
+                if (mine && ymask && xmask) {
+                    iy0 = __ffs(ymask) - 1; ix0 = __ffs(xmask) - 1;
+                    nx = 32 - __clz(xmask) - ix0;
+                    cnt = deg ? 4 : (32 - __clz(ymask) - iy0) * nx;       // <= 256 samples of this box may touch the tile
+                }
+                const unsigned inv = (65536u + nx - 1) / nx;              // s / nx == (s * inv) >> 16 for s < 256, nx <= 16
+                const int rect = iy0 | (ix0 << 4) | (nx << 8) | (deg ? 1 << 16 : 0);
+                int incl = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += v;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                // ---- emit: lane l describes sample g0 + l of the batch's (box, crop row, crop column)-ordered stream
+                for (int g0 = 0; g0 < total;) {
+                    const int room = min(min(32, total - g0), kQ - qn);
+                    const int g = g0 + lane;
+                    int j = 0;
+#pragma unroll
+                    for (int st = 16; st >= 1; st >>= 1) {
+                        const int probe = __shfl_sync(0xffffffffu, incl, min(j + st - 1, 31));
+                        if (probe <= g) j += st;
                     }
-                    qn += __popc(am);
-                    if (qn > kQ - 32) {
-                        drain_any<EXACT>(ws, qn, S.grads + coff, S.grads2 ? S.grads2 + coff : nullptr, C, tile_lane, !dirty);
+                    j = min(j, 31);
+                    const int s = g - (__shfl_sync(0xffffffffu, incl, j) - __shfl_sync(0xffffffffu, cnt, j));
+                    const float gby = __shfl_sync(0xffffffffu, geom.x, j), gsy = __shfl_sync(0xffffffffu, geom.y, j);
+                    const float gbx = __shfl_sync(0xffffffffu, geom.z, j), gsx = __shfl_sync(0xffffffffu, geom.w, j);
+                    const int jrect = __shfl_sync(0xffffffffu, rect, j);
+                    const unsigned jinv = __shfl_sync(0xffffffffu, inv, j);
+                    const int jgrow = __shfl_sync(0xffffffffu, grow, j), jrr = __shfl_sync(0xffffffffu, rr, j);
+                    const int jry = __shfl_sync(0xffffffffu, hr.x, j), jrx = __shfl_sync(0xffffffffu, hr.y, j);
+                    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+                    float4 wts = make_float4(0.f, 0.f, 0.f, 0.f);
+                    unsigned pmask = 0;                                // pixels of the tile this sample adds to
+                    if (lane < room) {
+                        if (jrect & (1 << 16)) {
+                            // degenerate box: its (<= 4) corner sums come from the collapse kernel as unit-weight samples
+                            const int bymin = (short)(jry & 0xffff), bymax = (short)(jry >> 16), bxmin = (short)(jrx & 0xffff), bxmax = (short)(jrx >> 16);
+                            const int cy = (s & 2) ? bymax : bymin, cx = (s & 1) ? bxmax : bxmin;
+                            const bool use = !((s & 2) && bymax == bymin) && !((s & 1) && bxmax == bxmin) && cy >= Y0 && cy < Y0 + TY && cx >= X0 &&
+                                             cx < X0 + TX;
+                            const int px = (cy - Y0) * TX + (cx - X0);
+                            const int pk = use ? (1 | kCollapsed | (px * 512)) : kCollapsed;
+                            if (use) pmask = 1u << px;
+                            q = make_uint4((unsigned)(jrr * 4 + s), 0u, (unsigned)pk, 0u);
+                            wts = make_float4(1.f, 0.f, 0.f, 0.f);
+                        } else {
+                            const int jnx = (jrect >> 8) & 0xff;
+                            const int ii = (int)(((unsigned)s * jinv) >> 16);
+                            int jj = s - ii * jnx;
+                            if (FI_TILE_ILV && !EXACT) {               // even columns first, then odd ones: neighbours in the queue rarely share a pixel
+                                const int half = (jnx + 1) >> 1;
+                                jj = jj < half ? 2 * jj : 2 * (jj - half) + 1;
+                            }
+                            const int iy = (jrect & 15) + ii, ix = ((jrect >> 4) & 15) + jj;
+                            const Tap ty = geom_tap(gby, gsy, iy, H), tx = geom_tap(gbx, gsx, ix, W);
+                            // a tap that coincides with its partner (integer sample position) carries weight 0: dropped
+                            const bool top = ty.lo >= Y0 && ty.lo < Y0 + TY, bot = ty.hi >= Y0 && ty.hi < Y0 + TY && ty.hi != ty.lo;
+                            const bool lef = tx.lo >= X0 && tx.lo < X0 + TX, rig = tx.hi >= X0 && tx.hi < X0 + TX && tx.hi != tx.lo;
+                            const int f = (top && lef ? 1 : 0) | (top && rig ? 2 : 0) | (bot && lef ? 4 : 0) | (bot && rig ? 8 : 0);
+                            const int px = (ty.lo - Y0) * TX + (tx.lo - X0);                              // TL pixel; may be negative
+                            const int pk = f ? (f | (px * 512)) : 0;
+                            if (f & 1) pmask |= 1u << px;
+                            if (f & 2) pmask |= 1u << (px + 1);
+                            if (f & 4) pmask |= 1u << (px + TX);
+                            if (f & 8) pmask |= 1u << (px + TX + 1);
+                            q = make_uint4((unsigned)((jgrow * ph + iy) * pw + ix), (unsigned)((jrr * ph + iy) * pw + ix), (unsigned)pk, 0u);
+                            const float wy0 = __fsub_rn(1.f, ty.frac), wx0 = __fsub_rn(1.f, tx.frac);      // crop_and_resize.c:241-247
+                            wts = EXACT ? make_float4(wy0, ty.frac, wx0, tx.frac)
+                                        : make_float4(wy0 * wx0, wy0 * tx.frac, ty.frac * wx0, ty.frac * tx.frac);
+                        }
+                    }
+                    {
+                        unsigned before = __shfl_up_sync(0xffffffffu, pmask, 1);
+                        if (lane == 0) before = carry_mask;
+                        if (((qn + lane) & 1) && !(pmask & before)) q.z |= kIndep;
+                        carry_mask = __shfl_sync(0xffffffffu, pmask, room - 1);
+                    }
+                    if (lane < room) {
+                        ws.qa[qn + lane] = q;
+                        ws.qw[qn + lane] = wts;
+                    }
+                    qn += room;
+                    g0 += room;
+                    if (qn == kQ) {                                    // full queue: 64 samples per drain
+                        drain_any<EXACT, TY, TX>(ws.qa, ws.qw, qn, G1, G2, COLL, C, tile_lane, !dirty);
                         dirty = true;
                         qn = 0;
                     }
                 }
             }
-            nl = 0;
-            __syncwarp();
         }
         if (qn > 0) {                                   // set boundary: the queue holds rows of one set only
-            drain_any<EXACT>(ws, qn, S.grads + coff, S.grads2 ? S.grads2 + coff : nullptr, C, tile_lane, !dirty);
+            drain_any<EXACT, TY, TX>(ws.qa, ws.qw, qn, G1, G2, COLL, C, tile_lane, !dirty);
             dirty = true;
         }
     }
     // ---- store the tile (or zeros), once
     __syncwarp();
     float *dst0 = M.gimg + (((long)b * H + Y0) * (long)W + X0) * C + coff;
-#pragma unroll 8
-    for (int p = 0; p < kTP; ++p) {
-        const int yy = p / kTX, xx = p % kTX;
-        if (Y0 + yy < H && X0 + xx < W) {
-            float *dst = dst0 + ((long)yy * W + xx) * C;
-            float4 v = dirty ? *reinterpret_cast<const float4 *>(tile_lane + p * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (P.accumulate) v = add_rn4(*reinterpret_cast<const float4 *>(dst), v);
-            __stcs(reinterpret_cast<float4 *>(dst), v);
+    const long row_stride = (long)W * C;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (Y0 + TY <= H && X0 + TX <= W && !P.accumulate) {            // interior tile: straight-line stores
+#pragma unroll
+        for (int yy = 0; yy < TY; ++yy) {
+#pragma unroll
+            for (int xx = 0; xx < TX; ++xx) {
+                const float4 v = dirty ? *reinterpret_cast<const float4 *>(tile_lane + (yy * TX + xx) * 128) : zero4;
+                __stcs(reinterpret_cast<float4 *>(dst0 + yy * row_stride + xx * C), v);
+            }
+        }
+    } else {
+        for (int yy = 0; yy < TY && Y0 + yy < H; ++yy) {
+            for (int xx = 0; xx < TX && X0 + xx < W; ++xx) {
+                float *dst = dst0 + yy * row_stride + xx * C;
+                float4 v = dirty ? *reinterpret_cast<const float4 *>(tile_lane + (yy * TX + xx) * 128) : zero4;
+                if (P.accumulate) v = add_rn4(*reinterpret_cast<const float4 *>(dst), v);
+                __stcs(reinterpret_cast<float4 *>(dst), v);
+            }
         }
     }
 }
@@ -329,26 +600,75 @@ __global__ void __launch_bounds__(64, 6) bwd_smem_tile_kernel(const TParams P) {
 using namespace fi;
 using namespace fi::tile;
 
+// Grow-only scratch memory, one block per (device, stream): every use is ordered on that stream, so consecutive calls can
+// share it without synchronisation.  (cudaMallocAsync / cudaFreeAsync per call cost periodic multi-millisecond host stalls.)
+namespace {
+struct WsSlot { int dev; cudaStream_t stream; char *ptr; size_t cap; };
+WsSlot g_ws[32];
+int g_nws = 0;
+std::mutex g_ws_mu;
+
+char *workspace(size_t bytes, cudaStream_t stream) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(g_ws_mu);
+    WsSlot *slot = nullptr;
+    for (int i = 0; i < g_nws; ++i) if (g_ws[i].dev == dev && g_ws[i].stream == stream) slot = &g_ws[i];
+    if (slot && slot->cap >= bytes) return slot->ptr;
+    if (!slot) {
+        if (g_nws == 32) {                             // recycle the oldest entry
+            cudaStreamSynchronize(g_ws[0].stream);
+            cudaFree(g_ws[0].ptr);
+            for (int i = 1; i < g_nws; ++i) g_ws[i - 1] = g_ws[i];
+            --g_nws;
+        }
+        slot = &g_ws[g_nws++];
+        slot->dev = dev; slot->stream = stream; slot->ptr = nullptr; slot->cap = 0;
+    } else {
+        cudaStreamSynchronize(stream);                 // the old block may still be in use by enqueued work
+        cudaFree(slot->ptr);
+        slot->ptr = nullptr; slot->cap = 0;
+    }
+    const size_t want = bytes + bytes / 2 + (1 << 20);
+    cudaError_t e = cudaMalloc((void **)&slot->ptr, want);
+    if (e != cudaSuccess) {
+        slot->ptr = nullptr;
+        set_error(FI_ERR_CUDA, "crop backward: workspace (%zu B): %s", want, cudaGetErrorString(e));
+        return nullptr;
+    }
+    slot->cap = want;
+    return slot->ptr;
+}
+}  // namespace
+
 // Host side.  Returns FI_ERR_UNSUPPORTED (nothing touched) when the sets do not qualify so that the caller can use the
 // reduction kernels.  exact != 0: arithmetic and order of crop_and_resize.c:190-250 (bit-identical for one set per map).
 int fi_tile_backward(const fi_bwd_set *sets, int num_sets, int accumulate, int exact, cudaStream_t stream) {
     if (num_sets < 1 || num_sets > kMaxSets) return FI_ERR_UNSUPPORTED;
+    // tile shape: 4 rows x 8 pixels by default (a tile row is 8 KB contiguous in NHWC, C = 256); FI_TILE=4x4 / 2x8 halve the
+    // shared memory per warp (more resident warps, more neighbour re-reads) -- kept for measurements
+    int TYs = 4, TXs = 8;
+    {
+        const char *shape = getenv("FI_TILE");
+        if (shape && shape[0] == '4' && shape[2] == '4') { TYs = 4; TXs = 4; }
+        if (shape && shape[0] == '2' && shape[2] == '8') { TYs = 2; TXs = 8; }
+    }
     TParams P;
-    P.nsets = 0; P.nmaps = 0; P.accumulate = accumulate ? 1 : 0;
+    P.nsets = 0; P.nmaps = 0; P.accumulate = accumulate ? 1 : 0; P.collapse = exact ? 0 : 1;
     // group the sets by map, maps in order of first appearance
     for (int i = 0; i < num_sets; ++i) {
         const fi_bwd_set &h = sets[i];
         if (h.depth % 128 != 0 || h.image_height > 32767 || h.image_width > 32767 || h.crop_height > kMaxCrop || h.crop_width > kMaxCrop ||
             h.crop_height < 1 || h.crop_width < 1) return FI_ERR_UNSUPPORTED;
-        if (((uintptr_t)h.grads_image % 16) || ((uintptr_t)h.grads % 16) || ((uintptr_t)h.grads2 % 16)) return FI_ERR_UNSUPPORTED;
-        if ((long)h.num_boxes * h.crop_height * h.crop_width >= (1L << 31)) return FI_ERR_UNSUPPORTED;
+        if (((uintptr_t)h.grads_image % 16) || ((uintptr_t)h.grads % 16) || ((uintptr_t)h.grads2 % 16) || ((uintptr_t)h.boxes % 16)) return FI_ERR_UNSUPPORTED;
+        if ((long)h.num_boxes * h.crop_height * h.crop_width >= (1L << 29) || h.num_boxes >= (1 << 24)) return FI_ERR_UNSUPPORTED;
         bool seen = false;
         for (int q = 0; q < i; ++q) seen = seen || (sets[q].grads_image == h.grads_image);
         if (seen) continue;
         if (P.nmaps == kMaxMaps) return FI_ERR_UNSUPPORTED;
         TMap &M = P.m[P.nmaps];
         M.gimg = h.grads_image; M.B = h.batch; M.H = h.image_height; M.W = h.image_width; M.C = h.depth;
-        M.tiles_x = ceil_div(M.W, kTX); M.tiles_y = ceil_div(M.H, kTY);
+        M.tiles_x = ceil_div(M.W, TXs); M.tiles_y = ceil_div(M.H, TYs);
         M.set_begin = P.nsets;
         for (int q = i; q < num_sets; ++q) {
             const fi_bwd_set &g = sets[q];
@@ -358,14 +678,14 @@ int fi_tile_backward(const fi_bwd_set *sets, int num_sets, int accumulate, int e
                 return FI_ERR_INVALID;
             }
             TSet &S = P.s[P.nsets++];
-            S.grads = g.grads; S.grads2 = g.grads2; S.boxes = g.boxes; S.box_ind = g.box_ind; S.src_row = g.src_row;
+            S.grads = g.grads; S.grads2 = g.grads2; S.boxes = reinterpret_cast<const float4 *>(g.boxes); S.box_ind = g.box_ind; S.src_row = g.src_row;
             S.R = g.num_boxes; S.ph = g.crop_height; S.pw = g.crop_width; S.map = P.nmaps;
         }
         M.set_end = P.nsets;
         ++P.nmaps;
     }
     long tiles = 0;
-    int max_slabs = 1, max_R = 0;
+    int max_slabs = 1, max_R = 0, total_R = 0;
     for (int m = 0; m < P.nmaps; ++m) {
         TMap &M = P.m[m];
         if (tiles + (long)M.B * M.tiles_x * M.tiles_y >= (1L << 31)) return FI_ERR_UNSUPPORTED;
@@ -373,49 +693,66 @@ int fi_tile_backward(const fi_bwd_set *sets, int num_sets, int accumulate, int e
         tiles += (long)M.B * M.tiles_x * M.tiles_y;
         max_slabs = max_slabs > M.C / 128 ? max_slabs : M.C / 128;
     }
-    // workspace: [ranges of all sets][bounds + taps per set]
-    size_t range_bytes = 0, bytes = 0;
-    for (int i = 0; i < P.nsets; ++i) range_bytes += ((size_t)P.m[P.s[i].map].B * 2 * sizeof(unsigned) + 15) / 16 * 16;
-    bytes = range_bytes;
+    // workspace: [ranges of all sets | degenerate counter + list] (one memset region each), then records and collapse rows
+    auto up16 = [](size_t v) { return (v + 15) / 16 * 16; };
+    size_t range_bytes = 0;
     for (int i = 0; i < P.nsets; ++i) {
-        bytes += (size_t)P.s[i].R * (sizeof(int4) + 32 * sizeof(TapEntry));
+        range_bytes += up16((size_t)P.m[P.s[i].map].B * 2 * sizeof(unsigned));
         max_R = max_R > P.s[i].R ? max_R : P.s[i].R;
+        total_R += P.s[i].R;
     }
-    static bool pool_ready = false;      // keep freed workspace cached in the stream-ordered pool across synchronisations
-    if (!pool_ready) {
-        int dev = 0;
-        cudaMemPool_t pool;
-        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            unsigned long long keep = ~0ULL;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-        pool_ready = true;
+    const size_t list_bytes = up16((size_t)(1 + total_R) * sizeof(int));
+    size_t bytes = range_bytes + list_bytes;
+    for (int i = 0; i < P.nsets; ++i) {
+        bytes += 2 * up16((size_t)P.s[i].R * sizeof(int4));
+        if (P.collapse) bytes += (size_t)P.s[i].R * 4 * P.m[P.s[i].map].C * sizeof(float);    // only degenerate rows are ever touched
     }
-    char *ws = nullptr;
-    cudaError_t e = cudaMallocAsync((void **)&ws, bytes, stream);
-    if (e != cudaSuccess) { set_error(FI_ERR_CUDA, "crop backward: workspace (%zu B): %s", bytes, cudaGetErrorString(e)); return FI_ERR_CUDA; }
+    char *ws = workspace(bytes, stream);
+    if (!ws) return FI_ERR_CUDA;
+    cudaError_t e;
     e = cudaMemsetAsync(ws, 0xFF, range_bytes, stream);
-    if (e != cudaSuccess) { cudaFreeAsync(ws, stream); set_error(FI_ERR_CUDA, "crop backward: memset: %s", cudaGetErrorString(e)); return FI_ERR_CUDA; }
+    if (e == cudaSuccess) e = cudaMemsetAsync(ws + range_bytes, 0, sizeof(int), stream);
+    if (e != cudaSuccess) { set_error(FI_ERR_CUDA, "crop backward: memset: %s", cudaGetErrorString(e)); return FI_ERR_CUDA; }
     char *p = ws;
     for (int i = 0; i < P.nsets; ++i) {
         P.s[i].range = reinterpret_cast<unsigned *>(p);
-        p += ((size_t)P.m[P.s[i].map].B * 2 * sizeof(unsigned) + 15) / 16 * 16;
+        p += up16((size_t)P.m[P.s[i].map].B * 2 * sizeof(unsigned));
+    }
+    P.deg_list = reinterpret_cast<int *>(p);
+    p += list_bytes;
+    for (int i = 0; i < P.nsets; ++i) {
+        P.s[i].rec = reinterpret_cast<int4 *>(p);
+        p += up16((size_t)P.s[i].R * sizeof(int4));
+        P.s[i].geom = reinterpret_cast<float4 *>(p);
+        p += up16((size_t)P.s[i].R * sizeof(float4));
     }
     for (int i = 0; i < P.nsets; ++i) {
-        P.s[i].bounds = reinterpret_cast<int4 *>(p); p += (size_t)P.s[i].R * sizeof(int4);
-        P.s[i].taps = reinterpret_cast<TapEntry *>(p); p += (size_t)P.s[i].R * 32 * sizeof(TapEntry);
+        P.s[i].coll = reinterpret_cast<float *>(p);
+        if (P.collapse) p += (size_t)P.s[i].R * 4 * P.m[P.s[i].map].C * sizeof(float);
     }
     int rc = ok();
     if (max_R > 0) {
-        tile_prep_kernel<<<dim3(ceil_div(max_R, 8), P.nsets), 256, 0, stream>>>(P);
+        tile_prep_kernel<<<dim3(ceil_div(max_R, 128), P.nsets), 128, 0, stream>>>(P);
         rc = check_launch("crop backward[prep]");
+        if (rc == FI_OK && P.collapse) {
+            const int grid = total_R < 4 * kNumSMs ? total_R : 4 * kNumSMs;
+            tile_collapse_kernel<<<grid, 256, 0, stream>>>(P);
+            rc = check_launch("crop backward[collapse]");
+        }
     }
     if (rc == FI_OK && tiles > 0) {
         const dim3 grid((unsigned)tiles, ceil_div(max_slabs, 2));
-        if (exact) bwd_smem_tile_kernel<true><<<grid, 64, 0, stream>>>(P);
-        else bwd_smem_tile_kernel<false><<<grid, 64, 0, stream>>>(P);
+        if (TXs == 8 && TYs == 4) {
+            if (exact) bwd_smem_tile_kernel<true, 4, 8, FI_TILE_MINB><<<grid, 64, 0, stream>>>(P);
+            else bwd_smem_tile_kernel<false, 4, 8, FI_TILE_MINB><<<grid, 64, 0, stream>>>(P);
+        } else if (TXs == 4) {
+            if (exact) bwd_smem_tile_kernel<true, 4, 4, 10><<<grid, 64, 0, stream>>>(P);
+            else bwd_smem_tile_kernel<false, 4, 4, 10><<<grid, 64, 0, stream>>>(P);
+        } else {
+            if (exact) bwd_smem_tile_kernel<true, 2, 8, 10><<<grid, 64, 0, stream>>>(P);
+            else bwd_smem_tile_kernel<false, 2, 8, 10><<<grid, 64, 0, stream>>>(P);
+        }
         rc = check_launch("crop backward[tile]");
     }
-    cudaFreeAsync(ws, stream);
     return rc;
 }
