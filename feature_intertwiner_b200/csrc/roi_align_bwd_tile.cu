@@ -75,10 +75,20 @@ struct TMap {
     float *gimg;
     int B, H, W, C, tiles_x, tiles_y, first_tile, set_begin, set_end;
 };
+struct BinWs {                         // per-tile sample lists of the two-kernel form (enumerate -> accumulate)
+    int *tile_head;                    // [tiles] first chunk of the tile's list
+    int *tile_n;                       // [tiles] entries in the list (a multiple of 8)
+    int *chunk_next;                   // [pool]  chunk -> next chunk of the same tile
+    uint2 *qa;                         // [pool * 64] (gradient row, pk2)
+    float4 *qw;                        // [pool * 64] tap weights
+    int *cursor;                       // [1] chunks handed out
+    int pool, total_tiles;
+};
 struct TParams {
     TSet s[kMaxSets];
     TMap m[kMaxMaps];
     int *deg_list;                     // [0] = count, then (set << 24 | box) entries
+    BinWs bin;
     int nsets, nmaps, accumulate, collapse;
 };
 
@@ -594,6 +604,354 @@ __global__ void __launch_bounds__(64, MINB) bwd_smem_tile_kernel(const TParams P
     }
 }
 
+
+// =====================================================================================================================
+// Two-kernel form (default).  The single kernel above exposes ~12 dependent memory round trips per tile (ranges, box
+// records chunk by chunk, box geometry, first gradient loads, ... per crop set) while only 12 warps fit next to their
+// 16 KB accumulators: ncu shows 16 % occupancy, 0.34 IPC per scheduler, every stall a scoreboard wait.  Split in two:
+//   bin_enumerate_kernel   one warp per TILE (not per slab), no accumulator, ~2 KB shared memory per warp -> many resident
+//                          warps hide those round trips; scan and expansion as above, but the described samples go to a
+//                          per-tile list in global memory (64-entry chunks handed out by one atomic, chained per tile);
+//   bin_accumulate_kernel  one warp per (tile, slab) streams its list: chunk -> shared memory, gradient rows requested
+//                          into L2 a window ahead, 8 register loads in flight, shared-memory adds, one store of the tile.
+// Two-source sets (mask head + critic gradient of the same crop) queue TWO entries per sample: the first only loads
+// (kDefer2) and is added to the second's gradient before the taps are applied -- (g1 + g2) first, like autograd's
+// accumulation in the reference.  Every set's segment is padded to a multiple of 8 entries so pairs never straddle a group.
+// pk2: tap flags (bits 0-3), kDefer2 (bit 4), source index 3 * set + {grads, grads2, collapse rows} (bits 5-10),
+//      TL pixel index inside the tile, signed (bits 11..).
+constexpr int kDefer2 = 1 << 4;
+constexpr int kChunk = 64;
+
+struct __align__(16) EnumSmem {
+    float4 qw[kChunk];
+    uint2 qa[kChunk];
+    int list[64];
+};
+
+// 128 threads: warp w of block b owns tile 4 * b + w
+template <bool EXACT, int TY, int TX>
+__global__ void __launch_bounds__(128) bin_enumerate_kernel(const TParams P) {
+    __shared__ EnumSmem smem[4];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int tile_id = blockIdx.x * 4 + w;
+    if (tile_id >= P.bin.total_tiles) return;          // warps never synchronise with each other
+    int t = tile_id, mi = 0;
+    while (mi + 1 < P.nmaps && t >= P.m[mi + 1].first_tile) ++mi;
+    const TMap &M = P.m[mi];
+    const int H = M.H, W = M.W;
+    t -= M.first_tile;
+    const int tiles_x = ceil_div(W, TX), tiles_y = ceil_div(H, TY);
+    const int per_img = tiles_x * tiles_y;
+    const int b = t / per_img;
+    t -= b * per_img;
+    const int tyi = t / tiles_x, txi = t - tyi * tiles_x;
+    const int X0 = txi * TX, Y0 = tyi * TY;
+    EnumSmem &ws = smem[w];
+    const unsigned lt = (1u << lane) - 1u;
+    int qn = 0, qtot = 0, prev_chunk = -1;
+    unsigned last_row = 0;
+    int last_src = 0;
+
+    auto flush = [&]() {                                // hand the queued entries (<= 64) to the tile's list
+        int c = 0;
+        if (lane == 0) {
+            c = atomicAdd(P.bin.cursor, 1);
+            if (c < P.bin.pool) {
+                if (prev_chunk < 0) P.bin.tile_head[tile_id] = c;
+                else P.bin.chunk_next[prev_chunk] = c;
+            }
+        }
+        c = __shfl_sync(0xffffffffu, c, 0);
+        __syncwarp();
+        if (c < P.bin.pool) {                           // cannot fail: the pool is sized for 4 tiles per sample
+            P.bin.qa[(size_t)c * kChunk + lane] = ws.qa[lane];
+            P.bin.qa[(size_t)c * kChunk + 32 + lane] = ws.qa[32 + lane];
+            P.bin.qw[(size_t)c * kChunk + lane] = ws.qw[lane];
+            P.bin.qw[(size_t)c * kChunk + 32 + lane] = ws.qw[32 + lane];
+        }
+        prev_chunk = c;
+        qn = 0;
+        __syncwarp();
+    };
+
+    auto pad_entries = [&](int pad) {                   // tap-less entries re-reading the last row (a valid address); pad <= 7
+        __syncwarp();
+        if (lane < pad) {                               // qn is even / a multiple of 8 away from 64 here: the pad always fits
+            ws.qa[qn + lane] = make_uint2(last_row, (unsigned)last_src);
+            ws.qw[qn + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        qn += pad;
+        qtot += pad;
+        __syncwarp();
+        if (qn == kChunk) flush();
+    };
+
+    for (int si = M.set_begin; si < M.set_end; ++si) {
+        const TSet &S = P.s[si];
+        const unsigned first = S.range[2 * b], last = ~S.range[2 * b + 1];
+        if (first > last) continue;                    // no box of this set lives in image b
+        const int ph = S.ph, pw = S.pw;
+        const bool dual = S.grads2 != nullptr;
+        int nl = 0;
+        int4 nxt = __ldg(S.rec + min((first & ~31u) + lane, last));
+        for (unsigned base = first & ~31u; base <= last; base += 32) {
+            // ---- scan: ordered compaction of the boxes whose footprint overlaps the tile (next chunk's records in flight)
+            const int4 rec = nxt;
+            const bool last_chunk = base + 32 > last;
+            if (!last_chunk) nxt = __ldg(S.rec + min(base + 32 + lane, last));
+            const unsigned r = base + lane;
+            const int ymin = (short)(rec.x & 0xffff), ymax = (short)(rec.x >> 16);
+            const int xmin = (short)(rec.y & 0xffff), xmax = (short)(rec.y >> 16);
+            const bool hit = r >= first && r <= last && rec.z == b && ymin <= Y0 + TY - 1 && ymax >= Y0 && xmin <= X0 + TX - 1 && xmax >= X0;
+            const unsigned hm = __ballot_sync(0xffffffffu, hit);
+            if (hit) ws.list[nl + __popc(hm & lt)] = (int)r;
+            nl += __popc(hm);
+            __syncwarp();
+            // ---- expand: a batch of up to 32 hit boxes, lane i <-> hit i
+            while (nl >= 32 || (last_chunk && nl > 0)) {
+                const int nb = min(nl, 32);
+                const bool mine = lane < nb;
+                const int rr = mine ? ws.list[lane] : 0;
+                float4 geom = make_float4(0.f, 0.f, 0.f, 0.f);
+                int4 hr = make_int4(0, 0, 0, 0);
+                int grow = 0;
+                if (mine) {
+                    geom = __ldg(S.geom + rr);
+                    hr = __ldg(S.rec + rr);
+                    grow = S.src_row ? __ldg(S.src_row + rr) : rr;
+                }
+                __syncwarp();
+                if (nl > 32) ws.list[lane] = ws.list[32 + lane];      // keep the overflow for the next batch
+                nl -= nb;
+                __syncwarp();
+                // crop rows / columns of MY box whose taps touch the tile (positions are monotone in k: contiguous ranges)
+                unsigned ymask = 0, xmask = 0;
+                for (int k = 0; k < ph; ++k) {
+                    const Tap tp = geom_tap(geom.x, geom.y, k, H);
+                    if ((tp.lo >= Y0 && tp.lo < Y0 + TY) || (tp.hi >= Y0 && tp.hi < Y0 + TY)) ymask |= 1u << k;
+                }
+                for (int k = 0; k < pw; ++k) {
+                    const Tap tp = geom_tap(geom.z, geom.w, k, W);
+                    if ((tp.lo >= X0 && tp.lo < X0 + TX) || (tp.hi >= X0 && tp.hi < X0 + TX)) xmask |= 1u << k;
+                }
+                const bool deg = (!EXACT) && hr.w != 0;
+                int iy0 = 0, ix0 = 0, nx = 1, cnt = 0;
+                if (mine && ymask && xmask) {
+                    iy0 = __ffs(ymask) - 1; ix0 = __ffs(xmask) - 1;
+                    nx = 32 - __clz(xmask) - ix0;
+                    cnt = deg ? 4 : (32 - __clz(ymask) - iy0) * nx * (dual ? 2 : 1);      // <= 512 entries
+                }
+                const unsigned inv = (65536u + nx - 1) / nx;              // s / nx == (s * inv) >> 16 for s < 256, nx <= 16
+                const int rect = iy0 | (ix0 << 4) | (nx << 8) | (deg ? 1 << 16 : 0);
+                int incl = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += v;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                // ---- emit: lane l describes entry g0 + l of the batch's (box, crop row, crop column)-ordered stream
+                for (int g0 = 0; g0 < total;) {
+                    const int room = min(min(32, total - g0), kChunk - qn);
+                    const int g = g0 + lane;
+                    int j = 0;
+#pragma unroll
+                    for (int st = 16; st >= 1; st >>= 1) {
+                        const int probe = __shfl_sync(0xffffffffu, incl, min(j + st - 1, 31));
+                        if (probe <= g) j += st;
+                    }
+                    j = min(j, 31);
+                    const int s = g - (__shfl_sync(0xffffffffu, incl, j) - __shfl_sync(0xffffffffu, cnt, j));
+                    const float gby = __shfl_sync(0xffffffffu, geom.x, j), gsy = __shfl_sync(0xffffffffu, geom.y, j);
+                    const float gbx = __shfl_sync(0xffffffffu, geom.z, j), gsx = __shfl_sync(0xffffffffu, geom.w, j);
+                    const int jrect = __shfl_sync(0xffffffffu, rect, j);
+                    const unsigned jinv = __shfl_sync(0xffffffffu, inv, j);
+                    const int jgrow = __shfl_sync(0xffffffffu, grow, j), jrr = __shfl_sync(0xffffffffu, rr, j);
+                    const int jry = __shfl_sync(0xffffffffu, hr.x, j), jrx = __shfl_sync(0xffffffffu, hr.y, j);
+                    uint2 q = make_uint2(0u, 0u);
+                    float4 wts = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (lane < room) {
+                        if (jrect & (1 << 16)) {
+                            // degenerate box: its (<= 4) corner sums come from the collapse kernel as unit-weight samples
+                            const int bymin = (short)(jry & 0xffff), bymax = (short)(jry >> 16), bxmin = (short)(jrx & 0xffff), bxmax = (short)(jrx >> 16);
+                            const int cy = (s & 2) ? bymax : bymin, cx = (s & 1) ? bxmax : bxmin;
+                            const bool use = !((s & 2) && bymax == bymin) && !((s & 1) && bxmax == bxmin) && cy >= Y0 && cy < Y0 + TY && cx >= X0 &&
+                                             cx < X0 + TX;
+                            const int px = use ? (cy - Y0) * TX + (cx - X0) : 0;
+                            q = make_uint2((unsigned)(jrr * 4 + s), (unsigned)((use ? 1 : 0) | ((3 * si + 2) << 5) | (px * 2048)));
+                            wts = EXACT ? make_float4(1.f, 0.f, 1.f, 0.f) : make_float4(1.f, 0.f, 0.f, 0.f);
+                        } else {
+                            const int smp = dual ? (s >> 1) : s;
+                            const bool defer = dual && !(s & 1);           // first of the pair: the scattered gradient, load only
+                            const int jnx = (jrect >> 8) & 0xff;
+                            const int ii = (int)(((unsigned)smp * jinv) >> 16);
+                            const int iy = (jrect & 15) + ii, ix = ((jrect >> 4) & 15) + (smp - ii * jnx);
+                            if (defer) {
+                                q = make_uint2((unsigned)((jgrow * ph + iy) * pw + ix), (unsigned)(kDefer2 | ((3 * si) << 5)));
+                            } else {
+                                const Tap ty = geom_tap(gby, gsy, iy, H), tx = geom_tap(gbx, gsx, ix, W);
+                                // a tap that coincides with its partner (integer sample position) carries weight 0: dropped
+                                const bool top = ty.lo >= Y0 && ty.lo < Y0 + TY, bot = ty.hi >= Y0 && ty.hi < Y0 + TY && ty.hi != ty.lo;
+                                const bool lef = tx.lo >= X0 && tx.lo < X0 + TX, rig = tx.hi >= X0 && tx.hi < X0 + TX && tx.hi != tx.lo;
+                                const int f = (top && lef ? 1 : 0) | (top && rig ? 2 : 0) | (bot && lef ? 4 : 0) | (bot && rig ? 8 : 0);
+                                const int px = f ? (ty.lo - Y0) * TX + (tx.lo - X0) : 0;                  // TL pixel; may be negative
+                                const unsigned row = dual ? (unsigned)((jrr * ph + iy) * pw + ix) : (unsigned)((jgrow * ph + iy) * pw + ix);
+                                q = make_uint2(row, (unsigned)(f | ((3 * si + (dual ? 1 : 0)) << 5) | (px * 2048)));
+                                const float wy0 = __fsub_rn(1.f, ty.frac), wx0 = __fsub_rn(1.f, tx.frac);  // crop_and_resize.c:241-247
+                                wts = EXACT ? make_float4(wy0, ty.frac, wx0, tx.frac)
+                                            : make_float4(wy0 * wx0, wy0 * tx.frac, ty.frac * wx0, ty.frac * tx.frac);
+                            }
+                        }
+                        ws.qa[qn + lane] = q;
+                        ws.qw[qn + lane] = wts;
+                    }
+                    last_row = __shfl_sync(0xffffffffu, q.x, room - 1);
+                    last_src = __shfl_sync(0xffffffffu, (int)q.y, room - 1) & (63 << 5);
+                    qn += room;
+                    qtot += room;
+                    g0 += room;
+                    if (qn == kChunk) flush();
+                }
+            }
+        }
+        // ---- pairs of a two-source set must start on an even slot: pad the set's segment to an even length
+        if (qtot & 1) pad_entries(1);
+    }
+    if (qtot & 7) pad_entries(8 - (qtot & 7));          // whole groups of 8 per tile
+    __syncwarp();
+    if (qn > 0) flush();
+    if (lane == 0) P.bin.tile_n[tile_id] = qtot;
+}
+
+// grid (total tiles, ceil(slabs / 2)), 64 threads: warp = (tile, 128-channel slab)
+template <bool EXACT, int TY, int TX, int U, int MINB>
+__global__ void __launch_bounds__(64, MINB) bin_accumulate_kernel(const TParams P) {
+    // separate objects on purpose: the compiler then knows that the (runtime-offset) tile stores cannot alias the queue, and
+    // hoists the queue reads of a whole group above the read-modify-write chain of the taps
+    __shared__ __align__(16) float tile_s[2][TY * TX * 128];
+    __shared__ __align__(16) float4 qw_s[2][kChunk];
+    __shared__ __align__(16) uint2 qa_s[2][kChunk];
+    __shared__ const float *srcs[3 * kMaxSets];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x < 3 * kMaxSets) {
+        const TSet &S = P.s[min((int)threadIdx.x / 3, P.nsets - 1)];
+        const int which = threadIdx.x % 3;
+        srcs[threadIdx.x] = which == 0 ? S.grads : which == 1 ? S.grads2 : S.coll;
+    }
+    __syncthreads();                                   // the only CTA-wide synchronisation
+    const int tile_id = blockIdx.x;
+    int t = tile_id, mi = 0;
+    while (mi + 1 < P.nmaps && t >= P.m[mi + 1].first_tile) ++mi;
+    const TMap &M = P.m[mi];
+    const int H = M.H, W = M.W, C = M.C;
+    const int slab = blockIdx.y * 2 + w;
+    if (slab * 128 >= C) return;
+    t -= M.first_tile;
+    const int tiles_x = ceil_div(W, TX), tiles_y = ceil_div(H, TY);
+    const int per_img = tiles_x * tiles_y;
+    const int b = t / per_img;
+    t -= b * per_img;
+    const int tyi = t / tiles_x, txi = t - tyi * tiles_x;
+    const int X0 = txi * TX, Y0 = tyi * TY;
+    const int coff = slab * 128 + lane * 4;
+    float *__restrict__ tile_lane = tile_s[w] + lane * 4;
+    float4 *__restrict__ qw = qw_s[w];
+    uint2 *__restrict__ qa = qa_s[w];
+    const int n = P.bin.tile_n[tile_id];
+    int c = n > 0 ? P.bin.tile_head[tile_id] : 0;
+    const bool dirty = n > 0;
+    if (dirty) {
+        // first chunk on its way while the accumulator is cleared
+        uint2 ea0 = P.bin.qa[(size_t)c * kChunk + lane], ea1 = P.bin.qa[(size_t)c * kChunk + 32 + lane];
+        float4 ew0 = P.bin.qw[(size_t)c * kChunk + lane], ew1 = P.bin.qw[(size_t)c * kChunk + 32 + lane];
+        int cn = n > kChunk ? P.bin.chunk_next[c] : 0;
+#pragma unroll
+        for (int p = 0; p < TY * TX; ++p) *reinterpret_cast<float4 *>(tile_lane + p * 128) = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int e0 = 0; e0 < n; e0 += kChunk) {
+            const int cnt = min(kChunk, n - e0);       // a multiple of 8
+            __syncwarp();
+            qa[lane] = ea0; qa[32 + lane] = ea1;
+            qw[lane] = ew0; qw[32 + lane] = ew1;
+            __syncwarp();
+            if (e0 + kChunk < n) {                      // next chunk's entries in flight while this one is consumed
+                c = cn;
+                ea0 = P.bin.qa[(size_t)c * kChunk + lane]; ea1 = P.bin.qa[(size_t)c * kChunk + 32 + lane];
+                ew0 = P.bin.qw[(size_t)c * kChunk + lane]; ew1 = P.bin.qw[(size_t)c * kChunk + 32 + lane];
+                if (e0 + 2 * kChunk < n) cn = P.bin.chunk_next[c];
+            }
+            // ---- consume the chunk: groups of 8, loads of group i+1 in flight while group i is added
+            float4 a0[U], a1[U];
+            auto prefetch8 = [&](int q0) {              // lane -> (entry q0 + lane / 4, 128-byte line lane % 4 of the slab's 512-byte run)
+                const int idx = q0 + (lane >> 2);
+                if (idx < cnt) {
+                    const uint2 e = qa[idx];
+                    prefetch_l2(srcs[(e.y >> 5) & 63] + slab * 128 + (lane & 3) * 32 + (size_t)e.x * C);
+                }
+            };
+            auto load = [&](int q0, float4(&a)[U]) {
+#pragma unroll
+                for (int k = 0; k < U; ++k) {
+                    const uint2 e = qa[q0 + k];
+                    a[k] = __ldcg(reinterpret_cast<const float4 *>(srcs[(e.y >> 5) & 63] + coff + (size_t)e.x * C));
+                }
+            };
+            auto process = [&](int q0, float4(&a)[U]) {
+#pragma unroll
+                for (int k = 0; k < U; ++k) {
+                    const int pk = (int)qa[q0 + k].y;
+                    if (pk & 15) {                                                       // tap-less entries (first of a pair, padding) only load
+                        const float4 wts = qw[q0 + k];
+                        float4 g = a[k];
+                        if (k & 1) {
+                            if (qa[q0 + k - 1].y & kDefer2) g = add_rn4(g, a[k - 1]);    // (g1 + g2) first
+                        }
+                        const int pk1 = (pk & 15) | ((pk >> 11) << 9);                   // flags | byte offset of the TL pixel
+                        apply_sample<EXACT, TX>(tile_lane, pk1, wts, g);
+                    }
+                }
+            };
+#pragma unroll
+            for (int q0 = U; q0 < U + 32; q0 += 8) prefetch8(q0);
+            load(0, a0);
+            for (int q0 = 0; q0 < cnt; q0 += 2 * U) {             // cnt is a multiple of 8, U is 4 or 8
+                const bool more = q0 + U < cnt;
+                prefetch8(q0 + U + 32);
+                if (more) load(q0 + U, a1);
+                process(q0, a0);
+                if (more) {
+                    if (U == 8) prefetch8(q0 + U + 40);
+                    if (q0 + 2 * U < cnt) load(q0 + 2 * U, a0);
+                    process(q0 + U, a1);
+                }
+            }
+        }
+    }
+    // ---- store the tile (or zeros), once
+    __syncwarp();
+    float *dst0 = M.gimg + (((long)b * H + Y0) * (long)W + X0) * C + coff;
+    const long row_stride = (long)W * C;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (Y0 + TY <= H && X0 + TX <= W && !P.accumulate) {            // interior tile: straight-line stores
+#pragma unroll
+        for (int yy = 0; yy < TY; ++yy) {
+#pragma unroll
+            for (int xx = 0; xx < TX; ++xx) {
+                const float4 v = dirty ? *reinterpret_cast<const float4 *>(tile_lane + (yy * TX + xx) * 128) : zero4;
+                __stcs(reinterpret_cast<float4 *>(dst0 + yy * row_stride + xx * C), v);
+            }
+        }
+    } else {
+        for (int yy = 0; yy < TY && Y0 + yy < H; ++yy) {
+            for (int xx = 0; xx < TX && X0 + xx < W; ++xx) {
+                float *dst = dst0 + yy * row_stride + xx * C;
+                float4 v = dirty ? *reinterpret_cast<const float4 *>(tile_lane + (yy * TX + xx) * 128) : zero4;
+                if (P.accumulate) v = add_rn4(*reinterpret_cast<const float4 *>(dst), v);
+                __stcs(reinterpret_cast<float4 *>(dst), v);
+            }
+        }
+    }
+}
+
 }  // namespace tile
 }  // namespace fi
 
@@ -701,17 +1059,30 @@ int fi_tile_backward(const fi_bwd_set *sets, int num_sets, int accumulate, int e
         max_R = max_R > P.s[i].R ? max_R : P.s[i].R;
         total_R += P.s[i].R;
     }
-    const size_t list_bytes = up16((size_t)(1 + total_R) * sizeof(int));
+    const size_t list_bytes = up16((size_t)(1 + total_R) * sizeof(int)) + 16;      // [degenerate count + list | chunk cursor]
+    // two-kernel form (default): per-tile sample lists in 64-entry chunks.  A sample's taps lie in at most 2x2 tiles, two-source
+    // sets queue two entries per sample, every tile may leave one chunk partly filled.  FI_BWD_TILE=fused: single kernel.
+    bool binned = true;
+    {
+        const char *form = getenv("FI_BWD_TILE");
+        if (form && form[0] == 'f') binned = false;
+    }
+    long entries_bound = 0;
+    for (int i = 0; i < P.nsets; ++i) entries_bound += 4L * P.s[i].R * P.s[i].ph * P.s[i].pw * (P.s[i].grads2 ? 2 : 1) + 8L * 4 * P.s[i].R;
+    const long pool = entries_bound / kChunk + tiles + 8;
+    if (pool >= (1L << 31) / kChunk) binned = false;
     size_t bytes = range_bytes + list_bytes;
     for (int i = 0; i < P.nsets; ++i) {
         bytes += 2 * up16((size_t)P.s[i].R * sizeof(int4));
         if (P.collapse) bytes += (size_t)P.s[i].R * 4 * P.m[P.s[i].map].C * sizeof(float);    // only degenerate rows are ever touched
     }
+    if (binned) bytes += 2 * up16((size_t)tiles * sizeof(int)) + up16((size_t)pool * sizeof(int)) + (size_t)pool * kChunk * (sizeof(uint2) + sizeof(float4));
     char *ws = workspace(bytes, stream);
     if (!ws) return FI_ERR_CUDA;
     cudaError_t e;
     e = cudaMemsetAsync(ws, 0xFF, range_bytes, stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(ws + range_bytes, 0, sizeof(int), stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ws + range_bytes + list_bytes - 16, 0, sizeof(int), stream);
     if (e != cudaSuccess) { set_error(FI_ERR_CUDA, "crop backward: memset: %s", cudaGetErrorString(e)); return FI_ERR_CUDA; }
     char *p = ws;
     for (int i = 0; i < P.nsets; ++i) {
@@ -719,6 +1090,7 @@ int fi_tile_backward(const fi_bwd_set *sets, int num_sets, int accumulate, int e
         p += up16((size_t)P.m[P.s[i].map].B * 2 * sizeof(unsigned));
     }
     P.deg_list = reinterpret_cast<int *>(p);
+    P.bin.cursor = reinterpret_cast<int *>(p + list_bytes - 16);
     p += list_bytes;
     for (int i = 0; i < P.nsets; ++i) {
         P.s[i].rec = reinterpret_cast<int4 *>(p);
@@ -730,6 +1102,15 @@ int fi_tile_backward(const fi_bwd_set *sets, int num_sets, int accumulate, int e
         P.s[i].coll = reinterpret_cast<float *>(p);
         if (P.collapse) p += (size_t)P.s[i].R * 4 * P.m[P.s[i].map].C * sizeof(float);
     }
+    P.bin.pool = (int)pool;
+    P.bin.total_tiles = (int)tiles;
+    if (binned) {
+        P.bin.tile_head = reinterpret_cast<int *>(p); p += up16((size_t)tiles * sizeof(int));
+        P.bin.tile_n = reinterpret_cast<int *>(p); p += up16((size_t)tiles * sizeof(int));
+        P.bin.chunk_next = reinterpret_cast<int *>(p); p += up16((size_t)pool * sizeof(int));
+        P.bin.qw = reinterpret_cast<float4 *>(p); p += (size_t)pool * kChunk * sizeof(float4);
+        P.bin.qa = reinterpret_cast<uint2 *>(p); p += (size_t)pool * kChunk * sizeof(uint2);
+    }
     int rc = ok();
     if (max_R > 0) {
         tile_prep_kernel<<<dim3(ceil_div(max_R, 128), P.nsets), 128, 0, stream>>>(P);
@@ -740,7 +1121,25 @@ int fi_tile_backward(const fi_bwd_set *sets, int num_sets, int accumulate, int e
             rc = check_launch("crop backward[collapse]");
         }
     }
-    if (rc == FI_OK && tiles > 0) {
+    if (rc == FI_OK && tiles > 0 && binned) {
+        const int egrid = (int)((tiles + 3) / 4);
+        const dim3 grid((unsigned)tiles, ceil_div(max_slabs, 2));
+#define FI_BIN_LAUNCH(TY_, TX_, U_, MINB_)                                                                    \
+    do {                                                                                                      \
+        if (exact) bin_enumerate_kernel<true, TY_, TX_><<<egrid, 128, 0, stream>>>(P);                        \
+        else bin_enumerate_kernel<false, TY_, TX_><<<egrid, 128, 0, stream>>>(P);                             \
+        rc = check_launch("crop backward[enumerate]");                                                        \
+        if (rc == FI_OK) {                                                                                    \
+            if (exact) bin_accumulate_kernel<true, TY_, TX_, U_, MINB_><<<grid, 64, 0, stream>>>(P);          \
+            else bin_accumulate_kernel<false, TY_, TX_, U_, MINB_><<<grid, 64, 0, stream>>>(P);               \
+            rc = check_launch("crop backward[accumulate]");                                                   \
+        }                                                                                                     \
+    } while (0)
+        if (TXs == 8 && TYs == 4) FI_BIN_LAUNCH(4, 8, 8, 6);
+        else if (TXs == 4) FI_BIN_LAUNCH(4, 4, 4, 10);
+        else FI_BIN_LAUNCH(2, 8, 4, 10);
+#undef FI_BIN_LAUNCH
+    } else if (rc == FI_OK && tiles > 0) {
         const dim3 grid((unsigned)tiles, ceil_div(max_slabs, 2));
         if (TXs == 8 && TYs == 4) {
             if (exact) bwd_smem_tile_kernel<true, 4, 8, FI_TILE_MINB><<<grid, 64, 0, stream>>>(P);

@@ -369,11 +369,11 @@ def test_nchw_tma_path_matches_plain_kernel(monkeypatch):
         assert torch.equal(plain, got)
 
 
-@pytest.mark.parametrize("mode", ["tile", "exact", "red", "gather"])
+@pytest.mark.parametrize("mode", ["tile", "exact", "fused", "fused_exact", "red", "gather"])
 @pytest.mark.parametrize("shape", [(2, 256, 26, 42, 150), (3, 128, 9, 11, 40), (1, 384, 33, 70, 300)])
 def test_backward_formulations_agree(monkeypatch, mode, shape):
-    """Every formulation of the NHWC backward (csrc/roi_align_bwd_tile.cu default + exact, reductions, register gather) on
-    the same maps: ragged tile edges (H, W not multiples of 4 / 8), 1-3 channel slabs, many boxes per tile (> the 64-entry hit
+    """Every formulation of the NHWC backward (csrc/roi_align_bwd_tile.cu: enumerate + accumulate kernels [default] and the fused
+    single kernel, each with default and exact arithmetic; reductions; register gather) on the same maps: ragged tile edges (H, W not multiples of 4 / 8), 1-3 channel slabs, many boxes per tile (> the 64-entry hit
     list), zero-padded / inverted / outside boxes.  exact and gather are bit-identical to the serial CPU reference."""
     fi = _fi()
     B, C, H, W, R = shape
@@ -388,6 +388,10 @@ def test_backward_formulations_agree(monkeypatch, mode, shape):
         img = image.cuda().contiguous(memory_format=torch.channels_last).requires_grad_()
         if mode in ("red", "exact"):
             monkeypatch.setenv("FI_BWD", mode)
+        if mode.startswith("fused"):
+            monkeypatch.setenv("FI_BWD_TILE", "fused")
+            if mode == "fused_exact":
+                monkeypatch.setenv("FI_BWD", "exact")
         if mode == "gather":
             monkeypatch.setenv("FI_BWD", "gather")
         old = fi.set_deterministic(mode == "gather")
@@ -396,8 +400,9 @@ def test_backward_formulations_agree(monkeypatch, mode, shape):
         finally:
             fi.set_deterministic(old)
             monkeypatch.delenv("FI_BWD", raising=False)
+            monkeypatch.delenv("FI_BWD_TILE", raising=False)
         got = img.grad.cpu().numpy()
-        if mode in ("exact", "gather"):
+        if mode in ("exact", "fused_exact", "gather"):
             np.testing.assert_array_equal(got, want)
         else:
             assert_bwd_close(got, grads.numpy(), rois.numpy(), box_ind.numpy(), tuple(image.shape), want)
