@@ -39,7 +39,6 @@ SIGNATURES = {
     "fi_roi_level": (_I, [_P, _I, _F, _F, _P, _P]),
     "fi_split_levels": (_I, [_P, _I, _P, _P, _P, _P, _P, _P]),
     "fi_split_levels_gather": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
-    "fi_crop_sets_backward_by_image": (_I, [_P, _I, _P, _I, _P]),
     "fi_segment_mean_forward": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "fi_segment_mean_backward": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "fi_sinkhorn": (_I, [_P, _P, _I, _I, _I, _F, _I, _P, _P, _P, _P]),

@@ -512,7 +512,6 @@ FI_API int fi_crop_sets_forward(const fi_fwd_set *sets, int num_sets, cudaStream
     return check_launch("fi_crop_sets_forward");
 }
 
-int fi_banded_backward(const fi_bwd_set *sets, int num_sets, int zero_first, cudaStream_t stream);   // roi_align_bwd_banded.cu
 int fi_tile_backward(const fi_bwd_set *sets, int num_sets, int accumulate, int exact, cudaStream_t stream);   // roi_align_bwd_tile.cu
 
 FI_API int fi_crop_sets_backward(const fi_bwd_set *sets, int num_sets, int zero_first, cudaStream_t stream) {
@@ -523,15 +522,11 @@ FI_API int fi_crop_sets_backward(const fi_bwd_set *sets, int num_sets, int zero_
         if (int e = check_common(h.grads, h.boxes, h.box_ind, h.grads_image, h.num_boxes, h.batch, h.image_height, h.image_width, h.crop_height,
                                  h.crop_width, h.depth)) return e;
     }
-    {   // Formulation.  Default: tile-owner kernel (roi_align_bwd_tile.cu) -- shared-memory accumulation,
+    {   // Formulation.  Default: tile-owner kernels (roi_align_bwd_tile.cu) -- shared-memory accumulation,
         // every map pixel written once, no zero fill, no atomics; exact (bit-identical to crop_and_resize.c) when
-        // fi_set_deterministic(1) or FI_BWD=exact.  FI_BWD=red: vector reductions (below).  FI_BWD=banded: L2-resident banded
-        // reductions (roi_align_bwd_banded.cu, experimental).
+        // fi_set_deterministic(1) or FI_BWD=exact.  FI_BWD=red: the vector reductions below (also the fallback for shapes
+        // the tile kernels do not take: crops wider than 16, more than 8 maps).
         const char *mode = getenv("FI_BWD");
-        if (mode && mode[0] == 'b') {
-            const int rc = fi_banded_backward(sets, num_sets, zero_first, stream);
-            if (rc != FI_ERR_UNSUPPORTED) return rc;
-        }
         if (!(mode && mode[0] == 'r')) {
             const int exact = fi_get_deterministic() || (mode && mode[0] == 'e');
             const int rc = fi_tile_backward(sets, num_sets, zero_first ? 0 : 1, exact, stream);
@@ -568,73 +563,6 @@ FI_API int fi_crop_sets_backward(const fi_bwd_set *sets, int num_sets, int zero_
     if (units == 0) return ok();
     crop_bwd_nhwc_sets_kernel<<<grid_for(units, kWarpsPerBlock, 8), kWarpsPerBlock * 32, 0, stream>>>(dev);
     return check_launch("fi_crop_sets_backward");
-}
-
-FI_API int fi_crop_sets_backward_by_image(const fi_bwd_set *sets, int num_sets, const int *img_offsets, int batch, cudaStream_t stream) {
-    FI_REQUIRE(sets && img_offsets && num_sets >= 1 && num_sets <= kMaxBwdSets && batch >= 1, "fi_crop_sets_backward_by_image: bad arguments");
-    for (int i = 0; i < num_sets; ++i) {
-        const fi_bwd_set &h = sets[i];
-        FI_REQUIRE(h.grads_image && h.batch == batch && h.image_height > 0 && h.image_width > 0 && h.depth > 0, "fi_crop_sets_backward_by_image: bad map in set %d", i);
-        if (int e = check_common(h.grads, h.boxes, h.box_ind, h.grads_image, h.num_boxes, h.batch, h.image_height, h.image_width, h.crop_height,
-                                 h.crop_width, h.depth)) return e;
-        const bool vec = (h.depth % 128 == 0) && ((uintptr_t)h.grads_image % 16 == 0) && ((uintptr_t)h.grads % 16 == 0) && ((uintptr_t)h.grads2 % 16 == 0);
-        if (!vec) { set_error(FI_ERR_UNSUPPORTED, "fi_crop_sets_backward_by_image: set %d needs NHWC, depth %% 128 == 0, 16-byte aligned tensors", i); return FI_ERR_UNSUPPORTED; }
-        const int *off = img_offsets + (size_t)i * (batch + 1);
-        FI_REQUIRE(off[0] == 0 && off[batch] == h.num_boxes, "fi_crop_sets_backward_by_image: img_offsets of set %d do not span its boxes", i);
-    }
-    // pack the distinct maps, in order of appearance, into groups whose per-image footprint stays L2-resident
-    const size_t kGroupBytes = 100u << 20;
-    int group_of[kMaxBwdSets];
-    int ngroups = 0;
-    {
-        size_t used = 0;
-        for (int i = 0; i < num_sets; ++i) {
-            int first = i;
-            for (int q = 0; q < i; ++q) if (sets[q].grads_image == sets[i].grads_image) { first = q; break; }
-            if (first != i) { group_of[i] = group_of[first]; continue; }
-            const size_t img_bytes = sizeof(float) * (size_t)sets[i].image_height * sets[i].image_width * sets[i].depth;
-            if (ngroups == 0 || used + img_bytes > kGroupBytes) { ++ngroups; used = 0; }
-            used += img_bytes;
-            group_of[i] = ngroups - 1;
-        }
-    }
-    for (int b = 0; b < batch; ++b) {
-        for (int g = 0; g < ngroups; ++g) {
-            BwdSets dev;
-            dev.n = 0;
-            long units = 0;
-            for (int i = 0; i < num_sets; ++i) {
-                if (group_of[i] != g) continue;
-                const fi_bwd_set &h = sets[i];
-                const size_t img_floats = (size_t)h.image_height * h.image_width * h.depth;
-                bool seen = false;
-                for (int q = 0; q < i; ++q) seen = seen || (sets[q].grads_image == h.grads_image);
-                if (!seen) {
-                    cudaError_t e = cudaMemsetAsync(h.grads_image + (size_t)b * img_floats, 0, sizeof(float) * img_floats, stream);
-                    if (e != cudaSuccess) { set_error(FI_ERR_CUDA, "fi_crop_sets_backward_by_image: memset: %s", cudaGetErrorString(e)); return FI_ERR_CUDA; }
-                }
-                const int *off = img_offsets + (size_t)i * (batch + 1);
-                const int lo = off[b], nb = off[b + 1] - off[b];
-                if (nb <= 0) continue;
-                const size_t row = (size_t)h.crop_height * h.crop_width * h.depth;
-                BwdSet &S = dev.s[dev.n];
-                // scattered gradients are addressed through src_row (slice the index list); compact ones by row r (slice the tensor)
-                S.grads = h.src_row ? h.grads : h.grads + (size_t)lo * row;
-                S.grads2 = h.grads2 ? h.grads2 + (size_t)lo * row : nullptr;
-                S.boxes = h.boxes + (size_t)lo * 4; S.box_ind = h.box_ind + lo; S.src_row = h.src_row ? h.src_row + lo : nullptr;
-                S.gimg = h.grads_image;
-                S.B = h.batch; S.H = h.image_height; S.W = h.image_width; S.C = h.depth; S.ph = h.crop_height; S.pw = h.crop_width; S.slabs = h.depth / 128;
-                dev.first_unit[dev.n] = units;
-                units += (long)nb * h.crop_height * S.slabs;
-                ++dev.n;
-            }
-            dev.first_unit[dev.n] = units;
-            if (units == 0) continue;
-            crop_bwd_nhwc_sets_kernel<<<grid_for(units, kWarpsPerBlock, 8), kWarpsPerBlock * 32, 0, stream>>>(dev);
-            if (int e = check_launch("fi_crop_sets_backward_by_image")) return e;
-        }
-    }
-    return ok();
 }
 
 // ---- reference-named launchers (lib/roi_align/src/cuda/crop_and_resize_kernel.h:8-18) ------------

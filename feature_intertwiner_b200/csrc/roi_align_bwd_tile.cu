@@ -38,14 +38,6 @@
 
 #include "fi_common.cuh"
 
-#ifndef FI_TILE_PAIR
-#define FI_TILE_PAIR 0      // 1: overlap the shared-memory round trips of two consecutive samples that touch disjoint pixels
-                            // (measured on C2: 1.65-1.69 ms vs 1.52 ms without -- bigger drain loop, spills, i-cache misses)
-#endif
-#ifndef FI_TILE_ILV
-#define FI_TILE_ILV 0       // 1: default mode queues even crop columns before odd ones, so that neighbours rarely share a pixel
-                            // (only useful with FI_TILE_PAIR; alone it measures the same 1.51 ms)
-#endif
 #ifndef FI_SCAN_DEPTH
 #define FI_SCAN_DEPTH 1     // chunks of box records in flight ahead of the scan (3 measured 1.58 ms vs 1.52 ms: register pressure)
 #endif
@@ -246,7 +238,6 @@ struct __align__(16) WarpSmemT {
 };
 // pk: in-tile flags TL|TR|BL|BR (bits 0-3), kCollapsed (bit 4), byte offset of the TL pixel inside the warp's tile (bits 9.., signed)
 constexpr int kCollapsed = 1 << 4;
-constexpr int kIndep = 1 << 5;                    // this sample (odd queue slot) shares no pixel with the one before it
 
 // One queued sample: up to 4 read-modify-writes of this lane's float4 in the tile.  Flags / offsets are warp-uniform.
 struct TapVals { float4 v0, v1, v2, v3; };
@@ -295,18 +286,6 @@ __device__ __forceinline__ void apply_sample(float *tile_lane, int pk, float4 w,
     taps_add<EXACT>(t, w, g);
     taps_store<TX>(tile_lane, pk, t);
 }
-// Two consecutive samples that the emitter found to touch disjoint pixels (kIndep on the second): their shared-memory
-// round trips overlap instead of queueing behind each other -- the LDS -> FFMA -> STS latency chain is what bounds a warp.
-template <bool EXACT, int TX>
-__device__ __forceinline__ void apply_pair(float *tile_lane, int pkA, float4 wA, float4 gA, int pkB, float4 wB, float4 gB) {
-    TapVals ta = taps_load<TX>(tile_lane, pkA);
-    TapVals tb = taps_load<TX>(tile_lane, pkB);
-    taps_add<EXACT>(ta, wA, gA);
-    taps_add<EXACT>(tb, wB, gB);
-    taps_store<TX>(tile_lane, pkA, ta);
-    taps_store<TX>(tile_lane, pkB, tb);
-}
-
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Consume the queue in order.  Groups of U samples; the loads of group i+1 are in flight while group i is added.
@@ -349,12 +328,8 @@ __device__ __forceinline__ void drain(const uint4 *qa, const float4 *qw, int qn,
             const float4 wA = qw[g0 + k], wB = qw[g0 + k + 1];
             const float4 gA = DUAL ? add_rn4(a[k], b[k]) : a[k];
             const float4 gB = DUAL ? add_rn4(a[k + 1], b[k + 1]) : a[k + 1];
-            if (FI_TILE_PAIR && (pkB & kIndep)) {
-                apply_pair<EXACT, TX>(tile_lane, pkA, wA, gA, pkB, wB, gB);
-            } else {
-                apply_sample<EXACT, TX>(tile_lane, pkA, wA, gA);
-                apply_sample<EXACT, TX>(tile_lane, pkB, wB, gB);
-            }
+            apply_sample<EXACT, TX>(tile_lane, pkA, wA, gA);
+            apply_sample<EXACT, TX>(tile_lane, pkB, wB, gB);
         }
     };
 #pragma unroll
@@ -426,7 +401,6 @@ __global__ void __launch_bounds__(64, MINB) bwd_smem_tile_kernel(const TParams P
         const int ph = S.ph, pw = S.pw;
         const float *G1 = S.grads + coff, *G2 = S.grads2 ? S.grads2 + coff : nullptr, *COLL = S.coll + coff;
         int qn = 0, nl = 0;
-        unsigned carry_mask = 0;                       // pixels of the last queued sample
         int4 nxt = __ldg(S.rec + min((first & ~31u) + lane, last));
 #if FI_SCAN_DEPTH >= 3
         int4 nxt2 = __ldg(S.rec + min((first & ~31u) + 32 + lane, last));
@@ -514,7 +488,6 @@ __global__ void __launch_bounds__(64, MINB) bwd_smem_tile_kernel(const TParams P
                     const int jry = __shfl_sync(0xffffffffu, hr.x, j), jrx = __shfl_sync(0xffffffffu, hr.y, j);
                     uint4 q = make_uint4(0u, 0u, 0u, 0u);
                     float4 wts = make_float4(0.f, 0.f, 0.f, 0.f);
-                    unsigned pmask = 0;                                // pixels of the tile this sample adds to
                     if (lane < room) {
                         if (jrect & (1 << 16)) {
                             // degenerate box: its (<= 4) corner sums come from the collapse kernel as unit-weight samples
@@ -524,18 +497,12 @@ __global__ void __launch_bounds__(64, MINB) bwd_smem_tile_kernel(const TParams P
                                              cx < X0 + TX;
                             const int px = (cy - Y0) * TX + (cx - X0);
                             const int pk = use ? (1 | kCollapsed | (px * 512)) : kCollapsed;
-                            if (use) pmask = 1u << px;
                             q = make_uint4((unsigned)(jrr * 4 + s), 0u, (unsigned)pk, 0u);
                             wts = make_float4(1.f, 0.f, 0.f, 0.f);
                         } else {
                             const int jnx = (jrect >> 8) & 0xff;
                             const int ii = (int)(((unsigned)s * jinv) >> 16);
-                            int jj = s - ii * jnx;
-                            if (FI_TILE_ILV && !EXACT) {               // even columns first, then odd ones: neighbours in the queue rarely share a pixel
-                                const int half = (jnx + 1) >> 1;
-                                jj = jj < half ? 2 * jj : 2 * (jj - half) + 1;
-                            }
-                            const int iy = (jrect & 15) + ii, ix = ((jrect >> 4) & 15) + jj;
+                            const int iy = (jrect & 15) + ii, ix = ((jrect >> 4) & 15) + (s - ii * jnx);
                             const Tap ty = geom_tap(gby, gsy, iy, H), tx = geom_tap(gbx, gsx, ix, W);
                             // a tap that coincides with its partner (integer sample position) carries weight 0: dropped
                             const bool top = ty.lo >= Y0 && ty.lo < Y0 + TY, bot = ty.hi >= Y0 && ty.hi < Y0 + TY && ty.hi != ty.lo;
@@ -543,21 +510,11 @@ __global__ void __launch_bounds__(64, MINB) bwd_smem_tile_kernel(const TParams P
                             const int f = (top && lef ? 1 : 0) | (top && rig ? 2 : 0) | (bot && lef ? 4 : 0) | (bot && rig ? 8 : 0);
                             const int px = (ty.lo - Y0) * TX + (tx.lo - X0);                              // TL pixel; may be negative
                             const int pk = f ? (f | (px * 512)) : 0;
-                            if (f & 1) pmask |= 1u << px;
-                            if (f & 2) pmask |= 1u << (px + 1);
-                            if (f & 4) pmask |= 1u << (px + TX);
-                            if (f & 8) pmask |= 1u << (px + TX + 1);
                             q = make_uint4((unsigned)((jgrow * ph + iy) * pw + ix), (unsigned)((jrr * ph + iy) * pw + ix), (unsigned)pk, 0u);
                             const float wy0 = __fsub_rn(1.f, ty.frac), wx0 = __fsub_rn(1.f, tx.frac);      // crop_and_resize.c:241-247
                             wts = EXACT ? make_float4(wy0, ty.frac, wx0, tx.frac)
                                         : make_float4(wy0 * wx0, wy0 * tx.frac, ty.frac * wx0, ty.frac * tx.frac);
                         }
-                    }
-                    {
-                        unsigned before = __shfl_up_sync(0xffffffffu, pmask, 1);
-                        if (lane == 0) before = carry_mask;
-                        if (((qn + lane) & 1) && !(pmask & before)) q.z |= kIndep;
-                        carry_mask = __shfl_sync(0xffffffffu, pmask, room - 1);
                     }
                     if (lane < room) {
                         ws.qa[qn + lane] = q;
@@ -952,6 +909,7 @@ __global__ void __launch_bounds__(64, MINB) bin_accumulate_kernel(const TParams 
     }
 }
 
+
 }  // namespace tile
 }  // namespace fi
 
@@ -1067,16 +1025,17 @@ int fi_tile_backward(const fi_bwd_set *sets, int num_sets, int accumulate, int e
         const char *form = getenv("FI_BWD_TILE");
         if (form && form[0] == 'f') binned = false;
     }
+    const long lists = tiles;
     long entries_bound = 0;
     for (int i = 0; i < P.nsets; ++i) entries_bound += 4L * P.s[i].R * P.s[i].ph * P.s[i].pw * (P.s[i].grads2 ? 2 : 1) + 8L * 4 * P.s[i].R;
-    const long pool = entries_bound / kChunk + tiles + 8;
+    const long pool = entries_bound / kChunk + lists + 8;
     if (pool >= (1L << 31) / kChunk) binned = false;
     size_t bytes = range_bytes + list_bytes;
     for (int i = 0; i < P.nsets; ++i) {
         bytes += 2 * up16((size_t)P.s[i].R * sizeof(int4));
         if (P.collapse) bytes += (size_t)P.s[i].R * 4 * P.m[P.s[i].map].C * sizeof(float);    // only degenerate rows are ever touched
     }
-    if (binned) bytes += 2 * up16((size_t)tiles * sizeof(int)) + up16((size_t)pool * sizeof(int)) + (size_t)pool * kChunk * (sizeof(uint2) + sizeof(float4));
+    if (binned) bytes += 2 * up16((size_t)lists * sizeof(int)) + up16((size_t)pool * sizeof(int)) + (size_t)pool * kChunk * (sizeof(uint2) + sizeof(float4));
     char *ws = workspace(bytes, stream);
     if (!ws) return FI_ERR_CUDA;
     cudaError_t e;
@@ -1105,8 +1064,8 @@ int fi_tile_backward(const fi_bwd_set *sets, int num_sets, int accumulate, int e
     P.bin.pool = (int)pool;
     P.bin.total_tiles = (int)tiles;
     if (binned) {
-        P.bin.tile_head = reinterpret_cast<int *>(p); p += up16((size_t)tiles * sizeof(int));
-        P.bin.tile_n = reinterpret_cast<int *>(p); p += up16((size_t)tiles * sizeof(int));
+        P.bin.tile_head = reinterpret_cast<int *>(p); p += up16((size_t)lists * sizeof(int));
+        P.bin.tile_n = reinterpret_cast<int *>(p); p += up16((size_t)lists * sizeof(int));
         P.bin.chunk_next = reinterpret_cast<int *>(p); p += up16((size_t)pool * sizeof(int));
         P.bin.qw = reinterpret_cast<float4 *>(p); p += (size_t)pool * kChunk * sizeof(float4);
         P.bin.qa = reinterpret_cast<uint2 *>(p); p += (size_t)pool * kChunk * sizeof(uint2);

@@ -10,42 +10,46 @@ Both accept the image in either memory format: contiguous NCHW (the reference's)
 ``torch.channels_last`` (the native one here -- see csrc/roi_align.cu); crops come back in the same format,
 logical shape ``[R, C, crop_h, crop_w]`` either way.
 """
-import ctypes as C
-import os
-
 import torch
 from torch import nn
 
 from . import _lib
 
-# FI_BWD_BY_IMAGE=1 (with FI_BWD=red): image-by-image (L2-resident) REDUCTION backward of crop_sets when per-image extents are
-# known.  Measured on C2: DRAM traffic drops to the algorithmic 4.6 GB but the time does not (1.81 vs 1.69 ms) -- the reduction
-# kernel is bound by L2 reduction throughput (~3.5 TB/s of RED payload), not by DRAM (DESIGN.md section 4).  Experimental.
-_BY_IMAGE = os.environ.get("FI_BWD_BY_IMAGE", "0") == "1"
-
-
 # ---- optional per-launch timing (bench.py): CUDA events on the launching stream + what is needed to count the
 # launch's algorithmic bytes afterwards.  Off by default; nothing is recorded and no event is created then.
 _PROFILE = None
+_EVENT_POOL = []
 
 
-def enable_profiling():
+def enable_profiling(prealloc_events=0):
+    """Record a (start, end) CUDA-event pair around every RoIAlign launch.  ``prealloc_events`` timing events are created AND
+    recorded once up front: creating them inside a timed loop costs sporadic 5-100 ms host stalls in the driver (measured with
+    bench.py: every third step or so), which would be charged to the step."""
     global _PROFILE
     _PROFILE = []
+    for _ in range(prealloc_events):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()                                   # torch creates the CUDA event lazily, on its first record
+        _EVENT_POOL.append(ev)
     return _PROFILE
 
 
 def disable_profiling():
     global _PROFILE
     rec, _PROFILE = _PROFILE, None
+    del _EVENT_POOL[:]
     return rec or []
+
+
+def _event():
+    return _EVENT_POOL.pop() if _EVENT_POOL else torch.cuda.Event(enable_timing=True)
 
 
 class _Timed(object):
     def __init__(self, kernel, **meta):
         self.rec = None
         if _PROFILE is not None:
-            self.rec = dict(kernel=kernel, start=torch.cuda.Event(enable_timing=True), end=torch.cuda.Event(enable_timing=True), **meta)
+            self.rec = dict(kernel=kernel, start=_event(), end=_event(), **meta)
 
     def __enter__(self):
         if self.rec is not None:
@@ -310,17 +314,9 @@ class _CropSets(torch.autograd.Function):
         if sets:
             L = _lib.lib()
             with torch.cuda.device(dev), _Timed("crop_bwd_nhwc", alg_bytes=nbytes):
+                # tile-owner kernels by default: every map written once (exact arithmetic under set_deterministic)
                 arr = (_lib.BwdSet * len(sets))(*sets)
-                nb = sets[0].batch
-                by_image = _BY_IMAGE and not L.fi_get_deterministic() and all(o is not None and len(o) == nb + 1 for o in offsets) \
-                    and all(st.batch == nb for st in sets) and len({st.grads_image for st in sets}) == len(g_images)
-                if by_image:
-                    # image by image: zero a slice, reduce into it while it is L2-resident (fi_crop_sets_backward_by_image)
-                    flat_off = (C.c_int * (len(sets) * (nb + 1)))(*[v for o in offsets for v in o])
-                    _lib.check(L.fi_crop_sets_backward_by_image(arr, len(sets), flat_off, nb, _lib.stream_ptr(dev)))
-                else:
-                    # default: tile-owner kernel, every map written once (exact arithmetic under set_deterministic)
-                    _lib.check(L.fi_crop_sets_backward(arr, len(sets), 1, _lib.stream_ptr(dev)))
+                _lib.check(L.fi_crop_sets_backward(arr, len(sets), 1, _lib.stream_ptr(dev)))
         touched = {st.grads_image for st in sets}
         for i, gi in g_images.items():
             if _lib.ptr(gi) not in touched:

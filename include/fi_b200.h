@@ -152,13 +152,6 @@ typedef struct fi_bwd_set {
 /* zero_first != 0: every distinct grads_image is zero-filled once before the (single) reduction launch. */
 int fi_crop_sets_backward(const fi_bwd_set *sets, int num_sets, int zero_first, cudaStream_t stream);
 
-/* The same reduction, image by image: for every image b, the slices of the dense maps that belong to b are zero-filled and
- * IMMEDIATELY reduced into while they are still in the 126 MB L2 (maps are packed into groups of <= ~100 MB per image), so
- * reductions hit L2 and every line goes to DRAM once -- instead of zero-filling 1.5 GB up front and fetching each line
- * back.  Requires box_ind non-decreasing in every set; img_offsets (HOST array [num_sets, batch + 1]) gives, for each set, the
- * first box of each image (img_offsets[s][batch] = num_boxes). */
-int fi_crop_sets_backward_by_image(const fi_bwd_set *sets, int num_sets, const int *img_offsets, int batch, cudaStream_t stream);
-
 /* Integer taps of every sample, taps[num_boxes,crop_h,crop_w,5] = (y_lo,y_hi,x_lo,x_hi,inside): the "RoI
  * indices" the parity bar requires bit-exact (crop_and_resize_kernel.cu:40-70). */
 int fi_crop_taps(const float *boxes, int num_boxes, int image_height, int image_width, int crop_height,

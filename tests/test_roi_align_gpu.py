@@ -81,7 +81,7 @@ def test_backward_matches_oracle(fmt, P, C):
             fi.set_deterministic(old)
         got = img.grad.cpu().numpy()
         if deterministic:
-            # gather backward (csrc/roi_align_bwd.cu): same order, same un-fused arithmetic as the serial CPU loop
+            # exact tile-owner backward (csrc/roi_align_bwd_tile.cu): same order, same un-fused arithmetic as the serial CPU loop
             np.testing.assert_array_equal(got, want)
         else:
             assert_bwd_close(got, grads.numpy(), rois.numpy(), box_ind.numpy(), tuple(image.shape), want)
@@ -369,12 +369,12 @@ def test_nchw_tma_path_matches_plain_kernel(monkeypatch):
         assert torch.equal(plain, got)
 
 
-@pytest.mark.parametrize("mode", ["tile", "exact", "fused", "fused_exact", "red", "gather"])
+@pytest.mark.parametrize("mode", ["tile", "exact", "fused", "fused_exact", "red", "det"])
 @pytest.mark.parametrize("shape", [(2, 256, 26, 42, 150), (3, 128, 9, 11, 40), (1, 384, 33, 70, 300)])
 def test_backward_formulations_agree(monkeypatch, mode, shape):
     """Every formulation of the NHWC backward (csrc/roi_align_bwd_tile.cu: enumerate + accumulate kernels [default] and the fused
-    single kernel, each with default and exact arithmetic; reductions; register gather) on the same maps: ragged tile edges (H, W not multiples of 4 / 8), 1-3 channel slabs, many boxes per tile (> the 64-entry hit
-    list), zero-padded / inverted / outside boxes.  exact and gather are bit-identical to the serial CPU reference."""
+    single kernel, each with default and exact arithmetic; reductions) on the same maps: ragged tile edges (H, W not multiples of 4 / 8), 1-3 channel slabs, many boxes per tile (> the 64-entry hit
+    list), zero-padded / inverted / outside boxes.  The exact modes are bit-identical to the serial CPU reference."""
     fi = _fi()
     B, C, H, W, R = shape
     image, rois, box_ind = _case(77, B, C, H, W, R, zero_rows=8)
@@ -389,12 +389,10 @@ def test_backward_formulations_agree(monkeypatch, mode, shape):
         if mode in ("red", "exact"):
             monkeypatch.setenv("FI_BWD", mode)
         if mode.startswith("fused"):
-            monkeypatch.setenv("FI_BWD_TILE", "fused")
-            if mode == "fused_exact":
+            monkeypatch.setenv("FI_BWD_TILE", mode.split("_")[0])
+            if mode.endswith("_exact"):
                 monkeypatch.setenv("FI_BWD", "exact")
-        if mode == "gather":
-            monkeypatch.setenv("FI_BWD", "gather")
-        old = fi.set_deterministic(mode == "gather")
+        old = fi.set_deterministic(mode == "det")              # the process-wide switch selects the exact arithmetic too
         try:
             fi.crop_and_resize(img, rois.cuda(), box_ind.cuda(), P, P).backward(grads.cuda().contiguous(memory_format=torch.channels_last))
         finally:
@@ -402,7 +400,7 @@ def test_backward_formulations_agree(monkeypatch, mode, shape):
             monkeypatch.delenv("FI_BWD", raising=False)
             monkeypatch.delenv("FI_BWD_TILE", raising=False)
         got = img.grad.cpu().numpy()
-        if mode in ("exact", "fused_exact", "gather"):
+        if mode in ("exact", "fused_exact", "det"):
             np.testing.assert_array_equal(got, want)
         else:
             assert_bwd_close(got, grads.numpy(), rois.numpy(), box_ind.numpy(), tuple(image.shape), want)
