@@ -160,7 +160,7 @@ class Step(object):
         import feature_intertwiner_b200 as fi
         self.fi, self.wl, self.dev, self.world = fi, wl, device, world
         self.spatial_sort = os.environ.get("FI_SPATIAL_SORT", "1") != "0"
-        self.use_graph = world == 1 and os.environ.get("FI_GRAPH", "1") != "0"     # CUDA-graph the fixed-shape loss head
+        self.use_graph = os.environ.get("FI_GRAPH", "1") != "0"     # CUDA-graph the fixed-shape loss head (no collective inside)
         self.graph_tried, self.graphed = False, False
         self.cfg = build_config(wl)
         torch.manual_seed(2000)

@@ -530,21 +530,24 @@ class IntertwinerLoss(nn.Module):
 
     # ---- optional CUDA-graph capture of the loss head ------------------------------------------------------------
     def enable_cuda_graph(self, feat_input):
-        """Capture forward AND backward of the loss head (statistics merge -> buffer update -> match -> OptTrans / Sinkhorn)
-        into CUDA graphs: ~60 small launches per iteration become two graph launches.  Possible when every shape is fixed:
-        class-level loss, l1 / l2 or padded OT, BUFFER_SIZE == 1, single process.  ``feat_input`` is a representative input
-        (shapes / requires_grad as in training).  Returns True when the graphed path is active; falls back to eager on any
-        failure.  The buffer is snapshotted around the warm-up replays, so capture does not disturb the running means."""
+        """Capture forward AND backward of the loss head (buffer update -> match -> OptTrans / Sinkhorn) into CUDA graphs:
+        ~60 small launches per iteration become two graph launches.  Possible when every shape is fixed: class-level loss,
+        l1 / l2 or padded OT, BUFFER_SIZE == 1.  The statistics merge (and, when distributed, its all-reduce) stays eager in
+        front of the graph, so the captured part contains no collective and the same graph serves 1 and N processes.
+        ``feat_input`` is a representative input (shapes / requires_grad as in training).  Returns True when the graphed path
+        is active; falls back to eager on any failure.  The buffer is snapshotted around the warm-up replays, so capture does
+        not disturb the running means."""
         cfg = self.config
-        ok = (not self.distributed) and self.buffer.size(0) == 1 and not cfg.DEV.INST_LOSS and \
+        ok = self.buffer.size(0) == 1 and not cfg.DEV.INST_LOSS and \
             (cfg.DEV.LOSS_CHOICE in ('l1', 'l2') or (cfg.DEV.LOSS_CHOICE == 'ot' and self.ot_padded))
         if not ok:
             return False
-        big_feat, big_cnt, small_feat, small_cnt = feat_input[:4]
         snap = (self.buffer.clone(), self.buffer_cnt.clone())
         try:
+            with torch.no_grad():
+                sums = self._stage_sums([t.detach() for t in feat_input[:4]])
             head = _LossHead(self)
-            sample = (big_feat.detach().clone(), big_cnt.detach().clone(), small_feat.detach().clone().requires_grad_(), small_cnt.detach().clone())
+            sample = (sums[0].clone(), sums[1].clone(), sums[2].clone().requires_grad_(), sums[3].clone())
             graphed = torch.cuda.make_graphed_callables(head, sample)
             self._graphed = graphed
             self._graph_shapes = tuple(tuple(t.shape) for t in sample)
@@ -557,19 +560,33 @@ class IntertwinerLoss(nn.Module):
 
     def forward(self, feat_input):
         g = getattr(self, '_graphed', None)
-        if g is not None and torch.is_grad_enabled() and feat_input[2].requires_grad and \
-                tuple(tuple(t.shape) for t in feat_input[:4]) == self._graph_shapes:
-            return g(feat_input[0].detach(), feat_input[1].detach(), feat_input[2], feat_input[3].detach())
+        if g is not None and torch.is_grad_enabled() and feat_input[2].requires_grad:
+            big_sum, big_n, s_sum, s_n = self._stage_sums(feat_input)
+            if tuple(tuple(t.shape) for t in (big_sum, big_n, s_sum, s_n)) == self._graph_shapes:
+                return g(big_sum.detach(), big_n.detach(), s_sum, s_n.detach())
+            return self._head(big_sum, big_n, s_sum, s_n, feat_input[4], feat_input[5])
         return self._forward_eager(feat_input)
 
+    def _stage_sums(self, feat_input):
+        """The exchange step: un-normalised class statistics of the reliable and of the less-reliable set, summed over
+        (gpu, scale) and -- when distributed -- all-reduced over the ranks (lib/model.py:151,177,217-224)."""
+        big_feat, big_cnt, small_feat, small_cnt = feat_input[:4]
+        big_sum, big_n = self._sums(big_feat.detach(), big_cnt.detach(), differentiable=False)
+        if self.config.DEV.INST_LOSS:
+            return big_sum.contiguous(), big_n.contiguous(), None, None
+        s_sum, s_n = self._sums(small_feat, small_cnt, differentiable=True)
+        return big_sum.contiguous(), big_n.contiguous(), s_sum, s_n
+
     def _forward_eager(self, feat_input):
-        big_feat, big_cnt, small_feat, small_cnt, small_output_all, small_gt_all = feat_input
+        big_sum, big_n, s_sum, s_n = self._stage_sums(feat_input)
+        return self._head(big_sum, big_n, s_sum, s_n, feat_input[4], feat_input[5])
+
+    def _head(self, big_sum, big_n, s_sum, s_n, small_output_all, small_gt_all):
         cfg = self.config
         Fd, ncls = self.feat_dim, cfg.DATASET.NUM_CLASSES
         B = self.buffer.size(0)
         dev = self.buffer.device
         # ---- reliable-set statistics -> historical buffer (model.py:148-166), one kernel
-        big_sum, big_n = self._sums(big_feat.detach(), big_cnt.detach(), differentiable=False)
         big_sum, big_n = big_sum.contiguous(), big_n.contiguous()
         final_big = torch.empty((Fd, ncls), device=dev, dtype=torch.float32)
         slot = int(self.ring_pos.item()) if B > 1 else 0
@@ -586,7 +603,6 @@ class IntertwinerLoss(nn.Module):
             mask = (gt != 0) & in_buffer[gt]
             SMALL_all, BIG_all = small_output_all, final_big.t()[gt]
         else:
-            s_sum, s_n = self._sums(small_feat, small_cnt, differentiable=True)
             final_small = s_sum / (s_n + EPS)
             s_n = s_n * self.fg_mask                                            # background excluded (model.py:178); no host scalar
             mask = (s_n > 0) & in_buffer
@@ -616,7 +632,8 @@ class IntertwinerLoss(nn.Module):
 
 
 class _LossHead(nn.Module):
-    """The fixed-shape part of IntertwinerLoss as a 4-tensor callable for torch.cuda.make_graphed_callables.  Shares the
+    """The fixed-shape part of IntertwinerLoss (everything after the statistics merge / all-reduce) as a 4-tensor callable for
+    torch.cuda.make_graphed_callables.  Shares the
     OptTrans module (so its parameters receive gradients) and reaches the buffers through the parent."""
 
     def __init__(self, parent):
@@ -625,8 +642,8 @@ class _LossHead(nn.Module):
         if hasattr(parent, 'ot_loss'):
             self.ot_loss = parent.ot_loss
 
-    def forward(self, big_feat, big_cnt, small_feat, small_cnt):
-        return self._parent._forward_eager([big_feat, big_cnt, small_feat, small_cnt, None, None])
+    def forward(self, big_sum, big_n, s_sum, s_n):
+        return self._parent._head(big_sum, big_n, s_sum, s_n, None, None)
 
 
 def meta_loss_module(config, ot_loss=None, **kw):

@@ -105,10 +105,12 @@ int fi_crop_and_resize_backward(const float *grads, int grads_layout, const floa
  * lib/sub_module.py:555-572), back-propagated in ONE pass that writes grads_image exactly once.  NHWC only.
  *   grads    [rows,crop_h,crop_w,depth]: gradient of crop r is row src_row[r] (row r when src_row is NULL)
  *   grads2   NULL, or a second gradient for the same crops in compact row order (row r), added to the first
- * deterministic != 0 (needs crop_h, crop_w <= 16 and depth % 128 == 0): every pixel is summed by one warp in the order
- * of the reference's serial CPU loop with un-fused fp32 arithmetic -- run-to-run identical and bit-identical to
- * crop_and_resize.c:157-252 for a single set -- and the map is written once (no zero fill, no atomics).
- * deterministic == 0: one zero fill, then 128-bit vector reductions set by set. */
+ * Both modes use the tile-owner kernels (crop_h, crop_w <= 16, depth % 128 == 0; csrc/roi_align_bwd_tile.cu): every
+ * 4x8-pixel tile is accumulated in shared memory by one warp per 128-channel slab, in the order of the reference's serial
+ * CPU loop, and the map is written exactly once (no zero fill, no atomics) -- run-to-run identical either way.
+ * deterministic != 0: un-fused fp32 arithmetic as well, bit-identical to crop_and_resize.c:157-252 for a single set.
+ * deterministic == 0: packed FMAs with pre-multiplied weights; zero-padded / sub-pixel boxes are pre-reduced in parallel.
+ * Other shapes (or FI_BWD=red): one zero fill, then 128-bit vector reductions set by set. */
 typedef struct fi_crop_set {
     const float *grads;
     const float *grads2;
@@ -120,8 +122,8 @@ typedef struct fi_crop_set {
 int fi_crop_and_resize_backward_multi(const fi_crop_set *sets, int num_sets, int batch, int image_height, int image_width,
                                       int depth, float *grads_image, int accumulate, int deterministic, cudaStream_t stream);
 
-/* Process-wide default for fi_crop_and_resize_backward (NHWC): 0 = vector reductions (default; like the reference's
- * atomics the summation order varies from run to run), 1 = deterministic write-once gather.  Returns the old value. */
+/* Process-wide arithmetic of the NHWC backward: 0 = default (packed FMAs), 1 = exact (bit-identical to the reference's
+ * CPU loop, see above).  Returns the old value. */
 int fi_set_deterministic(int on);
 int fi_get_deterministic(void);
 
@@ -149,7 +151,8 @@ typedef struct fi_bwd_set {
     const int *src_row;
     int batch, image_height, image_width, depth, num_boxes, crop_height, crop_width;
 } fi_bwd_set;
-/* zero_first != 0: every distinct grads_image is zero-filled once before the (single) reduction launch. */
+/* zero_first != 0: the maps are overwritten (the tile-owner kernels write every pixel once; the reduction fallback
+ * zero-fills each distinct grads_image first); zero_first == 0: the sums are added onto the existing contents. */
 int fi_crop_sets_backward(const fi_bwd_set *sets, int num_sets, int zero_first, cudaStream_t stream);
 
 /* Integer taps of every sample, taps[num_boxes,crop_h,crop_w,5] = (y_lo,y_hi,x_lo,x_hi,inside): the "RoI
