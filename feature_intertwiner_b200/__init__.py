@@ -6,7 +6,7 @@ from ._lib import FiError, lib, library_path  # noqa: F401
 from .roi_align import (CropAndResizeFunction, RoIAlign, crop_and_resize, crop_pair, crop_sets, crop_taps,  # noqa: F401
                         set_deterministic)
 from .roi_pool import RoIPoolFunction, _RoIPooling  # noqa: F401
-from .nms import nms, nms_batched, pth_nms  # noqa: F401
+from .nms import nms, nms_batched, nms_presorted, proposal_decode, proposal_layer, pth_nms  # noqa: F401
 from .ot import OptTrans, sinkhorn_loss  # noqa: F401
 from .intertwiner import (Dev, IntertwinerLoss, LevelSplit, assign_feat2cls, pyramid_roi_align, roi_level,  # noqa: F401
                           spatial_order, split_levels)

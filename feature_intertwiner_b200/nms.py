@@ -50,3 +50,66 @@ def nms(dets, thresh):
     keep, num = nms_batched(dets, thresh)
     m = int(num.min().item())            # the one host sync: the reference's API returns a numpy array
     return keep[:, :m].to(torch.int32).cpu().numpy().astype(np.int32)
+
+
+def nms_presorted(dets_xyxys, thresh):
+    """dets[bs,N,5] = (x1,y1,x2,y2,score), every image already in descending score order -> (keep[bs,N] int32 positions,
+    kept ones first in score order, rest -1; num_keep[bs] int32).  No sort, no host synchronisation."""
+    _lib.require_cuda(dets_xyxys)
+    bs, n, _ = dets_xyxys.shape
+    words = (n + 63) // 64
+    mask = torch.empty((bs, n, max(words, 1)), device=dets_xyxys.device, dtype=torch.int64)
+    keep = torch.empty((bs, n), device=dets_xyxys.device, dtype=torch.int32)
+    num = torch.empty((bs,), device=dets_xyxys.device, dtype=torch.int32)
+    with torch.cuda.device(dets_xyxys.device):
+        _lib.check(_lib.lib().fi_nms_batched(_lib.ptr(dets_xyxys), bs, n, float(thresh), _lib.ptr(mask), _lib.ptr(keep),
+                                             _lib.ptr(num), _lib.stream_ptr(dets_xyxys.device)))
+    return keep, num
+
+
+def proposal_decode(inputs, priors, config):
+    """Front half of proposal_layer (lib/layers.py:87-122): the PRE_NMS_LIMIT best anchors per image by foreground score,
+    refined by ``rpn_bbox * BBOX_STD_DEV`` and clipped to the image.  Returns (boxes[bs,K,4] = (y1,x1,y2,x2) in pixels,
+    dets[bs,K,5] = (x1,y1,x2,y2,score), both in descending score order).  One sort + one launch (fi_proposal_decode)."""
+    import ctypes as C
+    probs, deltas = inputs[0], inputs[1]
+    _lib.require_cuda(probs, deltas)
+    dev = probs.device
+    scores = probs.detach()[:, :, 1].float()
+    deltas = deltas.detach().float().contiguous()
+    anchors = priors.detach().to(device=dev, dtype=torch.float32).contiguous()
+    bs, A = scores.shape
+    if anchors.shape != (A, 4) or deltas.shape != (bs, A, 4):
+        raise _lib.FiError("proposal_layer: rpn_probs [bs,A,2], rpn_bbox [bs,A,4] and priors [A,4] do not agree")
+    pre = min(int(config.RPN.PRE_NMS_LIMIT), A)
+    scores_s, order = torch.sort(scores, dim=1, descending=True, stable=True)       # layers.py:103 (stable: ties are defined)
+    scores_s, order = scores_s[:, :pre].contiguous(), order[:, :pre].contiguous()
+    boxes = torch.empty((bs, pre, 4), device=dev, dtype=torch.float32)
+    dets = torch.empty((bs, pre, 5), device=dev, dtype=torch.float32)
+    std = (C.c_float * 4)(*[float(v) for v in config.DATA.BBOX_STD_DEV])
+    height, width = float(config.DATA.IMAGE_SHAPE[0]), float(config.DATA.IMAGE_SHAPE[1])
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().fi_proposal_decode(_lib.ptr(deltas), _lib.ptr(anchors), _lib.ptr(order), _lib.ptr(scores_s), bs, A, pre,
+                                                 C.cast(std, C.c_void_p), height, width, _lib.ptr(boxes), _lib.ptr(dets),
+                                                 _lib.stream_ptr(dev)))
+    return boxes, dets
+
+
+def proposal_layer(inputs, proposal_count, nms_threshold, priors, config=None):
+    """lib/layers.py:71-139 with the same call shape: ``inputs = [rpn_probs[bs,A,2], rpn_bbox[bs,A,4]]``, ``priors[A,4]`` anchors
+    in pixels (y1,x1,y2,x2) -> normalised proposals ``[bs, m, 4]``, m = min(proposal_count, smallest keep count of the batch)
+    like lib/nms/nms_wrapper.py:24-33.
+
+    The reference sorts on the device, gathers per image in a Python loop, runs five elementwise ops, concatenates for NMS,
+    copies the 4.5 MB suppression mask of every image to the host, reduces it there and indexes again per image.  Here:
+    one sort (torch), one decode launch (fi_proposal_decode: gather + deltas + clip + NMS layout), the batched on-device NMS,
+    one gather; the only host synchronisation left is reading ``m`` -- the reference's API returns a tensor of that size."""
+    boxes, dets = proposal_decode(inputs, priors, config)
+    bs, dev = boxes.size(0), boxes.device
+    height, width = float(config.DATA.IMAGE_SHAPE[0]), float(config.DATA.IMAGE_SHAPE[1])
+    keep, num = nms_presorted(dets, nms_threshold)
+    m = min(int(num.min().item()), int(proposal_count))                              # the one host sync
+    idx = keep[:, :m].long()
+    boxes_keep = torch.gather(boxes, 1, idx.unsqueeze(2).expand(bs, m, 4))
+    norm = torch.tensor([height, width, height, width], device=dev)
+    return boxes_keep / norm

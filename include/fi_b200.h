@@ -231,6 +231,14 @@ int fi_buffer_update(const float *big_sum, const float *big_n, int B, int slot, 
 int fi_nms_batched(const float *boxes, int n_images, int n, float thresh, unsigned long long *mask, int *keep,
                    int *num_keep, cudaStream_t stream);
 
+/* Front half of proposal_layer (lib/layers.py:87-122 + tools/box_utils.py:7-45) in one launch: for proposal k of image b,
+ * a = order[b,k] (descending-score order, int64 as torch.sort returns it); box = clip(apply_box_deltas(anchors[a],
+ * deltas[b,a] * std_dev), [0,0,window_height,window_width]).  Writes boxes[batch,K,4] = (y1,x1,y2,x2) and
+ * dets_xyxys[batch,K,5] = (x1,y1,x2,y2,scores_sorted[b,k]) -- the input layout of fi_nms_batched.  std_dev4: 4 HOST floats. */
+int fi_proposal_decode(const float *deltas, const float *anchors, const long long *order, const float *scores_sorted, int batch,
+                       int num_anchors, int num_proposals, const float *std_dev4, float window_height, float window_width,
+                       float *boxes, float *dets_xyxys, cudaStream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * 8. RoIPool with an argmax-scatter backward (lib/roi_pooling/src/roi_pooling_cuda.c:7-88).
  * ------------------------------------------------------------------------------------------- */

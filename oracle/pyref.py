@@ -35,8 +35,9 @@ def make_config(**over):
                INIT_BUFFER_WEIGHT="scratch"),
         ROIS=ns(METHOD="roi_align", ASSIGN_ANCHOR_BASE=224.0, TRAIN_ROIS_PER_IMAGE=200, ROI_POSITIVE_RATIO=0.33),
         MRCNN=ns(POOL_SIZE=7, MASK_POOL_SIZE=14),
-        DATA=ns(IMAGE_SHAPE=np.array([1024, 1024, 3])),
+        DATA=ns(IMAGE_SHAPE=np.array([1024, 1024, 3]), BBOX_STD_DEV=np.array([0.1, 0.1, 0.2, 0.2])),
         DATASET=ns(NUM_CLASSES=81),
+        RPN=ns(PRE_NMS_LIMIT=6000, NMS_THRESHOLD=0.7, POST_NMS_ROIS_TRAINING=2000, POST_NMS_ROIS_INFERENCE=1000),
     )
     for k, v in over.items():
         sec, key = k.split("__")
@@ -374,3 +375,44 @@ def nms_ref(dets, thresh, strict=True):
     for i, k in enumerate(keeps):
         out[i] = k[:m].numpy()
     return out
+
+
+# =============================================================================== proposal layer
+def apply_box_deltas_ref(boxes, deltas):
+    """tools/box_utils.py:7-29 (out-of-place: the in-place updates there act on temporaries)."""
+    height = boxes[:, :, 2] - boxes[:, :, 0]
+    width = boxes[:, :, 3] - boxes[:, :, 1]
+    center_y = boxes[:, :, 0] + 0.5 * height
+    center_x = boxes[:, :, 1] + 0.5 * width
+    center_y = center_y + deltas[:, :, 0] * height
+    center_x = center_x + deltas[:, :, 1] * width
+    height = height * torch.exp(deltas[:, :, 2])
+    width = width * torch.exp(deltas[:, :, 3])
+    y1 = center_y - 0.5 * height
+    x1 = center_x - 0.5 * width
+    return torch.stack([y1, x1, y1 + height, x1 + width], dim=2)
+
+
+def proposal_layer_ref(inputs, proposal_count, nms_threshold, priors, config):
+    """lib/layers.py:71-139 on CPU tensors: top PRE_NMS_LIMIT anchors by foreground score, deltas * BBOX_STD_DEV applied,
+    clipped to the image, NMS per image (GPU rule, via the C oracle), truncated to the smallest keep count of the batch
+    (lib/nms/nms_wrapper.py:24-33) and to proposal_count, normalised.  A stable sort stands in for the reference's
+    unstable one (ties are implementation-defined there).  Returns (normalised boxes [bs, m, 4], keep [bs, m])."""
+    scores = inputs[0][:, :, 1].detach().float().cpu()
+    deltas = inputs[1].detach().float().cpu() * torch.from_numpy(np.reshape(config.DATA.BBOX_STD_DEV, [1, 1, 4])).float()
+    anchors = priors.detach().float().cpu()
+    bs, prior_num = scores.size(0), anchors.size(0)
+    pre = min(config.RPN.PRE_NMS_LIMIT, prior_num)
+    scores, order = scores.sort(dim=1, descending=True, stable=True)
+    scores, order = scores[:, :pre], order[:, :pre]
+    deltas_trim = torch.stack([deltas[i][order[i]] for i in range(bs)])
+    anchors_trim = torch.stack([anchors[order[i]] for i in range(bs)])
+    boxes = apply_box_deltas_ref(anchors_trim, deltas_trim)
+    height, width = float(config.DATA.IMAGE_SHAPE[0]), float(config.DATA.IMAGE_SHAPE[1])
+    boxes = torch.stack([boxes[:, :, 0].clamp(0.0, height), boxes[:, :, 1].clamp(0.0, width),
+                         boxes[:, :, 2].clamp(0.0, height), boxes[:, :, 3].clamp(0.0, width)], 2)
+    keep = nms_ref(torch.cat((boxes, scores.unsqueeze(2)), 2), nms_threshold, strict=True)      # numpy int32 [bs, min_keep]
+    keep = torch.from_numpy(keep[:, :proposal_count].astype(np.int64))
+    boxes_keep = torch.stack([boxes[i][keep[i]] for i in range(bs)])
+    norm = torch.tensor([height, width, height, width])
+    return boxes_keep / norm, keep

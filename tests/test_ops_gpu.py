@@ -468,3 +468,52 @@ def test_dev_spatial_sort_changes_only_row_order():
     ka = torch.sort(fo[5].sum(1) * 1000 + fo[6])[0]
     kb = torch.sort(fo2[5].sum(1) * 1000 + fo2[6])[0]
     torch.testing.assert_close(ka, kb, rtol=1e-5, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------ proposal layer
+def _proposal_case(seed, bs, A, hw):
+    g = torch.Generator().manual_seed(seed)
+    H, W = hw
+    cy, cx = torch.rand(A, generator=g) * H, torch.rand(A, generator=g) * W
+    h = torch.exp(torch.rand(A, generator=g) * 3.0 + 2.5)
+    w = h * torch.exp(torch.rand(A, generator=g) * 1.4 - 0.7)
+    anchors = torch.stack([cy - h / 2, cx - w / 2, cy + h / 2, cx + w / 2], 1)
+    fg = torch.rand(bs, A, generator=g)
+    probs = torch.stack([1 - fg, fg], 2)
+    deltas = torch.randn(bs, A, 4, generator=g) * torch.tensor([1.5, 1.5, 2.0, 2.0])
+    return probs, deltas, anchors
+
+
+@pytest.mark.parametrize("bs,A,pre,count", [(2, 3000, 1000, 300), (3, 9000, 6000, 2000), (1, 70, 6000, 50)])
+def test_proposal_layer_vs_restatement(bs, A, pre, count):
+    """fi.proposal_layer (lib/layers.py:71-139): decoded boxes vs the torch restatement of apply_box_deltas / clip_boxes; the
+    final proposals are exactly what the CPU NMS oracle keeps of OUR decoded boxes (so a 1-ulp difference in exp() cannot flip
+    a suppression between the two sides), with the reference's truncation to the smallest keep count of the batch."""
+    fi = _fi()
+    hw = (832, 1344)
+    cfg = pyref.make_config(DATA__IMAGE_SHAPE=np.array([hw[0], hw[1], 3]), RPN__PRE_NMS_LIMIT=pre)
+    probs, deltas, anchors = _proposal_case(100 + A, bs, A, hw)
+    boxes, dets = fi.proposal_decode([probs.cuda(), deltas.cuda()], anchors.cuda(), cfg)
+    K = min(pre, A)
+    assert tuple(boxes.shape) == (bs, K, 4) and tuple(dets.shape) == (bs, K, 5)
+    # decode parity
+    scores_s, order = probs[:, :, 1].sort(dim=1, descending=True, stable=True)
+    scores_s, order = scores_s[:, :K], order[:, :K]
+    std = torch.from_numpy(np.reshape(cfg.DATA.BBOX_STD_DEV, [1, 1, 4])).float()
+    d_trim = torch.stack([(deltas * std)[i][order[i]] for i in range(bs)])
+    a_trim = torch.stack([anchors[order[i]] for i in range(bs)])
+    want = pyref.apply_box_deltas_ref(a_trim, d_trim)
+    want = torch.stack([want[:, :, 0].clamp(0.0, hw[0]), want[:, :, 1].clamp(0.0, hw[1]), want[:, :, 2].clamp(0.0, hw[0]), want[:, :, 3].clamp(0.0, hw[1])], 2)
+    np.testing.assert_allclose(boxes.cpu().numpy(), want.numpy(), rtol=2e-6, atol=1e-3)
+    b = boxes.cpu()
+    assert torch.equal(dets.cpu(), torch.cat((b[:, :, [1, 0, 3, 2]], scores_s.unsqueeze(2)), 2))
+    # end to end
+    got = fi.proposal_layer([probs.cuda(), deltas.cuda()], count, 0.7, anchors.cuda(), cfg).cpu()
+    keep = pyref.nms_ref(torch.cat((b, scores_s.unsqueeze(2)), 2), 0.7, strict=True)[:, :count].astype(np.int64)
+    exp = torch.stack([b[i][torch.from_numpy(keep[i])] for i in range(bs)]) / torch.tensor([hw[0], hw[1], hw[0], hw[1]], dtype=torch.float32)
+    assert tuple(got.shape) == tuple(exp.shape)
+    assert torch.equal(got, exp)
+    # and the whole restatement agrees whenever no suppression decision sits within rounding of the threshold
+    ref, _ = pyref.proposal_layer_ref([probs, deltas], count, 0.7, anchors, cfg)
+    if tuple(ref.shape) == tuple(got.shape):
+        assert (got - ref).abs().max() < 1e-5 or (got - ref).abs().median() < 1e-6

@@ -180,3 +180,32 @@ def test_dev_restatement_runs_and_scatter_order():
             fm = dev.upsample[0](maps[l])
             want = pyref.crop_and_resize_ref(fm, rois[b, r][None], torch.tensor([b], dtype=torch.int32), 7, 7)
             torch.testing.assert_close(po[b * 40 + r], want[0])
+
+
+def test_proposal_layer_restatement_known_answers():
+    """oracle/pyref.py::proposal_layer_ref (lib/layers.py:71-139): the reference's layer cannot be imported (its NMS extension
+    cannot be built), so the restatement is pinned by known answers: zero deltas return the clipped anchors in score order;
+    disjoint anchors are all kept; duplicates are suppressed; the batch is truncated to its smallest keep count."""
+    cfg = pyref.make_config(DATA__IMAGE_SHAPE=np.array([100, 200, 3]), RPN__PRE_NMS_LIMIT=6)
+    anchors = torch.tensor([[0, 0, 10, 10], [20, 20, 40, 40], [50, 150, 120, 260], [0, 0, 10, 10], [60, 10, 80, 30], [70, 70, 90, 90],
+                            [5, 5, 6, 6]], dtype=torch.float32)
+    A = anchors.size(0)
+    probs = torch.zeros(2, A, 2)
+    probs[0, :, 1] = torch.tensor([0.9, 0.8, 0.7, 0.6, 0.5, 0.4, 0.1])
+    probs[1, :, 1] = torch.tensor([0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7])
+    deltas = torch.zeros(2, A, 4)
+    out, keep = pyref.proposal_layer_ref([probs, deltas], 5, 0.7, anchors, cfg)
+    # image 0: top-6 = anchors 0..5; anchor 3 duplicates anchor 0 -> suppressed; 5 kept, in score order
+    # image 1: top-6 = anchors 6,5,4,3,2,1 (anchor 0 is cut by PRE_NMS_LIMIT) -> all disjoint, 6 kept; batch minimum = 5
+    assert tuple(out.shape) == (2, 5, 4)
+    assert keep[0].tolist() == [0, 1, 2, 4, 5] and keep[1].tolist() == [0, 1, 2, 3, 4]
+    norm = torch.tensor([100.0, 200.0, 100.0, 200.0])
+    np.testing.assert_allclose(out[0, 2].numpy(), (torch.tensor([50.0, 150.0, 100.0, 200.0]) / norm).numpy())   # clipped to the window
+    np.testing.assert_allclose(out[1, 0].numpy(), (anchors[6] / norm).numpy())
+    # deltas: (dy, dx) shift by delta * std * size, (dh, dw) scale by exp(delta * std)
+    deltas2 = torch.zeros(1, A, 4)
+    deltas2[0, 1] = torch.tensor([1.0, -1.0, np.log(2.0) / 0.2, 0.0])
+    out2, _ = pyref.proposal_layer_ref([probs[:1], deltas2], 5, 0.7, anchors, cfg)
+    cy, cx, h, w = 30 + 0.1 * 20, 30 - 0.1 * 20, 40.0, 20.0
+    want = torch.tensor([cy - h / 2, cx - w / 2, cy + h / 2, cx + w / 2]) / norm
+    np.testing.assert_allclose(out2[0, 1].numpy(), want.numpy(), rtol=1e-5)
