@@ -5,22 +5,23 @@
 // The vector-reduction rewrite of that formulation (roi_align.cu) is bound by L2 reduction throughput (~3.5 TB/s of
 // RED payload, ~5 GB per C2 step) plus a 1.5 GB zero fill -- 37 % of the HBM roofline.  Here the only HBM traffic is
 // the algorithmic one: every crop gradient is read (once, plus re-reads by neighbouring tiles that L2 absorbs) and
-// every map pixel is written once; no memset, no atomics, no read-modify-write in L2/HBM (ncu: 4.17 GB for 4.06 GB).
+// every map pixel is written once; no memset, no atomics, no read-modify-write in L2/HBM (ncu: 4.40 GB for 4.06 GB).
 //
-// Launches: prep (thread per box: footprint bounds, per-image index range, list of degenerate boxes), collapse
-// (degenerate boxes only, see below), tile kernel.
+// Launches of one backward (all crop sets / maps of a Dev.forward pass): tile_prep (thread per box: sample geometry,
+// footprint bounds, per-image index range, list of degenerate boxes) -> tile_collapse (degenerate boxes only, see below)
+// -> bin_enumerate + bin_accumulate (default), or the fused bwd_smem_tile_kernel (FI_BWD_TILE=fused).
 //
-// Tile kernel.  CTA = 2 warps = one tile x two 128-channel slabs; the warps never synchronise with each other (each owns
-// its slab of the tile in shared memory).  Per warp, per crop set of the map:
-//   scan     the boxes of the tile's image (index range from prep), 32 at a time: one 16 B record (bounds, image) +
-//            the box + its gradient row per lane, loads of the next chunk in flight while this one is expanded;
-//   expand   per hit box (ballot order = box order) the box is broadcast by shuffle and the lanes recompute its taps
-//            (lanes 0-15 = y taps, 16-31 = x taps, same device function as the forward); two ballots give the crop rows /
-//            columns that touch the tile; lanes then describe the samples of that rectangle in parallel (tap offsets,
-//            in-tile flags, lerp weights, gradient row) and append the ones with at least one tap inside the tile to a
-//            per-warp queue -- in (box, crop row, crop column) order.  No memory access on this path;
-//   drain    the queue is consumed in order, 8 (4 for two-source sets) 512-byte gradient loads in flight ahead of the
-//            adds (double-buffered in registers); each tap is one conflict-free LDS.128 / add / STS.128;
+// What a tile's work consists of (both forms; the two-kernel form splits it after "expand", see further down):
+//   scan     the boxes of the tile's image (index range from prep), 32 at a time: one 16 B record (bounds, image) per lane,
+//            footprint-bounds test, ballot-compacted IN BOX ORDER into a hit list; next chunk's records in flight;
+//   expand   a batch of up to 32 hit boxes, lane i <-> box i: each lane loads its box's geometry record and finds the crop
+//            rows / columns whose taps touch the tile (positions are monotone: contiguous ranges); a warp scan of the
+//            rectangle sizes orders the batch's samples as one (box, crop row, crop column) stream; lane l then describes
+//            sample g0 + l of that stream (binary search of its box by shuffle, taps from the geometry with the forward's
+//            fp32 operations, in-tile flags, pre-multiplied tap weights, gradient row) and appends it to the queue;
+//   drain    the queue is consumed in order, gradient rows requested into L2 a window ahead, 8 512-byte loads in flight
+//            ahead of the adds (double-buffered in registers); each tap is one conflict-free LDS.128 / add / STS.128 on
+//            the warp's 16 KB accumulator (tile x 128-channel slab);
 //   store    the tile is streamed out, 512 B per warp instruction.
 // Because every pixel is summed by ONE warp in the order (box, crop row, crop column, TL->TR->BL->BR) the result is
 // run-to-run deterministic; with EXACT arithmetic (un-fused fp32 mul then add, crop_and_resize.c:241-247) it is
