@@ -376,7 +376,7 @@ template <bool EXACT, int TY, int TX, int MINB>
 __global__ void __launch_bounds__(64, MINB) bwd_smem_tile_kernel(const TParams P) {
     __shared__ WarpSmemT<TY, TX> smem[2];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    int t = blockIdx.x, mi = 0;
+    int t = (int)gridDim.x - 1 - (int)blockIdx.x, mi = 0;          // heaviest (coarsest-level) tiles first, see bin_accumulate_kernel
     while (mi + 1 < P.nmaps && t >= P.m[mi + 1].first_tile) ++mi;
     const TMap &M = P.m[mi];
     const int H = M.H, W = M.W, C = M.C;
@@ -591,8 +591,8 @@ template <bool EXACT, int TY, int TX>
 __global__ void __launch_bounds__(128) bin_enumerate_kernel(const TParams P) {
     __shared__ EnumSmem smem[4];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int tile_id = blockIdx.x * 4 + w;
-    if (tile_id >= P.bin.total_tiles) return;          // warps never synchronise with each other
+    if ((int)blockIdx.x * 4 + w >= P.bin.total_tiles) return;      // warps never synchronise with each other
+    const int tile_id = P.bin.total_tiles - 1 - ((int)blockIdx.x * 4 + w);   // heaviest (coarsest-level) tiles first, see bin_accumulate_kernel
     int t = tile_id, mi = 0;
     while (mi + 1 < P.nmaps && t >= P.m[mi + 1].first_tile) ++mi;
     const TMap &M = P.m[mi];
@@ -797,7 +797,10 @@ __global__ void __launch_bounds__(64, MINB) bin_accumulate_kernel(const TParams 
         srcs[threadIdx.x] = which == 0 ? S.grads : which == 1 ? S.grads2 : S.coll;
     }
     __syncthreads();                                   // the only CTA-wide synchronisation
-    const int tile_id = blockIdx.x;
+    // Heaviest tiles first: callers list the maps from the finest pyramid level to the coarsest, and a tile of a coarse map
+    // collects ~10x the samples of a fine one (C2: ~700 queue entries per P5 tile against ~60 per P2 tile).  In launch order
+    // those few hundred long tiles would run last, a handful of warps per SM; reversed they overlap with the short ones.
+    const int tile_id = P.bin.total_tiles - 1 - (int)blockIdx.x;
     int t = tile_id, mi = 0;
     while (mi + 1 < P.nmaps && t >= P.m[mi + 1].first_tile) ++mi;
     const TMap &M = P.m[mi];
