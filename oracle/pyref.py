@@ -379,18 +379,16 @@ def nms_ref(dets, thresh, strict=True):
 
 # =============================================================================== proposal layer
 def apply_box_deltas_ref(boxes, deltas):
-    """tools/box_utils.py:7-29 (out-of-place: the in-place updates there act on temporaries)."""
-    height = boxes[:, :, 2] - boxes[:, :, 0]
-    width = boxes[:, :, 3] - boxes[:, :, 1]
-    center_y = boxes[:, :, 0] + 0.5 * height
-    center_x = boxes[:, :, 1] + 0.5 * width
-    center_y = center_y + deltas[:, :, 0] * height
-    center_x = center_x + deltas[:, :, 1] * width
-    height = height * torch.exp(deltas[:, :, 2])
-    width = width * torch.exp(deltas[:, :, 3])
-    y1 = center_y - 0.5 * height
-    x1 = center_x - 0.5 * width
-    return torch.stack([y1, x1, y1 + height, x1 + width], dim=2)
+    """Box refinement of tools/box_utils.py:7-29, restated: corners -> (centre, size), centre shifted by delta * size, size
+    scaled by exp(delta), back to corners.  The order of the fp32 operations is the reference's (one rounding per torch op)."""
+    y1, x1, y2, x2 = boxes.unbind(dim=2)
+    dy, dx, dh, dw = deltas.unbind(dim=2)
+    h, w = y2 - y1, x2 - x1                                  # :14-15
+    cy = (y1 + 0.5 * h) + dy * h                             # :16,19
+    cx = (x1 + 0.5 * w) + dx * w                             # :17,20
+    h, w = h * torch.exp(dh), w * torch.exp(dw)              # :21-22
+    top, left = cy - 0.5 * h, cx - 0.5 * w                   # :24-25
+    return torch.stack([top, left, top + h, left + w], dim=2)   # :26-28
 
 
 def proposal_layer_ref(inputs, proposal_count, nms_threshold, priors, config):
