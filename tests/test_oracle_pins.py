@@ -209,3 +209,17 @@ def test_proposal_layer_restatement_known_answers():
     cy, cx, h, w = 30 + 0.1 * 20, 30 - 0.1 * 20, 40.0, 20.0
     want = torch.tensor([cy - h / 2, cx - w / 2, cy + h / 2, cx + w / 2]) / norm
     np.testing.assert_allclose(out2[0, 1].numpy(), want.numpy(), rtol=1e-5)
+
+
+def test_cpu_baseline_extrapolation_does_not_depend_on_the_sample_size():
+    """bench.py::cpu_reference times a SAMPLE of every RoIAlign call and scales it to the full step: per-box work is scaled by
+    the sampling factor, the per-call allocation / zero fill of the dense gradient map is counted once.  (Scaling both
+    under-stated the reference by 2.2x on C2.)  On the small C1 workload a 1/3 sample and the full set must agree."""
+    import bench
+    from feature_intertwiner_b200 import synth
+    wl = synth.WORKLOADS["c1"]
+    small = bench.cpu_reference(wl, seed=2000, budget_s=1.5)
+    full = bench.cpu_reference(wl, seed=2000, budget_s=60.0)
+    assert full["cores"] >= 1 and full["kind"] in ("reference", "port") and "OT loss" in full["sample"]
+    ratio = small["roialign_s_full_step"] / full["roialign_s_full_step"]
+    assert 0.4 < ratio < 2.5, (small["sample"], full["sample"])
