@@ -1032,7 +1032,8 @@ int fi_tile_backward(const fi_bwd_set *sets, int num_sets, int accumulate, int e
     const long lists = tiles;
     long entries_bound = 0;
     for (int i = 0; i < P.nsets; ++i) entries_bound += 4L * P.s[i].R * P.s[i].ph * P.s[i].pw * (P.s[i].grads2 ? 2 : 1) + 8L * 4 * P.s[i].R;
-    const long pool = entries_bound / kChunk + lists + 8;
+    // + one partly filled chunk per tile, + one more for the (<= 7 + one per set) tap-less padding entries a tile may add
+    const long pool = entries_bound / kChunk + 2 * lists + 8;
     if (pool >= (1L << 31) / kChunk) binned = false;
     size_t bytes = range_bytes + list_bytes;
     for (int i = 0; i < P.nsets; ++i) {
