@@ -34,10 +34,11 @@
 // therefore pre-reduced by the collapse kernel (one CTA per box, all warps loading in parallel) into 4 corner sums
 // that the tile kernel consumes as 4 unit-weight samples.  EXACT mode keeps the reference's sample-by-sample order.
 #include <stdlib.h>
+#include <string.h>
 
 #include <mutex>
 
-#include "fi_common.cuh"
+#include "roi_align_bwd_tile.cuh"
 
 #ifndef FI_SCAN_DEPTH
 #define FI_SCAN_DEPTH 1     // chunks of box records in flight ahead of the scan (3 measured 1.58 ms vs 1.52 ms: register pressure)
@@ -48,63 +49,6 @@
 
 namespace fi {
 namespace tile {
-
-constexpr int kQ = 64;                             // per-warp sample queue
-constexpr int kMaxCrop = 16;                       // crop_h, crop_w <= 16 (the model uses 7 and 14)
-constexpr int kNoTap = -32768;
-constexpr int kMaxSets = 12, kMaxMaps = 8;
-
-struct TSet {
-    const float *grads, *grads2;
-    const float4 *boxes;
-    const int *box_ind, *src_row;
-    int4 *rec;                         // [R] (ymin | ymax << 16, xmin | xmax << 16, image or -1, degenerate)
-    float4 *geom;                      // [R] (y of sample row 0, y step, x of sample column 0, x step) in pixels
-    unsigned *range;                   // [B,2]: min box index of image b, ~(max box index); memset 0xFF = "none"
-    float *coll;                       // [R,4,C] corner sums of degenerate boxes (only those rows are written)
-    int R, ph, pw, map;
-};
-struct TMap {
-    float *gimg;
-    int B, H, W, C, tiles_x, tiles_y, first_tile, set_begin, set_end;
-};
-struct BinWs {                         // per-tile sample lists of the two-kernel form (enumerate -> accumulate)
-    int *tile_head;                    // [tiles] first chunk of the tile's list
-    int *tile_n;                       // [tiles] entries in the list (a multiple of 8)
-    int *chunk_next;                   // [pool]  chunk -> next chunk of the same tile
-    uint2 *qa;                         // [pool * 64] (gradient row, pk2)
-    float4 *qw;                        // [pool * 64] tap weights
-    int *cursor;                       // [1] chunks handed out
-    int pool, total_tiles;
-};
-struct TParams {
-    TSet s[kMaxSets];
-    TMap m[kMaxMaps];
-    int *deg_list;                     // [0] = count, then (set << 24 | box) entries
-    BinWs bin;
-    int nsets, nmaps, accumulate, collapse;
-};
-
-struct Tap {                           // one axis tap as the tile kernel uses it
-    int lo, hi;                        // kNoTap when the sample is outside the image
-    float frac;
-};
-// One axis tap from the per-box geometry record (base, step): the same fp32 operations as fi_common.cuh::axis_sample.
-__device__ __forceinline__ Tap geom_tap(float base, float step, int k, int extent) {
-    const float pos = __fadd_rn(base, __fmul_rn((float)k, step));
-    Tap t;
-    t.lo = kNoTap; t.hi = kNoTap; t.frac = 0.f;
-    if (!(pos < 0.f || pos > (float)(extent - 1))) {
-        t.lo = (int)floorf(pos);
-        t.hi = (int)ceilf(pos);
-        t.frac = __fsub_rn(pos, (float)t.lo);
-    }
-    return t;
-}
-__device__ __forceinline__ float geom_base(float c1, float c2, int extent, int crop) {      // crop_and_resize.c:52-56
-    if (crop > 1) return __fmul_rn(c1, (float)(extent - 1));
-    return (float)(0.5 * (double)__fadd_rn(c1, c2) * (double)(extent - 1));
-}
 
 // ---- prep: one thread per box (all sets in one launch): footprint bounds, per-image index range, degenerate list ----
 __global__ void __launch_bounds__(128) tile_prep_kernel(const TParams P) {
@@ -138,29 +82,6 @@ __global__ void __launch_bounds__(128) tile_prep_kernel(const TParams P) {
         if (degenerate && P.collapse) P.deg_list[1 + atomicAdd(P.deg_list, 1)] = ((int)blockIdx.y << 24) | r;
     }
     S.rec[r] = rec;
-}
-
-// ---- arithmetic -----------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float4 add_rn4(float4 a, float4 b) {
-    return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
-}
-__device__ __forceinline__ float4 mul_rn4(float w, float4 a) {
-    return make_float4(__fmul_rn(w, a.x), __fmul_rn(w, a.y), __fmul_rn(w, a.z), __fmul_rn(w, a.w));
-}
-// a + g * w on two packed pairs (FFMA2)
-__device__ __forceinline__ float4 fma4(float4 g, float w, float4 a) {
-    unsigned long long g0, g1, a0, a1, ww, r0, r1;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(g0) : "f"(g.x), "f"(g.y));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(g1) : "f"(g.z), "f"(g.w));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(a0) : "f"(a.x), "f"(a.y));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(a1) : "f"(a.z), "f"(a.w));
-    asm("mov.b64 %0, {%1, %1};" : "=l"(ww) : "f"(w));
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r0) : "l"(g0), "l"(ww), "l"(a0));
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r1) : "l"(g1), "l"(ww), "l"(a1));
-    float4 r;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(r0));
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.z), "=f"(r.w) : "l"(r1));
-    return r;
 }
 
 // ---- collapse: corner sums of degenerate boxes (footprint <= 2x2 pixels), one CTA per box -------------------------
@@ -577,8 +498,6 @@ __global__ void __launch_bounds__(64, MINB) bwd_smem_tile_kernel(const TParams P
 // accumulation in the reference.  Every set's segment is padded to a multiple of 8 entries so pairs never straddle a group.
 // pk2: tap flags (bits 0-3), kDefer2 (bit 4), source index 3 * set + {grads, grads2, collapse rows} (bits 5-10),
 //      TL pixel index inside the tile, signed (bits 11..).
-constexpr int kDefer2 = 1 << 4;
-constexpr int kChunk = 64;
 
 struct __align__(16) EnumSmem {
     float4 qw[kChunk];
@@ -961,18 +880,39 @@ char *workspace(size_t bytes, cudaStream_t stream) {
 }
 }  // namespace
 
+// Experiment switches, read from the environment ONCE per process (not per launch):
+//   FI_TILE=4x8|4x4|2x8   tile shape of the shared-memory accumulate kernels (default 4x8)
+//   FI_BWD_TILE=fused     single-kernel form (scan + expand + accumulate in one kernel)
+//   FI_BWD_ACC=smem       shared-memory accumulate kernel (bin_accumulate_kernel) instead of the bulk-copy staged,
+//                         register-accumulating one (roi_align_bwd_pix.cu, default for 4x8 tiles)
+namespace {
+struct TileEnv { int ty, tx; bool fused, smem_acc; };
+const TileEnv &tile_env() {
+    static const TileEnv env = [] {
+        TileEnv e{4, 8, false, false};
+        const char *shape = getenv("FI_TILE");
+        if (shape && !strcmp(shape, "4x4")) { e.ty = 4; e.tx = 4; }
+        if (shape && !strcmp(shape, "2x8")) { e.ty = 2; e.tx = 8; }
+        const char *form = getenv("FI_BWD_TILE");
+        e.fused = form && form[0] == 'f';
+        const char *acc = getenv("FI_BWD_ACC");
+        e.smem_acc = acc && acc[0] == 's';
+        return e;
+    }();
+    return env;
+}
+}  // namespace
+
+namespace fi { namespace tile { int pix_accumulate(const TParams &P, int exact, cudaStream_t stream); } }   // roi_align_bwd_pix.cu
+
 // Host side.  Returns FI_ERR_UNSUPPORTED (nothing touched) when the sets do not qualify so that the caller can use the
 // reduction kernels.  exact != 0: arithmetic and order of crop_and_resize.c:190-250 (bit-identical for one set per map).
 int fi_tile_backward(const fi_bwd_set *sets, int num_sets, int accumulate, int exact, cudaStream_t stream) {
     if (num_sets < 1 || num_sets > kMaxSets) return FI_ERR_UNSUPPORTED;
     // tile shape: 4 rows x 8 pixels by default (a tile row is 8 KB contiguous in NHWC, C = 256); FI_TILE=4x4 / 2x8 halve the
     // shared memory per warp (more resident warps, more neighbour re-reads) -- kept for measurements
-    int TYs = 4, TXs = 8;
-    {
-        const char *shape = getenv("FI_TILE");
-        if (shape && shape[0] == '4' && shape[2] == '4') { TYs = 4; TXs = 4; }
-        if (shape && shape[0] == '2' && shape[2] == '8') { TYs = 2; TXs = 8; }
-    }
+    const TileEnv &env = tile_env();
+    const int TYs = env.ty, TXs = env.tx;
     TParams P;
     P.nsets = 0; P.nmaps = 0; P.accumulate = accumulate ? 1 : 0; P.collapse = exact ? 0 : 1;
     // group the sets by map, maps in order of first appearance
@@ -1021,14 +961,10 @@ int fi_tile_backward(const fi_bwd_set *sets, int num_sets, int accumulate, int e
         max_R = max_R > P.s[i].R ? max_R : P.s[i].R;
         total_R += P.s[i].R;
     }
-    const size_t list_bytes = up16((size_t)(1 + total_R) * sizeof(int)) + 16;      // [degenerate count + list | chunk cursor]
+    const size_t list_bytes = up16((size_t)(1 + total_R) * sizeof(int)) + 16 + 128;   // [degenerate count + list | chunk cursor | 32 tile counters]
     // two-kernel form (default): per-tile sample lists in 64-entry chunks.  A sample's taps lie in at most 2x2 tiles, two-source
     // sets queue two entries per sample, every tile may leave one chunk partly filled.  FI_BWD_TILE=fused: single kernel.
-    bool binned = true;
-    {
-        const char *form = getenv("FI_BWD_TILE");
-        if (form && form[0] == 'f') binned = false;
-    }
+    bool binned = !env.fused;
     const long lists = tiles;
     long entries_bound = 0;
     for (int i = 0; i < P.nsets; ++i) entries_bound += 4L * P.s[i].R * P.s[i].ph * P.s[i].pw * (P.s[i].grads2 ? 2 : 1) + 8L * 4 * P.s[i].R;
@@ -1046,7 +982,7 @@ int fi_tile_backward(const fi_bwd_set *sets, int num_sets, int accumulate, int e
     cudaError_t e;
     e = cudaMemsetAsync(ws, 0xFF, range_bytes, stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(ws + range_bytes, 0, sizeof(int), stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(ws + range_bytes + list_bytes - 16, 0, sizeof(int), stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ws + range_bytes + list_bytes - 144, 0, 144, stream);
     if (e != cudaSuccess) { set_error(FI_ERR_CUDA, "crop backward: memset: %s", cudaGetErrorString(e)); return FI_ERR_CUDA; }
     char *p = ws;
     for (int i = 0; i < P.nsets; ++i) {
@@ -1054,7 +990,8 @@ int fi_tile_backward(const fi_bwd_set *sets, int num_sets, int accumulate, int e
         p += up16((size_t)P.m[P.s[i].map].B * 2 * sizeof(unsigned));
     }
     P.deg_list = reinterpret_cast<int *>(p);
-    P.bin.cursor = reinterpret_cast<int *>(p + list_bytes - 16);
+    P.bin.cursor = reinterpret_cast<int *>(p + list_bytes - 144);
+    P.bin.work = reinterpret_cast<int *>(p + list_bytes - 128);
     p += list_bytes;
     for (int i = 0; i < P.nsets; ++i) {
         P.s[i].rec = reinterpret_cast<int4 *>(p);
@@ -1099,7 +1036,24 @@ int fi_tile_backward(const fi_bwd_set *sets, int num_sets, int accumulate, int e
             rc = check_launch("crop backward[accumulate]");                                                   \
         }                                                                                                     \
     } while (0)
-        if (TXs == 8 && TYs == 4) FI_BIN_LAUNCH(4, 8, 8, 6);
+        bool done = false;
+        if (TXs == 8 && TYs == 4 && !env.smem_acc) {             // default: bulk-copy staged, register-accumulating kernel
+            if (exact) bin_enumerate_kernel<true, 4, 8><<<egrid, 128, 0, stream>>>(P);
+            else bin_enumerate_kernel<false, 4, 8><<<egrid, 128, 0, stream>>>(P);
+            rc = check_launch("crop backward[enumerate]");
+            if (rc == FI_OK) {
+                rc = pix_accumulate(P, exact, stream);
+                done = rc != FI_ERR_UNSUPPORTED;                 // (mixed channel counts: the shared-memory kernel takes it, lists are ready)
+                if (!done) {
+                    if (exact) bin_accumulate_kernel<true, 4, 8, 8, 6><<<grid, 64, 0, stream>>>(P);
+                    else bin_accumulate_kernel<false, 4, 8, 8, 6><<<grid, 64, 0, stream>>>(P);
+                    rc = check_launch("crop backward[accumulate]");
+                    done = true;
+                }
+            } else done = true;
+        }
+        if (done) {}
+        else if (TXs == 8 && TYs == 4) FI_BIN_LAUNCH(4, 8, 8, 6);
         else if (TXs == 4) FI_BIN_LAUNCH(4, 4, 4, 10);
         else FI_BIN_LAUNCH(2, 8, 4, 10);
 #undef FI_BIN_LAUNCH

@@ -7,6 +7,12 @@
 * nms.npz         outputs of lib/nms/src/nms.c compiled unmodified (oracle/_ref)
 * sinkhorn.npz    outputs of lib/OT_module.py::OptTrans._sinkhorn_iterate, module imported as-is
 * opttrans.npz    outputs of lib/OT_module.py::OptTrans.forward (1-D and 2-D), weights included
+* intertwiner.npz outputs of the reference's own Python bodies on the path, cut out of the source with `ast` and
+                  exec'd unmodified under a PyTorch-0.3 behaviour shim (tests/golden/ref_exec.py): the level rule
+                  (lib/sub_module.py:397-410 and its twin lib/layers.py:168-181), tools/utils.py unique1d / log2,
+                  Dev._assign_feat2cls (lib/sub_module.py:664-684), MaskRCNN._merge_feat_vec / meta_loss /
+                  _assign_from_buffer (lib/model.py:143-224; buffer sizes 1 and 3, l2 / l1 / ot, class- and
+                  instance-level, three consecutive iterations), tools/box_utils.py apply_box_deltas / clip_boxes
 
 The only liberty taken with lib/OT_module.py is neutralising ``Tensor.cuda`` (hard-coded at
 OT_module.py:118-119) because this container has no GPU; inputs are cloned before the call because the
@@ -113,6 +119,120 @@ def opttrans_cases(mod):
     np.savez_compressed(os.path.join(HERE, "opttrans.npz"), **out)
 
 
+def intertwiner_cases(ot_mod):
+    """Everything below runs the reference's own source text (see ref_exec.py); only the inputs are ours."""
+    sys.path.insert(0, HERE)
+    import ref_exec as rx
+    out, cited = {}, {}
+    g = torch.Generator().manual_seed(2000)
+    ns = rx.load_functions([("tools/utils.py", "unique1d", None), ("tools/utils.py", "log2", None),
+                            ("lib/sub_module.py", "_assign_feat2cls", "Dev"),
+                            ("lib/model.py", "_merge_feat_vec", "MaskRCNN"), ("lib/model.py", "_assign_from_buffer", "MaskRCNN"),
+                            ("lib/model.py", "meta_loss", "MaskRCNN"),
+                            ("tools/box_utils.py", "apply_box_deltas", None), ("tools/box_utils.py", "clip_boxes", None)])
+    cited.update(ns["__cited__"])
+
+    # ---- level rule: inline code of Dev.forward (lib/sub_module.py:396-410) and of pyramid_roi_align (lib/layers.py:167-181)
+    from feature_intertwiner_b200 import synth
+    level_src = {"dev": ("lib/sub_module.py", 397, 410), "pyramid": ("lib/layers.py", 168, 181)}
+    for tag, hw, bs, R in (("c1", (256, 256), 4, 64), ("c2", (832, 1344), 8, 512), ("sq", (1024, 1024), 2, 300)):
+        rois = synth.make_rois(bs, R, hw, g)
+        # level boundaries: squares whose side is 224 * 2^(k - 4 +- 1/2) * (1 +- tiny) pixels, k = 2..5
+        edge = []
+        for k in (2.5, 3.5, 4.5):
+            for rel in (-3e-7, -1e-7, 0.0, 1e-7, 3e-7):
+                s = 224.0 * 2.0 ** (k - 4) * (1 + rel)
+                edge.append([0.1, 0.1, 0.1 + s / hw[0], 0.1 + s / hw[1]])
+        rois[0, :len(edge)] = torch.tensor(edge)
+        out["level_%s_rois" % tag] = rois.numpy().copy()
+        out["level_%s_image_shape" % tag] = np.array([hw[0], hw[1], 3])
+        for which, (rel, a, b) in level_src.items():
+            with rx.torch03():
+                cfgobj = types.SimpleNamespace(DEV=types.SimpleNamespace(ASSIGN_BOX_ON_ALL_SCALE=False))
+                self_ = types.SimpleNamespace(config=cfgobj, image_shape=np.array([hw[0], hw[1], 3]))
+                loc = dict(ns, rois=rois.clone(), boxes=rois.clone(), self=self_, base=224.0, image_shape=np.array([hw[0], hw[1], 3]),
+                           inputs=[rois.clone()])
+                exec(compile(rx.extract_lines(rel, a, b), rel, "exec"), loc)
+                out["level_%s_%s" % (tag, which)] = loc["roi_level"].numpy().astype(np.int32)
+            cited["level_rule_" + which] = "%s:%d-%d" % (rel, a, b)
+        assert np.array_equal(out["level_%s_dev" % tag], out["level_%s_pyramid" % tag])
+
+    # ---- unique1d / log2
+    with rx.torch03():
+        v = torch.randint(0, 81, (300,), generator=g)
+        out["unique_in"], out["unique_out"] = v.numpy(), ns["unique1d"](v.clone()).numpy()
+        x = torch.rand(1000, generator=g) * 8 + 1e-3
+        out["log2_in"], out["log2_out"] = x.numpy(), ns["log2"](x.clone()).numpy()
+
+    # ---- _assign_feat2cls (feat given as [k,1024]: the [k,1024,1,1] form of the caller cannot be slice-assigned on torch 2.x)
+    self_ = types.SimpleNamespace(num_classs=81)
+    for tag, k in (("a", 1), ("b", 37), ("c", 500)):
+        gt = torch.randint(0, 81, (k,), generator=g)
+        gt[: k // 3] = 0
+        feat = torch.rand(k, 1024, generator=g)
+        with rx.torch03():
+            f, c = ns["_assign_feat2cls"](self_, [gt.clone(), feat.clone()])
+        out["seg_%s_gt" % tag], out["seg_%s_feat" % tag] = gt.numpy().astype(np.int32), feat.numpy()
+        out["seg_%s_mean" % tag], out["seg_%s_cnt" % tag] = f.numpy(), c.numpy()
+
+    # ---- _merge_feat_vec + meta_loss over three iterations
+    torch.manual_seed(2000)
+    cfg_ot = types.SimpleNamespace(DEV=types.SimpleNamespace(OT_ONE_DIM_FORM="conv"))
+    ot = ot_mod.OptTrans(cfg_ot, ch_x=1024, L=5).eval()
+    for k, v in ot.state_dict().items():
+        out["meta_ot_sd_" + k] = v.numpy()
+
+    def stats(G, S, density):
+        cnt = (torch.rand(G, S, 1, 81, generator=g) < density).float() * torch.randint(1, 9, (G, S, 1, 81), generator=g).float()
+        feat = torch.rand(G, S, 1024, 81, generator=g) * (cnt > 0).float()
+        return feat, cnt
+
+    f, c = stats(2, 3, 0.5)
+    with rx.torch03():
+        mf, mc = ns["_merge_feat_vec"](f.clone(), c.clone())
+    out["merge_feat"], out["merge_cnt"], out["merge_out_feat"], out["merge_out_cnt"] = f.numpy(), c.numpy(), mf.numpy(), mc.numpy()
+
+    for B in (1, 3):
+        for lc in ("l2", "l1", "ot"):
+            for inst in (False, True):
+                if inst and lc == "ot":
+                    continue            # 3 x n Sinkhorn problems per instance: covered at class level
+                tag = "meta_B%d_%s_%s" % (B, lc, "inst" if inst else "cls")
+                model = types.SimpleNamespace(
+                    config=types.SimpleNamespace(DEV=types.SimpleNamespace(INST_LOSS=inst, LOSS_CHOICE=lc)),
+                    buffer=torch.zeros(B, 1024, 81), buffer_cnt=torch.zeros(B, 1, 81), ot_loss=ot)
+                model._merge_feat_vec = ns["_merge_feat_vec"]
+                model._assign_from_buffer = ns["_assign_from_buffer"]
+                for it in range(3):
+                    bf, bc = stats(1, 3, 0.3 if it == 0 else 0.6)
+                    sf, sc = stats(1, 3, 0.4)
+                    n_inst = 40
+                    so = torch.rand(n_inst, 1024, generator=g)
+                    sg = torch.randint(0, 81, (n_inst,), generator=g)
+                    sg[::3] = 0
+                    with rx.torch03(), torch.no_grad():
+                        loss = ns["meta_loss"](model, [bf.clone(), bc.clone(), sf.clone(), sc.clone(), so.clone(), sg.clone()])
+                    pre = "%s_it%d_" % (tag, it)
+                    for name, t in (("big_feat", bf), ("big_cnt", bc), ("small_feat", sf), ("small_cnt", sc), ("small_out", so), ("small_gt", sg)):
+                        out[pre + name] = t.numpy()
+                    out[pre + "loss"] = loss.detach().numpy().reshape(-1)
+                    out[pre + "buffer"], out[pre + "buffer_cnt"] = model.buffer.numpy().copy(), model.buffer_cnt.numpy().copy()
+    # empty comparison set -> zeros(1) (lib/model.py:208-209) is a known answer; torch 0.3's "empty tensor has no size" has no 2.x analogue
+
+    # ---- apply_box_deltas / clip_boxes (tools/box_utils.py, imported functions exec'd as they are)
+    anchors = torch.rand(2, 400, 4, generator=g) * 600
+    anchors[:, :, 2:] = anchors[:, :, :2] + torch.rand(2, 400, 2, generator=g) * 300 + 1
+    deltas = torch.randn(2, 400, 4, generator=g) * 0.3
+    window = torch.tensor([0.0, 0.0, 832.0, 1344.0])
+    with rx.torch03():
+        boxes = ns["apply_box_deltas"](anchors.clone(), deltas.clone())
+        clipped = ns["clip_boxes"](boxes.clone(), window.clone())
+    out["box_anchors"], out["box_deltas"], out["box_window"] = anchors.numpy(), deltas.numpy(), window.numpy()
+    out["box_applied"], out["box_clipped"] = boxes.numpy(), clipped.numpy()
+    out["cited"] = np.array(sorted("%s=%s" % kv for kv in cited.items()))
+    np.savez_compressed(os.path.join(HERE, "intertwiner.npz"), **out)
+
+
 if __name__ == "__main__":
     assert os.path.isdir(REF), "run in the build container (needs /root/reference)"
     clib.build(ref=True)
@@ -121,6 +241,7 @@ if __name__ == "__main__":
     ot = load_reference_ot()
     sinkhorn_cases(ot)
     opttrans_cases(ot)
+    intertwiner_cases(ot)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))
