@@ -2,7 +2,7 @@
 class-mean buffer -> L2 / Sinkhorn intertwiner loss) as hand-written sm_100a CUDA behind a C ABI
 (include/fi_b200.h), with the reference's own operator API on top.  See DESIGN.md.
 """
-from ._lib import FiError, lib, library_path  # noqa: F401
+from ._lib import FiError, get_option, lib, library_path, set_option  # noqa: F401
 from .roi_align import (CropAndResizeFunction, RoIAlign, crop_and_resize, crop_pair, crop_sets, crop_taps,  # noqa: F401
                         set_deterministic)
 from .roi_pool import RoIPoolFunction, _RoIPooling  # noqa: F401

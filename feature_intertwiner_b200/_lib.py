@@ -22,6 +22,8 @@ SIGNATURES = {
     "fi_last_error": (C.c_char_p, []),
     "fi_last_status": (_I, []),
     "fi_kernel_launches": (C.c_ulonglong, []),
+    "fi_set_option": (_I, [_I, _I]),
+    "fi_get_option": (_I, [_I]),
     "CropAndResizeLaucher": (None, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P]),
     "CropAndResizeBackpropImageLaucher": (None, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "ROIPoolForwardLaucher": (_I, [_P, _F, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
@@ -35,6 +37,10 @@ SIGNATURES = {
     "fi_get_deterministic": (_I, []),
     "fi_crop_sets_forward": (_I, [_P, _I, _P]),
     "fi_crop_sets_backward": (_I, [_P, _I, _I, _P]),
+    "fi_crop_sets_backward_workspace": (C.c_size_t, [_P, _I, _I, C.c_long]),
+    "fi_crop_sets_backward_plan": (_I, [_P, _I, _I, C.c_long, _P, C.c_size_t, _P, _P]),
+    "fi_crop_sets_backward_run": (_I, [_P, _P, _I, _I, _P]),
+    "fi_crop_sets_backward_overflow": (_I, [_P, _P]),
     "fi_crop_taps": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "fi_roi_level": (_I, [_P, _I, _F, _F, _P, _P]),
     "fi_split_levels": (_I, [_P, _I, _P, _P, _P, _P, _P, _P]),
@@ -60,14 +66,19 @@ class FwdSet(C.Structure):
     """struct fi_fwd_set."""
     _fields_ = [("image", _P), ("boxes", _P), ("box_ind", _P), ("dst_row", _P), ("crops", _P), ("crops_compact", _P),
                 ("batch", _I), ("image_height", _I), ("image_width", _I), ("depth", _I), ("num_boxes", _I),
-                ("crop_height", _I), ("crop_width", _I), ("extrapolation_value", _F)]
+                ("crop_height", _I), ("crop_width", _I), ("extrapolation_value", _F), ("num_boxes_dev", _P)]
 
 
 class BwdSet(C.Structure):
     """struct fi_bwd_set."""
     _fields_ = [("grads_image", _P), ("grads", _P), ("grads2", _P), ("boxes", _P), ("box_ind", _P), ("src_row", _P),
                 ("batch", _I), ("image_height", _I), ("image_width", _I), ("depth", _I), ("num_boxes", _I),
-                ("crop_height", _I), ("crop_width", _I)]
+                ("crop_height", _I), ("crop_width", _I), ("num_boxes_dev", _P)]
+
+
+class BwdPlan(C.Structure):
+    """struct fi_bwd_plan (opaque)."""
+    _fields_ = [("opaque", C.c_ulonglong * 640)]
 
 
 def lib():
@@ -117,6 +128,24 @@ def require_cuda(*tensors):
 
 FI_LAYOUT_NCHW = 0
 FI_LAYOUT_NHWC = 1
+
+# fi_set_option keys (include/fi_b200.h)
+OPTIONS = {"bwd_form": 0, "tile_shape": 1, "nchw_tma": 2, "sinkhorn_generic": 3, "pix_cfg": 4, "pix_group": 5}
+BWD_FORMS = {"pix": 0, "smem": 1, "fused": 2, "red": 3}
+
+
+def set_option(name, value):
+    """Process-wide kernel-selection switch (experiments / tests); returns the previous value."""
+    if isinstance(value, str):
+        value = BWD_FORMS[value]
+    old = lib().fi_set_option(OPTIONS[name], int(value))
+    if old < 0:
+        raise FiError("fi_set_option(%s, %s): %s" % (name, value, lib().fi_last_error().decode()))
+    return old
+
+
+def get_option(name):
+    return lib().fi_get_option(OPTIONS[name])
 
 
 def layout_of(t):

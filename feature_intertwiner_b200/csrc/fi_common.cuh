@@ -15,6 +15,7 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multi
 void set_error(int status, const char *fmt, ...);
 int ok();
 void count_launch();   // bumps the process-wide kernel-launch counter behind fi_kernel_launches()
+int option(int key);   // fi_get_option without the range check (FI_OPT_*)
 
 // Checks the launch that was just enqueued (no sync).
 inline int check_launch(const char *what) {

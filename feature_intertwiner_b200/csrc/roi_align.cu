@@ -396,7 +396,7 @@ static int forward_impl(const float *image, int image_layout, const float *boxes
         const bool vec = (C % 128 == 0) && (W <= 32768) && ((uintptr_t)image % 16 == 0) && ((uintptr_t)crops % 16 == 0) && ((uintptr_t)crops2 % 16 == 0);
         if (vec) {
             FwdSet S;
-            S.image = image; S.boxes = boxes; S.box_ind = box_ind; S.dst_row = dst_row; S.crops = crops; S.crops2 = crops2;
+            S.image = image; S.boxes = boxes; S.box_ind = box_ind; S.dst_row = dst_row; S.R_dev = nullptr; S.crops = crops; S.crops2 = crops2;
             S.B = B; S.H = H; S.W = W; S.C = C; S.ph = ph; S.pw = pw; S.slabs = C / 128; S.extrap = extrap;
             const long nunits = (long)R * ph * S.slabs;  // one warp per (crop row, 128-channel slab)
             const int grid = grid_for(nunits, kWarpsPerBlock, 8);
@@ -415,8 +415,7 @@ static int forward_impl(const float *image, int image_layout, const float *boxes
         if (crops2) { set_error(FI_ERR_UNSUPPORTED, "fi_crop_and_resize_forward_dual is NHWC only"); return FI_ERR_UNSUPPORTED; }
         {   // TMA-staged region tiles (roi_align_nchw_tma.cu) when the shape qualifies; opt-in (FI_NCHW_TMA=1): measured on
             // C2 it is 0-60 % slower than the L1-cached direct loads below (profiles/r01_microbench_c2_tma.json), so it is not the default
-            const char *mode = getenv("FI_NCHW_TMA");
-            if (mode && mode[0] == '1') {
+            if (option(FI_OPT_NCHW_TMA)) {
                 const int rc = fi_crop_forward_nchw_tma(image, boxes, box_ind, dst_row, R, B, H, W, ph, pw, C, extrap, crops, stream);
                 if (rc != FI_ERR_UNSUPPORTED) return rc;
             }
@@ -499,7 +498,7 @@ FI_API int fi_crop_sets_forward(const fi_fwd_set *sets, int num_sets, cudaStream
         if (!vec) { set_error(FI_ERR_UNSUPPORTED, "fi_crop_sets_forward: set %d needs NHWC, depth %% 128 == 0, 16-byte aligned tensors", i); return FI_ERR_UNSUPPORTED; }
         if (h.num_boxes == 0) continue;
         FwdSet &S = dev.s[dev.n];
-        S.image = h.image; S.boxes = h.boxes; S.box_ind = h.box_ind; S.dst_row = h.dst_row; S.crops = h.crops; S.crops2 = h.crops_compact;
+        S.image = h.image; S.boxes = h.boxes; S.box_ind = h.box_ind; S.dst_row = h.dst_row; S.R_dev = h.num_boxes_dev; S.crops = h.crops; S.crops2 = h.crops_compact;
         S.B = h.batch; S.H = h.image_height; S.W = h.image_width; S.C = h.depth; S.ph = h.crop_height; S.pw = h.crop_width;
         S.slabs = h.depth / 128; S.extrap = h.extrapolation_value;
         dev.first_unit[dev.n] = units;
@@ -524,11 +523,10 @@ FI_API int fi_crop_sets_backward(const fi_bwd_set *sets, int num_sets, int zero_
     }
     {   // Formulation.  Default: tile-owner kernels (roi_align_bwd_tile.cu) -- shared-memory accumulation,
         // every map pixel written once, no zero fill, no atomics; exact (bit-identical to crop_and_resize.c) when
-        // fi_set_deterministic(1) or FI_BWD=exact.  FI_BWD=red: the vector reductions below (also the fallback for shapes
+        // fi_set_deterministic(1).  fi_set_option(FI_OPT_BWD_FORM, 3): the vector reductions below (also the fallback for shapes
         // the tile kernels do not take: crops wider than 16, more than 8 maps).
-        const char *mode = getenv("FI_BWD");
-        if (!(mode && mode[0] == 'r')) {
-            const int exact = fi_get_deterministic() || (mode && mode[0] == 'e');
+        if (option(FI_OPT_BWD_FORM) != 3) {
+            const int exact = fi_get_deterministic();
             const int rc = fi_tile_backward(sets, num_sets, zero_first ? 0 : 1, exact, stream);
             if (rc != FI_ERR_UNSUPPORTED) return rc;
         }
@@ -543,6 +541,7 @@ FI_API int fi_crop_sets_backward(const fi_bwd_set *sets, int num_sets, int zero_
                                  h.crop_width, h.depth)) return e;
         const bool vec = (h.depth % 128 == 0) && ((uintptr_t)h.grads_image % 16 == 0) && ((uintptr_t)h.grads % 16 == 0) && ((uintptr_t)h.grads2 % 16 == 0);
         if (!vec) { set_error(FI_ERR_UNSUPPORTED, "fi_crop_sets_backward: set %d needs NHWC, depth %% 128 == 0, 16-byte aligned tensors", i); return FI_ERR_UNSUPPORTED; }
+        if (h.num_boxes_dev) { set_error(FI_ERR_UNSUPPORTED, "fi_crop_sets_backward: device-side box counts need the tile-owner kernels (set %d)", i); return FI_ERR_UNSUPPORTED; }
         if (zero_first) {                       // each distinct map once
             bool seen = false;
             for (int q = 0; q < i; ++q) seen = seen || (sets[q].grads_image == h.grads_image);

@@ -17,9 +17,13 @@ int fi_scatter_backward_nhwc(const float *grads, const float *grads2, const floa
 
 int fi_tile_backward(const fi_bwd_set *sets, int num_sets, int accumulate, int exact, cudaStream_t stream);   // roi_align_bwd_tile.cu
 
-static int g_deterministic = 0;
-FI_API int fi_set_deterministic(int on) { const int old = g_deterministic; g_deterministic = on ? 1 : 0; return old; }
-FI_API int fi_get_deterministic(void) { return g_deterministic; }
+namespace fi { extern int g_deterministic_init; }   // abi.cu: FI_BWD=exact in the environment at first use
+static int g_deterministic = -1;                     // -1: not set yet, take the environment's word
+FI_API int fi_get_deterministic(void) {
+    if (g_deterministic < 0) { fi::option(FI_OPT_BWD_FORM); g_deterministic = fi::g_deterministic_init; }
+    return g_deterministic;
+}
+FI_API int fi_set_deterministic(int on) { const int old = fi_get_deterministic(); g_deterministic = on ? 1 : 0; return old; }
 
 FI_API int fi_crop_and_resize_backward_multi(const fi_crop_set *sets, int num_sets, int batch, int image_height, int image_width, int depth,
                                              float *grads_image, int accumulate, int deterministic, cudaStream_t stream) {
@@ -35,7 +39,7 @@ FI_API int fi_crop_and_resize_backward_multi(const fi_crop_set *sets, int num_se
         tmp[i].grads_image = grads_image; tmp[i].grads = sets[i].grads; tmp[i].grads2 = sets[i].grads2; tmp[i].boxes = sets[i].boxes;
         tmp[i].box_ind = sets[i].box_ind; tmp[i].src_row = sets[i].src_row; tmp[i].batch = batch; tmp[i].image_height = image_height;
         tmp[i].image_width = image_width; tmp[i].depth = depth; tmp[i].num_boxes = sets[i].num_boxes;
-        tmp[i].crop_height = sets[i].crop_height; tmp[i].crop_width = sets[i].crop_width;
+        tmp[i].crop_height = sets[i].crop_height; tmp[i].crop_width = sets[i].crop_width; tmp[i].num_boxes_dev = nullptr;
     }
     if (deterministic) {
         const int rc = fits ? fi_tile_backward(tmp, num_sets, accumulate, 1, stream) : FI_ERR_UNSUPPORTED;

@@ -26,7 +26,7 @@ namespace tile {
 
 constexpr int kPixWarps = 8;                       // consumer warps per CTA
 constexpr int kPixThreads = (kPixWarps + 1) * 32;  // + the producer warp
-constexpr int kPixGroup = 8;                       // tiles per grab of the work counter
+constexpr int kPixGroupMax = 8;                    // tiles per ticket of the work counter: 1..8 (P.bin.pix_group)
 constexpr unsigned kFullMask = 0xffffffffu;
 
 template <int CB, int BS, int NB>
@@ -34,7 +34,8 @@ struct __align__(128) PixSmem {
     float data[NB][BS][CB];                        // staged gradient rows (bulk-copy destination)
     float4 qw[NB][BS];                             // entry weights
     uint2 qa[NB][BS];                              // entry (row, pk2); pk2 == 0 for unused slots
-    int4 hdr[NB];                                  // (entries | flags << 8 | map << 16, image, Y0, X0); flags: 1 first, 2 last, 4 done
+    int4 hdr[NB];                                  // (entries | flags << 8 | map << 16, image, Y0, X0); flags: 1 first, 2 last, 4 done,
+                                                   // 8 split layout (two-source batch: load-only halves in slots 0-15, tapped halves in 16-31)
     unsigned long long full[NB], empty[NB];        // mbarriers: rows + metadata landed / all consumers done with the slot
     const float *srcs[3 * kMaxSets];
 };
@@ -71,8 +72,8 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
 }
 
 // grid (2 CTAs per SM, C / CB), kPixThreads threads, dynamic shared memory = sizeof(PixSmem)
-template <bool EXACT, int CB, int BS, int NB>
-__global__ void __launch_bounds__(kPixThreads, 2) pix_accumulate_kernel(const TParams P) {
+template <bool EXACT, int CB, int BS, int NB, int MINB>
+__global__ void __launch_bounds__(kPixThreads, MINB) pix_accumulate_kernel(const TParams P) {
     constexpr int TY = 4, TX = 8;
     constexpr int NCH = CB / 128;
     static_assert(kChunk % BS == 0 && BS <= 32, "a batch never straddles a list chunk");
@@ -101,24 +102,35 @@ __global__ void __launch_bounds__(kPixThreads, 2) pix_accumulate_kernel(const TP
         int *work = P.bin.work + cb;
         // group of kPixGroup consecutive tiles (heaviest-first order); lane i holds (entries, first chunk) of tile t0 + i
         int my_n = 0, my_head = 0, nx_n = 0, nx_head = 0;
+        // A ticket stands for kPixGroup tiles that are gridDim.x apart in the heaviest-first order: the CTAs that hold
+        // neighbouring tickets then work on neighbouring tiles at the same time, so the gradient rows two adjacent tiles share
+        // are still in L2 when the second one asks (consecutive tiles per ticket: L2 hit rate 6 %, +0.4 GB of DRAM reads).
+        const int gx = (int)gridDim.x;
+        const int kPixGroup = P.bin.pix_group;
+        auto tile_of = [&](int ticket, int i) { return (ticket / gx) * (kPixGroup * gx) + (ticket % gx) + i * gx; };
         auto load_info = [&](int base, int &n, int &head) {
             n = 0; head = 0;
-            const int t = base + lane;
+            const int t = tile_of(base, lane & (kPixGroupMax - 1));
             if (lane < kPixGroup && t < total) {
                 n = P.bin.tile_n[total - 1 - t];
                 head = P.bin.tile_head[total - 1 - t];            // only meaningful when n > 0
             }
         };
         int t0 = 0, t0n_l0 = 0;
-        if (lane == 0) t0 = atomicAdd(work, kPixGroup);
-        if (lane == 0) t0n_l0 = atomicAdd(work, kPixGroup);       // the next group's base stays in lane 0 until it is needed
+        if (lane == 0) t0 = atomicAdd(work, 1);
+        if (lane == 0) t0n_l0 = atomicAdd(work, 1);               // the next ticket stays in lane 0 until it is needed
         t0 = __shfl_sync(kFullMask, t0, 0);
         load_info(t0, my_n, my_head);
-        int gcount = min(kPixGroup, total - t0), ti = 0;
+        auto count_of = [&](int ticket) {                       // tiles of the ticket that exist (a prefix: tile_of grows with i)
+            int c = 0;
+            while (c < kPixGroup && tile_of(ticket, c) < total) ++c;
+            return c;
+        };
+        int gcount = count_of(t0), ti = 0;
         bool need_info = true;
 
         // current batch descriptor (t < 0: end marker) and its list entries (loads in flight)
-        int c_t = gcount > 0 ? t0 : -1, c_n = 0, c_e0 = 0, c_chunk = 0, nextc = 0;
+        int c_t = gcount > 0 ? tile_of(t0, 0) : -1, c_n = 0, c_e0 = 0, c_chunk = 0, nextc = 0;
         if (c_t >= 0) {
             c_n = __shfl_sync(kFullMask, my_n, 0);
             c_chunk = __shfl_sync(kFullMask, my_head, 0);
@@ -168,9 +180,9 @@ __global__ void __launch_bounds__(kPixThreads, 2) pix_accumulate_kernel(const TP
                         if (need_info) load_info(t0, nx_n, nx_head);
                         my_n = nx_n; my_head = nx_head;
                         ti = 0;
-                        gcount = min(kPixGroup, total - t0);
+                        gcount = count_of(t0);
                         need_info = true;
-                        if (gcount > 0 && lane == 0) t0n_l0 = atomicAdd(work, kPixGroup);
+                        if (gcount > 0 && lane == 0) t0n_l0 = atomicAdd(work, 1);
                     }
                     if (gcount <= 0) n_t = -1;
                     else {
@@ -178,7 +190,7 @@ __global__ void __launch_bounds__(kPixThreads, 2) pix_accumulate_kernel(const TP
                             load_info(__shfl_sync(kFullMask, t0n_l0, 0), nx_n, nx_head);
                             need_info = false;
                         }
-                        n_t = t0 + ti;
+                        n_t = tile_of(t0, ti);
                         n_n = __shfl_sync(kFullMask, my_n, ti);
                         n_chunk = __shfl_sync(kFullMask, my_head, ti);
                         n_e0 = 0;
@@ -192,24 +204,50 @@ __global__ void __launch_bounds__(kPixThreads, 2) pix_accumulate_kernel(const TP
             // ---- issue the current batch into ring slot it % NB
             const int slot = it % NB;
             if (it >= NB) mbar_wait(&S.empty[slot], ((it / NB) - 1) & 1);
+            // Two-source batches (every even entry is the load-only first half of a pair) are laid out split: first halves in
+            // slots 0-15, tapped halves in 16-31 -- the rows of each half are then consecutive in memory AND in the ring.
+            const int cnt = c_t >= 0 ? max(0, min(BS, c_n - c_e0)) : 0;
+            bool split = false;
+            if (BS == 32) {
+                const unsigned even_valid = __ballot_sync(kFullMask, lane < cnt && !(lane & 1));
+                const unsigned even_defer = __ballot_sync(kFullMask, lane < cnt && !(lane & 1) && ((int)ea.y & kDefer2));
+                split = cnt > 2 && even_valid == even_defer;
+                if (split) {
+                    const int from = ((lane & 15) << 1) | (lane >> 4);
+                    ea.x = __shfl_sync(kFullMask, ea.x, from); ea.y = __shfl_sync(kFullMask, ea.y, from);
+                    ew.x = __shfl_sync(kFullMask, ew.x, from); ew.y = __shfl_sync(kFullMask, ew.y, from);
+                    ew.z = __shfl_sync(kFullMask, ew.z, from); ew.w = __shfl_sync(kFullMask, ew.w, from);
+                }
+            }
             const int pk = (int)ea.y;
             if (lane < BS) {
                 S.qa[slot][lane] = ea;
                 S.qw[slot][lane] = ew;
             }
             if (lane == 0) {
-                const int cnt = c_t >= 0 ? max(0, min(BS, c_n - c_e0)) : 0;
-                const int flags = c_t < 0 ? 4 : ((c_e0 == 0 ? 1 : 0) | (c_e0 + BS >= c_n ? 2 : 0));
+                const int flags = c_t < 0 ? 4 : ((c_e0 == 0 ? 1 : 0) | (c_e0 + BS >= c_n ? 2 : 0) | (split ? 8 : 0));
                 S.hdr[slot] = make_int4(cnt | (flags << 8) | (mi << 16), tb, Y0, X0);
             }
+            // Runs of consecutive gradient rows (neighbouring samples of one crop row) in consecutive slots go out as ONE bulk
+            // copy: the copies are issued one at a time by this warp (UBLKCP takes uniform operands), 3-5x fewer of them.
             const bool needs = (pk & (15 | kDefer2)) != 0;        // tap-less padding entries are not fetched
+            const int src = (pk >> 5) & 63;
+            const unsigned row_p = __shfl_up_sync(kFullMask, ea.x, 1);
+            const int src_p = __shfl_up_sync(kFullMask, src, 1);
+            const bool needs_p = __shfl_up_sync(kFullMask, (int)needs, 1) != 0;
+            const bool cont = needs && lane > 0 && needs_p && src_p == src && ea.x == row_p + 1u && C == CB;
             const unsigned m = __ballot_sync(kFullMask, needs);
+            const unsigned breaks = ~__ballot_sync(kFullMask, cont);       // lanes that do not continue their left neighbour
             __syncwarp();
             if (lane == 0) {
                 if (m) mbar_arrive_expect_tx(&S.full[slot], (unsigned)__popc(m) * CB * 4u);
                 else mbar_arrive(&S.full[slot]);
             }
-            if (needs) bulk_g2s(&S.data[slot][lane][0], S.srcs[(pk >> 5) & 63] + (size_t)ea.x * C + cb * CB, CB * 4u, &S.full[slot]);
+            if (needs && !cont) {
+                const unsigned above = lane < 31 ? (breaks >> (lane + 1)) : 0u;
+                const int run = above ? __ffs(above) : 32 - lane;
+                bulk_g2s(&S.data[slot][lane][0], S.srcs[src] + (size_t)ea.x * C + cb * CB, (unsigned)run * CB * 4u, &S.full[slot]);
+            }
             if (c_t < 0) break;
             c_t = n_t; c_n = n_n; c_e0 = n_e0; c_chunk = n_chunk; ea = ea2; ew = ew2;
             if (new_tile && c_t >= 0) decode(c_t);
@@ -267,8 +305,9 @@ __global__ void __launch_bounds__(kPixThreads, 2) pix_accumulate_kernel(const TP
             }
         }
         // two-source samples: the entry before a tapped one may be its load-only first half (pairs start on even slots)
-        const int prev_pk = __shfl_up_sync(kFullMask, pk, 1);
-        const int info = mask | ((lane > 0 && (prev_pk & kDefer2)) ? 16 : 0);
+        const int poff = (flags & 8) ? 16 : 1;                    // split layout: the first half sits 16 slots below
+        const int prev_pk = __shfl_sync(kFullMask, pk, (lane - poff) & 31);
+        const int info = mask | ((lane >= poff && (prev_pk & kDefer2)) ? 16 : 0);
         unsigned hits = __ballot_sync(kFullMask, mask != 0);
         const float4 *rows = reinterpret_cast<const float4 *>(&S.data[slot][0][0]) + lane;
         while (hits) {
@@ -280,7 +319,7 @@ __global__ void __launch_bounds__(kPixThreads, 2) pix_accumulate_kernel(const TP
             for (int c = 0; c < NCH; ++c) g[c] = rows[e * (CB / 4) + c * 32];
             if (m & 16) {                                         // (g1 + g2) first, like autograd's accumulation in the reference
 #pragma unroll
-                for (int c = 0; c < NCH; ++c) g[c] = add_rn4(g[c], rows[(e - 1) * (CB / 4) + c * 32]);
+                for (int c = 0; c < NCH; ++c) g[c] = add_rn4(g[c], rows[(e - poff) * (CB / 4) + c * 32]);
             }
             const float u0 = __shfl_sync(kFullMask, wa0, e), u1 = __shfl_sync(kFullMask, wa1, e);
             const float u2 = __shfl_sync(kFullMask, wa2, e), u3 = __shfl_sync(kFullMask, wa3, e);
@@ -327,19 +366,23 @@ __global__ void __launch_bounds__(kPixThreads, 2) pix_accumulate_kernel(const TP
     }
 }
 
-template <bool EXACT, int CB, int BS, int NB>
-static int launch_pix(const TParams &P, int ctas_per_sm, cudaStream_t stream) {
+template <bool EXACT, int CB, int BS, int NB, int MINB>
+static int launch_pix(const TParams &P, cudaStream_t stream) {
+    const int ctas_per_sm = MINB;
     const size_t smem = sizeof(PixSmem<CB, BS, NB>);
-    static bool configured = false;
+    static bool configured_dev[64] = {};                          // the attribute is per function AND per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool &configured = configured_dev[dev & 63];
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(pix_accumulate_kernel<EXACT, CB, BS, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(pix_accumulate_kernel<EXACT, CB, BS, NB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error(FI_ERR_CUDA, "crop backward[accumulate]: shared memory attribute: %s", cudaGetErrorString(e)); return FI_ERR_CUDA; }
         configured = true;
     }
     const int chan_blocks = P.m[0].C / CB;
-    const long want = ((long)P.bin.total_tiles + kPixGroup - 1) / kPixGroup;
+    const long want = P.bin.total_tiles;
     const int grid_x = (int)(want < (long)kNumSMs * ctas_per_sm ? want : (long)kNumSMs * ctas_per_sm);
-    pix_accumulate_kernel<EXACT, CB, BS, NB><<<dim3(grid_x, chan_blocks), kPixThreads, smem, stream>>>(P);
+    pix_accumulate_kernel<EXACT, CB, BS, NB, MINB><<<dim3(grid_x, chan_blocks), kPixThreads, smem, stream>>>(P);
     return check_launch("crop backward[accumulate]");
 }
 
@@ -349,8 +392,14 @@ int pix_accumulate(const TParams &P, int exact, cudaStream_t stream) {
     for (int m = 1; m < P.nmaps; ++m)
         if (P.m[m].C != C) return FI_ERR_UNSUPPORTED;
     if (C % 128 != 0 || C / 128 > 32) return FI_ERR_UNSUPPORTED;
-    if (C % 256 == 0) return exact ? launch_pix<true, 256, 32, 3>(P, 2, stream) : launch_pix<false, 256, 32, 3>(P, 2, stream);
-    return exact ? launch_pix<true, 128, 32, 3>(P, 2, stream) : launch_pix<false, 128, 32, 3>(P, 2, stream);
+    const int cfg = option(FI_OPT_PIX_CFG);
+    if (C % 256 == 0) {
+        if (cfg == 1) return exact ? launch_pix<true, 256, 16, 6, 2>(P, stream) : launch_pix<false, 256, 16, 6, 2>(P, stream);
+        if (cfg == 2) return exact ? launch_pix<true, 256, 32, 2, 3>(P, stream) : launch_pix<false, 256, 32, 2, 3>(P, stream);
+        if (cfg == 3) return exact ? launch_pix<true, 256, 16, 4, 3>(P, stream) : launch_pix<false, 256, 16, 4, 3>(P, stream);
+        return exact ? launch_pix<true, 256, 32, 3, 2>(P, stream) : launch_pix<false, 256, 32, 3, 2>(P, stream);
+    }
+    return exact ? launch_pix<true, 128, 32, 3, 2>(P, stream) : launch_pix<false, 128, 32, 3, 2>(P, stream);
 }
 
 }  // namespace tile

@@ -54,7 +54,7 @@ namespace tile {
 __global__ void __launch_bounds__(128) tile_prep_kernel(const TParams P) {
     const TSet &S = P.s[blockIdx.y];
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= S.R) return;
+    if (r >= (S.R_dev ? min(*S.R_dev, S.R) : S.R)) return;
     const int B = P.m[S.map].B, H = P.m[S.map].H, W = P.m[S.map].W;
     const int b = S.box_ind[r];
     const float4 bx = S.boxes[r];                  // (y1, x1, y2, x2)
@@ -526,6 +526,8 @@ __global__ void __launch_bounds__(128) bin_enumerate_kernel(const TParams P) {
     EnumSmem &ws = smem[w];
     const unsigned lt = (1u << lane) - 1u;
     int qn = 0, qtot = 0, prev_chunk = -1;
+    int stored = 0;
+    bool overflow = false;
     unsigned last_row = 0;
     int last_src = 0;
 
@@ -536,17 +538,22 @@ __global__ void __launch_bounds__(128) bin_enumerate_kernel(const TParams P) {
             if (c < P.bin.pool) {
                 if (prev_chunk < 0) P.bin.tile_head[tile_id] = c;
                 else P.bin.chunk_next[prev_chunk] = c;
+            } else {
+                atomicExch(P.bin.cursor + 1, 1);        // overflow (only possible with a caller's own, too small, entry bound)
             }
         }
         c = __shfl_sync(0xffffffffu, c, 0);
         __syncwarp();
-        if (c < P.bin.pool) {                           // cannot fail: the pool is sized for 4 tiles per sample
+        if (c < P.bin.pool) {                           // the default pool is sized for 4 tiles per sample: always true then
             P.bin.qa[(size_t)c * kChunk + lane] = ws.qa[lane];
             P.bin.qa[(size_t)c * kChunk + 32 + lane] = ws.qa[32 + lane];
             P.bin.qw[(size_t)c * kChunk + lane] = ws.qw[lane];
             P.bin.qw[(size_t)c * kChunk + 32 + lane] = ws.qw[32 + lane];
+            prev_chunk = c;
+            stored += qn;
+        } else {
+            overflow = true;                            // the tile's list ends at the last chunk that fitted
         }
-        prev_chunk = c;
         qn = 0;
         __syncwarp();
     };
@@ -697,7 +704,7 @@ __global__ void __launch_bounds__(128) bin_enumerate_kernel(const TParams P) {
     if (qtot & 7) pad_entries(8 - (qtot & 7));          // whole groups of 8 per tile
     __syncwarp();
     if (qn > 0) flush();
-    if (lane == 0) P.bin.tile_n[tile_id] = qtot;
+    if (lane == 0) P.bin.tile_n[tile_id] = overflow ? stored : qtot;
 }
 
 // grid (total tiles, ceil(slabs / 2)), 64 threads: warp = (tile, 128-channel slab)
@@ -839,9 +846,197 @@ __global__ void __launch_bounds__(64, MINB) bin_accumulate_kernel(const TParams 
 using namespace fi;
 using namespace fi::tile;
 
-// Grow-only scratch memory, one block per (device, stream): every use is ordered on that stream, so consecutive calls can
-// share it without synchronisation.  (cudaMallocAsync / cudaFreeAsync per call cost periodic multi-millisecond host stalls.)
+namespace fi { namespace tile { int pix_accumulate(const TParams &P, int exact, cudaStream_t stream); } }   // roi_align_bwd_pix.cu
+
+// =====================================================================================================================
+// Host side.  One backward = PLAN (tile_prep + bin_enumerate: needs the boxes only, so it can run at forward time, on another
+// stream) + RUN (tile_collapse + accumulate: needs the gradients).  All scratch memory is ONE caller-provided block
+// (fi_crop_sets_backward_workspace tells its size) -- the Python layer takes it from torch's caching allocator, which also
+// makes the whole thing CUDA-graph capturable; the one-shot entry fi_crop_sets_backward uses a grow-only block per
+// (device, stream) instead and refuses to grow it while that stream is being captured.
+// =====================================================================================================================
 namespace {
+
+struct PlanData {                      // what fi_bwd_plan holds
+    unsigned magic;
+    int exact, form, nsets_in, binned;
+    size_t bytes;
+    fi_bwd_set in[kMaxSets];           // the caller's sets at plan time, for the consistency check of run
+    int set_of_in[kMaxSets];           // caller's set i -> index in P.s
+    TParams P;
+};
+static_assert(sizeof(PlanData) <= sizeof(fi_bwd_plan), "fi_bwd_plan too small");
+constexpr unsigned kPlanMagic = 0xf1b200a2u;
+
+size_t up16(size_t v) { return (v + 15) / 16 * 16; }
+
+// Fills P (maps, sets, tile counts) and binds every scratch array to ws (ws == nullptr: sizes only).  Returns the bytes
+// needed, 0 when the sets do not qualify (caller falls back to the reduction kernels), or (size_t)-1 on invalid input.
+size_t build(const fi_bwd_set *sets, int num_sets, int exact, long max_entries, char *ws, PlanData &D) {
+    TParams &P = D.P;
+    if (num_sets < 1 || num_sets > kMaxSets) return 0;
+    const int form = option(FI_OPT_BWD_FORM), shape = option(FI_OPT_TILE_SHAPE);
+    // tile shape: 4 rows x 8 pixels (a tile row is 8 KB contiguous in NHWC, C = 256); 4x4 / 2x8 only exist for the
+    // shared-memory forms (measurements)
+    const int TYs = (form != 0 && shape == 2) ? 2 : 4, TXs = (form != 0 && shape == 1) ? 4 : 8;
+    D.form = form; D.exact = exact ? 1 : 0; D.nsets_in = num_sets; D.binned = form != 2;
+    P.nsets = 0; P.nmaps = 0; P.accumulate = 0; P.collapse = exact ? 0 : 1;
+    // group the sets by map, maps in order of first appearance
+    for (int i = 0; i < num_sets; ++i) {
+        const fi_bwd_set &h = sets[i];
+        if (h.depth % 128 != 0 || h.image_height > 32767 || h.image_width > 32767 || h.crop_height > kMaxCrop || h.crop_width > kMaxCrop ||
+            h.crop_height < 1 || h.crop_width < 1) return 0;
+        if (((uintptr_t)h.grads_image % 16) || ((uintptr_t)h.grads % 16) || ((uintptr_t)h.grads2 % 16) || ((uintptr_t)h.boxes % 16)) return 0;
+        if ((long)h.num_boxes * h.crop_height * h.crop_width >= (1L << 29) || h.num_boxes >= (1 << 24)) return 0;
+        bool seen = false;
+        for (int q = 0; q < i; ++q) seen = seen || (sets[q].grads_image == h.grads_image);
+        if (seen) continue;
+        if (P.nmaps == kMaxMaps) return 0;
+        TMap &M = P.m[P.nmaps];
+        M.gimg = h.grads_image; M.B = h.batch; M.H = h.image_height; M.W = h.image_width; M.C = h.depth;
+        M.tiles_x = ceil_div(M.W, TXs); M.tiles_y = ceil_div(M.H, TYs);
+        M.set_begin = P.nsets;
+        for (int q = i; q < num_sets; ++q) {
+            const fi_bwd_set &g = sets[q];
+            if (g.grads_image != h.grads_image) continue;
+            if (g.batch != h.batch || g.image_height != h.image_height || g.image_width != h.image_width || g.depth != h.depth) {
+                set_error(FI_ERR_INVALID, "crop backward: sets %d and %d name the same map with different shapes", i, q);
+                return (size_t)-1;
+            }
+            D.set_of_in[q] = P.nsets;
+            TSet &S = P.s[P.nsets++];
+            S.grads = g.grads; S.grads2 = g.grads2; S.boxes = reinterpret_cast<const float4 *>(g.boxes); S.box_ind = g.box_ind; S.src_row = g.src_row;
+            S.R = g.num_boxes; S.R_dev = g.num_boxes_dev; S.ph = g.crop_height; S.pw = g.crop_width; S.map = P.nmaps;
+        }
+        M.set_end = P.nsets;
+        ++P.nmaps;
+    }
+    long tiles = 0;
+    long total_R = 0;
+    for (int m = 0; m < P.nmaps; ++m) {
+        TMap &M = P.m[m];
+        if (tiles + (long)M.B * M.tiles_x * M.tiles_y >= (1L << 31)) return 0;
+        M.first_tile = (int)tiles;
+        tiles += (long)M.B * M.tiles_x * M.tiles_y;
+    }
+    // per-tile sample lists in 64-entry chunks.  A sample's taps lie in at most 2x2 tiles, two-source sets queue two entries
+    // per sample; + one partly filled chunk per tile, + one more for the (<= 7 + one per set) tap-less padding entries.
+    // max_entries > 0: the caller's own bound on the entries (it may know that the sets partition the boxes).
+    long entries_bound = 0;
+    for (int i = 0; i < P.nsets; ++i) {
+        entries_bound += 4L * P.s[i].R * P.s[i].ph * P.s[i].pw * (P.s[i].grads2 ? 2 : 1) + 8L * 4 * P.s[i].R;
+        total_R += P.s[i].R;
+    }
+    if (max_entries > 0 && max_entries < entries_bound) entries_bound = max_entries;
+    const long pool = entries_bound / kChunk + 2 * tiles + 8;
+    if (pool >= (1L << 31) / kChunk) D.binned = 0;
+    // ---- layout: [per-set image ranges (memset 0xFF)] [degenerate count + list | chunk cursor, overflow flag, 32 tile counters
+    //      (memset 0)] [records, geometry] [collapse rows] [lists]
+    char *p = ws;
+    size_t bytes = 0;
+    auto take = [&](size_t n) { char *q = ws ? p : nullptr; if (ws) p += n; bytes += n; return q; };
+    for (int i = 0; i < P.nsets; ++i) P.s[i].range = reinterpret_cast<unsigned *>(take(up16((size_t)P.m[P.s[i].map].B * 2 * sizeof(unsigned))));
+    P.range_bytes = bytes;
+    P.deg_list = reinterpret_cast<int *>(take(up16((size_t)(1 + total_R) * sizeof(int))));
+    P.bin.cursor = reinterpret_cast<int *>(take(16));               // [0] chunks handed out, [1] overflow flag
+    P.bin.work = reinterpret_cast<int *>(take(128));
+    for (int i = 0; i < P.nsets; ++i) {
+        P.s[i].rec = reinterpret_cast<int4 *>(take(up16((size_t)P.s[i].R * sizeof(int4))));
+        P.s[i].geom = reinterpret_cast<float4 *>(take(up16((size_t)P.s[i].R * sizeof(float4))));
+    }
+    for (int i = 0; i < P.nsets; ++i)                                // only the rows of degenerate boxes are ever touched
+        P.s[i].coll = reinterpret_cast<float *>(take(P.collapse ? (size_t)P.s[i].R * 4 * P.m[P.s[i].map].C * sizeof(float) : 0));
+    P.bin.pool = (int)pool;
+    P.bin.total_tiles = (int)tiles;
+    P.bin.pix_group = 1 + option(FI_OPT_PIX_GROUP);
+    P.bin.tile_head = nullptr; P.bin.tile_n = nullptr; P.bin.chunk_next = nullptr; P.bin.qw = nullptr; P.bin.qa = nullptr;
+    if (D.binned) {
+        P.bin.tile_head = reinterpret_cast<int *>(take(up16((size_t)tiles * sizeof(int))));
+        P.bin.tile_n = reinterpret_cast<int *>(take(up16((size_t)tiles * sizeof(int))));
+        P.bin.chunk_next = reinterpret_cast<int *>(take(up16((size_t)pool * sizeof(int))));
+        P.bin.qw = reinterpret_cast<float4 *>(take((size_t)pool * kChunk * sizeof(float4)));
+        P.bin.qa = reinterpret_cast<uint2 *>(take((size_t)pool * kChunk * sizeof(uint2)));
+    }
+    D.bytes = bytes ? bytes : 16;
+    D.magic = kPlanMagic;
+    for (int i = 0; i < num_sets; ++i) D.in[i] = sets[i];
+    return D.bytes;
+}
+
+int max_slabs_of(const TParams &P) {
+    int m = 1;
+    for (int i = 0; i < P.nmaps; ++i) m = m > P.m[i].C / 128 ? m : P.m[i].C / 128;
+    return m;
+}
+
+// prep (+ enumerate): everything that depends on the boxes only
+int launch_plan(const PlanData &D, cudaStream_t stream) {
+    const TParams &P = D.P;
+    char *ws = reinterpret_cast<char *>(P.s[0].range);
+    cudaError_t e = cudaSuccess;
+    if (P.range_bytes) e = cudaMemsetAsync(ws, 0xFF, P.range_bytes, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(P.deg_list, 0, sizeof(int), stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(P.bin.cursor, 0, 16 + 128, stream);
+    if (e != cudaSuccess) { set_error(FI_ERR_CUDA, "crop backward: memset: %s", cudaGetErrorString(e)); return FI_ERR_CUDA; }
+    int max_R = 0;
+    for (int i = 0; i < P.nsets; ++i) max_R = max_R > P.s[i].R ? max_R : P.s[i].R;
+    int rc = ok();
+    if (max_R > 0) {
+        tile_prep_kernel<<<dim3(ceil_div(max_R, 128), P.nsets), 128, 0, stream>>>(P);
+        rc = check_launch("crop backward[prep]");
+    }
+    const int tiles = P.bin.total_tiles;
+    if (rc == FI_OK && tiles > 0 && D.binned) {
+        const int egrid = (tiles + 3) / 4;
+        const int shape = option(FI_OPT_TILE_SHAPE);
+        const bool t48 = D.form == 0 || shape == 0;
+        if (t48) { if (D.exact) bin_enumerate_kernel<true, 4, 8><<<egrid, 128, 0, stream>>>(P); else bin_enumerate_kernel<false, 4, 8><<<egrid, 128, 0, stream>>>(P); }
+        else if (shape == 1) { if (D.exact) bin_enumerate_kernel<true, 4, 4><<<egrid, 128, 0, stream>>>(P); else bin_enumerate_kernel<false, 4, 4><<<egrid, 128, 0, stream>>>(P); }
+        else { if (D.exact) bin_enumerate_kernel<true, 2, 8><<<egrid, 128, 0, stream>>>(P); else bin_enumerate_kernel<false, 2, 8><<<egrid, 128, 0, stream>>>(P); }
+        rc = check_launch("crop backward[enumerate]");
+    }
+    return rc;
+}
+
+// collapse + accumulate: everything that needs the gradients
+int launch_run(const PlanData &D, const TParams &P, cudaStream_t stream) {
+    int rc = ok();
+    long total_R = 0;
+    for (int i = 0; i < P.nsets; ++i) total_R += P.s[i].R;
+    if (total_R > 0 && P.collapse) {
+        const int grid = (int)(total_R < 4L * kNumSMs ? total_R : 4L * kNumSMs);
+        tile_collapse_kernel<<<grid, 256, 0, stream>>>(P);
+        rc = check_launch("crop backward[collapse]");
+    }
+    const int tiles = P.bin.total_tiles;
+    if (rc != FI_OK || tiles <= 0) return rc;
+    if (D.binned && D.form == 0) {                               // tile counters of the persistent kernel: a plan may be run more than once
+        cudaError_t e = cudaMemsetAsync(P.bin.work, 0, 128, stream);
+        if (e != cudaSuccess) { set_error(FI_ERR_CUDA, "crop backward: memset: %s", cudaGetErrorString(e)); return FI_ERR_CUDA; }
+    }
+    const int exact = D.exact, shape = option(FI_OPT_TILE_SHAPE);
+    const dim3 grid((unsigned)tiles, ceil_div(max_slabs_of(P), 2));
+    if (D.binned) {
+        if (D.form == 0) {                                       // default: bulk-copy staged, register-accumulating kernel
+            rc = pix_accumulate(P, exact, stream);
+            if (rc != FI_ERR_UNSUPPORTED) return rc;             // (mixed channel counts: the shared-memory kernel takes it, lists are ready)
+        }
+        const bool t48 = D.form == 0 || shape == 0;
+        if (t48) { if (exact) bin_accumulate_kernel<true, 4, 8, 8, 6><<<grid, 64, 0, stream>>>(P); else bin_accumulate_kernel<false, 4, 8, 8, 6><<<grid, 64, 0, stream>>>(P); }
+        else if (shape == 1) { if (exact) bin_accumulate_kernel<true, 4, 4, 4, 10><<<grid, 64, 0, stream>>>(P); else bin_accumulate_kernel<false, 4, 4, 4, 10><<<grid, 64, 0, stream>>>(P); }
+        else { if (exact) bin_accumulate_kernel<true, 2, 8, 4, 10><<<grid, 64, 0, stream>>>(P); else bin_accumulate_kernel<false, 2, 8, 4, 10><<<grid, 64, 0, stream>>>(P); }
+        return check_launch("crop backward[accumulate]");
+    }
+    if (shape == 0) { if (exact) bwd_smem_tile_kernel<true, 4, 8, FI_TILE_MINB><<<grid, 64, 0, stream>>>(P); else bwd_smem_tile_kernel<false, 4, 8, FI_TILE_MINB><<<grid, 64, 0, stream>>>(P); }
+    else if (shape == 1) { if (exact) bwd_smem_tile_kernel<true, 4, 4, 10><<<grid, 64, 0, stream>>>(P); else bwd_smem_tile_kernel<false, 4, 4, 10><<<grid, 64, 0, stream>>>(P); }
+    else { if (exact) bwd_smem_tile_kernel<true, 2, 8, 10><<<grid, 64, 0, stream>>>(P); else bwd_smem_tile_kernel<false, 2, 8, 10><<<grid, 64, 0, stream>>>(P); }
+    return check_launch("crop backward[tile]");
+}
+
+// Grow-only scratch memory of the one-shot entry, one block per (device, stream): every use is ordered on that stream, so
+// consecutive calls can share it without synchronisation.  Growing frees and re-allocates (a synchronisation): refused while
+// the stream is being captured -- a captured graph would keep the old pointer -- use the plan / run entries with a
+// caller-owned workspace there.
 struct WsSlot { int dev; cudaStream_t stream; char *ptr; size_t cap; };
 WsSlot g_ws[32];
 int g_nws = 0;
@@ -854,6 +1049,13 @@ char *workspace(size_t bytes, cudaStream_t stream) {
     WsSlot *slot = nullptr;
     for (int i = 0; i < g_nws; ++i) if (g_ws[i].dev == dev && g_ws[i].stream == stream) slot = &g_ws[i];
     if (slot && slot->cap >= bytes) return slot->ptr;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+        cudaGetLastError();
+        set_error(FI_ERR_UNSUPPORTED, "crop backward: the internal workspace cannot grow during stream capture; use fi_crop_sets_backward_plan / _run with "
+                                      "a caller-owned workspace");
+        return nullptr;
+    }
     if (!slot) {
         if (g_nws == 32) {                             // recycle the oldest entry
             cudaStreamSynchronize(g_ws[0].stream);
@@ -872,204 +1074,100 @@ char *workspace(size_t bytes, cudaStream_t stream) {
     cudaError_t e = cudaMalloc((void **)&slot->ptr, want);
     if (e != cudaSuccess) {
         slot->ptr = nullptr;
-        set_error(FI_ERR_CUDA, "crop backward: workspace (%zu B): %s", want, cudaGetErrorString(e));
+        set_error(FI_ERR_CUDA, "crop backward: workspace (%zu B): %s (torch's caching allocator may hold the memory: pass a torch-allocated workspace "
+                               "to fi_crop_sets_backward_plan instead)", want, cudaGetErrorString(e));
         return nullptr;
     }
     slot->cap = want;
     return slot->ptr;
 }
-}  // namespace
 
-// Experiment switches, read from the environment ONCE per process (not per launch):
-//   FI_TILE=4x8|4x4|2x8   tile shape of the shared-memory accumulate kernels (default 4x8)
-//   FI_BWD_TILE=fused     single-kernel form (scan + expand + accumulate in one kernel)
-//   FI_BWD_ACC=smem       shared-memory accumulate kernel (bin_accumulate_kernel) instead of the bulk-copy staged,
-//                         register-accumulating one (roi_align_bwd_pix.cu, default for 4x8 tiles)
-namespace {
-struct TileEnv { int ty, tx; bool fused, smem_acc; };
-const TileEnv &tile_env() {
-    static const TileEnv env = [] {
-        TileEnv e{4, 8, false, false};
-        const char *shape = getenv("FI_TILE");
-        if (shape && !strcmp(shape, "4x4")) { e.ty = 4; e.tx = 4; }
-        if (shape && !strcmp(shape, "2x8")) { e.ty = 2; e.tx = 8; }
-        const char *form = getenv("FI_BWD_TILE");
-        e.fused = form && form[0] == 'f';
-        const char *acc = getenv("FI_BWD_ACC");
-        e.smem_acc = acc && acc[0] == 's';
-        return e;
-    }();
-    return env;
+bool same_geometry(const fi_bwd_set &a, const fi_bwd_set &b) {
+    return a.boxes == b.boxes && a.box_ind == b.box_ind && a.src_row == b.src_row && a.batch == b.batch &&
+           a.image_height == b.image_height && a.image_width == b.image_width && a.depth == b.depth && a.num_boxes == b.num_boxes &&
+           a.num_boxes_dev == b.num_boxes_dev && a.crop_height == b.crop_height && a.crop_width == b.crop_width && (a.grads2 != nullptr) == (b.grads2 != nullptr);
 }
+
 }  // namespace
 
-namespace fi { namespace tile { int pix_accumulate(const TParams &P, int exact, cudaStream_t stream); } }   // roi_align_bwd_pix.cu
+FI_API size_t fi_crop_sets_backward_workspace(const fi_bwd_set *sets, int num_sets, int exact, long max_entries) {
+    if (!sets || option(FI_OPT_BWD_FORM) == 3) return 0;
+    PlanData D;
+    const size_t b = build(sets, num_sets, exact, max_entries, nullptr, D);
+    return b == (size_t)-1 ? 0 : b;
+}
 
-// Host side.  Returns FI_ERR_UNSUPPORTED (nothing touched) when the sets do not qualify so that the caller can use the
-// reduction kernels.  exact != 0: arithmetic and order of crop_and_resize.c:190-250 (bit-identical for one set per map).
-int fi_tile_backward(const fi_bwd_set *sets, int num_sets, int accumulate, int exact, cudaStream_t stream) {
-    if (num_sets < 1 || num_sets > kMaxSets) return FI_ERR_UNSUPPORTED;
-    // tile shape: 4 rows x 8 pixels by default (a tile row is 8 KB contiguous in NHWC, C = 256); FI_TILE=4x4 / 2x8 halve the
-    // shared memory per warp (more resident warps, more neighbour re-reads) -- kept for measurements
-    const TileEnv &env = tile_env();
-    const int TYs = env.ty, TXs = env.tx;
-    TParams P;
-    P.nsets = 0; P.nmaps = 0; P.accumulate = accumulate ? 1 : 0; P.collapse = exact ? 0 : 1;
-    // group the sets by map, maps in order of first appearance
+FI_API int fi_crop_sets_backward_plan(const fi_bwd_set *sets, int num_sets, int exact, long max_entries, void *workspace_ptr, size_t workspace_bytes,
+                                      fi_bwd_plan *plan, cudaStream_t stream) {
+    FI_REQUIRE(sets && plan && workspace_ptr, "fi_crop_sets_backward_plan: null pointer");
+    FI_REQUIRE(((uintptr_t)workspace_ptr % 16) == 0, "fi_crop_sets_backward_plan: the workspace must be 16-byte aligned");
+    if (option(FI_OPT_BWD_FORM) == 3) { set_error(FI_ERR_UNSUPPORTED, "crop backward: the reduction form has no plan"); return FI_ERR_UNSUPPORTED; }
+    PlanData &D = *reinterpret_cast<PlanData *>(plan);
+    D.magic = 0;
+    const size_t need = build(sets, num_sets, exact, max_entries, static_cast<char *>(workspace_ptr), D);
+    if (need == (size_t)-1) return FI_ERR_INVALID;
+    if (need == 0) { D.magic = 0; set_error(FI_ERR_UNSUPPORTED, "crop backward: these sets need the reduction kernels (depth %% 128, crops <= 16, <= 8 maps, 16-byte alignment)"); return FI_ERR_UNSUPPORTED; }
+    if (need > workspace_bytes) { D.magic = 0; set_error(FI_ERR_INVALID, "fi_crop_sets_backward_plan: workspace of %zu bytes, %zu needed", workspace_bytes, need); return FI_ERR_INVALID; }
+    return launch_plan(D, stream);
+}
+
+// `sets` carries the gradients (grads, grads2, grads_image may differ from plan time); boxes / sizes / two-source pattern must
+// be the plan's.
+FI_API int fi_crop_sets_backward_run(const fi_bwd_plan *plan, const fi_bwd_set *sets, int num_sets, int zero_first, cudaStream_t stream) {
+    FI_REQUIRE(plan && sets, "fi_crop_sets_backward_run: null pointer");
+    const PlanData &D = *reinterpret_cast<const PlanData *>(plan);
+    FI_REQUIRE(D.magic == kPlanMagic, "fi_crop_sets_backward_run: not a plan (fi_crop_sets_backward_plan failed or was not called)");
+    FI_REQUIRE(num_sets == D.nsets_in, "fi_crop_sets_backward_run: %d sets, the plan was made for %d", num_sets, D.nsets_in);
+    TParams P = D.P;
+    P.accumulate = zero_first ? 0 : 1;
     for (int i = 0; i < num_sets; ++i) {
-        const fi_bwd_set &h = sets[i];
-        if (h.depth % 128 != 0 || h.image_height > 32767 || h.image_width > 32767 || h.crop_height > kMaxCrop || h.crop_width > kMaxCrop ||
-            h.crop_height < 1 || h.crop_width < 1) return FI_ERR_UNSUPPORTED;
-        if (((uintptr_t)h.grads_image % 16) || ((uintptr_t)h.grads % 16) || ((uintptr_t)h.grads2 % 16) || ((uintptr_t)h.boxes % 16)) return FI_ERR_UNSUPPORTED;
-        if ((long)h.num_boxes * h.crop_height * h.crop_width >= (1L << 29) || h.num_boxes >= (1 << 24)) return FI_ERR_UNSUPPORTED;
-        bool seen = false;
-        for (int q = 0; q < i; ++q) seen = seen || (sets[q].grads_image == h.grads_image);
-        if (seen) continue;
-        if (P.nmaps == kMaxMaps) return FI_ERR_UNSUPPORTED;
-        TMap &M = P.m[P.nmaps];
-        M.gimg = h.grads_image; M.B = h.batch; M.H = h.image_height; M.W = h.image_width; M.C = h.depth;
-        M.tiles_x = ceil_div(M.W, TXs); M.tiles_y = ceil_div(M.H, TYs);
-        M.set_begin = P.nsets;
-        for (int q = i; q < num_sets; ++q) {
-            const fi_bwd_set &g = sets[q];
-            if (g.grads_image != h.grads_image) continue;
-            if (g.batch != h.batch || g.image_height != h.image_height || g.image_width != h.image_width || g.depth != h.depth) {
-                set_error(FI_ERR_INVALID, "crop backward: sets %d and %d name the same map with different shapes", i, q);
-                return FI_ERR_INVALID;
-            }
-            TSet &S = P.s[P.nsets++];
-            S.grads = g.grads; S.grads2 = g.grads2; S.boxes = reinterpret_cast<const float4 *>(g.boxes); S.box_ind = g.box_ind; S.src_row = g.src_row;
-            S.R = g.num_boxes; S.ph = g.crop_height; S.pw = g.crop_width; S.map = P.nmaps;
-        }
-        M.set_end = P.nsets;
-        ++P.nmaps;
+        FI_REQUIRE(same_geometry(sets[i], D.in[i]), "fi_crop_sets_backward_run: set %d differs from the planned one (boxes, sizes or two-source pattern)", i);
+        FI_REQUIRE(sets[i].num_boxes == 0 || sets[i].grads, "fi_crop_sets_backward_run: set %d has no gradient", i);
+        FI_REQUIRE(((uintptr_t)sets[i].grads % 16) == 0 && ((uintptr_t)sets[i].grads2 % 16) == 0, "fi_crop_sets_backward_run: unaligned gradient in set %d", i);
+        TSet &S = P.s[D.set_of_in[i]];
+        S.grads = sets[i].grads; S.grads2 = sets[i].grads2;
+        // the maps may be named only now (plan time: any distinct 16-byte aligned placeholders); sets that shared one still must
+        TMap &M = P.m[S.map];
+        bool first = true;
+        for (int q = 0; q < i; ++q) first = first && P.s[D.set_of_in[q]].map != S.map;
+        FI_REQUIRE(sets[i].grads_image && ((uintptr_t)sets[i].grads_image % 16) == 0, "fi_crop_sets_backward_run: bad grads_image in set %d", i);
+        FI_REQUIRE(first || M.gimg == sets[i].grads_image, "fi_crop_sets_backward_run: set %d no longer shares its map with the sets it was planned with", i);
+        M.gimg = sets[i].grads_image;
     }
-    long tiles = 0;
-    int max_slabs = 1, max_R = 0, total_R = 0;
-    for (int m = 0; m < P.nmaps; ++m) {
-        TMap &M = P.m[m];
-        if (tiles + (long)M.B * M.tiles_x * M.tiles_y >= (1L << 31)) return FI_ERR_UNSUPPORTED;
-        M.first_tile = (int)tiles;
-        tiles += (long)M.B * M.tiles_x * M.tiles_y;
-        max_slabs = max_slabs > M.C / 128 ? max_slabs : M.C / 128;
-    }
-    // workspace: [ranges of all sets | degenerate counter + list] (one memset region each), then records and collapse rows
-    auto up16 = [](size_t v) { return (v + 15) / 16 * 16; };
-    size_t range_bytes = 0;
-    for (int i = 0; i < P.nsets; ++i) {
-        range_bytes += up16((size_t)P.m[P.s[i].map].B * 2 * sizeof(unsigned));
-        max_R = max_R > P.s[i].R ? max_R : P.s[i].R;
-        total_R += P.s[i].R;
-    }
-    const size_t list_bytes = up16((size_t)(1 + total_R) * sizeof(int)) + 16 + 128;   // [degenerate count + list | chunk cursor | 32 tile counters]
-    // two-kernel form (default): per-tile sample lists in 64-entry chunks.  A sample's taps lie in at most 2x2 tiles, two-source
-    // sets queue two entries per sample, every tile may leave one chunk partly filled.  FI_BWD_TILE=fused: single kernel.
-    bool binned = !env.fused;
-    const long lists = tiles;
-    long entries_bound = 0;
-    for (int i = 0; i < P.nsets; ++i) entries_bound += 4L * P.s[i].R * P.s[i].ph * P.s[i].pw * (P.s[i].grads2 ? 2 : 1) + 8L * 4 * P.s[i].R;
-    // + one partly filled chunk per tile, + one more for the (<= 7 + one per set) tap-less padding entries a tile may add
-    const long pool = entries_bound / kChunk + 2 * lists + 8;
-    if (pool >= (1L << 31) / kChunk) binned = false;
-    size_t bytes = range_bytes + list_bytes;
-    for (int i = 0; i < P.nsets; ++i) {
-        bytes += 2 * up16((size_t)P.s[i].R * sizeof(int4));
-        if (P.collapse) bytes += (size_t)P.s[i].R * 4 * P.m[P.s[i].map].C * sizeof(float);    // only degenerate rows are ever touched
-    }
-    if (binned) bytes += 2 * up16((size_t)lists * sizeof(int)) + up16((size_t)pool * sizeof(int)) + (size_t)pool * kChunk * (sizeof(uint2) + sizeof(float4));
-    char *ws = workspace(bytes, stream);
-    if (!ws) return FI_ERR_CUDA;
-    cudaError_t e;
-    e = cudaMemsetAsync(ws, 0xFF, range_bytes, stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(ws + range_bytes, 0, sizeof(int), stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(ws + range_bytes + list_bytes - 144, 0, 144, stream);
-    if (e != cudaSuccess) { set_error(FI_ERR_CUDA, "crop backward: memset: %s", cudaGetErrorString(e)); return FI_ERR_CUDA; }
-    char *p = ws;
-    for (int i = 0; i < P.nsets; ++i) {
-        P.s[i].range = reinterpret_cast<unsigned *>(p);
-        p += up16((size_t)P.m[P.s[i].map].B * 2 * sizeof(unsigned));
-    }
-    P.deg_list = reinterpret_cast<int *>(p);
-    P.bin.cursor = reinterpret_cast<int *>(p + list_bytes - 144);
-    P.bin.work = reinterpret_cast<int *>(p + list_bytes - 128);
-    p += list_bytes;
-    for (int i = 0; i < P.nsets; ++i) {
-        P.s[i].rec = reinterpret_cast<int4 *>(p);
-        p += up16((size_t)P.s[i].R * sizeof(int4));
-        P.s[i].geom = reinterpret_cast<float4 *>(p);
-        p += up16((size_t)P.s[i].R * sizeof(float4));
-    }
-    for (int i = 0; i < P.nsets; ++i) {
-        P.s[i].coll = reinterpret_cast<float *>(p);
-        if (P.collapse) p += (size_t)P.s[i].R * 4 * P.m[P.s[i].map].C * sizeof(float);
-    }
-    P.bin.pool = (int)pool;
-    P.bin.total_tiles = (int)tiles;
-    if (binned) {
-        P.bin.tile_head = reinterpret_cast<int *>(p); p += up16((size_t)lists * sizeof(int));
-        P.bin.tile_n = reinterpret_cast<int *>(p); p += up16((size_t)lists * sizeof(int));
-        P.bin.chunk_next = reinterpret_cast<int *>(p); p += up16((size_t)pool * sizeof(int));
-        P.bin.qw = reinterpret_cast<float4 *>(p); p += (size_t)pool * kChunk * sizeof(float4);
-        P.bin.qa = reinterpret_cast<uint2 *>(p); p += (size_t)pool * kChunk * sizeof(uint2);
-    }
-    int rc = ok();
-    if (max_R > 0) {
-        tile_prep_kernel<<<dim3(ceil_div(max_R, 128), P.nsets), 128, 0, stream>>>(P);
-        rc = check_launch("crop backward[prep]");
-        if (rc == FI_OK && P.collapse) {
-            const int grid = total_R < 4 * kNumSMs ? total_R : 4 * kNumSMs;
-            tile_collapse_kernel<<<grid, 256, 0, stream>>>(P);
-            rc = check_launch("crop backward[collapse]");
-        }
-    }
-    if (rc == FI_OK && tiles > 0 && binned) {
-        const int egrid = (int)((tiles + 3) / 4);
-        const dim3 grid((unsigned)tiles, ceil_div(max_slabs, 2));
-#define FI_BIN_LAUNCH(TY_, TX_, U_, MINB_)                                                                    \
-    do {                                                                                                      \
-        if (exact) bin_enumerate_kernel<true, TY_, TX_><<<egrid, 128, 0, stream>>>(P);                        \
-        else bin_enumerate_kernel<false, TY_, TX_><<<egrid, 128, 0, stream>>>(P);                             \
-        rc = check_launch("crop backward[enumerate]");                                                        \
-        if (rc == FI_OK) {                                                                                    \
-            if (exact) bin_accumulate_kernel<true, TY_, TX_, U_, MINB_><<<grid, 64, 0, stream>>>(P);          \
-            else bin_accumulate_kernel<false, TY_, TX_, U_, MINB_><<<grid, 64, 0, stream>>>(P);               \
-            rc = check_launch("crop backward[accumulate]");                                                   \
-        }                                                                                                     \
-    } while (0)
-        bool done = false;
-        if (TXs == 8 && TYs == 4 && !env.smem_acc) {             // default: bulk-copy staged, register-accumulating kernel
-            if (exact) bin_enumerate_kernel<true, 4, 8><<<egrid, 128, 0, stream>>>(P);
-            else bin_enumerate_kernel<false, 4, 8><<<egrid, 128, 0, stream>>>(P);
-            rc = check_launch("crop backward[enumerate]");
-            if (rc == FI_OK) {
-                rc = pix_accumulate(P, exact, stream);
-                done = rc != FI_ERR_UNSUPPORTED;                 // (mixed channel counts: the shared-memory kernel takes it, lists are ready)
-                if (!done) {
-                    if (exact) bin_accumulate_kernel<true, 4, 8, 8, 6><<<grid, 64, 0, stream>>>(P);
-                    else bin_accumulate_kernel<false, 4, 8, 8, 6><<<grid, 64, 0, stream>>>(P);
-                    rc = check_launch("crop backward[accumulate]");
-                    done = true;
-                }
-            } else done = true;
-        }
-        if (done) {}
-        else if (TXs == 8 && TYs == 4) FI_BIN_LAUNCH(4, 8, 8, 6);
-        else if (TXs == 4) FI_BIN_LAUNCH(4, 4, 4, 10);
-        else FI_BIN_LAUNCH(2, 8, 4, 10);
-#undef FI_BIN_LAUNCH
-    } else if (rc == FI_OK && tiles > 0) {
-        const dim3 grid((unsigned)tiles, ceil_div(max_slabs, 2));
-        if (TXs == 8 && TYs == 4) {
-            if (exact) bwd_smem_tile_kernel<true, 4, 8, FI_TILE_MINB><<<grid, 64, 0, stream>>>(P);
-            else bwd_smem_tile_kernel<false, 4, 8, FI_TILE_MINB><<<grid, 64, 0, stream>>>(P);
-        } else if (TXs == 4) {
-            if (exact) bwd_smem_tile_kernel<true, 4, 4, 10><<<grid, 64, 0, stream>>>(P);
-            else bwd_smem_tile_kernel<false, 4, 4, 10><<<grid, 64, 0, stream>>>(P);
-        } else {
-            if (exact) bwd_smem_tile_kernel<true, 2, 8, 10><<<grid, 64, 0, stream>>>(P);
-            else bwd_smem_tile_kernel<false, 2, 8, 10><<<grid, 64, 0, stream>>>(P);
-        }
-        rc = check_launch("crop backward[tile]");
-    }
-    return rc;
+    for (int i = 0; i < num_sets; ++i)
+        for (int q = 0; q < i; ++q)
+            FI_REQUIRE((sets[i].grads_image == sets[q].grads_image) == (P.s[D.set_of_in[i]].map == P.s[D.set_of_in[q]].map),
+                       "fi_crop_sets_backward_run: sets %d and %d: map sharing differs from the plan", q, i);
+    return launch_run(D, P, stream);
+}
+
+// 1 when the sample lists overflowed their pool (cannot happen with the default bound; a caller's max_entries may be too
+// small), 0 when not, negative on error.  Synchronises the stream.
+FI_API int fi_crop_sets_backward_overflow(const fi_bwd_plan *plan, cudaStream_t stream) {
+    FI_REQUIRE(plan, "fi_crop_sets_backward_overflow: null pointer");
+    const PlanData &D = *reinterpret_cast<const PlanData *>(plan);
+    FI_REQUIRE(D.magic == kPlanMagic, "fi_crop_sets_backward_overflow: not a plan");
+    int flag = 0;
+    cudaError_t e = cudaMemcpyAsync(&flag, D.P.bin.cursor + 1, sizeof(int), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) { set_error(FI_ERR_CUDA, "fi_crop_sets_backward_overflow: %s", cudaGetErrorString(e)); return FI_ERR_CUDA; }
+    return flag ? 1 : 0;
+}
+
+// One-shot form on the internal workspace.  Returns FI_ERR_UNSUPPORTED (nothing touched) when the sets do not qualify so that
+// the caller can use the reduction kernels.  exact != 0: arithmetic and order of crop_and_resize.c:190-250 (bit-identical for
+// one set per map).
+int fi_tile_backward(const fi_bwd_set *sets, int num_sets, int accumulate, int exact, cudaStream_t stream) {
+    PlanData D;
+    const size_t need = build(sets, num_sets, exact, 0, nullptr, D);
+    if (need == (size_t)-1) return FI_ERR_INVALID;
+    if (need == 0) return FI_ERR_UNSUPPORTED;
+    char *ws = workspace(need, stream);
+    if (!ws) return fi_last_status();
+    build(sets, num_sets, exact, 0, ws, D);
+    int rc = launch_plan(D, stream);
+    if (rc != FI_OK) return rc;
+    TParams P = D.P;
+    P.accumulate = accumulate ? 1 : 0;
+    return launch_run(D, P, stream);
 }

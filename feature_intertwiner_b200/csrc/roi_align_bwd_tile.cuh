@@ -24,7 +24,8 @@ struct TSet {
     float4 *geom;                      // [R] (y of sample row 0, y step, x of sample column 0, x step) in pixels
     unsigned *range;                   // [B,2]: min box index of image b, ~(max box index); memset 0xFF = "none"
     float *coll;                       // [R,4,C] corner sums of degenerate boxes (only those rows are written)
-    int R, ph, pw, map;
+    const int *R_dev;                  // NULL, or the actual number of boxes (<= R) on the device
+    int R, ph, pw, map;                // R: capacity of the lists above
 };
 struct TMap {
     float *gimg;
@@ -36,15 +37,16 @@ struct BinWs {                         // per-tile sample lists of the two-kerne
     int *chunk_next;                   // [pool]  chunk -> next chunk of the same tile
     uint2 *qa;                         // [pool * 64] (gradient row, pk2)
     float4 *qw;                        // [pool * 64] tap weights
-    int *cursor;                       // [1] chunks handed out
+    int *cursor;                       // [0] chunks handed out, [1] overflow flag (a list chunk did not fit the pool)
     int *work;                         // [32] tile counters of the persistent accumulate kernel (one per channel block)
-    int pool, total_tiles;
+    int pool, total_tiles, pix_group;
 };
 struct TParams {
     TSet s[kMaxSets];
     TMap m[kMaxMaps];
     int *deg_list;                     // [0] = count, then (set << 24 | box) entries
     BinWs bin;
+    size_t range_bytes;                // the sets' `range` arrays are one block of this size, starting at s[0].range
     int nsets, nmaps, accumulate, collapse;
 };
 

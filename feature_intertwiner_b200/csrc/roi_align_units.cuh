@@ -1,5 +1,4 @@
-// Per-unit device code of the NHWC RoIAlign kernels, shared by roi_align.cu (plain and level-batched launches) and
-// roi_align_bwd_banded.cu (L2-resident banded backward).  One unit = (box r, crop row i, 128-channel slab) = one warp.
+// Per-unit device code of the NHWC RoIAlign kernels of roi_align.cu (plain and level-batched launches).  One unit = (box r, crop row i, 128-channel slab) = one warp.
 #pragma once
 #include "fi_common.cuh"
 
@@ -25,7 +24,7 @@ __device__ __forceinline__ AxisTap shfl_tap(const AxisTap &t, int src) {
 // Overlap between neighbouring samples / rows / boxes is left to L1 and L2.
 struct FwdSet {                  // one forward crop set (device view)
     const float *image, *boxes;
-    const int *box_ind, *dst_row;
+    const int *box_ind, *dst_row, *R_dev;     // R_dev: NULL, or the actual number of boxes on the device (units past it exit)
     float *crops, *crops2;
     int B, H, W, C, ph, pw, slabs;
     float extrap;
@@ -44,6 +43,7 @@ __device__ __forceinline__ void fwd_unit(const FwdSet &S, long u, int lane) {
     const int slab = (int)(u % slabs);
     const long q = u / slabs;
     const int r = (int)(q / ph), i = (int)(q - (long)r * ph);
+    if (S.R_dev && r >= *S.R_dev) return;
     const int b = box_ind[r];
     const long orow = dst_row ? (long)dst_row[r] : (long)r;
     const int coff = slab * 128 + lane * 4;

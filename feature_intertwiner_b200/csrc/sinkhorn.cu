@@ -523,7 +523,7 @@ FI_API int fi_sinkhorn(const float *x, const float *y, int n_problems, int N, in
     if (n_problems == 0) return ok();
     FI_REQUIRE(x && y && loss, "fi_sinkhorn: null pointer");
     FI_REQUIRE((grad_x == nullptr) == (grad_y == nullptr), "fi_sinkhorn: grad_x and grad_y must both be given or both be NULL");
-    if (N == 256 && D == 1 && getenv("FI_SINKHORN_GENERIC") == nullptr) {      // RoI-level loss: K in registers
+    if (N == 256 && D == 1 && !option(FI_OPT_SINKHORN_GENERIC)) {      // RoI-level loss: K in registers
         cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(float) * n_problems, stream);
         if (e != cudaSuccess) { set_error(FI_ERR_CUDA, "fi_sinkhorn: memset: %s", cudaGetErrorString(e)); return FI_ERR_CUDA; }
         cudaLaunchConfig_t cfg = {};

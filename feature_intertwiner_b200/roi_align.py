@@ -10,6 +10,9 @@ Both accept the image in either memory format: contiguous NCHW (the reference's)
 ``torch.channels_last`` (the native one here -- see csrc/roi_align.cu); crops come back in the same format,
 logical shape ``[R, C, crop_h, crop_w]`` either way.
 """
+import ctypes as C
+import os
+
 import torch
 from torch import nn
 
@@ -49,25 +52,27 @@ _SETS_BY_SHAPE = {}
 
 
 class _Timed(object):
-    def __init__(self, kernel, **meta):
+    def __init__(self, kernel, stream=None, **meta):
         self.rec = None
+        self.stream = stream                         # the events go on the stream the kernels are launched on
         if _PROFILE is not None:
             if "sets" in meta:
                 # Keep the tensors of ONE launch per shape signature (they are only needed afterwards, to count the distinct tap
                 # pixels); holding every step's box lists alive stops the caching allocator from recycling the split buffers,
                 # and the fresh cudaMalloc segments it then needs showed up as 5-100 ms steps in bench.py.
-                sig = (kernel,) + tuple((st["im_size"], st["crop"], int(st["boxes"].size(0)), bool(st.get("dual"))) for st in meta["sets"])
+                sig = (kernel,) + tuple((st["im_size"], st["crop"], int(st["boxes"].size(0)), bool(st.get("dual")), st.get("count") is not None)
+                                        for st in meta["sets"])
                 _SETS_BY_SHAPE.setdefault(sig, meta["sets"])
                 meta = dict(like=sig)
             self.rec = dict(kernel=kernel, start=_event(), end=_event(), **meta)
 
     def __enter__(self):
         if self.rec is not None:
-            self.rec["start"].record()
+            self.rec["start"].record(self.stream)
 
     def __exit__(self, *exc):
         if self.rec is not None:
-            self.rec["end"].record()
+            self.rec["end"].record(self.stream)
             _PROFILE.append(self.rec)
 
 
@@ -91,6 +96,9 @@ def algorithmic_bytes(rec):
     B, Cc, H, W = rec["im_size"]
     ph, pw = rec["crop"]
     R = rec["boxes"].size(0)
+    if rec.get("count") is not None:                   # device-side list length: only the live boxes move bytes
+        R = min(R, int(rec["count"].item()))
+        rec = dict(rec, boxes=rec["boxes"][:R], box_ind=rec["box_ind"][:R])
     base = 4 * Cc * R * ph * pw * (2 if rec.get("dual") else 1) + 20 * R
     if rec["kernel"].startswith("crop_bwd"):
         return base + 4 * Cc * B * H * W
@@ -247,10 +255,87 @@ def crop_pair(image, boxes, box_ind, dst_row, out_a, size_a, out_b, size_b, comp
     return _CropPair.apply(image, boxes, box_ind, dst_row, out_a, out_b, int(size_a), int(size_b), bool(compact_b))
 
 
+# ---- backward planning at forward time ---------------------------------------------------------------------------------
+# The per-tile sample lists of the backward (tile_prep + bin_enumerate, ~15 % of its time) depend on the boxes only.  They
+# are built right after the forward launch, on a side stream, into a torch-allocated workspace that the autograd node keeps:
+# the work overlaps with whatever runs between forward and backward (critic, loss head) and the backward proper is
+# tile_collapse + accumulate.  FI_PLAN_AT_FORWARD=0 (or plan_at_forward(False)) builds the lists inside backward instead.
+_PLAN = {"at_forward": os.environ.get("FI_PLAN_AT_FORWARD", "1") != "0", "side_stream": os.environ.get("FI_PLAN_STREAM", "side") == "side"}
+_SIDE_STREAMS = {}
+
+
+def plan_at_forward(on=True, side_stream=True):
+    old = dict(_PLAN)
+    _PLAN["at_forward"], _PLAN["side_stream"] = bool(on), bool(side_stream)
+    return old
+
+
+def _side_stream(dev):
+    key = (dev.type, dev.index)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[key]
+
+
+def _bwd_sets(keep, live, dual, g_images=None, grads=None):
+    """(BwdSet array, indices of the planned sets).  Without gradients (plan time) maps and second sources are named by
+    distinct aligned placeholders: only WHICH sets share a map / have two sources matters there."""
+    sets = []
+    for k, kp in enumerate(keep):
+        if not live[k]:
+            continue
+        B, Cc, H, W = kp["im_size"]
+        P = kp["crop"][0]
+        if grads is None:
+            gi, g1, g2 = 16 * (kp["image"] + 1), 16, (16 if dual[k] else None)
+        else:
+            gi, (g1, g2) = _lib.ptr(g_images[kp["image"]]), grads[k]
+        rows = kp["dst_row"] if kp["scattered"] else None
+        sets.append(_lib.BwdSet(gi, g1, g2, _lib.ptr(kp["boxes"]), _lib.ptr(kp["box_ind"]), _lib.ptr(rows), B, H, W, Cc, kp["cap"], P, P,
+                                _lib.ptr(kp["count"])))
+    return (_lib.BwdSet * len(sets))(*sets) if sets else None
+
+
+class _BwdPlan(object):
+    """Workspace + opaque fi_bwd_plan of one crop_sets pass, and the event that says the lists are built."""
+
+    def __init__(self, keep, live, dual, exact, max_entries, dev):
+        self.live, self.dual, self.exact, self.ok = list(live), list(dual), int(exact), False
+        self.ws, self.event = None, None
+        arr = _bwd_sets(keep, live, dual)
+        if arr is None:
+            return
+        L = _lib.lib()
+        nbytes = L.fi_crop_sets_backward_workspace(arr, len(arr), self.exact, int(max_entries))
+        if nbytes == 0:
+            return                                      # these sets take the reduction kernels: nothing to plan
+        self.ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        self.plan = _lib.BwdPlan()
+        cur = torch.cuda.current_stream(dev)
+        side = _side_stream(dev) if _PLAN["side_stream"] else cur
+        if side is not cur:
+            side.wait_stream(cur)                       # boxes / counts come from kernels queued on the current stream
+            self.ws.record_stream(side)
+        with torch.cuda.device(dev), _Timed("crop_bwd_lists", stream=side, alg_bytes=0):
+            rc = L.fi_crop_sets_backward_plan(arr, len(arr), self.exact, int(max_entries), _lib.ptr(self.ws), nbytes, C.byref(self.plan),
+                                              side.cuda_stream)
+        if rc == -3:
+            return
+        _lib.check(rc)
+        if side is not cur:
+            self.event = torch.cuda.Event()
+            self.event.record(side)
+        self.n = len(arr)
+        self.ok = True
+
+    def overflowed(self, dev):
+        return _lib.lib().fi_crop_sets_backward_overflow(C.byref(self.plan), _lib.stream_ptr(dev)) == 1
+
+
 class _CropSets(torch.autograd.Function):
     """Every RoIAlign of one Dev.forward pass as ONE autograd node and ONE launch each way (fi_crop_sets_forward /
-    fi_crop_sets_backward): the per-level calls of lib/sub_module.py:429-600 are far too small to fill a B200 one at a
-    time (a few hundred boxes on the 26x42 map of P5).  apply(plan, *images, *outs)."""
+    fi_crop_sets_backward_plan + _run): the per-level calls of lib/sub_module.py:429-600 are far too small to fill a B200 one
+    at a time (a few hundred boxes on the 26x42 map of P5).  apply(plan, *images, *outs)."""
 
     @staticmethod
     def forward(ctx, plan, *tensors):
@@ -273,6 +358,9 @@ class _CropSets(torch.autograd.Function):
             B, Cc, H, W = im.shape
             boxes, box_ind = _prep_boxes(sp["boxes"], sp["box_ind"], dev)
             R, P = boxes.size(0), sp["size"]
+            count = sp.get("count")
+            if count is not None:
+                count = count.detach().to(device=dev, dtype=torch.int32).reshape(-1)[:1].contiguous()
             dst_row = None if sp["dst_row"] is None else sp["dst_row"].to(device=dev, dtype=torch.int32).contiguous()
             out = outs[sp["out"]] if sp["out"] is not None else None
             if out is not None and not (out.is_contiguous(memory_format=cl) and tuple(out.shape[1:]) == (Cc, P, P) and out.dtype == torch.float32):
@@ -281,15 +369,22 @@ class _CropSets(torch.autograd.Function):
             compacts.append(comp)
             primary, second = (out, comp) if out is not None else (comp, None)
             arr[k] = _lib.FwdSet(_lib.ptr(im), _lib.ptr(boxes), _lib.ptr(box_ind), _lib.ptr(dst_row) if out is not None else None,
-                                 _lib.ptr(primary), _lib.ptr(second), B, H, W, Cc, R, P, P, float(sp.get("extrapolation", 0.0)))
+                                 _lib.ptr(primary), _lib.ptr(second), B, H, W, Cc, R, P, P, float(sp.get("extrapolation", 0.0)), _lib.ptr(count))
             keep.append(dict(boxes=boxes, box_ind=box_ind, dst_row=dst_row, im_size=(B, Cc, H, W), crop=(P, P), dual=(out is not None and comp is not None),
-                             img_offsets=sp.get("img_offsets")))
+                             img_offsets=sp.get("img_offsets"), image=sp["image"], cap=R, count=count, scattered=out is not None,
+                             out=sp["out"]))
         with torch.cuda.device(dev), _Timed("crop_fwd_nhwc", sets=keep):
             _lib.check(_lib.lib().fi_crop_sets_forward(arr, len(plan["sets"]), _lib.stream_ptr(dev)))
         ctx.mark_dirty(*outs)
         ctx.set_materialize_grads(False)
         ctx.plan, ctx.keep = plan, keep
         ctx.comp_slots = [k for k, c in enumerate(compacts) if c is not None]
+        ctx.bwd = None
+        if _PLAN["at_forward"] and any(ctx.needs_input_grad[1:1 + n_img]) and _lib.get_option("bwd_form") != 3:
+            # assume every output will receive a gradient (backward re-plans if not)
+            live = [kp["cap"] > 0 for kp in keep]
+            bp = _BwdPlan(keep, live, [kp["dual"] for kp in keep], _lib.lib().fi_get_deterministic(), plan.get("max_entries", 0), dev)
+            ctx.bwd = bp if bp.ok else None
         return tuple(outs) + tuple(c for c in compacts if c is not None)
 
     @staticmethod
@@ -300,49 +395,63 @@ class _CropSets(torch.autograd.Function):
         g_outs = [None if g is None else g.contiguous(memory_format=cl) for g in grads[:n_out]]
         g_comp = {k: (None if g is None else g.contiguous(memory_format=cl)) for k, g in zip(ctx.comp_slots, grads[n_out:])}
         dev = keep[0]["boxes"].device
-        # one standalone tensor per dense gradient map (autograd can then hand it to the leaf without a copy); the C entry
-        # zero-fills each distinct map once
-        sizes = {}
-        for k, sp in enumerate(plan["sets"]):
-            sizes[sp["image"]] = keep[k]["im_size"]
-        numel = {i: sz[0] * sz[1] * sz[2] * sz[3] for i, sz in sizes.items()}
+        # one standalone tensor per dense gradient map (autograd can then hand it to the leaf without a copy); the kernels
+        # write every pixel of every named map once (the reduction fallback zero-fills first)
+        sizes = {kp["image"]: kp["im_size"] for kp in keep}
         g_images = {i: torch.empty(sizes[i], device=dev, dtype=torch.float32, memory_format=cl) for i in sorted(sizes)}
-        sets, nbytes, offsets = [], 0, []
-        for k, sp in enumerate(plan["sets"]):
-            kp = keep[k]
-            B, Cc, H, W = kp["im_size"]
-            P = kp["crop"][0]
-            R = kp["boxes"].size(0)
-            gs = g_outs[sp["out"]] if sp["out"] is not None else None
+        live, dual, srcs, nbytes = [], [], [], 0
+        for k, kp in enumerate(keep):
+            gs = g_outs[kp["out"]] if kp["out"] is not None else None
             gc = g_comp.get(k)
-            if gs is not None:
-                g1, g2, rows = gs, gc, kp["dst_row"]
-            elif gc is not None:
-                g1, g2, rows = gc, None, None
-            else:
+            if kp["cap"] == 0 or (gs is None and gc is None):
+                live.append(False); dual.append(False); srcs.append(None)
                 continue
-            sets.append(_lib.BwdSet(_lib.ptr(g_images[sp["image"]]), _lib.ptr(g1), _lib.ptr(g2), _lib.ptr(kp["boxes"]), _lib.ptr(kp["box_ind"]),
-                                    _lib.ptr(rows), B, H, W, Cc, R, P, P))
-            offsets.append(kp.get("img_offsets"))
-            nbytes += 4 * Cc * R * P * P * (2 if g2 is not None else 1) + 20 * R
-        nbytes += 4 * sum(numel.values())
-        if sets:
+            live.append(True)
+            if gs is not None:
+                dual.append(gc is not None); srcs.append((_lib.ptr(gs), _lib.ptr(gc)))
+            else:
+                dual.append(False); srcs.append((_lib.ptr(gc), None))
+                if kp["scattered"]:                      # only the compact copy received a gradient: its rows are in box order
+                    kp = dict(kp, scattered=False)
+                    keep = keep[:k] + [kp] + keep[k + 1:]
+            Cc, P = kp["im_size"][1], kp["crop"][0]
+            nbytes += 4 * Cc * kp["cap"] * P * P * (2 if dual[-1] else 1) + 20 * kp["cap"]
+        touched = {keep[k]["image"] for k in range(len(keep)) if live[k]}
+        nbytes += 4 * sum(sizes[i][0] * sizes[i][1] * sizes[i][2] * sizes[i][3] for i in touched)
+        if any(live):
             L = _lib.lib()
+            arr = _bwd_sets(keep, live, dual, g_images, srcs)
+            exact = L.fi_get_deterministic()
+            bp = ctx.bwd
+            usable = bp is not None and bp.live == live and bp.dual == dual and bp.exact == exact and keep is ctx.keep \
+                and _lib.get_option("bwd_form") != 3
+            if not usable and _lib.get_option("bwd_form") != 3:
+                old = plan_at_forward(True, side_stream=False)         # lists built here, on this stream
+                try:
+                    bp = _BwdPlan(keep, live, dual, exact, plan.get("max_entries", 0), dev)
+                finally:
+                    _PLAN.update(old)
+                usable = bp.ok
             with torch.cuda.device(dev), _Timed("crop_bwd_nhwc", alg_bytes=nbytes):
-                # tile-owner kernels by default: every map written once (exact arithmetic under set_deterministic)
-                arr = (_lib.BwdSet * len(sets))(*sets)
-                _lib.check(L.fi_crop_sets_backward(arr, len(sets), 1, _lib.stream_ptr(dev)))
-        touched = {st.grads_image for st in sets}
+                if usable:
+                    if bp.event is not None:
+                        torch.cuda.current_stream(dev).wait_event(bp.event)
+                    _lib.check(L.fi_crop_sets_backward_run(C.byref(bp.plan), arr, len(arr), 1, _lib.stream_ptr(dev)))
+                else:                                                  # reduction kernels (shapes the tile-owner form does not take)
+                    _lib.check(L.fi_crop_sets_backward(arr, len(arr), 1, _lib.stream_ptr(dev)))
         for i, gi in g_images.items():
-            if _lib.ptr(gi) not in touched:
+            if i not in touched:
                 gi.zero_()                       # a map none of whose crops received a gradient
         return (None,) + tuple(g_images.get(i) for i in range(n_img)) + tuple(g_outs)
 
 
-def crop_sets(specs):
+def crop_sets(specs, max_entries=0):
     """specs: list of dict(image=Tensor, boxes=[R,4], box_ind=[R], size=int, out=Tensor|None, dst_row=[R]|None, compact=bool).
     A set with ``out`` writes crop r into row ``dst_row[r]`` of ``out`` (several sets may share one ``out``) and, with
     ``compact``, also returns the compact [R,C,size,size] crop; a set without ``out`` returns the compact crop only.
+    ``count`` (optional, a device int32): the actual number of boxes of the set, ``boxes.size(0)`` then being the capacity of the
+    lists -- no host ever needs to know the list lengths (fixed shapes, CUDA-graph capturable); rows past the count are not written.
+    ``max_entries``: see fi_crop_sets_backward_plan (a caller's tighter bound on the backward's sample lists).
     Returns (outs_by_spec, compacts_by_spec): per spec the (updated) ``out`` or None, and the compact crop or None."""
     images, outs, sets = [], [], []
 
@@ -356,10 +465,10 @@ def crop_sets(specs):
         sets.append(dict(image=slot(images, sp["image"]), out=(slot(outs, sp["out"]) if sp.get("out") is not None else None),
                          boxes=sp["boxes"], box_ind=sp["box_ind"], dst_row=sp.get("dst_row"), size=int(sp["size"]),
                          compact=bool(sp.get("compact", False)), extrapolation=float(sp.get("extrapolation", 0.0)),
-                         img_offsets=sp.get("img_offsets")))
+                         img_offsets=sp.get("img_offsets"), count=sp.get("count")))
         if sets[-1]["out"] is not None and sets[-1]["dst_row"] is None:
             raise _lib.FiError("crop_sets: a set with `out` needs `dst_row`")
-    plan = dict(n_img=len(images), n_out=len(outs), sets=sets)
+    plan = dict(n_img=len(images), n_out=len(outs), sets=sets, max_entries=int(max_entries))
     res = _CropSets.apply(plan, *images, *outs)
     new_outs, comps = res[:len(outs)], list(res[len(outs):])
     out_by_spec = [new_outs[st["out"]] if st["out"] is not None else None for st in sets]

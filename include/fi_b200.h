@@ -15,6 +15,8 @@
 #ifndef FI_B200_H
 #define FI_B200_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -35,6 +37,22 @@ int fi_abi_version(void);
 const char *fi_last_error(void); /* thread-local, never NULL */
 int fi_last_status(void);        /* status of the last call made by this thread */
 unsigned long long fi_kernel_launches(void); /* kernels this library has launched in this process */
+
+/* Process-wide kernel-selection switches (experiments, A/B measurements, tests).  Each option is initialised ONCE, on
+ * first use, from its environment variable and can be changed at run time; no entry point calls getenv() per launch.
+ * fi_set_option returns the previous value (FI_ERR_INVALID for an unknown option / value). */
+#define FI_OPT_BWD_FORM 0         /* NHWC RoIAlign backward: 0 bulk-copy staged register accumulation (default), 1 shared-memory
+                                     accumulate kernel [FI_BWD_ACC=smem], 2 fused single tile kernel [FI_BWD_TILE=fused],
+                                     3 vector reductions [FI_BWD=red] */
+#define FI_OPT_TILE_SHAPE 1       /* tile of forms 1 and 2: 0 = 4x8 (default), 1 = 4x4 [FI_TILE=4x4], 2 = 2x8 [FI_TILE=2x8] */
+#define FI_OPT_NCHW_TMA 2         /* 1: TMA-staged NCHW forward [FI_NCHW_TMA=1] */
+#define FI_OPT_SINKHORN_GENERIC 3 /* 1: generic shared-memory Sinkhorn kernel also for N=256, D=1 [FI_SINKHORN_GENERIC] */
+#define FI_OPT_PIX_CFG 4          /* form 0, ring shape (slots per batch x batches, CTAs per SM): 0 = 32x3,2 (default); 1 = 16x6,2;
+                                     2 = 32x2,3; 3 = 16x4,3 [FI_PIX_CFG] */
+#define FI_OPT_PIX_GROUP 5        /* form 0, tiles per work ticket minus 1: 0..7 [FI_PIX_GROUP] */
+#define FI_OPT_COUNT 6
+int fi_set_option(int option, int value);
+int fi_get_option(int option);
 
 /* ---------------------------------------------------------------------------------------------
  * 1. Reference-named launchers (exact signatures).
@@ -139,6 +157,7 @@ typedef struct fi_fwd_set {
     float *crops_compact;    /* NULL, or a second copy at row r */
     int batch, image_height, image_width, depth, num_boxes, crop_height, crop_width;
     float extrapolation_value;
+    const int *num_boxes_dev; /* NULL, or a device int: the actual number of boxes (<= num_boxes = capacity); rows past it are not written */
 } fi_fwd_set;
 int fi_crop_sets_forward(const fi_fwd_set *sets, int num_sets, cudaStream_t stream);
 
@@ -150,10 +169,31 @@ typedef struct fi_bwd_set {
     const int *box_ind;
     const int *src_row;
     int batch, image_height, image_width, depth, num_boxes, crop_height, crop_width;
+    const int *num_boxes_dev; /* NULL, or a device int: the actual number of boxes (<= num_boxes, which then is the capacity
+                                 of boxes / box_ind / src_row).  Lets a caller keep list lengths on the device (no host sync,
+                                 fixed shapes for CUDA graphs).  Tile-owner forms only. */
 } fi_bwd_set;
 /* zero_first != 0: the maps are overwritten (the tile-owner kernels write every pixel once; the reduction fallback
- * zero-fills each distinct grads_image first); zero_first == 0: the sums are added onto the existing contents. */
+ * zero-fills each distinct grads_image first); zero_first == 0: the sums are added onto the existing contents.
+ * Scratch memory: a grow-only block per (device, stream) inside the library; it cannot grow while `stream` is being
+ * captured -- use the plan / run pair below there. */
 int fi_crop_sets_backward(const fi_bwd_set *sets, int num_sets, int zero_first, cudaStream_t stream);
+
+/* The same backward in two steps on caller-owned scratch memory:
+ *   plan  tile_prep + bin_enumerate: per-tile sample lists.  Needs boxes / box_ind / src_row / sizes and WHETHER grads2 will
+ *         be given (any non-NULL value), not the gradients: it can run at forward time, on another stream.
+ *   run   tile_collapse + accumulate: reads the gradients named by `sets` (grads, grads2, grads_image may differ from plan
+ *         time; everything else must match the plan, FI_ERR_INVALID otherwise) and writes every map pixel once.
+ * `exact` as fi_set_deterministic.  max_entries > 0: caller's bound on the number of list entries (4 per sample of a
+ * one-source set, 8 of a two-source set, + 32 per box) when it knows better than the per-set capacities, e.g. because the
+ * sets partition the boxes; fi_crop_sets_backward_overflow tells (with a stream synchronisation) whether it was too small.
+ * fi_crop_sets_backward_workspace returns 0 when the sets need the reduction kernels (plan then returns FI_ERR_UNSUPPORTED). */
+typedef struct fi_bwd_plan { unsigned long long opaque[640]; } fi_bwd_plan;
+size_t fi_crop_sets_backward_workspace(const fi_bwd_set *sets, int num_sets, int exact, long max_entries);
+int fi_crop_sets_backward_plan(const fi_bwd_set *sets, int num_sets, int exact, long max_entries, void *workspace,
+                               size_t workspace_bytes, fi_bwd_plan *plan, cudaStream_t stream);
+int fi_crop_sets_backward_run(const fi_bwd_plan *plan, const fi_bwd_set *sets, int num_sets, int zero_first, cudaStream_t stream);
+int fi_crop_sets_backward_overflow(const fi_bwd_plan *plan, cudaStream_t stream);
 
 /* Integer taps of every sample, taps[num_boxes,crop_h,crop_w,5] = (y_lo,y_hi,x_lo,x_hi,inside): the "RoI
  * indices" the parity bar requires bit-exact (crop_and_resize_kernel.cu:40-70). */

@@ -166,7 +166,7 @@ def intertwiner_cases(ot_mod):
 
     # ---- _assign_feat2cls (feat given as [k,1024]: the [k,1024,1,1] form of the caller cannot be slice-assigned on torch 2.x)
     self_ = types.SimpleNamespace(num_classs=81)
-    for tag, k in (("a", 1), ("b", 37), ("c", 500)):
+    for tag, k in (("a", 1), ("b", 37), ("c", 150)):
         gt = torch.randint(0, 81, (k,), generator=g)
         gt[: k // 3] = 0
         feat = torch.rand(k, 1024, generator=g)
@@ -176,15 +176,16 @@ def intertwiner_cases(ot_mod):
         out["seg_%s_mean" % tag], out["seg_%s_cnt" % tag] = f.numpy(), c.numpy()
 
     # ---- _merge_feat_vec + meta_loss over three iterations
+    Fd = 64                                   # meta_loss takes the feature width from the buffer; 64 keeps the fixture small
     torch.manual_seed(2000)
     cfg_ot = types.SimpleNamespace(DEV=types.SimpleNamespace(OT_ONE_DIM_FORM="conv"))
-    ot = ot_mod.OptTrans(cfg_ot, ch_x=1024, L=5).eval()
+    ot = ot_mod.OptTrans(cfg_ot, ch_x=Fd, L=5).eval()
     for k, v in ot.state_dict().items():
         out["meta_ot_sd_" + k] = v.numpy()
 
     def stats(G, S, density):
         cnt = (torch.rand(G, S, 1, 81, generator=g) < density).float() * torch.randint(1, 9, (G, S, 1, 81), generator=g).float()
-        feat = torch.rand(G, S, 1024, 81, generator=g) * (cnt > 0).float()
+        feat = torch.rand(G, S, Fd, 81, generator=g) * (cnt > 0).float()
         return feat, cnt
 
     f, c = stats(2, 3, 0.5)
@@ -197,17 +198,20 @@ def intertwiner_cases(ot_mod):
             for inst in (False, True):
                 if inst and lc == "ot":
                     continue            # 3 x n Sinkhorn problems per instance: covered at class level
+                if B > 1 and not inst:
+                    continue            # the reference's class-level match is shape-invalid for BUFFER_SIZE > 1 (lib/model.py:180,
+                                        # `buffer_cnt.squeeze()` is [B,81]): it raises, there is nothing to pin
                 tag = "meta_B%d_%s_%s" % (B, lc, "inst" if inst else "cls")
                 model = types.SimpleNamespace(
                     config=types.SimpleNamespace(DEV=types.SimpleNamespace(INST_LOSS=inst, LOSS_CHOICE=lc)),
-                    buffer=torch.zeros(B, 1024, 81), buffer_cnt=torch.zeros(B, 1, 81), ot_loss=ot)
+                    buffer=torch.zeros(B, Fd, 81), buffer_cnt=torch.zeros(B, 1, 81), ot_loss=ot)
                 model._merge_feat_vec = ns["_merge_feat_vec"]
                 model._assign_from_buffer = ns["_assign_from_buffer"]
                 for it in range(3):
                     bf, bc = stats(1, 3, 0.3 if it == 0 else 0.6)
                     sf, sc = stats(1, 3, 0.4)
                     n_inst = 40
-                    so = torch.rand(n_inst, 1024, generator=g)
+                    so = torch.rand(n_inst, Fd, generator=g)
                     sg = torch.randint(0, 81, (n_inst,), generator=g)
                     sg[::3] = 0
                     with rx.torch03(), torch.no_grad():
@@ -220,8 +224,9 @@ def intertwiner_cases(ot_mod):
     # empty comparison set -> zeros(1) (lib/model.py:208-209) is a known answer; torch 0.3's "empty tensor has no size" has no 2.x analogue
 
     # ---- apply_box_deltas / clip_boxes (tools/box_utils.py, imported functions exec'd as they are)
-    anchors = torch.rand(2, 400, 4, generator=g) * 600
-    anchors[:, :, 2:] = anchors[:, :, :2] + torch.rand(2, 400, 2, generator=g) * 300 + 1
+    priors = torch.rand(400, 4, generator=g) * 600
+    priors[:, 2:] = priors[:, :2] + torch.rand(400, 2, generator=g) * 300 + 1
+    anchors = priors.unsqueeze(0).expand(2, 400, 4).contiguous()            # lib/layers.py:96
     deltas = torch.randn(2, 400, 4, generator=g) * 0.3
     window = torch.tensor([0.0, 0.0, 832.0, 1344.0])
     with rx.torch03():

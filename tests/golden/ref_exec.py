@@ -7,6 +7,9 @@ UNMODIFIED inside `torch03()`, a context that restores the PyTorch-0.3 behaviour
 
 * no 0-dim tensors: indexing / squeeze / full reductions give 1-element 1-D tensors (`window[0].data[0]`, `_idx.size(0)`);
 * comparisons give uint8 "ByteTensor"s, so `(a > 0) + (b > 0) == 2` (lib/model.py:180-181) means AND;
+* `x in tensor` is `(x == tensor).any()` for any x, numpy arrays included (lib/model.py:173);
+* `buf[:-1] = buf[1:]` (lib/model.py:161-164) is a front-to-back element copy, i.e. a shift: the value is cloned first
+  (torch 2.x refuses overlapping in-place copies);
 * `Variable(x, ...)` is x, `.cuda()` is the identity (this container has no GPU).
 
 Nothing here is imported by the tests or the product: it only feeds tests/golden/make_golden.py.
@@ -30,7 +33,7 @@ def _keep1(t):
 @contextlib.contextmanager
 def torch03():
     T = torch.Tensor
-    saved = {n: getattr(T, n) for n in ("__getitem__", "squeeze", "cuda", "__gt__", "__lt__", "__ge__", "__le__", "__eq__", "__ne__", "__hash__")}
+    saved = {n: getattr(T, n) for n in ("__getitem__", "squeeze", "cuda", "__gt__", "__lt__", "__ge__", "__le__", "__eq__", "__ne__", "__hash__", "__contains__", "__setitem__")}
     getitem, squeeze = T.__getitem__, T.squeeze
 
     def _cmp(name):
@@ -44,9 +47,12 @@ def torch03():
     T.__getitem__ = lambda self, idx: _keep1(getitem(self, idx))
     T.squeeze = lambda self, *a, **k: _keep1(squeeze(self, *a, **k))
     T.cuda = lambda self, *a, **k: self
+    setitem = T.__setitem__
+    T.__setitem__ = lambda self, idx, val: setitem(self, idx, val.clone() if isinstance(val, torch.Tensor) else val)
     for n in ("__gt__", "__lt__", "__ge__", "__le__", "__eq__", "__ne__"):
         setattr(T, n, _cmp(n))
     T.__hash__ = lambda self: id(self)          # defining __eq__ on a class drops its hash
+    T.__contains__ = lambda self, el: bool(saved["__eq__"](self, torch.as_tensor(el).to(self.dtype)).any())
     try:
         yield
     finally:

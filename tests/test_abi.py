@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_symbols():
     src = open(os.path.join(ROOT, "include", "fi_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    names = re.findall(r"^\s*(?:const\s+)?(?:unsigned long long|int|void|char)\s*\*?\s*(\w+)\s*\(", src, flags=re.M)
+    names = re.findall(r"^\s*(?:const\s+)?(?:unsigned long long|size_t|int|void|char)\s*\*?\s*(\w+)\s*\(", src, flags=re.M)
     return sorted(set(names))
 
 
@@ -44,6 +44,7 @@ def test_library_is_sm_100a_and_uses_vector_reductions():
     assert "REDG.E.ADD.F32x4" in sass          # 128-bit vector reduction in the NHWC backward
     assert "UTMALDG.4D" in sass                # cp.async.bulk.tensor.4d (TMA) in the NCHW region-tile forward
     assert "SYNCS.ARRIVE.TRANS64" in sass      # mbarrier expect_tx
+    assert "UBLKCP.S.G" in sass                # cp.async.bulk global -> shared: gradient rows of the NHWC backward (roi_align_bwd_pix.cu)
 
 
 def test_argument_validation_needs_no_gpu():

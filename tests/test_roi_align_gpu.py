@@ -340,7 +340,7 @@ def test_full_size_properties_c5():
         fi.set_deterministic(old)
 
 
-def test_nchw_tma_path_matches_plain_kernel(monkeypatch):
+def test_nchw_tma_path_matches_plain_kernel():
     """The TMA-staged NCHW forward (csrc/roi_align_nchw_tma.cu) is bit-identical to the plain NCHW kernel and to the oracle,
     over every tile shape (8/16/32 px footprints), the direct-load fallback (footprint > 32 px) and all-outside boxes."""
     fi = _fi()
@@ -360,21 +360,25 @@ def test_nchw_tma_path_matches_plain_kernel(monkeypatch):
     for P in (7, 14, (3, 5)):
         ph, pw = (P, P) if isinstance(P, int) else P
         want = clib.oracle_crop_and_resize_fwd(image.numpy(), boxes.numpy(), ind.numpy(), ph, pw, 0.25)
-        monkeypatch.setenv("FI_NCHW_TMA", "1")
-        got = fi.crop_and_resize(image.cuda(), boxes.cuda(), ind.cuda(), ph, pw, 0.25)
-        np.testing.assert_array_equal(got.cpu().numpy(), want)
-        monkeypatch.setenv("FI_NCHW_TMA", "0")
-        plain = fi.crop_and_resize(image.cuda(), boxes.cuda(), ind.cuda(), ph, pw, 0.25)
-        monkeypatch.delenv("FI_NCHW_TMA")
+        old = fi.set_option("nchw_tma", 1)
+        try:
+            got = fi.crop_and_resize(image.cuda(), boxes.cuda(), ind.cuda(), ph, pw, 0.25)
+            np.testing.assert_array_equal(got.cpu().numpy(), want)
+            fi.set_option("nchw_tma", 0)
+            plain = fi.crop_and_resize(image.cuda(), boxes.cuda(), ind.cuda(), ph, pw, 0.25)
+        finally:
+            fi.set_option("nchw_tma", old)
         assert torch.equal(plain, got)
 
 
-@pytest.mark.parametrize("mode", ["tile", "exact", "fused", "fused_exact", "red", "det"])
+@pytest.mark.parametrize("mode", ["pix", "pix_exact", "smem", "smem_exact", "fused", "fused_exact", "red", "pix16", "pix_g8_exact"])
 @pytest.mark.parametrize("shape", [(2, 256, 26, 42, 150), (3, 128, 9, 11, 40), (1, 384, 33, 70, 300)])
-def test_backward_formulations_agree(monkeypatch, mode, shape):
-    """Every formulation of the NHWC backward (csrc/roi_align_bwd_tile.cu: enumerate + accumulate kernels [default] and the fused
-    single kernel, each with default and exact arithmetic; reductions) on the same maps: ragged tile edges (H, W not multiples of 4 / 8), 1-3 channel slabs, many boxes per tile (> the 64-entry hit
-    list), zero-padded / inverted / outside boxes.  The exact modes are bit-identical to the serial CPU reference."""
+def test_backward_formulations_agree(mode, shape):
+    """Every formulation of the NHWC backward on the same maps -- tile-owner lists + the bulk-copy staged register-accumulating
+    kernel (csrc/roi_align_bwd_pix.cu, default; also with 16-slot batches / 8-tile tickets), + the shared-memory accumulate
+    kernel, the fused single kernel (csrc/roi_align_bwd_tile.cu), each with default and exact arithmetic; vector reductions --
+    over ragged tile edges (H, W not multiples of 4 / 8), 128 / 256 / 384 channels, many boxes per tile (> one 64-entry list
+    chunk), zero-padded / inverted / outside boxes.  The exact modes are bit-identical to the serial CPU reference."""
     fi = _fi()
     B, C, H, W, R = shape
     image, rois, box_ind = _case(77, B, C, H, W, R, zero_rows=8)
@@ -382,25 +386,25 @@ def test_backward_formulations_agree(monkeypatch, mode, shape):
     rois[4] = torch.tensor([-0.5, -0.5, 1.5, 1.5])        # mostly outside
     rois[5] = torch.tensor([0.5, 0.25, 0.5, 0.25])        # degenerate, on one (fractional) position
     g = torch.Generator().manual_seed(6)
+    form = mode.split("_")[0]
+    exact = mode.endswith("_exact")
+    saved = {k: fi.get_option(k) for k in ("bwd_form", "pix_cfg", "pix_group")}
     for P in (7, 14, 16):
         grads = torch.randn(R, C, P, P, generator=g)
         want = clib.oracle_crop_and_resize_bwd(grads.numpy(), rois.numpy(), box_ind.numpy(), tuple(image.shape))
         img = image.cuda().contiguous(memory_format=torch.channels_last).requires_grad_()
-        if mode in ("red", "exact"):
-            monkeypatch.setenv("FI_BWD", mode)
-        if mode.startswith("fused"):
-            monkeypatch.setenv("FI_BWD_TILE", mode.split("_")[0])
-            if mode.endswith("_exact"):
-                monkeypatch.setenv("FI_BWD", "exact")
-        old = fi.set_deterministic(mode == "det")              # the process-wide switch selects the exact arithmetic too
+        fi.set_option("bwd_form", "pix" if form.startswith("pix") else form)
+        fi.set_option("pix_cfg", 1 if form == "pix16" else 0)
+        fi.set_option("pix_group", 7 if "g8" in mode else 1)
+        old = fi.set_deterministic(exact)                   # the process-wide switch selects the exact arithmetic
         try:
             fi.crop_and_resize(img, rois.cuda(), box_ind.cuda(), P, P).backward(grads.cuda().contiguous(memory_format=torch.channels_last))
         finally:
             fi.set_deterministic(old)
-            monkeypatch.delenv("FI_BWD", raising=False)
-            monkeypatch.delenv("FI_BWD_TILE", raising=False)
+            for k, v in saved.items():
+                fi.set_option(k, v)
         got = img.grad.cpu().numpy()
-        if mode in ("exact", "fused_exact", "det"):
+        if exact:
             np.testing.assert_array_equal(got, want)
         else:
             assert_bwd_close(got, grads.numpy(), rois.numpy(), box_ind.numpy(), tuple(image.shape), want)
@@ -443,3 +447,230 @@ def test_tile_backward_full_size_c2_properties():
     for i in range(2):
         assert torch.equal(res["tile"][i], res["tile2"][i]) and torch.equal(res["exact"][i], res["exact2"][i])
         torch.testing.assert_close(res["tile"][i], res["exact"][i], rtol=1e-4, atol=1e-4)
+
+
+def _sets_case(seed=31, B=2, R=180, hw=(26, 42)):
+    from feature_intertwiner_b200 import synth
+    g = torch.Generator().manual_seed(seed)
+    cl = torch.channels_last
+    maps = [torch.randn(B, 256, hw[0] * s, hw[1] * s, generator=g).cuda().contiguous(memory_format=cl) for s in (2, 1)]
+    rois = synth.make_rois(1, R, (hw[0] * 32, hw[1] * 32), g, zero_frac=0.05, straddle_frac=0.03)[0].cuda()
+    ind = torch.randint(0, B, (R,), generator=g, dtype=torch.int32).cuda()
+    rows = torch.randperm(R + 20, generator=g)[:R].int().cuda()
+    return maps, rois, ind, rows
+
+
+def _run_sets(fi, maps, rois, ind, rows, n_live, capacity, use_counts, max_entries=0, grads=None, cnt=None):
+    """Two maps, three sets (7x7 scattered, 14x14 scattered + compact = two-source, 14x14 compact on the second map)."""
+    cl = torch.channels_last
+    xs = [m.clone().requires_grad_() for m in maps]
+    R = rois.size(0)
+    pad = lambda t: torch.cat([t[:n_live], t.new_zeros((capacity - n_live,) + tuple(t.shape[1:]))]) if capacity > n_live else t[:n_live]
+    boxes, bi, rw = pad(rois), pad(ind), pad(rows)
+    if capacity > n_live:                               # garbage past the count must be ignored
+        boxes[n_live:] = 0.37; bi[n_live:] = 99; rw[n_live:] = 0
+    if use_counts and cnt is None:
+        cnt = torch.tensor([n_live], dtype=torch.int32, device="cuda")
+    o7 = torch.zeros(R + 20, 256, 7, 7, device="cuda").contiguous(memory_format=cl)
+    o14 = torch.zeros(R + 20, 256, 14, 14, device="cuda").contiguous(memory_format=cl)
+    specs = [dict(image=xs[0], boxes=boxes, box_ind=bi, size=7, out=o7, dst_row=rw, count=cnt),
+             dict(image=xs[0], boxes=boxes, box_ind=bi, size=14, out=o14, dst_row=rw, compact=True, count=cnt),
+             dict(image=xs[1], boxes=boxes, box_ind=bi, size=14, count=cnt)]
+    outs, comps = fi.crop_sets(specs, max_entries=max_entries)
+    heads = [outs[0], outs[1], comps[1], comps[2]]
+    if grads is None:
+        g = torch.Generator().manual_seed(5)
+        grads = [torch.randn(h.shape, generator=g).cuda().contiguous(memory_format=cl) for h in heads]
+        for gg in grads[2:]:
+            gg[n_live:] = float("nan")                  # rows past the count are never read
+    else:
+        grads = [gr[: h.size(0)] if gr.size(0) >= h.size(0) else torch.cat([gr, gr.new_full((h.size(0) - gr.size(0),) + tuple(gr.shape[1:]), float("nan"))])
+                 for gr, h in zip(grads, heads)]
+        grads = [gr.contiguous(memory_format=cl) for gr in grads]
+    return xs, heads, grads
+
+
+@pytest.mark.parametrize("exact", [False, True])
+def test_crop_sets_device_counts_plan_reuse_and_side_stream(exact):
+    """Lists with a capacity and a device-side count give the same bits as exact-size lists (forward and backward); a plan built
+    at forward time on the side stream == lists built inside backward; running the same plan twice gives the same bits."""
+    fi = _fi()
+    maps, rois, ind, rows = _sets_case()
+    n = 150
+    old = fi.set_deterministic(exact)
+    try:
+        xs_a, heads_a, grads = _run_sets(fi, maps, rois, ind, rows, n, n, use_counts=False)
+        ga = torch.autograd.grad(heads_a, xs_a, grads, retain_graph=True)
+        ga2 = torch.autograd.grad(heads_a, xs_a, grads)                       # the same plan, run again
+        xs_b, heads_b, grads_b = _run_sets(fi, maps, rois, ind, rows, n, 180, use_counts=True, grads=grads)
+        gb = torch.autograd.grad(heads_b, xs_b, grads_b)
+        prev = fi.roi_align.plan_at_forward(False)
+        try:
+            xs_c, heads_c, _ = _run_sets(fi, maps, rois, ind, rows, n, n, use_counts=False)
+            gc = torch.autograd.grad(heads_c, xs_c, grads)
+        finally:
+            fi.roi_align.plan_at_forward(prev["at_forward"], prev["side_stream"])
+    finally:
+        fi.set_deterministic(old)
+    for a, b in zip(heads_a[2:], heads_b[2:]):
+        assert torch.equal(a, b[:n])                                          # compact crops: live rows identical
+    assert torch.equal(heads_a[0], heads_b[0]) and torch.equal(heads_a[1], heads_b[1])
+    for a, a2, b, c in zip(ga, ga2, gb, gc):
+        assert torch.equal(a, a2) and torch.equal(a, b) and torch.equal(a, c)
+        assert torch.isfinite(a).all()
+
+
+def test_crop_sets_backward_overflow_flag_and_graph_capture():
+    """A caller's own (too small) entry bound is detected, never written out of bounds; the plan / run pair on a torch-allocated
+    workspace can be captured into a CUDA graph and replays to the eager result."""
+    fi = _fi()
+    from feature_intertwiner_b200 import roi_align
+    maps, rois, ind, rows = _sets_case(seed=32)
+    xs, heads, grads = _run_sets(fi, maps, rois, ind, rows, 180, 180, use_counts=False, max_entries=4096)
+    node = heads[0].grad_fn
+    want_xs, want_heads, _ = _run_sets(fi, maps, rois, ind, rows, 180, 180, use_counts=False)
+    want = torch.autograd.grad(want_heads, want_xs, grads)
+    torch.autograd.grad(heads, xs, grads)                                      # runs, truncated lists, no crash
+    torch.cuda.synchronize()
+    assert node.bwd.overflowed(maps[0].device)
+    assert not want_heads[0].grad_fn.bwd.overflowed(maps[0].device)
+    # ---- capture forward (+ plan on the side stream) + backward, replay twice
+    old = roi_align.plan_at_forward(True, side_stream=True)
+    cnt = torch.tensor([180], dtype=torch.int32, device="cuda")                # made outside the capture (host -> device copy)
+    try:
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):                                                 # warm-up on the capture stream (allocator, attributes)
+                a, b, c = _run_sets(fi, maps, rois, ind, rows, 180, 180, use_counts=True, grads=grads, cnt=cnt)
+                torch.autograd.grad(b, a, c)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            a, b, c = _run_sets(fi, maps, rois, ind, rows, 180, 180, use_counts=True, grads=grads, cnt=cnt)
+            got = torch.autograd.grad(b, a, c)
+        for _ in range(2):
+            graph.replay()
+        torch.cuda.synchronize()
+    finally:
+        roi_align.plan_at_forward(old["at_forward"], old["side_stream"])
+    for g, w in zip(got, want):
+        assert torch.equal(g, w)
+
+
+@pytest.mark.parametrize("wl_name", ["c2", "c5"])
+def test_full_size_vs_compiled_reference(wl_name):
+    """BASELINE.json sizes (C2: batch 8 x 512 RoIs; C5: batch 4 x 2000 RoIs per GPU, 832x1344, P2 208x336 ... P5 26x42, 256
+    channels): forward AND exact-mode backward of every crop set of a Dev.forward pass, through the level-batched entry
+    (fi.crop_sets: heaviest-first tile order, collapse-free exact lists, > 64-entry chunk chains, two-source sets), against the
+    REFERENCE'S OWN C (lib/roi_align/src/crop_and_resize.c compiled unmodified, oracle/_ref; the restatement that is pinned
+    bit-identical to it where oracle/_ref did not travel).  Bit-exact both ways.  The exact backward equals the serial CPU loop
+    for one set per map, so the sets are run family by family (big 14x14 / small 7x7 / small 14x14 with its two gradient
+    sources pre-added as autograd does in the reference); the default-mode pass over all sets at once must agree with their
+    sum within the summation-order bound."""
+    fi = _fi()
+    from feature_intertwiner_b200 import synth
+    fwd = clib.ref_crop_and_resize_fwd if clib.have_ref() else clib.oracle_crop_and_resize_fwd
+    bwd = clib.ref_crop_and_resize_bwd if clib.have_ref() else clib.oracle_crop_and_resize_bwd
+    wl = synth.WORKLOADS[wl_name]
+    B, R, hw = wl["batch"], wl["rois_per_image"], wl["image"]
+    g = torch.Generator().manual_seed(2000)
+    cl = torch.channels_last
+    rois = synth.make_rois(B, R, hw, g).cuda()
+    raw = [m.cuda() for m in synth.make_feature_maps(B, hw, 256, g, channels_last=True)]
+    madeup = [m.cuda() for m in synth.make_feature_maps(B, hw, 256, g, channels_last=True)]
+    sp = fi.split_levels(fi.roi_level(rois, (hw[0], hw[1], 3)), rois=rois, order=fi.spatial_order(rois))
+    total = B * R
+    nchw = lambda t: t.detach().contiguous().cpu().numpy()
+    gg = torch.Generator(device="cuda").manual_seed(11)
+
+    def family(name):
+        """specs of one family on fresh leaves + (leaf, boxes, ind, rows, size, dual) per set"""
+        xs_raw = [m.clone().requires_grad_() for m in raw]
+        xs_mu = [m.clone().requires_grad_() for m in madeup]
+        pooled = torch.zeros((total, 256, 7, 7), device="cuda").contiguous(memory_format=cl)
+        mask = torch.zeros((total, 256, 14, 14), device="cuda").contiguous(memory_format=cl)
+        specs, meta = [], []
+        for i in range(4):
+            if sp.small_cnt[i] == 0:
+                continue
+            if name in ("big", "all") and i < 3 and sp.big_cnt[i]:
+                specs.append(dict(image=xs_raw[i], boxes=sp.big_boxes(i), box_ind=sp.big_ind(i), size=14))
+                meta.append((xs_raw[i], sp.big_boxes(i), sp.big_ind(i), None, 14, False))
+            if name in ("s7", "all"):
+                specs.append(dict(image=xs_mu[i], boxes=sp.small_boxes(i), box_ind=sp.small_ind(i), size=7, out=pooled, dst_row=sp.small(i)))
+                meta.append((xs_mu[i], sp.small_boxes(i), sp.small_ind(i), sp.small(i), 7, False))
+            if name in ("s14", "all"):
+                specs.append(dict(image=xs_mu[i], boxes=sp.small_boxes(i), box_ind=sp.small_ind(i), size=14, out=mask, dst_row=sp.small(i), compact=(i < 3)))
+                meta.append((xs_mu[i], sp.small_boxes(i), sp.small_ind(i), sp.small(i), 14, i < 3))
+        return specs, meta
+
+    def run(name, exact, grads_by_set=None):
+        specs, meta = family(name)
+        outs, comps = fi.crop_sets(specs)
+        heads, gr, per_set = [], [], []
+        seen = {}
+        for k, (leaf, boxes, ind, rows, P, dual) in enumerate(meta):
+            n = boxes.size(0)
+            if rows is None:
+                h = comps[k]
+                gk = (torch.randn((n, 256, P, P), device="cuda", generator=gg).contiguous(memory_format=cl),) if grads_by_set is None else grads_by_set[k]
+                heads.append(h); gr.append(gk[0]); per_set.append(gk)
+                continue
+            o = outs[k]
+            if id(o) not in seen:                         # one gradient tensor per shared output; rows of other levels stay zero here
+                seen[id(o)] = torch.zeros(o.shape, device="cuda").contiguous(memory_format=cl)
+                heads.append(o); gr.append(seen[id(o)])
+            gfull = seen[id(o)]
+            if grads_by_set is None:
+                g1 = torch.randn((n, 256, P, P), device="cuda", generator=gg).contiguous(memory_format=cl)
+                gk = (g1, torch.randn((n, 256, P, P), device="cuda", generator=gg).contiguous(memory_format=cl)) if dual else (g1,)
+            else:
+                gk = grads_by_set[k]
+            gfull[rows.long()] = gk[0]
+            if dual:
+                heads.append(comps[k]); gr.append(gk[1])
+            per_set.append(gk)
+        old = fi.set_deterministic(exact)
+        try:
+            leaves = []
+            for m in meta:
+                if not any(m[0] is l for l in leaves):
+                    leaves.append(m[0])
+            res = torch.autograd.grad(heads, leaves, gr)
+        finally:
+            fi.set_deterministic(old)
+        crops = [(outs[k][meta[k][3].long()] if meta[k][3] is not None else comps[k]) for k in range(len(meta))]
+        return meta, crops, per_set, leaves, res
+
+    sums, mags = {}, {}
+    all_grads = {}
+    for name in ("big", "s7", "s14"):
+        meta, crops, per_set, leaves, res = run(name, exact=True)
+        all_grads[name] = per_set
+        for k, (leaf, boxes, ind, rows, P, dual) in enumerate(meta):
+            img = nchw(leaf)
+            want = fwd(img, boxes.cpu().numpy(), ind.cpu().numpy(), P, P, 0.0)
+            np.testing.assert_array_equal(nchw(crops[k]), want)                               # forward: bit-exact
+            gsum = per_set[k][0] + per_set[k][1] if dual else per_set[k][0]                   # autograd's (g1 + g2) in the reference
+            want_g = bwd(nchw(gsum), boxes.cpu().numpy(), ind.cpu().numpy(), tuple(leaf.shape))
+            li = [i for i, l in enumerate(leaves) if l is leaf][0]
+            np.testing.assert_array_equal(nchw(res[li]), want_g)                              # exact backward: bit-exact
+            key = (name != "big", [tuple(m.shape) for m in madeup].index(tuple(leaf.shape)) if name != "big" else [tuple(m.shape) for m in raw].index(tuple(leaf.shape)))
+            sums[key] = sums.get(key, 0) + want_g.astype(np.float64)
+            mags[key] = mags.get(key, 0) + bwd(np.abs(nchw(gsum)), boxes.cpu().numpy(), ind.cpu().numpy(), tuple(leaf.shape)).astype(np.float64)
+    # ---- all sets in one pass, default arithmetic, same gradients
+    specs_all, meta_all = family("all")
+    order = []
+    cursor = {"big": 0, "s7": 0, "s14": 0}
+    for (leaf, boxes, ind, rows, P, dual) in meta_all:
+        fam = "big" if rows is None else ("s7" if P == 7 else "s14")
+        order.append(all_grads[fam][cursor[fam]]); cursor[fam] += 1
+    meta, crops, per_set, leaves, res = run("all", exact=False, grads_by_set=order)
+    shapes_raw, shapes_mu = [tuple(m.shape) for m in raw], [tuple(m.shape) for m in madeup]
+    for leaf, got in zip(leaves, res):
+        is_mu = any(leaf is m[0] and m[3] is not None for m in meta)
+        key = (is_mu, (shapes_mu if is_mu else shapes_raw).index(tuple(leaf.shape)))
+        err = np.abs(nchw(got).astype(np.float64) - sums[key])
+        assert np.all(err <= 2e-6 * mags[key] + 1e-6), "default-mode pass: max err/bound = %g" % float((err / (2e-6 * mags[key] + 1e-6)).max())

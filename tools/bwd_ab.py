@@ -48,7 +48,10 @@ def main():
     ap.add_argument("--exact", action="store_true")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--plan-in-backward", action="store_true", help="build the sample lists inside backward (timed) instead of at forward time")
     args = ap.parse_args()
+    if args.plan_in_backward:
+        fi.roi_align.plan_at_forward(False)
     dev = torch.device("cuda", 0)
     wl = synth.WORKLOADS[args.workload]
     raw, madeup, specs, split = build_specs(wl, dev)
@@ -87,7 +90,7 @@ def main():
         idx = torch.arange(flat.numel(), device=dev, dtype=torch.long)
         prints.append([int(flat.sum().item()), int(((flat * ((idx % 65521) + 1)) % 2147483647).sum().item()), float(r.abs().sum().item())])
     out = dict(workload=args.workload, exact=args.exact, env={k: v for k, v in os.environ.items() if k.startswith("FI_")},
-               bwd_ms_median=times[len(times) // 2], bwd_ms_min=times[0], bwd_ms_all=[round(t, 4) for t in times],
+               plan_in_backward=args.plan_in_backward, bwd_ms_median=times[len(times) // 2], bwd_ms_min=times[0], bwd_ms_all=[round(t, 4) for t in times],
                fingerprints=prints, small=split.small_cnt, big=split.big_cnt)
     s = json.dumps(out)
     print(s)
