@@ -12,9 +12,12 @@
 //     first decides for ONE entry whether any of its taps falls into the warp's block (and with which weights); the
 //     warp then walks the hits (ballot order = list order): one LDS.128 per 512 B of gradient, FFMA2 into registers.
 //     No shared-memory stores, no read-modify-write chain: ~13 wavefronts per 512 B of gradient;
-//   * CTAs are persistent (2 per SM) and take tiles from a work counter in groups of 8, heaviest (coarsest map) first;
-//     the producer prefetches tile descriptors a group ahead and list entries a batch ahead, so no per-tile round
-//     trip is exposed, and the sample list is read once per tile (not once per 128-channel slab).
+//   * CTAs are persistent (3 per SM, a two-batch ring each) and take tiles by tickets from a work counter, heaviest
+//     (coarsest map) first; the producer prefetches tile descriptors a ticket ahead and list entries a batch ahead, so
+//     no per-tile round trip is exposed, and the sample list is read once per tile (not once per 128-channel slab);
+//   * runs of consecutive gradient rows (neighbouring samples of a crop row) are fetched by ONE bulk copy.
+// Measured on C2 (profiles/r02_ncu_pix_v3.txt): 0.72 ms, 4.34 GB of DRAM traffic at 6.05 TB/s = 92 % of the copy peak
+// (bin_accumulate_kernel: 1.05 ms, 62 %).
 // Every pixel is still summed by ONE warp in list order (box, crop row, crop column) with the same operations as
 // bin_accumulate_kernel, so both modes give the same bits as before: default = packed FMAs with pre-multiplied
 // weights; EXACT = the un-fused arithmetic and order of crop_and_resize.c:190-250 (bit-identical to the reference's
@@ -71,7 +74,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
                  : "memory");
 }
 
-// grid (2 CTAs per SM, C / CB), kPixThreads threads, dynamic shared memory = sizeof(PixSmem)
+// grid (MINB CTAs per SM, C / CB), kPixThreads threads, dynamic shared memory = sizeof(PixSmem)
 template <bool EXACT, int CB, int BS, int NB, int MINB>
 __global__ void __launch_bounds__(kPixThreads, MINB) pix_accumulate_kernel(const TParams P) {
     constexpr int TY = 4, TX = 8;
@@ -392,14 +395,17 @@ int pix_accumulate(const TParams &P, int exact, cudaStream_t stream) {
     for (int m = 1; m < P.nmaps; ++m)
         if (P.m[m].C != C) return FI_ERR_UNSUPPORTED;
     if (C % 128 != 0 || C / 128 > 32) return FI_ERR_UNSUPPORTED;
+    // Ring shape (measured on C2, profiles/r02_pix_sweep.json): three CTAs per SM with a two-batch ring beat two CTAs with
+    // three batches (0.72 vs 0.86 ms, DRAM at 92 % vs 80 % of the copy peak): each CTA is latency-bound on its own ring, so
+    // more independent rings per SM keep more bytes in flight; 16-slot batches lose to the per-batch work of the consumers.
     const int cfg = option(FI_OPT_PIX_CFG);
     if (C % 256 == 0) {
-        if (cfg == 1) return exact ? launch_pix<true, 256, 16, 6, 2>(P, stream) : launch_pix<false, 256, 16, 6, 2>(P, stream);
-        if (cfg == 2) return exact ? launch_pix<true, 256, 32, 2, 3>(P, stream) : launch_pix<false, 256, 32, 2, 3>(P, stream);
+        if (cfg == 1) return exact ? launch_pix<true, 256, 32, 3, 2>(P, stream) : launch_pix<false, 256, 32, 3, 2>(P, stream);
+        if (cfg == 2) return exact ? launch_pix<true, 256, 16, 6, 2>(P, stream) : launch_pix<false, 256, 16, 6, 2>(P, stream);
         if (cfg == 3) return exact ? launch_pix<true, 256, 16, 4, 3>(P, stream) : launch_pix<false, 256, 16, 4, 3>(P, stream);
-        return exact ? launch_pix<true, 256, 32, 3, 2>(P, stream) : launch_pix<false, 256, 32, 3, 2>(P, stream);
+        return exact ? launch_pix<true, 256, 32, 2, 3>(P, stream) : launch_pix<false, 256, 32, 2, 3>(P, stream);
     }
-    return exact ? launch_pix<true, 128, 32, 3, 2>(P, stream) : launch_pix<false, 128, 32, 3, 2>(P, stream);
+    return exact ? launch_pix<true, 128, 32, 3, 3>(P, stream) : launch_pix<false, 128, 32, 3, 3>(P, stream);
 }
 
 }  // namespace tile

@@ -394,7 +394,7 @@ def test_backward_formulations_agree(mode, shape):
         want = clib.oracle_crop_and_resize_bwd(grads.numpy(), rois.numpy(), box_ind.numpy(), tuple(image.shape))
         img = image.cuda().contiguous(memory_format=torch.channels_last).requires_grad_()
         fi.set_option("bwd_form", "pix" if form.startswith("pix") else form)
-        fi.set_option("pix_cfg", 1 if form == "pix16" else 0)
+        fi.set_option("pix_cfg", 2 if form == "pix16" else 0)
         fi.set_option("pix_group", 7 if "g8" in mode else 1)
         old = fi.set_deterministic(exact)                   # the process-wide switch selects the exact arithmetic
         try:
