@@ -1,24 +1,29 @@
 #!/usr/bin/env python
 """Benchmark of the Feature Intertwiner hot path on B200 (BASELINE.json metric: RoIs/sec).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c5] [--impl ours|reference]
+                    [--mode graph|eager] [--with-critic] [--no-other-workloads]
 
 One "step" = one pass of the hot path over one batch of synthetic input:
 
-    level rule + reliable/less-reliable split  ->  every RoIAlign call of Dev.forward (big 14x14 on the raw
-    level maps, small 7x7 + 14x14 on the made-up maps; 7x7 written straight to its final row)  ->  per-class
-    segment means of the critic features  ->  buffer update + class match  ->  OptTrans / Sinkhorn(L) loss
-    ->  backward of all of it (Sinkhorn gradient, segment-mean backward, RoIAlign backward of every crop).
+    [c3: proposal layer -- decode + on-device NMS producing the RoIs]  ->  level rule + reliable/less-reliable split
+    ->  every RoIAlign call of Dev.forward (big 14x14 on the raw level maps, small 7x7 + 14x14 on the made-up maps;
+    crops written straight to their final rows)  ->  per-class segment means of the critic features  ->  statistics merge
+    (+ all-reduce)  ->  buffer update + class match  ->  OptTrans / Sinkhorn(L) loss  ->  backward of all of it
+    (Sinkhorn gradient, segment-mean backward, RoIAlign backward of every crop).
 
-The make-up conv and the critic convs are stock cuDNN and are NOT part of the path:
-their outputs (made-up maps, critic features) and the upstream crop gradients are synthetic inputs.
+Nothing in the step is read back by the host: list lengths stay on the device (fixed-capacity lists), so the WHOLE step
+is captured in one CUDA graph (`--mode graph`, default) and replayed; `--mode eager` enqueues it launch by launch.
+
+The make-up conv and the critic convs are stock cuDNN.  In the default step their outputs (made-up
+maps, critic features) and the upstream crop gradients are synthetic inputs; `--with-critic` times the a5-inclusive variant
+instead: fi.Dev.forward (make-up conv + all crops + critic) + fi.IntertwinerLoss + backward, called directly.
 
 `value`  : RoIs/s with all inputs resident in HBM (device-timed, CUDA events, max over ranks).
-`e2e`    : the same step through the public API starting from pinned HOST buffers (H2D of every input,
-           D2H of the loss) inside the timed region.
-`--impl reference`: the reference's own CPU implementation (oracle/_ref: lib/roi_align/src/crop_and_resize.c
-           compiled unmodified, OpenMP forward + serial backward) plus the torch-CPU restatement of
-           lib/OT_module.py for the loss, on a bounded sample of the same workload.
+`e2e`    : the same step starting from pinned HOST buffers (H2D of every input, D2H of the loss) inside the timed region.
+`--impl reference`: the reference's own CPU implementation (oracle/_ref: lib/roi_align/src/crop_and_resize.c compiled
+           unmodified, OpenMP forward + serial backward) on every crop of the step -- FULL steps, nothing sampled --
+           plus the torch-CPU port of lib/OT_module.py for the loss (oracle/pyref.py).
 """
 import argparse
 import gc
@@ -37,6 +42,7 @@ sys.path.insert(0, ROOT)
 FEAT = 1024
 NCLS = 81
 DEPTH = 256
+METRIC = "RoIs/sec (RoIAlign fwd+bwd + split + class means + Sinkhorn intertwiner loss, fwd+bwd)"
 
 
 def dist_env():
@@ -52,6 +58,12 @@ def measured_peak():
         d = json.load(open(p))
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def workload_name(name, wl):
+    extra = ", proposal layer + NMS in the step" if wl.get("proposals") else ""
+    return "%s: batch %d/GPU, %dx%d, %d RoIs/img, FPN P2-P5 C=256, pools 7+14, Sinkhorn N=256 L=%d, class-level OT loss%s" % (
+        name, wl["batch"], wl["image"][0], wl["image"][1], wl["rois_per_image"], wl["sinkhorn_iters"], extra)
 
 
 class ClockSampler(object):
@@ -123,8 +135,21 @@ class ClockSampler(object):
 
 
 # =================================================================================================== inputs
+def anchors_for(hw, gen):
+    """RPN anchors of the five pyramid levels (3 ratios per cell, scales 32..512, lib/config.py:90-91,318) in pixels."""
+    out = []
+    for stride, scale in zip((4, 8, 16, 32, 64), (32, 64, 128, 256, 512)):
+        h, w = -(-hw[0] // stride), -(-hw[1] // stride)
+        ys = (torch.arange(h, dtype=torch.float32) * stride).view(h, 1, 1).expand(h, w, 3)
+        xs = (torch.arange(w, dtype=torch.float32) * stride).view(1, w, 1).expand(h, w, 3)
+        ratios = torch.tensor([0.5, 1.0, 2.0]).view(1, 1, 3).expand(h, w, 3)
+        hh, ww = scale / ratios.sqrt(), scale * ratios.sqrt()
+        out.append(torch.stack([ys - hh / 2, xs - ww / 2, ys + hh / 2, xs + ww / 2], dim=3).reshape(-1, 4))
+    return torch.cat(out).contiguous()
+
+
 def make_inputs(wl, seed):
-    """Everything a step consumes, on the HOST (pinned), seeded.  The split itself is computed by the step."""
+    """Everything a step consumes, on the HOST, seeded.  The split itself is computed by the step."""
     from feature_intertwiner_b200 import synth
     g = torch.Generator().manual_seed(seed)
     B, R, hw = wl["batch"], wl["rois_per_image"], wl["image"]
@@ -134,6 +159,26 @@ def make_inputs(wl, seed):
         "raw": synth.make_feature_maps(B, hw, DEPTH, g, channels_last=True),      # P2..P5
         "madeup": synth.make_feature_maps(B, hw, DEPTH, g, channels_last=True),   # upsample(P2..P5): stock conv output
     }
+    if wl.get("proposals"):
+        # RPN outputs whose proposals ARE the RoIs of the step: anchor a of image b regresses (with noise) onto one of the
+        # boxes make_rois drew; the foreground score decays with the anchor's index so that the sort is well defined
+        anchors = anchors_for(hw, g)
+        A = anchors.size(0)
+        tgt = host["rois"] * torch.tensor([hw[0], hw[1], hw[0], hw[1]], dtype=torch.float32)
+        pick = torch.randint(0, R, (B, A), generator=g)
+        t = torch.gather(tgt, 1, pick.unsqueeze(2).expand(B, A, 4))
+        t = torch.where((t[:, :, 2:3] - t[:, :, 0:1]) > 1, t, anchors.unsqueeze(0).expand(B, A, 4))     # zero-padded RoIs: keep the anchor
+        ah, aw = anchors[:, 2] - anchors[:, 0], anchors[:, 3] - anchors[:, 1]
+        th, tw = (t[:, :, 2] - t[:, :, 0]).clamp(min=1.0), (t[:, :, 3] - t[:, :, 1]).clamp(min=1.0)
+        acy, acx = anchors[:, 0] + 0.5 * ah, anchors[:, 1] + 0.5 * aw
+        tcy, tcx = t[:, :, 0] + 0.5 * th, t[:, :, 1] + 0.5 * tw
+        std = torch.tensor([0.1, 0.1, 0.2, 0.2])
+        deltas = torch.stack([(tcy - acy) / ah, (tcx - acx) / aw, torch.log(th / ah), torch.log(tw / aw)], dim=2)
+        deltas = (deltas.clamp(-4, 4) + 0.02 * torch.randn(B, A, 4, generator=g)) / std
+        fg = torch.rand(B, A, generator=g)
+        host["rpn_probs"] = torch.stack([1 - fg, fg], dim=2).contiguous()
+        host["rpn_bbox"] = deltas.contiguous()
+        host["anchors"] = anchors
     return host
 
 
@@ -150,42 +195,63 @@ def build_config(wl):
                INST_LOSS=False, FEAT_BRANCH_POOL_SIZE=14, ASSIGN_BOX_ON_ALL_SCALE=False, BIG_FEAT_DETACH=True, UPSAMPLE_FAC=1.0,
                MULTI_UPSAMPLER=False, BIG_SUPERVISE=False, DIS_UPSAMPLER=False, INIT_BUFFER_WEIGHT="scratch"),
         ROIS=ns(METHOD="roi_align", ASSIGN_ANCHOR_BASE=224.0), MRCNN=ns(POOL_SIZE=7, MASK_POOL_SIZE=14),
-        DATA=ns(IMAGE_SHAPE=np.array([wl["image"][0], wl["image"][1], 3])), DATASET=ns(NUM_CLASSES=NCLS))
+        RPN=ns(PRE_NMS_LIMIT=6000), DATA=ns(IMAGE_SHAPE=np.array([wl["image"][0], wl["image"][1], 3]), BBOX_STD_DEV=np.array([0.1, 0.1, 0.2, 0.2])),
+        DATASET=ns(NUM_CLASSES=NCLS))
 
 
 class Step(object):
-    """Device-side state + one pass of the hot path through the public API."""
+    """Device-side state + one pass of the hot path through the public API.  Every list keeps its capacity (batch * RoIs per
+    image) with its length on the device, so the step has fixed shapes and no host read."""
 
     def __init__(self, wl, device, world, seed):
         import feature_intertwiner_b200 as fi
         self.fi, self.wl, self.dev, self.world = fi, wl, device, world
         self.spatial_sort = os.environ.get("FI_SPATIAL_SORT", "1") != "0"
-        self.use_graph = os.environ.get("FI_GRAPH", "1") != "0"     # CUDA-graph the fixed-shape loss head (no collective inside)
-        self.graph_tried, self.graphed = False, False
         self.cfg = build_config(wl)
         torch.manual_seed(2000)
         self.ot = fi.OptTrans(self.cfg, ch_x=FEAT, L=wl["sinkhorn_iters"]).to(device)
         self.loss_mod = fi.IntertwinerLoss(self.cfg, ot_loss=self.ot, feat_dim=FEAT, distributed=world > 1, ot_padded=True).to(device)
         self.host = make_inputs(wl, seed)
         B, R = wl["batch"], wl["rois_per_image"]
-        # the split of THIS input fixes the shapes of the synthetic critic features / upstream gradients
+        total = B * R
+        self.total = total
+        # the split of THIS input tells how many rows of the (capacity-sized) synthetic critic features / upstream gradients are live
         rois_d = self.host["rois"].to(device)
+        if wl.get("proposals"):
+            with torch.no_grad():
+                rois_d, _ = fi.proposal_layer([self.host["rpn_probs"].to(device), self.host["rpn_bbox"].to(device)], R, 0.7,
+                                              self.host["anchors"].to(device), self.cfg, static=True)
         split = fi.split_levels(fi.roi_level(rois_d, self.cfg.DATA.IMAGE_SHAPE))
         self.counts = (list(split.small_cnt), list(split.big_cnt))
         g = torch.Generator().manual_seed(seed + 1)
         self.host["small_feat"] = [torch.rand(split.small_cnt[i], FEAT, generator=g) for i in range(3)]
         self.host["big_feat"] = [torch.rand(split.big_cnt[i], FEAT, generator=g) for i in range(3)]
-        self.host["g_pooled"] = torch.randn(B * R, DEPTH, 7, 7, generator=g).contiguous(memory_format=torch.channels_last)
-        self.host["g_mask"] = torch.randn(B * R, DEPTH, 14, 14, generator=g).contiguous(memory_format=torch.channels_last)
+        self.host["g_pooled"] = torch.randn(total, DEPTH, 7, 7, generator=g).contiguous(memory_format=torch.channels_last)
+        self.host["g_mask"] = torch.randn(total, DEPTH, 14, 14, generator=g).contiguous(memory_format=torch.channels_last)
         self.host["g_small"] = [torch.randn(split.small_cnt[i], DEPTH, 14, 14, generator=g).contiguous(memory_format=torch.channels_last)
                                 for i in range(3)]           # gradient the critic sends back into the compact 14x14 crops
         self.host["g_big"] = [torch.randn(split.big_cnt[i], DEPTH, 14, 14, generator=g).contiguous(memory_format=torch.channels_last)
                               for i in range(3)]
-        self.h2d_bytes = 0
-        self.pinned = self._map(self.host, pin)
-        self.resident = self._map(self.host, lambda t: t.to(device))
+        if wl.get("proposals"):
+            del self.host["rois"]                            # the step makes its own RoIs
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in self._flat(self.host))
-        self.algo = None
+        self.pinned = self._map(self.host, pin)
+        # device buffers: per-level tensors at full capacity (only the live rows are ever read), the rest as they are
+        cl = torch.channels_last
+        self.resident = {}
+        for k, v in self.host.items():
+            if k in ("small_feat", "big_feat"):
+                self.resident[k] = [torch.zeros(total, FEAT, device=device) for _ in v]
+            elif k in ("g_small", "g_big"):
+                self.resident[k] = [torch.zeros((total, DEPTH, 14, 14), device=device).contiguous(memory_format=cl) for _ in v]
+            else:
+                self.resident[k] = [t.to(device) for t in v] if isinstance(v, list) else v.to(device)
+        self.upload(sync=True)
+        # upper bound on the backward's sample-list entries for ANY split of `total` boxes: every RoI is small at exactly one
+        # level (7x7 + 14x14, the latter with two gradient sources) and big at no more than three (14x14)
+        self.max_entries = total * (4 * 49 + 8 * 196 + 12 * 196 + 32 * 11)
+        self.graph, self.graph_loss, self.graph_error = None, None, None
+        self.launches_per_step = None
 
     @staticmethod
     def _map(d, f):
@@ -197,6 +263,12 @@ class Step(object):
             for t in (v if isinstance(v, list) else [v]):
                 yield t
 
+    def upload(self, sync=False):
+        """H2D of every input of the step from pinned host memory into the step's device buffers (the e2e leg)."""
+        for k, v in self.pinned.items():
+            for src, dst in zip(v if isinstance(v, list) else [v], self.resident[k] if isinstance(v, list) else [self.resident[k]]):
+                dst[: src.size(0)].copy_(src, non_blocking=not sync)
+
     def loss_only(self):
         """The intertwiner loss alone (BASELINE.json's second metric): statistics merge (+ all-reduce) -> buffer update ->
         class match -> OptTrans / Sinkhorn, forward and backward, on the class statistics of the last step."""
@@ -207,15 +279,18 @@ class Step(object):
             p.grad = None
         return loss
 
-    def upload(self):
-        """H2D of every input of the step from pinned host memory (the e2e leg)."""
-        return self._map(self.pinned, lambda t: t.to(self.dev, non_blocking=True))
-
-    def run(self, inp):
+    def run(self, inp=None):
         fi, cfg = self.fi, self.cfg
+        inp = self.resident if inp is None else inp
         B, R = self.wl["batch"], self.wl["rois_per_image"]
         total = B * R
-        rois, gt = inp["rois"], inp["gt"]
+        gt = inp["gt"]
+        if self.wl.get("proposals"):
+            # producer of the RoIs (lib/layers.py:71-139): decode + batched on-device NMS + gather, no host read
+            with torch.no_grad():
+                rois, _ = fi.proposal_layer([inp["rpn_probs"], inp["rpn_bbox"]], R, 0.7, inp["anchors"], cfg, static=True)
+        else:
+            rois = inp["rois"]
         # fresh leaves every step (a training loop clears .grad each iteration; re-using the leaf would time an extra
         # read-modify-write of every map in AccumulateGrad)
         raw = [m.detach().requires_grad_() for m in inp["raw"]]
@@ -223,45 +298,35 @@ class Step(object):
         small_f = [t.detach().requires_grad_() for t in inp["small_feat"]]
         big_f = inp["big_feat"]
         split = fi.split_levels(fi.roi_level(rois, cfg.DATA.IMAGE_SHAPE, cfg.ROIS.ASSIGN_ANCHOR_BASE), rois=rois, gt=gt,
-                                order=fi.spatial_order(rois) if self.spatial_sort else None)
+                                order=fi.spatial_order(rois) if self.spatial_sort else None, sync=False)
         pooled_out = torch.empty((total, DEPTH, 7, 7), device=self.dev, memory_format=torch.channels_last)
         mask_out = torch.empty((total, DEPTH, 14, 14), device=self.dev, memory_format=torch.channels_last)
         # every crop of the pass in one level-batched launch (fi.crop_sets), like Dev.forward
         specs, where = [], {}
         for i in range(4):
-            if split.small_cnt[i] == 0:
-                continue
-            if i < 3 and split.big_cnt[i]:
+            if i < 3:
                 where[("big", i)] = len(specs)
-                specs.append(dict(image=raw[i], boxes=split.big_boxes(i), box_ind=split.big_ind(i), size=14, img_offsets=split.big_img_offsets(i)))
+                specs.append(dict(image=raw[i], boxes=split.big_boxes(i), box_ind=split.big_ind(i), size=14, count=split.big_count(i)))
             s32 = split.small(i)
             boxes, ind = split.small_boxes(i), split.small_ind(i)
             where[("small", i)] = len(specs)
-            specs.append(dict(image=madeup[i], boxes=boxes, box_ind=ind, size=7, out=pooled_out, dst_row=s32, img_offsets=split.small_img_offsets(i)))
-            specs.append(dict(image=madeup[i], boxes=boxes, box_ind=ind, size=14, out=mask_out, dst_row=s32, compact=(i < 3),
-                              img_offsets=split.small_img_offsets(i)))
-        res_out, res_comp = fi.crop_sets(specs)
+            specs.append(dict(image=madeup[i], boxes=boxes, box_ind=ind, size=7, out=pooled_out, dst_row=s32, count=split.small_count(i)))
+            specs.append(dict(image=madeup[i], boxes=boxes, box_ind=ind, size=14, out=mask_out, dst_row=s32, compact=(i < 3), count=split.small_count(i)))
+        res_out, res_comp = fi.crop_sets(specs, max_entries=self.max_entries)
         outs, grads = [], []
         bfeat, bcnt, sfeat, scnt = [], [], [], []
-        for i in range(4):
-            if ("small", i) not in where:
-                continue
-            if ("big", i) in where:
-                k = where[("big", i)]
-                outs.append(res_comp[k]); grads.append(inp["g_big"][i])      # compact 14x14 crop -> critic (stock conv, not timed)
-                f, c = fi.assign_feat2cls(split.big_gt(i), big_f[i], NCLS)
-                bfeat.append(f); bcnt.append(c)
+        for i in range(3):
+            k = where[("big", i)]
+            outs.append(res_comp[k]); grads.append(inp["g_big"][i])          # compact 14x14 crop -> critic (stock conv, not timed)
+            f, c = fi.assign_feat2cls(split.big_gt(i), big_f[i], NCLS, count=split.big_count(i))
+            bfeat.append(f); bcnt.append(c)
             k = where[("small", i)]
-            pooled_out, mask_out = res_out[k], res_out[k + 1]
-            if i < 3:
-                outs.append(res_comp[k + 1]); grads.append(inp["g_small"][i])
-                f, c = fi.assign_feat2cls(split.small_gt(i), small_f[i], NCLS)
-                sfeat.append(f); scnt.append(c)
+            outs.append(res_comp[k + 1]); grads.append(inp["g_small"][i])
+            f, c = fi.assign_feat2cls(split.small_gt(i), small_f[i], NCLS, count=split.small_count(i))
+            sfeat.append(f); scnt.append(c)
+        pooled_out, mask_out = res_out[where[("small", 3)]], res_out[where[("small", 3)] + 1]
         feat_in = [torch.stack(bfeat)[None].detach(), torch.stack(bcnt)[None], torch.stack(sfeat)[None], torch.stack(scnt)[None], None, None]
         self.last_feat_in = [t.detach() for t in feat_in[:4]]          # for the loss-head-only timing
-        if self.use_graph and not self.graph_tried:
-            self.graph_tried = True
-            self.graphed = self.loss_mod.enable_cuda_graph([feat_in[0], feat_in[1], feat_in[2].detach().requires_grad_(), feat_in[3]])
         loss = self.loss_mod(feat_in).sum()
         torch.autograd.backward([loss, pooled_out, mask_out] + outs, [torch.ones_like(loss), inp["g_pooled"], inp["g_mask"]] + grads)
         if self.world > 1:
@@ -270,10 +335,157 @@ class Step(object):
             dist.all_reduce(flat)                     # gradient all-reduce of the path's own parameters (OptTrans)
         for p in self.ot.parameters():
             p.grad = None
+        self.last_split = split
+        return loss
+
+    def capture(self):
+        """The whole step (side-stream list building included) as ONE CUDA graph.  Returns True when the graph is live."""
+        lib = self.fi.lib()
+        try:
+            s = torch.cuda.Stream(device=self.dev)
+            s.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(s):
+                for _ in range(3):
+                    self.run()
+            torch.cuda.current_stream(self.dev).wait_stream(s)
+            torch.cuda.synchronize(self.dev)
+            graph = torch.cuda.CUDAGraph()
+            n0 = lib.fi_kernel_launches()
+            with torch.cuda.graph(graph):
+                self.graph_loss = self.run()
+            self.launches_per_step = int(lib.fi_kernel_launches() - n0)
+            graph.replay()
+            torch.cuda.synchronize(self.dev)
+            self.graph = graph
+        except Exception as exc:            # noqa: BLE001 -- capture is an optimisation: fall back to launch-by-launch
+            self.graph, self.graph_error = None, repr(exc)[:300]
+            torch.cuda.synchronize(self.dev)
+        return self.graph is not None
+
+    def step(self):
+        if self.graph is not None:
+            self.graph.replay()
+            return self.graph_loss
+        return self.run()
+
+
+class CriticStep(object):
+    """The a5-inclusive variant: fi.Dev.forward (make-up conv, level rule, split, every crop, critic convs, class means) +
+    fi.IntertwinerLoss + backward, called directly, with stock cuDNN convolutions inside the timed region."""
+
+    def __init__(self, wl, device, world, seed):
+        import feature_intertwiner_b200 as fi
+        self.fi, self.wl, self.dev, self.world = fi, wl, device, world
+        self.cfg = build_config(wl)
+        torch.manual_seed(2000)
+        self.dev_mod = fi.Dev(self.cfg, DEPTH).to(device).to(memory_format=torch.channels_last)
+        self.dev_mod.spatial_sort = True
+        self.dev_mod.eval()                               # the reference always runs in eval() (SURVEY.md Appendix B.1)
+        self.ot = fi.OptTrans(self.cfg, ch_x=FEAT, L=wl["sinkhorn_iters"]).to(device)
+        self.loss_mod = fi.IntertwinerLoss(self.cfg, ot_loss=self.ot, feat_dim=FEAT, distributed=world > 1, ot_padded=True).to(device)
+        host = make_inputs(dict(wl, proposals=False), seed)
+        self.rois, self.gt = host["rois"].to(device), host["gt"].to(device)
+        self.maps = [m.to(device) for m in host["raw"]]
+        g = torch.Generator().manual_seed(seed + 1)
+        total = wl["batch"] * wl["rois_per_image"]
+        self.g_pooled = torch.randn(total, DEPTH, 7, 7, generator=g).to(device).contiguous(memory_format=torch.channels_last)
+        self.g_mask = torch.randn(total, DEPTH, 14, 14, generator=g).to(device).contiguous(memory_format=torch.channels_last)
+
+    def step(self):
+        x = [m.detach().requires_grad_() for m in self.maps]
+        pooled, mask, feat_out = self.dev_mod(x, self.rois, self.gt)
+        loss = self.loss_mod([feat_out[0], feat_out[1], feat_out[2], feat_out[3], None, None]).sum()
+        torch.autograd.backward([loss, pooled, mask], [torch.ones_like(loss), self.g_pooled, self.g_mask])
+        for p in list(self.ot.parameters()) + list(self.dev_mod.parameters()):
+            p.grad = None
         return loss
 
 
 # =================================================================================================== ours
+class Timer(object):
+    def __init__(self, dev, world, lib, flush):
+        self.dev, self.world, self.lib, self.flush = dev, world, lib, flush
+        self.host_s, self.per_step, self.launches = 0.0, [], 0
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def __call__(self, fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        # the cyclic collector of a process with torch loaded walks millions of objects: a generation-2 pass landing inside a
+        # 2 ms step shows up as a 6-60 ms step.  Collect now, keep it off for the K timed steps (training loops do the same with
+        # gc.freeze / a manual collection between iterations).
+        gc.collect()
+        gc.disable()
+        evs = []
+        pool = [torch.cuda.Event(enable_timing=True) for _ in range(2 * steps)]     # created and first-recorded outside the timed steps
+        for ev in pool:
+            ev.record()
+        torch.cuda.synchronize()
+        self.host_s = 0.0
+        launch0 = self.lib.fi_kernel_launches()
+        for _ in range(steps):
+            self.flush.add_(1.0)
+            a, b = pool.pop(), pool.pop()
+            t0 = time.perf_counter()
+            a.record(); fn(); b.record()
+            self.host_s += time.perf_counter() - t0          # host time to ENQUEUE a step
+            evs.append((a, b))
+        self.barrier()
+        gc.enable()
+        self.launches = self.lib.fi_kernel_launches() - launch0
+        self.per_step = [a.elapsed_time(b) for a, b in evs]
+        ms = sum(self.per_step)
+        t = torch.tensor([ms], device=self.dev, dtype=torch.float64)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps
+
+
+def kernel_families(fi, step, timer, steps, peak):
+    """Per-launch CUDA events of the RoIAlign kernels (eager pass: events inside a captured graph cannot be timed)."""
+    fi.roi_align.enable_profiling(prealloc_events=12 * (steps + 3) + 64)
+    ms = timer(step.run, steps, 3)
+    records = fi.roi_align.disable_profiling()
+    fam = {}
+    n_per = len(records) // (steps + 3)
+    for rec in (records[3 * n_per:] if records else []):
+        d = fam.setdefault(rec["kernel"], [0.0, 0.0, 0])
+        d[0] += fi.roi_align.algorithmic_bytes(rec); d[1] += rec["start"].elapsed_time(rec["end"]); d[2] += 1
+    out = {}
+    for k, v in fam.items():
+        out[k] = {"launches_per_step": v[2] // steps, "avg_ms": v[1] / v[2], "alg_bytes_per_launch": v[0] / v[2]}
+        if v[0] > 0:
+            out[k].update(gbs=v[0] / v[1] / 1e6, frac=v[0] / v[1] / 1e6 / peak)
+    return out, ms
+
+
+def measure_workload(name, wl, dev, rank, world, args, lib, flush, full):
+    """One workload: device-resident value (graph or eager), e2e, loss-only, kernel families.  `full`: all legs; else value only."""
+    import feature_intertwiner_b200 as fi
+    timer = Timer(dev, world, lib, flush)
+    step = Step(wl, dev, world, seed=2000 + rank)
+    graphed = args.mode == "graph" and step.capture()
+    ms = timer(step.step, args.steps if full else max(3, args.steps // 2), args.warmup)
+    res = {"ms_per_step": ms, "value": wl["batch"] * wl["rois_per_image"] * world / (ms / 1e3), "graphed": graphed,
+           "host_enqueue_ms_per_step": 1e3 * timer.host_s / (args.steps if full else max(3, args.steps // 2)),
+           "ms_each_step": [round(v, 3) for v in timer.per_step], "counts": step.counts, "graph_error": step.graph_error}
+    res["launches_in_region"] = int(timer.launches)
+    res["launches_per_step"] = step.launches_per_step if graphed else timer.launches / max(1, len(timer.per_step))
+    if not full:
+        del step
+        torch.cuda.empty_cache()
+        return res, None
+    res["step"] = step
+    return res, timer
+
+
 def run_ours(args):
     rank, world, local = dist_env()
     import feature_intertwiner_b200 as fi
@@ -283,72 +495,67 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    wl = synth.WORKLOADS[args.workload]
-    step = Step(wl, dev, world, seed=2000 + rank)
     lib = _lib.lib()
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)    # 256 MB > 126 MB L2 (inputs alone are > 3 GB anyway)
+    wl = dict(synth.WORKLOADS[args.workload])
+    peak, peak_kind = measured_peak()
 
-    def barrier():
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    host = {"s": 0.0}
-
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
-        barrier()
-        # the cyclic collector of a process with torch loaded walks millions of objects: a generation-2 pass landing inside a
-        # 4 ms step shows up as a 6-60 ms step.  Collect now, keep it off for the K timed steps (training loops do the same with
-        # gc.freeze / a manual collection between iterations).
-        gc.collect()
-        gc.disable()
-        evs = []
-        pool = [torch.cuda.Event(enable_timing=True) for _ in range(2 * steps)]     # created and first-recorded outside the timed steps
-        for ev in pool:
-            ev.record()
-        torch.cuda.synchronize()
-        host["s"] = 0.0
-        host["launch0"] = lib.fi_kernel_launches()
-        for _ in range(steps):
-            flush.add_(1.0)
-            a, b = pool.pop(), pool.pop()
-            t0 = time.perf_counter()
-            a.record(); fn(); b.record()
-            host["s"] += time.perf_counter() - t0          # host time to ENQUEUE a step (no sync inside except the split read)
-            evs.append((a, b))
-        barrier()
-        gc.enable()
-        host["launches"] = lib.fi_kernel_launches() - host["launch0"]
-        per_step = [a.elapsed_time(b) for a, b in evs]
-        host["per_step"] = per_step
-        ms = sum(per_step)
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        if world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()) / steps
+    if args.with_critic:
+        return run_with_critic(args, wl, dev, rank, world, lib, flush)
 
     # ---- device-resident value ------------------------------------------------------------------
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    if os.environ.get("FI_BENCH_NOPROF") != "1":
-        fi.roi_align.enable_profiling(prealloc_events=8 * (args.steps + args.warmup) + 64)     # 2 launches x 2 events per step + slack
-    ms = timed(lambda: step.run(step.resident), args.steps, args.warmup)
-    host_ms = 1e3 * host["s"] / args.steps
-    per_step_ms = [round(v, 3) for v in host["per_step"]]
-    launches = host["launches"]            # kernels of libfi_b200 enqueued directly inside the timed region
-    records = fi.roi_align.disable_profiling()
+    res, timer = measure_workload(args.workload, wl, dev, rank, world, args, lib, flush, full=True)
     clocks = sampler.stop() if rank == 0 else None
+    step = res.pop("step")
+    ms = res["ms_per_step"]
+    h2d_bytes = step.h2d_bytes
     # ---- e2e: pinned host -> device -> step -> loss back on the host ------------------------------
     def e2e_step():
-        loss = step.run(step.upload())
-        return float(loss.item())
-    ms_e2e = timed(e2e_step, max(2, args.steps // 2), 2)
-    ms_loss = timed(step.loss_only, args.steps, args.warmup)          # intertwiner loss alone, fwd + bwd
+        step.upload()
+        return float(step.step().item())
+    ms_e2e = timer(e2e_step, max(2, args.steps // 2), 2)
+    # ---- kernel families (eager, per-launch events) and the loss head alone ------------------------
+    kernels, ms_eager = kernel_families(fi, step, timer, max(3, args.steps // 2), peak)
+    host_eager = 1e3 * timer.host_s / max(3, args.steps // 2)
+    step.loss_mod.enable_cuda_graph([step.last_feat_in[0], step.last_feat_in[1], step.last_feat_in[2].detach().requires_grad_(), step.last_feat_in[3]])
+    ms_loss = timer(step.loss_only, args.steps, args.warmup)          # intertwiner loss alone, fwd + bwd
+    # all-reduce of the class statistics: bus bandwidth at this size (it is latency, not bandwidth, that matters at 1.3 MB)
+    nvlink = None
+    if world > 1:
+        import torch.distributed as dist
+        buf = torch.zeros(2 * (FEAT * NCLS + NCLS), device=dev)
+        big = torch.zeros(64 * 1024 * 1024, device=dev)
+        def ar_small():
+            dist.all_reduce(buf)
+        def ar_big():
+            dist.all_reduce(big)
+        t_small = timer(ar_small, 20, 5)
+        t_big = timer(ar_big, 10, 3)
+        f = 2.0 * (world - 1) / world
+        nvlink = {"class_stats_allreduce": {"bytes": buf.numel() * 4, "ms": t_small, "bus_gbs": f * buf.numel() * 4 / t_small / 1e6},
+                  "allreduce_256MB": {"bytes": big.numel() * 4, "ms": t_big, "bus_gbs": f * big.numel() * 4 / t_big / 1e6},
+                  "nvlink_peak_gbs_per_direction": 900.0, "measured_reference_bus_gbs_8rank_1GiB": 725.0}
+        del big
+    # loss value of the last step against the CPU port on the same class statistics (north_star: loss within 1e-4)
+    stats = [t.detach().cpu() for t in step.last_feat_in]
+    ot_state = {k: v.detach().cpu() for k, v in step.ot.state_dict().items()}
+    with torch.no_grad():
+        step.loss_mod.initialize_buffer()
+        gpu_loss = step.loss_mod([t.to(dev) for t in stats] + [None, None]).detach().cpu()
+
+    others = {}
+    if not args.no_other_workloads:
+        del step
+        torch.cuda.empty_cache()
+        for name in ("c1", "c3", "c5"):
+            if name == args.workload:
+                continue
+            r, _ = measure_workload(name, dict(synth.WORKLOADS[name]), dev, rank, world, args, lib, flush, full=False)
+            others[name] = {"workload": workload_name(name, synth.WORKLOADS[name]), "value": r["value"], "unit": "RoIs/s", "ms_per_step": r["ms_per_step"],
+                            "graphed": r["graphed"], "small_counts": r["counts"][0], "big_counts": r["counts"][1], "steps": len(r["ms_each_step"])}
 
     rois_per_step = wl["batch"] * wl["rois_per_image"] * world
     if world > 1:
@@ -357,61 +564,96 @@ def run_ours(args):
         dist.destroy_process_group()
     if rank != 0:
         return
-    peak, peak_kind = measured_peak()
-    # ---- roofline of the dominant kernel family, from the per-launch events of the timed region ----
-    fam = {}
-    per_step = len(records) // (args.steps + args.warmup)
-    for rec in (records[args.warmup * per_step:] if records else []):
-        d = fam.setdefault(rec["kernel"], [0.0, 0.0, 0])
-        d[0] += fi.roi_align.algorithmic_bytes(rec); d[1] += rec["start"].elapsed_time(rec["end"]); d[2] += 1
-    kernels = {k: {"launches_per_step": v[2] // args.steps, "avg_ms": v[1] / v[2], "alg_bytes_per_launch": v[0] / v[2], "gbs": v[0] / v[1] / 1e6,
-                   "frac": v[0] / v[1] / 1e6 / peak, "share_of_step": v[1] / args.steps / ms} for k, v in fam.items()}
+    # ---- roofline of the dominant kernel family -----------------------------------------------------
+    for k in kernels:
+        kernels[k]["share_of_step"] = kernels[k]["avg_ms"] * kernels[k]["launches_per_step"] / ms
     if not kernels:
-        kernels = {"none": {"share_of_step": 0.0, "gbs": 0.0, "frac": 0.0}}
-    dom = max(kernels, key=lambda k: kernels[k]["share_of_step"])
-    # DRAM bytes per launch of the same kernels from the committed `ncu --set full` capture of this command (profiles/)
+        kernels = {"none": {"share_of_step": 0.0, "gbs": 0.0, "frac": 0.0, "avg_ms": 0.0}}
+    cand = [k for k in kernels if "frac" in kernels[k]]
+    dom = max(cand, key=lambda k: kernels[k]["share_of_step"]) if cand else "none"
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.exists(tpath) and args.workload == "c2":
         tj = json.load(open(tpath))
         traffic, traffic_src = tj.get(dom), tj.get("source")
         for k in kernels:
             kernels[k]["dram_traffic_per_launch"] = tj.get(k)
+    roof = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom].get("gbs"), "peak": peak, "unit": "GB/s", "frac": kernels[dom].get("frac"),
+            "traffic": traffic, "traffic_source": traffic_src, "peak_kind": peak_kind}
+    if "crop_bwd_nhwc" in kernels and "crop_bwd_lists" in kernels and "frac" in kernels["crop_bwd_nhwc"]:
+        b, l = kernels["crop_bwd_nhwc"], kernels["crop_bwd_lists"]
+        roof["note"] = ("crop_bwd_nhwc = tile_collapse + accumulate, the part of the backward that needs the gradients; its per-tile sample lists "
+                        "(crop_bwd_lists = tile_prep + bin_enumerate, boxes only) are built at forward time on a side stream and overlap with the "
+                        "segment means / loss head; frac_with_lists charges them to the backward as if nothing overlapped")
+        roof["frac_with_lists"] = b["alg_bytes_per_launch"] / (b["avg_ms"] + l["avg_ms"]) / 1e6 / peak
+        if "crop_fwd_nhwc" in kernels:
+            f = kernels["crop_fwd_nhwc"]
+            tot_b = b["alg_bytes_per_launch"] + f["alg_bytes_per_launch"]
+            roof["fwd_plus_bwd_frac"] = tot_b / (b["avg_ms"] + f["avg_ms"]) / 1e6 / peak
+            roof["fwd_plus_bwd_frac_with_lists"] = tot_b / (b["avg_ms"] + f["avg_ms"] + l["avg_ms"]) / 1e6 / peak
     out = {
-        "metric": "RoIs/sec (RoIAlign fwd+bwd + split + class means + Sinkhorn intertwiner loss, fwd+bwd)",
-        "value": rois_per_step / (ms / 1e3), "unit": "RoIs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC, "value": rois_per_step / (ms / 1e3), "unit": "RoIs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: batch %d/GPU, %dx%d, %d RoIs/img, FPN P2-P5 C=256, pools 7+14, Sinkhorn N=256 L=%d, class-level OT loss"
-                               % (args.workload, wl["batch"], wl["image"][0], wl["image"][1], wl["rois_per_image"], wl["sinkhorn_iters"]),
+        "config": {"workload": workload_name(args.workload, wl),
                    "layout": "channels_last maps/crops (logical NCHW)", "ot": "all 80 foreground classes, absent ones masked (fixed shapes, no host sync)",
-                   "roi_order": "spatially sorted per image (L2 reuse)" if step.spatial_sort else "index order",
-                   "loss_head": "CUDA graph (fwd+bwd)" if step.graphed else "eager", "critic_and_makeup_convs": "excluded (stock cuDNN; SURVEY.md 8 a5)",
-                   "l2": "512 MB-class working set per step (> 126 MB L2) + 256 MB flush write between steps", "gc": "python cyclic GC collected before and disabled during the timed steps",
-                   "small_counts": step.counts[0], "big_counts": step.counts[1], "parallelism": "dp%d by image batch" % world},
+                   "roi_order": "spatially sorted per image (L2 reuse)" if os.environ.get("FI_SPATIAL_SORT", "1") != "0" else "index order",
+                   "step": ("ONE CUDA graph replay per step (whole step: split, crops, list building on a side stream, class means, loss head, backward)"
+                            if res["graphed"] else "eager, launch by launch" + (" (graph capture failed: %s)" % res["graph_error"] if res["graph_error"] else "")),
+                   "list_lengths": "kept on the device (fixed-capacity lists): the step has no device->host read",
+                   "critic_and_makeup_convs": "excluded (stock cuDNN; SURVEY.md 8 a5) -- see --with-critic for the inclusive variant",
+                   "l2": "GB-class working set per step (> 126 MB L2) + 256 MB flush write between steps", "gc": "python cyclic GC collected before and disabled during the timed steps",
+                   "small_counts": res["counts"][0], "big_counts": res["counts"][1], "parallelism": "dp%d by image batch" % world},
         "e2e": {"value": rois_per_step / (ms_e2e / 1e3), "unit": "RoIs/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": step.h2d_bytes, "d2h_bytes_per_step": 4},
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
         "intertwiner_loss": {"ms_per_iter": ms_loss, "what": "statistics merge -> buffer update -> class match -> OptTrans / Sinkhorn(L=%d), "
-                             "%d classes, forward + backward, device-timed alone (it is also inside every step above)" % (wl["sinkhorn_iters"], NCLS - 1)},
-        "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
-        "gpu_launches_note": "libfi_b200 kernels launched directly in the timed region; with the loss head captured in CUDA graphs its 3 "
-                             "libfi_b200 kernels per step (buffer update x2, Sinkhorn) replay from the graph and are not in this count",
-        "host_enqueue_ms_per_step": host_ms, "ms_each_step": per_step_ms,
-        "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                     "frac": kernels[dom]["frac"], "traffic": traffic, "traffic_source": traffic_src, "peak_kind": peak_kind},
-        "kernels": kernels,
-        "clocks": clocks,
+                             "%d classes, forward + backward, device-timed alone (it is also inside every step above)" % (wl["sinkhorn_iters"], NCLS - 1),
+                             "gpu_vs_cpu_port_abs_diff": None},
+        "gpu_launches": int(round(res["launches_per_step"] * args.steps)), "gpu_launches_per_step": res["launches_per_step"],
+        "gpu_launches_note": "libfi_b200 kernels per step (counted while the step was captured) x steps; they run from the replayed graph" if res["graphed"]
+                             else "libfi_b200 kernels launched directly in the timed region",
+        "host_enqueue_ms_per_step": res["host_enqueue_ms_per_step"], "ms_each_step": res["ms_each_step"],
+        "eager": {"ms_per_step": ms_eager, "host_enqueue_ms_per_step": host_eager, "what": "the same step launch by launch with per-launch events (kernel families below)"},
+        "roofline": roof, "kernels": kernels, "clocks": clocks, "other_workloads": others,
     }
+    if nvlink:
+        out["nvlink"] = nvlink
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_reference(wl, seed=2000, budget_s=args.cpu_budget)
+        out["cpu_baseline"] = cpu_reference(wl, seed=2000, budget_s=args.cpu_budget, stats=stats, ot_state=ot_state)
+        cpu_loss = out["cpu_baseline"].pop("loss_vector", None)
+        if cpu_loss is not None:
+            out["intertwiner_loss"]["gpu_vs_cpu_port_abs_diff"] = float((gpu_loss.view(-1) - torch.tensor(cpu_loss).view(-1)).abs().max())
+            out["intertwiner_loss"]["loss_sum"] = float(gpu_loss.sum())
     print(json.dumps(out), flush=True)
 
 
+def run_with_critic(args, wl, dev, rank, world, lib, flush):
+    timer = Timer(dev, world, lib, flush)
+    step = CriticStep(wl, dev, world, seed=2000 + rank)
+    ms = timer(step.step, args.steps, args.warmup)
+    host_ms = 1e3 * timer.host_s / args.steps
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    rois_per_step = wl["batch"] * wl["rois_per_image"] * world
+    print(json.dumps({
+        "metric": METRIC + " + make-up conv + critic convs (a5 inclusive)", "value": rois_per_step / (ms / 1e3), "unit": "RoIs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": workload_name(args.workload, wl), "variant": "fi.Dev.forward + fi.IntertwinerLoss + backward called "
+                                        "directly: make-up conv3x3+BN+ReLU on every level map and the 27.9 M-parameter critic (stock cuDNN, fp32, TF32 off) are inside "
+                                        "the timed region; one host read per step (the list lengths size the critic's batches)"},
+        "host_enqueue_ms_per_step": host_ms, "ms_each_step": [round(v, 3) for v in timer.per_step], "gpu_launches": int(timer.launches),
+        "e2e": None, "roofline": None}), flush=True)
+
+
 # =================================================================================================== reference (CPU)
-def cpu_reference(wl, seed, budget_s=20.0):
-    """The reference's CPU path on a bounded sample: crop_and_resize.c (compiled unmodified, oracle/_ref) for every
-    RoIAlign call of the step on 1/k of the boxes, forward (OpenMP, all cores) + backward (serial, as written), plus
-    the whole class-level OT loss (torch-CPU restatement of lib/OT_module.py, all cores).  Throughput is scaled to
-    the full step: t_full = t_roialign_sample * k + t_loss."""
+def cpu_reference(wl, seed, budget_s=20.0, full=False, stats=None, ot_state=None):
+    """The reference's CPU path: crop_and_resize.c (compiled unmodified, oracle/_ref) for every RoIAlign call of the step, forward
+    (OpenMP, all cores) + backward (serial, as written), plus the whole class-level OT loss (torch-CPU port of lib/OT_module.py,
+    all cores).  full=True: every crop of the step.  Otherwise a bounded sample -- 1/k of the boxes of every call, per-box work
+    scaled by k, the per-call map allocation / zero fill counted once -- sized to cost about budget_s seconds."""
     import numpy as np
     from oracle import clib, pyref
     from feature_intertwiner_b200 import synth
@@ -428,8 +670,13 @@ def cpu_reference(wl, seed, budget_s=20.0):
     level = level.view(-1).numpy()
     flat = rois.view(-1, 4).numpy()
     shapes = synth.level_shapes(hw)
-    rng = np.random.default_rng(seed)
-    maps = [rng.standard_normal((B, DEPTH, h, w), dtype=np.float32) for (h, w) in shapes]
+    cache = cpu_reference.__dict__.setdefault("maps", {})
+    key = (B, hw)
+    if key not in cache:
+        rng = np.random.default_rng(seed)
+        cache.clear()
+        cache[key] = [rng.standard_normal((B, DEPTH, h, w), dtype=np.float32) for (h, w) in shapes]
+    maps = cache[key]
     calls = []
     for i in range(4):
         sm = np.nonzero(level == i + 2)[0]
@@ -440,23 +687,27 @@ def cpu_reference(wl, seed, budget_s=20.0):
         if i < 3 and len(bg):
             calls += [(i, 14, bg)]
     total_crops = sum(len(c[2]) for c in calls)
-    # one probe call sizes the sample so the whole baseline costs about budget_s
-    t0 = time.perf_counter()
-    probe = calls[0][2][:16]
-    o = fwd(maps[0], flat[probe], (probe // R).astype(np.int32), 7, 7)
-    bwd(o, flat[probe], (probe // R).astype(np.int32), maps[0].shape)
-    per_crop = (time.perf_counter() - t0) / 16 * 2.5
-    k = max(1, int(np.ceil(total_crops * per_crop / (0.6 * budget_s))))
+    k = 1
+    if not full:
+        # one probe call sizes the sample so the whole baseline costs about budget_s
+        t0 = time.perf_counter()
+        probe = calls[0][2][:16]
+        o = fwd(maps[0], flat[probe], (probe // R).astype(np.int32), 7, 7)
+        bwd(o, flat[probe], (probe // R).astype(np.int32), maps[0].shape)
+        per_crop = (time.perf_counter() - t0) / 16 * 2.5
+        k = max(1, int(np.ceil(total_crops * per_crop / (0.6 * budget_s))))
     t_var, t_fixed, n_sample = 0.0, 0.0, 0
     empty_b, empty_i = np.zeros((0, 4), np.float32), np.zeros((0,), np.int32)
     for (i, P, idx) in calls:
         sub = idx[::k]
         ind = (sub // R).astype(np.int32)
-        # per-call cost that does not depend on the number of boxes (allocation + memset of the dense gradient map, as the
-        # reference does it): measured with an empty box list and counted ONCE per call, not scaled by the sampling factor
-        t0 = time.perf_counter()
-        bwd(np.zeros((0, DEPTH, P, P), np.float32), empty_b, empty_i, maps[i].shape)
-        fixed = time.perf_counter() - t0
+        fixed = 0.0
+        if k > 1:
+            # per-call cost that does not depend on the number of boxes (allocation + memset of the dense gradient map, as the
+            # reference does it): measured with an empty box list and counted ONCE per call, not scaled by the sampling factor
+            t0 = time.perf_counter()
+            bwd(np.zeros((0, DEPTH, P, P), np.float32), empty_b, empty_i, maps[i].shape)
+            fixed = time.perf_counter() - t0
         t0 = time.perf_counter()
         o = fwd(maps[i], flat[sub], ind, P, P)
         bwd(o, flat[sub], ind, maps[i].shape)
@@ -465,21 +716,43 @@ def cpu_reference(wl, seed, budget_s=20.0):
         t_var += max(0.0, whole - fixed)
         n_sample += len(sub)
     t_roi_full = t_fixed + t_var * k
+    # ---- the loss: torch-CPU PORT of lib/OT_module.py + lib/model.py:meta_loss (oracle/pyref.py), all 80 foreground classes
     torch.manual_seed(seed)
     ot = pyref.OptTransRef(ch_x=FEAT, L=wl["sinkhorn_iters"])
     n_cls = NCLS - 1
-    x = torch.rand(n_cls, FEAT, 1).requires_grad_()
-    y = torch.rand(n_cls, FEAT, 1)
-    t0 = time.perf_counter()
-    ot(x, y).sum().backward()
-    t_loss = time.perf_counter() - t0
+    loss_vec = None
+    if stats is not None:
+        # the very class statistics of the GPU step, same OptTrans weights: merge -> buffer -> padded class match -> OT loss
+        ot.load_state_dict(ot_state)
+        bf, bc, sf, sc = stats
+        s_mean, s_n = pyref.merge_feat_vec_ref(sf, sc)
+        b_mean, b_n = pyref.merge_feat_vec_ref(bf, bc)
+        x = s_mean.t()[1:].unsqueeze(-1).contiguous().requires_grad_()
+        y = b_mean.t()[1:].unsqueeze(-1).contiguous()
+        mask = ((s_n.view(-1) > 0) & (b_n.view(-1) > 0))[1:].float()
+        t0 = time.perf_counter()
+        w = ot(x, y)
+        (w * mask).sum().backward()
+        t_loss = time.perf_counter() - t0
+        loss_vec = (w * mask).detach().tolist()
+    else:
+        x = torch.rand(n_cls, FEAT, 1).requires_grad_()
+        y = torch.rand(n_cls, FEAT, 1)
+        t0 = time.perf_counter()
+        ot(x, y).sum().backward()
+        t_loss = time.perf_counter() - t0
     t_full = t_roi_full + t_loss
+    if full:
+        sample = ("full step: every crop of every RoIAlign call (%d crops; fwd OpenMP x%d + bwd serial, %.2f s) + the full %d-class OT loss "
+                  "fwd+bwd, L=%d (torch-CPU port, %.2f s)" % (total_crops, cores, t_roi_full, n_cls, wl["sinkhorn_iters"], t_loss))
+    else:
+        sample = ("every RoIAlign call of the step on 1/%d of its boxes (%d of %d crops; fwd OpenMP x%d + bwd serial: %.2f s per-box "
+                  "work, scaled by %d, + %.2f s per-call map allocation / zero fill, counted once) + the full %d-class OT loss fwd+bwd, "
+                  "L=%d (torch-CPU port, %.2f s); full step %.1f s; `--impl reference` runs full steps"
+                  % (k, n_sample, total_crops, cores, t_var, k, t_fixed, n_cls, wl["sinkhorn_iters"], t_loss, t_full))
     return {"value": B * R / t_full, "unit": "RoIs/s", "cores": cores, "kind": kind,
-            "sample": "every RoIAlign call of the step on 1/%d of its boxes (%d of %d crops; fwd OpenMP x%d + bwd serial: %.2f s per-box "
-                      "work, scaled by %d, + %.2f s per-call map allocation / zero fill, counted once) + the full %d-class OT loss fwd+bwd, "
-                      "L=%d (%.2f s); full step %.1f s"
-                      % (k, n_sample, total_crops, cores, t_var, k, t_fixed, n_cls, wl["sinkhorn_iters"], t_loss, t_full),
-            "roialign_s_full_step": t_roi_full, "loss_s": t_loss}
+            "kind_note": "RoIAlign: lib/roi_align/src/crop_and_resize.c compiled unmodified (reference); loss: torch-CPU port of lib/OT_module.py (oracle/pyref.py)",
+            "sample": sample, "roialign_s_full_step": t_roi_full, "loss_s": t_loss, "loss_vector": loss_vec}
 
 
 def run_reference(args):
@@ -488,24 +761,25 @@ def run_reference(args):
         return
     from feature_intertwiner_b200 import synth
     wl = synth.WORKLOADS[args.workload]
-    # every step is a bounded sample of the workload; its size is chosen so that the W + K steps end within a few minutes
-    budget = max(3.0, min(args.cpu_budget, 150.0 / max(1, args.warmup + args.steps)))
+    # FULL steps (every crop of the step, ~3 s each at c2); only if W + K of them would take more than ~4 minutes are the steps
+    # bounded samples instead
+    probe = cpu_reference(wl, seed=2000, full=True)
+    t_step = wl["batch"] * wl["rois_per_image"] / probe["value"]
+    n = args.warmup + args.steps
+    full = t_step * n <= 240.0
     vals = []
-    for s in range(args.warmup + args.steps):
-        r = cpu_reference(wl, seed=2000, budget_s=budget)
+    for s in range(n):
+        r = cpu_reference(wl, seed=2000, full=full, budget_s=max(3.0, 200.0 / n))
         if s >= args.warmup:
             vals.append(r)
     v = sum(r["value"] for r in vals) / len(vals)
+    last = dict(vals[-1], value=v)
+    last.pop("loss_vector", None)
     out = {
-        "impl": "reference",
-        "metric": "RoIs/sec (RoIAlign fwd+bwd + split + class means + Sinkhorn intertwiner loss, fwd+bwd)",
-        "value": v, "unit": "RoIs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "RoIs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * wl["batch"] * wl["rois_per_image"] / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: batch %d/GPU, %dx%d, %d RoIs/img, FPN P2-P5 C=256, pools 7+14, Sinkhorn N=256 L=%d, class-level OT loss"
-                               % (args.workload, wl["batch"], wl["image"][0], wl["image"][1], wl["rois_per_image"], wl["sinkhorn_iters"])},
-        "cpu_baseline": dict(vals[-1], value=v),
-        "e2e": {"value": v, "unit": "RoIs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(args.workload, wl)},
+        "cpu_baseline": last, "e2e": {"value": v, "unit": "RoIs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out), flush=True)
 
@@ -515,9 +789,12 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c5"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work per reference sample")
+    ap.add_argument("--mode", default="graph", choices=["graph", "eager"])
+    ap.add_argument("--with-critic", action="store_true", help="a5-inclusive variant: fi.Dev.forward + fi.IntertwinerLoss called directly")
+    ap.add_argument("--no-other-workloads", action="store_true", help="skip the short c1 / c3 / c5 measurements")
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -47,10 +47,13 @@ SIGNATURES = {
     "fi_split_levels_gather": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "fi_segment_mean_forward": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "fi_segment_mean_backward": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    "fi_segment_mean_forward_n": (_I, [_P, _P, _I, _P, _I, _I, _P, _P, _P]),
+    "fi_segment_mean_backward_n": (_I, [_P, _P, _P, _I, _P, _I, _I, _P, _P]),
     "fi_sinkhorn": (_I, [_P, _P, _I, _I, _I, _F, _I, _P, _P, _P, _P]),
     "fi_buffer_update": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "fi_nms_batched": (_I, [_P, _I, _I, _F, _P, _P, _P, _P]),
     "fi_proposal_decode": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _F, _F, _P, _P, _P]),
+    "fi_proposal_gather": (_I, [_P, _P, _P, _I, _I, _I, _F, _F, _P, _P, _P]),
     "fi_roi_pool_forward": (_I, [_P, _F, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "fi_roi_pool_backward": (_I, [_P, _F, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
 }

@@ -121,9 +121,11 @@ constexpr int kSegThreads = 128;
 constexpr int kSegStage = 1024;
 
 __global__ void __launch_bounds__(kSegThreads) segment_mean_fwd_kernel(const int *__restrict__ gt, const float *__restrict__ feat, int k,
-                                                                      int F, int ncls, float *__restrict__ mean, float *__restrict__ cnt) {
+                                                                      const int *__restrict__ k_dev, int F, int ncls, float *__restrict__ mean,
+                                                                      float *__restrict__ cnt) {
     __shared__ int rows[kSegStage];
     __shared__ int nrows;
+    if (k_dev) k = min(k, *k_dev);                 // list length kept on the device: k is the capacity
     const int c = blockIdx.x;
     const int f = blockIdx.y * kSegThreads + threadIdx.x;
     float acc = 0.f;
@@ -170,11 +172,12 @@ __global__ void __launch_bounds__(kSegThreads) segment_mean_fwd_kernel(const int
 }
 
 __global__ void segment_mean_bwd_kernel(const int *__restrict__ gt, const float *__restrict__ gmean, const float *__restrict__ cnt, int k,
-                                        int F, int ncls, float *__restrict__ gfeat) {
+                                        const int *__restrict__ k_dev, int F, int ncls, float *__restrict__ gfeat) {
     const long total = (long)k * F;
+    const int live = k_dev ? min(k, *k_dev) : k;   // rows past the device-side length get a zero gradient
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
         const int i = (int)(e / F), f = (int)(e - (long)i * F);
-        const int c = gt[i];
+        const int c = i < live ? gt[i] : 0;
         float v = 0.f;
         if (c > 0 && c < ncls) v = __fdiv_rn(__ldg(gmean + (long)f * ncls + c), cnt[c]);
         gfeat[e] = v;
@@ -265,25 +268,32 @@ FI_API int fi_split_levels_gather(const int *level, const float *rois, const int
     return check_launch("fi_split_levels_gather");
 }
 
-FI_API int fi_segment_mean_forward(const int *gt, const float *feat, int k, int F, int ncls, float *mean, float *cnt,
-                                   cudaStream_t stream) {
+FI_API int fi_segment_mean_forward_n(const int *gt, const float *feat, int k, const int *k_dev, int F, int ncls, float *mean, float *cnt,
+                                     cudaStream_t stream) {
     FI_REQUIRE(k >= 0 && F > 0 && ncls > 0 && ncls <= 1024 && mean && cnt, "fi_segment_mean_forward: bad arguments");
     FI_REQUIRE(k == 0 || (gt && feat), "fi_segment_mean_forward: null pointer");
     dim3 grid(ncls, ceil_div(F, kSegThreads));
-    segment_mean_fwd_kernel<<<grid, kSegThreads, 0, stream>>>(gt, feat, k, F, ncls, mean, cnt);
+    segment_mean_fwd_kernel<<<grid, kSegThreads, 0, stream>>>(gt, feat, k, k_dev, F, ncls, mean, cnt);
     return check_launch("fi_segment_mean_forward");
 }
+FI_API int fi_segment_mean_forward(const int *gt, const float *feat, int k, int F, int ncls, float *mean, float *cnt, cudaStream_t stream) {
+    return fi_segment_mean_forward_n(gt, feat, k, nullptr, F, ncls, mean, cnt, stream);
+}
 
-FI_API int fi_segment_mean_backward(const int *gt, const float *grad_mean, const float *cnt, int k, int F, int ncls,
-                                    float *grad_feat, cudaStream_t stream) {
+FI_API int fi_segment_mean_backward_n(const int *gt, const float *grad_mean, const float *cnt, int k, const int *k_dev, int F, int ncls,
+                                      float *grad_feat, cudaStream_t stream) {
     FI_REQUIRE(k >= 0 && F > 0 && ncls > 0, "fi_segment_mean_backward: bad arguments");
     if (k == 0) return ok();
     FI_REQUIRE(gt && grad_mean && cnt && grad_feat, "fi_segment_mean_backward: null pointer");
     long total = (long)k * F;
     long grid = (total + 255) / 256;
     if (grid > kNumSMs * 8) grid = kNumSMs * 8;
-    segment_mean_bwd_kernel<<<(int)grid, 256, 0, stream>>>(gt, grad_mean, cnt, k, F, ncls, grad_feat);
+    segment_mean_bwd_kernel<<<(int)grid, 256, 0, stream>>>(gt, grad_mean, cnt, k, k_dev, F, ncls, grad_feat);
     return check_launch("fi_segment_mean_backward");
+}
+FI_API int fi_segment_mean_backward(const int *gt, const float *grad_mean, const float *cnt, int k, int F, int ncls, float *grad_feat,
+                                    cudaStream_t stream) {
+    return fi_segment_mean_backward_n(gt, grad_mean, cnt, k, nullptr, F, ncls, grad_feat, stream);
 }
 
 FI_API int fi_buffer_update(const float *big_sum, const float *big_n, int B, int slot, int F, int ncls, float *buffer,

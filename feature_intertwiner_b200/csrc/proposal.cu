@@ -40,9 +40,44 @@ __global__ void __launch_bounds__(256) proposal_decode_kernel(const float *__res
     d[0] = x1; d[1] = y1; d[2] = x2; d[3] = y2; d[4] = scores[i];                                                       // pth_nms.py:28-33
 }
 
+// Back half (lib/layers.py:128-139 + lib/nms/nms_wrapper.py:24-33): every image is truncated to the smallest keep count of
+// the batch (and to proposal_count), the kept boxes are gathered and normalised; rows past that count are zero -- what
+// the reference's later layers pad with anyway (lib/layers.py:413,427).  The count itself stays on the device.
+__global__ void __launch_bounds__(256) proposal_gather_kernel(const float *__restrict__ boxes, const int *__restrict__ keep, const int *__restrict__ num,
+                                                             int bs, int K, int count, float norm_h, float norm_w, float *__restrict__ out,
+                                                             int *__restrict__ m_out) {
+    int m = count;
+    for (int b = 0; b < bs; ++b) m = min(m, num[b]);        // bs is a handful of images: every thread reads them (L1 broadcast)
+    const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i == 0 && m_out) *m_out = m;
+    if (i >= (long)bs * count) return;
+    const int b = (int)(i / count), j = (int)(i - (long)b * count);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < m) {
+        const int k = keep[(long)b * K + j];
+        if (k >= 0 && k < K) {
+            const float4 bx = *reinterpret_cast<const float4 *>(boxes + ((long)b * K + k) * 4);
+            v = make_float4(__fdiv_rn(bx.x, norm_h), __fdiv_rn(bx.y, norm_w), __fdiv_rn(bx.z, norm_h), __fdiv_rn(bx.w, norm_w));   // boxes_keep / norm
+        }
+    }
+    *reinterpret_cast<float4 *>(out + i * 4) = v;
+}
+
 }  // namespace fi
 
 using namespace fi;
+
+FI_API int fi_proposal_gather(const float *boxes, const int *keep, const int *num_keep, int batch, int num_proposals, int proposal_count,
+                              float window_height, float window_width, float *rois, int *num_rois, cudaStream_t stream) {
+    FI_REQUIRE(batch >= 0 && num_proposals >= 0 && proposal_count >= 0 && window_height > 0.f && window_width > 0.f, "fi_proposal_gather: bad sizes");
+    if (batch == 0 || proposal_count == 0) return ok();
+    FI_REQUIRE(boxes && keep && num_keep && rois, "fi_proposal_gather: null pointer");
+    FI_REQUIRE(((uintptr_t)boxes % 16) == 0 && ((uintptr_t)rois % 16) == 0, "fi_proposal_gather: 16-byte aligned tensors");
+    const long total = (long)batch * proposal_count;
+    proposal_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(boxes, keep, num_keep, batch, num_proposals, proposal_count,
+                                                                               window_height, window_width, rois, num_rois);
+    return check_launch("fi_proposal_gather");
+}
 
 FI_API int fi_proposal_decode(const float *deltas, const float *anchors, const long long *order, const float *scores_sorted, int batch,
                               int num_anchors, int num_proposals, const float *std_dev4, float window_height, float window_width,

@@ -26,7 +26,7 @@ struct FwdSet {                  // one forward crop set (device view)
     const float *image, *boxes;
     const int *box_ind, *dst_row, *R_dev;     // R_dev: NULL, or the actual number of boxes on the device (units past it exit)
     float *crops, *crops2;
-    int B, H, W, C, ph, pw, slabs;
+    int B, H, W, C, ph, pw, slabs, R;         // R: number of boxes (capacity of the lists when R_dev is given)
     float extrap;
 };
 

@@ -46,13 +46,20 @@ class LevelSplit(object):
     """Per-level index lists of flat RoI ids (torch.nonzero order) for levels 2..5, optionally with the gathered boxes,
     image indices and class ids of every list (one kernel, one 8-int host read for all of it)."""
 
-    def __init__(self, small_idx, small_cnt, big_idx, big_cnt, slot, gathered=None, img_cnt=None):
+    def __init__(self, small_idx, small_cnt, big_idx, big_cnt, slot, gathered=None, img_cnt=None, sync=True):
         self.small_idx, self.big_idx, self.slot = small_idx, big_idx, slot
         self.g = gathered
+        self.small_cnt_dev, self.big_cnt_dev = small_cnt, big_cnt      # int32 [4] each, on the device
+        self.img_offsets = None
+        if not sync:
+            # No host read at all: every list keeps its full capacity (n) and its length stays on the device
+            # (small_count(i) / big_count(i)); crop_sets / assign_feat2cls take those (fixed shapes, CUDA-graph capturable).
+            n = small_idx.size(1)
+            self.small_cnt, self.big_cnt = [n] * 4, [n] * 4
+            return
         parts = [small_cnt, big_cnt] + ([img_cnt.view(-1)] if img_cnt is not None else [])
         counts = torch.cat(parts).tolist()                       # the only host sync of the split
         self.small_cnt, self.big_cnt = counts[:4], counts[4:8]
-        self.img_offsets = None
         if img_cnt is not None:                                  # per list: first member of every image (lists are image-major)
             nb = img_cnt.size(1)
             self.img_offsets = []
@@ -62,6 +69,13 @@ class LevelSplit(object):
                     acc += v
                     off.append(acc)
                 self.img_offsets.append(off)
+
+    def small_count(self, i):
+        """Length of list i as a device int32 [1] tensor."""
+        return self.small_cnt_dev[i:i + 1]
+
+    def big_count(self, i):
+        return self.big_cnt_dev[i:i + 1]
 
     def small_img_offsets(self, i):
         return None if self.img_offsets is None else self.img_offsets[i]
@@ -109,10 +123,12 @@ def spatial_order(rois, grid=None):
     return torch.sort(key, stable=True)[1].int()
 
 
-def split_levels(level, rois=None, gt=None, order=None):
+def split_levels(level, rois=None, gt=None, order=None, sync=True):
     """level[...] int32 -> LevelSplit: small(l) = {level == l}, big(l) = {level > l} (lib/sub_module.py:442,367-378).
     With ``rois`` ([bs,R,4]) the same launch also gathers boxes / image index / class id (``gt`` [bs,R]) of every list;
-    ``order`` (a permutation, e.g. ``spatial_order(rois)``) replaces torch.nonzero order by that visiting order."""
+    ``order`` (a permutation, e.g. ``spatial_order(rois)``) replaces torch.nonzero order by that visiting order.
+    ``sync=False``: the list lengths are NOT read back; the lists keep their capacity and ``small_count(i)`` / ``big_count(i)``
+    hand the device-side lengths to crop_sets / assign_feat2cls."""
     _lib.require_cuda(level)
     flat = level.contiguous().view(-1)
     n = flat.numel()
@@ -127,7 +143,7 @@ def split_levels(level, rois=None, gt=None, order=None):
         if rois is None:
             _lib.check(_lib.lib().fi_split_levels(_lib.ptr(flat), n, _lib.ptr(small_idx), _lib.ptr(small_cnt), _lib.ptr(big_idx),
                                                   _lib.ptr(big_cnt), _lib.ptr(slot), _lib.stream_ptr(dev)))
-            return LevelSplit(small_idx, small_cnt, big_idx, big_cnt, slot)
+            return LevelSplit(small_idx, small_cnt, big_idx, big_cnt, slot, sync=sync)
         rois_flat = rois.detach().float().contiguous().view(-1, 4)
         gt_flat = None if gt is None else gt.detach().to(torch.int32).contiguous().view(-1)
         g = dict(small_boxes=torch.empty((4, m, 4), device=dev), big_boxes=torch.empty((4, m, 4), device=dev),
@@ -136,29 +152,32 @@ def split_levels(level, rois=None, gt=None, order=None):
             g["small_gt"] = torch.empty((4, m), device=dev, dtype=torch.int32)
             g["big_gt"] = torch.empty((4, m), device=dev, dtype=torch.int32)
         order = None if order is None else order.to(device=dev, dtype=torch.int32).contiguous()
-        img_cnt = torch.empty((8, max(int(rois.size(0)), 1)), device=dev, dtype=torch.int32) if rois.dim() == 3 else None
+        img_cnt = torch.empty((8, max(int(rois.size(0)), 1)), device=dev, dtype=torch.int32) if (rois.dim() == 3 and sync) else None
         _lib.check(_lib.lib().fi_split_levels_gather(
             _lib.ptr(flat), _lib.ptr(rois_flat), _lib.ptr(gt_flat), _lib.ptr(order), n, int(rois.size(-2)), _lib.ptr(small_idx), _lib.ptr(small_cnt),
             _lib.ptr(big_idx), _lib.ptr(big_cnt), _lib.ptr(slot), _lib.ptr(g["small_boxes"]), _lib.ptr(g["small_ind"]), _lib.ptr(g.get("small_gt")),
             _lib.ptr(g["big_boxes"]), _lib.ptr(g["big_ind"]), _lib.ptr(g.get("big_gt")), _lib.ptr(img_cnt), _lib.stream_ptr(dev)))
     # per-image extents are only meaningful when the visiting order is image-major (index order and spatial_order are)
-    return LevelSplit(small_idx, small_cnt, big_idx, big_cnt, slot, gathered=g, img_cnt=img_cnt)
+    return LevelSplit(small_idx, small_cnt, big_idx, big_cnt, slot, gathered=g, img_cnt=img_cnt, sync=sync)
 
 
 # ----------------------------------------------------------------------------------------------- segment mean
 class _SegmentMean(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, gt, feat, ncls):
+    def forward(ctx, gt, feat, ncls, count):
         _lib.require_cuda(feat, gt)
         feat2 = feat.flatten(1).float().contiguous()
         gt = gt.detach().to(torch.int32).contiguous()
         k, Fd = feat2.shape
+        if count is not None:
+            count = count.detach().to(device=feat2.device, dtype=torch.int32).reshape(-1)[:1].contiguous()
         mean = torch.empty((Fd, ncls), device=feat2.device, dtype=torch.float32)
         cnt = torch.empty((1, ncls), device=feat2.device, dtype=torch.float32)
         with torch.cuda.device(feat2.device):
-            _lib.check(_lib.lib().fi_segment_mean_forward(_lib.ptr(gt), _lib.ptr(feat2), k, Fd, ncls, _lib.ptr(mean), _lib.ptr(cnt),
-                                                          _lib.stream_ptr(feat2.device)))
-        ctx.save_for_backward(gt, cnt)
+            _lib.check(_lib.lib().fi_segment_mean_forward_n(_lib.ptr(gt), _lib.ptr(feat2), k, _lib.ptr(count), Fd, ncls, _lib.ptr(mean),
+                                                            _lib.ptr(cnt), _lib.stream_ptr(feat2.device)))
+        ctx.save_for_backward(gt, cnt, count if count is not None else torch.empty(0))
+        ctx.has_count = count is not None
         ctx.shape = tuple(feat.shape)
         ctx.dims = (k, Fd, ncls)
         ctx.mark_non_differentiable(cnt)
@@ -166,19 +185,20 @@ class _SegmentMean(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gmean, _gcnt):
-        gt, cnt = ctx.saved_tensors
+        gt, cnt, count = ctx.saved_tensors
         k, Fd, ncls = ctx.dims
         gmean = gmean.contiguous()
         gfeat = torch.empty((k, Fd), device=gmean.device, dtype=torch.float32)
         with torch.cuda.device(gmean.device):
-            _lib.check(_lib.lib().fi_segment_mean_backward(_lib.ptr(gt), _lib.ptr(gmean), _lib.ptr(cnt), k, Fd, ncls, _lib.ptr(gfeat),
-                                                           _lib.stream_ptr(gmean.device)))
-        return None, gfeat.view(ctx.shape), None
+            _lib.check(_lib.lib().fi_segment_mean_backward_n(_lib.ptr(gt), _lib.ptr(gmean), _lib.ptr(cnt), k, _lib.ptr(count) if ctx.has_count else None,
+                                                             Fd, ncls, _lib.ptr(gfeat), _lib.stream_ptr(gmean.device)))
+        return None, gfeat.view(ctx.shape), None, None
 
 
-def assign_feat2cls(box_gt, input_feat, num_classes):
-    """lib/sub_module.py:664-684: per-class mean of instance features -> (feat[F,ncls], cnt[1,ncls]); background skipped."""
-    return _SegmentMean.apply(box_gt, input_feat, int(num_classes))
+def assign_feat2cls(box_gt, input_feat, num_classes, count=None):
+    """lib/sub_module.py:664-684: per-class mean of instance features -> (feat[F,ncls], cnt[1,ncls]); background skipped.
+    ``count`` (a device int32): only the first ``count`` rows are in use (list length kept on the device)."""
+    return _SegmentMean.apply(box_gt, input_feat, int(num_classes), count)
 
 
 # ----------------------------------------------------------------------------------------------- Dev

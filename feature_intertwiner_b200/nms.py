@@ -95,7 +95,7 @@ def proposal_decode(inputs, priors, config):
     return boxes, dets
 
 
-def proposal_layer(inputs, proposal_count, nms_threshold, priors, config=None):
+def proposal_layer(inputs, proposal_count, nms_threshold, priors, config=None, static=False):
     """lib/layers.py:71-139 with the same call shape: ``inputs = [rpn_probs[bs,A,2], rpn_bbox[bs,A,4]]``, ``priors[A,4]`` anchors
     in pixels (y1,x1,y2,x2) -> normalised proposals ``[bs, m, 4]``, m = min(proposal_count, smallest keep count of the batch)
     like lib/nms/nms_wrapper.py:24-33.
@@ -103,13 +103,20 @@ def proposal_layer(inputs, proposal_count, nms_threshold, priors, config=None):
     The reference sorts on the device, gathers per image in a Python loop, runs five elementwise ops, concatenates for NMS,
     copies the 4.5 MB suppression mask of every image to the host, reduces it there and indexes again per image.  Here:
     one sort (torch), one decode launch (fi_proposal_decode: gather + deltas + clip + NMS layout), the batched on-device NMS,
-    one gather; the only host synchronisation left is reading ``m`` -- the reference's API returns a tensor of that size."""
+    one gather launch (fi_proposal_gather: truncation to the batch's smallest keep count + gather + normalisation).
+
+    ``static=False`` returns the reference's ``[bs, m, 4]`` -- reading ``m`` is the one host synchronisation, the API demands a
+    tensor of that size.  ``static=True`` returns ``(rois[bs, proposal_count, 4], m)`` with the rows past ``m`` zero (what the
+    reference's later layers pad with, lib/layers.py:413,427) and ``m`` a device int32: no host read at all, fixed shapes."""
     boxes, dets = proposal_decode(inputs, priors, config)
     bs, dev = boxes.size(0), boxes.device
     height, width = float(config.DATA.IMAGE_SHAPE[0]), float(config.DATA.IMAGE_SHAPE[1])
     keep, num = nms_presorted(dets, nms_threshold)
-    m = min(int(num.min().item()), int(proposal_count))                              # the one host sync
-    idx = keep[:, :m].long()
-    boxes_keep = torch.gather(boxes, 1, idx.unsqueeze(2).expand(bs, m, 4))
-    norm = torch.tensor([height, width, height, width], device=dev)
-    return boxes_keep / norm
+    rois = torch.empty((bs, int(proposal_count), 4), device=dev, dtype=torch.float32)
+    m_dev = torch.empty((1,), device=dev, dtype=torch.int32)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().fi_proposal_gather(_lib.ptr(boxes), _lib.ptr(keep), _lib.ptr(num), bs, boxes.size(1), int(proposal_count), height, width,
+                                                 _lib.ptr(rois), _lib.ptr(m_dev), _lib.stream_ptr(dev)))
+    if static:
+        return rois, m_dev
+    return rois[:, : int(m_dev.item())]                                              # the one host sync

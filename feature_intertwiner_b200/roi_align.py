@@ -86,6 +86,13 @@ def algorithmic_bytes(rec):
     U = distinct (b,y,x) tap pixels, counted on the device from the kernel's own tap table."""
     if "alg_bytes" in rec:
         return rec["alg_bytes"]
+    if "bwd" in rec:                                   # backward of a crop_sets pass: (C, P, two sources, capacity, device count) per set
+        total = rec["bwd"]["map_bytes"]
+        for Cc, P, dual, cap, count in rec["bwd"]["items"]:
+            R = cap if count is None else min(cap, int(count.item()))
+            total += 4 * Cc * R * P * P * (2 if dual else 1) + 20 * R
+        rec["alg_bytes"] = total
+        return total
     if "like" in rec:                                  # same shapes as the launch whose tensors were kept
         sets = _SETS_BY_SHAPE[rec["like"]]
         if isinstance(sets, list):
@@ -399,7 +406,7 @@ class _CropSets(torch.autograd.Function):
         # write every pixel of every named map once (the reduction fallback zero-fills first)
         sizes = {kp["image"]: kp["im_size"] for kp in keep}
         g_images = {i: torch.empty(sizes[i], device=dev, dtype=torch.float32, memory_format=cl) for i in sorted(sizes)}
-        live, dual, srcs, nbytes = [], [], [], 0
+        live, dual, srcs, items = [], [], [], []
         for k, kp in enumerate(keep):
             gs = g_outs[kp["out"]] if kp["out"] is not None else None
             gc = g_comp.get(k)
@@ -414,10 +421,9 @@ class _CropSets(torch.autograd.Function):
                 if kp["scattered"]:                      # only the compact copy received a gradient: its rows are in box order
                     kp = dict(kp, scattered=False)
                     keep = keep[:k] + [kp] + keep[k + 1:]
-            Cc, P = kp["im_size"][1], kp["crop"][0]
-            nbytes += 4 * Cc * kp["cap"] * P * P * (2 if dual[-1] else 1) + 20 * kp["cap"]
+            items.append((kp["im_size"][1], kp["crop"][0], dual[-1], kp["cap"], kp["count"]))
         touched = {keep[k]["image"] for k in range(len(keep)) if live[k]}
-        nbytes += 4 * sum(sizes[i][0] * sizes[i][1] * sizes[i][2] * sizes[i][3] for i in touched)
+        meta = dict(items=items, map_bytes=4 * sum(sizes[i][0] * sizes[i][1] * sizes[i][2] * sizes[i][3] for i in touched))
         if any(live):
             L = _lib.lib()
             arr = _bwd_sets(keep, live, dual, g_images, srcs)
@@ -432,7 +438,7 @@ class _CropSets(torch.autograd.Function):
                 finally:
                     _PLAN.update(old)
                 usable = bp.ok
-            with torch.cuda.device(dev), _Timed("crop_bwd_nhwc", alg_bytes=nbytes):
+            with torch.cuda.device(dev), _Timed("crop_bwd_nhwc", bwd=meta):
                 if usable:
                     if bp.event is not None:
                         torch.cuda.current_stream(dev).wait_event(bp.event)

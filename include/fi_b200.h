@@ -237,6 +237,12 @@ int fi_segment_mean_forward(const int *gt, const float *feat, int k, int F, int 
 /* grad_feat[i,:] = grad_mean[:,gt_i] / cnt[gt_i]  (0 for background rows) */
 int fi_segment_mean_backward(const int *gt, const float *grad_mean, const float *cnt, int k, int F, int ncls,
                              float *grad_feat, cudaStream_t stream);
+/* The same with the list length on the device: k is the capacity of gt / feat, *k_dev (NULL: k) the rows in use;
+ * backward writes zeros into the rows past it. */
+int fi_segment_mean_forward_n(const int *gt, const float *feat, int k, const int *k_dev, int F, int ncls, float *mean, float *cnt,
+                              cudaStream_t stream);
+int fi_segment_mean_backward_n(const int *gt, const float *grad_mean, const float *cnt, int k, const int *k_dev, int F, int ncls,
+                               float *grad_feat, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * 5. Sinkhorn optimal-transport loss (lib/OT_module.py:104-135), batched.
@@ -278,6 +284,13 @@ int fi_nms_batched(const float *boxes, int n_images, int n, float thresh, unsign
 int fi_proposal_decode(const float *deltas, const float *anchors, const long long *order, const float *scores_sorted, int batch,
                        int num_anchors, int num_proposals, const float *std_dev4, float window_height, float window_width,
                        float *boxes, float *dets_xyxys, cudaStream_t stream);
+
+/* Back half (lib/layers.py:128-139, lib/nms/nms_wrapper.py:24-33) without a host read: m = min(proposal_count, min_b num_keep[b]);
+ * rois[batch, proposal_count, 4] = boxes[b, keep[b,j]] / (H,W,H,W) for j < m, zeros after (the reference zero-pads RoI lists,
+ * lib/layers.py:413,427); *num_rois = m (device int, may be NULL).  boxes[batch,K,4], keep[batch,K], num_keep[batch] as
+ * fi_proposal_decode / fi_nms_batched leave them. */
+int fi_proposal_gather(const float *boxes, const int *keep, const int *num_keep, int batch, int num_proposals, int proposal_count,
+                       float window_height, float window_width, float *rois, int *num_rois, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * 8. RoIPool with an argmax-scatter backward (lib/roi_pooling/src/roi_pooling_cuda.c:7-88).

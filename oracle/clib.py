@@ -238,3 +238,23 @@ def ref_cpu_nms(dets_yxyxs, thresh):
     tk, tn, td, to, ta = _th(keep), _th(num), _th(d), _th(order), _th(areas)
     _ref_nms.cpu_nms(C.byref(tk), C.byref(tn), C.byref(td), C.byref(to), C.byref(ta), thresh)
     return keep[: int(num[0])].copy()
+
+
+def ref_cuda():
+    """The reference's own CUDA kernels (lib/roi_align/src/cuda/crop_and_resize_kernel.cu, lib/roi_pooling/src/roi_pooling_kernel.cu,
+    lib/nms/src/cuda/nms_kernel.cu) compiled unmodified for sm_100a (oracle/_ref/libref_cuda.so): a second oracle on the GPU box.
+    None when the library did not travel."""
+    p = os.path.join(_REF_DIR, "libref_cuda.so")
+    if not os.path.exists(p):
+        return None
+    L = C.CDLL(p)
+    P, I, F = C.c_void_p, C.c_int, C.c_float
+    L.CropAndResizeLaucher.argtypes = [P, P, P, I, I, I, I, I, I, I, F, P, P]
+    L.CropAndResizeLaucher.restype = None
+    L.CropAndResizeBackpropImageLaucher.argtypes = [P, P, P, I, I, I, I, I, I, I, P, P]
+    L.CropAndResizeBackpropImageLaucher.restype = None
+    L.ROIPoolForwardLaucher.argtypes = [P, F, I, I, I, I, I, I, P, P, P, P]          # roi_pooling_kernel.h:8-12
+    L.ROIPoolForwardLaucher.restype = I
+    L.ROIPoolBackwardLaucher.argtypes = [P, F, I, I, I, I, I, I, I, P, P, P, P]      # roi_pooling_kernel.h:14-18
+    L.ROIPoolBackwardLaucher.restype = I
+    return L

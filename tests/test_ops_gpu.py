@@ -517,3 +517,61 @@ def test_proposal_layer_vs_restatement(bs, A, pre, count):
     ref, _ = pyref.proposal_layer_ref([probs, deltas], count, 0.7, anchors, cfg)
     if tuple(ref.shape) == tuple(got.shape):
         assert (got - ref).abs().max() < 1e-5 or (got - ref).abs().median() < 1e-6
+
+
+@pytest.mark.parametrize("scale,hw", [(0.25, (52, 84)), (0.0625, (26, 42)), (0.125, (104, 168))])
+def test_roi_pool_vs_reference_cuda_kernel(scale, hw):
+    """RoIPool forward (values + argmax) and backward against the REFERENCE'S OWN CUDA kernels (lib/roi_pooling/src/roi_pooling_kernel.cu
+    compiled unmodified for sm_100a, oracle/_ref/libref_cuda.so), on level-sized maps, through the reference-named launchers of both
+    libraries; the reference's backward is a gather over the RoIs (fixed order), ours sums the same terms: compared to summation tolerance."""
+    ref = clib.ref_cuda()
+    if ref is None:
+        pytest.skip("oracle/_ref/libref_cuda.so did not travel")
+    from feature_intertwiner_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(17)
+    B, Cc, (H, W), R = 3, 64, hw, 400
+    feat = torch.randn(B, Cc, H, W, generator=g).cuda()
+    xy = torch.rand(R, 2, generator=g) * torch.tensor([W / scale, H / scale])
+    wh = torch.exp(torch.rand(R, 2, generator=g) * 3.5 + 2.0)
+    rois = torch.cat([torch.randint(0, B, (R, 1), generator=g).float(), xy - wh / 2, xy + wh / 2], 1)
+    rois[0, 1:] = torch.tensor([40., 40., 20., 20.])                    # end < start
+    rois[1, 1:] = torch.tensor([1e5, 1e5, 1e5 + 5, 1e5 + 5])            # outside the map: empty bins
+    rois = rois.cuda().contiguous()
+    s = torch.cuda.current_stream().cuda_stream
+    out = {}
+    for name, lib in (("ref", ref), ("ours", L)):
+        top = torch.full((R, Cc, 7, 7), 3.0, device="cuda")
+        arg = torch.full((R, Cc, 7, 7), -7, device="cuda", dtype=torch.int32)
+        assert lib.ROIPoolForwardLaucher(feat.data_ptr(), scale, R, H, W, Cc, 7, 7, rois.data_ptr(), top.data_ptr(), arg.data_ptr(), s) == 1
+        out[name] = (top, arg)
+    torch.cuda.synchronize()
+    assert torch.equal(out["ours"][0], out["ref"][0]) and torch.equal(out["ours"][1], out["ref"][1])
+    gy = torch.randn(R, Cc, 7, 7, generator=g).cuda()
+    grads = {}
+    for name, lib in (("ref", ref), ("ours", L)):
+        gi = torch.zeros(B, Cc, H, W, device="cuda")
+        assert lib.ROIPoolBackwardLaucher(gy.data_ptr(), scale, B, R, H, W, Cc, 7, 7, rois.data_ptr(), gi.data_ptr(), out["ref"][1].data_ptr(), s) == 1
+        grads[name] = gi
+    torch.cuda.synchronize()
+    torch.testing.assert_close(grads["ours"], grads["ref"], rtol=1e-5, atol=1e-5)
+    # and the operator layer on top (autograd) gives the same numbers
+    fi = _fi()
+    fc = feat.clone().requires_grad_()
+    o = fi.RoIPoolFunction(7, 7, scale)(fc, rois)
+    assert torch.equal(o, out["ref"][0])
+    o.backward(gy)
+    torch.testing.assert_close(fc.grad, grads["ref"], rtol=1e-5, atol=1e-5)
+
+
+def test_proposal_layer_static_has_no_host_read_and_matches():
+    """static=True: [bs, proposal_count, 4] zero-padded past the batch's smallest keep count, which stays on the device."""
+    fi = _fi()
+    hw = (832, 1344)
+    cfg = pyref.make_config(DATA__IMAGE_SHAPE=np.array([hw[0], hw[1], 3]), RPN__PRE_NMS_LIMIT=2000)
+    probs, deltas, anchors = _proposal_case(321, 3, 5000, hw)
+    want = fi.proposal_layer([probs.cuda(), deltas.cuda()], 600, 0.7, anchors.cuda(), cfg)
+    rois, m = fi.proposal_layer([probs.cuda(), deltas.cuda()], 600, 0.7, anchors.cuda(), cfg, static=True)
+    assert tuple(rois.shape) == (3, 600, 4) and m.dtype == torch.int32 and m.is_cuda
+    k = int(m.item())
+    assert k == want.size(1) and torch.equal(rois[:, :k], want) and float(rois[:, k:].abs().sum()) == 0.0
