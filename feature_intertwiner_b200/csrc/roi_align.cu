@@ -396,8 +396,8 @@ FI_API int fi_crop_taps(const float *boxes, int num_boxes, int H, int W, int ph,
     return check_launch("fi_crop_taps");
 }
 
-int fi_crop_forward_nchw_tma(const float *image, const float *boxes, const int *box_ind, const int *dst_row, int R, int B, int H, int W, int ph,
-                             int pw, int C, float extrap, float *crops, cudaStream_t stream);   // roi_align_nchw_tma.cu
+int fi_nchw_backward_via_nhwc(const float *grads, const float *boxes, const int *box_ind, const int *src_row, int R, int B, int H, int W, int ph,
+                              int pw, int C, float *gimg, int accumulate, cudaStream_t stream);   // roi_align_nchw_bwd.cu
 
 static int forward_impl(const float *image, int image_layout, const float *boxes, const int *box_ind, const int *dst_row, int R, int B, int H,
                         int W, int ph, int pw, int C, float extrap, float *crops, int crops_layout, float *crops2, cudaStream_t stream) {
@@ -428,13 +428,6 @@ static int forward_impl(const float *image, int image_layout, const float *boxes
     }
     if (image_layout == FI_LAYOUT_NCHW) {
         if (crops2) { set_error(FI_ERR_UNSUPPORTED, "fi_crop_and_resize_forward_dual is NHWC only"); return FI_ERR_UNSUPPORTED; }
-        {   // TMA-staged region tiles (roi_align_nchw_tma.cu) when the shape qualifies; opt-in (FI_NCHW_TMA=1): measured on
-            // C2 it is 0-60 % slower than the L1-cached direct loads below (profiles/r01_microbench_c2_tma.json), so it is not the default
-            if (option(FI_OPT_NCHW_TMA)) {
-                const int rc = fi_crop_forward_nchw_tma(image, boxes, box_ind, dst_row, R, B, H, W, ph, pw, C, extrap, crops, stream);
-                if (rc != FI_ERR_UNSUPPORTED) return rc;
-            }
-        }
         if (ph <= kNchwMaxTaps && pw <= kNchwMaxTaps) {
             dim3 grid(R, ceil_div(C, kNchwChunk));
             crop_fwd_nchw_kernel<<<grid, 256, 0, stream>>>(image, boxes, box_ind, dst_row, B, H, W, ph, pw, C, extrap, crops);
@@ -473,11 +466,16 @@ FI_API int fi_crop_and_resize_backward(const float *grads, int grads_layout, con
         FI_REQUIRE(R >= 0 && ph > 0 && pw > 0, "fi_crop_and_resize_backward: bad sizes");
         return fi_crop_and_resize_backward_multi(&one, 1, B, H, W, C, gimg, accumulate, fi_get_deterministic(), stream);
     }
+    if (int e = check_common(grads, boxes, box_ind, gimg, R, B, H, W, ph, pw, C)) return e;
+    if (image_layout == FI_LAYOUT_NCHW && grads_layout == FI_LAYOUT_NCHW && R > 0) {
+        // transposed through the NHWC tile-owner kernels when the shape qualifies (roi_align_nchw_bwd.cu): no zero fill, no atomics
+        const int rc = fi_nchw_backward_via_nhwc(grads, boxes, box_ind, src_row, R, B, H, W, ph, pw, C, gimg, accumulate, stream);
+        if (rc != FI_ERR_UNSUPPORTED) return rc;
+    }
     if (!accumulate) {
         cudaError_t e = cudaMemsetAsync(gimg, 0, sizeof(float) * (size_t)B * C * H * W, stream);
         if (e != cudaSuccess) { set_error(FI_ERR_CUDA, "fi_crop_and_resize_backward: memset: %s", cudaGetErrorString(e)); return FI_ERR_CUDA; }
     }
-    if (int e = check_common(grads, boxes, box_ind, gimg, R, B, H, W, ph, pw, C)) return e;
     if (R == 0) return ok();
     if (image_layout != grads_layout) {
         set_error(FI_ERR_UNSUPPORTED, "fi_crop_and_resize_backward: mixed layouts (grads %d, image %d)", grads_layout, image_layout);

@@ -1082,6 +1082,12 @@ char *workspace(size_t bytes, cudaStream_t stream) {
     return slot->ptr;
 }
 
+}  // namespace
+
+namespace fi { char *tile_workspace(size_t bytes, cudaStream_t stream) { return workspace(bytes, stream); } }   // for roi_align_nchw_bwd.cu
+
+namespace {
+
 bool same_geometry(const fi_bwd_set &a, const fi_bwd_set &b) {
     return a.boxes == b.boxes && a.box_ind == b.box_ind && a.src_row == b.src_row && a.batch == b.batch &&
            a.image_height == b.image_height && a.image_width == b.image_width && a.depth == b.depth && a.num_boxes == b.num_boxes &&

@@ -42,7 +42,6 @@ def test_library_is_sm_100a_and_uses_vector_reductions():
     assert "sm_100a" in out, out
     sass = subprocess.run(["cuobjdump", "-sass", build.build_library()], capture_output=True, text=True).stdout
     assert "REDG.E.ADD.F32x4" in sass          # 128-bit vector reduction in the NHWC backward
-    assert "UTMALDG.4D" in sass                # cp.async.bulk.tensor.4d (TMA) in the NCHW region-tile forward
     assert "SYNCS.ARRIVE.TRANS64" in sass      # mbarrier expect_tx
     assert "UBLKCP.S.G" in sass                # cp.async.bulk global -> shared: gradient rows of the NHWC backward (roi_align_bwd_pix.cu)
 

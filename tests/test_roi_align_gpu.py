@@ -70,7 +70,8 @@ def test_backward_matches_oracle(fmt, P, C):
     g = torch.Generator().manual_seed(5)
     grads = torch.randn(150, C, P, P, generator=g)
     want = clib.oracle_crop_and_resize_bwd(grads.numpy(), rois.numpy(), box_ind.numpy(), tuple(image.shape))
-    for deterministic in ((False, True) if (fmt == "nhwc" and C % 128 == 0) else (False,)):
+    # NCHW with C % 128 == 0 goes through the same tile-owner kernels between two transposes (csrc/roi_align_nchw_bwd.cu)
+    for deterministic in ((False, True) if C % 128 == 0 else (False,)):
         img = image.cuda().requires_grad_()
         x = img.contiguous(memory_format=torch.channels_last) if fmt == "nhwc" else img
         old = fi.set_deterministic(deterministic)
@@ -338,37 +339,6 @@ def test_full_size_properties_c5():
         assert torch.equal(grads[0], grads[1])
     finally:
         fi.set_deterministic(old)
-
-
-def test_nchw_tma_path_matches_plain_kernel():
-    """The TMA-staged NCHW forward (csrc/roi_align_nchw_tma.cu) is bit-identical to the plain NCHW kernel and to the oracle,
-    over every tile shape (8/16/32 px footprints), the direct-load fallback (footprint > 32 px) and all-outside boxes."""
-    fi = _fi()
-    g = torch.Generator().manual_seed(77)
-    B, C, H, W = 2, 128, 60, 72
-    image = torch.randn(B, C, H, W, generator=g)
-    sizes = torch.tensor([3., 6., 10., 14., 20., 28., 40., 55.])          # footprints from < 8 px to > 32 px
-    boxes = []
-    for sh in sizes:
-        for sw in sizes:
-            cy, cx = torch.rand(2, generator=g).tolist()
-            y1 = cy * (H - 1 - float(sh)) / (H - 1); x1 = cx * (W - 1 - float(sw)) / (W - 1)
-            boxes.append([y1, x1, y1 + float(sh) / (H - 1), x1 + float(sw) / (W - 1)])
-    boxes += [[1.5, 1.5, 1.9, 1.9], [-0.3, -0.2, 0.2, 0.3], [0., 0., 0., 0.], [0.7, 0.8, 1.2, 1.1]]
-    boxes = torch.tensor(boxes, dtype=torch.float32)
-    ind = torch.randint(0, B, (boxes.size(0),), generator=g, dtype=torch.int32)
-    for P in (7, 14, (3, 5)):
-        ph, pw = (P, P) if isinstance(P, int) else P
-        want = clib.oracle_crop_and_resize_fwd(image.numpy(), boxes.numpy(), ind.numpy(), ph, pw, 0.25)
-        old = fi.set_option("nchw_tma", 1)
-        try:
-            got = fi.crop_and_resize(image.cuda(), boxes.cuda(), ind.cuda(), ph, pw, 0.25)
-            np.testing.assert_array_equal(got.cpu().numpy(), want)
-            fi.set_option("nchw_tma", 0)
-            plain = fi.crop_and_resize(image.cuda(), boxes.cuda(), ind.cuda(), ph, pw, 0.25)
-        finally:
-            fi.set_option("nchw_tma", old)
-        assert torch.equal(plain, got)
 
 
 @pytest.mark.parametrize("mode", ["pix", "pix_exact", "smem", "smem_exact", "fused", "fused_exact", "red", "pix16", "pix_g8_exact"])
@@ -674,3 +644,29 @@ def test_full_size_vs_compiled_reference(wl_name):
         key = (is_mu, (shapes_mu if is_mu else shapes_raw).index(tuple(leaf.shape)))
         err = np.abs(nchw(got).astype(np.float64) - sums[key])
         assert np.all(err <= 2e-6 * mags[key] + 1e-6), "default-mode pass: max err/bound = %g" % float((err / (2e-6 * mags[key] + 1e-6)).max())
+
+
+def test_reference_named_backward_launcher_c256_accumulates_and_matches_reference_kernel():
+    """CropAndResizeBackpropImageLaucher at the model's channel count (NCHW, C = 256: transposed through the tile-owner kernels):
+    ADDS onto the caller's map like the reference kernel (crop_and_resize_kernel.cu:84-165), compared with that kernel itself
+    (oracle/_ref/libref_cuda.so, atomics: summation-order tolerance) and with the CPU oracle."""
+    from feature_intertwiner_b200 import _lib
+    image, rois, box_ind = _case(8, 3, 256, 52, 84, 300, zero_rows=12)
+    b, bi = rois.cuda(), box_ind.cuda()
+    L = _lib.lib()
+    s = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator().manual_seed(4)
+    for P in (7, 14):
+        grads = torch.randn(300, 256, P, P, generator=g)
+        base = torch.randn(3, 256, 52, 84, generator=g)
+        gi = base.clone().cuda()
+        L.CropAndResizeBackpropImageLaucher(grads.cuda().data_ptr(), b.data_ptr(), bi.data_ptr(), 300, 3, 52, 84, P, P, 256, gi.data_ptr(), s)
+        assert L.fi_last_status() == 0, L.fi_last_error()
+        want = clib.oracle_crop_and_resize_bwd(grads.numpy(), rois.numpy(), box_ind.numpy(), (3, 256, 52, 84))
+        np.testing.assert_allclose(gi.cpu().numpy(), base.numpy() + want, rtol=1e-5, atol=2e-5)
+        ref = clib.ref_cuda()
+        if ref is not None:
+            gr = base.clone().cuda()
+            ref.CropAndResizeBackpropImageLaucher(grads.cuda().data_ptr(), b.data_ptr(), bi.data_ptr(), 300, 3, 52, 84, P, P, 256, gr.data_ptr(), s)
+            torch.cuda.synchronize()
+            torch.testing.assert_close(gi, gr, rtol=1e-5, atol=2e-5)

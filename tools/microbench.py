@@ -112,10 +112,6 @@ def main():
                     _lib.check(_lib.lib().fi_crop_and_resize_backward(grads.data_ptr(), lay, boxes.data_ptr(), ind.data_ptr(), None, n, B, Hh, Ww,
                                                                       P, P, 256, gimg.data_ptr(), lay, 0, s))
                 tb = timeit(bwd, args.iters)
-                if fmt == "nchw":          # the plain (non-TMA) NCHW forward for comparison
-                    os.environ["FI_NCHW_TMA"] = "0"
-                    row["nchw_plain_fwd_ms"] = timeit(lambda: fi.crop_and_resize(img, boxes, ind, P, P), args.iters)
-                    del os.environ["FI_NCHW_TMA"]
                 row[fmt] = dict(fwd_ms=t, bwd_ms=tb, fwd_gbs=fwd_bytes / t / 1e6, bwd_gbs=bwd_bytes / tb / 1e6,
                                 fwd_frac=fwd_bytes / t / 1e6 / peak, bwd_frac=bwd_bytes / tb / 1e6 / peak)
                 del crops, grads, gimg
