@@ -66,6 +66,34 @@ def workload_name(name, wl):
         name, wl["batch"], wl["image"][0], wl["image"][1], wl["rois_per_image"], wl["sinkhorn_iters"], extra)
 
 
+def bind_to_gpu_numa(local):
+    """Pin this process (and, by first touch, its pinned host buffers) to the NUMA node the GPU hangs off: with every rank's
+    buffers on node 0 the e2e leg of ranks 4-7 crossed the socket link (round 1: 77 -> 180 ms/step from 1 to 8 GPUs)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(visible.split(",")[local]) if visible and visible.split(",")[local].isdigit() else local
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(phys)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]                                   # nvml: 00000000:1b:00.0, sysfs: 0000:1b:00.0
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus += list(range(int(lo), int(hi or lo) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return {"numa_node": node, "cpus": len(allowed)}
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler(object):
     """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  NVML is queried in-process from
     a thread (every 10 ms; a K-step region lasts tens of ms, an `nvidia-smi -lms 100` loop would see 0-1 samples of it and
@@ -250,6 +278,10 @@ class Step(object):
         # upper bound on the backward's sample-list entries for ANY split of `total` boxes: every RoI is small at exactly one
         # level (7x7 + 14x14, the latter with two gradient sources) and big at no more than three (14x14)
         self.max_entries = total * (4 * 49 + 8 * 196 + 12 * 196 + 32 * 11)
+        self.grad_bucket = None
+        if world > 1:
+            from feature_intertwiner_b200.dist import GradAllReduce
+            self.grad_bucket = GradAllReduce(self.ot.parameters())
         self.graph, self.graph_loss, self.graph_error = None, None, None
         self.launches_per_step = None
 
@@ -330,9 +362,9 @@ class Step(object):
         loss = self.loss_mod(feat_in).sum()
         torch.autograd.backward([loss, pooled_out, mask_out] + outs, [torch.ones_like(loss), inp["g_pooled"], inp["g_mask"]] + grads)
         if self.world > 1:
-            import torch.distributed as dist
-            flat = torch.cat([p.grad.reshape(-1) for p in self.ot.parameters()])
-            dist.all_reduce(flat)                     # gradient all-reduce of the path's own parameters (OptTrans)
+            # gradient all-reduce of the path's own parameters (OptTrans, 15.7 MB): started by a hook as soon as the loss head's
+            # backward has produced them, i.e. overlapped with the RoIAlign backward that follows it on the compute stream
+            self.grad_bucket.finish()
         for p in self.ot.parameters():
             p.grad = None
         self.last_split = split
@@ -490,6 +522,7 @@ def run_ours(args):
     rank, world, local = dist_env()
     import feature_intertwiner_b200 as fi
     from feature_intertwiner_b200 import _lib, synth
+    numa = bind_to_gpu_numa(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -520,6 +553,8 @@ def run_ours(args):
     # ---- kernel families (eager, per-launch events) and the loss head alone ------------------------
     kernels, ms_eager = kernel_families(fi, step, timer, max(3, args.steps // 2), peak)
     host_eager = 1e3 * timer.host_s / max(3, args.steps // 2)
+    if step.grad_bucket is not None:
+        step.grad_bucket.remove()       # the loss-only leg: statistics all-reduce included, OptTrans gradient all-reduce not
     step.loss_mod.enable_cuda_graph([step.last_feat_in[0], step.last_feat_in[1], step.last_feat_in[2].detach().requires_grad_(), step.last_feat_in[3]])
     ms_loss = timer(step.loss_only, args.steps, args.warmup)          # intertwiner loss alone, fwd + bwd
     # all-reduce of the class statistics: bus bandwidth at this size (it is latency, not bandwidth, that matters at 1.3 MB)
@@ -604,7 +639,7 @@ def run_ours(args):
                    "l2": "GB-class working set per step (> 126 MB L2) + 256 MB flush write between steps", "gc": "python cyclic GC collected before and disabled during the timed steps",
                    "small_counts": res["counts"][0], "big_counts": res["counts"][1], "parallelism": "dp%d by image batch" % world},
         "e2e": {"value": rois_per_step / (ms_e2e / 1e3), "unit": "RoIs/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "host_buffers": "pinned, first-touched on the GPU's NUMA node: %s" % (numa,)},
         "intertwiner_loss": {"ms_per_iter": ms_loss, "what": "statistics merge -> buffer update -> class match -> OptTrans / Sinkhorn(L=%d), "
                              "%d classes, forward + backward, device-timed alone (it is also inside every step above)" % (wl["sinkhorn_iters"], NCLS - 1),
                              "gpu_vs_cpu_port_abs_diff": None},

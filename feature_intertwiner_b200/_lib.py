@@ -54,6 +54,8 @@ SIGNATURES = {
     "fi_nms_batched": (_I, [_P, _I, _I, _F, _P, _P, _P, _P]),
     "fi_proposal_decode": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _F, _F, _P, _P, _P]),
     "fi_proposal_gather": (_I, [_P, _P, _P, _I, _I, _I, _F, _F, _P, _P, _P]),
+    "fi_mask_targets": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "fi_detection_decode": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _F, _F, _F, _P, _P, _P, _P, _P]),
     "fi_roi_pool_forward": (_I, [_P, _F, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "fi_roi_pool_backward": (_I, [_P, _F, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
 }

@@ -40,6 +40,7 @@ struct SinkParams {
     int TPR;                   // threads cooperating on one row in the a-update
     int TPC;                   // threads cooperating on one column in the b-update
     int keepC;                 // C kept in shared memory next to K (else recomputed for the loss)
+    int masked;                // only problems whose loss slot holds NaN are solved (the others were done by the D = 1 class kernel)
 };
 
 __host__ __device__ inline int round4(int v) { return (v + 3) & ~3; }
@@ -127,6 +128,14 @@ __global__ void __launch_bounds__(kSinkThreads) sinkhorn_kernel(const SinkParams
     float *red = smem + L.red;
     const int Np = round4(N);
 
+    if (p.masked) {                                               // the whole cluster reads the same flag: all or none return
+        const float flag = p.loss[prob];
+        if (!isnan(flag)) return;
+        if (CS > 1) {
+            cluster.sync();                                       // every CTA has seen the flag before it is cleared
+            if (rank == 0 && t == 0) p.loss[prob] = 0.f;          // the CTAs add their parts onto it at the end
+        }
+    }
     const int row0g = rank * NR;                                  // first global row owned by this CTA
     const int nrows = max(0, min(NR, N - row0g));                 // valid local rows
     const float *xp = p.x + (long)prob * N * D;
@@ -348,11 +357,17 @@ __device__ __forceinline__ float cta_column_sum(float (&cp)[32], Sink256Smem &sm
 }
 
 __global__ void __launch_bounds__(256, 1) sinkhorn_n256_d1_kernel(const float *__restrict__ x, const float *__restrict__ y, float *__restrict__ loss,
-                                                                 float *__restrict__ gx, float *__restrict__ gy, float inv_eps, int L) {
+                                                                 float *__restrict__ gx, float *__restrict__ gy, float inv_eps, int L, int masked) {
     __shared__ __align__(16) Sink256Smem sm;
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int prob = blockIdx.x >> 1;
+    if (masked) {                                          // solved by sinkhorn_d1_classes_kernel unless its loss slot holds NaN
+        const float flag = loss[prob];
+        if (!isnan(flag)) return;                          // both CTAs of the pair read the same flag
+        cluster.sync();
+        if (rank == 0 && threadIdx.x == 0) loss[prob] = 0.f;
+    }
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     const int cgp = lane & 7, rl = lane >> 3;
     const int r0 = (w * 4 + rl) * 4;                       // first of this thread's 4 local rows
@@ -494,6 +509,115 @@ __global__ void __launch_bounds__(256, 1) sinkhorn_n256_d1_kernel(const float *_
     cluster.sync();   // no CTA may exit while its peer can still read its shared memory
 }
 
+// ------------------------------------------------------------------------------------------------
+// D = 1 by CLASSES.  With one feature per row the cosine normalisation x^ = x / (|x| + 1e-20) is a sign function: every
+// entry with |x| >> 1e-20 becomes exactly -1, 0 or +1 in fp32 (the critic ends in a ReLU: 0 or 1).
+// Then C_ij = 1 - x^_i y^_j and K_ij = exp(-C_ij / eps) take one value per (class of i, class of j), all rows of a class see
+// the same sums, and the iteration a = c0 / (K b + EPS), b = c0 / (K^T a + EPS) closes on THREE a's and THREE b's weighted by
+// the class sizes: O(L) work per problem instead of O(L N^2).  One warp per problem; lane l holds elements l, l + 32, ...
+// A problem with any other value of x^ or y^ (|x| within a few orders of 1e-20) is left to the dense kernels: its loss slot
+// is set to NaN, which those kernels take as their work mask.
+// Values: the same K entries, the same update formulas; the sums over j run over classes instead of elements, i.e. another
+// summation order of identical terms (differences ~1e-7 relative against the 1e-4 bar).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sinkhorn_d1_classes_kernel(const float *__restrict__ x, const float *__restrict__ y, float *__restrict__ loss,
+                                                                 float *__restrict__ gx, float *__restrict__ gy, int P, int N, float inv_eps, int L) {
+    const int lane = threadIdx.x & 31;
+    const int prob = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (prob >= P) return;
+    const float *xp = x + (long)prob * N, *yp = y + (long)prob * N;
+    float xh[8], yh[8], dx[8], dy[8];
+    int nx0 = 0, nx1 = 0, nx2 = 0, ny0 = 0, ny1 = 0, ny2 = 0;      // class sizes: x^ = -1, 0, +1
+    bool clean = true;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int i = lane + 32 * k;
+        xh[k] = 0.f; yh[k] = 0.f; dx[k] = 1.f; dy[k] = 1.f;
+        if (i < N) {
+            const float v = __ldg(xp + i), w = __ldg(yp + i);
+            dx[k] = __fadd_rn(sqrtf(__fmul_rn(v, v)), kEps);     // OT_module.py:111-112 with D == 1
+            dy[k] = __fadd_rn(sqrtf(__fmul_rn(w, w)), kEps);
+            xh[k] = __fdiv_rn(v, dx[k]);
+            yh[k] = __fdiv_rn(w, dy[k]);
+            nx0 += xh[k] == -1.f; nx1 += xh[k] == 0.f; nx2 += xh[k] == 1.f;
+            ny0 += yh[k] == -1.f; ny1 += yh[k] == 0.f; ny2 += yh[k] == 1.f;
+            clean = clean && (xh[k] == -1.f || xh[k] == 0.f || xh[k] == 1.f) && (yh[k] == -1.f || yh[k] == 0.f || yh[k] == 1.f);
+        }
+    }
+    clean = __all_sync(0xffffffffu, clean);
+    if (!clean) {
+        if (lane == 0) loss[prob] = __int_as_float(0x7fc00000);   // NaN: "still to do" for the dense kernels
+        if (gy != nullptr)
+            for (int i = lane; i < N; i += 32) gy[(long)prob * N + i] = 0.f;   // the CTA-pair kernels add their halves onto it
+        return;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        nx0 += __shfl_xor_sync(0xffffffffu, nx0, d); nx1 += __shfl_xor_sync(0xffffffffu, nx1, d); nx2 += __shfl_xor_sync(0xffffffffu, nx2, d);
+        ny0 += __shfl_xor_sync(0xffffffffu, ny0, d); ny1 += __shfl_xor_sync(0xffffffffu, ny1, d); ny2 += __shfl_xor_sync(0xffffffffu, ny2, d);
+    }
+    const float nxf[3] = {(float)nx0, (float)nx1, (float)nx2}, nyf[3] = {(float)ny0, (float)ny1, (float)ny2};
+    float K[3][3], Cc[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            Cc[r][c] = __fsub_rn(1.f, __fmul_rn((float)(r - 1), (float)(c - 1)));   // OT_module.py:113
+            K[r][c] = expf(-inv_eps * Cc[r][c]);                                    // :116
+        }
+    const float c0 = 1.0f / (float)N;                              // :118-119
+    float a[3] = {c0, c0, c0}, b[3] = {c0, c0, c0};
+    for (int it = 0; it < L; ++it) {                               // :120-122, every lane the same scalars
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            float sum = 0.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) sum = fmaf(__fmul_rn(nyf[c], K[r][c]), b[c], sum);
+            a[r] = __fdiv_rn(c0, __fadd_rn(sum, kEps));
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float sum = 0.f;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) sum = fmaf(__fmul_rn(nxf[r], K[r][c]), a[r], sum);
+            b[c] = __fdiv_rn(c0, __fadd_rn(sum, kEps));
+        }
+    }
+    // P = a K b^T, loss = <P, C>   (:129-134)
+    float Pm[3][3], total = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            Pm[r][c] = __fmul_rn(__fmul_rn(a[r], K[r][c]), b[c]);
+            total = fmaf(__fmul_rn(__fmul_rn(nxf[r], nyf[c]), Pm[r][c]), Cc[r][c], total);
+        }
+    if (lane == 0) loss[prob] = total;
+    if (gx == nullptr) return;
+    // gradients with P constant: dL/dx^_i = -sum_j P_ij y^_j, then through the normalisation exactly as the dense kernels do
+    float gxh[3], gyh[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) gxh[r] = -(__fmul_rn(nyf[2], Pm[r][2]) - __fmul_rn(nyf[0], Pm[r][0]));
+#pragma unroll
+    for (int c = 0; c < 3; ++c) gyh[c] = -(__fmul_rn(nxf[2], Pm[2][c]) - __fmul_rn(nxf[0], Pm[0][c]));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int i = lane + 32 * k;
+        if (i < N) {
+            {
+                const float h = xh[k], g = h == -1.f ? gxh[0] : (h == 0.f ? gxh[1] : gxh[2]), den = dx[k];
+                const float shrink = __fdiv_rn(__fsub_rn(den, kEps), den);
+                gx[(long)prob * N + i] = __fdiv_rn(__fsub_rn(g, __fmul_rn(__fmul_rn(h, __fmul_rn(g, h)), shrink)), den);
+            }
+            {
+                const float h = yh[k], g = h == -1.f ? gyh[0] : (h == 0.f ? gyh[1] : gyh[2]), den = dy[k];
+                const float shrink = __fdiv_rn(__fsub_rn(den, kEps), den);
+                gy[(long)prob * N + i] = __fdiv_rn(__fsub_rn(g, __fmul_rn(__fmul_rn(h, __fmul_rn(g, h)), shrink)), den);
+            }
+        }
+    }
+}
+
 constexpr int kMaxSmemBytes = 227 * 1024;
 
 static int pow2_floor(int v) { int r = 1; while (r * 2 <= v) r *= 2; return r; }
@@ -523,8 +647,18 @@ FI_API int fi_sinkhorn(const float *x, const float *y, int n_problems, int N, in
     if (n_problems == 0) return ok();
     FI_REQUIRE(x && y && loss, "fi_sinkhorn: null pointer");
     FI_REQUIRE((grad_x == nullptr) == (grad_y == nullptr), "fi_sinkhorn: grad_x and grad_y must both be given or both be NULL");
-    if (N == 256 && D == 1 && !option(FI_OPT_SINKHORN_GENERIC)) {      // RoI-level loss: K in registers
-        cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(float) * n_problems, stream);
+    // D = 1: solved by classes (O(L) per problem) unless an entry's normalised value is not exactly -1 / 0 / +1; those problems
+    // keep NaN in their loss slot and the dense kernels below pick them up (masked).  FI_OPT_SINKHORN_GENERIC: 1 = dense only.
+    const int dense_only = option(FI_OPT_SINKHORN_GENERIC);
+    int masked = 0;
+    if (D == 1 && dense_only == 0) {
+        sinkhorn_d1_classes_kernel<<<ceil_div(n_problems, 8), 256, 0, stream>>>(x, y, loss, grad_x, grad_y, n_problems, N, inv_eps, L);
+        if (int e = check_launch("fi_sinkhorn[d1 classes]")) return e;
+        masked = 1;
+    }
+    if (N == 256 && D == 1 && dense_only != 2) {      // RoI-level loss: K in registers
+        cudaError_t e = cudaSuccess;
+        if (!masked) e = cudaMemsetAsync(loss, 0, sizeof(float) * n_problems, stream);
         if (e != cudaSuccess) { set_error(FI_ERR_CUDA, "fi_sinkhorn: memset: %s", cudaGetErrorString(e)); return FI_ERR_CUDA; }
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)(n_problems * 2));
@@ -535,7 +669,7 @@ FI_API int fi_sinkhorn(const float *x, const float *y, int n_problems, int N, in
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        e = cudaLaunchKernelEx(&cfg, sinkhorn_n256_d1_kernel, x, y, loss, grad_x, grad_y, inv_eps, L);
+        e = cudaLaunchKernelEx(&cfg, sinkhorn_n256_d1_kernel, x, y, loss, grad_x, grad_y, inv_eps, L, masked);
         if (e != cudaSuccess) { set_error(FI_ERR_CUDA, "fi_sinkhorn: launch: %s", cudaGetErrorString(e)); return FI_ERR_CUDA; }
         return check_launch("fi_sinkhorn[n256 d1]");
     }
@@ -551,8 +685,9 @@ FI_API int fi_sinkhorn(const float *x, const float *y, int n_problems, int N, in
             return FI_ERR_UNSUPPORTED;
         }
     }
+    p.masked = masked;
     cudaError_t e;
-    if (CS > 1) {
+    if (CS > 1 && !masked) {
         e = cudaMemsetAsync(loss, 0, sizeof(float) * n_problems, stream);
         if (e == cudaSuccess && grad_y) e = cudaMemsetAsync(grad_y, 0, sizeof(float) * (size_t)n_problems * N * D, stream);
         if (e != cudaSuccess) { set_error(FI_ERR_CUDA, "fi_sinkhorn: memset: %s", cudaGetErrorString(e)); return FI_ERR_CUDA; }

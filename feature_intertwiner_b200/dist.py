@@ -42,6 +42,62 @@ def merged_class_sums(feat, cnt, group=None, distributed=False, differentiable=T
     return s, n
 
 
+def merged_class_sums_pair(big_feat, big_cnt, small_feat, small_cnt, group=None, distributed=False, compensate=True):
+    """Both exchanges of an iteration -- reliable set (no gradient) and less-reliable set (differentiable) -- in ONE all-reduce of
+    the packed sums: (big_sum [F,ncls], big_n [ncls], small_sum [F,ncls], small_n [ncls]).  At 1.3 MB the cost of an all-reduce on
+    NVSwitch is its launch + latency, not bandwidth, so one call instead of two halves it."""
+    bs = (big_feat.detach() * big_cnt.detach()).sum(dim=(0, 1))
+    bn = big_cnt.detach().sum(dim=(0, 1)).reshape(-1)
+    ss = (small_feat * small_cnt).sum(dim=(0, 1))
+    sn = small_cnt.sum(dim=(0, 1)).reshape(-1)
+    if distributed:
+        import torch.distributed as dist
+        packed = torch.cat([bs.reshape(-1), bn, ss.reshape(-1), sn])
+        if packed.requires_grad:
+            packed = _AllReduceSum.apply(packed, group, compensate)
+        else:
+            packed = packed.detach().clone()
+            dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+        a, b = bs.numel(), bn.numel()
+        bs, bn = packed[:a].view_as(bs).detach(), packed[a:a + b].detach()
+        ss, sn = packed[a + b:2 * a + b].view_as(ss), packed[2 * a + b:]
+    return bs, bn, ss, sn
+
+
+class GradAllReduce(object):
+    """All-reduce(SUM) of a module's parameter gradients in one flat bucket, started the moment the LAST of them has been
+    accumulated (post-accumulate-grad hooks, like DDP's buckets) so that it overlaps with the rest of the backward pass -- here the
+    RoIAlign backward, which runs after the loss head's.  ``finish()`` waits and writes the reduced values back."""
+
+    def __init__(self, params, group=None):
+        import torch.distributed as dist
+        self.params = [p for p in params if p.requires_grad]
+        self.group, self.dist = group, dist
+        self.pending, self.work, self.flat = len(self.params), None, None
+        self.handles = [p.register_post_accumulate_grad_hook(self._hook) for p in self.params]
+
+    def _hook(self, _param):
+        self.pending -= 1
+        if self.pending == 0:
+            self.flat = torch.cat([p.grad.reshape(-1) for p in self.params])
+            self.work = self.dist.all_reduce(self.flat, op=self.dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def finish(self):
+        if self.work is not None:
+            self.work.wait()
+            off = 0
+            for p in self.params:
+                n = p.numel()
+                p.grad.copy_(self.flat[off:off + n].view_as(p.grad))
+                off += n
+        self.pending, self.work = len(self.params), None
+        return self.flat
+
+    def remove(self):
+        for h in self.handles:
+            h.remove()
+
+
 def shard_batch(n_items, rank, world):
     """Contiguous shard [lo, hi) of a batch of n_items images for `rank` of `world` (DataParallel's scatter along dim 0)."""
     per = (n_items + world - 1) // world

@@ -25,7 +25,7 @@ import torch.nn.functional as F
 from . import _lib
 from .roi_align import crop_and_resize, crop_pair, crop_sets
 from .roi_pool import RoIPoolFunction
-from .dist import merged_class_sums
+from .dist import merged_class_sums, merged_class_sums_pair
 
 EPS = 1e-20
 
@@ -589,12 +589,13 @@ class IntertwinerLoss(nn.Module):
 
     def _stage_sums(self, feat_input):
         """The exchange step: un-normalised class statistics of the reliable and of the less-reliable set, summed over
-        (gpu, scale) and -- when distributed -- all-reduced over the ranks (lib/model.py:151,177,217-224)."""
+        (gpu, scale) and -- when distributed -- all-reduced over the ranks in ONE collective (lib/model.py:151,177,217-224)."""
         big_feat, big_cnt, small_feat, small_cnt = feat_input[:4]
-        big_sum, big_n = self._sums(big_feat.detach(), big_cnt.detach(), differentiable=False)
         if self.config.DEV.INST_LOSS:
+            big_sum, big_n = self._sums(big_feat.detach(), big_cnt.detach(), differentiable=False)
             return big_sum.contiguous(), big_n.contiguous(), None, None
-        s_sum, s_n = self._sums(small_feat, small_cnt, differentiable=True)
+        big_sum, big_n, s_sum, s_n = merged_class_sums_pair(big_feat, big_cnt, small_feat, small_cnt, self.process_group if self.distributed else None,
+                                                            self.distributed, self.ddp_compensate)
         return big_sum.contiguous(), big_n.contiguous(), s_sum, s_n
 
     def _forward_eager(self, feat_input):

@@ -46,7 +46,9 @@ unsigned long long fi_kernel_launches(void); /* kernels this library has launche
                                      3 vector reductions [FI_BWD=red] */
 #define FI_OPT_TILE_SHAPE 1       /* tile of forms 1 and 2: 0 = 4x8 (default), 1 = 4x4 [FI_TILE=4x4], 2 = 2x8 [FI_TILE=2x8] */
 #define FI_OPT_RESERVED 2         /* (was: TMA-staged NCHW forward -- measured 0-60 % slower than the L1-cached direct loads, removed) */
-#define FI_OPT_SINKHORN_GENERIC 3 /* 1: generic shared-memory Sinkhorn kernel also for N=256, D=1 [FI_SINKHORN_GENERIC] */
+#define FI_OPT_SINKHORN_GENERIC 3 /* D = 1 problems: 0 = solved by classes, dense kernels only for what that leaves (default);
+                                     1 = dense kernels only (K in registers for N = 256); 2 = generic shared-memory kernel only
+                                     [FI_SINKHORN_GENERIC=1|2] */
 #define FI_OPT_PIX_CFG 4          /* form 0, ring shape (slots per batch x batches, CTAs per SM): 0 = 32x2,3 (default); 1 = 32x3,2;
                                      2 = 16x6,2; 3 = 16x4,3 [FI_PIX_CFG] */
 #define FI_OPT_PIX_GROUP 5        /* form 0, tiles per work ticket minus 1: 0..7 [FI_PIX_GROUP] */
@@ -291,6 +293,22 @@ int fi_proposal_decode(const float *deltas, const float *anchors, const long lon
  * fi_proposal_decode / fi_nms_batched leave them. */
 int fi_proposal_gather(const float *boxes, const int *keep, const int *num_keep, int batch, int num_proposals, int proposal_count,
                        float window_height, float window_width, float *rois, int *num_rois, cudaStream_t stream);
+
+/* Mask targets of the positive RoIs (lib/layers.py:296-323) in one launch: targets[i] = round(crop_and_resize(gt_masks[assignment[i]],
+ * box_i, target_h x target_w)), box_i = pos_rois[i] rewritten into the frame of gt_boxes[assignment[i]] when use_mini_mask
+ * (lib/layers.py:304-313), else pos_rois[i].  gt_masks[num_gt, mask_h, mask_w] fp32, pos_rois[num_rois,4], gt_boxes[num_gt,4],
+ * assignment[num_rois] int32 -> targets[num_rois, target_h, target_w]. */
+int fi_mask_targets(const float *gt_masks, const float *pos_rois, const float *gt_boxes, const int *assignment, int num_rois, int num_gt,
+                    int mask_height, int mask_width, int target_height, int target_width, int use_mini_mask, float *targets,
+                    cudaStream_t stream);
+
+/* Decode half of detection_layer (lib/layers.py:738-766) in one launch, one RoI per thread: arg-max class, its deltas * std_dev
+ * (4 HOST floats), apply_box_deltas, scale to pixels, clip to windows[batch,4], round, keep = class > 0 && score >= min_confidence
+ * && area > 0.  rois[batch*R,4] normalised, probs[batch*R,ncls], deltas[batch*R,ncls,4] -> boxes[batch*R,4] (y1,x1,y2,x2) pixels,
+ * scores, class_ids, keep. */
+int fi_detection_decode(const float *rois, const float *probs, const float *deltas, const float *windows, int batch, int rois_per_image,
+                        int num_classes, const float *std_dev4, float image_height, float image_width, float min_confidence, float *boxes,
+                        float *scores, int *class_ids, int *keep, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * 8. RoIPool with an argmax-scatter backward (lib/roi_pooling/src/roi_pooling_cuda.c:7-88).

@@ -414,3 +414,54 @@ def proposal_layer_ref(inputs, proposal_count, nms_threshold, priors, config):
     boxes_keep = torch.stack([boxes[i][keep[i]] for i in range(bs)])
     norm = torch.tensor([height, width, height, width])
     return boxes_keep / norm, keep
+
+
+# =============================================================================== mask targets / detection layer
+def mask_targets_ref(pos_rois, gt_boxes, assignment, gt_masks, mask_shape, use_mini_mask=True):
+    """lib/layers.py:296-323: RoI rewritten into its GT box's frame, C = 1 crop of the assigned GT mask (C oracle), rounded."""
+    a = assignment.long()
+    roi_gt = gt_boxes[a]
+    boxes = pos_rois
+    if use_mini_mask:                                                                    # :304-313
+        y1, x1, y2, x2 = pos_rois.chunk(4, dim=1)
+        gy1, gx1, gy2, gx2 = roi_gt.chunk(4, dim=1)
+        gh, gw = gy2 - gy1, gx2 - gx1
+        boxes = torch.cat([(y1 - gy1) / gh, (x1 - gx1) / gw, (y2 - gy1) / gh, (x2 - gx1) / gw], dim=1)
+    crops = clib.oracle_crop_and_resize_fwd(gt_masks[a].unsqueeze(1).contiguous().numpy(), boxes.contiguous().numpy(),
+                                            np.arange(a.numel(), dtype=np.int32), int(mask_shape[0]), int(mask_shape[1]), 0.0)
+    return torch.round(torch.from_numpy(crops).squeeze(1))                               # :323
+
+
+def detection_layer_ref(rois, probs, deltas, windows, config):
+    """lib/layers.py:720-802 + conduct_nms (:664-717): arg-max class, class-specific refinement, clip to the window, round, then per
+    image and per class a greedy NMS in score order (C oracle, CPU rule IoU >= thr) and the DET_MAX_INSTANCES best survivors."""
+    bs, R = rois.size(0), rois.size(1)
+    K = int(config.TEST.DET_MAX_INSTANCES)
+    scores, cls = probs.max(dim=1)
+    d = deltas[torch.arange(bs * R), cls] * torch.from_numpy(np.reshape(config.DATA.BBOX_STD_DEV, [1, 4])).float()
+    refined = apply_box_deltas_ref(rois.reshape(1, -1, 4), d.unsqueeze(0))[0]
+    H, W = float(config.DATA.IMAGE_SHAPE[0]), float(config.DATA.IMAGE_SHAPE[1])
+    refined = refined * torch.tensor([H, W, H, W])
+    win = windows.repeat_interleave(R, dim=0)
+    refined = torch.stack([torch.minimum(torch.maximum(refined[:, 0], win[:, 0]), win[:, 2]), torch.minimum(torch.maximum(refined[:, 1], win[:, 1]), win[:, 3]),
+                           torch.minimum(torch.maximum(refined[:, 2], win[:, 0]), win[:, 2]), torch.minimum(torch.maximum(refined[:, 3], win[:, 1]), win[:, 3])], 1)
+    refined = torch.round(refined)
+    area = (refined[:, 0] - refined[:, 2]) * (refined[:, 1] - refined[:, 3])
+    keep = (cls > 0) & (scores >= float(config.TEST.DET_MIN_CONFIDENCE)) & (area > 0)
+    out = torch.zeros(bs, K, 6)
+    for b in range(bs):
+        sl = slice(b * R, (b + 1) * R)
+        idx = torch.nonzero(keep[sl]).squeeze(1)
+        if idx.numel() == 0:
+            continue
+        survivors = []
+        for c in torch.unique(cls[sl][idx]).tolist():
+            ix = idx[cls[sl][idx] == c]
+            sc, order = scores[sl][ix].sort(descending=True, stable=True)
+            bx = refined[sl][ix][order]
+            k = clib.oracle_nms(torch.cat([bx[:, [1, 0, 3, 2]], sc.unsqueeze(1)], 1).numpy(), float(config.TEST.DET_NMS_THRESHOLD), False)
+            survivors.append(ix[order[torch.from_numpy(k.astype(np.int64))]])
+        surv = torch.cat(survivors)
+        top = surv[scores[sl][surv].sort(descending=True, stable=True)[1][:K]]
+        out[b, : top.numel()] = torch.cat([refined[sl][top], cls[sl][top].unsqueeze(1).float(), scores[sl][top].unsqueeze(1)], 1)
+    return out

@@ -7,6 +7,9 @@
 * nms.npz         outputs of lib/nms/src/nms.c compiled unmodified (oracle/_ref)
 * sinkhorn.npz    outputs of lib/OT_module.py::OptTrans._sinkhorn_iterate, module imported as-is
 * opttrans.npz    outputs of lib/OT_module.py::OptTrans.forward (1-D and 2-D), weights included
+* targets.npz     mask targets (lib/layers.py:297-323, inline code of generate_roi, with CropAndResizeFunction bound to the compiled
+                  crop_and_resize.c) and detection_layer + conduct_nms (lib/layers.py:664-802, with `nms` bound to the compiled
+                  cpu_nms), same ast / PyTorch-0.3-shim mechanism as intertwiner.npz
 * intertwiner.npz outputs of the reference's own Python bodies on the path, cut out of the source with `ast` and
                   exec'd unmodified under a PyTorch-0.3 behaviour shim (tests/golden/ref_exec.py): the level rule
                   (lib/sub_module.py:397-410 and its twin lib/layers.py:168-181), tools/utils.py unique1d / log2,
@@ -238,6 +241,83 @@ def intertwiner_cases(ot_mod):
     np.savez_compressed(os.path.join(HERE, "intertwiner.npz"), **out)
 
 
+def targets_cases():
+    """Mask targets and the detection layer from the reference's own source text (ref_exec.py)."""
+    sys.path.insert(0, HERE)
+    import ref_exec as rx
+    out, cited = {}, {}
+    g = torch.Generator().manual_seed(2002)
+
+    class CropAndResizeFunction(object):                     # lib/roi_align/crop_and_resize.py:14-37 over the compiled reference C
+        def __init__(self, h, w, extrapolation_value=0):
+            self.h, self.w, self.e = h, w, extrapolation_value
+
+        def __call__(self, image, boxes, box_ind):
+            o = clib.ref_crop_and_resize_fwd(image.numpy(), boxes.numpy(), box_ind.numpy(), self.h, self.w, float(self.e))
+            return torch.from_numpy(o)
+
+    def nms(dets, thresh):                                   # lib/nms/nms_wrapper.py:14-34 over the compiled cpu_nms (lib/nms/src/nms.c)
+        keeps = [clib.ref_cpu_nms(dets[i].numpy(), thresh) for i in range(dets.size(0))]
+        m = min(len(k) for k in keeps)
+        return np.stack([k[:m] for k in keeps]).astype(np.int32)
+
+    ns = rx.load_functions([("tools/utils.py", "unique1d", None), ("tools/utils.py", "intersect1d", None),
+                            ("tools/box_utils.py", "apply_box_deltas", None), ("tools/box_utils.py", "clip_boxes", None),
+                            ("lib/layers.py", "conduct_nms", None), ("lib/layers.py", "detection_layer", None)],
+                           CropAndResizeFunction=CropAndResizeFunction, nms=nms)
+    cited.update(ns["__cited__"])
+
+    # ---- mask targets: lib/layers.py:297-323
+    G, n = 9, 60
+    for mini in (True, False):
+        mh, mw = (56, 56) if mini else (120, 168)
+        gt_masks = (torch.rand(G, mh, mw, generator=g) < 0.5).float()
+        for k in range(G):                                   # blobs rather than noise: a disc per mask
+            yy, xx = torch.meshgrid(torch.arange(mh).float(), torch.arange(mw).float(), indexing="ij")
+            cy, cx, rad = mh * (0.3 + 0.4 * torch.rand(1, generator=g)), mw * (0.3 + 0.4 * torch.rand(1, generator=g)), min(mh, mw) * (0.15 + 0.2 * torch.rand(1, generator=g))
+            gt_masks[k] = (((yy - cy) ** 2 + (xx - cx) ** 2) < rad ** 2).float()
+        gt_boxes = torch.rand(G, 4, generator=g) * 0.5
+        gt_boxes[:, 2:] = gt_boxes[:, :2] + 0.1 + torch.rand(G, 2, generator=g) * 0.4
+        assign = torch.randint(0, G, (n,), generator=g)
+        roi_gt = gt_boxes[assign]
+        POS_ROIS = (roi_gt + (torch.rand(n, 4, generator=g) - 0.5) * 0.12).clamp(0, 1)
+        cfgobj = types.SimpleNamespace(MRCNN=types.SimpleNamespace(USE_MINI_MASK=mini, MASK_SHAPE=[28, 28]))
+        loc = dict(ns, gt_masks=gt_masks.clone(), roi_gt_box_assignment=assign.clone(), POS_ROIS=POS_ROIS.clone(), roi_gt_boxes=roi_gt.clone(), config=cfgobj)
+        with rx.torch03():
+            exec(compile(rx.extract_lines("lib/layers.py", 297, 323), "lib/layers.py", "exec"), loc)
+        tag = "mask_mini" if mini else "mask_full"
+        out[tag + "_gt_masks"], out[tag + "_gt_boxes"], out[tag + "_assign"] = gt_masks.numpy(), gt_boxes.numpy(), assign.numpy().astype(np.int32)
+        out[tag + "_pos_rois"], out[tag + "_targets"] = POS_ROIS.numpy(), loc["MASKS"].numpy()
+    cited["mask_targets"] = "lib/layers.py:297-323"
+
+    # ---- detection_layer + conduct_nms: lib/layers.py:664-802
+    bs, R, ncls, hw = 2, 300, 81, (832, 1344)
+    cfgobj = types.SimpleNamespace(TEST=types.SimpleNamespace(DET_MAX_INSTANCES=100, DET_MIN_CONFIDENCE=0.3, DET_NMS_THRESHOLD=0.3),
+                                   DATA=types.SimpleNamespace(BBOX_STD_DEV=np.array([0.1, 0.1, 0.2, 0.2]), IMAGE_SHAPE=np.array([hw[0], hw[1], 3])),
+                                   MISC=types.SimpleNamespace(GPU_COUNT=0))
+    ctr = torch.rand(bs, R, 2, generator=g) * 0.8 + 0.1
+    size = torch.rand(bs, R, 2, generator=g) * 0.25 + 0.03
+    rois = torch.cat([ctr - size / 2, ctr + size / 2], dim=2).clamp(0, 1)
+    rois[:, 200:] = rois[:, :100] + (torch.rand(bs, 100, 4, generator=g) - 0.5) * 0.02      # near-duplicates: NMS has work to do
+    logits = torch.randn(bs * R, ncls, generator=g) * 2.0
+    logits[:, 0] += 1.0
+    cls = torch.randint(1, 12, (bs * R,), generator=g)                                      # few classes: several boxes per class
+    logits[torch.arange(bs * R), cls] += 6.0 * torch.rand(bs * R, generator=g)
+    probs = torch.softmax(logits, dim=1)
+    deltas = torch.randn(bs * R, ncls, 4, generator=g) * 0.5
+    windows = torch.tensor([[0.0, 0.0, 832.0, 1344.0], [16.0, 40.0, 800.0, 1300.0]])
+    with rx.torch03(), torch.no_grad():
+        det, _ = ns["detection_layer"](rois.clone(), probs.clone(), deltas.clone(), windows.clone(), cfgobj, feature=torch.zeros(bs * R, 4))
+    out["det_rois"], out["det_probs"], out["det_deltas"], out["det_windows"] = rois.numpy(), probs.numpy(), deltas.numpy(), windows.numpy()
+    out["det_out"] = det.numpy()
+    cfgobj.TEST.DET_MIN_CONFIDENCE = 0.93                        # fewer candidates than DET_MAX_INSTANCES: zero rows after the detections
+    with rx.torch03(), torch.no_grad():
+        det2, _ = ns["detection_layer"](rois.clone(), probs.clone(), deltas.clone(), windows.clone(), cfgobj, feature=torch.zeros(bs * R, 4))
+    out["det_out_conf093"] = det2.numpy()
+    out["cited"] = np.array(sorted("%s=%s" % kv for kv in cited.items()))
+    np.savez_compressed(os.path.join(HERE, "targets.npz"), **out)
+
+
 if __name__ == "__main__":
     assert os.path.isdir(REF), "run in the build container (needs /root/reference)"
     clib.build(ref=True)
@@ -247,6 +327,7 @@ if __name__ == "__main__":
     sinkhorn_cases(ot)
     opttrans_cases(ot)
     intertwiner_cases(ot)
+    targets_cases()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -44,7 +44,7 @@ def torch03():
             return r.to(torch.uint8) if isinstance(r, torch.Tensor) else r
         return op
 
-    T.__getitem__ = lambda self, idx: _keep1(getitem(self, idx))
+    T.__getitem__ = lambda self, idx: _keep1(getitem(self.view(1) if self.dim() == 0 else self, idx))
     T.squeeze = lambda self, *a, **k: _keep1(squeeze(self, *a, **k))
     T.cuda = lambda self, *a, **k: self
     setitem = T.__setitem__

@@ -45,6 +45,29 @@ def _worker(rank, world, port, out):
     gathered = [torch.empty_like(s2) for _ in range(world)]
     dist.all_gather(gathered, s2)
     ok = ok and all(torch.equal(gathered[0], t) for t in gathered)
+    # both exchanges of an iteration in ONE collective (merged_class_sums_pair) == the two separate ones
+    from feature_intertwiner_b200.dist import GradAllReduce, merged_class_sums_pair
+    cnt_s = torch.randint(0, 3, (G, S, 1, ncls), generator=g).float()
+    feat_s = torch.rand(G, S, Fd, ncls, generator=g) * (cnt_s > 0)
+    fs = feat_s[lo:hi].clone().requires_grad_()
+    bs, bn, ss, sn = merged_class_sums_pair(feat[lo:hi], cnt[lo:hi], fs, cnt_s[lo:hi], None, True, True)
+    ss_ref, sn_ref = merged_class_sums(feat_s[lo:hi].clone(), cnt_s[lo:hi], None, True, differentiable=False)
+    ok = ok and torch.equal(bs, s2) and torch.equal(bn, n2) and torch.allclose(ss, ss_ref) and torch.equal(sn, sn_ref) and not bs.requires_grad
+    (ss * w).sum().backward()
+    fr = feat_s.clone().requires_grad_()
+    ((fr * cnt_s).sum(dim=(0, 1)) * w).sum().backward()
+    ok = ok and torch.allclose(fs.grad / world, fr.grad[lo:hi], rtol=1e-5, atol=1e-8)
+    # gradient bucket: hooks fire on the last accumulated gradient, finish() leaves the SUM over ranks in .grad
+    lin = torch.nn.Linear(4, 3)
+    with torch.no_grad():
+        lin.weight.fill_(0.5); lin.bias.fill_(0.1)
+    bucket = GradAllReduce(lin.parameters())
+    x = torch.full((2, 4), float(rank + 1))
+    lin(x).sum().backward()
+    bucket.finish()
+    want_w = sum(2.0 * (r + 1) for r in range(world))
+    ok = ok and torch.allclose(lin.weight.grad, torch.full((3, 4), want_w)) and torch.allclose(lin.bias.grad, torch.full((3,), 2.0 * world))
+    bucket.remove()
     out[rank] = bool(ok)
     dist.destroy_process_group()
 

@@ -52,6 +52,49 @@ def test_sinkhorn_vs_oracle_values_and_grads(N, D):
         np.testing.assert_allclose(yc.grad[p].cpu().numpy() / w[p].item(), gy, rtol=2e-3, atol=2e-6)
 
 
+@pytest.mark.parametrize("N", [256, 100, 1])
+def test_sinkhorn_d1_class_kernel_vs_dense_kernels_and_oracle(N):
+    """D = 1: problems whose normalised entries are exactly -1 / 0 / +1 are solved by classes (sinkhorn_d1_classes_kernel, O(L) per
+    problem); problems with an entry within a few orders of 1e-20 fall through to the dense kernels (masked launch).  Both
+    against the fp64-accumulated oracle and against the dense kernels alone (fi_set_option: K in registers / generic)."""
+    fi = _fi()
+    g = torch.Generator().manual_seed(40 + N)
+    P = 12
+    x = torch.randn(P, N, 1, generator=g).abs()
+    y = torch.randn(P, N, 1, generator=g).abs()
+    x[:, ::5] = 0                                           # ReLU zeros
+    y[2:, ::7] = 0
+    x[3] = -x[3]                                            # a problem with -1 entries (never produced by the critic; API is general)
+    if N > 1:
+        y[4, 1::2] *= -1
+        x[5, 3] = 2.5e-20                                   # x^ = 0.71...: problem 5 must go to the dense kernel
+        y[6, 0] = 7.0e-21
+        x[7] = 0                                            # all-zero rows: C = 1 everywhere
+    res = {}
+    for mode in (0, 1, 2):
+        old = fi.set_option("sinkhorn_generic", mode)
+        try:
+            xc, yc = x.cuda().requires_grad_(), y.cuda().requires_grad_()
+            loss = fi.sinkhorn_loss(xc, yc, epsilon=0.7, L=30)
+            loss.sum().backward()
+            res[mode] = (loss.detach().cpu(), xc.grad.cpu(), yc.grad.cpu())
+        finally:
+            fi.set_option("sinkhorn_generic", old)
+    for p in range(P):
+        want, _, gx, gy = clib.oracle_sinkhorn(x[p].numpy(), y[p].numpy(), inv_eps=1.0 / 0.7, L=30, wide=True, want_grad=True)
+        for mode in (0, 1, 2):
+            assert abs(res[mode][0][p].item() - want) < 2e-5, (N, p, mode, res[mode][0][p].item(), want)
+        well = (x[p].abs().view(-1) > 1e-10).numpy()        # d/dx of x / (|x| + 1e-20) is 1e20 at 0: compare the well-posed rows
+        welly = (y[p].abs().view(-1) > 1e-10).numpy()
+        np.testing.assert_allclose(res[0][1][p].numpy()[well], gx[well], rtol=2e-3, atol=2e-6)
+        np.testing.assert_allclose(res[0][2][p].numpy()[welly], gy[welly], rtol=2e-3, atol=2e-6)
+    # the class path reproduces the dense kernels to rounding, ill-posed rows included
+    torch.testing.assert_close(res[0][0], res[1][0], rtol=2e-6, atol=2e-7)
+    torch.testing.assert_close(res[0][0], res[2][0], rtol=2e-6, atol=2e-7)
+    for k in (1, 2):
+        torch.testing.assert_close(res[0][k], res[1][k], rtol=1e-4, atol=1e-7)
+
+
 def test_sinkhorn_properties_full_size():
     """Size-independent properties at BASELINE sizes: x == y => debiased loss 0; batch order invariance."""
     fi = _fi()

@@ -189,3 +189,96 @@ def test_proposal_decode_cuda_vs_reference(Z):
     np.testing.assert_allclose(boxes.cpu().numpy(), Z["box_clipped"], rtol=3e-6, atol=2e-4)
     inside = (Z["box_applied"] == Z["box_clipped"])
     assert inside.mean() > 0.5 and (~inside).sum() > 0                      # both clipped and unclipped corners are exercised
+
+
+# ======================================================================================= mask targets / detection layer (8 f3, f4)
+@pytest.fixture(scope="module")
+def T(golden_dir):
+    return np.load(golden_dir + "/targets.npz")
+
+
+def _det_cfg(min_conf):
+    cfg = pyref.make_config(DATA__IMAGE_SHAPE=np.array([832, 1344, 3]))
+    cfg.TEST = types.SimpleNamespace(DET_MAX_INSTANCES=100, DET_MIN_CONFIDENCE=min_conf, DET_NMS_THRESHOLD=0.3)
+    cfg.DATA.BBOX_STD_DEV = np.array([0.1, 0.1, 0.2, 0.2])
+    return cfg
+
+
+def _same_detections(got, want):
+    """Rows agree; scores that tie may come in either order (the reference's sort is unstable)."""
+    assert got.shape == want.shape
+    n_got, n_want = (got[:, :, 5] > 0).sum(1), (want[:, :, 5] > 0).sum(1)
+    np.testing.assert_array_equal(n_got, n_want)
+    for b in range(got.shape[0]):
+        g = got[b][np.lexsort((got[b][:, 0], got[b][:, 1], -got[b][:, 5]))]
+        w = want[b][np.lexsort((want[b][:, 0], want[b][:, 1], -want[b][:, 5]))]
+        np.testing.assert_allclose(g[:, :5], w[:, :5], rtol=0, atol=0)
+        np.testing.assert_allclose(g[:, 5], w[:, 5], rtol=1e-6, atol=0)
+
+
+def test_targets_fixture_names_the_reference_code(T):
+    cited = set(T["cited"].tolist())
+    for need in ("mask_targets=lib/layers.py:297-323", "conduct_nms=lib/layers.py:664-717", "detection_layer=lib/layers.py:720-802"):
+        assert need in cited, need
+
+
+def test_mask_targets_oracle_vs_reference(T):
+    for tag, mini in (("mask_mini", True), ("mask_full", False)):
+        got = pyref.mask_targets_ref(torch.from_numpy(T[tag + "_pos_rois"]), torch.from_numpy(T[tag + "_gt_boxes"]), torch.from_numpy(T[tag + "_assign"]),
+                                     torch.from_numpy(T[tag + "_gt_masks"]), (28, 28), mini)
+        np.testing.assert_array_equal(got.numpy(), T[tag + "_targets"])
+        assert 0.05 < T[tag + "_targets"].mean() < 0.95 and set(np.unique(T[tag + "_targets"])) == {0.0, 1.0}
+
+
+def test_detection_layer_oracle_vs_reference(T):
+    for key, conf in (("det_out", 0.3), ("det_out_conf093", 0.93)):
+        got = pyref.detection_layer_ref(torch.from_numpy(T["det_rois"]), torch.from_numpy(T["det_probs"]), torch.from_numpy(T["det_deltas"]),
+                                        torch.from_numpy(T["det_windows"]), _det_cfg(conf))
+        _same_detections(got.numpy(), T[key])
+    assert (T["det_out_conf093"][:, :, 5] > 0).sum(1).max() < 100 and (T["det_out"][:, :, 5] > 0).sum(1).min() == 100
+
+
+@pytest.mark.gpu
+def test_mask_targets_cuda_vs_reference(T):
+    import feature_intertwiner_b200 as fi
+    for tag, mini in (("mask_mini", True), ("mask_full", False)):
+        got = fi.mask_targets(torch.from_numpy(T[tag + "_pos_rois"]).cuda(), torch.from_numpy(T[tag + "_gt_boxes"]).cuda(),
+                              torch.from_numpy(T[tag + "_assign"]).cuda(), torch.from_numpy(T[tag + "_gt_masks"]).cuda(), (28, 28), mini)
+        np.testing.assert_array_equal(got.cpu().numpy(), T[tag + "_targets"])
+        # and the operator the reference itself calls (CropAndResizeFunction with C = 1, one image per box) gives the same targets
+        a = torch.from_numpy(T[tag + "_assign"]).long()
+        boxes = torch.from_numpy(T[tag + "_pos_rois"])
+        if mini:
+            gb = torch.from_numpy(T[tag + "_gt_boxes"])[a]
+            gh, gw = gb[:, 2:3] - gb[:, 0:1], gb[:, 3:4] - gb[:, 1:2]
+            boxes = torch.cat([(boxes[:, 0:1] - gb[:, 0:1]) / gh, (boxes[:, 1:2] - gb[:, 1:2]) / gw, (boxes[:, 2:3] - gb[:, 0:1]) / gh,
+                               (boxes[:, 3:4] - gb[:, 1:2]) / gw], 1)
+        crops = fi.CropAndResizeFunction(28, 28)(torch.from_numpy(T[tag + "_gt_masks"])[a].unsqueeze(1).cuda(), boxes.cuda(),
+                                                 torch.arange(a.numel(), dtype=torch.int32).cuda())
+        np.testing.assert_array_equal(torch.round(crops.squeeze(1)).cpu().numpy(), T[tag + "_targets"])
+
+
+@pytest.mark.gpu
+def test_detection_layer_cuda_vs_reference(T):
+    import feature_intertwiner_b200 as fi
+    for key, conf in (("det_out", 0.3), ("det_out_conf093", 0.93)):
+        feat = torch.arange(600, dtype=torch.float32).view(600, 1).cuda()
+        got, gfeat = fi.detection_layer(torch.from_numpy(T["det_rois"]).cuda(), torch.from_numpy(T["det_probs"]).cuda(),
+                                        torch.from_numpy(T["det_deltas"]).cuda(), torch.from_numpy(T["det_windows"]).cuda(), _det_cfg(conf), feature=feat)
+        got = got.cpu().numpy()
+        # expf on the device may differ from the host's in the last place; after rounding to pixels the boxes agree except on exact .5 ties
+        want = T[key]
+        n_got, n_want = (got[:, :, 5] > 0).sum(1), (want[:, :, 5] > 0).sum(1)
+        np.testing.assert_array_equal(n_got, n_want)
+        for b in range(2):
+            g = got[b][np.lexsort((got[b][:, 0], got[b][:, 1], -got[b][:, 5]))]
+            w = want[b][np.lexsort((want[b][:, 0], want[b][:, 1], -want[b][:, 5]))]
+            np.testing.assert_allclose(g[:, 5], w[:, 5], rtol=1e-6)
+            np.testing.assert_array_equal(g[:, 4], w[:, 4])
+            assert np.abs(g[:, :4] - w[:, :4]).max() <= 1.0 and (g[:, :4] != w[:, :4]).mean() < 0.01
+        # the gathered feature rows name the RoI every detection came from
+        src = gfeat.cpu().numpy()[:, :, 0].astype(np.int64)
+        probs = T["det_probs"]
+        for b in range(2):
+            k = int(n_got[b])
+            np.testing.assert_allclose(probs[src[b, :k]].max(1), got[b, :k, 5], rtol=1e-6)
