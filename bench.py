@@ -311,9 +311,10 @@ class Step(object):
             p.grad = None
         return loss
 
-    def run(self, inp=None):
+    # ---- the step in three parts (one process: run() chains them; several: the two all-reduces sit between them) ----------
+    def forward_part(self, inp):
+        """[proposal layer] -> level rule + split -> every crop -> class means -> this rank's packed un-normalised statistics."""
         fi, cfg = self.fi, self.cfg
-        inp = self.resident if inp is None else inp
         B, R = self.wl["batch"], self.wl["rois_per_image"]
         total = B * R
         gt = inp["gt"]
@@ -359,15 +360,26 @@ class Step(object):
         pooled_out, mask_out = res_out[where[("small", 3)]], res_out[where[("small", 3)] + 1]
         feat_in = [torch.stack(bfeat)[None].detach(), torch.stack(bcnt)[None], torch.stack(sfeat)[None], torch.stack(scnt)[None], None, None]
         self.last_feat_in = [t.detach() for t in feat_in[:4]]          # for the loss-head-only timing
-        loss = self.loss_mod(feat_in).sum()
-        torch.autograd.backward([loss, pooled_out, mask_out] + outs, [torch.ones_like(loss), inp["g_pooled"], inp["g_mask"]] + grads)
+        self.last_split = split
+        return dict(feat_in=feat_in, heads=[pooled_out, mask_out] + outs, head_grads=[inp["g_pooled"], inp["g_mask"]] + grads,
+                    leaves=raw + madeup + small_f)
+
+    def run(self, inp=None):
+        """One process: the whole step through the public API, autograd end to end."""
+        inp = self.resident if inp is None else inp
+        st = self.forward_part(inp)
+        loss = self.loss_mod(st["feat_in"]).sum()
+        torch.autograd.backward([loss] + st["heads"], [torch.ones_like(loss)] + st["head_grads"])
         if self.world > 1:
             # gradient all-reduce of the path's own parameters (OptTrans, 15.7 MB): started by a hook as soon as the loss head's
             # backward has produced them, i.e. overlapped with the RoIAlign backward that follows it on the compute stream
-            self.grad_bucket.finish()
+            if self.grad_bucket is not None:
+                self.grad_bucket.finish()
+            else:
+                import torch.distributed as dist
+                dist.all_reduce(torch.cat([p.grad.reshape(-1) for p in self.ot.parameters()]))
         for p in self.ot.parameters():
             p.grad = None
-        self.last_split = split
         return loss
 
     def capture(self):
@@ -394,10 +406,99 @@ class Step(object):
             torch.cuda.synchronize(self.dev)
         return self.graph is not None
 
+    # ---- several processes: three graphs, the two all-reduces eager between them (no collective inside a capture) ---------
+    def _packed_local(self, st):
+        from feature_intertwiner_b200.dist import merged_class_sums_pair
+        bs, bn, ss, sn = merged_class_sums_pair(st["feat_in"][0], st["feat_in"][1], st["feat_in"][2], st["feat_in"][3], None, False)
+        return torch.cat([bs.reshape(-1), bn, ss.reshape(-1), sn])
+
+    def _head_from_packed(self, packed):
+        a, b = FEAT * NCLS, NCLS
+        big_sum, big_n = packed[:a].view(FEAT, NCLS).detach(), packed[a:a + b].detach()
+        s_sum, s_n = packed[a + b:2 * a + b].view(FEAT, NCLS), packed[2 * a + b:].detach()
+        return self.loss_mod._head(big_sum, big_n, s_sum, s_n, None, None).sum()
+
+    def capture_segmented(self):
+        """Graph A: forward part -> packed local statistics.  [all-reduce]  Graph B: loss head forward + backward -> gradient of
+        the packed statistics, OptTrans parameter gradients (flat).  [async all-reduce of those, overlapping graph C]  Graph C:
+        backward of the forward part (class-mean backward, RoIAlign backward of every crop)."""
+        import torch.distributed as dist
+        lib = self.fi.lib()
+        ok = True
+        try:
+            if self.grad_bucket is not None:
+                self.grad_bucket.remove()
+                self.grad_bucket = None
+            params = [p for p in self.ot.parameters()]
+            s = torch.cuda.Stream(device=self.dev)
+            s.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(s):
+                for _ in range(3):                                  # warm-up of every op on a side stream (allocator, lazy init)
+                    st = self.forward_part(self.resident)
+                    packed = self._packed_local(st)
+                    pin_ = packed.detach().clone().requires_grad_()
+                    loss = self._head_from_packed(pin_)
+                    gs = torch.autograd.grad(loss, [pin_] + params)
+                    torch.autograd.grad([packed] + st["heads"], st["leaves"], [gs[0]] + st["head_grads"], allow_unused=True)
+            torch.cuda.current_stream(self.dev).wait_stream(s)
+            torch.cuda.synchronize(self.dev)
+            n0 = lib.fi_kernel_launches()
+            pool = torch.cuda.graph_pool_handle()
+            gA, gB, gC = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gA, pool=pool):
+                st = self.forward_part(self.resident)
+                node = st["heads"][0].grad_fn                       # the crop_sets node: join its side-stream list building HERE
+                if getattr(node, "bwd", None) is not None and node.bwd.event is not None:
+                    torch.cuda.current_stream(self.dev).wait_event(node.bwd.event)
+                    node.bwd.event = None
+                packed = self._packed_local(st)
+                self.seg_packed = packed.detach().clone()           # all-reduced in place between the graphs
+            self.seg_in = self.seg_packed.clone().requires_grad_()
+            with torch.cuda.graph(gB, pool=pool):
+                self.seg_in.data.copy_(self.seg_packed)
+                loss = self._head_from_packed(self.seg_in)
+                gs = torch.autograd.grad(loss, [self.seg_in] + params)
+                self.graph_loss = loss.detach()
+                self.seg_gpacked = gs[0] * float(self.world)        # DataParallel sums replica gradients (dist.py::_AllReduceSum)
+                self.seg_flat = torch.cat([g_.reshape(-1) for g_ in gs[1:]])
+            with torch.cuda.graph(gC, pool=pool):
+                self.seg_grads = torch.autograd.grad([packed] + st["heads"], st["leaves"], [self.seg_gpacked] + st["head_grads"], allow_unused=True)
+            self.launches_per_step = int(lib.fi_kernel_launches() - n0)
+            self.seg = (gA, gB, gC)
+            self._seg_state = st                                     # keeps the autograd graph of A alive
+        except Exception as exc:            # noqa: BLE001
+            ok = False
+            self.graph_error = repr(exc)[:300]
+        torch.cuda.synchronize(self.dev)
+        flag = torch.tensor([1 if ok else 0], device=self.dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)                 # every rank or none: the collectives must stay matched
+        if int(flag.item()) == 0:
+            self.seg = None
+            if self.grad_bucket is None:
+                from feature_intertwiner_b200.dist import GradAllReduce
+                self.grad_bucket = GradAllReduce(self.ot.parameters())
+            return False
+        self.step_segmented()
+        torch.cuda.synchronize(self.dev)
+        return True
+
+    def step_segmented(self):
+        import torch.distributed as dist
+        gA, gB, gC = self.seg
+        gA.replay()
+        dist.all_reduce(self.seg_packed)                            # class statistics of both sets, one collective (1.3 MB)
+        gB.replay()
+        work = dist.all_reduce(self.seg_flat, async_op=True)        # OptTrans gradients (15.7 MB): overlaps graph C
+        gC.replay()
+        work.wait()
+        return self.graph_loss
+
     def step(self):
         if self.graph is not None:
             self.graph.replay()
             return self.graph_loss
+        if getattr(self, "seg", None) is not None:
+            return self.step_segmented()
         return self.run()
 
 
@@ -503,7 +604,7 @@ def measure_workload(name, wl, dev, rank, world, args, lib, flush, full):
     import feature_intertwiner_b200 as fi
     timer = Timer(dev, world, lib, flush)
     step = Step(wl, dev, world, seed=2000 + rank)
-    graphed = args.mode == "graph" and step.capture()
+    graphed = args.mode == "graph" and (step.capture() if world == 1 else step.capture_segmented())
     ms = timer(step.step, args.steps if full else max(3, args.steps // 2), args.warmup)
     res = {"ms_per_step": ms, "value": wl["batch"] * wl["rois_per_image"] * world / (ms / 1e3), "graphed": graphed,
            "host_enqueue_ms_per_step": 1e3 * timer.host_s / (args.steps if full else max(3, args.steps // 2)),
@@ -632,7 +733,9 @@ def run_ours(args):
         "config": {"workload": workload_name(args.workload, wl),
                    "layout": "channels_last maps/crops (logical NCHW)", "ot": "all 80 foreground classes, absent ones masked (fixed shapes, no host sync)",
                    "roi_order": "spatially sorted per image (L2 reuse)" if os.environ.get("FI_SPATIAL_SORT", "1") != "0" else "index order",
-                   "step": ("ONE CUDA graph replay per step (whole step: split, crops, list building on a side stream, class means, loss head, backward)"
+                   "step": (("ONE CUDA graph replay per step (whole step: split, crops, list building on a side stream, class means, loss head, backward)"
+                             if world == 1 else "three CUDA graph replays per step (forward part | loss head fwd+bwd | backward part) with the two NCCL "
+                             "all-reduces (class statistics; OptTrans gradients, overlapped with the backward graph) eager between them")
                             if res["graphed"] else "eager, launch by launch" + (" (graph capture failed: %s)" % res["graph_error"] if res["graph_error"] else "")),
                    "list_lengths": "kept on the device (fixed-capacity lists): the step has no device->host read",
                    "critic_and_makeup_convs": "excluded (stock cuDNN; SURVEY.md 8 a5) -- see --with-critic for the inclusive variant",

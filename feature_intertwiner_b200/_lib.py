@@ -50,6 +50,8 @@ SIGNATURES = {
     "fi_segment_mean_forward_n": (_I, [_P, _P, _I, _P, _I, _I, _P, _P, _P]),
     "fi_segment_mean_backward_n": (_I, [_P, _P, _P, _I, _P, _I, _I, _P, _P]),
     "fi_sinkhorn": (_I, [_P, _P, _I, _I, _I, _F, _I, _P, _P, _P, _P]),
+    "fi_sinkhorn_workspace": (C.c_size_t, [_I, _I, _I, _I]),
+    "fi_sinkhorn_ws": (_I, [_P, _P, _I, _I, _I, _F, _I, _P, _P, _P, _P, C.c_size_t, _P]),
     "fi_buffer_update": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "fi_nms_batched": (_I, [_P, _I, _I, _F, _P, _P, _P, _P]),
     "fi_proposal_decode": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _F, _F, _P, _P, _P]),

@@ -41,6 +41,8 @@ struct SinkParams {
     int TPC;                   // threads cooperating on one column in the b-update
     int keepC;                 // C kept in shared memory next to K (else recomputed for the loss)
     int masked;                // only problems whose loss slot holds NaN are solved (the others were done by the D = 1 class kernel)
+    float *pbuf;               // null, or [P, N*N + 2N]: the plan P and the row norms go here and the gradient is left to
+                               // sinkhorn_grad_raw_kernel / sinkhorn_grad_chain_kernel (large D: one CTA per problem cannot feed it)
 };
 
 __host__ __device__ inline int round4(int v) { return (v + 3) & ~3; }
@@ -268,7 +270,12 @@ __global__ void __launch_bounds__(kSinkThreads) sinkhorn_kernel(const SinkParams
     // ---- phase 4: gradients with P constant ----------------------------------------------------------
     //   dL/dx^_i = -sum_j P_ij y^_j ,  dL/dy^_j = -sum_i P_ij x^_i ,
     //   x^ = x / (|x| + EPS)  =>  dL/dx = (g - x^ <x^,g> |x|/(|x|+EPS)) / (|x|+EPS)
-    if (p.gx != nullptr) {
+    if (p.gx != nullptr && p.pbuf != nullptr) {              // CS == 1 here (host): the whole plan is in this CTA's shared memory
+        __syncthreads();
+        float *w = p.pbuf + (long)prob * ((long)N * N + 2 * N);
+        for (int e = t; e < N * N; e += kSinkThreads) w[e] = Ks[(e / N) * pitch + (e % N)];
+        for (int e = t; e < N; e += kSinkThreads) { w[N * N + e] = denx[e]; w[N * N + N + e] = deny[e]; }
+    } else if (p.gx != nullptr) {
         float *gxp = p.gx + (long)prob * N * D, *gyp = p.gy + (long)prob * N * D;
         for (long e = t; e < (long)nrows * D; e += kSinkThreads) {
             const int il = (int)(e / D), d = (int)(e - (long)il * D);
@@ -304,6 +311,90 @@ __global__ void __launch_bounds__(kSinkThreads) sinkhorn_kernel(const SinkParams
         }
     }
     if (CS > 1) cluster.sync();   // no CTA may exit while a peer can still read its shared memory
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gradient for large D (the FPN-level loss: N = 64, D = (s/4)^2 up to 4096, lib/sub_module.py:179-213).  Inside the solver
+// kernel one CTA per problem walks N*D outputs with an N-term sum each -- 24 CTAs on 148 SMs, 28 ms for 24 problems at
+// D = 4096.  The plan P (N x N) is tiny, so it is handed over through global memory and the two products
+//     g~x = -P y^   [N x D],      g~y = -P^T x^   [N x D]
+// are spread over (problem, 64-column chunk of D) CTAs: P in shared memory (broadcast reads, float4 along the summed index),
+// thread = (column d, quarter of the rows), the same ascending summation order as the in-kernel form (identical bits).
+// A second launch (warp per row) applies the chain through the row normalisation, which needs the full-row dot product.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sinkhorn_grad_raw_kernel(const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ pbuf,
+                                                               float *__restrict__ gx, float *__restrict__ gy, int N, int D) {
+    extern __shared__ __align__(16) float sm[];
+    float *Ps = sm, *denx = sm + N * N, *deny = denx + N;
+    const int prob = blockIdx.x, t = threadIdx.x;
+    const float *w = pbuf + (long)prob * ((long)N * N + 2 * N);
+    for (int e = t; e < N * N + 2 * N; e += 256) sm[e] = w[e];
+    __syncthreads();
+    const int d = blockIdx.y * 64 + (t & 63);
+    const int q = t >> 6;                                   // quarter of the rows (gx) / columns (gy): 4 * ceil(N / 16) each
+    const int per = ((N + 15) / 16) * 4, r0 = q * per;
+    if (d >= D) return;
+    const float *xp = x + (long)prob * N * D + d, *yp = y + (long)prob * N * D + d;
+    float *gxp = gx + (long)prob * N * D + d, *gyp = gy + (long)prob * N * D + d;
+    float acc[32];
+    // g~x[i][d] = -sum_j P[i][j] y^[j][d]
+#pragma unroll
+    for (int r = 0; r < 32; ++r) acc[r] = 0.f;
+    for (int j = 0; j < N; j += 4) {
+        float yv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) yv[u] = __fdiv_rn(__ldg(yp + (long)(j + u) * D), deny[j + u]);
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            if (r < per && r0 + r < N) {
+                const float4 pv = *reinterpret_cast<const float4 *>(Ps + (r0 + r) * N + j);
+                acc[r] = fmaf(pv.x, yv[0], acc[r]); acc[r] = fmaf(pv.y, yv[1], acc[r]);
+                acc[r] = fmaf(pv.z, yv[2], acc[r]); acc[r] = fmaf(pv.w, yv[3], acc[r]);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 32; ++r)
+        if (r < per && r0 + r < N) gxp[(long)(r0 + r) * D] = -acc[r];
+    // g~y[j][d] = -sum_i P[i][j] x^[i][d]
+#pragma unroll
+    for (int r = 0; r < 32; ++r) acc[r] = 0.f;
+    for (int i = 0; i < N; ++i) {
+        const float xv = __fdiv_rn(__ldg(xp + (long)i * D), denx[i]);
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+            if (4 * c4 < per && r0 + 4 * c4 < N) {
+                const float4 pv = *reinterpret_cast<const float4 *>(Ps + i * N + r0 + 4 * c4);
+                acc[4 * c4 + 0] = fmaf(pv.x, xv, acc[4 * c4 + 0]); acc[4 * c4 + 1] = fmaf(pv.y, xv, acc[4 * c4 + 1]);
+                acc[4 * c4 + 2] = fmaf(pv.z, xv, acc[4 * c4 + 2]); acc[4 * c4 + 3] = fmaf(pv.w, xv, acc[4 * c4 + 3]);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 32; ++r)
+        if (r < per && r0 + r < N) gyp[(long)(r0 + r) * D] = -acc[r];
+}
+
+// warp per row (x rows then y rows of every problem): dL/dx = (g - x^ <x^, g> |x| / (|x| + EPS)) / (|x| + EPS)
+__global__ void __launch_bounds__(256) sinkhorn_grad_chain_kernel(const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ pbuf,
+                                                                 float *__restrict__ gx, float *__restrict__ gy, int P, int N, int D) {
+    const int lane = threadIdx.x & 31;
+    const long row = blockIdx.x * 8L + (threadIdx.x >> 5);
+    if (row >= 2L * P * N) return;
+    const int prob = (int)(row / (2 * N)), q = (int)(row - (long)prob * 2 * N);
+    const bool isx = q < N;
+    const int i = isx ? q : q - N;
+    const float *src = (isx ? x : y) + ((long)prob * N + i) * D;
+    float *g = (isx ? gx : gy) + ((long)prob * N + i) * D;
+    const float den = pbuf[(long)prob * ((long)N * N + 2 * N) + (long)N * N + (isx ? 0 : N) + i];
+    float dot = 0.f;
+    for (int d = lane; d < D; d += 32) dot = fmaf(g[d], __fdiv_rn(__ldg(src + d), den), dot);
+    dot = warp_sum(dot);
+    const float shrink = __fdiv_rn(__fsub_rn(den, kEps), den);   // |x| / (|x| + EPS)
+    for (int d = lane; d < D; d += 32) {
+        const float xh = __fdiv_rn(__ldg(src + d), den);
+        g[d] = __fdiv_rn(__fsub_rn(g[d], __fmul_rn(__fmul_rn(xh, dot), shrink)), den);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -641,8 +732,20 @@ static bool plan(int N, int CS, int keepC, SinkParams &p, size_t &bytes) {
 
 using namespace fi;
 
+// Scratch floats the split gradient needs (0: the gradient stays inside the solver kernel).  Large D only: the plan of every
+// problem (N x N) and its row norms.
+FI_API size_t fi_sinkhorn_workspace(int n_problems, int N, int D, int want_grad) {
+    if (!want_grad || n_problems <= 0 || D < 128 || N < 4 || N > 128 || (N % 4) != 0) return 0;
+    return (size_t)n_problems * ((size_t)N * N + 2 * (size_t)N) * sizeof(float);
+}
+
 FI_API int fi_sinkhorn(const float *x, const float *y, int n_problems, int N, int D, float inv_eps, int L, float *loss,
                        float *grad_x, float *grad_y, cudaStream_t stream) {
+    return fi_sinkhorn_ws(x, y, n_problems, N, D, inv_eps, L, loss, grad_x, grad_y, nullptr, 0, stream);
+}
+
+FI_API int fi_sinkhorn_ws(const float *x, const float *y, int n_problems, int N, int D, float inv_eps, int L, float *loss,
+                          float *grad_x, float *grad_y, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
     FI_REQUIRE(n_problems >= 0 && N >= 1 && N <= 256 && D >= 1 && L >= 1, "fi_sinkhorn: need N in [1,256], D >= 1, L >= 1 (N=%d D=%d L=%d)", N, D, L);
     if (n_problems == 0) return ok();
     FI_REQUIRE(x && y && loss, "fi_sinkhorn: null pointer");
@@ -686,6 +789,10 @@ FI_API int fi_sinkhorn(const float *x, const float *y, int n_problems, int N, in
         }
     }
     p.masked = masked;
+    p.pbuf = nullptr;
+    const size_t need_ws = fi_sinkhorn_workspace(n_problems, N, D, grad_x != nullptr);
+    if (CS == 1 && need_ws > 0 && workspace != nullptr && workspace_bytes >= need_ws && ((uintptr_t)workspace % 16) == 0)
+        p.pbuf = static_cast<float *>(workspace);
     cudaError_t e;
     if (CS > 1 && !masked) {
         e = cudaMemsetAsync(loss, 0, sizeof(float) * n_problems, stream);
@@ -706,5 +813,16 @@ FI_API int fi_sinkhorn(const float *x, const float *y, int n_problems, int N, in
     cfg.attrs = attr; cfg.numAttrs = 1;
     e = cudaLaunchKernelEx(&cfg, kern, p);
     if (e != cudaSuccess) { set_error(FI_ERR_CUDA, "fi_sinkhorn: launch: %s", cudaGetErrorString(e)); return FI_ERR_CUDA; }
-    return check_launch("fi_sinkhorn");
+    if (int rc = check_launch("fi_sinkhorn")) return rc;
+    if (p.pbuf != nullptr) {                                 // large D: the gradient as two more launches over (problem, D chunk) / rows
+        const size_t sm = ((size_t)N * N + 2 * (size_t)N) * sizeof(float);
+        e = cudaFuncSetAttribute(sinkhorn_grad_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) { set_error(FI_ERR_CUDA, "fi_sinkhorn: smem attr (%zu B): %s", sm, cudaGetErrorString(e)); return FI_ERR_CUDA; }
+        sinkhorn_grad_raw_kernel<<<dim3((unsigned)n_problems, (unsigned)ceil_div(D, 64)), 256, sm, stream>>>(x, y, p.pbuf, grad_x, grad_y, N, D);
+        if (int rc = check_launch("fi_sinkhorn[gradient]")) return rc;
+        const long rows = 2L * n_problems * N;
+        sinkhorn_grad_chain_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(x, y, p.pbuf, grad_x, grad_y, n_problems, N, D);
+        return check_launch("fi_sinkhorn[gradient chain]");
+    }
+    return ok();
 }

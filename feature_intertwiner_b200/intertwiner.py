@@ -648,8 +648,14 @@ class IntertwinerLoss(nn.Module):
         diff = SMALL_all - BIG_all
         per = diff * diff if lc == 'l2' else diff.abs()
         m = mask.to(per.dtype).unsqueeze(1)
-        denom = (m.sum() * per.size(1)).clamp(min=1.0)
-        return (per * m).sum() / denom
+        err, cnt = (per * m).sum(), m.sum() * per.size(1)
+        if cfg.DEV.INST_LOSS and self.distributed:
+            # instance level under sharding: every rank scores its own rows of small_output_all against the
+            # replicated buffer; (sum of errors, element count) are all-reduced so that every rank holds the mean over ALL instances
+            from .dist import _AllReduceSum
+            pair = _AllReduceSum.apply(torch.stack([err, cnt.to(err.dtype)]), self.process_group, self.ddp_compensate)
+            err, cnt = pair[0], pair[1].detach()
+        return err / cnt.clamp(min=1.0)
 
 
 class _LossHead(nn.Module):

@@ -24,9 +24,12 @@ class _Sinkhorn(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad[:2])
         gx = torch.empty_like(x) if need_grad else None
         gy = torch.empty_like(y) if need_grad else None
+        L_ = _lib.lib()
+        nbytes = L_.fi_sinkhorn_workspace(P, N, D, 1 if need_grad else 0)          # large D: the gradient runs as its own launches
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=x.device) if nbytes else None
         with torch.cuda.device(x.device):
-            _lib.check(_lib.lib().fi_sinkhorn(_lib.ptr(x), _lib.ptr(y), P, N, D, float(inv_eps), int(L), _lib.ptr(loss),
-                                              _lib.ptr(gx), _lib.ptr(gy), _lib.stream_ptr(x.device)))
+            _lib.check(L_.fi_sinkhorn_ws(_lib.ptr(x), _lib.ptr(y), P, N, D, float(inv_eps), int(L), _lib.ptr(loss),
+                                         _lib.ptr(gx), _lib.ptr(gy), _lib.ptr(ws), nbytes, _lib.stream_ptr(x.device)))
         if need_grad:
             ctx.save_for_backward(gx, gy)
         return loss

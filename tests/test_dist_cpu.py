@@ -68,6 +68,21 @@ def _worker(rank, world, port, out):
     want_w = sum(2.0 * (r + 1) for r in range(world))
     ok = ok and torch.allclose(lin.weight.grad, torch.full((3, 4), want_w)) and torch.allclose(lin.bias.grad, torch.full((3,), 2.0 * world))
     bucket.remove()
+    # instance-level loss under sharding: all-reduced (sum of errors, count) == the loss over the concatenated instances
+    from feature_intertwiner_b200.dist import _AllReduceSum
+    inst = torch.rand(world, 5 + 3, Fd, generator=g)
+    tgt = torch.rand(world, 5 + 3, Fd, generator=g)
+    msk = (torch.rand(world, 5 + 3, generator=g) < 0.6).float()
+    mine_i = inst[rank].clone().requires_grad_()
+    per = (mine_i - tgt[rank]) ** 2 * msk[rank].unsqueeze(1)
+    pair = _AllReduceSum.apply(torch.stack([per.sum(), msk[rank].sum() * Fd]), None, True)
+    loss_sh = pair[0] / pair[1].detach().clamp(min=1.0)
+    loss_sh.backward()
+    full_i = inst.clone().requires_grad_()
+    per_f = (full_i - tgt) ** 2 * msk.unsqueeze(2)
+    loss_full = per_f.sum() / (msk.sum() * Fd).clamp(min=1.0)
+    loss_full.backward()
+    ok = ok and torch.allclose(loss_sh, loss_full, rtol=1e-6) and torch.allclose(mine_i.grad / world, full_i.grad[rank], rtol=1e-5, atol=1e-9)
     out[rank] = bool(ok)
     dist.destroy_process_group()
 

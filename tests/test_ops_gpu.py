@@ -95,6 +95,32 @@ def test_sinkhorn_d1_class_kernel_vs_dense_kernels_and_oracle(N):
         torch.testing.assert_close(res[0][k], res[1][k], rtol=1e-4, atol=1e-7)
 
 
+def test_sinkhorn_split_gradient_identical_to_in_kernel_gradient():
+    """Large D (FPN-level loss shapes): the gradient as its own (problem, D chunk) launches on a workspace == the gradient computed
+    inside the solver kernel (fi_sinkhorn without workspace), bit for bit -- same products, same ascending summation order."""
+    from feature_intertwiner_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(9)
+    s = torch.cuda.current_stream().cuda_stream
+    for (P, N, D) in ((6, 64, 256), (3, 64, 1500), (2, 128, 128), (4, 100, 300)):
+        x = torch.randn(P, N, D, generator=g).abs().cuda()
+        y = torch.randn(P, N, D, generator=g).abs().cuda()
+        x[:, 3] = 0
+        res = []
+        for use_ws in (False, True):
+            loss = torch.empty(P, device="cuda")
+            gx, gy = torch.full_like(x, 7.0), torch.full_like(y, 7.0)
+            nbytes = L.fi_sinkhorn_workspace(P, N, D, 1) if use_ws else 0
+            assert (not use_ws) or nbytes == P * (N * N + 2 * N) * 4
+            ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device="cuda")
+            _lib.check(L.fi_sinkhorn_ws(x.data_ptr(), y.data_ptr(), P, N, D, 2.0, 5, loss.data_ptr(), gx.data_ptr(), gy.data_ptr(),
+                                        ws.data_ptr() if use_ws else None, nbytes, s))
+            res.append((loss, gx, gy))
+        for a, b in zip(res[0], res[1]):
+            assert torch.equal(a, b)
+    assert L.fi_sinkhorn_workspace(240, 256, 1, 1) == 0 and L.fi_sinkhorn_workspace(24, 64, 4096, 0) == 0
+
+
 def test_sinkhorn_properties_full_size():
     """Size-independent properties at BASELINE sizes: x == y => debiased loss 0; batch order invariance."""
     fi = _fi()

@@ -663,10 +663,16 @@ def test_reference_named_backward_launcher_c256_accumulates_and_matches_referenc
         L.CropAndResizeBackpropImageLaucher(grads.cuda().data_ptr(), b.data_ptr(), bi.data_ptr(), 300, 3, 52, 84, P, P, 256, gi.data_ptr(), s)
         assert L.fi_last_status() == 0, L.fi_last_error()
         want = clib.oracle_crop_and_resize_bwd(grads.numpy(), rois.numpy(), box_ind.numpy(), (3, 256, 52, 84))
-        np.testing.assert_allclose(gi.cpu().numpy(), base.numpy() + want, rtol=1e-5, atol=2e-5)
+        # summation-order bound on the scatter sum + one rounding of (base + sum)
+        mag = clib.oracle_crop_and_resize_bwd(np.abs(grads.numpy()), rois.numpy(), box_ind.numpy(), (3, 256, 52, 84))
+        total = base.numpy() + want
+        bound = 2e-6 * mag + 2e-6 * np.abs(total) + 1e-6
+        assert np.all(np.abs(gi.cpu().numpy() - total) <= bound)
         ref = clib.ref_cuda()
         if ref is not None:
             gr = base.clone().cuda()
             ref.CropAndResizeBackpropImageLaucher(grads.cuda().data_ptr(), b.data_ptr(), bi.data_ptr(), 300, 3, 52, 84, P, P, 256, gr.data_ptr(), s)
             torch.cuda.synchronize()
-            torch.testing.assert_close(gi, gr, rtol=1e-5, atol=2e-5)
+            # the reference kernel adds every term onto (base + partial sum) with atomics, in arrival order: each of its hundreds of
+            # additions rounds at the magnitude of the running value -- a sanity cross-check, the parity bound is the one above
+            torch.testing.assert_close(gi, gr, rtol=1e-4, atol=2e-4)
