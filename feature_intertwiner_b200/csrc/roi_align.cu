@@ -62,11 +62,13 @@ struct FwdSets {
     int n;
 };
 
-template <bool PREFETCH>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) crop_fwd_nhwc_sets_kernel(const FwdSets sets) {
     // unit -> set: prefix of the sets' unit counts.  With list lengths on the device the prefix is formed here from the LIVE
     // lengths: walking the capacity ranges instead leaves the live units of every set as a prefix of its own range, and their
     // round-robin assignment to the (persistent) warps then differs by a unit or two per set -- measured +17 % on C2.
+    // Tried on this kernel in round 2 and not kept (profiles/r02_fwd_variants.json): taps staged by cp.async.bulk into a per-warp
+    // double buffer, lerps from shared memory (bit-identical; 0.96 ms with 7 warps per SM, 1.36 ms with 4: too few warps fit next
+    // to their buffers to cover the loaded DRAM latency) and an L2 prefetch of the warp's next unit (1.00 ms) -- against 0.85 ms.
     __shared__ long first[kMaxFwdSets + 1];
     if (threadIdx.x == 0) {
         long acc = 0;
@@ -86,199 +88,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) crop_fwd_nhwc_sets_kernel
     for (long u = warp; u < total; u += nwarps) {
         int k = 0;
         while (u >= first[k + 1]) ++k;
-        if (PREFETCH && u + nwarps < total) {          // the unit after this one: its taps on their way into L2
-            int k2 = k;
-            while (u + nwarps >= first[k2 + 1]) ++k2;
-            fwd_prefetch_unit(sets.s[k2], u + nwarps - first[k2], lane);
-        }
         fwd_unit<4>(sets.s[k], u - first[k], lane);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// The same level-batched forward with the taps STAGED BY BULK COPIES (cp.async.bulk + mbarrier, SASS UBLKCP / SYNCS).
-//
-// crop_fwd_nhwc_sets_kernel keeps 16 tap loads per lane in flight, then lerps and stores while nothing is in flight: ncu shows
-// it at 77 % of DRAM peak, latency-bound (long-scoreboard 3.5 per issue, 25 % occupancy at 115 registers).  Here every warp is
-// its own producer AND consumer over a double buffer in shared memory: the taps of sub-batch n + 1 (SUB samples of a crop row)
-// are requested before sub-batch n is interpolated, so every warp always has one request outstanding, and the loads cost no
-// registers and no LSU slots.  Dense crops (the "small" sets: sample spacing <= 2 px) fetch the two map-row SEGMENTS their
-// samples span -- 2 copies per sub-batch, each pixel once instead of once per tap; sparse crops (the "big" boxes on finer
-// maps) fetch their (x_lo, x_hi) pixel pairs -- 2 copies per sample.  Interpolation is the same un-fused arithmetic on the
-// same values (bit-exact), 4 LDS.128 per sample.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned fwd_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void fwd_bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(fwd_smem_u32(dst)), "l"(src),
-                 "r"(bytes), "r"(fwd_smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void fwd_mbar_wait(unsigned long long *bar, unsigned parity) {
-    unsigned done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(fwd_smem_u32(bar)), "r"(parity)
-            : "memory");
-    }
-}
-
-template <int SUB, int NCH>
-struct __align__(128) FwdWarpSmem {
-    float buf[2][2][2 * SUB][NCH * 128];           // [buffer][top / bottom map row][pixel slot][all C = NCH * 128 channels]
-    unsigned long long bar[2];
-};
-
-// One sub-batch of a crop row: which unit, which samples, and what the issue step decided (kept in registers, warp-uniform).
-struct FwdCursor {
-    long u;                                        // unit = (set, box, crop row), strided over the warps; the sub-batch starts at sample j0
-    int j0, k, r, i, pw, W, C;
-    bool row_ok, bad;                              // row_ok: image index valid and the y tap inside the map
-    float x1, x2, sx, fy, extrap;
-    const float *rowT, *rowB;
-    float *out, *out2;
-};
-
-template <int SUB, int WARPS, int NCH>
-__global__ void __launch_bounds__(WARPS * 32) crop_fwd_nhwc_sets_tma_kernel(const FwdSets sets) {
-    extern __shared__ __align__(128) unsigned char fwd_smem_raw[];
-    __shared__ long first[kMaxFwdSets + 1];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    FwdWarpSmem<SUB, NCH> &S = reinterpret_cast<FwdWarpSmem<SUB, NCH> *>(fwd_smem_raw)[wib];
-    constexpr unsigned kPx = NCH * 512u;           // bytes of one pixel (all channels are contiguous in NHWC)
-    if (threadIdx.x == 0) {                        // unit -> set prefix from the LIVE list lengths (see crop_fwd_nhwc_sets_kernel)
-        long acc = 0;
-        for (int k = 0; k < sets.n; ++k) {
-            const FwdSet &T = sets.s[k];
-            const int R = T.R_dev ? max(0, min(*T.R_dev, T.R)) : T.R;
-            first[k] = acc;
-            acc += (long)R * T.ph;
-        }
-        first[sets.n] = acc;
-    }
-    if (lane == 0) {
-        for (int q = 0; q < 2; ++q) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fwd_smem_u32(&S.bar[q])), "r"(1) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    __syncthreads();
-    const long total = first[sets.n];
-    const long warp = (long)blockIdx.x * WARPS + wib;
-    const long nwarps = (long)gridDim.x * WARPS;
-
-    auto enter_unit = [&](FwdCursor &c) {          // per-unit quantities (box, y tap, row pointers)
-        int k = 0;
-        while (c.u >= first[k + 1]) ++k;
-        const FwdSet &T = sets.s[k];
-        const long q = c.u - first[k];
-        const int r = (int)(q / T.ph), i = (int)(q - (long)r * T.ph);
-        c.k = k; c.r = r; c.i = i; c.pw = T.pw; c.W = T.W; c.C = T.C; c.extrap = T.extrap; c.j0 = 0;
-        const int b = T.box_ind[r];
-        const long orow = T.dst_row ? (long)T.dst_row[r] : (long)r;
-        c.out = T.crops + ((orow * T.ph + i) * (long)T.pw) * T.C;
-        c.out2 = T.crops2 ? T.crops2 + (((long)r * T.ph + i) * (long)T.pw) * T.C : nullptr;
-        c.bad = (b < 0 || b >= T.B);
-        const float y1 = T.boxes[4 * r + 0], y2 = T.boxes[4 * r + 2];
-        c.x1 = T.boxes[4 * r + 1]; c.x2 = T.boxes[4 * r + 3];
-        const AxisTap ty = axis_sample(y1, y2, axis_step(y1, y2, T.H, T.ph), i, T.H, T.ph);
-        c.row_ok = !c.bad && ty.inside;
-        c.fy = ty.frac;
-        c.sx = axis_step(c.x1, c.x2, T.W, T.pw);
-        const int bl = c.bad ? 0 : b, ylo = c.row_ok ? ty.lo : 0, yhi = c.row_ok ? ty.hi : 0;
-        c.rowT = T.image + ((long)bl * T.H + ylo) * (long)T.W * T.C;
-        c.rowB = T.image + ((long)bl * T.H + yhi) * (long)T.W * T.C;
-    };
-    auto advance = [&](FwdCursor &c) -> bool {     // next sub-batch of this warp's sequence
-        c.j0 += SUB;
-        if (c.j0 < c.pw) return true;
-        c.u += nwarps;
-        if (c.u >= total) return false;
-        enter_unit(c);
-        return true;
-    };
-    // issue the taps of cursor c into buffer q; returns (mode | xmin << 2): mode 0 = nothing requested, 1 = dense, 2 = sparse
-    auto issue = [&](const FwdCursor &c, int q) -> int {
-        const int n = min(SUB, c.pw - c.j0);
-        const AxisTap t = axis_sample(c.x1, c.x2, c.sx, c.j0 + lane, c.W, c.pw);
-        const bool in = c.row_ok && lane < n && t.inside;
-        const unsigned in_mask = __ballot_sync(0xffffffffu, in);
-        if (in_mask == 0) return 0;
-        const int xmin = __reduce_min_sync(0xffffffffu, in ? t.lo : 0x7fffffff);
-        const int xmax = __reduce_max_sync(0xffffffffu, in ? t.hi : -1);
-        const int span = xmax - xmin + 1;
-        __syncwarp();
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // this warp's earlier reads of the buffer are done
-        if (span <= 2 * SUB) {                                              // dense: the two row segments
-            const unsigned bytes = (unsigned)span * kPx;
-            if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fwd_smem_u32(&S.bar[q])), "r"(2u * bytes) : "memory");
-            __syncwarp();
-            if (lane < 2) fwd_bulk_g2s(&S.buf[q][lane][0][0], (lane ? c.rowB : c.rowT) + (long)xmin * c.C, bytes, &S.bar[q]);
-            return 1 | (xmin << 2);
-        }
-        const unsigned two = __ballot_sync(0xffffffffu, in && t.hi != t.lo);
-        const unsigned bytes = (unsigned)(__popc(in_mask) + __popc(two)) * 2u * kPx;
-        if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fwd_smem_u32(&S.bar[q])), "r"(bytes) : "memory");
-        __syncwarp();
-        if (in) {                                                           // sparse: (x_lo, x_hi) pixel pairs of the two rows
-            const unsigned nb = (t.hi != t.lo) ? 2u * kPx : kPx;
-            fwd_bulk_g2s(&S.buf[q][0][2 * lane][0], c.rowT + (long)t.lo * c.C, nb, &S.bar[q]);
-            fwd_bulk_g2s(&S.buf[q][1][2 * lane][0], c.rowB + (long)t.lo * c.C, nb, &S.bar[q]);
-        }
-        return 2;
-    };
-    auto compute = [&](const FwdCursor &c, int q, int st, unsigned parity) {
-        const int n = min(SUB, c.pw - c.j0);
-        const AxisTap mine = axis_sample(c.x1, c.x2, c.sx, c.j0 + lane, c.W, c.pw);
-        const int mode = st & 3, xmin = st >> 2;
-        if (mode) fwd_mbar_wait(&S.bar[q], parity);
-        const float ev = c.bad ? 0.f : c.extrap;   // rows of a bad image index are zeros (crop_and_resize_kernel.cu:34-38)
-        const float4 e4 = make_float4(ev, ev, ev, ev);
-        const float *top = &S.buf[q][0][0][0] + lane * 4, *bot = &S.buf[q][1][0][0] + lane * 4;
-#pragma unroll
-        for (int j = 0; j < SUB; ++j) {
-            if (j >= n) break;
-            const int lo = __shfl_sync(0xffffffffu, mine.lo, j), hi = __shfl_sync(0xffffffffu, mine.hi, j);
-            const float fx = __shfl_sync(0xffffffffu, mine.frac, j);
-            const bool in = __shfl_sync(0xffffffffu, (int)mine.inside, j) != 0 && c.row_ok;
-            const int pl = mode == 1 ? lo - xmin : 2 * j, ph = mode == 1 ? hi - xmin : 2 * j + (hi != lo ? 1 : 0);
-#pragma unroll
-            for (int ch = 0; ch < NCH; ++ch) {
-                float4 v = e4;
-                if (in) {
-                    const int o = ch * 128;
-                    const float4 tl = *reinterpret_cast<const float4 *>(top + pl * (NCH * 128) + o), tr = *reinterpret_cast<const float4 *>(top + ph * (NCH * 128) + o);
-                    const float4 bl = *reinterpret_cast<const float4 *>(bot + pl * (NCH * 128) + o), br = *reinterpret_cast<const float4 *>(bot + ph * (NCH * 128) + o);
-                    const float4 t4 = lerp_rn(tl, tr, fx);                  // crop_and_resize.c:102
-                    const float4 b4 = lerp_rn(bl, br, fx);                  // :103-104
-                    v = lerp_rn(t4, b4, c.fy);                              // :106
-                }
-                st_stream4(c.out + (long)(c.j0 + j) * c.C + ch * 128 + lane * 4, v);
-                if (c.out2) st_stream4(c.out2 + (long)(c.j0 + j) * c.C + ch * 128 + lane * 4, v);
-            }
-        }
-    };
-
-    FwdCursor cI, cC;
-    cI.u = warp;
-    if (cI.u >= total) return;
-    enter_unit(cI);
-    cC = cI;
-    unsigned uses[2] = {0u, 0u};                  // completed phases per buffer
-    int st_cur = issue(cI, 0), st_next = 0;
-    for (int n = 0;; ++n) {
-        const int q = n & 1;
-        const bool more = advance(cI);
-        if (more) st_next = issue(cI, q ^ 1);
-        compute(cC, q, st_cur, uses[q] & 1u);
-        if (st_cur & 3) ++uses[q];
-        if (!more) break;
-        advance(cC);
-        st_cur = st_next;
     }
 }
 
@@ -713,32 +523,7 @@ FI_API int fi_crop_sets_forward(const fi_fwd_set *sets, int num_sets, cudaStream
     }
     dev.first_unit[dev.n] = units;
     if (units == 0) return ok();
-    const int form = option(FI_OPT_FWD_FORM);
-    bool same_c = dev.n > 0 && (dev.s[0].C == 128 || dev.s[0].C == 256);
-    for (int k = 1; k < dev.n; ++k) same_c = same_c && dev.s[k].C == dev.s[0].C;
-    if ((form == 1 || form == 2) && same_c) {
-        // bulk-copy staged forward, persistent CTAs: unit = (set, box, crop row) for all channels
-        long rows = 0;
-        for (int k = 0; k < dev.n; ++k) rows += (long)dev.s[k].R * dev.s[k].ph;
-#define FI_FWD_TMA(SUB_, WARPS_, NCH_, PER_SM_)                                                                                              \
-    do {                                                                                                                                     \
-        const size_t smem = WARPS_ * sizeof(FwdWarpSmem<SUB_, NCH_>);                                                                        \
-        cudaError_t e = cudaFuncSetAttribute(crop_fwd_nhwc_sets_tma_kernel<SUB_, WARPS_, NCH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e != cudaSuccess) { set_error(FI_ERR_CUDA, "fi_crop_sets_forward: shared memory attribute: %s", cudaGetErrorString(e)); return FI_ERR_CUDA; }    \
-        crop_fwd_nhwc_sets_tma_kernel<SUB_, WARPS_, NCH_><<<grid_for(rows, WARPS_, PER_SM_), WARPS_ * 32, smem, stream>>>(dev);             \
-    } while (0)
-        if (dev.s[0].C == 256) {
-            if (form == 1) FI_FWD_TMA(7, 4, 2, 1);         // 56 KB per warp: 4 warps on an SM
-            else FI_FWD_TMA(4, 7, 2, 1);                   // 32 KB per warp: 7 warps
-        } else {
-            if (form == 1) FI_FWD_TMA(7, 7, 1, 1);
-            else FI_FWD_TMA(4, 13, 1, 1);
-        }
-#undef FI_FWD_TMA
-        return check_launch("fi_crop_sets_forward[bulk-copy staged]");
-    }
-    if (form == 3) crop_fwd_nhwc_sets_kernel<true><<<grid_for(units, kWarpsPerBlock, 8), kWarpsPerBlock * 32, 0, stream>>>(dev);
-    else crop_fwd_nhwc_sets_kernel<false><<<grid_for(units, kWarpsPerBlock, 8), kWarpsPerBlock * 32, 0, stream>>>(dev);
+    crop_fwd_nhwc_sets_kernel<<<grid_for(units, kWarpsPerBlock, 8), kWarpsPerBlock * 32, 0, stream>>>(dev);
     return check_launch("fi_crop_sets_forward");
 }
 

@@ -97,46 +97,6 @@ __device__ __forceinline__ void fwd_unit(const FwdSet &S, long u, int lane) {
     }
 }
 
-// Requests the taps of a unit into L2 (prefetch.global.L2) -- called for the unit a warp will take NEXT, while it works on the
-// current one: the kernel is latency-bound (16 tap loads in flight per lane, then nothing while it interpolates), the prefetch
-// starts the DRAM reads a whole unit early and the later loads see L2 latency.  Dense rows (span <= 2 * pw pixels) are walked
-// line by line across the lanes, sparse ones sample by sample.
-__device__ __forceinline__ void fwd_prefetch_unit(const FwdSet &S, long u, int lane) {
-    const int slab = (int)(u % S.slabs);
-    const long q = u / S.slabs;
-    const int r = (int)(q / S.ph), i = (int)(q - (long)r * S.ph);
-    if (S.R_dev && r >= *S.R_dev) return;
-    const int b = S.box_ind[r];
-    if (b < 0 || b >= S.B) return;
-    const float y1 = S.boxes[4 * r + 0], x1 = S.boxes[4 * r + 1], y2 = S.boxes[4 * r + 2], x2 = S.boxes[4 * r + 3];
-    const AxisTap ty = axis_sample(y1, y2, axis_step(y1, y2, S.H, S.ph), i, S.H, S.ph);
-    if (!ty.inside) return;
-    const AxisTap t = axis_sample(x1, x2, axis_step(x1, x2, S.W, S.pw), lane, S.W, S.pw);
-    const bool in = lane < S.pw && t.inside;
-    if (__ballot_sync(0xffffffffu, in) == 0) return;
-    const int xmin = __reduce_min_sync(0xffffffffu, in ? t.lo : 0x7fffffff), xmax = __reduce_max_sync(0xffffffffu, in ? t.hi : -1);
-    const float *rowT = S.image + ((long)b * S.H + ty.lo) * (long)S.W * S.C + slab * 128;
-    const float *rowB = S.image + ((long)b * S.H + ty.hi) * (long)S.W * S.C + slab * 128;
-    const int span = xmax - xmin + 1;
-    if (span <= 2 * S.pw) {
-        for (int l = lane; l < span * 4; l += 32) {                // 4 lines of 128 B per pixel of this slab
-            const long off = (long)(xmin + (l >> 2)) * S.C + (l & 3) * 32;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(rowT + off));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(rowB + off));
-        }
-    } else if (in) {
-#pragma unroll
-        for (int l = 0; l < 4; ++l) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(rowT + (long)t.lo * S.C + l * 32));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(rowB + (long)t.lo * S.C + l * 32));
-            if (t.hi != t.lo) {
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(rowT + (long)t.hi * S.C + l * 32));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(rowB + (long)t.hi * S.C + l * 32));
-            }
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // NHWC backward, scatter form.  Same warp-per-crop-row walk.  The contributions to the current
 // (x_lo, x_hi) pixel pair of the top and of the bottom image row are kept in registers and flushed with

@@ -52,10 +52,7 @@ unsigned long long fi_kernel_launches(void); /* kernels this library has launche
 #define FI_OPT_PIX_CFG 4          /* form 0, ring shape (slots per batch x batches, CTAs per SM): 0 = 32x2,3 (default); 1 = 32x3,2;
                                      2 = 16x6,2; 3 = 16x4,3 [FI_PIX_CFG] */
 #define FI_OPT_PIX_GROUP 5        /* form 0, tiles per work ticket minus 1: 0..7 [FI_PIX_GROUP] */
-#define FI_OPT_FWD_FORM 6         /* level-batched NHWC forward: 0 = register-staged loads; 1 = taps staged by bulk copies, 7-sample
-                                     sub-batches, 4 warps per SM; 2 = the same with 4-sample sub-batches, 7 warps per SM; 3 = form 0 + L2 prefetch of the
-                                     next unit's taps [FI_FWD_FORM] */
-#define FI_OPT_COUNT 7
+#define FI_OPT_COUNT 6
 int fi_set_option(int option, int value);
 int fi_get_option(int option);
 

@@ -676,47 +676,3 @@ def test_reference_named_backward_launcher_c256_accumulates_and_matches_referenc
             # the reference kernel adds every term onto (base + partial sum) with atomics, in arrival order: each of its hundreds of
             # additions rounds at the magnitude of the running value -- a sanity cross-check, the parity bound is the one above
             torch.testing.assert_close(gi, gr, rtol=1e-4, atol=2e-4)
-
-
-@pytest.mark.parametrize("C", [256, 128])
-def test_forward_bulk_copy_staged_is_bit_identical(C):
-    """The level-batched forward with taps staged by cp.async.bulk (fi_set_option fwd_form 1 / 2: dense row segments for the small
-    sets, pixel pairs for sparse crops) writes the same bits as the register-staged kernel: scattered + compact destinations,
-    device-side list lengths, boxes straddling the border / zero-padded / inverted, bad image indices, 7x7 and 14x14, and a 3x5
-    crop through the plain entry for the sub-batch tails."""
-    fi = _fi()
-    from feature_intertwiner_b200 import synth
-    g = torch.Generator().manual_seed(61)
-    cl = torch.channels_last
-    B, R = 3, 260
-    maps = [torch.randn(B, C, 52 // s, 84 // s, generator=g).cuda().contiguous(memory_format=cl) for s in (1, 2)]
-    rois = synth.make_rois(1, R, (832, 1344), g, zero_frac=0.05, straddle_frac=0.05)[0]
-    rois[7] = torch.tensor([0.9, 0.8, 0.1, 0.2])                 # inverted
-    rois[8] = torch.tensor([-0.5, -0.5, 1.5, 1.5])               # mostly outside
-    rois[9] = torch.tensor([1.2, 1.2, 1.5, 1.5])                 # fully outside
-    rois[10] = torch.tensor([0.0, 0.0, 1.0, 1.0])                # whole map: sparse on the fine one
-    rois = rois.cuda()
-    ind = torch.randint(0, B, (R,), generator=g, dtype=torch.int32)
-    ind[11] = 7; ind[12] = -1                                    # bad image indices: zero rows
-    ind = ind.cuda()
-    rows = torch.randperm(R + 9, generator=g)[:R].int().cuda()
-    cnt = torch.tensor([R - 17], dtype=torch.int32, device="cuda")
-    res = {}
-    for form in (0, 1, 2, 3):
-        old = fi.set_option("fwd_form", form)
-        try:
-            o7 = torch.full((R + 9, C, 7, 7), 5.0, device="cuda").contiguous(memory_format=cl)
-            o14 = torch.full((R + 9, C, 14, 14), 5.0, device="cuda").contiguous(memory_format=cl)
-            specs = [dict(image=maps[0], boxes=rois, box_ind=ind, size=7, out=o7, dst_row=rows, extrapolation=0.25),
-                     dict(image=maps[0], boxes=rois, box_ind=ind, size=14, out=o14, dst_row=rows, compact=True, count=cnt),
-                     dict(image=maps[1], boxes=rois, box_ind=ind, size=14),
-                     dict(image=maps[1], boxes=rois, box_ind=ind, size=7, extrapolation=-1.5)]
-            outs, comps = fi.crop_sets(specs)
-            res[form] = [outs[0].clone(), outs[1].clone(), comps[1][: R - 17].clone(), comps[2].clone(), comps[3].clone()]
-        finally:
-            fi.set_option("fwd_form", old)
-    for form in (1, 2, 3):
-        for a, b in zip(res[0], res[form]):
-            assert torch.equal(a, b), form
-    want = clib.oracle_crop_and_resize_fwd(maps[1].contiguous().cpu().numpy(), rois.cpu().numpy()[13:], ind.cpu().numpy()[13:], 14, 14, 0.0)
-    np.testing.assert_array_equal(res[1][3][13:].contiguous().cpu().numpy(), want)       # and both are the oracle's bits
