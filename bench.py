@@ -346,17 +346,20 @@ class Step(object):
             specs.append(dict(image=madeup[i], boxes=boxes, box_ind=ind, size=7, out=pooled_out, dst_row=s32, count=split.small_count(i)))
             specs.append(dict(image=madeup[i], boxes=boxes, box_ind=ind, size=14, out=mask_out, dst_row=s32, compact=(i < 3), count=split.small_count(i)))
         res_out, res_comp = fi.crop_sets(specs, max_entries=self.max_entries)
-        outs, grads = [], []
-        bfeat, bcnt, sfeat, scnt = [], [], [], []
+        outs, grads, lists = [], [], []
         for i in range(3):
             k = where[("big", i)]
             outs.append(res_comp[k]); grads.append(inp["g_big"][i])          # compact 14x14 crop -> critic (stock conv, not timed)
-            f, c = fi.assign_feat2cls(split.big_gt(i), big_f[i], NCLS, count=split.big_count(i))
-            bfeat.append(f); bcnt.append(c)
             k = where[("small", i)]
             outs.append(res_comp[k + 1]); grads.append(inp["g_small"][i])
-            f, c = fi.assign_feat2cls(split.small_gt(i), small_f[i], NCLS, count=split.small_count(i))
-            sfeat.append(f); scnt.append(c)
+        # class means of the 3 reliable + 3 less-reliable lists: one launch each way (lib/sub_module.py:664-684)
+        for i in range(3):
+            lists.append((split.big_gt(i), big_f[i], split.big_count(i)))
+        for i in range(3):
+            lists.append((split.small_gt(i), small_f[i], split.small_count(i)))
+        stats = fi.assign_feat2cls_multi(lists, NCLS)
+        bfeat, bcnt = [stats[i][0] for i in range(3)], [stats[i][1] for i in range(3)]
+        sfeat, scnt = [stats[3 + i][0] for i in range(3)], [stats[3 + i][1] for i in range(3)]
         pooled_out, mask_out = res_out[where[("small", 3)]], res_out[where[("small", 3)] + 1]
         feat_in = [torch.stack(bfeat)[None].detach(), torch.stack(bcnt)[None], torch.stack(sfeat)[None], torch.stack(scnt)[None], None, None]
         self.last_feat_in = [t.detach() for t in feat_in[:4]]          # for the loss-head-only timing

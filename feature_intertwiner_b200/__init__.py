@@ -9,5 +9,5 @@ from .roi_pool import RoIPoolFunction, _RoIPooling  # noqa: F401
 from .nms import nms, nms_batched, nms_presorted, proposal_decode, proposal_layer, pth_nms  # noqa: F401
 from .ot import OptTrans, sinkhorn_loss  # noqa: F401
 from .targets import detection_decode, detection_layer, mask_targets  # noqa: F401
-from .intertwiner import (Dev, IntertwinerLoss, LevelSplit, assign_feat2cls, pyramid_roi_align, roi_level,  # noqa: F401
+from .intertwiner import (Dev, IntertwinerLoss, LevelSplit, assign_feat2cls, assign_feat2cls_multi, pyramid_roi_align, roi_level,  # noqa: F401
                           spatial_order, split_levels)

@@ -47,6 +47,9 @@ SIGNATURES = {
     "fi_split_levels_gather": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "fi_segment_mean_forward": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "fi_segment_mean_backward": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    "fi_segment_mean_forward_batch": (_I, [_P, _I, _I, _I, _P]),
+    "fi_segment_mean_backward_batch": (_I, [_P, _I, _I, _I, _P]),
+    "fi_spatial_order": (_I, [_P, _I, _I, _I, _P, _P]),
     "fi_segment_mean_forward_n": (_I, [_P, _P, _I, _P, _I, _I, _P, _P, _P]),
     "fi_segment_mean_backward_n": (_I, [_P, _P, _P, _I, _P, _I, _I, _P, _P]),
     "fi_sinkhorn": (_I, [_P, _P, _I, _I, _I, _F, _I, _P, _P, _P, _P]),
@@ -81,6 +84,11 @@ class BwdSet(C.Structure):
     _fields_ = [("grads_image", _P), ("grads", _P), ("grads2", _P), ("boxes", _P), ("box_ind", _P), ("src_row", _P),
                 ("batch", _I), ("image_height", _I), ("image_width", _I), ("depth", _I), ("num_boxes", _I),
                 ("crop_height", _I), ("crop_width", _I), ("num_boxes_dev", _P)]
+
+
+class SegSet(C.Structure):
+    """struct fi_seg_set."""
+    _fields_ = [("gt", _P), ("feat", _P), ("k", _I), ("k_dev", _P), ("mean", _P), ("cnt", _P), ("grad_mean", _P), ("grad_feat", _P)]
 
 
 class BwdPlan(C.Structure):

@@ -120,12 +120,26 @@ __global__ void __launch_bounds__(kSplitThreads) split_levels_kernel(const int *
 constexpr int kSegThreads = 128;
 constexpr int kSegStage = 1024;
 
-__global__ void __launch_bounds__(kSegThreads) segment_mean_fwd_kernel(const int *__restrict__ gt, const float *__restrict__ feat, int k,
-                                                                      const int *__restrict__ k_dev, int F, int ncls, float *__restrict__ mean,
-                                                                      float *__restrict__ cnt) {
+// Up to kSegSets (gt, feat) lists in one launch (blockIdx.z): Dev.forward takes the class means of 3 reliable + 3 less-reliable
+// lists per pass, each a launch-latency sized problem.
+constexpr int kSegSets = 8;
+struct SegSet {
+    const int *gt, *k_dev;
+    const float *feat, *gmean, *cntp;
+    float *mean, *cnt, *gfeat;
+    int k;
+};
+struct SegSets { SegSet s[kSegSets]; };
+
+__global__ void __launch_bounds__(kSegThreads) segment_mean_fwd_kernel(const SegSets sets, int F, int ncls) {
     __shared__ int rows[kSegStage];
     __shared__ int nrows;
-    if (k_dev) k = min(k, *k_dev);                 // list length kept on the device: k is the capacity
+    const SegSet &S = sets.s[blockIdx.z];
+    const int *__restrict__ gt = S.gt;
+    const float *__restrict__ feat = S.feat;
+    float *__restrict__ mean = S.mean, *__restrict__ cnt = S.cnt;
+    int k = S.k;
+    if (S.k_dev) k = min(k, *S.k_dev);             // list length kept on the device: k is the capacity
     const int c = blockIdx.x;
     const int f = blockIdx.y * kSegThreads + threadIdx.x;
     float acc = 0.f;
@@ -171,10 +185,14 @@ __global__ void __launch_bounds__(kSegThreads) segment_mean_fwd_kernel(const int
     if (blockIdx.y == 0 && threadIdx.x == 0) cnt[c] = (float)total;
 }
 
-__global__ void segment_mean_bwd_kernel(const int *__restrict__ gt, const float *__restrict__ gmean, const float *__restrict__ cnt, int k,
-                                        const int *__restrict__ k_dev, int F, int ncls, float *__restrict__ gfeat) {
+__global__ void segment_mean_bwd_kernel(const SegSets sets, int F, int ncls) {
+    const SegSet &S = sets.s[blockIdx.y];
+    const int *__restrict__ gt = S.gt;
+    const float *__restrict__ gmean = S.gmean, *__restrict__ cnt = S.cntp;
+    float *__restrict__ gfeat = S.gfeat;
+    const int k = S.k;
     const long total = (long)k * F;
-    const int live = k_dev ? min(k, *k_dev) : k;   // rows past the device-side length get a zero gradient
+    const int live = S.k_dev ? min(k, *S.k_dev) : k;   // rows past the device-side length get a zero gradient
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
         const int i = (int)(e / F), f = (int)(e - (long)i * F);
         const int c = i < live ? gt[i] : 0;
@@ -215,6 +233,35 @@ __global__ void buffer_update_kernel(const float *__restrict__ big_sum, const fl
             }
             final_big[e] = __fdiv_rn(s, __fadd_rn(cn, kEps));
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Visiting order of the RoIs (intertwiner.py::spatial_order): every image walked coarse tile by coarse tile (grid x grid, by box
+// centre, boustrophedon), stable.  One CTA per image; the rank of an element is counted directly (R <= 4096 per image: R^2 / 256
+// comparisons per thread against keys broadcast from shared memory) -- replaces ~10 pointwise launches and a radix sort.
+// ------------------------------------------------------------------------------------------------
+constexpr int kOrderMaxR = 4096;
+__global__ void __launch_bounds__(256) spatial_order_kernel(const float4 *__restrict__ rois, int R, int grid, int *__restrict__ order) {
+    __shared__ short keys[kOrderMaxR];
+    const int b = blockIdx.x;
+    const float g2 = __fmul_rn(0.5f, (float)grid), top = (float)(grid - 1);
+    for (int i = threadIdx.x; i < R; i += blockDim.x) {
+        const float4 r = __ldg(rois + (long)b * R + i);               // y1, x1, y2, x2
+        const float cy = floorf(fminf(fmaxf(__fmul_rn(__fadd_rn(r.x, r.z), g2), 0.f), top));
+        const float cx = floorf(fminf(fmaxf(__fmul_rn(__fadd_rn(r.y, r.w), g2), 0.f), top));
+        const int iy = (int)cy, ix = (int)cx;
+        keys[i] = (short)(iy * grid + ((iy & 1) ? grid - 1 - ix : ix));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < R; i += blockDim.x) {
+        const int k = keys[i];
+        int rank = 0;
+        for (int j = 0; j < R; ++j) {
+            const int kj = keys[j];
+            rank += (kj < k) || (kj == k && j < i);
+        }
+        order[(long)b * R + rank] = b * R + i;
     }
 }
 
@@ -268,28 +315,50 @@ FI_API int fi_split_levels_gather(const int *level, const float *rois, const int
     return check_launch("fi_split_levels_gather");
 }
 
+FI_API int fi_segment_mean_forward_batch(const fi_seg_set *sets, int num_sets, int F, int ncls, cudaStream_t stream) {
+    FI_REQUIRE(sets && num_sets >= 1 && num_sets <= kSegSets && F > 0 && ncls > 0 && ncls <= 1024, "fi_segment_mean_forward: 1..%d lists, F > 0, ncls in [1,1024]", kSegSets);
+    SegSets dev = {};
+    for (int i = 0; i < num_sets; ++i) {
+        const fi_seg_set &h = sets[i];
+        FI_REQUIRE(h.k >= 0 && h.mean && h.cnt && (h.k == 0 || (h.gt && h.feat)), "fi_segment_mean_forward: bad list %d", i);
+        dev.s[i].gt = h.gt; dev.s[i].k_dev = h.k_dev; dev.s[i].feat = h.feat; dev.s[i].mean = h.mean; dev.s[i].cnt = h.cnt; dev.s[i].k = h.k;
+    }
+    dim3 grid(ncls, ceil_div(F, kSegThreads), num_sets);
+    segment_mean_fwd_kernel<<<grid, kSegThreads, 0, stream>>>(dev, F, ncls);
+    return check_launch("fi_segment_mean_forward");
+}
 FI_API int fi_segment_mean_forward_n(const int *gt, const float *feat, int k, const int *k_dev, int F, int ncls, float *mean, float *cnt,
                                      cudaStream_t stream) {
-    FI_REQUIRE(k >= 0 && F > 0 && ncls > 0 && ncls <= 1024 && mean && cnt, "fi_segment_mean_forward: bad arguments");
-    FI_REQUIRE(k == 0 || (gt && feat), "fi_segment_mean_forward: null pointer");
-    dim3 grid(ncls, ceil_div(F, kSegThreads));
-    segment_mean_fwd_kernel<<<grid, kSegThreads, 0, stream>>>(gt, feat, k, k_dev, F, ncls, mean, cnt);
-    return check_launch("fi_segment_mean_forward");
+    fi_seg_set one = {gt, feat, k, k_dev, mean, cnt, nullptr, nullptr};
+    return fi_segment_mean_forward_batch(&one, 1, F, ncls, stream);
 }
 FI_API int fi_segment_mean_forward(const int *gt, const float *feat, int k, int F, int ncls, float *mean, float *cnt, cudaStream_t stream) {
     return fi_segment_mean_forward_n(gt, feat, k, nullptr, F, ncls, mean, cnt, stream);
 }
 
+/* backward of every list: grad_feat rows from grad_mean (h.grad_mean) and the forward's counts (h.cnt) */
+FI_API int fi_segment_mean_backward_batch(const fi_seg_set *sets, int num_sets, int F, int ncls, cudaStream_t stream) {
+    FI_REQUIRE(sets && num_sets >= 1 && num_sets <= kSegSets && F > 0 && ncls > 0, "fi_segment_mean_backward: 1..%d lists", kSegSets);
+    SegSets dev = {};
+    int max_k = 0;
+    for (int i = 0; i < num_sets; ++i) {
+        const fi_seg_set &h = sets[i];
+        FI_REQUIRE(h.k >= 0 && (h.k == 0 || (h.gt && h.grad_mean && h.cnt && h.grad_feat)), "fi_segment_mean_backward: bad list %d", i);
+        dev.s[i].gt = h.gt; dev.s[i].k_dev = h.k_dev; dev.s[i].gmean = h.grad_mean; dev.s[i].cntp = h.cnt; dev.s[i].gfeat = h.grad_feat; dev.s[i].k = h.k;
+        max_k = max_k > h.k ? max_k : h.k;
+    }
+    if (max_k == 0) return ok();
+    long grid = ((long)max_k * F + 255) / 256;
+    if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+    segment_mean_bwd_kernel<<<dim3((unsigned)grid, num_sets), 256, 0, stream>>>(dev, F, ncls);
+    return check_launch("fi_segment_mean_backward");
+}
 FI_API int fi_segment_mean_backward_n(const int *gt, const float *grad_mean, const float *cnt, int k, const int *k_dev, int F, int ncls,
                                       float *grad_feat, cudaStream_t stream) {
     FI_REQUIRE(k >= 0 && F > 0 && ncls > 0, "fi_segment_mean_backward: bad arguments");
     if (k == 0) return ok();
-    FI_REQUIRE(gt && grad_mean && cnt && grad_feat, "fi_segment_mean_backward: null pointer");
-    long total = (long)k * F;
-    long grid = (total + 255) / 256;
-    if (grid > kNumSMs * 8) grid = kNumSMs * 8;
-    segment_mean_bwd_kernel<<<(int)grid, 256, 0, stream>>>(gt, grad_mean, cnt, k, k_dev, F, ncls, grad_feat);
-    return check_launch("fi_segment_mean_backward");
+    fi_seg_set one = {gt, nullptr, k, k_dev, nullptr, const_cast<float *>(cnt), grad_mean, grad_feat};
+    return fi_segment_mean_backward_batch(&one, 1, F, ncls, stream);
 }
 FI_API int fi_segment_mean_backward(const int *gt, const float *grad_mean, const float *cnt, int k, int F, int ncls, float *grad_feat,
                                     cudaStream_t stream) {
@@ -306,4 +375,13 @@ FI_API int fi_buffer_update(const float *big_sum, const float *big_n, int B, int
     if (int e = check_launch("fi_buffer_update")) return e;
     buffer_cnt_kernel<<<ceil_div(ncls, 128), 128, 0, stream>>>(big_n, B, slot, ncls, buffer_cnt);
     return check_launch("fi_buffer_update[cnt]");
+}
+
+FI_API int fi_spatial_order(const float *rois, int batch, int rois_per_image, int grid, int *order, cudaStream_t stream) {
+    FI_REQUIRE(batch >= 0 && rois_per_image >= 0 && grid >= 1 && grid <= 128, "fi_spatial_order: bad sizes");
+    if (batch == 0 || rois_per_image == 0) return ok();
+    if (rois_per_image > kOrderMaxR) { set_error(FI_ERR_UNSUPPORTED, "fi_spatial_order: more than %d RoIs per image", kOrderMaxR); return FI_ERR_UNSUPPORTED; }
+    FI_REQUIRE(rois && order && ((uintptr_t)rois % 16) == 0, "fi_spatial_order: rois must be a 16-byte aligned device pointer");
+    spatial_order_kernel<<<batch, 256, 0, stream>>>(reinterpret_cast<const float4 *>(rois), rois_per_image, grid, order);
+    return check_launch("fi_spatial_order");
 }

@@ -116,6 +116,13 @@ def spatial_order(rois, grid=None):
     if grid is None:
         grid = int(os.environ.get("FI_SORT_GRID", "8"))
     bs, R = rois.shape[0], rois.shape[1]
+    if rois.is_cuda and rois.dim() == 3 and R <= 4096 and grid <= 128:
+        flat = rois.detach().float().contiguous()
+        order = torch.empty((bs * R,), device=rois.device, dtype=torch.int32)
+        with torch.cuda.device(rois.device):
+            _lib.check(_lib.lib().fi_spatial_order(_lib.ptr(flat), bs, R, int(grid), _lib.ptr(order), _lib.stream_ptr(rois.device)))
+        return order
+    # the same order with torch ops (CPU tensors in tests, more than 4096 RoIs per image)
     cy = ((rois[..., 0] + rois[..., 2]) * (0.5 * grid)).clamp(0, grid - 1).floor()
     cx = ((rois[..., 1] + rois[..., 3]) * (0.5 * grid)).clamp(0, grid - 1).floor()
     snake = torch.where(cy.long() % 2 == 0, cx, grid - 1 - cx)            # boustrophedon: neighbouring tiles stay neighbours
@@ -193,6 +200,62 @@ class _SegmentMean(torch.autograd.Function):
             _lib.check(_lib.lib().fi_segment_mean_backward_n(_lib.ptr(gt), _lib.ptr(gmean), _lib.ptr(cnt), k, _lib.ptr(count) if ctx.has_count else None,
                                                              Fd, ncls, _lib.ptr(gfeat), _lib.stream_ptr(gmean.device)))
         return None, gfeat.view(ctx.shape), None, None
+
+
+class _SegmentMeanMulti(torch.autograd.Function):
+    """Class means of several (gt, feat) lists in ONE launch each way.  apply(ncls, n, *gts, *counts, *feats) -> means..., cnts..."""
+
+    @staticmethod
+    def forward(ctx, ncls, n, *args):
+        gts, counts, feats = args[:n], args[n:2 * n], args[2 * n:3 * n]
+        dev = feats[0].device
+        _lib.require_cuda(*feats)
+        feat2 = [f.flatten(1).float().contiguous() for f in feats]
+        gts = [g.detach().to(torch.int32).contiguous() for g in gts]
+        counts = [None if c is None else c.detach().to(device=dev, dtype=torch.int32).reshape(-1)[:1].contiguous() for c in counts]
+        Fd = feat2[0].size(1)
+        if any(f.size(1) != Fd for f in feat2):
+            raise _lib.FiError("assign_feat2cls_multi: all lists must share the feature width")
+        means = [torch.empty((Fd, ncls), device=dev, dtype=torch.float32) for _ in range(n)]
+        cnts = [torch.empty((1, ncls), device=dev, dtype=torch.float32) for _ in range(n)]
+        arr = (_lib.SegSet * n)(*[_lib.SegSet(_lib.ptr(gts[i]), _lib.ptr(feat2[i]), feat2[i].size(0), _lib.ptr(counts[i]), _lib.ptr(means[i]), _lib.ptr(cnts[i]),
+                                               None, None) for i in range(n)])
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().fi_segment_mean_forward_batch(arr, n, Fd, ncls, _lib.stream_ptr(dev)))
+        ctx.lists = (gts, counts, cnts)
+        ctx.shapes = [tuple(f.shape) for f in feats]
+        ctx.dims = (n, Fd, ncls)
+        ctx.mark_non_differentiable(*cnts)
+        ctx.set_materialize_grads(False)
+        return tuple(means) + tuple(cnts)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        n, Fd, ncls = ctx.dims
+        gts, counts, cnts = ctx.lists
+        dev = cnts[0].device
+        live = [i for i in range(n) if grads[i] is not None and ctx.needs_input_grad[2 + 2 * n + i]]
+        out = [None] * n
+        if live:
+            gm = {i: grads[i].contiguous() for i in live}
+            for i in live:
+                out[i] = torch.empty((gts[i].numel(), Fd), device=dev, dtype=torch.float32)
+            arr = (_lib.SegSet * len(live))(*[_lib.SegSet(_lib.ptr(gts[i]), None, gts[i].numel(), _lib.ptr(counts[i]), None, _lib.ptr(cnts[i]), _lib.ptr(gm[i]),
+                                                           _lib.ptr(out[i])) for i in live])
+            with torch.cuda.device(dev):
+                _lib.check(_lib.lib().fi_segment_mean_backward_batch(arr, len(live), Fd, ncls, _lib.stream_ptr(dev)))
+        return (None, None) + (None,) * (2 * n) + tuple(None if o is None else o.view(ctx.shapes[i]) for i, o in enumerate(out))
+
+
+def assign_feat2cls_multi(lists, num_classes):
+    """``lists`` = [(box_gt, input_feat[, count]), ...] (at most 8) -> [(feat[F,ncls], cnt[1,ncls]), ...]: assign_feat2cls of every
+    list in one launch forward and one backward."""
+    n = len(lists)
+    gts = [l[0] for l in lists]
+    feats = [l[1] for l in lists]
+    counts = [l[2] if len(l) > 2 else None for l in lists]
+    res = _SegmentMeanMulti.apply(int(num_classes), n, *gts, *counts, *feats)
+    return [(res[i], res[n + i]) for i in range(n)]
 
 
 def assign_feat2cls(box_gt, input_feat, num_classes, count=None):

@@ -239,6 +239,25 @@ int fi_segment_mean_forward(const int *gt, const float *feat, int k, int F, int 
 /* grad_feat[i,:] = grad_mean[:,gt_i] / cnt[gt_i]  (0 for background rows) */
 int fi_segment_mean_backward(const int *gt, const float *grad_mean, const float *cnt, int k, int F, int ncls,
                              float *grad_feat, cudaStream_t stream);
+/* Several lists in one launch (Dev.forward takes 6 per pass).  Forward reads gt / feat / k / k_dev and writes mean / cnt;
+ * backward reads gt / k / k_dev / cnt / grad_mean and writes grad_feat.  At most 8 lists. */
+typedef struct fi_seg_set {
+    const int *gt;
+    const float *feat;
+    int k;
+    const int *k_dev;
+    float *mean;
+    float *cnt;
+    const float *grad_mean;
+    float *grad_feat;
+} fi_seg_set;
+int fi_segment_mean_forward_batch(const fi_seg_set *sets, int num_sets, int F, int ncls, cudaStream_t stream);
+int fi_segment_mean_backward_batch(const fi_seg_set *sets, int num_sets, int F, int ncls, cudaStream_t stream);
+
+/* Visiting order of rois[batch, R, 4] that walks every image coarse tile by coarse tile (grid x grid by box centre, boustrophedon,
+ * stable): order[batch * R] int32, a permutation of the flat RoI ids, image-major.  R <= 4096. */
+int fi_spatial_order(const float *rois, int batch, int rois_per_image, int grid, int *order, cudaStream_t stream);
+
 /* The same with the list length on the device: k is the capacity of gt / feat, *k_dev (NULL: k) the rows in use;
  * backward writes zeros into the rows past it. */
 int fi_segment_mean_forward_n(const int *gt, const float *feat, int k, const int *k_dev, int F, int ncls, float *mean, float *cnt,

@@ -263,6 +263,40 @@ def test_segment_mean_fwd_bwd(k):
     np.testing.assert_allclose(fc.grad.cpu().numpy(), fr.grad.numpy(), rtol=1e-5, atol=1e-7)
 
 
+def test_segment_mean_multi_and_spatial_order_match_the_single_forms():
+    """assign_feat2cls_multi (one launch for several lists, device-side lengths) == assign_feat2cls list by list, forward and
+    backward; fi_spatial_order == the torch formulation of the same visiting order."""
+    fi = _fi()
+    from feature_intertwiner_b200 import synth
+    g = torch.Generator().manual_seed(77)
+    lists, singles = [], []
+    for k, live in ((300, 300), (1, 1), (50, 20), (0, 0), (700, 650)):
+        gt = torch.randint(0, 81, (k,), generator=g, dtype=torch.int32).cuda()
+        f = torch.randn(k, 1024, generator=g).cuda()
+        cnt = torch.tensor([live], dtype=torch.int32, device="cuda") if live != k else None
+        a, b = f.clone().requires_grad_(), f.clone().requires_grad_()
+        lists.append((gt, a, cnt)); singles.append((gt, b, cnt))
+    multi = fi.assign_feat2cls_multi(lists, 81)
+    w = [torch.randn(1024, 81, generator=g).cuda() for _ in lists]
+    sum((m * wi).sum() for (m, _), wi in zip(multi, w)).backward()
+    for (gt, b, cnt), (m, c), wi, (_, a, _) in zip(singles, multi, w, lists):
+        ms, cs = fi.assign_feat2cls(gt, b, 81, count=cnt)
+        assert torch.equal(ms, m) and torch.equal(cs, c)
+        if b.numel():
+            (ms * wi).sum().backward()
+            assert torch.equal(a.grad, b.grad)
+    for (bs, R, hw) in ((8, 512, (832, 1344)), (4, 2000, (832, 1344)), (2, 1, (256, 256))):
+        rois = synth.make_rois(bs, R, hw, g).cuda()
+        got = fi.spatial_order(rois)
+        grid = 8
+        cy = ((rois[..., 0] + rois[..., 2]) * (0.5 * grid)).clamp(0, grid - 1).floor()
+        cx = ((rois[..., 1] + rois[..., 3]) * (0.5 * grid)).clamp(0, grid - 1).floor()
+        snake = torch.where(cy.long() % 2 == 0, cx, grid - 1 - cx)
+        key = (torch.arange(bs, device="cuda").view(bs, 1) * (grid * grid) + cy * grid + snake).view(-1)
+        want = torch.sort(key, stable=True)[1].int()
+        assert torch.equal(got, want)
+
+
 @pytest.mark.parametrize("B,loss", [(1, "l2"), (1, "l1"), (3, "l2"), (1, "ot")])
 @pytest.mark.parametrize("inst", [False, True])
 def test_intertwiner_loss_vs_restatement(B, loss, inst):
