@@ -67,31 +67,44 @@ def workload_name(name, wl):
 
 
 def bind_to_gpu_numa(local):
-    """Pin this process (and, by first touch, its pinned host buffers) to the NUMA node the GPU hangs off: with every rank's
-    buffers on node 0 the e2e leg of ranks 4-7 crossed the socket link (round 1: 77 -> 180 ms/step from 1 to 8 GPUs)."""
+    """Pin this process (and, by first touch, its pinned host buffers) to the CPUs next to its GPU -- NVML's ideal CPU affinity of
+    the device, or the NUMA node sysfs names for its PCI function: with every rank's buffers on node 0 the e2e leg of ranks 4-7
+    crossed the socket link (round 1: 77 -> 180 ms/step from 1 to 8 GPUs)."""
     try:
         import pynvml
         pynvml.nvmlInit()
         visible = os.environ.get("CUDA_VISIBLE_DEVICES")
         phys = int(visible.split(",")[local]) if visible and visible.split(",")[local].isdigit() else local
-        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(phys)).busId
-        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
-        if len(bus.split(":")[0]) == 8:
-            bus = bus[4:]                                   # nvml: 00000000:1b:00.0, sysfs: 0000:1b:00.0
-        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
-        if node < 0:
-            return None
-        cpus = []
-        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
-            lo, _, hi = part.partition("-")
-            cpus += list(range(int(lo), int(hi or lo) + 1))
-        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
-        if allowed:
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        ncpu = os.cpu_count() or 1
+        allowed_now = set(os.sched_getaffinity(0))
+        cpus, how = [], None
+        try:
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+            cpus = [64 * i + bit for i, wd in enumerate(words) for bit in range(64) if (int(wd) >> bit) & 1]
+            how = "nvml cpu affinity"
+        except Exception:
+            cpus = []
+        if not cpus or set(cpus) >= allowed_now:
+            bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+            bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+            if len(bus.split(":")[0]) == 8:
+                bus = bus[4:]                               # nvml: 00000000:1b:00.0, sysfs: 0000:1b:00.0
+            node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+            if node < 0:
+                return {"bound": False, "why": "no NUMA information for the GPU (nvml affinity = all CPUs, sysfs numa_node = -1)"}
+            cpus = []
+            for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus += list(range(int(lo), int(hi or lo) + 1))
+            how = "sysfs numa_node %d" % node
+        allowed = sorted(set(cpus) & allowed_now)
+        if allowed and len(allowed) < len(allowed_now):
             os.sched_setaffinity(0, allowed)
-            return {"numa_node": node, "cpus": len(allowed)}
-    except Exception:
-        pass
-    return None
+            return {"bound": True, "how": how, "cpus": len(allowed)}
+        return {"bound": False, "why": "the GPU's CPU set is every CPU this process may use"}
+    except Exception as exc:        # noqa: BLE001
+        return {"bound": False, "why": repr(exc)[:120]}
 
 
 class ClockSampler(object):

@@ -63,6 +63,8 @@ SIGNATURES = {
     "fi_detection_decode": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _F, _F, _F, _P, _P, _P, _P, _P]),
     "fi_roi_pool_forward": (_I, [_P, _F, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "fi_roi_pool_backward": (_I, [_P, _F, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "fi_roi_pool_forward_nhwc": (_I, [_P, _F, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "fi_roi_pool_backward_nhwc": (_I, [_P, _F, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
 }
 
 

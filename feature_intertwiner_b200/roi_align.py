@@ -186,8 +186,16 @@ class _CropAndResize(torch.autograd.Function):
             _lib.check(_lib.lib().fi_crop_and_resize_backward(
                 _lib.ptr(grad_out), layout, _lib.ptr(boxes), _lib.ptr(box_ind), _lib.ptr(rows), boxes.size(0), B, H, W,
                 ctx.crop[0], ctx.crop[1], Cc, _lib.ptr(grad_image), layout, 0, _lib.stream_ptr(grad_out.device)))
-        # `out` was written in place: rows this call did not touch pass their gradient through to whoever wrote them
-        return grad_image, None, None, None, None, None, (grad_out if ctx.has_out else None), None
+        # `out` was written in place: rows this call did not touch pass their gradient through to whoever wrote them; the rows it
+        # overwrote no longer depend on the previous contents (zero gradient)
+        g_prev = None
+        if ctx.has_out and ctx.needs_input_grad[6]:
+            g_prev = grad_out.clone()
+            if rows is not None:
+                g_prev.index_fill_(0, rows.long(), 0.0)
+            else:
+                g_prev[: boxes.size(0)].zero_()
+        return grad_image, None, None, None, None, None, g_prev, None
 
 
 class _CropPair(torch.autograd.Function):
@@ -254,7 +262,16 @@ class _CropPair(torch.autograd.Function):
             with torch.cuda.device(dev), _Timed("crop_bwd_nhwc", im_size=(B, Cc, H, W), crop=(size_b, size_b), boxes=boxes, box_ind=box_ind, alg_bytes=nbytes):
                 _lib.check(_lib.lib().fi_crop_and_resize_backward_multi(arr, len(sets), B, H, W, Cc, _lib.ptr(grad_image), 0,
                                                                         _lib.lib().fi_get_deterministic(), _lib.stream_ptr(dev)))
-        return grad_image, None, None, None, g_a, g_b, None, None, None
+        # gradient w.r.t. the previous contents of the in-place outputs: the rows this call overwrote get none
+        prev = []
+        for pos, gg in ((4, g_a), (5, g_b)):
+            if gg is not None and ctx.needs_input_grad[pos]:
+                gg = gg.clone()
+                gg.index_fill_(0, dst_row.long(), 0.0)
+                prev.append(gg)
+            else:
+                prev.append(None)
+        return grad_image, None, None, None, prev[0], prev[1], None, None, None
 
 
 def crop_pair(image, boxes, box_ind, dst_row, out_a, size_a, out_b, size_b, compact_b=False):
@@ -448,7 +465,23 @@ class _CropSets(torch.autograd.Function):
         for i, gi in g_images.items():
             if i not in touched:
                 gi.zero_()                       # a map none of whose crops received a gradient
-        return (None,) + tuple(g_images.get(i) for i in range(n_img)) + tuple(g_outs)
+        # gradient w.r.t. the previous contents of the in-place outputs (only when somebody asks for it: Dev hands in fresh
+        # tensors): the rows the sets overwrote no longer depend on them
+        g_prev = []
+        for o in range(n_out):
+            if g_outs[o] is None or not ctx.needs_input_grad[1 + n_img + o]:
+                g_prev.append(None)
+                continue
+            gp = g_outs[o].clone()
+            for kp in ctx.keep:
+                if kp["out"] == o and kp["dst_row"] is not None and kp["cap"] > 0:
+                    if kp["count"] is None:
+                        gp.index_fill_(0, kp["dst_row"].long(), 0.0)
+                    else:                                # device-side length: only the live rows were written
+                        livemask = torch.arange(kp["cap"], device=dev) < kp["count"].to(dev)
+                        gp.index_put_((kp["dst_row"].long()[livemask],), torch.zeros((), device=dev))
+            g_prev.append(gp)
+        return (None,) + tuple(g_images.get(i) for i in range(n_img)) + tuple(g_prev)
 
 
 def crop_sets(specs, max_entries=0):

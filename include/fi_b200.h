@@ -347,6 +347,14 @@ int fi_roi_pool_backward(const float *top_diff, float spatial_scale, int batch, 
                          int channels, int pooled_h, int pooled_w, const float *rois, float *bottom_diff,
                          const int *argmax, cudaStream_t stream);
 
+/* The same on torch.channels_last tensors (bottom[B,H,W,C], top / argmax[R,ph,pw,C], channels % 128 == 0): warp per (RoI, bin,
+ * 128-channel slab), coalesced 128-bit loads.  argmax holds the reference's flat NCHW offsets (layout-independent): values and
+ * indices equal those of ROIPoolForwardLaucher on the same data. */
+int fi_roi_pool_forward_nhwc(const float *bottom, float spatial_scale, int batch, int num_rois, int height, int width, int channels,
+                             int pooled_h, int pooled_w, const float *rois, float *top, int *argmax, cudaStream_t stream);
+int fi_roi_pool_backward_nhwc(const float *top_diff, float spatial_scale, int batch, int num_rois, int height, int width, int channels,
+                              int pooled_h, int pooled_w, const float *rois, float *bottom_diff, const int *argmax, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

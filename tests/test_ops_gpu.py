@@ -667,6 +667,40 @@ def test_roi_pool_vs_reference_cuda_kernel(scale, hw):
     torch.testing.assert_close(fc.grad, grads["ref"], rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("scale,hw", [(0.25, (52, 84)), (0.0625, (26, 42))])
+def test_roi_pool_nhwc_kernel_equals_nchw_and_reference(scale, hw):
+    """channels_last RoIPool (warp per bin, 128-bit loads): values and arg-max identical to the NCHW kernel and to the reference's own
+    CUDA kernel; backward equal to the NCHW one to summation tolerance."""
+    fi = _fi()
+    from feature_intertwiner_b200 import _lib
+    g = torch.Generator().manual_seed(23)
+    B, Cc, (H, W), R = 2, 256, hw, 300
+    feat = torch.randn(B, Cc, H, W, generator=g).cuda()
+    xy = torch.rand(R, 2, generator=g) * torch.tensor([W / scale, H / scale])
+    wh = torch.exp(torch.rand(R, 2, generator=g) * 3.5 + 2.0)
+    rois = torch.cat([torch.randint(0, B, (R, 1), generator=g).float(), xy - wh / 2, xy + wh / 2], 1)
+    rois[0, 1:] = torch.tensor([40., 40., 20., 20.])
+    rois[1, 1:] = torch.tensor([1e5, 1e5, 1e5 + 5, 1e5 + 5])
+    rois = rois.cuda()
+    a = feat.clone().requires_grad_()
+    b = feat.clone().contiguous(memory_format=torch.channels_last).requires_grad_()
+    oa = fi.RoIPoolFunction(7, 7, scale)(a, rois)
+    ob = fi.RoIPoolFunction(7, 7, scale)(b, rois)
+    assert ob.is_contiguous(memory_format=torch.channels_last) and torch.equal(oa, ob)
+    arg_nhwc = ob.grad_fn.saved_tensors[1].contiguous()
+    assert torch.equal(oa.grad_fn.saved_tensors[1], arg_nhwc)                                      # arg-max: the same flat NCHW offsets
+    gy = torch.randn(oa.shape, generator=g).cuda()
+    oa.backward(gy); ob.backward(gy)
+    torch.testing.assert_close(a.grad, b.grad, rtol=1e-5, atol=1e-5)
+    ref = clib.ref_cuda()
+    if ref is not None:
+        top = torch.empty(R, Cc, 7, 7, device="cuda"); arg = torch.empty(R, Cc, 7, 7, device="cuda", dtype=torch.int32)
+        assert ref.ROIPoolForwardLaucher(feat.data_ptr(), scale, R, H, W, Cc, 7, 7, rois.data_ptr(), top.data_ptr(), arg.data_ptr(),
+                                         torch.cuda.current_stream().cuda_stream) == 1
+        torch.cuda.synchronize()
+        assert torch.equal(ob, top) and torch.equal(arg_nhwc, arg)
+
+
 def test_proposal_layer_static_has_no_host_read_and_matches():
     """static=True: [bs, proposal_count, 4] zero-padded past the batch's smallest keep count, which stays on the device."""
     fi = _fi()

@@ -676,3 +676,26 @@ def test_reference_named_backward_launcher_c256_accumulates_and_matches_referenc
             # the reference kernel adds every term onto (base + partial sum) with atomics, in arrival order: each of its hundreds of
             # additions rounds at the magnitude of the running value -- a sanity cross-check, the parity bound is the one above
             torch.testing.assert_close(gi, gr, rtol=1e-4, atol=2e-4)
+
+
+def test_in_place_out_gradient_is_zero_on_overwritten_rows():
+    """An `out` that carries a gradient: the rows a crop call overwrites no longer depend on its previous contents."""
+    fi = _fi()
+    image, rois, box_ind = _case(21, 2, 256, 26, 42, 40, zero_rows=2)
+    cl = torch.channels_last
+    img = image.cuda().contiguous(memory_format=cl).requires_grad_()
+    base = torch.randn(60, 256, 7, 7, device="cuda").contiguous(memory_format=cl).requires_grad_()
+    rows = torch.randperm(60)[:40].int().cuda()
+    prev = base * 2.0                                       # has a grad_fn
+    out = fi.crop_and_resize(img, rois.cuda(), box_ind.cuda(), 7, 7, out=prev, dst_row=rows)
+    out.sum().backward()
+    untouched = torch.ones(60, dtype=torch.bool)
+    untouched[rows.cpu().long()] = False
+    assert torch.all(base.grad[untouched] == 2.0) and torch.all(base.grad[~untouched] == 0.0)
+    # the level-batched entry
+    img2 = image.cuda().contiguous(memory_format=cl).requires_grad_()
+    base2 = torch.randn(60, 256, 7, 7, device="cuda").contiguous(memory_format=cl).requires_grad_()
+    outs, _ = fi.crop_sets([dict(image=img2, boxes=rois.cuda(), box_ind=box_ind.cuda(), size=7, out=base2 * 2.0, dst_row=rows)])
+    outs[0].sum().backward()
+    assert torch.all(base2.grad[untouched] == 2.0) and torch.all(base2.grad[~untouched] == 0.0)
+    torch.testing.assert_close(img.grad, img2.grad)

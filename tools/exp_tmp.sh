@@ -1,7 +1,7 @@
-timeout 900 python -m pytest tests/test_ops_gpu.py -m gpu -x -q 2>&1 | tail -6
-for w in c2 c3; do timeout 300 python bench.py --workload $w --steps 5 --warmup 3 --no-other-workloads --no-cpu-baseline > gpurun_out/bench_$w.json 2>gpurun_out/bench_$w.err; python - <<PY
+timeout 900 python -m pytest tests/test_ops_gpu.py tests/test_roi_align_gpu.py -m gpu -x -q -k "roi_pool or formulations or in_place or device_counts or golden or overflow" 2>&1 | tail -4
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"bin_enumerate|tile_prep" -c 6 --csv --log-file gpurun_out/r02_launches_enum3.csv python tools/bwd_ab.py --iters 2 > /dev/null 2>&1; grep -o '"[a-z_:A-Z ]*\(bin_enumerate\|tile_prep\)[^"]*".*' gpurun_out/r02_launches_enum3.csv | awk -F'","' '{print $1, $NF}' | tail -4
+timeout 120 python tools/bwd_ab.py --iters 12 --plan-in-backward --out gpurun_out/ab_enum3_all.json > /dev/null 2>gpurun_out/ab_enum3.err
+python - <<PY
 import json
-d=json.loads(open("gpurun_out/bench_$w.json").read().strip().splitlines()[-1])
-print("$w", "ms/step", round(d["ms_per_step"],4), "value", round(d["value"]), {k:round(v["avg_ms"],4) for k,v in d["kernels"].items()}, "loss", round(d["intertwiner_loss"]["ms_per_iter"],4))
+d=json.load(open("gpurun_out/ab_enum3_all.json")); print("all", round(d["bwd_ms_median"],4), round(d["bwd_ms_min"],4), d["fingerprints"][0][0])
 PY
-done
