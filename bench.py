@@ -240,13 +240,46 @@ def build_config(wl):
         DATASET=ns(NUM_CLASSES=NCLS))
 
 
+PEER = {}      # "stats" / "grads": feature_intertwiner_b200.dist.PeerAllReduce of this process (several ranks only)
+
+
+def setup_peer_allreduce(dev, world):
+    """The two exchanges of a step as this library's peer-memory kernel (csrc/peer_allreduce.cu) instead of NCCL: the packed
+    class statistics (0.66 MB, on the critical path) and the OptTrans gradients (15.7 MB, on a side stream under the RoIAlign
+    backward).  Collective.  FI_PEER_ALLREDUCE=0 keeps NCCL (and the three-graph step)."""
+    if world == 1 or os.environ.get("FI_PEER_ALLREDUCE", "1") == "0":
+        return False
+    import feature_intertwiner_b200 as fi
+    from feature_intertwiner_b200 import dist as fdist
+    cfg = build_config(dict(image=(64, 64)))
+    n_grads = sum(p.numel() for p in fi.OptTrans(cfg, ch_x=FEAT, L=1).parameters())
+    stats = fdist.install_peer_allreduce(2 * (FEAT * NCLS + NCLS), None, dev)
+    if not stats.ok:
+        PEER["why"] = stats.why
+        return False
+    grads = fdist.PeerAllReduce(n_grads, None, dev)
+    if not grads.ok:
+        PEER["why"] = grads.why
+        fdist.uninstall_peer_allreduce(None)
+        return False
+    PEER.update(stats=stats, grads=grads)
+    return True
+
+
 class Step(object):
     """Device-side state + one pass of the hot path through the public API.  Every list keeps its capacity (batch * RoIs per
     image) with its length on the device, so the step has fixed shapes and no host read."""
 
-    def __init__(self, wl, device, world, seed):
+    def __init__(self, wl, device, world, seed, ot_grad_allreduce=False):
         import feature_intertwiner_b200 as fi
         self.fi, self.wl, self.dev, self.world = fi, wl, device, world
+        # The reference computes meta_loss ONCE, on GPU 0, from the gathered statistics (lib/model.py:143-144 "the loss is computed
+        # in GPU 0"; lib/workflow.py:191): OptTrans lives on one device and its gradients are never exchanged.  Sharded, every rank
+        # evaluates the same loss head on the same all-reduced totals, so every rank already holds the full, bit-identical OptTrans
+        # gradient (tests/test_dist_gpu.py) and the path needs ONE exchange, the class statistics.  ot_grad_allreduce=True adds
+        # what wrapping OptTrans in DistributedDataParallel would do anyway (a 15.7 MB all-reduce of identical values, overlapped
+        # with the RoIAlign backward) -- reported as a variant, not needed for the result.
+        self.ot_grad_allreduce = bool(ot_grad_allreduce) and world > 1
         self.spatial_sort = os.environ.get("FI_SPATIAL_SORT", "1") != "0"
         self.cfg = build_config(wl)
         torch.manual_seed(2000)
@@ -292,9 +325,9 @@ class Step(object):
         # level (7x7 + 14x14, the latter with two gradient sources) and big at no more than three (14x14)
         self.max_entries = total * (4 * 49 + 8 * 196 + 12 * 196 + 32 * 11)
         self.grad_bucket = None
-        if world > 1:
+        if self.ot_grad_allreduce:
             from feature_intertwiner_b200.dist import GradAllReduce
-            self.grad_bucket = GradAllReduce(self.ot.parameters())
+            self.grad_bucket = GradAllReduce(self.ot.parameters(), peer=PEER.get("grads"))
         self.graph, self.graph_loss, self.graph_error = None, None, None
         self.launches_per_step = None
 
@@ -386,7 +419,7 @@ class Step(object):
         st = self.forward_part(inp)
         loss = self.loss_mod(st["feat_in"]).sum()
         torch.autograd.backward([loss] + st["heads"], [torch.ones_like(loss)] + st["head_grads"])
-        if self.world > 1:
+        if self.ot_grad_allreduce:
             # gradient all-reduce of the path's own parameters (OptTrans, 15.7 MB): started by a hook as soon as the loss head's
             # backward has produced them, i.e. overlapped with the RoIAlign backward that follows it on the compute stream
             if self.grad_bucket is not None:
@@ -414,11 +447,20 @@ class Step(object):
             with torch.cuda.graph(graph):
                 self.graph_loss = self.run()
             self.launches_per_step = int(lib.fi_kernel_launches() - n0)
-            graph.replay()
-            torch.cuda.synchronize(self.dev)
             self.graph = graph
         except Exception as exc:            # noqa: BLE001 -- capture is an optimisation: fall back to launch-by-launch
             self.graph, self.graph_error = None, repr(exc)[:300]
+        torch.cuda.synchronize(self.dev)
+        if self.world > 1:
+            # every rank replays or none does: the peer all-reduce kernels inside the graph must stay matched
+            import torch.distributed as dist
+            flag = torch.tensor([1 if self.graph is not None else 0], device=self.dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                self.graph = None
+                self.graph_error = self.graph_error or "capture failed on another rank"
+        if self.graph is not None:
+            self.graph.replay()
             torch.cuda.synchronize(self.dev)
         return self.graph is not None
 
@@ -490,7 +532,7 @@ class Step(object):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)                 # every rank or none: the collectives must stay matched
         if int(flag.item()) == 0:
             self.seg = None
-            if self.grad_bucket is None:
+            if self.grad_bucket is None and self.ot_grad_allreduce:
                 from feature_intertwiner_b200.dist import GradAllReduce
                 self.grad_bucket = GradAllReduce(self.ot.parameters())
             return False
@@ -504,9 +546,10 @@ class Step(object):
         gA.replay()
         dist.all_reduce(self.seg_packed)                            # class statistics of both sets, one collective (1.3 MB)
         gB.replay()
-        work = dist.all_reduce(self.seg_flat, async_op=True)        # OptTrans gradients (15.7 MB): overlaps graph C
+        work = dist.all_reduce(self.seg_flat, async_op=True) if self.ot_grad_allreduce else None   # OptTrans gradients (15.7 MB): overlaps graph C
         gC.replay()
-        work.wait()
+        if work is not None:
+            work.wait()
         return self.graph_loss
 
     def step(self):
@@ -554,7 +597,7 @@ class CriticStep(object):
 class Timer(object):
     def __init__(self, dev, world, lib, flush):
         self.dev, self.world, self.lib, self.flush = dev, world, lib, flush
-        self.host_s, self.per_step, self.launches = 0.0, [], 0
+        self.host_s, self.per_step, self.launches, self.by_rank = 0.0, [], 0, []
 
     def barrier(self):
         if self.world > 1:
@@ -591,8 +634,12 @@ class Timer(object):
         self.per_step = [a.elapsed_time(b) for a, b in evs]
         ms = sum(self.per_step)
         t = torch.tensor([ms], device=self.dev, dtype=torch.float64)
+        self.by_rank = [ms / steps]
         if self.world > 1:
             import torch.distributed as dist
+            every = [torch.empty_like(t) for _ in range(self.world)]
+            dist.all_gather(every, t)
+            self.by_rank = [round(float(v.item()) / steps, 4) for v in every]
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()) / steps
 
@@ -615,16 +662,17 @@ def kernel_families(fi, step, timer, steps, peak):
     return out, ms
 
 
-def measure_workload(name, wl, dev, rank, world, args, lib, flush, full):
+def measure_workload(name, wl, dev, rank, world, args, lib, flush, full, ot_grad_allreduce=None):
     """One workload: device-resident value (graph or eager), e2e, loss-only, kernel families.  `full`: all legs; else value only."""
     import feature_intertwiner_b200 as fi
     timer = Timer(dev, world, lib, flush)
-    step = Step(wl, dev, world, seed=2000 + rank)
-    graphed = args.mode == "graph" and (step.capture() if world == 1 else step.capture_segmented())
+    step = Step(wl, dev, world, seed=2000 + rank, ot_grad_allreduce=args.ddp_ot_grads if ot_grad_allreduce is None else ot_grad_allreduce)
+    graphed = args.mode == "graph" and (step.capture() if (world == 1 or "stats" in PEER) else step.capture_segmented())
     ms = timer(step.step, args.steps if full else max(3, args.steps // 2), args.warmup)
     res = {"ms_per_step": ms, "value": wl["batch"] * wl["rois_per_image"] * world / (ms / 1e3), "graphed": graphed,
            "host_enqueue_ms_per_step": 1e3 * timer.host_s / (args.steps if full else max(3, args.steps // 2)),
-           "ms_each_step": [round(v, 3) for v in timer.per_step], "counts": step.counts, "graph_error": step.graph_error}
+           "ms_each_step": [round(v, 3) for v in timer.per_step], "counts": step.counts, "graph_error": step.graph_error,
+           "ms_per_step_by_rank": timer.by_rank}
     res["launches_in_region"] = int(timer.launches)
     res["launches_per_step"] = step.launches_per_step if graphed else timer.launches / max(1, len(timer.per_step))
     if not full:
@@ -646,6 +694,7 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.lib()
+    peer_on = setup_peer_allreduce(dev, world)
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)    # 256 MB > 126 MB L2 (inputs alone are > 3 GB anyway)
     wl = dict(synth.WORKLOADS[args.workload])
     peak, peak_kind = measured_peak()
@@ -687,10 +736,19 @@ def run_ours(args):
         t_small = timer(ar_small, 20, 5)
         t_big = timer(ar_big, 10, 3)
         f = 2.0 * (world - 1) / world
-        nvlink = {"class_stats_allreduce": {"bytes": buf.numel() * 4, "ms": t_small, "bus_gbs": f * buf.numel() * 4 / t_small / 1e6},
-                  "allreduce_256MB": {"bytes": big.numel() * 4, "ms": t_big, "bus_gbs": f * big.numel() * 4 / t_big / 1e6},
+        nvlink = {"class_stats_allreduce_nccl": {"bytes": buf.numel() * 4, "ms": t_small, "bus_gbs": f * buf.numel() * 4 / t_small / 1e6},
+                  "allreduce_256MB_nccl": {"bytes": big.numel() * 4, "ms": t_big, "bus_gbs": f * big.numel() * 4 / t_big / 1e6},
                   "nvlink_peak_gbs_per_direction": 900.0, "measured_reference_bus_gbs_8rank_1GiB": 725.0}
         del big
+        if peer_on:
+            # the same two exchanges through csrc/peer_allreduce.cu (one-shot: every rank READS (world-1) x bytes over NVLink)
+            gbuf = torch.zeros(PEER["grads"].capacity, device=dev)
+            t_ps = timer(lambda: PEER["stats"](buf), 20, 5)
+            t_pg = timer(lambda: PEER["grads"](gbuf), 20, 5)
+            nvlink["class_stats_allreduce_peer_kernel"] = {"bytes": buf.numel() * 4, "ms": t_ps, "nvlink_read_gbs_per_rank": (world - 1) * buf.numel() * 4 / t_ps / 1e6}
+            nvlink["ot_gradients_allreduce_peer_kernel"] = {"bytes": gbuf.numel() * 4, "ms": t_pg, "nvlink_read_gbs_per_rank": (world - 1) * gbuf.numel() * 4 / t_pg / 1e6}
+            nvlink["peer_kernel_timeouts"] = bool(PEER["stats"].error() or PEER["grads"].error())
+            del gbuf
     # loss value of the last step against the CPU port on the same class statistics (north_star: loss within 1e-4)
     stats = [t.detach().cpu() for t in step.last_feat_in]
     ot_state = {k: v.detach().cpu() for k, v in step.ot.state_dict().items()}
@@ -709,6 +767,14 @@ def run_ours(args):
             others[name] = {"workload": workload_name(name, synth.WORKLOADS[name]), "value": r["value"], "unit": "RoIs/s", "ms_per_step": r["ms_per_step"],
                             "graphed": r["graphed"], "small_counts": r["counts"][0], "big_counts": r["counts"][1], "steps": len(r["ms_each_step"])}
 
+    variants = {}
+    if world > 1 and not args.ddp_ot_grads and not args.no_other_workloads:
+        r, _ = measure_workload(args.workload, wl, dev, rank, world, args, lib, flush, full=False, ot_grad_allreduce=True)
+        variants["with_ddp_style_ot_gradient_allreduce"] = {
+            "ms_per_step": r["ms_per_step"], "value": r["value"], "unit": "RoIs/s", "graphed": r["graphed"],
+            "what": "the same step + a 15.7 MB all-reduce of the OptTrans gradients on a side branch under the RoIAlign backward (what wrapping "
+                    "OptTrans in DistributedDataParallel adds; the values are identical on every rank, the reference never exchanges them)"}
+    peer_timeouts = bool(peer_on and (PEER["stats"].error() or PEER["grads"].error()))
     rois_per_step = wl["batch"] * wl["rois_per_image"] * world
     if world > 1:
         import torch.distributed as dist
@@ -750,7 +816,9 @@ def run_ours(args):
                    "layout": "channels_last maps/crops (logical NCHW)", "ot": "all 80 foreground classes, absent ones masked (fixed shapes, no host sync)",
                    "roi_order": "spatially sorted per image (L2 reuse)" if os.environ.get("FI_SPATIAL_SORT", "1") != "0" else "index order",
                    "step": (("ONE CUDA graph replay per step (whole step: split, crops, list building on a side stream, class means, loss head, backward)"
-                             if world == 1 else "three CUDA graph replays per step (forward part | loss head fwd+bwd | backward part) with the two NCCL "
+                             if world == 1 else "ONE CUDA graph replay per step on every rank; the exchange of the class statistics is this library's peer-memory all-reduce "
+                             "kernel over NVLink (csrc/peer_allreduce.cu), inside the graph"
+                             if peer_on else "three CUDA graph replays per step (forward part | loss head fwd+bwd | backward part) with the two NCCL "
                              "all-reduces (class statistics; OptTrans gradients, overlapped with the backward graph) eager between them")
                             if res["graphed"] else "eager, launch by launch" + (" (graph capture failed: %s)" % res["graph_error"] if res["graph_error"] else "")),
                    "list_lengths": "kept on the device (fixed-capacity lists): the step has no device->host read",
@@ -771,6 +839,14 @@ def run_ours(args):
     }
     if nvlink:
         out["nvlink"] = nvlink
+    if world > 1:
+        out["ms_per_step_by_rank"] = res["ms_per_step_by_rank"]
+        out["exchange"] = {"class_statistics": "peer-memory all-reduce kernel (csrc/peer_allreduce.cu), inside the step's graph" if peer_on
+                           else "NCCL all-reduce between the graphs (%s)" % PEER.get("why", "FI_PEER_ALLREDUCE=0"),
+                           "ot_gradients": "all-reduced every step (--ddp-ot-grads)" if args.ddp_ot_grads else
+                           "not exchanged: every rank computes the same loss head on the same totals (the reference computes it on GPU 0 only, lib/model.py:143-144)",
+                           "peer_kernel_timeouts": peer_timeouts}
+        out["variants"] = variants
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_reference(wl, seed=2000, budget_s=args.cpu_budget, stats=stats, ot_state=ot_state)
         cpu_loss = out["cpu_baseline"].pop("loss_vector", None)
@@ -947,6 +1023,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="graph", choices=["graph", "eager"])
     ap.add_argument("--with-critic", action="store_true", help="a5-inclusive variant: fi.Dev.forward + fi.IntertwinerLoss called directly")
+    ap.add_argument("--ddp-ot-grads", action="store_true", help="several ranks: also all-reduce the (identical) OptTrans gradients every step, as "
+                    "DistributedDataParallel would; default: measured as a variant next to the headline")
     ap.add_argument("--no-other-workloads", action="store_true", help="skip the short c1 / c3 / c5 measurements")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")

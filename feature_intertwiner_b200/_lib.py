@@ -65,6 +65,14 @@ SIGNATURES = {
     "fi_roi_pool_backward": (_I, [_P, _F, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "fi_roi_pool_forward_nhwc": (_I, [_P, _F, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "fi_roi_pool_backward_nhwc": (_I, [_P, _F, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "fi_peer_region_bytes": (C.c_size_t, [C.c_size_t]),
+    "fi_peer_region_alloc": (_I, [C.c_size_t, _P]),
+    "fi_peer_region_free": (_I, [_P]),
+    "fi_peer_region_export": (_I, [_P, _P]),
+    "fi_peer_region_import": (_I, [_P, _P]),
+    "fi_peer_region_release": (_I, [_P]),
+    "fi_peer_error": (_I, [_P, _P]),
+    "fi_peer_allreduce_sum": (_I, [_P, _P, C.c_size_t, _I, _I, _P, C.c_size_t, _P]),
 }
 
 

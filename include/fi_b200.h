@@ -355,6 +355,27 @@ int fi_roi_pool_forward_nhwc(const float *bottom, float spatial_scale, int batch
 int fi_roi_pool_backward_nhwc(const float *top_diff, float spatial_scale, int batch, int num_rois, int height, int width, int channels,
                               int pooled_h, int pooled_w, const float *rois, float *bottom_diff, const int *argmax, cudaStream_t stream);
 
+/* ---- the exchange step over NVLink / NVSwitch peer memory (one process per GPU) -------------------------------------------
+ * Replaces the gather of nn.DataParallel + _merge_feat_vec's reduction over the gpu axis (lib/model.py:217-224, 394-402;
+ * tools/utils.py:645-654): an all-reduce(SUM) of fp32 values as ONE kernel per rank that reads every peer's copy through
+ * peer-mapped memory and adds in rank order (bit-identical totals on every rank).  Capturable in a CUDA graph: the call counter
+ * lives on the device.  Set-up: every rank allocates a region, exports its handle, the host side exchanges the handles
+ * (any transport: torch.distributed, MPI, a file) and imports the peers' ones; `regions[r]` = rank r's region as mapped in THIS
+ * process (regions[rank] = the pointer fi_peer_region_alloc returned).  All ranks must make the same sequence of calls on one
+ * set of regions; `n` may vary per call up to the capacity.  A peer that does not arrive within 4 s sets the error word read by
+ * fi_peer_error instead of hanging the device. */
+#define FI_PEER_MAX_WORLD 16
+#define FI_PEER_HANDLE_BYTES 64
+size_t fi_peer_region_bytes(size_t capacity_floats);
+int fi_peer_region_alloc(size_t capacity_floats, void **region);
+int fi_peer_region_free(void *region);
+int fi_peer_region_export(void *region, unsigned char handle[FI_PEER_HANDLE_BYTES]);
+int fi_peer_region_import(const unsigned char handle[FI_PEER_HANDLE_BYTES], void **region);
+int fi_peer_region_release(void *imported);
+int fi_peer_error(void *own_region, int *error);
+int fi_peer_allreduce_sum(const float *in, float *out, size_t n, int rank, int world, void *const *regions, size_t capacity_floats,
+                          cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
