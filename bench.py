@@ -276,7 +276,8 @@ class Step(object):
         # The reference computes meta_loss ONCE, on GPU 0, from the gathered statistics (lib/model.py:143-144 "the loss is computed
         # in GPU 0"; lib/workflow.py:191): OptTrans lives on one device and its gradients are never exchanged.  Sharded, every rank
         # evaluates the same loss head on the same all-reduced totals, so every rank already holds the full, bit-identical OptTrans
-        # gradient (tests/test_dist_gpu.py) and the path needs ONE exchange, the class statistics.  ot_grad_allreduce=True adds
+        # gradient (tests/test_dist_gpu.py; with one position per row the cosine cost is a sign, so that gradient is in fact
+        # exactly zero: tools/diag_ot_identity.py) and the path needs ONE exchange, the class statistics.  ot_grad_allreduce=True adds
         # what wrapping OptTrans in DistributedDataParallel would do anyway (a 15.7 MB all-reduce of identical values, overlapped
         # with the RoIAlign backward) -- reported as a variant, not needed for the result.
         self.ot_grad_allreduce = bool(ot_grad_allreduce) and world > 1
@@ -826,7 +827,9 @@ def run_ours(args):
                    "l2": "GB-class working set per step (> 126 MB L2) + 256 MB flush write between steps", "gc": "python cyclic GC collected before and disabled during the timed steps",
                    "small_counts": res["counts"][0], "big_counts": res["counts"][1], "parallelism": "dp%d by image batch" % world},
         "e2e": {"value": rois_per_step / (ms_e2e / 1e3), "unit": "RoIs/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "host_buffers": "pinned, first-touched on the GPU's NUMA node: %s" % (numa,)},
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "h2d_gbs_per_gpu": h2d_bytes / (ms_e2e - ms) / 1e6,
+                "bound": "the host->device copies (PCIe Gen5 x16: ~55 GB/s per GPU in practice); the step itself is %.1f %% of the e2e time" % (100.0 * ms / ms_e2e),
+                "host_buffers": "pinned, first-touched on the GPU's NUMA node: %s" % (numa,)},
         "intertwiner_loss": {"ms_per_iter": ms_loss, "what": "statistics merge -> buffer update -> class match -> OptTrans / Sinkhorn(L=%d), "
                              "%d classes, forward + backward, device-timed alone (it is also inside every step above)" % (wl["sinkhorn_iters"], NCLS - 1),
                              "gpu_vs_cpu_port_abs_diff": None},

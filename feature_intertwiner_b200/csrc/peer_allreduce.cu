@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_kernel(const Peer
 
 static int peer_grid(size_t cap) {          // a function of the regions' capacity alone: equal on all ranks and for every call
     const size_t n4 = cap / 4;
-    size_t g = (n4 + 2 * kPeerThreads - 1) / (2 * kPeerThreads);              // >= 2 float4 per thread and rank
+    size_t g = (n4 + kPeerThreads - 1) / kPeerThreads;                        // one float4 per thread and rank, up to kPeerMaxCtas CTAs
     if (g < 1) g = 1;
     if (g > (size_t)kPeerMaxCtas) g = kPeerMaxCtas;
     return (int)g;

