@@ -328,7 +328,7 @@ class Step(object):
         self.grad_bucket = None
         if self.ot_grad_allreduce:
             from feature_intertwiner_b200.dist import GradAllReduce
-            self.grad_bucket = GradAllReduce(self.ot.parameters(), peer=PEER.get("grads"))
+            self.grad_bucket = GradAllReduce(self.ot.parameters())
         self.graph, self.graph_loss, self.graph_error = None, None, None
         self.launches_per_step = None
 
@@ -543,9 +543,10 @@ class Step(object):
 
     def step_segmented(self):
         import torch.distributed as dist
+        from feature_intertwiner_b200.dist import all_reduce_sum_
         gA, gB, gC = self.seg
         gA.replay()
-        dist.all_reduce(self.seg_packed)                            # class statistics of both sets, one collective (1.3 MB)
+        all_reduce_sum_(self.seg_packed)                            # class statistics of both sets, one collective (0.66 MB)
         gB.replay()
         work = dist.all_reduce(self.seg_flat, async_op=True) if self.ot_grad_allreduce else None   # OptTrans gradients (15.7 MB): overlaps graph C
         gC.replay()
@@ -609,7 +610,7 @@ class Timer(object):
     def __call__(self, fn, steps, warmup):
         for _ in range(warmup):
             fn()
-        self.barrier()
+        torch.cuda.synchronize()
         # the cyclic collector of a process with torch loaded walks millions of objects: a generation-2 pass landing inside a
         # 2 ms step shows up as a 6-60 ms step.  Collect now, keep it off for the K timed steps (training loops do the same with
         # gc.freeze / a manual collection between iterations).
@@ -619,7 +620,9 @@ class Timer(object):
         pool = [torch.cuda.Event(enable_timing=True) for _ in range(2 * steps)]     # created and first-recorded outside the timed steps
         for ev in pool:
             ev.record()
-        torch.cuda.synchronize()
+        # barrier + synchronize LAST, right before the first timed step: the collection above takes tens of ms and a different
+        # time on every rank -- with the barrier in front of it the first step of the early ranks timed their wait for the late ones
+        self.barrier()
         self.host_s = 0.0
         launch0 = self.lib.fi_kernel_launches()
         for _ in range(steps):
@@ -668,7 +671,10 @@ def measure_workload(name, wl, dev, rank, world, args, lib, flush, full, ot_grad
     import feature_intertwiner_b200 as fi
     timer = Timer(dev, world, lib, flush)
     step = Step(wl, dev, world, seed=2000 + rank, ot_grad_allreduce=args.ddp_ot_grads if ot_grad_allreduce is None else ot_grad_allreduce)
-    graphed = args.mode == "graph" and (step.capture() if (world == 1 or "stats" in PEER) else step.capture_segmented())
+    # several ranks: one graph when the exchange is the peer-memory kernel; NCCL (no peer mapping, or the DDP-style gradient
+    # all-reduce variant, where NCCL's ring beats a one-shot read of 8 x 15.7 MB) stays outside captures: three graphs
+    one_graph = world == 1 or ("stats" in PEER and not step.ot_grad_allreduce)
+    graphed = args.mode == "graph" and (step.capture() if one_graph else step.capture_segmented())
     ms = timer(step.step, args.steps if full else max(3, args.steps // 2), args.warmup)
     res = {"ms_per_step": ms, "value": wl["batch"] * wl["rois_per_image"] * world / (ms / 1e3), "graphed": graphed,
            "host_enqueue_ms_per_step": 1e3 * timer.host_s / (args.steps if full else max(3, args.steps // 2)),
@@ -773,8 +779,8 @@ def run_ours(args):
         r, _ = measure_workload(args.workload, wl, dev, rank, world, args, lib, flush, full=False, ot_grad_allreduce=True)
         variants["with_ddp_style_ot_gradient_allreduce"] = {
             "ms_per_step": r["ms_per_step"], "value": r["value"], "unit": "RoIs/s", "graphed": r["graphed"],
-            "what": "the same step + a 15.7 MB all-reduce of the OptTrans gradients on a side branch under the RoIAlign backward (what wrapping "
-                    "OptTrans in DistributedDataParallel adds; the values are identical on every rank, the reference never exchanges them)"}
+            "what": "the same step as three graphs + an async NCCL all-reduce of the OptTrans gradients (15.7 MB) under the RoIAlign backward graph "
+                    "(what wrapping OptTrans in DistributedDataParallel adds; the values are identical on every rank, the reference never exchanges them)"}
     peer_timeouts = bool(peer_on and (PEER["stats"].error() or PEER["grads"].error()))
     rois_per_step = wl["batch"] * wl["rois_per_image"] * world
     if world > 1:

@@ -43,6 +43,9 @@ struct SinkParams {
     int masked;                // only problems whose loss slot holds NaN are solved (the others were done by the D = 1 class kernel)
     float *pbuf;               // null, or [P, N*N + 2N]: the plan P and the row norms go here and the gradient is left to
                                // sinkhorn_grad_raw_kernel / sinkhorn_grad_chain_kernel (large D: one CTA per problem cannot feed it)
+    const float *nbuf;         // null, or the same [P, N*N + 2N] block with the row norms ALREADY in its tail (sinkhorn_norm_kernel)
+    const float *gram;         // null, or [P, S, N, N]: x^ y^T summed over S slices of D by sinkhorn_gram_split_kernel
+    int S;
 };
 
 __host__ __device__ inline int round4(int v) { return (v + 3) & ~3; }
@@ -78,30 +81,46 @@ __device__ __forceinline__ float warp_sum(float v) {
 // x rows are this CTA's local rows; operands are normalised on load with a true division, exactly as the
 // reference normalises before its mm (OT_module.py:111-113).
 __device__ __forceinline__ void gram_tile(const float *__restrict__ xp, const float *__restrict__ yp, int N, int D, int row0g, int nrows,
-                                          int ti, int tj, const float *denx, const float *deny, float *xs, float *ys, float acc[4][4]) {
+                                          int ti, int tj, const float *denx, const float *deny, float *xs, float *ys, float acc[4][4],
+                                          int d_begin = 0, int d_end = -1) {
+    if (d_end < 0) d_end = D;
     const int t = threadIdx.x;
     const int tx = t & 15, ty = t >> 4;
 #pragma unroll
     for (int u = 0; u < 4; ++u)
 #pragma unroll
         for (int v = 0; v < 4; ++v) acc[u][v] = 0.f;
-    for (int d0 = 0; d0 < D; d0 += kDT) {
+    // software pipeline: the global loads of chunk k+1 are in flight while chunk k is multiplied (one CTA walks its share of D
+    // alone -- without this every chunk paid a full DRAM round trip before its FMAs could start)
+    constexpr int kPer = (kTile * kDT) / kSinkThreads;
+    float xr[kPer], yr[kPer];
+    auto fetch = [&](int d0) {
 #pragma unroll
-        for (int k = 0; k < (kTile * kDT) / kSinkThreads; ++k) {
+        for (int k = 0; k < kPer; ++k) {
             const int e = t + k * kSinkThreads;
             const int dd = e % kDT, r = e / kDT;
             const int d = d0 + dd;
             const int il = ti * kTile + r;          // local x row
             const int j = tj * kTile + r;           // y row (= column of K)
-            float xv = 0.f, yv = 0.f;
-            if (d < D) {
-                if (il < nrows) xv = __fdiv_rn(__ldg(xp + (long)(row0g + il) * D + d), denx[il]);
-                if (j < N) yv = __fdiv_rn(__ldg(yp + (long)j * D + d), deny[j]);
+            xr[k] = 0.f; yr[k] = 0.f;
+            if (d < d_end) {
+                if (il < nrows) xr[k] = __ldg(xp + (long)(row0g + il) * D + d);
+                if (j < N) yr[k] = __ldg(yp + (long)j * D + d);
             }
-            xs[dd * kTile + r] = xv;
-            ys[dd * kTile + r] = yv;
+        }
+    };
+    if (d_begin < d_end) fetch(d_begin);
+    for (int d0 = d_begin; d0 < d_end; d0 += kDT) {
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            const int e = t + k * kSinkThreads;
+            const int dd = e % kDT, r = e / kDT;
+            const int il = ti * kTile + r, j = tj * kTile + r;
+            xs[dd * kTile + r] = il < nrows ? __fdiv_rn(xr[k], denx[il]) : 0.f;
+            ys[dd * kTile + r] = j < N ? __fdiv_rn(yr[k], deny[j]) : 0.f;
         }
         __syncthreads();
+        if (d0 + kDT < d_end) fetch(d0 + kDT);
 #pragma unroll
         for (int dd = 0; dd < kDT; ++dd) {
             const float4 a4 = *reinterpret_cast<const float4 *>(xs + dd * kTile + ty * 4);
@@ -144,6 +163,10 @@ __global__ void __launch_bounds__(kSinkThreads) sinkhorn_kernel(const SinkParams
     const float *yp = p.y + (long)prob * N * D;
 
     // ---- phase 0: row norms (warp per row; OT_module.py:111-112), stored as (norm + EPS) -------------
+    if (p.nbuf != nullptr) {                                      // large D (CS == 1): done by sinkhorn_norm_kernel, same bits
+        const float *w = p.nbuf + (long)prob * ((long)N * N + 2 * N) + (long)N * N;
+        for (int e = t; e < N; e += kSinkThreads) { denx[e] = w[e]; deny[e] = w[N + e]; }
+    } else
     for (int q = wid; q < nrows + N; q += kSinkThreads / 32) {
         const float *src = q < nrows ? xp + (long)(row0g + q) * D : yp + (long)(q - nrows) * D;
         float s = 0.f;
@@ -158,6 +181,17 @@ __global__ void __launch_bounds__(kSinkThreads) sinkhorn_kernel(const SinkParams
 
     // ---- phase 1: C = 1 - x^ y^T,  K = exp(-C / eps)   (OT_module.py:113,116) ------------------------
     const int tx = t & 15, ty = t >> 4;
+    if (p.gram != nullptr) {                                      // the D-slices of sinkhorn_gram_split_kernel, added in slice order
+        const float *g = p.gram + (long)prob * p.S * N * N;
+        for (int e = t; e < N * N; e += kSinkThreads) {
+            float acc = g[e];
+            for (int sl = 1; sl < p.S; ++sl) acc = __fadd_rn(acc, g[(long)sl * N * N + e]);
+            const int il = e / N, j = e - il * N;
+            const float c = __fsub_rn(1.f, acc);
+            Ks[il * pitch + j] = expf(-p.inv_eps * c);
+            Cs[il * pitch + j] = c;                                // keepC is a precondition of this form (host)
+        }
+    } else
     for (int ti = 0; ti * kTile < nrows; ++ti)
         for (int tj = 0; tj * kTile < N; ++tj) {
             float acc[4][4];
@@ -314,6 +348,48 @@ __global__ void __launch_bounds__(kSinkThreads) sinkhorn_kernel(const SinkParams
 }
 
 // ------------------------------------------------------------------------------------------------
+// Cost matrix for large D (the FPN-level loss: N = 64, D = (s/4)^2 up to 4096, lib/sub_module.py:179-213).  Inside the solver
+// kernel ONE CTA per problem walks all of D for its 64x64 tile: 24 CTAs on 148 SMs, 0.7 ms for 24 problems at D = 4096 where
+// the 48 MB of operands are a 10 us read.  So for D >= 128 the two D-long passes leave the solver:
+//   sinkhorn_norm_kernel        warp per row: |row| + EPS into the workspace (the solver's own summation order: same bits);
+//   sinkhorn_gram_split_kernel  CTA = (problem, slice of D, 64x64 tile): the slice's share of x^ y^T (fp32 FMA, operands
+//                               normalised on load as the reference does before its mm, OT_module.py:111-113);
+// and the solver adds the S slices in order.  Deterministic; differs from the one-CTA form only in the summation order over D.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sinkhorn_norm_kernel(const float *__restrict__ x, const float *__restrict__ y, float *__restrict__ nbuf, int P,
+                                                           int N, int D) {
+    const int lane = threadIdx.x & 31;
+    const long row = blockIdx.x * 8L + (threadIdx.x >> 5);
+    if (row >= 2L * P * N) return;
+    const int prob = (int)(row / (2 * N)), q = (int)(row - (long)prob * 2 * N);
+    const float *src = (q < N ? x : y) + ((long)prob * N + (q < N ? q : q - N)) * D;
+    float s = 0.f;
+#pragma unroll 8
+    for (int d = lane; d < D; d += 32) { const float v = __ldg(src + d); s = fmaf(v, v, s); }
+    s = warp_sum(s);
+    if (lane == 0) nbuf[(long)prob * ((long)N * N + 2 * N) + (long)N * N + q] = __fadd_rn(sqrtf(s), kEps);
+}
+
+__global__ void __launch_bounds__(kSinkThreads) sinkhorn_gram_split_kernel(const float *__restrict__ x, const float *__restrict__ y,
+                                                                          const float *__restrict__ nbuf, float *__restrict__ gram, int N, int D,
+                                                                          int S, int Dc) {
+    __shared__ __align__(16) float xs[kDT * kTile], ys[kDT * kTile];
+    const int prob = blockIdx.x, sl = blockIdx.y;
+    const int tiles = (N + kTile - 1) / kTile, ti = blockIdx.z / tiles, tj = blockIdx.z % tiles;
+    const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+    const float *den = nbuf + (long)prob * ((long)N * N + 2 * N) + (long)N * N;
+    float acc[4][4];
+    const int d0 = sl * Dc, d1 = min(D, d0 + Dc);
+    gram_tile(x + (long)prob * N * D, y + (long)prob * N * D, N, D, 0, N, ti, tj, den, den + N, xs, ys, acc, d0, d1);
+    float *g = gram + ((long)prob * S + sl) * N * N;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int il = ti * kTile + ty * 4 + u, j = tj * kTile + tx * 4;
+        if (il < N && j < N) *reinterpret_cast<float4 *>(g + (long)il * N + j) = make_float4(acc[u][0], acc[u][1], acc[u][2], acc[u][3]);   // N % 4 == 0
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Gradient for large D (the FPN-level loss: N = 64, D = (s/4)^2 up to 4096, lib/sub_module.py:179-213).  Inside the solver
 // kernel one CTA per problem walks N*D outputs with an N-term sum each -- 24 CTAs on 148 SMs, 28 ms for 24 problems at
 // D = 4096.  The plan P (N x N) is tiny, so it is handed over through global memory and the two products
@@ -322,31 +398,22 @@ __global__ void __launch_bounds__(kSinkThreads) sinkhorn_kernel(const SinkParams
 // thread = (column d, quarter of the rows), the same ascending summation order as the in-kernel form (identical bits).
 // A second launch (warp per row) applies the chain through the row normalisation, which needs the full-row dot product.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) sinkhorn_grad_raw_kernel(const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ pbuf,
-                                                               float *__restrict__ gx, float *__restrict__ gy, int N, int D) {
-    extern __shared__ __align__(16) float sm[];
-    float *Ps = sm, *denx = sm + N * N, *deny = denx + N;
-    const int prob = blockIdx.x, t = threadIdx.x;
-    const float *w = pbuf + (long)prob * ((long)N * N + 2 * N);
-    for (int e = t; e < N * N + 2 * N; e += 256) sm[e] = w[e];
-    __syncthreads();
-    const int d = blockIdx.y * 64 + (t & 63);
-    const int q = t >> 6;                                   // quarter of the rows (gx) / columns (gy): 4 * ceil(N / 16) each
-    const int per = ((N + 15) / 16) * 4, r0 = q * per;
-    if (d >= D) return;
-    const float *xp = x + (long)prob * N * D + d, *yp = y + (long)prob * N * D + d;
-    float *gxp = gx + (long)prob * N * D + d, *gyp = gy + (long)prob * N * D + d;
-    float acc[32];
+// The two products for one column d and PER rows / columns starting at r0 (compile-time PER: a run-time bound on the unrolled
+// accumulators is predication, and predicated-off FFMAs still issue -- ncu: twice the useful FFMA count at N = 64).
+template <int PER, bool RAGGED>
+__device__ __forceinline__ void grad_raw_products(const float *Ps, const float *xt, const float *yt, float *gxp, float *gyp, int N, int D, int r0,
+                                                  int c) {
+    float acc[PER];
     // g~x[i][d] = -sum_j P[i][j] y^[j][d]
 #pragma unroll
-    for (int r = 0; r < 32; ++r) acc[r] = 0.f;
+    for (int r = 0; r < PER; ++r) acc[r] = 0.f;
     for (int j = 0; j < N; j += 4) {
         float yv[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) yv[u] = __fdiv_rn(__ldg(yp + (long)(j + u) * D), deny[j + u]);
+        for (int u = 0; u < 4; ++u) yv[u] = yt[(j + u) * 64 + c];
 #pragma unroll
-        for (int r = 0; r < 32; ++r) {
-            if (r < per && r0 + r < N) {
+        for (int r = 0; r < PER; ++r) {
+            if (!RAGGED || r0 + r < N) {
                 const float4 pv = *reinterpret_cast<const float4 *>(Ps + (r0 + r) * N + j);
                 acc[r] = fmaf(pv.x, yv[0], acc[r]); acc[r] = fmaf(pv.y, yv[1], acc[r]);
                 acc[r] = fmaf(pv.z, yv[2], acc[r]); acc[r] = fmaf(pv.w, yv[3], acc[r]);
@@ -354,16 +421,16 @@ __global__ void __launch_bounds__(256) sinkhorn_grad_raw_kernel(const float *__r
         }
     }
 #pragma unroll
-    for (int r = 0; r < 32; ++r)
-        if (r < per && r0 + r < N) gxp[(long)(r0 + r) * D] = -acc[r];
+    for (int r = 0; r < PER; ++r)
+        if (!RAGGED || r0 + r < N) gxp[(long)(r0 + r) * D] = -acc[r];
     // g~y[j][d] = -sum_i P[i][j] x^[i][d]
 #pragma unroll
-    for (int r = 0; r < 32; ++r) acc[r] = 0.f;
+    for (int r = 0; r < PER; ++r) acc[r] = 0.f;
     for (int i = 0; i < N; ++i) {
-        const float xv = __fdiv_rn(__ldg(xp + (long)i * D), denx[i]);
+        const float xv = xt[i * 64 + c];
 #pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-            if (4 * c4 < per && r0 + 4 * c4 < N) {
+        for (int c4 = 0; c4 < PER / 4; ++c4) {
+            if (!RAGGED || r0 + 4 * c4 < N) {                              // N % 4 == 0: a float4 of columns is all in or all out
                 const float4 pv = *reinterpret_cast<const float4 *>(Ps + i * N + r0 + 4 * c4);
                 acc[4 * c4 + 0] = fmaf(pv.x, xv, acc[4 * c4 + 0]); acc[4 * c4 + 1] = fmaf(pv.y, xv, acc[4 * c4 + 1]);
                 acc[4 * c4 + 2] = fmaf(pv.z, xv, acc[4 * c4 + 2]); acc[4 * c4 + 3] = fmaf(pv.w, xv, acc[4 * c4 + 3]);
@@ -371,8 +438,40 @@ __global__ void __launch_bounds__(256) sinkhorn_grad_raw_kernel(const float *__r
         }
     }
 #pragma unroll
-    for (int r = 0; r < 32; ++r)
-        if (r < per && r0 + r < N) gyp[(long)(r0 + r) * D] = -acc[r];
+    for (int r = 0; r < PER; ++r)
+        if (!RAGGED || r0 + r < N) gyp[(long)(r0 + r) * D] = -acc[r];
+}
+
+template <int PER>
+__global__ void __launch_bounds__(256) sinkhorn_grad_raw_kernel(const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ pbuf,
+                                                               float *__restrict__ gx, float *__restrict__ gy, int N, int D) {
+    extern __shared__ __align__(16) float sm[];
+    float *Ps = sm, *denx = sm + N * N, *deny = denx + N;
+    float *xt = deny + N, *yt = xt + N * 64;                // the CTA's 64 columns of x^ and y^ (N x 64 each), normalised once
+    const int prob = blockIdx.y, chunk = blockIdx.x, t = threadIdx.x;   // chunk fastest: co-running CTAs read neighbouring 256 B pieces of the same rows
+    const float *w = pbuf + (long)prob * ((long)N * N + 2 * N);
+    for (int e = t; e < N * N + 2 * N; e += 256) sm[e] = w[e];
+    __syncthreads();
+    {
+        // all loads of the tile in flight at once: the loops below used to fetch one operand per iteration straight from
+        // global memory -- 64 dependent DRAM round trips per CTA, 0.5 ms for 24 problems at D = 4096
+        const float *xb = x + (long)prob * N * D + chunk * 64, *yb = y + (long)prob * N * D + chunk * 64;
+        const int c = t & 63, dcol = chunk * 64 + c;
+#pragma unroll 8
+        for (int r = t >> 6; r < N; r += 4) {
+            float xv = 0.f, yv = 0.f;
+            if (dcol < D) { xv = __ldg(xb + (long)r * D + c); yv = __ldg(yb + (long)r * D + c); }
+            xt[r * 64 + c] = __fdiv_rn(xv, denx[r]);
+            yt[r * 64 + c] = __fdiv_rn(yv, deny[r]);
+        }
+    }
+    __syncthreads();
+    const int c = t & 63, d = chunk * 64 + c;
+    const int r0 = (t >> 6) * PER;                          // quarter of the rows (gx) / columns (gy): PER = 4 * ceil(N / 16) each
+    if (d >= D || r0 >= N) return;
+    float *gxp = gx + (long)prob * N * D + d, *gyp = gy + (long)prob * N * D + d;
+    if (r0 + PER <= N) grad_raw_products<PER, false>(Ps, xt, yt, gxp, gyp, N, D, r0, c);
+    else grad_raw_products<PER, true>(Ps, xt, yt, gxp, gyp, N, D, r0, c);       // ragged last quarter (N % 16 != 0), warp-uniform
 }
 
 // warp per row (x rows then y rows of every problem): dL/dx = (g - x^ <x^, g> |x| / (|x| + EPS)) / (|x| + EPS)
@@ -388,12 +487,54 @@ __global__ void __launch_bounds__(256) sinkhorn_grad_chain_kernel(const float *_
     float *g = (isx ? gx : gy) + ((long)prob * N + i) * D;
     const float den = pbuf[(long)prob * ((long)N * N + 2 * N) + (long)N * N + (isx ? 0 : N) + i];
     float dot = 0.f;
+#pragma unroll 8
     for (int d = lane; d < D; d += 32) dot = fmaf(g[d], __fdiv_rn(__ldg(src + d), den), dot);
     dot = warp_sum(dot);
     const float shrink = __fdiv_rn(__fsub_rn(den, kEps), den);   // |x| / (|x| + EPS)
+#pragma unroll 8
     for (int d = lane; d < D; d += 32) {
         const float xh = __fdiv_rn(__ldg(src + d), den);
         g[d] = __fdiv_rn(__fsub_rn(g[d], __fmul_rn(__fmul_rn(xh, dot), shrink)), den);
+    }
+}
+
+// The same chain with one CTA per row and the row kept in registers (D <= 256 * kChainCache): one pass over memory, 16 loads in
+// flight per thread.  The warp-per-row form above has 0.4 waves of warps each waiting on its own DRAM round trips (ncu: 50
+// stalled-on-long-scoreboard warps per issue, 190 us for 24 problems at D = 4096).
+constexpr int kChainCache = 16;
+__global__ void __launch_bounds__(256) sinkhorn_grad_chain_rows_kernel(const float *__restrict__ x, const float *__restrict__ y,
+                                                                      const float *__restrict__ pbuf, float *__restrict__ gx, float *__restrict__ gy,
+                                                                      int P, int N, int D) {
+    __shared__ float red[8];
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const long row = blockIdx.x;
+    const int prob = (int)(row / (2 * N)), q = (int)(row - (long)prob * 2 * N);
+    const bool isx = q < N;
+    const int i = isx ? q : q - N;
+    const float *src = (isx ? x : y) + ((long)prob * N + i) * D;
+    float *g = (isx ? gx : gy) + ((long)prob * N + i) * D;
+    const float den = pbuf[(long)prob * ((long)N * N + 2 * N) + (long)N * N + (isx ? 0 : N) + i];
+    float xh[kChainCache], gv[kChainCache];
+#pragma unroll
+    for (int k = 0; k < kChainCache; ++k) {
+        const int d = t + k * 256;
+        xh[k] = d < D ? __ldg(src + d) : 0.f;
+        gv[k] = d < D ? g[d] : 0.f;
+    }
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < kChainCache; ++k) { xh[k] = __fdiv_rn(xh[k], den); dot = fmaf(gv[k], xh[k], dot); }
+    dot = warp_sum(dot);
+    if (lane == 0) red[wid] = dot;
+    __syncthreads();
+    dot = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) dot = __fadd_rn(dot, red[w]);
+    const float shrink = __fdiv_rn(__fsub_rn(den, kEps), den);   // |x| / (|x| + EPS)
+#pragma unroll
+    for (int k = 0; k < kChainCache; ++k) {
+        const int d = t + k * 256;
+        if (d < D) g[d] = __fdiv_rn(__fsub_rn(gv[k], __fmul_rn(__fmul_rn(xh[k], dot), shrink)), den);
     }
 }
 
@@ -732,11 +873,24 @@ static bool plan(int N, int CS, int keepC, SinkParams &p, size_t &bytes) {
 
 using namespace fi;
 
-// Scratch floats the split gradient needs (0: the gradient stays inside the solver kernel).  Large D only: the plan of every
-// problem (N x N) and its row norms.
+// Slices of D the cost matrix is spread over: enough CTAs for two waves of the 148 SMs, at least 64 columns each.
+static int gram_slices(int n_problems, int N, int D) {
+    const int tiles = ceil_div(N, kTile) * ceil_div(N, kTile);
+    int S = ceil_div(2 * kNumSMs, n_problems * tiles);
+    S = S < 1 ? 1 : (S > 32 ? 32 : S);
+    if (S > D / 64) S = D / 64 > 0 ? D / 64 : 1;
+    return S;
+}
+static int gram_slice_width(int D, int S) { return ceil_div(ceil_div(D, S), kDT) * kDT; }
+
+// Scratch bytes of the large-D form (0: everything stays inside the solver kernel): per problem the plan (N x N) and its row
+// norms (2N) -- what the split gradient reads -- and the S slices of the cost matrix.  `want_grad` no longer changes the size
+// (the norms and the slices serve the forward pass too); the argument stays for ABI stability.
 FI_API size_t fi_sinkhorn_workspace(int n_problems, int N, int D, int want_grad) {
-    if (!want_grad || n_problems <= 0 || D < 128 || N < 4 || N > 128 || (N % 4) != 0) return 0;
-    return (size_t)n_problems * ((size_t)N * N + 2 * (size_t)N) * sizeof(float);
+    (void)want_grad;
+    if (n_problems <= 0 || D < 128 || N < 4 || N > 128 || (N % 4) != 0) return 0;
+    const size_t per = (size_t)N * N + 2 * (size_t)N;
+    return (size_t)n_problems * (per + (size_t)gram_slices(n_problems, N, D) * N * N) * sizeof(float);
 }
 
 FI_API int fi_sinkhorn(const float *x, const float *y, int n_problems, int N, int D, float inv_eps, int L, float *loss,
@@ -789,11 +943,22 @@ FI_API int fi_sinkhorn_ws(const float *x, const float *y, int n_problems, int N,
         }
     }
     p.masked = masked;
-    p.pbuf = nullptr;
+    p.pbuf = nullptr; p.nbuf = nullptr; p.gram = nullptr; p.S = 0;
     const size_t need_ws = fi_sinkhorn_workspace(n_problems, N, D, grad_x != nullptr);
-    if (CS == 1 && need_ws > 0 && workspace != nullptr && workspace_bytes >= need_ws && ((uintptr_t)workspace % 16) == 0)
-        p.pbuf = static_cast<float *>(workspace);
     cudaError_t e;
+    if (CS == 1 && p.keepC && need_ws > 0 && workspace != nullptr && workspace_bytes >= need_ws && ((uintptr_t)workspace % 16) == 0) {
+        float *base = static_cast<float *>(workspace);
+        float *gram = base + (size_t)n_problems * ((size_t)N * N + 2 * (size_t)N);
+        const int S = gram_slices(n_problems, N, D), Dc = gram_slice_width(D, S);
+        const long rows = 2L * n_problems * N;
+        sinkhorn_norm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(x, y, base, n_problems, N, D);
+        if (int rc = check_launch("fi_sinkhorn[norms]")) return rc;
+        const int tiles = ceil_div(N, kTile) * ceil_div(N, kTile);
+        sinkhorn_gram_split_kernel<<<dim3((unsigned)n_problems, (unsigned)S, (unsigned)tiles), kSinkThreads, 0, stream>>>(x, y, base, gram, N, D, S, Dc);
+        if (int rc = check_launch("fi_sinkhorn[cost slices]")) return rc;
+        p.nbuf = base; p.gram = gram; p.S = S;
+        if (grad_x != nullptr) p.pbuf = base;
+    }
     if (CS > 1 && !masked) {
         e = cudaMemsetAsync(loss, 0, sizeof(float) * n_problems, stream);
         if (e == cudaSuccess && grad_y) e = cudaMemsetAsync(grad_y, 0, sizeof(float) * (size_t)n_problems * N * D, stream);
@@ -815,13 +980,26 @@ FI_API int fi_sinkhorn_ws(const float *x, const float *y, int n_problems, int N,
     if (e != cudaSuccess) { set_error(FI_ERR_CUDA, "fi_sinkhorn: launch: %s", cudaGetErrorString(e)); return FI_ERR_CUDA; }
     if (int rc = check_launch("fi_sinkhorn")) return rc;
     if (p.pbuf != nullptr) {                                 // large D: the gradient as two more launches over (problem, D chunk) / rows
-        const size_t sm = ((size_t)N * N + 2 * (size_t)N) * sizeof(float);
-        e = cudaFuncSetAttribute(sinkhorn_grad_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        const size_t sm = ((size_t)N * N + 2 * (size_t)N + 2 * (size_t)N * 64) * sizeof(float);
+        const int per = ((N + 15) / 16) * 4;
+        void (*raw)(const float *, const float *, const float *, float *, float *, int, int) = nullptr;
+        switch (per) {
+            case 4: raw = sinkhorn_grad_raw_kernel<4>; break;
+            case 8: raw = sinkhorn_grad_raw_kernel<8>; break;
+            case 12: raw = sinkhorn_grad_raw_kernel<12>; break;
+            case 16: raw = sinkhorn_grad_raw_kernel<16>; break;
+            case 20: raw = sinkhorn_grad_raw_kernel<20>; break;
+            case 24: raw = sinkhorn_grad_raw_kernel<24>; break;
+            case 28: raw = sinkhorn_grad_raw_kernel<28>; break;
+            default: raw = sinkhorn_grad_raw_kernel<32>; break;
+        }
+        e = cudaFuncSetAttribute(raw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) { set_error(FI_ERR_CUDA, "fi_sinkhorn: smem attr (%zu B): %s", sm, cudaGetErrorString(e)); return FI_ERR_CUDA; }
-        sinkhorn_grad_raw_kernel<<<dim3((unsigned)n_problems, (unsigned)ceil_div(D, 64)), 256, sm, stream>>>(x, y, p.pbuf, grad_x, grad_y, N, D);
+        raw<<<dim3((unsigned)ceil_div(D, 64), (unsigned)n_problems), 256, sm, stream>>>(x, y, p.pbuf, grad_x, grad_y, N, D);
         if (int rc = check_launch("fi_sinkhorn[gradient]")) return rc;
         const long rows = 2L * n_problems * N;
-        sinkhorn_grad_chain_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(x, y, p.pbuf, grad_x, grad_y, n_problems, N, D);
+        if (D <= 256 * kChainCache) sinkhorn_grad_chain_rows_kernel<<<(unsigned)rows, 256, 0, stream>>>(x, y, p.pbuf, grad_x, grad_y, n_problems, N, D);
+        else sinkhorn_grad_chain_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(x, y, p.pbuf, grad_x, grad_y, n_problems, N, D);
         return check_launch("fi_sinkhorn[gradient chain]");
     }
     return ok();

@@ -275,9 +275,10 @@ int fi_segment_mean_backward_n(const int *gt, const float *grad_mean, const floa
  * OT_module.py:130-131) through the row normalisation.  N <= 256; any D >= 1. */
 int fi_sinkhorn(const float *x, const float *y, int n_problems, int N, int D, float inv_eps, int L, float *loss,
                 float *grad_x, float *grad_y, cudaStream_t stream);
-/* The same with caller-owned scratch memory for the large-D gradient (FPN-level loss, N = 64, D up to 4096: the N x D gradient
- * products are spread over (problem, D chunk) CTAs instead of one CTA per problem).  fi_sinkhorn_workspace: bytes needed, 0 when
- * the shape keeps the gradient inside the solver kernel (then workspace may be NULL). */
+/* The same with caller-owned scratch memory for large D (FPN-level loss, N = 64, D up to 4096): the two D-long parts -- the cost
+ * matrix x^ y^T and the N x D gradient products -- are spread over (problem, slice of D) CTAs instead of one CTA per problem.
+ * fi_sinkhorn_workspace: bytes needed, 0 when the shape keeps everything inside the solver kernel (then workspace may be NULL;
+ * without a workspace a large-D call still works, one CTA per problem).  `want_grad` does not change the size. */
 size_t fi_sinkhorn_workspace(int n_problems, int N, int D, int want_grad);
 int fi_sinkhorn_ws(const float *x, const float *y, int n_problems, int N, int D, float inv_eps, int L, float *loss, float *grad_x,
                    float *grad_y, void *workspace, size_t workspace_bytes, cudaStream_t stream);

@@ -62,6 +62,10 @@ def ref_cuda():
     L.CropAndResizeLaucher.restype = None
     L.CropAndResizeBackpropImageLaucher.argtypes = [P, P, P, I, I, I, I, I, I, I, P, P]
     L.CropAndResizeBackpropImageLaucher.restype = None
+    L.ROIPoolForwardLaucher.argtypes = [P, Fl, I, I, I, I, I, I, P, P, P, P]           # roi_pooling_kernel.h:8-12
+    L.ROIPoolForwardLaucher.restype = I
+    L.ROIPoolBackwardLaucher.argtypes = [P, Fl, I, I, I, I, I, I, I, P, P, P, P]       # roi_pooling_kernel.h:14-18
+    L.ROIPoolBackwardLaucher.restype = I
     return L
 
 
@@ -144,8 +148,43 @@ def main():
     zero_row = dict(kind="memset_1GiB", ms=t, gbs=a.numel() * 4 / t / 1e6)
     print(json.dumps(zero_row), flush=True)
     del a, b
+    # RoIPool (lib/roi_pooling): every RoI of the workload on the P3 map at 7x7, both layouts, next to the reference's kernel
+    pool_rows = []
+    g = torch.Generator().manual_seed(5)
+    Hh, Ww = maps[1].shape[2], maps[1].shape[3]
+    R = wl["batch"] * wl["rois_per_image"]
+    ctr = torch.rand(R, 2, generator=g) * torch.tensor([Ww * 8.0, Hh * 8.0])
+    half = 16 + 100 * torch.rand(R, 2, generator=g)
+    rois5 = torch.cat([torch.randint(0, wl["batch"], (R, 1), generator=g).float(), (ctr - half).clamp(min=0), ctr + half], dim=1).cuda()
+    for fmt in ("nhwc", "nchw"):
+        img = maps[1] if fmt == "nhwc" else maps[1].contiguous()
+        op = fi.RoIPoolFunction(7, 7, 1.0 / 8)
+        x = img.detach().requires_grad_()
+        out = op(x, rois5)
+        gy = torch.randn_like(out)
+        t = timeit(lambda: op(img, rois5), args.iters)
+        tb = timeit(lambda: torch.autograd.grad(out, x, gy, retain_graph=True), args.iters)
+        pool_rows.append(dict(kind="roi_pool", layout=fmt, rois=R, map=[Hh, Ww], fwd_ms=t, bwd_ms=tb))
+        del out, gy, x
+    if refL is not None:
+        img = maps[1].contiguous()
+        top = torch.empty(R, 256, 7, 7, device="cuda")
+        arg = torch.empty(R, 256, 7, 7, device="cuda", dtype=torch.int32)
+        t = timeit(lambda: refL.ROIPoolForwardLaucher(img.data_ptr(), 1.0 / 8, R, Hh, Ww, 256, 7, 7, rois5.data_ptr(), top.data_ptr(), arg.data_ptr(), s),
+                   args.iters)
+        gimg = torch.empty_like(img)
+        gy = torch.randn_like(top)
+
+        def rpb():
+            gimg.zero_()                                                   # roi_pooling_cuda.c zero-fills before the atomics kernel
+            refL.ROIPoolBackwardLaucher(gy.data_ptr(), 1.0 / 8, wl["batch"], R, Hh, Ww, 256, 7, 7, rois5.data_ptr(), gimg.data_ptr(), arg.data_ptr(), s)
+        tb = timeit(rpb, args.iters)
+        pool_rows.append(dict(kind="roi_pool", layout="reference_cuda_sm100a (nchw)", rois=R, map=[Hh, Ww], fwd_ms=t, bwd_ms=tb))
+        del top, arg, gimg, gy
+    for r in pool_rows:
+        print(json.dumps(r), flush=True)
     sk = []
-    for (P, N, D, L) in [(240, 256, 1, 50), (240, 256, 1, wl["sinkhorn_iters"]), (4050, 256, 1, 50), (24, 64, 256, 5), (24, 64, 4096, 5), (240, 128, 1, 50), (240, 200, 1, 50)]:
+    for (P, N, D, L) in [(240, 256, 1, 50), (240, 256, 1, wl["sinkhorn_iters"]), (4050, 256, 1, 50), (12288, 256, 1, 50), (24, 64, 256, 5), (24, 64, 4096, 5), (240, 128, 1, 50), (240, 200, 1, 50)]:
         x = torch.randn(P, N, D, device="cuda").abs()
         y = torch.randn(P, N, D, device="cuda").abs()
         t = timeit(lambda: fi.sinkhorn_loss(x, y, 1.0, L), args.iters)
@@ -156,7 +195,7 @@ def main():
         print(json.dumps(r), flush=True)
         sk.append(r)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
-    json.dump(dict(workload=args.workload, peak_gbs=peak, peak_kind=peak_kind, roi_align=rows, copy=copy_row, memset=zero_row, sinkhorn=sk),
+    json.dump(dict(workload=args.workload, peak_gbs=peak, peak_kind=peak_kind, roi_align=rows, roi_pool=pool_rows, copy=copy_row, memset=zero_row, sinkhorn=sk),
               open(args.out, "w"), indent=1)
 
 
