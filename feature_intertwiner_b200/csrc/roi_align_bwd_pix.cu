@@ -398,6 +398,10 @@ int pix_accumulate(const TParams &P, int exact, cudaStream_t stream) {
     // Ring shape (measured on C2, profiles/r02_pix_sweep.json): three CTAs per SM with a two-batch ring beat two CTAs with
     // three batches (0.72 vs 0.86 ms, DRAM at 92 % vs 80 % of the copy peak): each CTA is latency-bound on its own ring, so
     // more independent rings per SM keep more bytes in flight; 16-slot batches lose to the per-batch work of the consumers.
+    // (Tried for small maps -- a level-4 / level-5 call alone has fewer tiles than a few rounds of the persistent grid and lasts
+    // as long as its heaviest tile: 128-channel work items on a 256-channel map, twice the items at half the bytes, were SLOWER,
+    // 172 vs 125 us at level 5 and 131 vs 93 us at level 4 of C2: the per-entry work of the producer, not the bytes, is the tile's
+    // critical path, and rows of half a pixel cannot be run-coalesced.  profiles/r02_small_map_bwd.txt)
     const int cfg = option(FI_OPT_PIX_CFG);
     if (C % 256 == 0) {
         if (cfg == 1) return exact ? launch_pix<true, 256, 32, 3, 2>(P, stream) : launch_pix<false, 256, 32, 3, 2>(P, stream);
