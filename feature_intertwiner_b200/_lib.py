@@ -57,6 +57,7 @@ SIGNATURES = {
     "fi_sinkhorn_ws": (_I, [_P, _P, _I, _I, _I, _F, _I, _P, _P, _P, _P, C.c_size_t, _P]),
     "fi_buffer_update": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "fi_nms_batched": (_I, [_P, _I, _I, _F, _P, _P, _P, _P]),
+    "fi_nms_batched_topk": (_I, [_P, _I, _I, _F, _I, _P, _P, _P, _P]),
     "fi_proposal_decode": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _F, _F, _P, _P, _P]),
     "fi_proposal_gather": (_I, [_P, _P, _P, _I, _I, _I, _F, _F, _P, _P, _P]),
     "fi_mask_targets": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),

@@ -238,15 +238,15 @@ __global__ void buffer_update_kernel(const float *__restrict__ big_sum, const fl
 
 // ------------------------------------------------------------------------------------------------
 // Visiting order of the RoIs (intertwiner.py::spatial_order): every image walked coarse tile by coarse tile (grid x grid, by box
-// centre, boustrophedon), stable.  One CTA per image; the rank of an element is counted directly (R <= 4096 per image: R^2 / 256
-// comparisons per thread against keys broadcast from shared memory) -- replaces ~10 pointwise launches and a radix sort.
+// centre, boustrophedon), stable.  The rank of an element is counted directly (R <= 4096 per image, keys in shared memory) -- replaces ~10 pointwise launches and a radix sort.
 // ------------------------------------------------------------------------------------------------
 constexpr int kOrderMaxR = 4096;
+constexpr int kOrderPerCta = 32;      // RoIs ranked by one CTA (8 warps x 4): grid = (images, ceil(R / 32))
 __global__ void __launch_bounds__(256) spatial_order_kernel(const float4 *__restrict__ rois, int R, int grid, int *__restrict__ order) {
     __shared__ short keys[kOrderMaxR];
-    const int b = blockIdx.x;
+    const int b = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const float g2 = __fmul_rn(0.5f, (float)grid), top = (float)(grid - 1);
-    for (int i = threadIdx.x; i < R; i += blockDim.x) {
+    for (int i = threadIdx.x; i < R; i += blockDim.x) {             // every CTA of the image forms all keys (R float4 loads from L2)
         const float4 r = __ldg(rois + (long)b * R + i);               // y1, x1, y2, x2
         const float cy = floorf(fminf(fmaxf(__fmul_rn(__fadd_rn(r.x, r.z), g2), 0.f), top));
         const float cx = floorf(fminf(fmaxf(__fmul_rn(__fadd_rn(r.y, r.w), g2), 0.f), top));
@@ -254,14 +254,20 @@ __global__ void __launch_bounds__(256) spatial_order_kernel(const float4 *__rest
         keys[i] = (short)(iy * grid + ((iy & 1) ? grid - 1 - ix : ix));
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < R; i += blockDim.x) {
+    // warp per RoI, lanes stride over the others (one CTA per image walked R^2 / 256 comparisons per thread: 53 us at R = 1000,
+    // 0.2 ms at R = 2000 on 4 of 148 SMs)
+    for (int q = 0; q < kOrderPerCta / 8; ++q) {
+        const int i = blockIdx.y * kOrderPerCta + wid * (kOrderPerCta / 8) + q;
+        if (i >= R) break;
         const int k = keys[i];
         int rank = 0;
-        for (int j = 0; j < R; ++j) {
+        for (int j = lane; j < R; j += 32) {
             const int kj = keys[j];
             rank += (kj < k) || (kj == k && j < i);
         }
-        order[(long)b * R + rank] = b * R + i;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, d);
+        if (lane == 0) order[(long)b * R + rank] = b * R + i;
     }
 }
 
@@ -382,6 +388,7 @@ FI_API int fi_spatial_order(const float *rois, int batch, int rois_per_image, in
     if (batch == 0 || rois_per_image == 0) return ok();
     if (rois_per_image > kOrderMaxR) { set_error(FI_ERR_UNSUPPORTED, "fi_spatial_order: more than %d RoIs per image", kOrderMaxR); return FI_ERR_UNSUPPORTED; }
     FI_REQUIRE(rois && order && ((uintptr_t)rois % 16) == 0, "fi_spatial_order: rois must be a 16-byte aligned device pointer");
-    spatial_order_kernel<<<batch, 256, 0, stream>>>(reinterpret_cast<const float4 *>(rois), rois_per_image, grid, order);
+    spatial_order_kernel<<<dim3((unsigned)batch, (unsigned)ceil_div(rois_per_image, kOrderPerCta)), 256, 0, stream>>>(
+        reinterpret_cast<const float4 *>(rois), rois_per_image, grid, order);
     return check_launch("fi_spatial_order");
 }

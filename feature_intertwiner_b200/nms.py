@@ -52,18 +52,20 @@ def nms(dets, thresh):
     return keep[:, :m].to(torch.int32).cpu().numpy().astype(np.int32)
 
 
-def nms_presorted(dets_xyxys, thresh):
+def nms_presorted(dets_xyxys, thresh, max_keep=None):
     """dets[bs,N,5] = (x1,y1,x2,y2,score), every image already in descending score order -> (keep[bs,N] int32 positions,
-    kept ones first in score order, rest -1; num_keep[bs] int32).  No sort, no host synchronisation."""
+    kept ones first in score order, rest -1; num_keep[bs] int32).  No sort, no host synchronisation.  ``max_keep``: the caller
+    uses only that many survivors per image -- the sweep stops there (same head of the list; num_keep >= max_keep means cut)."""
     _lib.require_cuda(dets_xyxys)
     bs, n, _ = dets_xyxys.shape
     words = (n + 63) // 64
     mask = torch.empty((bs, n, max(words, 1)), device=dets_xyxys.device, dtype=torch.int64)
     keep = torch.empty((bs, n), device=dets_xyxys.device, dtype=torch.int32)
     num = torch.empty((bs,), device=dets_xyxys.device, dtype=torch.int32)
+    limit = n if max_keep is None else max(1, min(int(max_keep), n))
     with torch.cuda.device(dets_xyxys.device):
-        _lib.check(_lib.lib().fi_nms_batched(_lib.ptr(dets_xyxys), bs, n, float(thresh), _lib.ptr(mask), _lib.ptr(keep),
-                                             _lib.ptr(num), _lib.stream_ptr(dets_xyxys.device)))
+        _lib.check(_lib.lib().fi_nms_batched_topk(_lib.ptr(dets_xyxys), bs, n, float(thresh), max(limit, 1), _lib.ptr(mask), _lib.ptr(keep),
+                                                  _lib.ptr(num), _lib.stream_ptr(dets_xyxys.device)))
     return keep, num
 
 
@@ -111,7 +113,7 @@ def proposal_layer(inputs, proposal_count, nms_threshold, priors, config=None, s
     boxes, dets = proposal_decode(inputs, priors, config)
     bs, dev = boxes.size(0), boxes.device
     height, width = float(config.DATA.IMAGE_SHAPE[0]), float(config.DATA.IMAGE_SHAPE[1])
-    keep, num = nms_presorted(dets, nms_threshold)
+    keep, num = nms_presorted(dets, nms_threshold, max_keep=int(proposal_count))
     rois = torch.empty((bs, int(proposal_count), 4), device=dev, dtype=torch.float32)
     m_dev = torch.empty((1,), device=dev, dtype=torch.int32)
     with torch.cuda.device(dev):

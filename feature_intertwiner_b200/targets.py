@@ -82,7 +82,7 @@ def detection_layer(rois, probs, deltas, windows, config, feature=None):
     extent = float(max(int(config.DATA.IMAGE_SHAPE[0]), int(config.DATA.IMAGE_SHAPE[1])) + 2)
     shift = (sc.float() * extent).unsqueeze(2)
     dets = torch.cat([sb[:, :, [1, 0, 3, 2]] + shift, key.unsqueeze(2)], dim=2).contiguous()     # (x1,y1,x2,y2,score): pth_nms.py:28-33
-    kept, num = nms_presorted(dets, float(config.TEST.DET_NMS_THRESHOLD))   # positions in score order, survivors first
+    kept, num = nms_presorted(dets, float(config.TEST.DET_NMS_THRESHOLD), max_keep=K)   # positions in score order, survivors first
     pos = kept[:, :K] if kept.size(1) >= K else torch.cat([kept, kept.new_full((bs, K - kept.size(1)), -1)], dim=1)
     valid = (pos >= 0) & (pos < n_cand)                                      # a survivor that is no candidate sits behind all candidates
     idx = pos.clamp(min=0).long()

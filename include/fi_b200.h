@@ -304,6 +304,11 @@ int fi_buffer_update(const float *big_sum, const float *big_n, int B, int slot, 
  * num_keep[n_images].  Suppress when IoU > thresh (the reference's GPU rule, nms_kernel.cu:63). */
 int fi_nms_batched(const float *boxes, int n_images, int n, float thresh, unsigned long long *mask, int *keep,
                    int *num_keep, cudaStream_t stream);
+/* The same for callers that use only the first max_keep survivors of every image (proposal_count, lib/layers.py:118-121;
+ * DET_MAX_INSTANCES, :790-795): the sweep of an image stops once it knows that many.  keep[] holds at least
+ * min(max_keep, all survivors) entries, identical to the head of fi_nms_batched's list; num_keep[i] >= max_keep means "cut". */
+int fi_nms_batched_topk(const float *boxes, int n_images, int n, float thresh, int max_keep, unsigned long long *mask, int *keep,
+                        int *num_keep, cudaStream_t stream);
 
 /* Front half of proposal_layer (lib/layers.py:87-122 + tools/box_utils.py:7-45) in one launch: for proposal k of image b,
  * a = order[b,k] (descending-score order, int64 as torch.sort returns it); box = clip(apply_box_deltas(anchors[a],

@@ -427,6 +427,25 @@ def test_nms_batched_vs_oracle(n):
     np.testing.assert_array_equal(keep, want)
 
 
+@pytest.mark.parametrize("n,limit", [(6000, 1000), (6000, 1), (1000, 100), (200, 500), (65, 64), (9000, 2000)])
+def test_nms_early_exit_keeps_the_same_head(n, limit):
+    """fi_nms_batched_topk: the sweep stops once `limit` survivors are known; the first `limit` entries equal the full sweep's."""
+    from feature_intertwiner_b200 import synth
+    from feature_intertwiner_b200.nms import nms_presorted
+    g = torch.Generator().manual_seed(n + limit)
+    dets = synth.make_nms_boxes(3, n, g)
+    order = torch.sort(dets[:, :, 4], dim=1, descending=True, stable=True)[1]
+    srt = torch.gather(dets, 1, order.unsqueeze(2).expand(3, n, 5))[:, :, [1, 0, 3, 2, 4]].contiguous().cuda()
+    full, num_full = nms_presorted(srt, 0.7)
+    cut, num_cut = nms_presorted(srt, 0.7, max_keep=limit)
+    for b in range(3):
+        m = min(limit, int(num_full[b]))
+        assert int(num_cut[b]) >= m and int(num_cut[b]) <= int(num_full[b])
+        assert torch.equal(cut[b, :m], full[b, :m])
+        k = int(num_cut[b])
+        assert torch.equal(cut[b, :k], full[b, :k]) and bool((cut[b, k:] == -1).all())
+
+
 def test_nms_known_answers_and_threshold_rule():
     fi = _fi()
     # disjoint boxes keep all; identical boxes keep the first
