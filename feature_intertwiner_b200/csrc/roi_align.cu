@@ -15,6 +15,7 @@
 
 #include "fi_common.cuh"
 #include "roi_align_units.cuh"
+#include "roi_align_fwd_lean.cuh"
 
 namespace fi {
 
@@ -89,6 +90,40 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) crop_fwd_nhwc_sets_kernel
         int k = 0;
         while (u >= first[k + 1]) ++k;
         fwd_unit<4>(sets.s[k], u - first[k], lane);
+    }
+}
+
+// Lean formulation (roi_align_fwd_lean.cuh): WARPS warps per block, MINB blocks per SM, persistent over the units.
+template <int VPL, int U, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) crop_fwd_nhwc_lean_kernel(const FwdSet S, unsigned nunits, u64 nz) {
+    const int lane = threadIdx.x & 31;
+    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned u = warp; u < nunits; u += nwarps) fwd_unit_lean<VPL, U>(S, u, lane, nz);
+}
+
+template <int VPL, int U, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) crop_fwd_nhwc_sets_lean_kernel(const FwdSets sets, u64 nz) {
+    __shared__ unsigned first[kMaxFwdSets + 1];         // prefix of the sets' LIVE unit counts (see crop_fwd_nhwc_sets_kernel)
+    if (threadIdx.x == 0) {
+        unsigned acc = 0;
+        for (int k = 0; k < sets.n; ++k) {
+            const FwdSet &S = sets.s[k];
+            const int R = S.R_dev ? max(0, min(*S.R_dev, S.R)) : S.R;
+            first[k] = acc;
+            acc += (unsigned)R * (unsigned)S.ph * (unsigned)S.slabs;
+        }
+        first[sets.n] = acc;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
+    const unsigned total = first[sets.n];
+    for (unsigned u = warp; u < total; u += nwarps) {
+        int k = 0;
+        while (u >= first[k + 1]) ++k;
+        fwd_unit_lean<VPL, U>(sets.s[k], u - first[k], lane, nz);
     }
 }
 
@@ -402,6 +437,47 @@ FI_API int fi_crop_taps(const float *boxes, int num_boxes, int H, int W, int ph,
 int fi_nchw_backward_via_nhwc(const float *grads, const float *boxes, const int *box_ind, const int *src_row, int R, int B, int H, int W, int ph,
                               int pw, int C, float *gimg, int accumulate, cudaStream_t stream);   // roi_align_nchw_bwd.cu
 
+// ---- lean forward launchers (FI_OPT_FWD_FORM) -------------------------------------------------------------------------------
+// form 0 = default (kLeanDefault), 1 = round-1 unit (fwd_unit), 2.. = the other lean shapes kept for A/B runs.
+struct LeanShape { int vpl, u, warps, minb; };
+static const LeanShape kLeanShapes[] = {
+    {2, 2, 4, 5},   // form 2: both slabs per warp, 16 tap loads in flight, 20 warps / SM
+    {2, 2, 8, 2},   // form 3: the same at 16 warps / SM (round-1 occupancy)
+    {2, 1, 4, 8},   // form 4: 8 loads in flight, 32 warps / SM
+    {1, 4, 4, 5},   // form 5: one slab per warp, 16 loads in flight
+    {2, 3, 4, 4},   // form 6: both slabs per warp, 24 loads in flight, 16 warps / SM
+};
+constexpr int kLeanDefault = 2;
+
+static int lean_shape_index() {           // -1: round-1 unit
+    int form = option(FI_OPT_FWD_FORM);
+    if (form == 0) form = kLeanDefault;
+    if (form == 1) return -1;
+    return form - 2;
+}
+
+static bool lean_ok(const void *image, const void *boxes, const void *crops, const void *crops2, int W, int C, int vpl, long units) {
+    return (C % (128 * vpl) == 0) && ((long)W * C * 4 <= (1L << 30)) && units < (1L << 31) && ((uintptr_t)image % 16 == 0) &&
+           ((uintptr_t)boxes % 16 == 0) && ((uintptr_t)crops % 16 == 0) && ((uintptr_t)crops2 % 16 == 0);
+}
+
+template <int VPL, int U, int WARPS, int MINB>
+static void launch_lean_one(const FwdSet &S, unsigned nunits, cudaStream_t stream) {
+    crop_fwd_nhwc_lean_kernel<VPL, U, WARPS, MINB><<<grid_for(nunits, WARPS, MINB), WARPS * 32, 0, stream>>>(S, nunits, kNegZeroPair);
+}
+template <int VPL, int U, int WARPS, int MINB>
+static void launch_lean_sets(const FwdSets &sets, long units, cudaStream_t stream) {
+    crop_fwd_nhwc_sets_lean_kernel<VPL, U, WARPS, MINB><<<grid_for(units, WARPS, MINB), WARPS * 32, 0, stream>>>(sets, kNegZeroPair);
+}
+#define FI_LEAN_DISPATCH(idx, CALL)                  \
+    switch (idx) {                                   \
+        case 0: CALL(2, 2, 4, 5); break;             \
+        case 1: CALL(2, 2, 8, 2); break;             \
+        case 2: CALL(2, 1, 4, 8); break;             \
+        case 3: CALL(1, 4, 4, 5); break;             \
+        default: CALL(2, 3, 4, 4); break;            \
+    }
+
 static int forward_impl(const float *image, int image_layout, const float *boxes, const int *box_ind, const int *dst_row, int R, int B, int H,
                         int W, int ph, int pw, int C, float extrap, float *crops, int crops_layout, float *crops2, cudaStream_t stream) {
     if (int e = check_common(image, boxes, box_ind, crops, R, B, H, W, ph, pw, C)) return e;
@@ -416,6 +492,16 @@ static int forward_impl(const float *image, int image_layout, const float *boxes
             FwdSet S;
             S.image = image; S.boxes = boxes; S.box_ind = box_ind; S.dst_row = dst_row; S.R_dev = nullptr; S.crops = crops; S.crops2 = crops2;
             S.B = B; S.H = H; S.W = W; S.C = C; S.ph = ph; S.pw = pw; S.slabs = C / 128; S.R = R; S.extrap = extrap;
+            int li = lean_shape_index();
+            if (li >= 0 && !lean_ok(image, boxes, crops, crops2, W, C, kLeanShapes[li].vpl, (long)R * ph * S.slabs)) li = (kLeanShapes[li].vpl == 2) ? 3 : -1;   // one slab per warp
+            if (li >= 0 && lean_ok(image, boxes, crops, crops2, W, C, kLeanShapes[li].vpl, (long)R * ph * S.slabs)) {
+                S.slabs = C / (128 * kLeanShapes[li].vpl);
+                const unsigned nu = (unsigned)((long)R * ph * S.slabs);
+#define FI_CALL_ONE(V, UU, WW, MB) launch_lean_one<V, UU, WW, MB>(S, nu, stream)
+                FI_LEAN_DISPATCH(li, FI_CALL_ONE)
+#undef FI_CALL_ONE
+                return check_launch("fi_crop_and_resize_forward[nhwc lean]");
+            }
             const long nunits = (long)R * ph * S.slabs;  // one warp per (crop row, 128-channel slab)
             const int grid = grid_for(nunits, kWarpsPerBlock, 8);
             if (pw % 4 == 0 || pw > 12)
@@ -523,6 +609,27 @@ FI_API int fi_crop_sets_forward(const fi_fwd_set *sets, int num_sets, cudaStream
     }
     dev.first_unit[dev.n] = units;
     if (units == 0) return ok();
+    {   // lean formulation when every set qualifies for the chosen shape (else: a one-slab lean shape, else the round-1 unit)
+        int li = lean_shape_index();
+        for (int pass = 0; pass < 2 && li >= 0; ++pass) {
+            bool all = true;
+            long lu = 0;
+            for (int k = 0; k < dev.n; ++k) {
+                const FwdSet &S = dev.s[k];
+                lu += (long)S.R * S.ph * (S.C / (128 * kLeanShapes[li].vpl));
+                all = all && lean_ok(S.image, S.boxes, S.crops, S.crops2, S.W, S.C, kLeanShapes[li].vpl, 0);
+            }
+            all = all && lu < (1L << 31);
+            if (all) {
+                for (int k = 0; k < dev.n; ++k) dev.s[k].slabs = dev.s[k].C / (128 * kLeanShapes[li].vpl);
+#define FI_CALL_SETS(V, UU, WW, MB) launch_lean_sets<V, UU, WW, MB>(dev, lu, stream)
+                FI_LEAN_DISPATCH(li, FI_CALL_SETS)
+#undef FI_CALL_SETS
+                return check_launch("fi_crop_sets_forward[lean]");
+            }
+            li = (kLeanShapes[li].vpl == 2) ? 3 : -1;      // retry with one slab per warp
+        }
+    }
     crop_fwd_nhwc_sets_kernel<<<grid_for(units, kWarpsPerBlock, 8), kWarpsPerBlock * 32, 0, stream>>>(dev);
     return check_launch("fi_crop_sets_forward");
 }

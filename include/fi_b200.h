@@ -45,7 +45,9 @@ unsigned long long fi_kernel_launches(void); /* kernels this library has launche
                                      accumulate kernel [FI_BWD_ACC=smem], 2 fused single tile kernel [FI_BWD_TILE=fused],
                                      3 vector reductions [FI_BWD=red] */
 #define FI_OPT_TILE_SHAPE 1       /* tile of forms 1 and 2: 0 = 4x8 (default), 1 = 4x4 [FI_TILE=4x4], 2 = 2x8 [FI_TILE=2x8] */
-#define FI_OPT_RESERVED 2         /* (was: TMA-staged NCHW forward -- measured 0-60 % slower than the L1-cached direct loads, removed) */
+#define FI_OPT_FWD_FORM 2         /* NHWC RoIAlign forward: 0 = default (the lean unit, both 128-channel slabs per warp, 20 warps / SM);
+                                     1 = round-1 unit (one slab per warp, scalar lerps); 2..6 = lean shapes kept for A/B runs
+                                     (csrc/roi_align.cu::kLeanShapes).  All forms give identical bits. [FI_FWD_FORM] */
 #define FI_OPT_SINKHORN_GENERIC 3 /* D = 1 problems: 0 = solved by classes, dense kernels only for what that leaves (default);
                                      1 = dense kernels only (K in registers for N = 256); 2 = generic shared-memory kernel only
                                      [FI_SINKHORN_GENERIC=1|2] */

@@ -208,6 +208,57 @@ def test_crop_sets_matches_separate_calls():
             fi.set_deterministic(old)
 
 
+@pytest.mark.parametrize("form", [0, 1, 2, 3, 4, 5, 6])
+def test_forward_forms_bit_identical(form):
+    """Every NHWC forward formulation (fi_set_option fwd_form: 0 default, 1 round-1 unit, 2..6 the lean shapes with packed
+    two-float lerps) gives the bits of the reference: single calls on 128 / 256 / 384 / 512 channels, crops 1..33 wide (more than
+    one 32-sample pass), extrapolation, out-of-range image indices, and the level-batched launch with scattered rows + compact
+    copies + device-side counts."""
+    fi = _fi()
+    cl = torch.channels_last
+    old = fi.set_option("fwd_form", form)
+    try:
+        for C, (ph, pw), extrap in ((256, (7, 7), 0.0), (256, (14, 14), 0.5), (128, (3, 5), -1.0), (384, (14, 14), 0.0), (512, (2, 33), 0.25),
+                                    (256, (1, 1), 0.0)):
+            image, rois, box_ind = _case(40 + C + pw, 3, C, 26, 42, 83, zero_rows=5)
+            box_ind[3] = -1
+            box_ind[7] = 3
+            want = clib.oracle_crop_and_resize_fwd(image.numpy(), rois.numpy(), np.clip(box_ind.numpy(), 0, 2), ph, pw, extrap)
+            want[3] = 0
+            want[7] = 0
+            got = fi.CropAndResizeFunction(ph, pw, extrap)(image.cuda().contiguous(memory_format=cl), rois.cuda(), box_ind.cuda())
+            np.testing.assert_array_equal(got.cpu().numpy(), want, err_msg="C=%d crop %dx%d" % (C, ph, pw))
+        # level-batched launch: two maps, 7x7 + 14x14 into shared outputs by dst_row, a compact copy, a device-side count
+        g = torch.Generator().manual_seed(77)
+        maps = [torch.randn(2, 256, 30 >> k, 34 >> k, generator=g) for k in range(2)]
+        cases = [_case(50 + k, 2, 1, 30 >> k, 34 >> k, 40 + 10 * k, zero_rows=3)[1:] for k in range(2)]
+        total = 90
+        rows = torch.randperm(total, generator=g).int().cuda()
+        dst = [rows[:40], rows[40:]]
+        live = [40, 33]                                              # the second list is only partly live
+        o7 = torch.full((total, 256, 7, 7), -7.0, device="cuda").contiguous(memory_format=cl)
+        o14 = torch.full((total, 256, 14, 14), -7.0, device="cuda").contiguous(memory_format=cl)
+        xs = [m.cuda().contiguous(memory_format=cl) for m in maps]
+        specs = []
+        for k in range(2):
+            cnt = torch.tensor(live[k], dtype=torch.int32, device="cuda")
+            specs.append(dict(image=xs[k], boxes=cases[k][0].cuda(), box_ind=cases[k][1].cuda(), size=7, out=o7, dst_row=dst[k], count=cnt))
+            specs.append(dict(image=xs[k], boxes=cases[k][0].cuda(), box_ind=cases[k][1].cuda(), size=14, out=o14, dst_row=dst[k],
+                              compact=(k == 0), count=cnt))
+        outs, comps = fi.crop_sets(specs)
+        for k in range(2):
+            n = live[k]
+            for P, out in ((7, outs[0]), (14, outs[1])):
+                want = clib.oracle_crop_and_resize_fwd(maps[k].numpy(), cases[k][0].numpy()[:n], cases[k][1].numpy()[:n], P, P, 0.0)
+                np.testing.assert_array_equal(out[dst[k][:n].long()].cpu().numpy(), want)
+                if n < len(dst[k]):                                 # rows past the count are not written
+                    assert bool((out[dst[k][n:].long()] == -7.0).all())
+        want = clib.oracle_crop_and_resize_fwd(maps[0].numpy(), cases[0][0].numpy(), cases[0][1].numpy(), 14, 14, 0.0)
+        np.testing.assert_array_equal(comps[1].cpu().numpy(), want)
+    finally:
+        fi.set_option("fwd_form", old)
+
+
 def test_known_answers():
     """SURVEY.md 8(c) i-vi: identity crop, constant image, linear ramp, extrapolation, P=1 centre, zero box."""
     fi = _fi()

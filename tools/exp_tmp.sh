@@ -1,7 +1,7 @@
-timeout 900 python -m pytest tests/test_ops_gpu.py tests/test_roi_align_gpu.py -m gpu -x -q -k "roi_pool or formulations or in_place or device_counts or golden or overflow" 2>&1 | tail -4
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"bin_enumerate|tile_prep" -c 6 --csv --log-file gpurun_out/r02_launches_enum3.csv python tools/bwd_ab.py --iters 2 > /dev/null 2>&1; grep -o '"[a-z_:A-Z ]*\(bin_enumerate\|tile_prep\)[^"]*".*' gpurun_out/r02_launches_enum3.csv | awk -F'","' '{print $1, $NF}' | tail -4
-timeout 120 python tools/bwd_ab.py --iters 12 --plan-in-backward --out gpurun_out/ab_enum3_all.json > /dev/null 2>gpurun_out/ab_enum3.err
-python - <<PY
-import json
-d=json.load(open("gpurun_out/ab_enum3_all.json")); print("all", round(d["bwd_ms_median"],4), round(d["bwd_ms_min"],4), d["fingerprints"][0][0])
-PY
+# round 2, session 2, call 1: full GPU suite, forward formulation sweep, ncu of the lean forward, bench line
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 > gpurun_out/s2c1_pytest.txt; cat gpurun_out/s2c1_pytest.txt
+timeout 300 python tools/fwd_ab.py --workload c2 --iters 20 --forms 1,0,3,4,5,6,1,0 --out gpurun_out/s2c1_fwd_ab_c2.json 2>gpurun_out/s2c1_fwd_ab_c2.err | tail -12
+timeout 300 python tools/fwd_ab.py --workload c5 --iters 10 --forms 1,0,3,4,5,6 --out gpurun_out/s2c1_fwd_ab_c5.json 2>gpurun_out/s2c1_fwd_ab_c5.err | tail -8
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:crop_fwd_nhwc_sets -c 2 -o gpurun_out/s2c1_ncu_fwd_lean -f python tools/fwd_ab.py --iters 1 --forms 0 > gpurun_out/s2c1_ncu.log 2>&1; tail -2 gpurun_out/s2c1_ncu.log
+timeout 600 python bench.py > gpurun_out/s2c1_bench.json 2> gpurun_out/s2c1_bench.err; tail -c 1500 gpurun_out/s2c1_bench.json
