@@ -95,35 +95,72 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) crop_fwd_nhwc_sets_kernel
 
 // Lean formulation (roi_align_fwd_lean.cuh): WARPS warps per block, MINB blocks per SM, persistent over the units.
 template <int VPL, int U, int WARPS, int MINB>
-__global__ void __launch_bounds__(WARPS * 32, MINB) crop_fwd_nhwc_lean_kernel(const FwdSet S, unsigned nunits, u64 nz) {
-    const int lane = threadIdx.x & 31;
-    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (unsigned u = warp; u < nunits; u += nwarps) fwd_unit_lean<VPL, U>(S, u, lane, nz);
+__global__ void __launch_bounds__(WARPS * 32, MINB) crop_fwd_nhwc_lean_kernel(const FwdSet S, unsigned nunits, unsigned chunk, u64 nz) {
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    for (unsigned c0 = blockIdx.x * chunk; c0 < nunits; c0 += gridDim.x * chunk) {        // chunks: see the level-batched kernel below
+        const unsigned c1 = min(c0 + chunk, nunits);
+        for (unsigned u = c0 + wib; u < c1; u += WARPS) fwd_unit_lean<VPL, U>(S, u, lane, nz);
+    }
 }
 
+// Level-batched launch.  Schedule (both measured, profiles/r02_fwd_ab_*.json):
+//   * PAIRS: Dev crops every small box twice from the same made-up map (7x7 for the box head, 14x14 for the mask head /
+//     critic).  Two consecutive sets with the same map, boxes and list are walked box by box -- the 7 rows of the 7x7 crop, then
+//     the 14 rows of the 14x14 crop -- so the second crop finds the box's pixels in L1 / L2 instead of reading them from DRAM a
+//     second time (as separate unit ranges the two passes over a 760 MB map are far apart in time).
+//   * CHUNKS: the unit sequence is cut into chunks of `chunk` units; chunk c goes to block c % gridDim.x, whose warps stride
+//     through it.  All rows of a box (which share image rows) and the spatially sorted neighbours that follow it then run on ONE
+//     SM close in time; with units dealt round-robin to all warps of the grid, neighbouring rows land on different SMs.
+struct FwdPlan {
+    unsigned pair_mask;           // bit k: sets k and k + 1 are interleaved by box (k + 1 is then skipped)
+    int chunk;                    // units per block chunk
+};
+
 template <int VPL, int U, int WARPS, int MINB>
-__global__ void __launch_bounds__(WARPS * 32, MINB) crop_fwd_nhwc_sets_lean_kernel(const FwdSets sets, u64 nz) {
-    __shared__ unsigned first[kMaxFwdSets + 1];         // prefix of the sets' LIVE unit counts (see crop_fwd_nhwc_sets_kernel)
+__global__ void __launch_bounds__(WARPS * 32, MINB) crop_fwd_nhwc_sets_lean_kernel(const FwdSets sets, const FwdPlan plan, u64 nz) {
+    // groups = single sets or pairs; prefix of their LIVE unit counts (see crop_fwd_nhwc_sets_kernel)
+    __shared__ unsigned gfirst[kMaxFwdSets + 1];
+    __shared__ int gset[kMaxFwdSets], ngroups;
     if (threadIdx.x == 0) {
         unsigned acc = 0;
+        int g = 0;
         for (int k = 0; k < sets.n; ++k) {
             const FwdSet &S = sets.s[k];
             const int R = S.R_dev ? max(0, min(*S.R_dev, S.R)) : S.R;
-            first[k] = acc;
-            acc += (unsigned)R * (unsigned)S.ph * (unsigned)S.slabs;
+            gfirst[g] = acc;
+            gset[g] = k;
+            unsigned rows = (unsigned)S.ph;
+            if ((plan.pair_mask >> k) & 1u) rows += (unsigned)sets.s[++k].ph;
+            acc += (unsigned)R * rows * (unsigned)S.slabs;
+            ++g;
         }
-        first[sets.n] = acc;
+        gfirst[g] = acc;
+        ngroups = g;
     }
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
-    const unsigned total = first[sets.n];
-    for (unsigned u = warp; u < total; u += nwarps) {
-        int k = 0;
-        while (u >= first[k + 1]) ++k;
-        fwd_unit_lean<VPL, U>(sets.s[k], u - first[k], lane, nz);
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned total = gfirst[ngroups];
+    const unsigned chunk = (unsigned)plan.chunk;
+    for (unsigned c0 = blockIdx.x * chunk; c0 < total; c0 += gridDim.x * chunk) {
+        const unsigned c1 = min(c0 + chunk, total);
+        for (unsigned u = c0 + wib; u < c1; u += WARPS) {
+            int g = 0;
+            while (u >= gfirst[g + 1]) ++g;
+            const int k = gset[g];
+            unsigned v = u - gfirst[g];
+            if (!((plan.pair_mask >> k) & 1u)) {
+                fwd_unit_lean<VPL, U>(sets.s[k], v, lane, nz);
+            } else {
+                const FwdSet &A = sets.s[k], &Bs = sets.s[k + 1];
+                const unsigned slabs = (unsigned)A.slabs, ua = (unsigned)A.ph * slabs, per = ua + (unsigned)Bs.ph * slabs;
+                const unsigned r = v / per;
+                unsigned w = v - r * per;
+                const FwdSet &S = (w < ua) ? A : Bs;
+                if (w >= ua) w -= ua;
+                const unsigned i = w / slabs;
+                fwd_unit_lean<VPL, U>(S, (int)r, (int)i, (int)(w - i * slabs), lane, nz);
+            }
+        }
     }
 }
 
@@ -441,19 +478,26 @@ int fi_nchw_backward_via_nhwc(const float *grads, const float *boxes, const int 
 // form 0 = default (kLeanDefault), 1 = round-1 unit (fwd_unit), 2.. = the other lean shapes kept for A/B runs.
 struct LeanShape { int vpl, u, warps, minb; };
 static const LeanShape kLeanShapes[] = {
-    {2, 2, 4, 5},   // form 2: both slabs per warp, 16 tap loads in flight, 20 warps / SM
-    {2, 2, 8, 2},   // form 3: the same at 16 warps / SM (round-1 occupancy)
-    {2, 1, 4, 8},   // form 4: 8 loads in flight, 32 warps / SM
-    {1, 4, 4, 5},   // form 5: one slab per warp, 16 loads in flight
-    {2, 3, 4, 4},   // form 6: both slabs per warp, 24 loads in flight, 16 warps / SM
+    {2, 2, 4, 5},   // form 2: both slabs per warp, 16 tap loads in flight, 20 warps / SM in blocks of 4 (96 registers)
+    {2, 2, 8, 2},   // form 3: 16 warps / SM in blocks of 8 (112 registers, nothing spilled) -- the default
+    {2, 2, 16, 1},  // form 4: one block of 16 warps / SM
+    {1, 4, 8, 2},   // form 5: one slab per warp, 16 loads in flight (also what depth % 256 != 0 falls back to)
+    {2, 2, 4, 4},   // form 6: blocks of 4 warps without the 96-register cap
 };
-constexpr int kLeanDefault = 2;
+constexpr int kLeanDefault = 3;
+constexpr int kLeanChunkDefault = 16;
 
 static int lean_shape_index() {           // -1: round-1 unit
     int form = option(FI_OPT_FWD_FORM);
     if (form == 0) form = kLeanDefault;
     if (form == 1) return -1;
     return form - 2;
+}
+
+static int lean_chunk(int warps) {         // units per block chunk: FI_OPT_FWD_CHUNK 1..6 -> 8, 16, 32, 64, 128, 256
+    const int copt = option(FI_OPT_FWD_CHUNK);
+    const int chunk = copt ? (4 << copt) : kLeanChunkDefault;
+    return chunk < warps ? warps : chunk;
 }
 
 static bool lean_ok(const void *image, const void *boxes, const void *crops, const void *crops2, int W, int C, int vpl, long units) {
@@ -463,19 +507,20 @@ static bool lean_ok(const void *image, const void *boxes, const void *crops, con
 
 template <int VPL, int U, int WARPS, int MINB>
 static void launch_lean_one(const FwdSet &S, unsigned nunits, cudaStream_t stream) {
-    crop_fwd_nhwc_lean_kernel<VPL, U, WARPS, MINB><<<grid_for(nunits, WARPS, MINB), WARPS * 32, 0, stream>>>(S, nunits, kNegZeroPair);
+    const unsigned chunk = (unsigned)lean_chunk(WARPS);
+    crop_fwd_nhwc_lean_kernel<VPL, U, WARPS, MINB><<<grid_for((nunits + chunk - 1) / chunk, 1, MINB), WARPS * 32, 0, stream>>>(S, nunits, chunk, kNegZeroPair);
 }
 template <int VPL, int U, int WARPS, int MINB>
-static void launch_lean_sets(const FwdSets &sets, long units, cudaStream_t stream) {
-    crop_fwd_nhwc_sets_lean_kernel<VPL, U, WARPS, MINB><<<grid_for(units, WARPS, MINB), WARPS * 32, 0, stream>>>(sets, kNegZeroPair);
+static void launch_lean_sets(const FwdSets &sets, const FwdPlan &plan, long units, cudaStream_t stream) {
+    crop_fwd_nhwc_sets_lean_kernel<VPL, U, WARPS, MINB><<<grid_for((units + plan.chunk - 1) / plan.chunk, 1, MINB), WARPS * 32, 0, stream>>>(sets, plan, kNegZeroPair);
 }
 #define FI_LEAN_DISPATCH(idx, CALL)                  \
     switch (idx) {                                   \
         case 0: CALL(2, 2, 4, 5); break;             \
         case 1: CALL(2, 2, 8, 2); break;             \
-        case 2: CALL(2, 1, 4, 8); break;             \
-        case 3: CALL(1, 4, 4, 5); break;             \
-        default: CALL(2, 3, 4, 4); break;            \
+        case 2: CALL(2, 2, 16, 1); break;            \
+        case 3: CALL(1, 4, 8, 2); break;             \
+        default: CALL(2, 2, 4, 4); break;            \
     }
 
 static int forward_impl(const float *image, int image_layout, const float *boxes, const int *box_ind, const int *dst_row, int R, int B, int H,
@@ -622,7 +667,20 @@ FI_API int fi_crop_sets_forward(const fi_fwd_set *sets, int num_sets, cudaStream
             all = all && lu < (1L << 31);
             if (all) {
                 for (int k = 0; k < dev.n; ++k) dev.s[k].slabs = dev.s[k].C / (128 * kLeanShapes[li].vpl);
-#define FI_CALL_SETS(V, UU, WW, MB) launch_lean_sets<V, UU, WW, MB>(dev, lu, stream)
+                FwdPlan plan;
+                const int popt = option(FI_OPT_FWD_PAIR);
+                plan.chunk = lean_chunk(kLeanShapes[li].warps);
+                plan.pair_mask = 0;
+                if (popt != 1)
+                    for (int k = 0; k + 1 < dev.n; ++k) {
+                        const FwdSet &A = dev.s[k], &Bs = dev.s[k + 1];
+                        if (A.image == Bs.image && A.boxes == Bs.boxes && A.box_ind == Bs.box_ind && A.R == Bs.R && A.R_dev == Bs.R_dev &&
+                            A.C == Bs.C && A.B == Bs.B && A.H == Bs.H && A.W == Bs.W) {
+                            plan.pair_mask |= 1u << k;
+                            ++k;
+                        }
+                    }
+#define FI_CALL_SETS(V, UU, WW, MB) launch_lean_sets<V, UU, WW, MB>(dev, plan, lu, stream)
                 FI_LEAN_DISPATCH(li, FI_CALL_SETS)
 #undef FI_CALL_SETS
                 return check_launch("fi_crop_sets_forward[lean]");

@@ -45,18 +45,12 @@ __device__ __forceinline__ void st_stream_v4(float *p, ulonglong2 v) { __stcs(re
 
 constexpr u64 kNegZeroPair = 0x8000000080000000ull;
 
-// unit = (box r, crop row i, slab of 128 * VPL channels).  S.slabs = C / (128 * VPL); W * C * 4 <= 2^30; units < 2^31.
+// unit = (box r, crop row i, slab of 128 * VPL channels).  W * C * 4 <= 2^30.
 template <int VPL, int U>
-__device__ __forceinline__ void fwd_unit_lean(const FwdSet &S, unsigned u, int lane, u64 nz) {
+__device__ __forceinline__ void fwd_unit_lean(const FwdSet &S, int r, int i, int slab, int lane, u64 nz) {
     const float *__restrict__ boxes = S.boxes;
     const int B = S.B, H = S.H, W = S.W, ph = S.ph, pw = S.pw, C = S.C;
-    unsigned q = u;
-    int coff = lane * 4;
-    if (S.slabs > 1) {
-        q = u / (unsigned)S.slabs;
-        coff += (int)(u - q * (unsigned)S.slabs) * (128 * VPL);
-    }
-    const int r = (int)(q / (unsigned)ph), i = (int)(q - (unsigned)r * (unsigned)ph);
+    const int coff = lane * 4 + slab * (128 * VPL);
     const int b = __ldg(S.box_ind + r);
     const long orow = S.dst_row ? (long)__ldg(S.dst_row + r) : (long)r;
     const long row_elems = (long)pw * C;
@@ -139,6 +133,19 @@ __device__ __forceinline__ void fwd_unit_lean(const FwdSet &S, unsigned u, int l
             }
         }
     }
+}
+
+// local unit index of a set -> (r, i, slab).  S.slabs = C / (128 * VPL); units < 2^31.
+template <int VPL, int U>
+__device__ __forceinline__ void fwd_unit_lean(const FwdSet &S, unsigned u, int lane, u64 nz) {
+    unsigned q = u;
+    int slab = 0;
+    if (S.slabs > 1) {
+        q = u / (unsigned)S.slabs;
+        slab = (int)(u - q * (unsigned)S.slabs);
+    }
+    const int r = (int)(q / (unsigned)S.ph);
+    fwd_unit_lean<VPL, U>(S, r, (int)(q - (unsigned)r * (unsigned)S.ph), slab, lane, nz);
 }
 
 }  // namespace fi

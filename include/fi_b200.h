@@ -45,7 +45,7 @@ unsigned long long fi_kernel_launches(void); /* kernels this library has launche
                                      accumulate kernel [FI_BWD_ACC=smem], 2 fused single tile kernel [FI_BWD_TILE=fused],
                                      3 vector reductions [FI_BWD=red] */
 #define FI_OPT_TILE_SHAPE 1       /* tile of forms 1 and 2: 0 = 4x8 (default), 1 = 4x4 [FI_TILE=4x4], 2 = 2x8 [FI_TILE=2x8] */
-#define FI_OPT_FWD_FORM 2         /* NHWC RoIAlign forward: 0 = default (the lean unit, both 128-channel slabs per warp, 20 warps / SM);
+#define FI_OPT_FWD_FORM 2         /* NHWC RoIAlign forward: 0 = default (the lean unit, both 128-channel slabs per warp, 2 x 8 warps / SM);
                                      1 = round-1 unit (one slab per warp, scalar lerps); 2..6 = lean shapes kept for A/B runs
                                      (csrc/roi_align.cu::kLeanShapes).  All forms give identical bits. [FI_FWD_FORM] */
 #define FI_OPT_SINKHORN_GENERIC 3 /* D = 1 problems: 0 = solved by classes, dense kernels only for what that leaves (default);
@@ -54,7 +54,9 @@ unsigned long long fi_kernel_launches(void); /* kernels this library has launche
 #define FI_OPT_PIX_CFG 4          /* form 0, ring shape (slots per batch x batches, CTAs per SM): 0 = 32x2,3 (default); 1 = 32x3,2;
                                      2 = 16x6,2; 3 = 16x4,3 [FI_PIX_CFG] */
 #define FI_OPT_PIX_GROUP 5        /* form 0, tiles per work ticket minus 1: 0..7 [FI_PIX_GROUP] */
-#define FI_OPT_COUNT 6
+#define FI_OPT_FWD_CHUNK 6        /* level-batched lean forward: units per block chunk; 0 = default (16), 1..6 = 8, 16, 32, 64, 128, 256 [FI_FWD_CHUNK] */
+#define FI_OPT_FWD_PAIR 7         /* level-batched lean forward: 0 / 2 = walk two sets over the same map and boxes box by box (default), 1 = off [FI_FWD_PAIR] */
+#define FI_OPT_COUNT 8
 int fi_set_option(int option, int value);
 int fi_get_option(int option);
 

@@ -228,33 +228,41 @@ def test_forward_forms_bit_identical(form):
             want[7] = 0
             got = fi.CropAndResizeFunction(ph, pw, extrap)(image.cuda().contiguous(memory_format=cl), rois.cuda(), box_ind.cuda())
             np.testing.assert_array_equal(got.cpu().numpy(), want, err_msg="C=%d crop %dx%d" % (C, ph, pw))
-        # level-batched launch: two maps, 7x7 + 14x14 into shared outputs by dst_row, a compact copy, a device-side count
+        # level-batched launch: two maps, 7x7 + 14x14 into shared outputs by dst_row, a compact copy, a device-side count; the 7x7 and
+        # 14x14 sets of a map share their box tensors (walked box by box as a pair unless fwd_pair = 1), every chunk size
         g = torch.Generator().manual_seed(77)
         maps = [torch.randn(2, 256, 30 >> k, 34 >> k, generator=g) for k in range(2)]
         cases = [_case(50 + k, 2, 1, 30 >> k, 34 >> k, 40 + 10 * k, zero_rows=3)[1:] for k in range(2)]
+        dev_cases = [(c[0].cuda(), c[1].cuda()) for c in cases]
         total = 90
         rows = torch.randperm(total, generator=g).int().cuda()
         dst = [rows[:40], rows[40:]]
         live = [40, 33]                                              # the second list is only partly live
-        o7 = torch.full((total, 256, 7, 7), -7.0, device="cuda").contiguous(memory_format=cl)
-        o14 = torch.full((total, 256, 14, 14), -7.0, device="cuda").contiguous(memory_format=cl)
         xs = [m.cuda().contiguous(memory_format=cl) for m in maps]
-        specs = []
-        for k in range(2):
-            cnt = torch.tensor(live[k], dtype=torch.int32, device="cuda")
-            specs.append(dict(image=xs[k], boxes=cases[k][0].cuda(), box_ind=cases[k][1].cuda(), size=7, out=o7, dst_row=dst[k], count=cnt))
-            specs.append(dict(image=xs[k], boxes=cases[k][0].cuda(), box_ind=cases[k][1].cuda(), size=14, out=o14, dst_row=dst[k],
-                              compact=(k == 0), count=cnt))
-        outs, comps = fi.crop_sets(specs)
-        for k in range(2):
-            n = live[k]
-            for P, out in ((7, outs[0]), (14, outs[1])):
-                want = clib.oracle_crop_and_resize_fwd(maps[k].numpy(), cases[k][0].numpy()[:n], cases[k][1].numpy()[:n], P, P, 0.0)
-                np.testing.assert_array_equal(out[dst[k][:n].long()].cpu().numpy(), want)
-                if n < len(dst[k]):                                 # rows past the count are not written
-                    assert bool((out[dst[k][n:].long()] == -7.0).all())
-        want = clib.oracle_crop_and_resize_fwd(maps[0].numpy(), cases[0][0].numpy(), cases[0][1].numpy(), 14, 14, 0.0)
-        np.testing.assert_array_equal(comps[1].cpu().numpy(), want)
+        cnts = [torch.tensor(live[k], dtype=torch.int32, device="cuda") for k in range(2)]
+        for chunk, pair in ((0, 0), (1, 1), (1, 2), (3, 0), (6, 1), (6, 2)):
+            oc, op = fi.set_option("fwd_chunk", chunk), fi.set_option("fwd_pair", pair)
+            try:
+                o7 = torch.full((total, 256, 7, 7), -7.0, device="cuda").contiguous(memory_format=cl)
+                o14 = torch.full((total, 256, 14, 14), -7.0, device="cuda").contiguous(memory_format=cl)
+                specs = []
+                for k in range(2):
+                    specs.append(dict(image=xs[k], boxes=dev_cases[k][0], box_ind=dev_cases[k][1], size=7, out=o7, dst_row=dst[k], count=cnts[k]))
+                    specs.append(dict(image=xs[k], boxes=dev_cases[k][0], box_ind=dev_cases[k][1], size=14, out=o14, dst_row=dst[k],
+                                      compact=(k == 0), count=cnts[k]))
+                outs, comps = fi.crop_sets(specs)
+                for k in range(2):
+                    n = live[k]
+                    for P, out in ((7, outs[0]), (14, outs[1])):
+                        want = clib.oracle_crop_and_resize_fwd(maps[k].numpy(), cases[k][0].numpy()[:n], cases[k][1].numpy()[:n], P, P, 0.0)
+                        np.testing.assert_array_equal(out[dst[k][:n].long()].cpu().numpy(), want, err_msg="chunk %d pair %d" % (chunk, pair))
+                        if n < len(dst[k]):                         # rows past the count are not written
+                            assert bool((out[dst[k][n:].long()] == -7.0).all())
+                want = clib.oracle_crop_and_resize_fwd(maps[0].numpy(), cases[0][0].numpy(), cases[0][1].numpy(), 14, 14, 0.0)
+                np.testing.assert_array_equal(comps[1].cpu().numpy(), want)
+            finally:
+                fi.set_option("fwd_chunk", oc)
+                fi.set_option("fwd_pair", op)
     finally:
         fi.set_option("fwd_form", old)
 

@@ -2,7 +2,9 @@
 fi.crop_sets (ONE launch), timed with CUDA events per formulation (fi_set_option fwd_form; L2 flushed between iterations),
 each formulation's outputs compared bit for bit with the round-1 unit (form 1).
 
-    python tools/fwd_ab.py --workload c2 --iters 20 --forms 1,0,3,4,5,6 --out gpurun_out/fwd_ab.json
+    python tools/fwd_ab.py --workload c2 --iters 20 --forms 1,0,3:1:1,3:2:2,4:3:2 --out gpurun_out/fwd_ab.json
+
+A configuration is fwd_form[:fwd_chunk[:fwd_pair]] (include/fi_b200.h FI_OPT_FWD_*).
 """
 import argparse
 import json
@@ -34,8 +36,11 @@ def main():
     flush = torch.empty(512 * 1024 * 1024 // 4, device=dev)
     want = None
     rows = []
-    for form in [int(f) for f in args.forms.split(",")]:
+    for cfg in args.forms.split(","):
+        form, chunk, pair = ([int(v) for v in cfg.split(":")] + [0, 0])[:3]
         fi.set_option("fwd_form", form)
+        fi.set_option("fwd_chunk", chunk)
+        fi.set_option("fwd_pair", pair)
         times = []
         res = None
         for it in range(args.iters + 3):
@@ -58,9 +63,10 @@ def main():
             want = got
         else:
             same = all(torch.equal(a.view(torch.int32), b.view(torch.int32)) for a, b in zip(got, want))
-        rows.append(dict(form=form, fwd_ms_median=round(times[len(times) // 2], 4), fwd_ms_min=round(times[0], 4), identical_to_first=same))
+        rows.append(dict(form=form, chunk=chunk, pair=pair, fwd_ms_median=round(times[len(times) // 2], 4), fwd_ms_min=round(times[0], 4), identical_to_first=same))
         print(rows[-1], flush=True)
-    fi.set_option("fwd_form", 0)
+    for k in ("fwd_form", "fwd_chunk", "fwd_pair"):
+        fi.set_option(k, 0)
     out = dict(workload=args.workload, rows=rows, small=split.small_cnt, big=split.big_cnt,
                note="time = one fi_crop_sets_forward launch + the Python call around it (a few us of host time, the launch is ~0.8 ms)")
     s = json.dumps(out)
