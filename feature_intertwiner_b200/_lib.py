@@ -56,6 +56,14 @@ SIGNATURES = {
     "fi_sinkhorn_workspace": (C.c_size_t, [_I, _I, _I, _I]),
     "fi_sinkhorn_ws": (_I, [_P, _P, _I, _I, _I, _F, _I, _P, _P, _P, _P, C.c_size_t, _P]),
     "fi_buffer_update": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "fi_merge_stats": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P]),
+    "fi_merge_stats_backward": (_I, [_P, _P, _I, _I, _I, _F, _P, _P]),
+    "fi_ot_head_prep": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
+    "fi_ot_head_combine": (_I, [_P, _P, _I, _P, _P]),
+    "fi_ot_head_dcritic": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P]),
+    "fi_relu_mask": (_I, [_P, _P, C.c_long, _P]),
+    "fi_ot_head_dsum": (_I, [_P, _P, _I, _I, _P, _P]),
+    "fi_centre_tap_embed": (_I, [_P, C.c_long, _P, _P]),
     "fi_nms_batched": (_I, [_P, _I, _I, _F, _P, _P, _P, _P]),
     "fi_nms_batched_topk": (_I, [_P, _I, _I, _F, _I, _P, _P, _P, _P]),
     "fi_proposal_decode": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _F, _F, _P, _P, _P]),

@@ -103,14 +103,16 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) crop_fwd_nhwc_lean_kernel(co
     }
 }
 
-// Level-batched launch.  Schedule (both measured, profiles/r02_fwd_ab_*.json):
+// Level-batched launch.  Schedule (measured, profiles/r02_fwd_ab_c2_v2.json):
 //   * PAIRS: Dev crops every small box twice from the same made-up map (7x7 for the box head, 14x14 for the mask head /
 //     critic).  Two consecutive sets with the same map, boxes and list are walked box by box -- the 7 rows of the 7x7 crop, then
 //     the 14 rows of the 14x14 crop -- so the second crop finds the box's pixels in L1 / L2 instead of reading them from DRAM a
-//     second time (as separate unit ranges the two passes over a 760 MB map are far apart in time).
+//     second time (as separate unit ranges the two passes over a 760 MB map are far apart in time): 0.736 -> 0.704 ms on C2.
 //   * CHUNKS: the unit sequence is cut into chunks of `chunk` units; chunk c goes to block c % gridDim.x, whose warps stride
-//     through it.  All rows of a box (which share image rows) and the spatially sorted neighbours that follow it then run on ONE
-//     SM close in time; with units dealt round-robin to all warps of the grid, neighbouring rows land on different SMs.
+//     through it.  chunk = warps per block (the default) deals consecutive units to consecutive warps of the whole grid: at any
+//     moment the machine works on ONE window of ~2400 consecutive crop rows (~110 spatially sorted boxes of one image), which
+//     is what L2 and the DRAM pages like.  Larger chunks (a block keeps a box and its neighbours to itself) were tried for L1
+//     reuse and are monotonically WORSE -- 0.83 ms at 16, 1.00 ms at 256: the window spreads over the whole map.
 struct FwdPlan {
     unsigned pair_mask;           // bit k: sets k and k + 1 are interleaved by box (k + 1 is then skipped)
     int chunk;                    // units per block chunk
@@ -485,7 +487,7 @@ static const LeanShape kLeanShapes[] = {
     {2, 2, 4, 4},   // form 6: blocks of 4 warps without the 96-register cap
 };
 constexpr int kLeanDefault = 3;
-constexpr int kLeanChunkDefault = 16;
+constexpr int kLeanChunkDefault = 0;      // 0: one unit per warp per pass (chunk = warps per block)
 
 static int lean_shape_index() {           // -1: round-1 unit
     int form = option(FI_OPT_FWD_FORM);

@@ -13,6 +13,7 @@ import ctypes as C
 import torch
 
 _PEER = {}        # group (None = default) -> PeerAllReduce used by all_reduce_sum_ for CUDA fp32 tensors that fit
+FUSED_MERGE = True   # merged_class_sums_pair on CUDA tensors: one kernel each way (False: the torch op sequence, kept for A/B tests)
 
 
 class PeerAllReduce(object):
@@ -171,10 +172,63 @@ def merged_class_sums(feat, cnt, group=None, distributed=False, differentiable=T
     return s, n
 
 
+class _MergeStats(torch.autograd.Function):
+    """_merge_feat_vec of both sets + the exchange, CUDA path: ONE kernel writes the un-normalised sums of the reliable and the
+    less-reliable set straight into the packed buffer the all-reduce works on (csrc/loss_head.cu::merge_stats_kernel), the
+    collective runs in place, and the four results are views of that buffer.  Backward is one kernel as well (through the
+    all-reduce's scale and the count weighting).  Replaces ~12 pointwise / reduction / cat launches each way."""
+
+    @staticmethod
+    def forward(ctx, big_feat, big_cnt, small_feat, small_cnt, group, distributed, compensate):
+        from . import _lib
+        G, S, Fd, ncls = small_feat.shape
+        bf, bc = big_feat.detach().contiguous(), big_cnt.detach().contiguous()
+        sf, sc = small_feat.detach().contiguous(), small_cnt.detach().contiguous()
+        a = Fd * ncls
+        packed = torch.empty((2 * (a + ncls),), device=sf.device, dtype=torch.float32)
+        with torch.cuda.device(sf.device):
+            _lib.check(_lib.lib().fi_merge_stats(_lib.ptr(bf), _lib.ptr(bc), _lib.ptr(sf), _lib.ptr(sc), G * S, Fd, ncls, _lib.ptr(packed),
+                                                 _lib.stream_ptr(sf.device)))
+        ctx.scale = 1.0
+        if distributed:
+            import torch.distributed as dist
+            all_reduce_sum_(packed, group)
+            ctx.scale = float(dist.get_world_size(group)) if compensate else 1.0
+        ctx.save_for_backward(sc)
+        ctx.dims = (G, S, Fd, ncls)
+        bs, bn = packed[:a].view(Fd, ncls), packed[a:a + ncls]
+        ss, sn = packed[a + ncls:2 * a + ncls].view(Fd, ncls), packed[2 * a + ncls:]
+        ctx.mark_non_differentiable(bs, bn, sn)
+        return bs, bn, ss, sn
+
+    @staticmethod
+    def backward(ctx, _dbs, _dbn, dss, _dsn):
+        from . import _lib
+        if dss is None or not ctx.needs_input_grad[2]:
+            return None, None, None, None, None, None, None
+        (sc,) = ctx.saved_tensors
+        G, S, Fd, ncls = ctx.dims
+        dss = dss.contiguous()
+        dsf = torch.empty((G, S, Fd, ncls), device=dss.device, dtype=torch.float32)
+        with torch.cuda.device(dss.device):
+            _lib.check(_lib.lib().fi_merge_stats_backward(_lib.ptr(dss), _lib.ptr(sc), G * S, Fd, ncls, ctx.scale, _lib.ptr(dsf),
+                                                          _lib.stream_ptr(dss.device)))
+        return None, None, dsf, None, None, None, None
+
+
+def _merge_kernel_ok(big_feat, big_cnt, small_feat, small_cnt):
+    ts = (big_feat, big_cnt, small_feat, small_cnt)
+    return all(t.is_cuda and t.dtype == torch.float32 for t in ts) and small_feat.dim() == 4 and big_feat.shape == small_feat.shape \
+        and big_cnt.numel() == small_cnt.numel() == small_feat.size(0) * small_feat.size(1) * small_feat.size(3) \
+        and not small_cnt.requires_grad
+
+
 def merged_class_sums_pair(big_feat, big_cnt, small_feat, small_cnt, group=None, distributed=False, compensate=True):
     """Both exchanges of an iteration -- reliable set (no gradient) and less-reliable set (differentiable) -- in ONE all-reduce of
     the packed sums: (big_sum [F,ncls], big_n [ncls], small_sum [F,ncls], small_n [ncls]).  At 1.3 MB the cost of an all-reduce on
     NVSwitch is its launch + latency, not bandwidth, so one call instead of two halves it."""
+    if FUSED_MERGE and _merge_kernel_ok(big_feat, big_cnt, small_feat, small_cnt):
+        return _MergeStats.apply(big_feat, big_cnt, small_feat, small_cnt, group, bool(distributed), bool(compensate))
     bs = (big_feat.detach() * big_cnt.detach()).sum(dim=(0, 1))
     bn = big_cnt.detach().sum(dim=(0, 1)).reshape(-1)
     ss = (small_feat * small_cnt).sum(dim=(0, 1))

@@ -11,25 +11,32 @@ import torch.nn as nn
 from . import _lib
 
 
+def sinkhorn_raw(x, y, inv_eps, L, need_grad):
+    """One batched launch (plus the large-D gradient launches) of csrc/sinkhorn.cu on [P,N,D] problems: (loss[P], dloss/dx, dloss/dy)
+    with the transport plan held constant (no_bp_P_L); the gradients are None unless ``need_grad``.  No autograd."""
+    if x.shape != y.shape or x.dim() != 3:
+        raise _lib.FiError("sinkhorn: x and y must both be [P,N,D]; got %s / %s" % (tuple(x.shape), tuple(y.shape)))
+    _lib.require_cuda(x, y)
+    x = x.detach().float().contiguous()
+    y = y.detach().float().contiguous()
+    P, N, D = x.shape
+    loss = torch.empty((P,), device=x.device, dtype=torch.float32)
+    gx = torch.empty_like(x) if need_grad else None
+    gy = torch.empty_like(y) if need_grad else None
+    L_ = _lib.lib()
+    nbytes = L_.fi_sinkhorn_workspace(P, N, D, 1 if need_grad else 0)          # large D: the gradient runs as its own launches
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=x.device) if nbytes else None
+    with torch.cuda.device(x.device):
+        _lib.check(L_.fi_sinkhorn_ws(_lib.ptr(x), _lib.ptr(y), P, N, D, float(inv_eps), int(L), _lib.ptr(loss),
+                                     _lib.ptr(gx), _lib.ptr(gy), _lib.ptr(ws), nbytes, _lib.stream_ptr(x.device)))
+    return loss, gx, gy
+
+
 class _Sinkhorn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, y, inv_eps, L):
-        if x.shape != y.shape or x.dim() != 3:
-            raise _lib.FiError("sinkhorn: x and y must both be [P,N,D]; got %s / %s" % (tuple(x.shape), tuple(y.shape)))
-        _lib.require_cuda(x, y)
-        x = x.detach().float().contiguous()
-        y = y.detach().float().contiguous()
-        P, N, D = x.shape
-        loss = torch.empty((P,), device=x.device, dtype=torch.float32)
         need_grad = any(ctx.needs_input_grad[:2])
-        gx = torch.empty_like(x) if need_grad else None
-        gy = torch.empty_like(y) if need_grad else None
-        L_ = _lib.lib()
-        nbytes = L_.fi_sinkhorn_workspace(P, N, D, 1 if need_grad else 0)          # large D: the gradient runs as its own launches
-        ws = torch.empty((nbytes,), dtype=torch.uint8, device=x.device) if nbytes else None
-        with torch.cuda.device(x.device):
-            _lib.check(L_.fi_sinkhorn_ws(_lib.ptr(x), _lib.ptr(y), P, N, D, float(inv_eps), int(L), _lib.ptr(loss),
-                                         _lib.ptr(gx), _lib.ptr(gy), _lib.ptr(ws), nbytes, _lib.stream_ptr(x.device)))
+        loss, gx, gy = sinkhorn_raw(x, y, inv_eps, L, need_grad)
         if need_grad:
             ctx.save_for_backward(gx, gy)
         return loss

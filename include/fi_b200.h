@@ -54,7 +54,8 @@ unsigned long long fi_kernel_launches(void); /* kernels this library has launche
 #define FI_OPT_PIX_CFG 4          /* form 0, ring shape (slots per batch x batches, CTAs per SM): 0 = 32x2,3 (default); 1 = 32x3,2;
                                      2 = 16x6,2; 3 = 16x4,3 [FI_PIX_CFG] */
 #define FI_OPT_PIX_GROUP 5        /* form 0, tiles per work ticket minus 1: 0..7 [FI_PIX_GROUP] */
-#define FI_OPT_FWD_CHUNK 6        /* level-batched lean forward: units per block chunk; 0 = default (16), 1..6 = 8, 16, 32, 64, 128, 256 [FI_FWD_CHUNK] */
+#define FI_OPT_FWD_CHUNK 6        /* level-batched lean forward: units per block chunk; 0 = default (warps per block: consecutive
+                                     units go to consecutive warps of the grid), 1..6 = 8, 16, 32, 64, 128, 256 (slower, kept for A/B) [FI_FWD_CHUNK] */
 #define FI_OPT_FWD_PAIR 7         /* level-batched lean forward: 0 / 2 = walk two sets over the same map and boxes box by box (default), 1 = off [FI_FWD_PAIR] */
 #define FI_OPT_COUNT 8
 int fi_set_option(int option, int value);
@@ -298,6 +299,32 @@ int fi_sinkhorn_ws(const float *x, const float *y, int n_problems, int N, int D,
  * overwrites (the reference instead shifts the whole buffer left each iteration, model.py:161-164). */
 int fi_buffer_update(const float *big_sum, const float *big_n, int B, int slot, int F, int ncls, float *buffer,
                      float *buffer_cnt, float *final_big, cudaStream_t stream);
+
+/* The pointwise steps of the class-level loss head between its library GEMMs, one launch each (csrc/loss_head.cu); fp32, every
+ * tensor contiguous.  n = ncls - 1 foreground classes.
+ *   fi_merge_stats           _merge_feat_vec (model.py:217-224): feat[GS,F,ncls], cnt[GS,ncls] of the reliable and the less-reliable
+ *                            set -> packed = [big_sum F*ncls | big_n ncls | small_sum F*ncls | small_n ncls], the all-reduce operand
+ *   fi_merge_stats_backward  d small_feat[GS,F,ncls] = d small_sum[F,ncls] * scale * small_cnt
+ *   fi_ot_head_prep          X[n,F] = (small_sum / (small_n + EPS))^T, Y[n,F] = final_big^T without the background class,
+ *                            mask[n] = class seen in this batch and present in the buffer (model.py:176-190)
+ *   fi_ot_head_combine       loss[n] = (2 w[0:n] - w[n:2n] - w[2n:3n]) * mask          (OT_module.py:78-80)
+ *   fi_ot_head_dcritic       the gradient of that combination through the Sinkhorn problems (cx,cy), (cx,cx), (cy,cy) -- gx, gy [3n,N]
+ *                            as fi_sinkhorn returns them, g[n] upstream -- and through the ReLU of Cc = [cx; cy] -> dC[2n,N]
+ *   fi_relu_mask             d[i] = 0 where h[i] <= 0 (ReLU backward, in place)
+ *   fi_ot_head_dsum          d small_sum[F,ncls] from dX[n,F] (the division and the transpose backwards; background column 0)
+ *   fi_centre_tap_embed      full[count,3] = (0, w1[count], 0): the gradient of Conv1d weight[:, :, 1] as the whole weight's */
+int fi_merge_stats(const float *big_feat, const float *big_cnt, const float *small_feat, const float *small_cnt, int GS, int F, int ncls,
+                   float *packed, cudaStream_t stream);
+int fi_merge_stats_backward(const float *d_small_sum, const float *small_cnt, int GS, int F, int ncls, float scale, float *d_small_feat,
+                            cudaStream_t stream);
+int fi_ot_head_prep(const float *final_big, const float *small_sum, const float *small_n, const float *buffer_cnt, int B, int F, int ncls,
+                    float *X, float *Y, float *mask, cudaStream_t stream);
+int fi_ot_head_combine(const float *w, const float *mask, int n, float *loss, cudaStream_t stream);
+int fi_ot_head_dcritic(const float *gx, const float *gy, const float *g, const float *mask, const float *Cc, int n, int N, float *dC,
+                       cudaStream_t stream);
+int fi_relu_mask(float *d, const float *h, long count, cudaStream_t stream);
+int fi_ot_head_dsum(const float *dX, const float *small_n, int F, int ncls, float *d_small_sum, cudaStream_t stream);
+int fi_centre_tap_embed(const float *w1, long count, float *full, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * 7. NMS with the reduce on the device (lib/nms/src/nms_cuda.c:17-67, no host round trip).

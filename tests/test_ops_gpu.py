@@ -365,6 +365,61 @@ def test_intertwiner_ot_padded_equals_compact():
     torch.testing.assert_close(s1.grad, s2.grad, rtol=1e-4, atol=1e-7)
 
 
+@pytest.mark.parametrize("surrogate", [False, True])
+def test_fused_loss_head_matches_torch_ops(surrogate, monkeypatch):
+    """The kernel-fused class-level OT head (dist._MergeStats + intertwiner._ClassOTHead: csrc/loss_head.cu between library GEMMs)
+    against the same head written in torch ops (fused_head = False, FUSED_MERGE = False): loss vector, buffers over two
+    iterations, and every gradient -- class means and the four OptTrans parameters.  With one feature position per row the real
+    Sinkhorn gradient is exactly zero behind the critic's ReLU, so the backward chain is ALSO run with a smooth stand-in for the
+    Sinkhorn launch (same call signature, patched under both heads) that gives dense, non-zero gradients."""
+    fi = _fi()
+    from feature_intertwiner_b200 import dist as fdist, ot as fot
+    if surrogate:
+        def fake(x, y, inv_eps, L, need_grad):
+            x, y = x.detach().float(), y.detach().float()
+            loss = (x * y).sum(dim=(1, 2)) * 1e-2 + 0.5e-2 * (x * x).sum(dim=(1, 2))
+            return loss, ((y + x) * 1e-2 if need_grad else None), (x * 1e-2 if need_grad else None)
+        monkeypatch.setattr(fot, "sinkhorn_raw", fake)
+    torch.manual_seed(11)
+    cfg = pyref.make_config(DEV__LOSS_CHOICE="ot")
+    ot_a = fi.OptTrans(cfg, ch_x=1024, L=5).cuda()
+    ot_b = fi.OptTrans(cfg, ch_x=1024, L=5).cuda()
+    ot_b.load_state_dict(ot_a.state_dict())
+    a = fi.IntertwinerLoss(cfg, ot_loss=ot_a, ot_padded=True).cuda()          # fused (default)
+    b = fi.IntertwinerLoss(cfg, ot_loss=ot_b, ot_padded=True).cuda()
+    b.fused_head = False
+    assert a.fused_head
+    for it in range(2):
+        cnt = torch.randint(0, 3, (1, 3, 1, 81)).float().cuda()
+        bf = torch.rand(1, 3, 1024, 81).cuda() * (cnt > 0)
+        scnt = torch.randint(0, 3, (1, 3, 1, 81)).float().cuda()
+        sf = (torch.rand(1, 3, 1024, 81).cuda() - 0.3) * (scnt > 0)
+        s1, s2 = sf.clone().requires_grad_(), sf.clone().requires_grad_()
+        up = torch.rand(80).cuda() + 0.5
+        n0 = fi.lib().fi_kernel_launches()
+        la = a([bf, cnt, s1, scnt, None, None])
+        assert fi.lib().fi_kernel_launches() - n0 >= 4             # merge, buffer update, prep, combine are this library's kernels
+        monkeypatch.setattr(fdist, "FUSED_MERGE", False)
+        lb = b([bf, cnt, s2, scnt, None, None])
+        monkeypatch.setattr(fdist, "FUSED_MERGE", True)
+        assert la.shape == lb.shape == (80,)
+        torch.testing.assert_close(la, lb, rtol=1e-5, atol=2e-6)
+        torch.testing.assert_close(a.buffer, b.buffer, rtol=1e-6, atol=1e-7)
+        assert torch.equal(a.buffer_cnt, b.buffer_cnt)
+        (la * up).sum().backward()
+        (lb * up).sum().backward()
+        torch.testing.assert_close(s1.grad, s2.grad, rtol=2e-4, atol=1e-7)
+        if surrogate:
+            assert float(s1.grad.abs().max()) > 0
+        for (name, pa), (_, pb) in zip(ot_a.named_parameters(), ot_b.named_parameters()):
+            assert pa.grad is not None and pb.grad is not None, name
+            torch.testing.assert_close(pa.grad, pb.grad, rtol=2e-4, atol=1e-6, msg=lambda m, name=name: "%s: %s" % (name, m))
+            if surrogate:
+                assert float(pa.grad.abs().max()) > 0, name
+            pa.grad = None
+            pb.grad = None
+
+
 @pytest.mark.parametrize("loss", ["l2", "ot"])
 def test_intertwiner_loss_cuda_graph_matches_eager(loss):
     """enable_cuda_graph(): graphed forward+backward of the loss head == eager, including the buffer's evolution."""

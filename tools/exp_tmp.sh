@@ -1,7 +1,13 @@
-# round 2, session 2, call 2: forward schedule sweep (shape x chunk x pairing), parity of the new schedules, ncu of the default
+# round 2, session 2, call 3: fused loss head + final forward default: full GPU suite, forward timing, ncu of the default forward, bench line, launch list
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_roi_align_gpu.py -m gpu -x -q -k "forward or crop_sets or full_size or golden or known" 2>&1 | tail -4 > gpurun_out/s2c2_pytest.txt; cat gpurun_out/s2c2_pytest.txt
-timeout 400 python tools/fwd_ab.py --workload c2 --iters 20 --forms 1,3:1:1,3:1:2,3:2:1,3:2:2,3:3:2,3:4:2,3:5:2,3:6:2,4:2:2,4:3:2,4:4:2,5:2:2,5:4:2,6:2:2,6:3:2,2:2:2,3:2:2,3:3:2 --out gpurun_out/s2c2_fwd_ab_c2.json 2>gpurun_out/s2c2_fwd_ab_c2.err | grep -v '^{"' 
-timeout 300 python tools/fwd_ab.py --workload c5 --iters 10 --forms 1,3:1:1,3:2:2,3:3:2,3:4:2,4:3:2,5:2:2,6:2:2 --out gpurun_out/s2c2_fwd_ab_c5.json 2>gpurun_out/s2c2_fwd_ab_c5.err | grep -v '^{"'
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:crop_fwd_nhwc_sets -c 1 -o gpurun_out/s2c2_ncu_fwd_lean -f python tools/fwd_ab.py --iters 1 --forms 0 > gpurun_out/s2c2_ncu.log 2>&1; tail -2 gpurun_out/s2c2_ncu.log
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:crop_fwd_nhwc_sets -c 1 -o gpurun_out/s2c2_ncu_fwd_lean_nopair -f python tools/fwd_ab.py --iters 1 --forms 3:1:1 > gpurun_out/s2c2_ncu2.log 2>&1; tail -2 gpurun_out/s2c2_ncu2.log
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/s2c3_pytest.txt; cat gpurun_out/s2c3_pytest.txt
+timeout 300 python tools/fwd_ab.py --workload c2 --iters 20 --forms 1,0,1,0 --out gpurun_out/s2c3_fwd_ab_c2.json 2>gpurun_out/s2c3_fwd_ab_c2.err | grep -v '^{"'
+timeout 300 python tools/fwd_ab.py --workload c5 --iters 10 --forms 1,0 --out gpurun_out/s2c3_fwd_ab_c5.json 2>gpurun_out/s2c3_fwd_ab_c5.err | grep -v '^{"'
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:crop_fwd_nhwc_sets -c 1 -o gpurun_out/s2c3_ncu_fwd_default -f python tools/fwd_ab.py --iters 1 --forms 0 > gpurun_out/s2c3_ncu.log 2>&1; tail -2 gpurun_out/s2c3_ncu.log
+timeout 600 python bench.py > gpurun_out/s2c3_bench.json 2> gpurun_out/s2c3_bench.err; tail -c 600 gpurun_out/s2c3_bench.err; python - <<'PY'
+import json
+for l in open('gpurun_out/s2c3_bench.json'):
+    if l.startswith('{'):
+        d=json.loads(l); print(d['ms_per_step'], d['value'], d['roofline']['frac'], d['intertwiner_loss'], d['gpu_launches_per_step'], {k:v.get('avg_ms') for k,v in d['kernels'].items()}, {k:v.get('ms_per_step') for k,v in d.get('other_workloads',{}).items()})
+PY
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/s2c3_launches.csv python bench.py --steps 2 --warmup 3 --no-other-workloads --no-cpu-baseline > gpurun_out/s2c3_launches_bench.log 2>&1; tail -c 300 gpurun_out/s2c3_launches_bench.log
