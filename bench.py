@@ -728,7 +728,9 @@ def run_ours(args):
     host_eager = 1e3 * timer.host_s / max(3, args.steps // 2)
     if step.grad_bucket is not None:
         step.grad_bucket.remove()       # the loss-only leg: statistics all-reduce included, OptTrans gradient all-reduce not
-    step.loss_mod.enable_cuda_graph([step.last_feat_in[0], step.last_feat_in[1], step.last_feat_in[2].detach().requires_grad_(), step.last_feat_in[3]])
+    loss_graphed = step.loss_mod.enable_cuda_graph([step.last_feat_in[0], step.last_feat_in[1], step.last_feat_in[2].detach().requires_grad_(),
+                                                    step.last_feat_in[3]])
+    loss_graph_error = getattr(step.loss_mod, "_graph_error", None)
     ms_loss = timer(step.loss_only, args.steps, args.warmup)          # intertwiner loss alone, fwd + bwd
     # all-reduce of the class statistics: bus bandwidth at this size (it is latency, not bandwidth, that matters at 1.3 MB)
     nvlink = None
@@ -836,7 +838,8 @@ def run_ours(args):
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "h2d_gbs_per_gpu": h2d_bytes / (ms_e2e - ms) / 1e6,
                 "bound": "the host->device copies (PCIe Gen5 x16: ~55 GB/s per GPU in practice); the step itself is %.1f %% of the e2e time" % (100.0 * ms / ms_e2e),
                 "host_buffers": "pinned, first-touched on the GPU's NUMA node: %s" % (numa,)},
-        "intertwiner_loss": {"ms_per_iter": ms_loss, "what": "statistics merge -> buffer update -> class match -> OptTrans / Sinkhorn(L=%d), "
+        "intertwiner_loss": {"ms_per_iter": ms_loss, "graphed": bool(loss_graphed), "graph_error": loss_graph_error,
+                             "what": "statistics merge -> buffer update -> class match -> OptTrans / Sinkhorn(L=%d), "
                              "%d classes, forward + backward, device-timed alone (it is also inside every step above)" % (wl["sinkhorn_iters"], NCLS - 1),
                              "gpu_vs_cpu_port_abs_diff": None},
         "gpu_launches": int(round(res["launches_per_step"] * args.steps)), "gpu_launches_per_step": res["launches_per_step"],

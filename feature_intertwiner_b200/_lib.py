@@ -62,6 +62,7 @@ SIGNATURES = {
     "fi_ot_head_combine": (_I, [_P, _P, _I, _P, _P]),
     "fi_ot_head_dcritic": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P]),
     "fi_relu_mask": (_I, [_P, _P, C.c_long, _P]),
+    "fi_col_sum": (_I, [_P, _I, _I, _P, _P]),
     "fi_ot_head_dsum": (_I, [_P, _P, _I, _I, _P, _P]),
     "fi_centre_tap_embed": (_I, [_P, C.c_long, _P, _P]),
     "fi_nms_batched": (_I, [_P, _I, _I, _F, _P, _P, _P, _P]),

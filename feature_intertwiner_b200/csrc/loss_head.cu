@@ -9,7 +9,7 @@
 //   ot_head_prep     final_small = sum / (n + EPS), comparison mask, and the [class, feature] transposes the critic wants
 //   ot_head_combine  2 W(x^,y) - W(x^,x^) - W(y,y), masked                                   (OT_module.py:78-80)
 //   ot_head_dcritic  gradient of that combination through the three Sinkhorn problems and the critic's ReLU
-//   relu_mask        ReLU backward in place
+//   relu_mask        ReLU backward in place;  col_sum: the bias gradients
 //   ot_head_dsum / merge_stats_bwd   back through the division and the transpose; through the all-reduce scale and the count weighting
 //   centre_tap_embed gradient of W[:, :, 1] as the full [out, in, 3] Conv1d weight gradient (zeros elsewhere)
 #include "fi_common.cuh"
@@ -107,6 +107,20 @@ __global__ void merge_stats_bwd_kernel(const float *__restrict__ dss, const floa
     }
 }
 
+// dst[c] = sum over rows of src[r, c] (bias gradients: a few hundred rows at most; one thread per column, coalesced across columns)
+__global__ void col_sum_kernel(const float *__restrict__ src, int rows, int cols, float *__restrict__ dst) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int r = 0;
+    for (; r + 4 <= rows; r += 4) {
+        a0 += src[(long)r * cols + c]; a1 += src[(long)(r + 1) * cols + c];
+        a2 += src[(long)(r + 2) * cols + c]; a3 += src[(long)(r + 3) * cols + c];
+    }
+    for (; r < rows; ++r) a0 += src[(long)r * cols + c];
+    dst[c] = (a0 + a1) + (a2 + a3);
+}
+
 __global__ void centre_tap_embed_kernel(const float *__restrict__ w1, long count, float *__restrict__ full) {
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < count; e += (long)gridDim.x * blockDim.x) {
         full[3 * e + 0] = 0.f;
@@ -170,6 +184,12 @@ FI_API int fi_merge_stats_backward(const float *d_small_sum, const float *small_
     FI_REQUIRE(GS >= 1 && F > 0 && ncls > 0 && d_small_sum && small_cnt && d_small_feat, "fi_merge_stats_backward: bad arguments");
     merge_stats_bwd_kernel<<<grid_1d((long)F * ncls, 256), 256, 0, stream>>>(d_small_sum, small_cnt, GS, F, ncls, scale, d_small_feat);
     return check_launch("fi_merge_stats_backward");
+}
+
+FI_API int fi_col_sum(const float *src, int rows, int cols, float *dst, cudaStream_t stream) {
+    FI_REQUIRE(rows >= 0 && cols > 0 && src && dst, "fi_col_sum: bad arguments");
+    col_sum_kernel<<<ceil_div(cols, 64), 64, 0, stream>>>(src, rows, cols, dst);
+    return check_launch("fi_col_sum");
 }
 
 FI_API int fi_centre_tap_embed(const float *w1, long count, float *full, cudaStream_t stream) {

@@ -199,6 +199,7 @@ class _MergeStats(torch.autograd.Function):
         bs, bn = packed[:a].view(Fd, ncls), packed[a:a + ncls]
         ss, sn = packed[a + ncls:2 * a + ncls].view(Fd, ncls), packed[2 * a + ncls:]
         ctx.mark_non_differentiable(bs, bn, sn)
+        ctx.set_materialize_grads(False)          # no zero-filled gradients for the three outputs nothing differentiates
         return bs, bn, ss, sn
 
     @staticmethod

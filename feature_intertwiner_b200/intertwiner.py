@@ -565,6 +565,17 @@ def pyramid_roi_align(inputs, pool_size, image_shape, base=224.):
 
 
 # ----------------------------------------------------------------------------------------------- meta loss
+def _linear_relu(bias, x, w, out):
+    """out = relu(x @ w^T + bias): one cuBLASLt call with the bias + ReLU epilogue where torch offers it, else addmm + relu_."""
+    fused = getattr(torch, "_addmm_activation", None)
+    if fused is not None:
+        fused(bias, x, w.t(), out=out)
+    else:
+        torch.addmm(bias, x, w.t(), out=out)
+        out.relu_()
+    return out
+
+
 class _ClassOTHead(torch.autograd.Function):
     """The class-level OT loss head after the buffer update, 1-D OptTrans (lib/model.py:176-207 + lib/OT_module.py:67-102), with
     every pointwise step a kernel of csrc/loss_head.cu and the dense products library GEMMs:
@@ -595,10 +606,9 @@ class _ClassOTHead(torch.autograd.Function):
             _lib.check(L_.fi_ot_head_prep(_lib.ptr(final_big), _lib.ptr(s_sum), _lib.ptr(s_n), _lib.ptr(buffer_cnt), buffer_cnt.size(0), Fd, ncls,
                                           _lib.ptr(X), _lib.ptr(Z[n:]), _lib.ptr(mask), st))
         Wg1, Wc1 = Wg.detach()[:, :, 1].contiguous(), Wc.detach()[:, :, 1].contiguous()    # Conv1d(k=3, pad=1) on length 1: the centre tap
-        torch.addmm(bg.detach(), X, Wg1.t(), out=Z[:n])
-        Z[:n].relu_()
-        Cc = torch.addmm(bc.detach(), Z, Wc1.t())
-        Cc.relu_()
+        Cc = torch.empty((2 * n, N), device=dev, dtype=torch.float32)
+        _linear_relu(bg.detach(), X, Wg1, Z[:n])
+        _linear_relu(bc.detach(), Z, Wc1, Cc)
         cx, cy = Cc[:n], Cc[n:]
         need = any(ctx.needs_input_grad)
         w, gx, gy = sinkhorn_raw(torch.cat([cx, cx, cy]).unsqueeze(2), torch.cat([cy, cx, cy]).unsqueeze(2), mod.ot_loss.epsilon, mod.ot_loss.L, need)
@@ -624,7 +634,10 @@ class _ClassOTHead(torch.autograd.Function):
         dC = torch.empty((2 * n, N), device=dev, dtype=torch.float32)
         with torch.cuda.device(dev):
             _lib.check(L_.fi_ot_head_dcritic(_lib.ptr(gx), _lib.ptr(gy), _lib.ptr(g), _lib.ptr(mask), _lib.ptr(Cc), n, N, _lib.ptr(dC), st))
-            dbc = dC.sum(dim=0) if need[7] else None
+            dbc = None
+            if need[7]:
+                dbc = torch.empty((N,), device=dev, dtype=torch.float32)
+                _lib.check(L_.fi_col_sum(_lib.ptr(dC), 2 * n, N, _lib.ptr(dbc), st))
             dWc = None
             if need[6]:
                 dWc = torch.empty(ctx.wshapes[1], device=dev, dtype=torch.float32)
@@ -635,7 +648,8 @@ class _ClassOTHead(torch.autograd.Function):
                 dH = dC[:n].mm(Wc1)
                 _lib.check(L_.fi_relu_mask(_lib.ptr(dH), _lib.ptr(Z), dH.numel(), st))          # Z[:n] = H
                 if need[5]:
-                    dbg = dH.sum(dim=0)
+                    dbg = torch.empty((Fd,), device=dev, dtype=torch.float32)
+                    _lib.check(L_.fi_col_sum(_lib.ptr(dH), n, Fd, _lib.ptr(dbg), st))
                 if need[4]:
                     dWg = torch.empty(ctx.wshapes[0], device=dev, dtype=torch.float32)
                     dWg1 = dH.t().mm(X)

@@ -311,6 +311,7 @@ int fi_buffer_update(const float *big_sum, const float *big_n, int B, int slot, 
  *   fi_ot_head_dcritic       the gradient of that combination through the Sinkhorn problems (cx,cy), (cx,cx), (cy,cy) -- gx, gy [3n,N]
  *                            as fi_sinkhorn returns them, g[n] upstream -- and through the ReLU of Cc = [cx; cy] -> dC[2n,N]
  *   fi_relu_mask             d[i] = 0 where h[i] <= 0 (ReLU backward, in place)
+ *   fi_col_sum               dst[cols] = column sums of src[rows,cols] (bias gradients)
  *   fi_ot_head_dsum          d small_sum[F,ncls] from dX[n,F] (the division and the transpose backwards; background column 0)
  *   fi_centre_tap_embed      full[count,3] = (0, w1[count], 0): the gradient of Conv1d weight[:, :, 1] as the whole weight's */
 int fi_merge_stats(const float *big_feat, const float *big_cnt, const float *small_feat, const float *small_cnt, int GS, int F, int ncls,
@@ -323,6 +324,7 @@ int fi_ot_head_combine(const float *w, const float *mask, int n, float *loss, cu
 int fi_ot_head_dcritic(const float *gx, const float *gy, const float *g, const float *mask, const float *Cc, int n, int N, float *dC,
                        cudaStream_t stream);
 int fi_relu_mask(float *d, const float *h, long count, cudaStream_t stream);
+int fi_col_sum(const float *src, int rows, int cols, float *dst, cudaStream_t stream);
 int fi_ot_head_dsum(const float *dX, const float *small_n, int F, int ncls, float *d_small_sum, cudaStream_t stream);
 int fi_centre_tap_embed(const float *w1, long count, float *full, cudaStream_t stream);
 
