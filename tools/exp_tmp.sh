@@ -1,10 +1,10 @@
-# round 2, session 2, call 4: loss-head graph diagnosis, fused head v2 (fused ReLU epilogue, column sums), bench
+# round 2, session 2, call 5 (2 GPUs): NCCL parity tests of the sharded step with the kernel merge, N=2 bench line
 mkdir -p gpurun_out
-timeout 300 python tools/diag_loss_graph.py > gpurun_out/s2c4_diag.txt 2>&1; grep -v Warning gpurun_out/s2c4_diag.txt | tail -30
-timeout 600 python -m pytest tests/test_ops_gpu.py -m gpu -x -q 2>&1 | tail -3
-timeout 600 python bench.py > gpurun_out/s2c4_bench.json 2> gpurun_out/s2c4_bench.err; python - <<'PY'
+timeout 600 python -m pytest tests/test_dist_gpu.py -m gpu -x -q 2>&1 | tail -4
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 10 --warmup 3 --no-other-workloads > gpurun_out/s2c5_bench_n2.json 2> gpurun_out/s2c5_bench_n2.err; python - <<'PY'
 import json
-for l in open('gpurun_out/s2c4_bench.json'):
+for l in open('gpurun_out/s2c5_bench_n2.json'):
     if l.startswith('{'):
-        d=json.loads(l); print(d['ms_per_step'], d['value'], d['roofline']['frac'], d['intertwiner_loss'], d['gpu_launches_per_step'], {k:v.get('avg_ms') for k,v in d['kernels'].items()}, {k:v.get('ms_per_step') for k,v in d.get('other_workloads',{}).items()})
+        d=json.loads(l); print(d['n_gpus'], d['ms_per_step'], d['value'], d['config'].get('step'), d['intertwiner_loss'], d['gpu_launches_per_step'], d.get('nvlink',{}).get('class_stats_allreduce_peer_kernel'))
 PY
+tail -c 400 gpurun_out/s2c5_bench_n2.err
