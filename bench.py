@@ -650,6 +650,14 @@ class Timer(object):
         # barrier + synchronize LAST, right before the first timed step: the collection above takes tens of ms and a different
         # time on every rank -- with the barrier in front of it the first step of the early ranks timed their wait for the late ones
         self.barrier()
+        if self.world > 1:
+            # ... and a DEVICE-side rendezvous behind it: the ranks leave the host barrier up to a few hundred microseconds apart,
+            # which the first timed step would otherwise spend waiting for its peers inside the statistics exchange.  The tiny
+            # all-reduce completes on every GPU at the same moment, with the first step already queued behind it.
+            import torch.distributed as dist
+            if getattr(self, "_rdv", None) is None:
+                self._rdv = torch.zeros(1, device=self.dev)
+            dist.all_reduce(self._rdv)
         self.host_s = 0.0
         launch0 = self.lib.fi_kernel_launches()
         for _ in range(steps):
