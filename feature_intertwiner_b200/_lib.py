@@ -165,7 +165,7 @@ FI_LAYOUT_NCHW = 0
 FI_LAYOUT_NHWC = 1
 
 # fi_set_option keys (include/fi_b200.h)
-OPTIONS = {"bwd_form": 0, "tile_shape": 1, "fwd_form": 2, "sinkhorn_generic": 3, "pix_cfg": 4, "pix_group": 5, "fwd_chunk": 6, "fwd_pair": 7}
+OPTIONS = {"bwd_form": 0, "tile_shape": 1, "fwd_form": 2, "sinkhorn_generic": 3, "pix_cfg": 4, "pix_group": 5, "fwd_chunk": 6, "fwd_pair": 7, "fwd_sched": 8}
 BWD_FORMS = {"pix": 0, "smem": 1, "fused": 2, "red": 3}
 
 

@@ -41,6 +41,7 @@ static void init_options() {
     if ((v = getenv("FI_PIX_CFG")) && v[0] >= '0' && v[0] <= '3') g_options[FI_OPT_PIX_CFG] = v[0] - '0';
     if ((v = getenv("FI_FWD_FORM")) && v[0] >= '0' && v[0] <= '6') g_options[FI_OPT_FWD_FORM] = v[0] - '0';
     if ((v = getenv("FI_FWD_CHUNK")) && v[0] >= '0' && v[0] <= '6') g_options[FI_OPT_FWD_CHUNK] = v[0] - '0';
+    if ((v = getenv("FI_FWD_SCHED")) && v[0] >= '0' && v[0] <= '2') g_options[FI_OPT_FWD_SCHED] = v[0] - '0';
     if ((v = getenv("FI_FWD_PAIR")) && v[0] >= '0' && v[0] <= '2') g_options[FI_OPT_FWD_PAIR] = v[0] - '0';
     g_options[FI_OPT_PIX_GROUP] = 1;
     if ((v = getenv("FI_PIX_GROUP")) && v[0] >= '0' && v[0] <= '7') g_options[FI_OPT_PIX_GROUP] = v[0] - '0';
@@ -69,7 +70,7 @@ FI_API int fi_get_option(int opt) {
     return fi::option(opt);
 }
 FI_API int fi_set_option(int opt, int value) {
-    static const int limit[FI_OPT_COUNT] = {3, 2, 6, 2, 3, 7, 6, 2};
+    static const int limit[FI_OPT_COUNT] = {3, 2, 6, 2, 3, 7, 6, 2, 2};
     if (opt < 0 || opt >= FI_OPT_COUNT || value < 0 || value > limit[opt]) {
         fi::set_error(FI_ERR_INVALID, "fi_set_option: option %d value %d", opt, value);
         return FI_ERR_INVALID;

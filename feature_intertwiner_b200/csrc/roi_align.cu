@@ -113,12 +113,41 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) crop_fwd_nhwc_lean_kernel(co
 //     moment the machine works on ONE window of ~2400 consecutive crop rows (~110 spatially sorted boxes of one image), which
 //     is what L2 and the DRAM pages like.  Larger chunks (a block keeps a box and its neighbours to itself) were tried for L1
 //     reuse and are monotonically WORSE -- 0.83 ms at 16, 1.00 ms at 256: the window spreads over the whole map.
+//   * TICKETS: ncu on the static schedule shows the SMs' active cycles spread from 1.07 M to 1.29 M around a mean of 1.13 M
+//     (profiles/r02_ncu_fwd_lean_v2_default.txt): equal SHARES are not equal TIMES -- GPCs hold different numbers of SMs behind the
+//     same port into L2, half of L2 is on the other die -- and the launch lasts as long as its slowest SM.  With tickets every
+//     warp draws its next `grab` consecutive units from one counter in global memory (the draw for the NEXT units is issued
+//     before the current ones are processed, so its round trip is hidden); units are still handed out in order, i.e. the
+//     machine-wide window stays contiguous, and a warp that draws rows i, i + 1 of a box re-uses the image row they share from
+//     L1.  The counter resets itself: the last block to finish zeroes it for the next launch that is given the same slot.
 struct FwdPlan {
     unsigned pair_mask;           // bit k: sets k and k + 1 are interleaved by box (k + 1 is then skipped)
-    int chunk;                    // units per block chunk
+    int chunk;                    // static schedule: units per block chunk
+    int grab;                     // ticket schedule: units per draw; 0 = static schedule
+    int slot;                     // ticket schedule: which counter pair of g_fwd_tickets
 };
 
-template <int VPL, int U, int WARPS, int MINB>
+constexpr int kTicketSlots = 256;
+__device__ unsigned g_fwd_tickets[2 * kTicketSlots];      // per slot: next unit, finished blocks
+
+__device__ __forceinline__ unsigned draw_ticket(unsigned *next, unsigned grab, int lane) {
+    unsigned u = 0;
+    if (lane == 0) u = atomicAdd(next, grab);
+    return __shfl_sync(0xffffffffu, u, 0);
+}
+__device__ __forceinline__ void retire_tickets(unsigned *next, unsigned *done) {      // every block, after its last draw
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(done, 1u) == gridDim.x - 1) {
+            *next = 0u;
+            *done = 0u;
+            __threadfence();
+        }
+    }
+}
+
+template <int VPL, int U, int WARPS, int MINB, bool TICKETS>
 __global__ void __launch_bounds__(WARPS * 32, MINB) crop_fwd_nhwc_sets_lean_kernel(const FwdSets sets, const FwdPlan plan, u64 nz) {
     // groups = single sets or pairs; prefix of their LIVE unit counts (see crop_fwd_nhwc_sets_kernel)
     __shared__ unsigned gfirst[kMaxFwdSets + 1];
@@ -142,26 +171,36 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) crop_fwd_nhwc_sets_lean_kern
     __syncthreads();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const unsigned total = gfirst[ngroups];
-    const unsigned chunk = (unsigned)plan.chunk;
-    for (unsigned c0 = blockIdx.x * chunk; c0 < total; c0 += gridDim.x * chunk) {
-        const unsigned c1 = min(c0 + chunk, total);
-        for (unsigned u = c0 + wib; u < c1; u += WARPS) {
-            int g = 0;
-            while (u >= gfirst[g + 1]) ++g;
-            const int k = gset[g];
-            unsigned v = u - gfirst[g];
-            if (!((plan.pair_mask >> k) & 1u)) {
-                fwd_unit_lean<VPL, U>(sets.s[k], v, lane, nz);
-            } else {
-                const FwdSet &A = sets.s[k], &Bs = sets.s[k + 1];
-                const unsigned slabs = (unsigned)A.slabs, ua = (unsigned)A.ph * slabs, per = ua + (unsigned)Bs.ph * slabs;
-                const unsigned r = v / per;
-                unsigned w = v - r * per;
-                const FwdSet &S = (w < ua) ? A : Bs;
-                if (w >= ua) w -= ua;
-                const unsigned i = w / slabs;
-                fwd_unit_lean<VPL, U>(S, (int)r, (int)i, (int)(w - i * slabs), lane, nz);
-            }
+    auto unit = [&](unsigned u) {                                  // unit -> (set, box, crop row, slab); ONE inlined copy of the unit
+        int g = 0;
+        while (u >= gfirst[g + 1]) ++g;
+        int k = gset[g];
+        const unsigned v = u - gfirst[g];
+        const unsigned slabs = (unsigned)sets.s[k].slabs, ua = (unsigned)sets.s[k].ph * slabs;
+        unsigned per = ua;
+        if ((plan.pair_mask >> k) & 1u) per += (unsigned)sets.s[k + 1].ph * slabs;
+        const unsigned r = v / per;
+        unsigned w = v - r * per;
+        if (w >= ua) { w -= ua; ++k; }                             // second set of a pair
+        const unsigned i = w / slabs;
+        fwd_unit_lean<VPL, U>(sets.s[k], (int)r, (int)i, (int)(w - i * slabs), lane, nz);
+    };
+    if (TICKETS) {
+        unsigned *next = g_fwd_tickets + 2 * plan.slot, *done = next + 1;
+        const unsigned grab = (unsigned)plan.grab;
+        unsigned u = draw_ticket(next, grab, lane);
+        while (u < total) {
+            const unsigned un = draw_ticket(next, grab, lane);     // in flight while this draw's units are processed
+            const unsigned ue = min(u + grab, total);
+            for (; u < ue; ++u) unit(u);
+            u = un;
+        }
+        retire_tickets(next, done);
+    } else {
+        const unsigned chunk = (unsigned)plan.chunk;
+        for (unsigned c0 = blockIdx.x * chunk; c0 < total; c0 += gridDim.x * chunk) {
+            const unsigned c1 = min(c0 + chunk, total);
+            for (unsigned u = c0 + wib; u < c1; u += WARPS) unit(u);
         }
     }
 }
@@ -487,6 +526,7 @@ static const LeanShape kLeanShapes[] = {
     {2, 2, 4, 4},   // form 6: blocks of 4 warps without the 96-register cap
 };
 constexpr int kLeanDefault = 3;
+constexpr int kLeanGrabDefault = 2;       // ticket schedule: units per draw
 constexpr int kLeanChunkDefault = 0;      // 0: one unit per warp per pass (chunk = warps per block)
 
 static int lean_shape_index() {           // -1: round-1 unit
@@ -514,7 +554,12 @@ static void launch_lean_one(const FwdSet &S, unsigned nunits, cudaStream_t strea
 }
 template <int VPL, int U, int WARPS, int MINB>
 static void launch_lean_sets(const FwdSets &sets, const FwdPlan &plan, long units, cudaStream_t stream) {
-    crop_fwd_nhwc_sets_lean_kernel<VPL, U, WARPS, MINB><<<grid_for((units + plan.chunk - 1) / plan.chunk, 1, MINB), WARPS * 32, 0, stream>>>(sets, plan, kNegZeroPair);
+    if (plan.grab > 0) {
+        const long per_block = (long)plan.grab * WARPS;
+        crop_fwd_nhwc_sets_lean_kernel<VPL, U, WARPS, MINB, true><<<grid_for((units + per_block - 1) / per_block, 1, MINB), WARPS * 32, 0, stream>>>(sets, plan, kNegZeroPair);
+    } else {
+        crop_fwd_nhwc_sets_lean_kernel<VPL, U, WARPS, MINB, false><<<grid_for((units + plan.chunk - 1) / plan.chunk, 1, MINB), WARPS * 32, 0, stream>>>(sets, plan, kNegZeroPair);
+    }
 }
 #define FI_LEAN_DISPATCH(idx, CALL)                  \
     switch (idx) {                                   \
@@ -670,8 +715,16 @@ FI_API int fi_crop_sets_forward(const fi_fwd_set *sets, int num_sets, cudaStream
             if (all) {
                 for (int k = 0; k < dev.n; ++k) dev.s[k].slabs = dev.s[k].C / (128 * kLeanShapes[li].vpl);
                 FwdPlan plan;
-                const int popt = option(FI_OPT_FWD_PAIR);
+                const int popt = option(FI_OPT_FWD_PAIR), sopt = option(FI_OPT_FWD_SCHED);
                 plan.chunk = lean_chunk(kLeanShapes[li].warps);
+                plan.grab = 0;
+                plan.slot = 0;
+                if (sopt != 1) {                                   // tickets (default): units per draw 1..6 -> 1, 2, 3, 4, 7, 14
+                    static const int kGrab[7] = {kLeanGrabDefault, 1, 2, 3, 4, 7, 14};
+                    static unsigned next_slot = 0;
+                    plan.grab = kGrab[option(FI_OPT_FWD_CHUNK)];
+                    plan.slot = (int)(__atomic_fetch_add(&next_slot, 1u, __ATOMIC_RELAXED) % kTicketSlots);
+                }
                 plan.pair_mask = 0;
                 if (popt != 1)
                     for (int k = 0; k + 1 < dev.n; ++k) {

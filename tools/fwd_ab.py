@@ -4,7 +4,7 @@ each formulation's outputs compared bit for bit with the round-1 unit (form 1).
 
     python tools/fwd_ab.py --workload c2 --iters 20 --forms 1,0,3:1:1,3:2:2,4:3:2 --out gpurun_out/fwd_ab.json
 
-A configuration is fwd_form[:fwd_chunk[:fwd_pair]] (include/fi_b200.h FI_OPT_FWD_*).
+A configuration is fwd_form[:fwd_chunk[:fwd_pair[:fwd_sched]]] (include/fi_b200.h FI_OPT_FWD_*).
 """
 import argparse
 import json
@@ -37,10 +37,11 @@ def main():
     want = None
     rows = []
     for cfg in args.forms.split(","):
-        form, chunk, pair = ([int(v) for v in cfg.split(":")] + [0, 0])[:3]
+        form, chunk, pair, sched = ([int(v) for v in cfg.split(":")] + [0, 0, 0])[:4]
         fi.set_option("fwd_form", form)
         fi.set_option("fwd_chunk", chunk)
         fi.set_option("fwd_pair", pair)
+        fi.set_option("fwd_sched", sched)
         times = []
         res = None
         for it in range(args.iters + 3):
@@ -63,9 +64,9 @@ def main():
             want = got
         else:
             same = all(torch.equal(a.view(torch.int32), b.view(torch.int32)) for a, b in zip(got, want))
-        rows.append(dict(form=form, chunk=chunk, pair=pair, fwd_ms_median=round(times[len(times) // 2], 4), fwd_ms_min=round(times[0], 4), identical_to_first=same))
+        rows.append(dict(form=form, chunk=chunk, pair=pair, sched=sched, fwd_ms_median=round(times[len(times) // 2], 4), fwd_ms_min=round(times[0], 4), identical_to_first=same))
         print(rows[-1], flush=True)
-    for k in ("fwd_form", "fwd_chunk", "fwd_pair"):
+    for k in ("fwd_form", "fwd_chunk", "fwd_pair", "fwd_sched"):
         fi.set_option(k, 0)
     out = dict(workload=args.workload, rows=rows, small=split.small_cnt, big=split.big_cnt,
                note="time = one fi_crop_sets_forward launch + the Python call around it (a few us of host time, the launch is ~0.8 ms)")
