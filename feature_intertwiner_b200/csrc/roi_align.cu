@@ -118,8 +118,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) crop_fwd_nhwc_lean_kernel(co
 //     same port into L2, half of L2 is on the other die -- and the launch lasts as long as its slowest SM.  With tickets every
 //     warp draws its next `grab` consecutive units from one counter in global memory (the draw for the NEXT units is issued
 //     before the current ones are processed, so its round trip is hidden); units are still handed out in order, i.e. the
-//     machine-wide window stays contiguous, and a warp that draws rows i, i + 1 of a box re-uses the image row they share from
-//     L1.  The counter resets itself: the last block to finish zeroes it for the next launch that is given the same slot.
+//     machine-wide window stays contiguous.  C2: 0.703 ms (static) -> 0.587 ms with one unit per draw, SM active cycles 98.7 % of
+//     elapsed; more units per draw (rows i, i + 1 of a box to the same warp, for L1) only coarsen the balance: 0.647 ms at 2,
+//     0.75 at 4, 0.98 at 14 (profiles/r02_fwd_ab_c2_v4_tickets.json).  The counter resets itself: the last block to finish zeroes
+//     it for the next launch that is given the same slot (256 slots, handed out round-robin per launch; a launch baked into a CUDA
+//     graph keeps its slot, replays of one graph being ordered).
 struct FwdPlan {
     unsigned pair_mask;           // bit k: sets k and k + 1 are interleaved by box (k + 1 is then skipped)
     int chunk;                    // static schedule: units per block chunk
@@ -526,7 +529,7 @@ static const LeanShape kLeanShapes[] = {
     {2, 2, 4, 4},   // form 6: blocks of 4 warps without the 96-register cap
 };
 constexpr int kLeanDefault = 3;
-constexpr int kLeanGrabDefault = 2;       // ticket schedule: units per draw
+constexpr int kLeanGrabDefault = 1;       // ticket schedule: units per draw
 constexpr int kLeanChunkDefault = 0;      // 0: one unit per warp per pass (chunk = warps per block)
 
 static int lean_shape_index() {           // -1: round-1 unit

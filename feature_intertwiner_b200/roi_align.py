@@ -79,11 +79,50 @@ class _Timed(object):
 _UNIQUE_CACHE = {}
 
 
+def _distinct_pixels(boxes, box_ind, B, H, W, crops):
+    """Number of distinct (image, y, x) feature pixels the crops of these boxes tap -- the UNION over the crop sizes in ``crops``
+    -- counted on the device from the kernel's own tap table."""
+    R = boxes.size(0)
+    key = (boxes.data_ptr(), box_ind.data_ptr(), R, B, H, W, tuple(crops))
+    if key not in _UNIQUE_CACHE:
+        seen = torch.zeros(B * H * W, dtype=torch.bool, device=boxes.device)
+        for ph, pw in crops:
+            taps = crop_taps(boxes, H, W, ph, pw).view(R, -1, 5).long()
+            b = box_ind.long().view(R, 1).expand(R, taps.size(1))
+            ok = (taps[:, :, 4] == 1) & (b >= 0) & (b < B)
+            for yy, xx in ((0, 2), (0, 3), (1, 2), (1, 3)):
+                lin = (b * H + taps[:, :, yy]) * W + taps[:, :, xx]
+                seen[lin[ok]] = True
+        _UNIQUE_CACHE[key] = int(seen.sum().item())
+    return _UNIQUE_CACHE[key]
+
+
+def _sets_forward_bytes(sets):
+    """Level-batched forward launch: every set writes its crops; the sets that crop the SAME boxes from the SAME map (Dev's 7x7 and
+    14x14 crops of the small boxes) are walked box by box by the kernel, so a pixel they both tap is read once: U is the union."""
+    total, groups = 0, {}
+    for st in sets:
+        B, Cc, H, W = st["im_size"]
+        ph, pw = st["crop"]
+        R = st["boxes"].size(0)
+        if st.get("count") is not None:
+            R = min(R, int(st["count"].item()))
+        total += 4 * Cc * R * ph * pw * (2 if st.get("dual") else 1) + 20 * R
+        key = (st.get("image"), st["boxes"].data_ptr(), st["box_ind"].data_ptr(), R, st["im_size"])
+        groups.setdefault(key, dict(st=st, R=R, crops=[]))["crops"].append((ph, pw))
+    for g in groups.values():
+        st, R = g["st"], g["R"]
+        B, Cc, H, W = st["im_size"]
+        total += 4 * Cc * _distinct_pixels(st["boxes"][:R], st["box_ind"][:R], B, H, W, sorted(set(g["crops"])))
+    return total
+
+
 def algorithmic_bytes(rec):
     """Algorithmic bytes of one recorded launch:
     forward  = 4*C*R*P^2 (write crops) + 4*C*U (each touched feature pixel read once) + 20*R (boxes, box_ind)
     backward = 4*C*R*P^2 (read grads)  + 4*C*B*H*W (dense grad map written once)      + 20*R
-    U = distinct (b,y,x) tap pixels, counted on the device from the kernel's own tap table."""
+    U = distinct (b,y,x) tap pixels, counted on the device from the kernel's own tap table; in a level-batched launch the union
+    over the crop sizes taken from the same boxes on the same map (_sets_forward_bytes)."""
     if "alg_bytes" in rec:
         return rec["alg_bytes"]
     if "bwd" in rec:                                   # backward of a crop_sets pass: (C, P, two sources, capacity, device count) per set
@@ -96,9 +135,12 @@ def algorithmic_bytes(rec):
     if "like" in rec:                                  # same shapes as the launch whose tensors were kept
         sets = _SETS_BY_SHAPE[rec["like"]]
         if isinstance(sets, list):
-            _SETS_BY_SHAPE[rec["like"]] = sum(algorithmic_bytes(dict(kernel=rec["kernel"], **st)) for st in sets)
+            _SETS_BY_SHAPE[rec["like"]] = _sets_forward_bytes(sets) if rec["kernel"].startswith("crop_fwd") else \
+                sum(algorithmic_bytes(dict(kernel=rec["kernel"], **st)) for st in sets)
         return _SETS_BY_SHAPE[rec["like"]]
     if "sets" in rec:
+        if rec["kernel"].startswith("crop_fwd"):
+            return _sets_forward_bytes(rec["sets"])
         return sum(algorithmic_bytes(dict(kernel=rec["kernel"], **st)) for st in rec["sets"])
     B, Cc, H, W = rec["im_size"]
     ph, pw = rec["crop"]
@@ -109,17 +151,7 @@ def algorithmic_bytes(rec):
     base = 4 * Cc * R * ph * pw * (2 if rec.get("dual") else 1) + 20 * R
     if rec["kernel"].startswith("crop_bwd"):
         return base + 4 * Cc * B * H * W
-    key = (rec["boxes"].data_ptr(), R, H, W, ph, pw)
-    if key not in _UNIQUE_CACHE:
-        taps = crop_taps(rec["boxes"], H, W, ph, pw).view(R, -1, 5).long()
-        b = rec["box_ind"].long().view(R, 1).expand(R, taps.size(1))
-        ok = (taps[:, :, 4] == 1) & (b >= 0) & (b < B)
-        seen = torch.zeros(B * H * W, dtype=torch.bool, device=taps.device)
-        for yy, xx in ((0, 2), (0, 3), (1, 2), (1, 3)):
-            lin = (b * H + taps[:, :, yy]) * W + taps[:, :, xx]
-            seen[lin[ok]] = True
-        _UNIQUE_CACHE[key] = int(seen.sum().item())
-    return base + 4 * Cc * _UNIQUE_CACHE[key]
+    return base + 4 * Cc * _distinct_pixels(rec["boxes"], rec["box_ind"], B, H, W, [(ph, pw)])
 
 
 def _mem_format(layout):

@@ -58,7 +58,7 @@ unsigned long long fi_kernel_launches(void); /* kernels this library has launche
                                      units go to consecutive warps of the grid), 1..6 = 8, 16, 32, 64, 128, 256 (slower, kept for A/B) [FI_FWD_CHUNK] */
 #define FI_OPT_FWD_PAIR 7         /* level-batched lean forward: 0 / 2 = walk two sets over the same map and boxes box by box (default), 1 = off [FI_FWD_PAIR] */
 #define FI_OPT_FWD_SCHED 8        /* level-batched lean forward: 0 / 2 = tickets (every warp draws its next units from a counter in global
-                                     memory: faster SMs take more; FI_OPT_FWD_CHUNK then selects the units per draw, 0 = default (2),
+                                     memory: faster SMs take more; FI_OPT_FWD_CHUNK then selects the units per draw, 0 = default (1),
                                      1..6 = 1, 2, 3, 4, 7, 14), 1 = static chunks [FI_FWD_SCHED] */
 #define FI_OPT_COUNT 9
 int fi_set_option(int option, int value);
