@@ -93,13 +93,47 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) crop_fwd_nhwc_sets_kernel
     }
 }
 
-// Lean formulation (roi_align_fwd_lean.cuh): WARPS warps per block, MINB blocks per SM, persistent over the units.
-template <int VPL, int U, int WARPS, int MINB>
-__global__ void __launch_bounds__(WARPS * 32, MINB) crop_fwd_nhwc_lean_kernel(const FwdSet S, unsigned nunits, unsigned chunk, u64 nz) {
+// Ticket counters of the lean kernels (see "TICKETS" below).
+constexpr int kTicketSlots = 256;
+__device__ unsigned g_fwd_tickets[2 * kTicketSlots];      // per slot: next unit, finished blocks
+
+__device__ __forceinline__ unsigned draw_ticket(unsigned *next, unsigned grab, int lane) {
+    unsigned u = 0;
+    if (lane == 0) u = atomicAdd(next, grab);
+    return __shfl_sync(0xffffffffu, u, 0);
+}
+__device__ __forceinline__ void retire_tickets(unsigned *next, unsigned *done) {      // every block, after its last draw
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(done, 1u) == gridDim.x - 1) {
+            *next = 0u;
+            *done = 0u;
+            __threadfence();
+        }
+    }
+}
+
+// Lean formulation (roi_align_fwd_lean.cuh): WARPS warps per block, MINB blocks per SM, persistent over the units; schedule as in
+// the level-batched kernel below (tickets: `chunk` = units per draw, `slot` = counter pair; else static chunks).
+template <int VPL, int U, int WARPS, int MINB, bool TICKETS>
+__global__ void __launch_bounds__(WARPS * 32, MINB) crop_fwd_nhwc_lean_kernel(const FwdSet S, unsigned nunits, unsigned chunk, int slot, u64 nz) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    for (unsigned c0 = blockIdx.x * chunk; c0 < nunits; c0 += gridDim.x * chunk) {        // chunks: see the level-batched kernel below
-        const unsigned c1 = min(c0 + chunk, nunits);
-        for (unsigned u = c0 + wib; u < c1; u += WARPS) fwd_unit_lean<VPL, U>(S, u, lane, nz);
+    if (TICKETS) {
+        unsigned *next = g_fwd_tickets + 2 * slot, *done = next + 1;
+        unsigned u = draw_ticket(next, chunk, lane);
+        while (u < nunits) {
+            const unsigned un = draw_ticket(next, chunk, lane);
+            const unsigned ue = min(u + chunk, nunits);
+            for (; u < ue; ++u) fwd_unit_lean<VPL, U>(S, u, lane, nz);
+            u = un;
+        }
+        retire_tickets(next, done);
+    } else {
+        for (unsigned c0 = blockIdx.x * chunk; c0 < nunits; c0 += gridDim.x * chunk) {
+            const unsigned c1 = min(c0 + chunk, nunits);
+            for (unsigned u = c0 + wib; u < c1; u += WARPS) fwd_unit_lean<VPL, U>(S, u, lane, nz);
+        }
     }
 }
 
@@ -129,26 +163,6 @@ struct FwdPlan {
     int grab;                     // ticket schedule: units per draw; 0 = static schedule
     int slot;                     // ticket schedule: which counter pair of g_fwd_tickets
 };
-
-constexpr int kTicketSlots = 256;
-__device__ unsigned g_fwd_tickets[2 * kTicketSlots];      // per slot: next unit, finished blocks
-
-__device__ __forceinline__ unsigned draw_ticket(unsigned *next, unsigned grab, int lane) {
-    unsigned u = 0;
-    if (lane == 0) u = atomicAdd(next, grab);
-    return __shfl_sync(0xffffffffu, u, 0);
-}
-__device__ __forceinline__ void retire_tickets(unsigned *next, unsigned *done) {      // every block, after its last draw
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd(done, 1u) == gridDim.x - 1) {
-            *next = 0u;
-            *done = 0u;
-            __threadfence();
-        }
-    }
-}
 
 template <int VPL, int U, int WARPS, int MINB, bool TICKETS>
 __global__ void __launch_bounds__(WARPS * 32, MINB) crop_fwd_nhwc_sets_lean_kernel(const FwdSets sets, const FwdPlan plan, u64 nz) {
@@ -545,6 +559,15 @@ static int lean_chunk(int warps) {         // units per block chunk: FI_OPT_FWD_
     return chunk < warps ? warps : chunk;
 }
 
+// ticket schedule (default): units per draw (FI_OPT_FWD_CHUNK 1..6 -> 1, 2, 3, 4, 7, 14) and the counter slot of this launch; 0: static
+static int lean_grab(int *slot) {
+    if (option(FI_OPT_FWD_SCHED) == 1) return 0;
+    static const int kGrab[7] = {kLeanGrabDefault, 1, 2, 3, 4, 7, 14};
+    static unsigned next_slot = 0;
+    *slot = (int)(__atomic_fetch_add(&next_slot, 1u, __ATOMIC_RELAXED) % kTicketSlots);
+    return kGrab[option(FI_OPT_FWD_CHUNK)];
+}
+
 static bool lean_ok(const void *image, const void *boxes, const void *crops, const void *crops2, int W, int C, int vpl, long units) {
     return (C % (128 * vpl) == 0) && ((long)W * C * 4 <= (1L << 30)) && units < (1L << 31) && ((uintptr_t)image % 16 == 0) &&
            ((uintptr_t)boxes % 16 == 0) && ((uintptr_t)crops % 16 == 0) && ((uintptr_t)crops2 % 16 == 0);
@@ -552,8 +575,17 @@ static bool lean_ok(const void *image, const void *boxes, const void *crops, con
 
 template <int VPL, int U, int WARPS, int MINB>
 static void launch_lean_one(const FwdSet &S, unsigned nunits, cudaStream_t stream) {
-    const unsigned chunk = (unsigned)lean_chunk(WARPS);
-    crop_fwd_nhwc_lean_kernel<VPL, U, WARPS, MINB><<<grid_for((nunits + chunk - 1) / chunk, 1, MINB), WARPS * 32, 0, stream>>>(S, nunits, chunk, kNegZeroPair);
+    int slot = 0;
+    const int grab = lean_grab(&slot);
+    if (grab > 0) {
+        const unsigned per_block = (unsigned)grab * WARPS;
+        crop_fwd_nhwc_lean_kernel<VPL, U, WARPS, MINB, true><<<grid_for((nunits + per_block - 1) / per_block, 1, MINB), WARPS * 32, 0, stream>>>(
+            S, nunits, (unsigned)grab, slot, kNegZeroPair);
+    } else {
+        const unsigned chunk = (unsigned)lean_chunk(WARPS);
+        crop_fwd_nhwc_lean_kernel<VPL, U, WARPS, MINB, false><<<grid_for((nunits + chunk - 1) / chunk, 1, MINB), WARPS * 32, 0, stream>>>(
+            S, nunits, chunk, 0, kNegZeroPair);
+    }
 }
 template <int VPL, int U, int WARPS, int MINB>
 static void launch_lean_sets(const FwdSets &sets, const FwdPlan &plan, long units, cudaStream_t stream) {
@@ -718,16 +750,10 @@ FI_API int fi_crop_sets_forward(const fi_fwd_set *sets, int num_sets, cudaStream
             if (all) {
                 for (int k = 0; k < dev.n; ++k) dev.s[k].slabs = dev.s[k].C / (128 * kLeanShapes[li].vpl);
                 FwdPlan plan;
-                const int popt = option(FI_OPT_FWD_PAIR), sopt = option(FI_OPT_FWD_SCHED);
+                const int popt = option(FI_OPT_FWD_PAIR);
                 plan.chunk = lean_chunk(kLeanShapes[li].warps);
-                plan.grab = 0;
                 plan.slot = 0;
-                if (sopt != 1) {                                   // tickets (default): units per draw 1..6 -> 1, 2, 3, 4, 7, 14
-                    static const int kGrab[7] = {kLeanGrabDefault, 1, 2, 3, 4, 7, 14};
-                    static unsigned next_slot = 0;
-                    plan.grab = kGrab[option(FI_OPT_FWD_CHUNK)];
-                    plan.slot = (int)(__atomic_fetch_add(&next_slot, 1u, __ATOMIC_RELAXED) % kTicketSlots);
-                }
+                plan.grab = lean_grab(&plan.slot);
                 plan.pair_mask = 0;
                 if (popt != 1)
                     for (int k = 0; k + 1 < dev.n; ++k) {

@@ -226,8 +226,13 @@ def test_forward_forms_bit_identical(form):
             want = clib.oracle_crop_and_resize_fwd(image.numpy(), rois.numpy(), np.clip(box_ind.numpy(), 0, 2), ph, pw, extrap)
             want[3] = 0
             want[7] = 0
-            got = fi.CropAndResizeFunction(ph, pw, extrap)(image.cuda().contiguous(memory_format=cl), rois.cuda(), box_ind.cuda())
-            np.testing.assert_array_equal(got.cpu().numpy(), want, err_msg="C=%d crop %dx%d" % (C, ph, pw))
+            for sched in (1, 2):                                    # static chunks / tickets
+                osd = fi.set_option("fwd_sched", sched)
+                try:
+                    got = fi.CropAndResizeFunction(ph, pw, extrap)(image.cuda().contiguous(memory_format=cl), rois.cuda(), box_ind.cuda())
+                finally:
+                    fi.set_option("fwd_sched", osd)
+                np.testing.assert_array_equal(got.cpu().numpy(), want, err_msg="C=%d crop %dx%d sched %d" % (C, ph, pw, sched))
         # level-batched launch: two maps, 7x7 + 14x14 into shared outputs by dst_row, a compact copy, a device-side count; the 7x7 and
         # 14x14 sets of a map share their box tensors (walked box by box as a pair unless fwd_pair = 1), every chunk size
         g = torch.Generator().manual_seed(77)
