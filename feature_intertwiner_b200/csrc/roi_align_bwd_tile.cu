@@ -101,27 +101,39 @@ __global__ void __launch_bounds__(256) tile_collapse_kernel(const TParams P) {
         const float4 geom = S.geom[r];
         const long grow = S.src_row ? (long)S.src_row[r] : (long)r;
         const int pp = S.ph * S.pw;
-        for (int slab = 0; slab * 128 < C; ++slab) {
+        // Two 128-channel slabs and 8 samples per warp per round: the kernel is one CTA per box and as long as its chain of
+        // dependent DRAM round trips (0.048 ms with one slab and 4 samples per round).  Every warp still sums its samples
+        // w, w + 8, w + 16, ... in that order and the 8 partial sums meet in the same order: the bits do not change.
+        for (int slab = 0; slab * 128 < C; slab += 2) {
             const int coff = slab * 128 + lane * 4;
-            float4 acc[4];
+            const bool two = (slab + 1) * 128 < C;
+            float4 acc[2][4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int s0 = w; s0 < pp; s0 += 32) {                      // 4 samples per warp per round, loads first
-                float4 g[4];
-                Tap ty[4], tx[4];
+            for (int h = 0; h < 2; ++h)
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int c = 0; c < 4; ++c) acc[h][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int s0 = w; s0 < pp; s0 += 64) {                      // 8 samples per warp per round, loads first
+                float4 g[8][2];
+                Tap ty[8], tx[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
                     const int s = s0 + 8 * q;
                     const int sc = min(s, pp - 1);
                     const int i = sc / S.pw, j = sc - i * S.pw;
                     ty[q] = geom_tap(geom.x, geom.y, i, H);
                     tx[q] = geom_tap(geom.z, geom.w, j, W);
                     if (s >= pp) ty[q].lo = kNoTap;
-                    g[q] = __ldcs(reinterpret_cast<const float4 *>(S.grads + ((grow * S.ph + i) * S.pw + j) * (long)C + coff));
-                    if (S.grads2) g[q] = add_rn4(g[q], __ldcs(reinterpret_cast<const float4 *>(S.grads2 + (((long)r * S.ph + i) * S.pw + j) * (long)C + coff)));
+                    const float *p1 = S.grads + ((grow * S.ph + i) * S.pw + j) * (long)C + coff;
+                    g[q][0] = __ldcs(reinterpret_cast<const float4 *>(p1));
+                    g[q][1] = two ? __ldcs(reinterpret_cast<const float4 *>(p1 + 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (S.grads2) {
+                        const float *p2 = S.grads2 + (((long)r * S.ph + i) * S.pw + j) * (long)C + coff;
+                        g[q][0] = add_rn4(g[q][0], __ldcs(reinterpret_cast<const float4 *>(p2)));
+                        if (two) g[q][1] = add_rn4(g[q][1], __ldcs(reinterpret_cast<const float4 *>(p2 + 128)));
+                    }
                 }
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < 8; ++q) {
                     if (ty[q].lo == kNoTap || tx[q].lo == kNoTap) continue;
                     const float wy1 = ty[q].frac, wy0 = 1.f - wy1, wx1 = tx[q].frac, wx0 = 1.f - wx1;
                     const int cy0 = ty[q].lo - ymin, cy1 = ty[q].hi - ymin, cx0 = tx[q].lo - xmin, cx1 = tx[q].hi - xmin;   // each 0 or 1
@@ -133,20 +145,25 @@ __global__ void __launch_bounds__(256) tile_collapse_kernel(const TParams P) {
                         if (cy == cy0 && cx == cx1 && cx1 != cx0) wgt += wy0 * wx1;
                         if (cy == cy1 && cy1 != cy0 && cx == cx0) wgt += wy1 * wx0;
                         if (cy == cy1 && cy1 != cy0 && cx == cx1 && cx1 != cx0) wgt += wy1 * wx1;
-                        acc[c] = fma4(g[q], wgt, acc[c]);
+                        acc[0][c] = fma4(g[q][0], wgt, acc[0][c]);
+                        acc[1][c] = fma4(g[q][1], wgt, acc[1][c]);
                     }
                 }
             }
 #pragma unroll
-            for (int c = 0; c < 4; ++c) part[w][c][lane] = acc[c];
-            __syncthreads();
-            if (w < 4) {
-                float4 v = part[0][w][lane];
+            for (int h = 0; h < 2; ++h) {
+                if (h == 1 && !two) break;
 #pragma unroll
-                for (int q = 1; q < 8; ++q) v = add_rn4(v, part[q][w][lane]);
-                *reinterpret_cast<float4 *>(S.coll + ((long)r * 4 + w) * C + coff) = v;
+                for (int c = 0; c < 4; ++c) part[w][c][lane] = acc[h][c];
+                __syncthreads();
+                if (w < 4) {
+                    float4 v = part[0][w][lane];
+#pragma unroll
+                    for (int q = 1; q < 8; ++q) v = add_rn4(v, part[q][w][lane]);
+                    *reinterpret_cast<float4 *>(S.coll + ((long)r * 4 + w) * C + coff + h * 128) = v;
+                }
+                __syncthreads();
             }
-            __syncthreads();
         }
     }
 }
