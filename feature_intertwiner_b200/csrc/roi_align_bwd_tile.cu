@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(128) tile_prep_kernel(const TParams P) {
 // ---- collapse: corner sums of degenerate boxes (footprint <= 2x2 pixels), one CTA per box -------------------------
 // coll[r][corner][c] = sum over the box's samples of (tap weight on that corner) * (grads + grads2); corner =
 // 2 * (y - ymin) + (x - xmin).  8 warps split the samples, lanes hold float4 of a 128-channel slab.
-__global__ void __launch_bounds__(256) tile_collapse_kernel(const TParams P) {
+__global__ void __launch_bounds__(256, 2) tile_collapse_kernel(const TParams P) {
     __shared__ float4 part[8][4][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int count = P.deg_list[0];
@@ -114,15 +114,10 @@ __global__ void __launch_bounds__(256) tile_collapse_kernel(const TParams P) {
                 for (int c = 0; c < 4; ++c) acc[h][c] = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int s0 = w; s0 < pp; s0 += 64) {                      // 8 samples per warp per round, loads first
                 float4 g[8][2];
-                Tap ty[8], tx[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    const int s = s0 + 8 * q;
-                    const int sc = min(s, pp - 1);
+                    const int sc = min(s0 + 8 * q, pp - 1);
                     const int i = sc / S.pw, j = sc - i * S.pw;
-                    ty[q] = geom_tap(geom.x, geom.y, i, H);
-                    tx[q] = geom_tap(geom.z, geom.w, j, W);
-                    if (s >= pp) ty[q].lo = kNoTap;
                     const float *p1 = S.grads + ((grow * S.ph + i) * S.pw + j) * (long)C + coff;
                     g[q][0] = __ldcs(reinterpret_cast<const float4 *>(p1));
                     g[q][1] = two ? __ldcs(reinterpret_cast<const float4 *>(p1 + 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -133,10 +128,14 @@ __global__ void __launch_bounds__(256) tile_collapse_kernel(const TParams P) {
                     }
                 }
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    if (ty[q].lo == kNoTap || tx[q].lo == kNoTap) continue;
-                    const float wy1 = ty[q].frac, wy0 = 1.f - wy1, wx1 = tx[q].frac, wx0 = 1.f - wx1;
-                    const int cy0 = ty[q].lo - ymin, cy1 = ty[q].hi - ymin, cx0 = tx[q].lo - xmin, cx1 = tx[q].hi - xmin;   // each 0 or 1
+                for (int q = 0; q < 8; ++q) {                          // the taps are formed here, after the loads: fewer live registers
+                    const int s = s0 + 8 * q;
+                    if (s >= pp) break;
+                    const int i = s / S.pw, j = s - i * S.pw;
+                    const Tap tyq = geom_tap(geom.x, geom.y, i, H), txq = geom_tap(geom.z, geom.w, j, W);
+                    if (tyq.lo == kNoTap || txq.lo == kNoTap) continue;
+                    const float wy1 = tyq.frac, wy0 = 1.f - wy1, wx1 = txq.frac, wx0 = 1.f - wx1;
+                    const int cy0 = tyq.lo - ymin, cy1 = tyq.hi - ymin, cx0 = txq.lo - xmin, cx1 = txq.hi - xmin;   // each 0 or 1
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         const int cy = c >> 1, cx = c & 1;
