@@ -65,8 +65,6 @@ SIGNATURES = {
     "fi_col_sum": (_I, [_P, _I, _I, _P, _P]),
     "fi_ot_head_dsum": (_I, [_P, _P, _I, _I, _P, _P]),
     "fi_centre_tap_embed": (_I, [_P, C.c_long, _P, _P]),
-    "fi_small_gemm_workspace": (C.c_size_t, [_I, _I, _I]),
-    "fi_small_gemm": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _P, _P, C.c_size_t, _P]),
     "fi_nms_batched": (_I, [_P, _I, _I, _F, _P, _P, _P, _P]),
     "fi_nms_batched_topk": (_I, [_P, _I, _I, _F, _I, _P, _P, _P, _P]),
     "fi_proposal_decode": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _F, _F, _P, _P, _P]),

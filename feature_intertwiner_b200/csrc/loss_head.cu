@@ -209,103 +209,3 @@ FI_API int fi_centre_tap_embed(const float *w1, long count, float *full, cudaStr
     centre_tap_embed_kernel<<<grid_1d(count, 256), 256, 0, stream>>>(w1, count, full);
     return check_launch("fi_centre_tap_embed");
 }
-
-// ------------------------------------------------------------------------------------------------
-// fp32 GEMM for the head's short-and-wide products: C[M,N] = A[M,K] . op(B) (+ bias[N], ReLU) with M = 80 ... 160 rows.
-//
-// The library's SIMT kernels cut such a product into 32x32 output tiles -- 96 CTAs that each walk all of K alone: 27 us for
-// 80 x 1024 x 1024 (168 MFLOP, 4 MB of weights: microseconds of work).  Here a CTA owns an 80 x 32 output tile over ONE SLICE of K
-// (grid = N/32 x ceil(M/80) x S slices: >= 128 CTAs), K in chunks of 32 through shared memory, 5 x 2 outputs per thread; the S
-// partial tiles are then summed in a fixed order (deterministic, unlike atomics) together with the bias and the ReLU.
-//   B_KN = false: B is [N,K] row-major (x @ W^T, the forward products);  B_KN = true: B is [K,N] row-major (g @ W, the input gradients).
-// ------------------------------------------------------------------------------------------------
-namespace fi {
-
-constexpr int kSgMT = 80, kSgNT = 32, kSgKC = 32;
-
-template <bool B_KN>
-__global__ void __launch_bounds__(256) small_gemm_partial_kernel(const float *__restrict__ A, const float *__restrict__ B, int M, int N, int K,
-                                                                 int kslice, float *__restrict__ part) {
-    __shared__ float As[kSgMT][kSgKC + 1];
-    __shared__ float Bs[kSgNT][kSgKC + 1];          // [n][k] in both modes
-    const int n0 = blockIdx.x * kSgNT, m0 = blockIdx.y * kSgMT, kb = blockIdx.z * kslice;
-    const int ke = min(K, kb + kslice);
-    const int t = threadIdx.x, mg = t >> 4, ng = t & 15;          // 16 row groups x 16 column groups: rows mg, mg+16, .. (5), columns 2 ng, 2 ng + 1
-    float acc[5][2];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; }
-    for (int k0 = kb; k0 < ke; k0 += kSgKC) {
-        // A chunk: 80 rows x 32 k, coalesced along k (rows past M read as 0)
-        for (int e = t; e < kSgMT * kSgKC; e += 256) {
-            const int r = e >> 5, k = e & 31;
-            As[r][k] = (m0 + r < M && k0 + k < ke) ? A[(long)(m0 + r) * K + k0 + k] : 0.f;
-        }
-        if (B_KN) {                                               // B[k][n]: coalesced along n
-            for (int e = t; e < kSgKC * kSgNT; e += 256) {
-                const int k = e >> 5, n = e & 31;
-                Bs[n][k] = (k0 + k < ke) ? B[(long)(k0 + k) * N + n0 + n] : 0.f;
-            }
-        } else {                                                  // B[n][k]: coalesced along k
-            for (int e = t; e < kSgNT * kSgKC; e += 256) {
-                const int n = e >> 5, k = e & 31;
-                Bs[n][k] = (k0 + k < ke) ? B[(long)(n0 + n) * K + k0 + k] : 0.f;
-            }
-        }
-        __syncthreads();
-#pragma unroll 8
-        for (int k = 0; k < kSgKC; ++k) {
-            const float b0 = Bs[2 * ng][k], b1 = Bs[2 * ng + 1][k];
-#pragma unroll
-            for (int i = 0; i < 5; ++i) {
-                const float a = As[mg + 16 * i][k];
-                acc[i][0] = fmaf(a, b0, acc[i][0]);
-                acc[i][1] = fmaf(a, b1, acc[i][1]);
-            }
-        }
-        __syncthreads();
-    }
-    float *out = part + (long)blockIdx.z * M * N;
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-        const int m = m0 + mg + 16 * i;
-        if (m < M) *reinterpret_cast<float2 *>(out + (long)m * N + n0 + 2 * ng) = make_float2(acc[i][0], acc[i][1]);
-    }
-}
-
-__global__ void small_gemm_reduce_kernel(const float *__restrict__ part, int slices, long count, int N, const float *__restrict__ bias, int relu,
-                                         float *__restrict__ C) {
-    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < count; e += (long)gridDim.x * blockDim.x) {
-        float s = part[e];
-        for (int z = 1; z < slices; ++z) s += part[(long)z * count + e];
-        if (bias) s += bias[e % N];
-        if (relu) s = fmaxf(s, 0.f);
-        C[e] = s;
-    }
-}
-
-}  // namespace fi
-
-FI_API size_t fi_small_gemm_workspace(int M, int N, int K) {
-    if (M <= 0 || N <= 0 || K <= 0) return 0;
-    int slices = 1;
-    const int tiles = (N / kSgNT) * ceil_div(M, kSgMT);
-    while (tiles * slices < kNumSMs && slices * 2 * 64 <= K) slices *= 2;        // at least 64 k per slice
-    return (size_t)slices * M * N * sizeof(float);
-}
-
-FI_API int fi_small_gemm(const float *A, const float *B, int b_is_kn, int M, int N, int K, const float *bias, int relu, float *C, void *workspace,
-                         size_t workspace_bytes, cudaStream_t stream) {
-    FI_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, "fi_small_gemm: bad arguments");
-    if (N % kSgNT != 0 || ((uintptr_t)C % 8) != 0) { set_error(FI_ERR_UNSUPPORTED, "fi_small_gemm: N %% 32 == 0 and an 8-byte aligned C"); return FI_ERR_UNSUPPORTED; }
-    const size_t need = fi_small_gemm_workspace(M, N, K);
-    FI_REQUIRE(workspace && workspace_bytes >= need && ((uintptr_t)workspace % 8) == 0, "fi_small_gemm: workspace of %zu bytes", need);
-    const int slices = (int)(need / ((size_t)M * N * sizeof(float)));
-    const int kslice = ceil_div(ceil_div(K, slices), kSgKC) * kSgKC;
-    const dim3 grid(N / kSgNT, ceil_div(M, kSgMT), slices);
-    float *part = reinterpret_cast<float *>(workspace);
-    if (b_is_kn) small_gemm_partial_kernel<true><<<grid, 256, 0, stream>>>(A, B, M, N, K, kslice, part);
-    else small_gemm_partial_kernel<false><<<grid, 256, 0, stream>>>(A, B, M, N, K, kslice, part);
-    if (int e = check_launch("fi_small_gemm[partial]")) return e;
-    small_gemm_reduce_kernel<<<grid_1d((long)M * N, 256), 256, 0, stream>>>(part, slices, (long)M * N, N, bias, relu, C);
-    return check_launch("fi_small_gemm[reduce]");
-}

@@ -565,34 +565,8 @@ def pyramid_roi_align(inputs, pool_size, image_shape, base=224.):
 
 
 # ----------------------------------------------------------------------------------------------- meta loss
-SMALL_GEMM = True     # the head's 80 ... 160-row products through fi_small_gemm (False: the library's kernels)
-
-
-def small_gemm(a, b, b_is_kn, bias=None, relu=False, out=None):
-    """out[M,N] = a[M,K] @ (b[K,N] if b_is_kn else b[N,K]^T) (+ bias) (ReLU) by csrc/loss_head.cu::small_gemm_* -- a split-K kernel for
-    short-and-wide fp32 products, deterministic.  Contiguous fp32 CUDA tensors, N % 32 == 0."""
-    M, K = a.shape
-    N = b.size(1) if b_is_kn else b.size(0)
-    if out is None:
-        out = torch.empty((M, N), device=a.device, dtype=torch.float32)
-    L_ = _lib.lib()
-    nbytes = L_.fi_small_gemm_workspace(M, N, K)
-    ws = torch.empty((nbytes,), dtype=torch.uint8, device=a.device)
-    with torch.cuda.device(a.device):
-        _lib.check(L_.fi_small_gemm(_lib.ptr(a), _lib.ptr(b), 1 if b_is_kn else 0, M, N, K, _lib.ptr(bias), 1 if relu else 0, _lib.ptr(out),
-                                    _lib.ptr(ws), nbytes, _lib.stream_ptr(a.device)))
-    return out
-
-
-def _small_gemm_ok(*ts):
-    return SMALL_GEMM and all(t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() for t in ts)
-
-
 def _linear_relu(bias, x, w, out):
-    """out = relu(x @ w^T + bias): fi_small_gemm, else one cuBLASLt call with the bias + ReLU epilogue where torch offers it, else
-    addmm + relu_."""
-    if _small_gemm_ok(bias, x, w, out) and w.size(0) % 32 == 0:
-        return small_gemm(x, w, False, bias, True, out)
+    """out = relu(x @ w^T + bias): one cuBLASLt call with the bias + ReLU epilogue where torch offers it, else addmm + relu_."""
     fused = getattr(torch, "_addmm_activation", None)
     if fused is not None:
         fused(bias, x, w.t(), out=out)
@@ -671,7 +645,7 @@ class _ClassOTHead(torch.autograd.Function):
                 _lib.check(L_.fi_centre_tap_embed(_lib.ptr(dWc1), dWc1.numel(), _lib.ptr(dWc), st))
             dss = dWg = dbg = None
             if need[2] or need[4] or need[5]:
-                dH = small_gemm(dC[:n], Wc1, True) if (_small_gemm_ok(dC, Wc1) and Fd % 32 == 0) else dC[:n].mm(Wc1)
+                dH = dC[:n].mm(Wc1)
                 _lib.check(L_.fi_relu_mask(_lib.ptr(dH), _lib.ptr(Z), dH.numel(), st))          # Z[:n] = H
                 if need[5]:
                     dbg = torch.empty((Fd,), device=dev, dtype=torch.float32)
@@ -681,7 +655,7 @@ class _ClassOTHead(torch.autograd.Function):
                     dWg1 = dH.t().mm(X)
                     _lib.check(L_.fi_centre_tap_embed(_lib.ptr(dWg1), dWg1.numel(), _lib.ptr(dWg), st))
                 if need[2]:
-                    dX = small_gemm(dH, Wg1, True) if (_small_gemm_ok(dH, Wg1) and Fd % 32 == 0) else dH.mm(Wg1)
+                    dX = dH.mm(Wg1)
                     dss = torch.empty((Fd, ncls), device=dev, dtype=torch.float32)
                     _lib.check(L_.fi_ot_head_dsum(_lib.ptr(dX), _lib.ptr(s_n), Fd, ncls, _lib.ptr(dss), st))
         return None, None, dss, None, dWg, dbg, dWc, dbc

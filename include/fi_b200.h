@@ -331,14 +331,6 @@ int fi_col_sum(const float *src, int rows, int cols, float *dst, cudaStream_t st
 int fi_ot_head_dsum(const float *dX, const float *small_n, int F, int ncls, float *d_small_sum, cudaStream_t stream);
 int fi_centre_tap_embed(const float *w1, long count, float *full, cudaStream_t stream);
 
-/* fp32 GEMM for the head's short-and-wide products (M = 80 ... 160 rows; any M works): C[M,N] = A[M,K] . op(B) (+ bias[N]) (ReLU).
- * b_is_kn == 0: B is [N,K] row-major (x @ W^T); b_is_kn != 0: B is [K,N] row-major (g @ W).  N % 32 == 0.  K is split into
- * slices over the grid and the partial tiles are summed in a fixed order (deterministic); `workspace` holds them
- * (fi_small_gemm_workspace bytes, 8-byte aligned). */
-size_t fi_small_gemm_workspace(int M, int N, int K);
-int fi_small_gemm(const float *A, const float *B, int b_is_kn, int M, int N, int K, const float *bias, int relu, float *C, void *workspace,
-                  size_t workspace_bytes, cudaStream_t stream);
-
 /* ---------------------------------------------------------------------------------------------
  * 7. NMS with the reduce on the device (lib/nms/src/nms_cuda.c:17-67, no host round trip).
  * ------------------------------------------------------------------------------------------- */
