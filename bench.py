@@ -658,9 +658,6 @@ class Timer(object):
             if getattr(self, "_rdv", None) is None:
                 self._rdv = torch.zeros(1, device=self.dev)
             dist.all_reduce(self._rdv)
-            # ... followed by ~1 ms of device-side spinning, so that every host has queued its first timed step by the time any GPU
-            # leaves the rendezvous (measured without it at N = 2: one rank's first step still waited 0.5 ms for its peer)
-            torch.cuda._sleep(2000000)
         self.host_s = 0.0
         launch0 = self.lib.fi_kernel_launches()
         for _ in range(steps):
