@@ -635,18 +635,19 @@ class Timer(object):
         torch.cuda.synchronize()
 
     def __call__(self, fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
-        torch.cuda.synchronize()
         # the cyclic collector of a process with torch loaded walks millions of objects: a generation-2 pass landing inside a
         # 2 ms step shows up as a 6-60 ms step.  Collect now, keep it off for the K timed steps (training loops do the same with
-        # gc.freeze / a manual collection between iterations).
+        # gc.freeze / a manual collection between iterations).  Done BEFORE the warm-up steps, like the creation of the timing
+        # events: the collection takes tens of ms, and a GPU left idle that long right before the timed region starts it cold.
         gc.collect()
         gc.disable()
         evs = []
         pool = [torch.cuda.Event(enable_timing=True) for _ in range(2 * steps)]     # created and first-recorded outside the timed steps
         for ev in pool:
             ev.record()
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
         # barrier + synchronize LAST, right before the first timed step: the collection above takes tens of ms and a different
         # time on every rank -- with the barrier in front of it the first step of the early ranks timed their wait for the late ones
         self.barrier()
