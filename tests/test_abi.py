@@ -46,6 +46,31 @@ def test_library_is_sm_100a_and_uses_vector_reductions():
     assert "UBLKCP.S.G" in sass                # cp.async.bulk global -> shared: gradient rows of the NHWC backward (roi_align_bwd_pix.cu)
 
 
+def test_option_table_matches_the_header():
+    """Every FI_OPT_* of the header is bound by name in _lib.OPTIONS (or is the count), fi_set_option accepts 0 for each, returns
+    the previous value, and refuses values past the documented range -- no GPU needed; and the packed-lerp forward is in the SASS
+    un-fused: FFMA2 with the opaque -0.0 addend between two FADD2 (a contraction of the reference's `top + (bottom - top) * w`
+    would change bits)."""
+    from feature_intertwiner_b200 import _lib, build
+    src = open(os.path.join(ROOT, "include", "fi_b200.h")).read()
+    keys = {name: int(v) for name, v in re.findall(r"#define\s+(FI_OPT_\w+)\s+(\d+)", src)}
+    count = keys.pop("FI_OPT_COUNT")
+    assert sorted(keys.values()) == list(range(count))
+    assert sorted(_lib.OPTIONS.values()) == sorted(keys.values())
+    assert {"FI_OPT_" + k.upper() for k in _lib.OPTIONS} == set(keys)
+    L = _lib.lib()
+    for name, key in _lib.OPTIONS.items():
+        old = L.fi_get_option(key)
+        assert L.fi_set_option(key, 0) == old
+        assert L.fi_set_option(key, 99) == -1 and L.fi_get_option(key) == 0
+        assert L.fi_set_option(key, old) == 0
+    assert L.fi_set_option(count, 0) == -1
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN2fi30crop_fwd_nhwc_sets_lean_kernelILi2ELi2ELi8ELi2ELb1EEEvNS_7FwdSetsENS_7FwdPlanEy",
+                           build.build_library()], capture_output=True, text=True).stdout
+    assert sass.count("FADD2") >= 48 and sass.count("FFMA2") >= 24 and "FMUL2" not in sass, "packed lerps of the lean forward changed shape"
+    assert "ATOMG.E.ADD" in sass               # the ticket draw
+
+
 def test_argument_validation_needs_no_gpu():
     from feature_intertwiner_b200 import _lib
     L = _lib.lib()
