@@ -1,5 +1,5 @@
 // NHWC RoIAlign forward, second formulation ("lean"): the same warp-per-crop-row walk as roi_align_units.cuh::fwd_unit with the
-// per-sample instruction count cut to about a third.
+// per-sample instruction count more than halved (445 M -> 193 M warp instructions on C2).
 //
 // ncu on fwd_unit (profiles/r01_ncu_prof_fwd_sets_v2.txt): 445 M warp instructions for 3.6 M (crop sample, 128-channel slab)
 // pairs = ~94 instructions per 4 tap loads, issue slots 51 % busy at 16 warps per SM -- the kernel is as much issue-bound as it
@@ -11,8 +11,8 @@
 //     PARAMETER (a value ptxas cannot fold): d*w + (-0) rounds exactly like d*w, signed zeros included, and the following packed
 //     add has nothing left to fuse with.
 //   * 64-bit multiplies for every tap address and output address -> 32-bit element offsets formed once per lane (lo * C, with the
-//     `hi != lo` and `inside` flags in the top bits of the same word, so a sample still costs two shuffles), one IMAD.WIDE per
-//     tap address, running output pointers.
+//     `hi != lo` and `inside` flags in the top bits of the same word, so a sample still costs two shuffles), one 64-bit add per
+//     tap address on opaque row base addresses, running output pointers.
 //   * a warp takes BOTH 128-channel slabs of a 256-channel pixel (VPL = 2): shuffles, unpacking, address formation and loop
 //     control are paid once per 1 KB tap instead of once per 512 B.
 //   * 64-bit div/mod chains per unit -> 32-bit.
